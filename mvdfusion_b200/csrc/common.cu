@@ -1,0 +1,83 @@
+#include "common.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace mvd {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static int encode(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode();
+  if (fn == nullptr) return set_error(MVD_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(MVD_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d, rank %d, dims %llu/%llu, box %u/%u)",
+                     static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0],
+                     box[1]);
+  return MVD_OK;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, int cols, int rows, int ld, int box_cols, int box_rows) {
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  return encode(out, base, 2, dims, strides, box);
+}
+
+int make_tmap_3d(CUtensorMap* out, const void* base, int d0, int d1, int d2, long long ld1, long long ld2, int b0,
+                 int b1, int b2) {
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld1) * 2, static_cast<cuuint64_t>(ld2) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(b0), static_cast<cuuint32_t>(b1), static_cast<cuuint32_t>(b2)};
+  return encode(out, base, 3, dims, strides, box);
+}
+
+int make_tmap_nhwc(CUtensorMap* out, const void* base, int n, int h, int w, int c, int bc, int bw, int bh, int bn) {
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
+                        static_cast<cuuint64_t>(n)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w) * c * 2,
+                           static_cast<cuuint64_t>(h) * w * c * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(bc), static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh),
+                       static_cast<cuuint32_t>(bn)};
+  return encode(out, base, 4, dims, strides, box);
+}
+
+}  // namespace mvd
+
+extern "C" const char* mvd_last_error(void) { return mvd::g_err; }
+extern "C" int mvd_abi_version(void) { return 1; }
+extern "C" long long mvd_launch_count(void) { return mvd::g_launches.load(std::memory_order_relaxed); }

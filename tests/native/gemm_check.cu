@@ -1,0 +1,269 @@
+// Native parity check of mvd_gemm_f16 (through the C ABI) against a double-precision CPU loop.
+// Build: make -C tests/native ; run on a B200: tests/native/gemm_check
+// Exit code 0 = all cases within tolerance.  Prints one line per case.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/mvd_b200.h"
+
+#define CK(x)                                                                              \
+  do {                                                                                     \
+    cudaError_t e = (x);                                                                   \
+    if (e != cudaSuccess) {                                                                \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__);       \
+      exit(2);                                                                             \
+    }                                                                                      \
+  } while (0)
+
+static std::mt19937 rng(1234);
+static float frand() { return std::uniform_real_distribution<float>(-1.f, 1.f)(rng); }
+
+template <class T>
+static T* dev(const std::vector<T>& h) {
+  T* d;
+  CK(cudaMalloc(&d, h.size() * sizeof(T) + 16));
+  CK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+static double gelu(double x) { return 0.5 * x * (1.0 + erf(x * 0.7071067811865476)); }
+static double silu(double x) { return x / (1.0 + exp(-x)); }
+
+struct Case {
+  std::string name;
+  int M, N, K;
+  int a_mode = MVD_A_ROWMAJOR;
+  int n_img = 0, H = 0, W = 0, C = 0;
+  bool bias = false, rowbias = false, residual = false;
+  int rows_per_group = 1;
+  int act = MVD_ACT_NONE;
+  int out_mode = MVD_OUT_F32;
+  int split_k = 1;
+  int tile_n = 0;
+  int heads = 0, dhead = 0, dpad = 0, seq = 0;
+  int lda_pad = 0;
+};
+
+static int g_fail = 0;
+
+static void run(const Case& c) {
+  const int M = c.M, N = c.N, K = c.K;
+  const int lda = K + c.lda_pad, ldw = (K + 7) / 8 * 8;
+  std::vector<__half> hA, hW(static_cast<size_t>(N) * ldw);
+  std::vector<float> fA, fW(static_cast<size_t>(N) * ldw);
+  if (c.a_mode == MVD_A_ROWMAJOR) {
+    hA.resize(static_cast<size_t>(M) * lda);
+  } else {
+    hA.resize(static_cast<size_t>(c.n_img) * c.H * c.W * c.C);
+  }
+  fA.resize(hA.size());
+  for (size_t i = 0; i < hA.size(); ++i) {
+    hA[i] = __float2half(frand());
+    fA[i] = __half2float(hA[i]);
+  }
+  for (size_t i = 0; i < hW.size(); ++i) {
+    hW[i] = __float2half(frand() * 0.25f);
+    fW[i] = __half2float(hW[i]);
+  }
+  std::vector<float> hb(N), hrb, hres;
+  for (auto& v : hb) v = frand();
+  const int groups = (M + c.rows_per_group - 1) / c.rows_per_group;
+  if (c.rowbias) {
+    hrb.resize(static_cast<size_t>(groups) * N);
+    for (auto& v : hrb) v = frand();
+  }
+  if (c.residual) {
+    hres.resize(static_cast<size_t>(M) * N);
+    for (auto& v : hres) v = frand();
+  }
+
+  // ---- CPU reference (pre-activation accumulators in double)
+  std::vector<double> acc(static_cast<size_t>(M) * N, 0.0);
+  if (c.a_mode == MVD_A_ROWMAJOR) {
+    for (int m = 0; m < M; ++m)
+      for (int n = 0; n < N; ++n) {
+        double s = 0;
+        const float* a = &fA[static_cast<size_t>(m) * lda];
+        const float* w = &fW[static_cast<size_t>(n) * ldw];
+        for (int k = 0; k < K; ++k) s += static_cast<double>(a[k]) * w[k];
+        acc[static_cast<size_t>(m) * N + n] = s;
+      }
+  } else {
+    for (int im = 0; im < c.n_img; ++im)
+      for (int y = 0; y < c.H; ++y)
+        for (int x = 0; x < c.W; ++x) {
+          const size_t m = (static_cast<size_t>(im) * c.H + y) * c.W + x;
+          for (int n = 0; n < N; ++n) {
+            double s = 0;
+            for (int ky = 0; ky < 3; ++ky)
+              for (int kx = 0; kx < 3; ++kx) {
+                const int yy = y + ky - 1, xx = x + kx - 1;
+                if (yy < 0 || yy >= c.H || xx < 0 || xx >= c.W) continue;
+                const float* a = &fA[((static_cast<size_t>(im) * c.H + yy) * c.W + xx) * c.C];
+                const float* w = &fW[static_cast<size_t>(n) * ldw + (ky * 3 + kx) * c.C];
+                for (int ch = 0; ch < c.C; ++ch) s += static_cast<double>(a[ch]) * w[ch];
+              }
+            acc[m * N + n] = s;
+          }
+        }
+  }
+  auto pre = [&](int m, int n) {
+    double v = acc[static_cast<size_t>(m) * N + n];
+    if (c.bias) v += hb[n];
+    if (c.rowbias) v += hrb[static_cast<size_t>(m / c.rows_per_group) * N + n];
+    return v;
+  };
+
+  // ---- device
+  __half* dA = dev(hA);
+  __half* dW = dev(hW);
+  float* db = dev(hb);
+  float* drb = c.rowbias ? dev(hrb) : nullptr;
+  float* dres = c.residual ? dev(hres) : nullptr;
+
+  mvd_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.K = K; g.a_mode = c.a_mode;
+  g.A = dA; g.lda = lda;
+  g.n_img = c.n_img; g.H = c.H; g.W = c.W; g.C = c.C;
+  g.Wt = dW; g.ldw = ldw;
+  g.bias = c.bias ? db : nullptr;
+  g.rowbias = drb; g.rows_per_group = c.rows_per_group;
+  g.residual = dres; g.ldr = N;
+  g.act = c.act; g.out_mode = c.out_mode;
+  g.split_k = c.split_k; g.tile_n = c.tile_n;
+
+  double max_err = 0, max_ref = 0;
+  size_t bad = 0, total = 0;
+  int first_bad_m = -1, first_bad_n = -1;
+  double first_got = 0, first_want = 0;
+  auto cmp = [&](double got, double want, int m, int n, double tol_abs) {
+    const double e = fabs(got - want);
+    if (!(e <= tol_abs) ) {
+      if (bad == 0) { first_bad_m = m; first_bad_n = n; first_got = got; first_want = want; }
+      ++bad;
+    }
+    if (e > max_err || std::isnan(e)) max_err = e;
+    if (fabs(want) > max_ref) max_ref = fabs(want);
+    ++total;
+  };
+  const double tol32 = 2e-3, tol16 = 2e-2;
+  int rc = 0;
+
+  if (c.out_mode == MVD_OUT_QKV_HEADS) {
+    const int BH = (M / c.seq) * c.heads;
+    const size_t nqk = static_cast<size_t>(BH) * c.seq * c.dpad;
+    __half *dq, *dk, *dv;
+    CK(cudaMalloc(&dq, nqk * 2)); CK(cudaMalloc(&dk, nqk * 2)); CK(cudaMalloc(&dv, nqk * 2));
+    CK(cudaMemset(dq, 0, nqk * 2)); CK(cudaMemset(dk, 0, nqk * 2)); CK(cudaMemset(dv, 0, nqk * 2));
+    g.out = dq; g.out_k = dk; g.out_vt = dv;
+    g.heads = c.heads; g.dhead = c.dhead; g.dpad = c.dpad; g.seq = c.seq;
+    rc = mvd_gemm_f16(&g, nullptr);
+    CK(cudaDeviceSynchronize());
+    std::vector<__half> q(nqk), k(nqk), v(nqk);
+    CK(cudaMemcpy(q.data(), dq, nqk * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(k.data(), dk, nqk * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(v.data(), dv, nqk * 2, cudaMemcpyDeviceToHost));
+    const int inner = c.heads * c.dhead;
+    for (int m = 0; m < M; ++m) {
+      const int img = m / c.seq, pos = m % c.seq;
+      for (int n = 0; n < N; ++n) {
+        const int which = n / inner, h = (n % inner) / c.dhead, j = n % c.dhead;
+        const size_t bh = static_cast<size_t>(img) * c.heads + h;
+        double got;
+        if (which == 0) got = __half2float(q[(bh * c.seq + pos) * c.dpad + j]);
+        else if (which == 1) got = __half2float(k[(bh * c.seq + pos) * c.dpad + j]);
+        else got = __half2float(v[(bh * c.dpad + j) * c.seq + pos]);
+        cmp(got, pre(m, n), m, n, tol16);
+      }
+    }
+    // padding must stay zero
+    for (size_t bh = 0; bh < static_cast<size_t>(BH); ++bh)
+      for (int pos = 0; pos < c.seq; ++pos)
+        for (int j = c.dhead; j < c.dpad; ++j)
+          if (__half2float(q[(bh * c.seq + pos) * c.dpad + j]) != 0.f) ++bad;
+    cudaFree(dq); cudaFree(dk); cudaFree(dv);
+  } else {
+    const bool geglu = c.act == MVD_ACT_GEGLU;
+    const int No = geglu ? N / 2 : N;
+    const size_t nout = static_cast<size_t>(M) * No;
+    void* dout;
+    CK(cudaMalloc(&dout, nout * 4));
+    CK(cudaMemset(dout, 0xff, nout * 4));
+    g.out = dout; g.ldc = No;
+    rc = mvd_gemm_f16(&g, nullptr);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> out(nout);
+    if (c.out_mode == MVD_OUT_F32) {
+      CK(cudaMemcpy(out.data(), dout, nout * 4, cudaMemcpyDeviceToHost));
+    } else {
+      std::vector<__half> oh(nout);
+      CK(cudaMemcpy(oh.data(), dout, nout * 2, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < nout; ++i) out[i] = __half2float(oh[i]);
+    }
+    const double tol = c.out_mode == MVD_OUT_F32 ? tol32 : tol16;
+    const int bn = c.tile_n ? c.tile_n : (N <= 64 ? 64 : 128);
+    for (int m = 0; m < M; ++m)
+      for (int n = 0; n < No; ++n) {
+        double want;
+        if (geglu) {
+          // packed layout: inside each bn-wide tile, first half = value, second half = gate
+          const int tile = n / (bn / 2), w = n % (bn / 2);
+          const double val = pre(m, tile * bn + w), gate = pre(m, tile * bn + bn / 2 + w);
+          want = val * gelu(gate);
+        } else {
+          want = pre(m, n);
+          if (c.act == MVD_ACT_GELU) want = gelu(want);
+          if (c.act == MVD_ACT_SILU) want = silu(want);
+          if (c.residual) want += hres[static_cast<size_t>(m) * N + n];
+        }
+        cmp(out[static_cast<size_t>(m) * No + n], want, m, n, tol);
+      }
+    cudaFree(dout);
+  }
+  const bool ok = (rc == 0) && bad == 0;
+  printf("%-34s rc=%d max_err=%.3e max_ref=%.3e bad=%zu/%zu %s\n", c.name.c_str(), rc, max_err, max_ref, bad, total,
+         ok ? "OK" : "FAIL");
+  if (rc != 0) printf("    error: %s\n", mvd_last_error());
+  if (bad) printf("    first mismatch at (m=%d, n=%d): got %.6f want %.6f\n", first_bad_m, first_bad_n, first_got, first_want);
+  if (!ok) ++g_fail;
+  cudaFree(dA); cudaFree(dW); cudaFree(db);
+  if (drb) cudaFree(drb);
+  if (dres) cudaFree(dres);
+}
+
+int main(int argc, char** argv) {
+  int only = argc > 1 ? atoi(argv[1]) : -1;
+  std::vector<Case> cases;
+  { Case c; c.name = "plain 128x128x64"; c.M = 128; c.N = 128; c.K = 64; cases.push_back(c); }
+  { Case c; c.name = "plain 256x128x256"; c.M = 256; c.N = 128; c.K = 256; cases.push_back(c); }
+  { Case c; c.name = "tails 300x200x736 bias+res"; c.M = 300; c.N = 200; c.K = 736; c.bias = c.residual = true; cases.push_back(c); }
+  { Case c; c.name = "bn64 200x48x320"; c.M = 200; c.N = 48; c.K = 320; c.bias = true; cases.push_back(c); }
+  { Case c; c.name = "bn256 512x512x1280 rowbias"; c.M = 512; c.N = 512; c.K = 1280; c.tile_n = 256; c.rowbias = true; c.rows_per_group = 64; cases.push_back(c); }
+  { Case c; c.name = "f16 gelu 384x256x256"; c.M = 384; c.N = 256; c.K = 256; c.bias = true; c.act = MVD_ACT_GELU; c.out_mode = MVD_OUT_F16; cases.push_back(c); }
+  { Case c; c.name = "f16 silu bn64 130x64x128"; c.M = 130; c.N = 64; c.K = 128; c.act = MVD_ACT_SILU; c.out_mode = MVD_OUT_F16; cases.push_back(c); }
+  { Case c; c.name = "geglu 256x512x320"; c.M = 256; c.N = 512; c.K = 320; c.bias = true; c.act = MVD_ACT_GEGLU; c.out_mode = MVD_OUT_F16; cases.push_back(c); }
+  { Case c; c.name = "geglu bn256 256x1024x320"; c.M = 256; c.N = 1024; c.K = 320; c.bias = true; c.act = MVD_ACT_GEGLU; c.out_mode = MVD_OUT_F16; c.tile_n = 256; cases.push_back(c); }
+  { Case c; c.name = "splitk4 128x256x2048 bias+res"; c.M = 128; c.N = 256; c.K = 2048; c.split_k = 4; c.bias = c.residual = true; cases.push_back(c); }
+  { Case c; c.name = "splitk3 200x130x1000"; c.M = 200; c.N = 130; c.K = 1000; c.split_k = 3; c.lda_pad = 0; cases.push_back(c); }
+  { Case c; c.name = "conv 2x32x32x64->64"; c.a_mode = MVD_A_CONV3X3; c.n_img = 2; c.H = c.W = 32; c.C = 64; c.N = 64; c.K = 9 * 64; c.M = 2 * 32 * 32; c.bias = true; cases.push_back(c); }
+  { Case c; c.name = "conv 3x16x16x128->160 res"; c.a_mode = MVD_A_CONV3X3; c.n_img = 3; c.H = c.W = 16; c.C = 128; c.N = 160; c.K = 9 * 128; c.M = 3 * 256; c.bias = c.residual = true; cases.push_back(c); }
+  { Case c; c.name = "conv 3x8x8x192->128 rowbias"; c.a_mode = MVD_A_CONV3X3; c.n_img = 3; c.H = c.W = 8; c.C = 192; c.N = 128; c.K = 9 * 192; c.M = 3 * 64; c.rowbias = true; c.rows_per_group = 64; cases.push_back(c); }
+  { Case c; c.name = "conv 5x4x4x64->64 splitk"; c.a_mode = MVD_A_CONV3X3; c.n_img = 5; c.H = c.W = 4; c.C = 64; c.N = 64; c.K = 9 * 64; c.M = 5 * 16; c.split_k = 3; cases.push_back(c); }
+  { Case c; c.name = "conv stem 2x32x32x16->320"; c.a_mode = MVD_A_CONV3X3; c.n_img = 2; c.H = c.W = 32; c.C = 16; c.N = 320; c.K = 9 * 16; c.M = 2048; c.bias = true; cases.push_back(c); }
+  { Case c; c.name = "conv head 2x32x32x320->5"; c.a_mode = MVD_A_CONV3X3; c.n_img = 2; c.H = c.W = 32; c.C = 320; c.N = 5; c.K = 9 * 320; c.M = 2048; c.bias = true; cases.push_back(c); }
+  { Case c; c.name = "conv 1x64x64x64->64"; c.a_mode = MVD_A_CONV3X3; c.n_img = 1; c.H = c.W = 64; c.C = 64; c.N = 64; c.K = 9 * 64; c.M = 4096; cases.push_back(c); }
+  { Case c; c.name = "qkv heads 2x64 d40"; c.M = 128; c.N = 3 * 8 * 40; c.K = 320; c.out_mode = MVD_OUT_QKV_HEADS; c.heads = 8; c.dhead = 40; c.dpad = 64; c.seq = 64; cases.push_back(c); }
+  { Case c; c.name = "qkv heads 3x16 d160"; c.M = 48; c.N = 3 * 8 * 160; c.K = 1280; c.out_mode = MVD_OUT_QKV_HEADS; c.heads = 8; c.dhead = 160; c.dpad = 192; c.seq = 16; cases.push_back(c); }
+  for (size_t i = 0; i < cases.size(); ++i)
+    if (only < 0 || only == static_cast<int>(i)) run(cases[i]);
+  printf("%s (%d failing)\n", g_fail ? "GEMM CHECK FAILED" : "GEMM CHECK PASSED", g_fail);
+  return g_fail ? 1 : 0;
+}
