@@ -45,7 +45,8 @@ long long mvd_launch_count(void);
  *   replaces conv_nd(…,3,padding=1) (openaimodel.py:107,204,230; mvdfusion/unet.py:323,499).
  *
  * Epilogue (per element, in this order):
- *   v = acc + bias[n] + rowbias[(m / rows_per_group), n] ; v = act(v) ; v += residual[m, n] ; store
+ *   v = acc + bias[n] + rowbias[(m / rows_per_group), n] ; v = act(v) ; v *= colscale[n] ;
+ *   v += residual[m, n] ; store        (colscale = the adaLN gate of a DiT block, view_attn_efficient2.py:65-66)
  *   act: NONE, GELU (exact erf), SILU, GEGLU (weights pre-interleaved per tile so that column
  *        j and column j + BN/2 of a tile are value/gate; output has N/2 columns:
  *        out = value * gelu(gate); external/sd1/ldm/modules/attention.py:42-44)
@@ -69,6 +70,7 @@ typedef struct mvd_gemm_args {
   const float* bias;   /* [N] or NULL */
   const float* rowbias;/* [ceil(M/rows_per_group), N] or NULL */
   int32_t rows_per_group;
+  const float* colscale; /* [N] or NULL */
   const float* residual; /* fp32 [M, ldr] or NULL */
   int32_t ldr;
   int32_t act;
@@ -88,6 +90,84 @@ int mvd_gemm_f16(const mvd_gemm_args* args, void* stream);
 /* GEGLU weight interleave used by MVD_ACT_GEGLU for a given tile width: row index of the
  * packed weight -> row index of the original nn.Linear(dim, 2*inner) weight. */
 int mvd_geglu_row_permutation(int32_t inner_dim, int32_t tile_n, int32_t* perm_out /* [2*inner_dim] */);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-head self-attention (tcgen05 QK^T and PV, softmax in registers, scores stay in TMEM).
+ * Replaces CrossAttention.forward with context=None: external/sd1/ldm/modules/attention.py:170-193
+ * (called from :220 and mvdfusion/attention.py:52).
+ *   q, k : fp16 [n_img*heads, seq, dpad]   vt : fp16 [n_img*heads, dpad, seq]
+ *   out  : fp16 [n_img*seq, ldo], columns h*dhead + j  ('b n (h d)')
+ * ---------------------------------------------------------------------------------------------- */
+int mvd_attn_self_f16(const void* q, const void* k, const void* vt, void* out, int32_t n_img, int32_t heads,
+                      int32_t seq, int32_t dhead, int32_t dpad, int32_t ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Normalisation (fp32 residual stream in, fp16 GEMM operand out).
+ *   groupnorm : 32 groups over [n_img, hw, C]; optional SiLU.  util.py:200-217 (eps 1e-5, ResBlock/out),
+ *               external/sd1/ldm/modules/attention.py:76-77 (eps 1e-6).  stats_ws: n_img*64 doubles.
+ *   layernorm : nn.LayerNorm(C) (external/sd1/ldm/modules/attention.py:211-213, mvdfusion/attention.py:35-37)
+ *   ln_modulate : LayerNorm(no affine) then x*(1+scale)+shift (mvdfusion/view_attn_efficient2.py:15-16,65-66)
+ * ---------------------------------------------------------------------------------------------- */
+int mvd_groupnorm_f32_f16(const float* x, const float* gamma, const float* beta, void* y, void* stats_ws,
+                          int32_t n_img, int32_t hw, int32_t C, float eps, int32_t apply_silu, void* stream);
+int mvd_layernorm_f32_f16(const float* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t C,
+                          float eps, void* stream);
+int mvd_ln_modulate_f32_f16(const float* x, const float* shift, const float* scale, void* y, int32_t rows, int32_t C,
+                            float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Data movement / elementwise.
+ * ---------------------------------------------------------------------------------------------- */
+int mvd_cast_f32_f16(const float* x, void* y, long long n, void* stream);
+/* torch.cat([h, hs.pop()], dim=1) in rows x channels form (mvdfusion/unet.py:550) */
+int mvd_concat_f32(const float* a, const float* b, float* out, long long rows, int32_t C1, int32_t C2, void* stream);
+/* F.interpolate(scale_factor=2, mode="nearest") (openaimodel.py:116); fp32 NHWC -> fp16 NHWC */
+int mvd_upsample2x_f32_f16(const float* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C, void* stream);
+/* im2col of the stride-2 Downsample conv (openaimodel.py:151): fp32 NHWC -> fp16 [n*(H/2)*(W/2), 9*C] */
+int mvd_im2col_s2_f32_f16(const float* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C, void* stream);
+/* small-M linear: y = act_out(act_in(x) W^T + b); x fp32 [M, ldx], W fp16 [N, ldw], y fp32 [M, ldy].
+ * t-only MLPs: ResBlock.emb_layers (openaimodel.py:218-224), UNetModel.time_embed (unet.py:310-314),
+ * ViewFusion.time_embed / cc_projection (viewfusion_zero_depth_rgb.py:107-132), DiT adaLN (view_attn_efficient2.py:58-61) */
+int mvd_gemv_f16(const float* x, int32_t ldx, const void* W, int32_t ldw, const float* bias, float* y, int32_t ldy,
+                 int32_t M, int32_t N, int32_t K, int32_t silu_in, int32_t silu_out, void* stream);
+/* timestep_embedding (util.py:152-172): out[dim] = [cos(t f) | sin(t f)], t and f tables in device memory */
+int mvd_timestep_embedding(const float* t_dev, const float* freqs_dev, float* out, int32_t dim, void* stream);
+/* UNet input assembly incl. the unconditional CFG branch (mvdfusion/unet.py:153-161,173-186) -> fp16 NHWC */
+int mvd_unet_input_f16(const float* noisy, const float* cond, int32_t cond_batched, void* out, int32_t n_views,
+                       int32_t n_img, int32_t hw, int32_t Cpad, void* stream);
+/* CFG combine (mvdfusion/unet.py:195) + optional DDIM update (mvdfusion/sampler.py:55-65).
+ * coef_dev = {a_t, a_prev, sqrt(1-a_t), sigma_t, add_noise, cfg_scale} in device memory. */
+int mvd_cfg_ddim(const float* head, int32_t ld, int32_t two_branch, const float* coef_dev, const float* xt,
+                 const float* noise, float* eps_out, float* x_prev, float* x0_out, int32_t n_views, int32_t hw,
+                 void* stream);
+int mvd_nchw_to_rows_f32(const float* x, float* y, int32_t n_img, int32_t C, int32_t hw, void* stream);
+int mvd_rows_to_nchw_f32(const float* x, float* y, int32_t n_img, int32_t C, int32_t ld, int32_t hw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GridAttn: depth-guided cross-view aggregation (mvdfusion/view_attn_efficient2.py:269-442).
+ *   prep    : z-depth samples (:418-432) and z_embedder maps (:434-437).  scal_dev = {sqrt_alphas_cumprod[t], depth_std}
+ *             feat_out fp16 [n_views+1, S*S, 256] (last = input view); zdepth_out fp32 [n_views, D, S*S]
+ *   tokens  : unproject -> reproject -> bilinear gather -> Plucker/depth harmonics -> fp16 [q_count*S*S*D*n_views, 736]
+ *             cams fp32 [n_views+1, 16] = R(9, row-major) T(3) f(2) pp(2); last = input camera (pytorch3d conventions)
+ *   view_attention : timm Attention over the view axis; qkv fp16 [P*V, 768] -> out fp16 [P*V, 256]
+ *   view_pool      : weight_layer + softmax over V + weighted sum (:83,92,396-397) -> fp16 [P, 256]
+ *   frustum_pool   : area pyramid of the frustum features (mvdfusion/unet.py:198-209)
+ *   pixel_cross_attn : DualAttnetionBlock.attn2 with D > 1 keys per pixel (mvdfusion/attention.py:56-62)
+ * ---------------------------------------------------------------------------------------------- */
+int mvd_gridattn_prep(const float* noisy, const float* input_latent, const float* depth_override, const float* depth_eps,
+                      const float* scal_dev, const float* Wz, const float* bz, void* feat_out, float* zdepth_out,
+                      int32_t n_views, int32_t S, int32_t D, float depth_scale, float depth_shift, void* stream);
+int mvd_gridattn_tokens(const void* feat, const float* zdepth, const float* cams, const float* mask, const float* freqs,
+                        const float* ndc_grid, void* tokens, int32_t n_views, int32_t S, int32_t D, int32_t q_first,
+                        int32_t q_count, void* stream);
+int mvd_view_attention_f16(const void* qkv, void* out, int32_t P, int32_t V, int32_t heads, int32_t hd, void* stream);
+int mvd_view_pool_f16(const float* x, const float* w, const float* b, void* out, int32_t P, int32_t V, int32_t C,
+                      void* stream);
+int mvd_frustum_pool_f16(const void* in, void* out, int32_t n_img, int32_t S, int32_t D, int32_t C, int32_t factor,
+                         void* stream);
+int mvd_pixel_cross_attn_f16(const void* q, const void* kv, void* out, int32_t M, int32_t D, int32_t heads,
+                             int32_t dhead, void* stream);
 
 #ifdef __cplusplus
 }

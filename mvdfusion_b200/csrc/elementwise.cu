@@ -1,0 +1,353 @@
+// Data-movement / elementwise kernels of the UNet path (HBM/L2-bound; coalesced, vectorised):
+//   cast, channel concat, nearest x2 upsample, stride-2 im2col, small-M GEMV, sinusoidal timestep
+//   embedding, UNet input assembly, CFG combine + DDIM update.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mvd {
+
+__device__ __forceinline__ uint2 pack4(float a, float b, float c, float d) {
+  __half2 h0 = __floats2half2_rn(a, b);
+  __half2 h1 = __floats2half2_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  return u;
+}
+
+__global__ void cast_f32_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, size_t n4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<uint2*>(y)[i] = pack4(v.x, v.y, v.z, v.w);
+  }
+}
+
+// out[r, 0:C1] = a[r, :], out[r, C1:C1+C2] = b[r, :]   (torch.cat([h, hs.pop()], dim=1), mvdfusion/unet.py:550)
+__global__ void concat_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                  int C1, int C2, size_t total4) {
+  const int C = C1 + C2;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t e = i * 4;
+    const size_t r = e / C;
+    const int c = static_cast<int>(e - r * C);
+    float4 v;
+    if (c < C1)
+      v = *reinterpret_cast<const float4*>(a + r * C1 + c);
+    else
+      v = *reinterpret_cast<const float4*>(b + r * C2 + (c - C1));
+    *reinterpret_cast<float4*>(out + e) = v;
+  }
+}
+
+// F.interpolate(scale_factor=2, mode='nearest') (openaimodel.py:116): fp32 [n,H,W,C] -> fp16 [n,2H,2W,C]
+__global__ void upsample2x_kernel(const float* __restrict__ x, __half* __restrict__ y, int H, int W, int C,
+                                  size_t total4) {
+  const int W2 = 2 * W, H2 = 2 * H;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t e = i * 4;
+    const int c = static_cast<int>(e % C);
+    size_t pix = e / C;
+    const int ox = static_cast<int>(pix % W2);
+    pix /= W2;
+    const int oy = static_cast<int>(pix % H2);
+    const size_t img = pix / H2;
+    const float4 v = *reinterpret_cast<const float4*>(x + ((img * H + (oy >> 1)) * W + (ox >> 1)) * C + c);
+    *reinterpret_cast<uint2*>(y + e) = pack4(v.x, v.y, v.z, v.w);
+  }
+}
+
+// im2col for conv3x3 stride 2 pad 1 (Downsample.op, openaimodel.py:151):
+// fp32 [n,H,W,C] -> fp16 [n*(H/2)*(W/2), 9*C], k = (ky*3+kx)*C + c
+__global__ void im2col_s2_kernel(const float* __restrict__ x, __half* __restrict__ y, int H, int W, int C,
+                                 size_t total4) {
+  const int Ho = H / 2, Wo = W / 2, K = 9 * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t e = i * 4;
+    const int k = static_cast<int>(e % K);
+    size_t row = e / K;
+    const int tap = k / C, c = k - tap * C;
+    const int ky = tap / 3, kx = tap - ky * 3;
+    const int ox = static_cast<int>(row % Wo);
+    row /= Wo;
+    const int oy = static_cast<int>(row % Ho);
+    const size_t img = row / Ho;
+    const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = *reinterpret_cast<const float4*>(x + ((img * H + iy) * W + ix) * C + c);
+    *reinterpret_cast<uint2*>(y + e) = pack4(v.x, v.y, v.z, v.w);
+  }
+}
+
+// y[m, n] = act_out( sum_k act_in(x[m, k]) * W[n, k] + b[n] ),  tiny M (t-only MLPs, per-view context vectors).
+// One warp per output column n; W is fp16 [N, ldw]; x fp32 [M, ldx]; y fp32 [M, ldy].
+__global__ void gemv_kernel(const float* __restrict__ x, int ldx, const __half* __restrict__ W, int ldw,
+                            const float* __restrict__ bias, float* __restrict__ y, int ldy, int M, int N, int K,
+                            int silu_in, int silu_out) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const __half* w = W + static_cast<size_t>(n) * ldw;
+  for (int m0 = 0; m0 < M; m0 += 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane * 8; k < K; k += 256) {
+      const uint4 u = *reinterpret_cast<const uint4*>(w + k);
+      const __half2* hp = reinterpret_cast<const __half2*>(&u);
+      float wf[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(hp[j]);
+        wf[2 * j] = f.x;
+        wf[2 * j + 1] = f.y;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (m0 + r < M) {
+          const float* xr = x + static_cast<size_t>(m0 + r) * ldx + k;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float xv = (k + j < K) ? xr[j] : 0.f;
+            if (silu_in) xv = xv / (1.f + expf(-xv));
+            acc[r] = fmaf(xv, wf[j], acc[r]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float v = acc[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && m0 + r < M) {
+        if (bias != nullptr) v += bias[n];
+        if (silu_out) v = v / (1.f + expf(-v));
+        y[static_cast<size_t>(m0 + r) * ldy + n] = v;
+      }
+    }
+  }
+}
+
+// timestep_embedding (util.py:152-172 / mvdfusion/embedder.py:114-134): [cos(t*f_i) | sin(t*f_i)],
+// f_i = exp(-ln(max_period) * i / half) supplied as a host-built fp32 table (bit-identical to the
+// reference's torch.exp).  t is read from device memory (graph-replay friendly).
+__global__ void timestep_embed_kernel(const float* __restrict__ t_ptr, const float* __restrict__ freqs,
+                                      float* __restrict__ out, int dim) {
+  const int half = dim / 2;
+  const float t = *t_ptr;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float f = freqs[i];
+    const float a = t * f;
+    out[i] = cosf(a);
+    out[half + i] = sinf(a);
+  }
+  if ((dim & 1) && threadIdx.x == 0) out[dim - 1] = 0.f;
+}
+
+// UNet input (mvdfusion/unet.py:153-161,173-186): per image, NHWC fp16 with Cpad channels:
+//   ch 0..4  = noisy latent, ch 5..8 = input latent / 0.18215, ch 9 = input depth channel, rest 0.
+//   images [n_views, 2*n_views) are the unconditional branch: concat channels zeroed.
+__global__ void unet_input_kernel(const float* __restrict__ noisy /*[n,5,hw]*/, const float* __restrict__ cond /*[1 or n,5,hw]*/,
+                                  int cond_batched, __half* __restrict__ out, int n_views, int n_img, int hw, int Cpad) {
+  const size_t total = static_cast<size_t>(n_img) * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int img = static_cast<int>(i / hw);
+    const int pix = static_cast<int>(i - static_cast<size_t>(img) * hw);
+    const int view = img % n_views;
+    const bool uncond = img >= n_views;
+    __half* o = out + i * Cpad;
+    for (int c = 0; c < 5; ++c) o[c] = __float2half_rn(noisy[(static_cast<size_t>(view) * 5 + c) * hw + pix]);
+    const float* cb = cond + (cond_batched ? static_cast<size_t>(view) * 5 * hw : 0);
+    for (int c = 0; c < 5; ++c) {
+      float v = uncond ? 0.f : cb[static_cast<size_t>(c) * hw + pix];
+      if (c < 4) v = v / 0.18215f;
+      o[5 + c] = __float2half_rn(v);
+    }
+    for (int c = 10; c < Cpad; ++c) o[c] = __float2half_rn(0.f);
+  }
+}
+
+// eps = s_uc + w (s - s_uc) (mvdfusion/unet.py:195) from the UNet head output [n_img*hw, ld] (rows of
+// images [0,n) = conditional, [n,2n) = unconditional), written NCHW [n,5,hw]; when `xt` is given also the
+// DDIM update (mvdfusion/sampler.py:55-65):
+//   x0 = (x - sqrt(1-a_t) eps)/sqrt(a_t); x_prev = sqrt(a_prev) x0 + sqrt(max(1-a_prev-sigma^2,1e-7)) eps + sigma*noise
+// coef (device) = {a_t, a_prev, sqrt_one_minus_at, sigma_t, add_noise(0/1), cfg_scale}
+__global__ void cfg_ddim_kernel(const float* __restrict__ head, int ld, int two_branch, const float* __restrict__ coef,
+                                const float* __restrict__ xt, const float* __restrict__ noise, float* __restrict__ eps_out,
+                                float* __restrict__ x_prev, float* __restrict__ x0_out, int n, int hw) {
+  const size_t total = static_cast<size_t>(n) * 5 * hw;
+  const float w = coef[5];
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int pix = static_cast<int>(i % hw);
+    const int c = static_cast<int>((i / hw) % 5);
+    const int view = static_cast<int>(i / (static_cast<size_t>(hw) * 5));
+    const float s = head[(static_cast<size_t>(view) * hw + pix) * ld + c];
+    float e = s;
+    if (two_branch) {
+      const float su = head[(static_cast<size_t>(view + n) * hw + pix) * ld + c];
+      e = su + w * (s - su);
+    }
+    if (eps_out != nullptr) eps_out[i] = e;
+    if (xt != nullptr) {
+      const float a_t = coef[0], a_prev = coef[1], somat = coef[2], sigma = coef[3];
+      const float x = xt[i];
+      const float x0 = (x - somat * e) / sqrtf(a_t);
+      const float dir = sqrtf(fmaxf(1.f - a_prev - sigma * sigma, 1e-7f)) * e;
+      float xp = sqrtf(a_prev) * x0 + dir;
+      if (coef[4] != 0.f) xp += sigma * noise[i];
+      x_prev[i] = xp;
+      if (x0_out != nullptr) x0_out[i] = x0;
+    }
+  }
+}
+
+// NCHW fp32 <-> rows x channels fp32 (public per-module entry points only; the fused path never transposes)
+__global__ void nchw_to_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int hw, size_t total) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t r = i / C;
+    const size_t img = r / hw, pix = r % hw;
+    y[i] = x[(img * C + c) * hw + pix];
+  }
+}
+__global__ void rows_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int ld, int hw,
+                                    size_t total) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = i % hw;
+    const int c = static_cast<int>((i / hw) % C);
+    const size_t img = i / (static_cast<size_t>(hw) * C);
+    y[i] = x[(img * hw + pix) * ld + c];
+  }
+}
+
+static inline int grid_for(size_t n, int threads = 256) {
+  size_t b = (n + threads - 1) / threads;
+  if (b > 148u * 16u) b = 148u * 16u;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace mvd
+
+using namespace mvd;
+
+extern "C" int mvd_cast_f32_f16(const float* x, void* y, long long n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !y || n <= 0 || (n & 3)) return set_error(MVD_EINVAL, "mvd_cast_f32_f16: n must be a positive multiple of 4");
+  cast_f32_f16_kernel<<<grid_for(n / 4), 256, 0, stream>>>(x, static_cast<__half*>(y), static_cast<size_t>(n / 4));
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_concat_f32(const float* a, const float* b, float* out, long long rows, int32_t C1, int32_t C2,
+                              void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!a || !b || !out || rows <= 0 || C1 <= 0 || C2 <= 0 || (C1 & 3) || (C2 & 3))
+    return set_error(MVD_EINVAL, "mvd_concat_f32: channel counts must be multiples of 4");
+  const size_t total4 = static_cast<size_t>(rows) * (C1 + C2) / 4;
+  concat_f32_kernel<<<grid_for(total4), 256, 0, stream>>>(a, b, out, C1, C2, total4);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_upsample2x_f32_f16(const float* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                                      void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !y || n_img <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return set_error(MVD_EINVAL, "mvd_upsample2x_f32_f16: bad arguments");
+  const size_t total4 = static_cast<size_t>(n_img) * H * W * 4 * C / 4;
+  upsample2x_kernel<<<grid_for(total4), 256, 0, stream>>>(x, static_cast<__half*>(y), H, W, C, total4);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_im2col_s2_f32_f16(const float* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                                     void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !y || n_img <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || C <= 0 || (C & 3))
+    return set_error(MVD_EINVAL, "mvd_im2col_s2_f32_f16: bad arguments");
+  const size_t total4 = static_cast<size_t>(n_img) * (H / 2) * (W / 2) * 9 * C / 4;
+  im2col_s2_kernel<<<grid_for(total4), 256, 0, stream>>>(x, static_cast<__half*>(y), H, W, C, total4);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_gemv_f16(const float* x, int32_t ldx, const void* W, int32_t ldw, const float* bias, float* y,
+                            int32_t ldy, int32_t M, int32_t N, int32_t K, int32_t silu_in, int32_t silu_out,
+                            void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !W || !y || M <= 0 || N <= 0 || K <= 0) return set_error(MVD_EINVAL, "mvd_gemv_f16: bad arguments");
+  if ((ldw & 7) || ldw < ((K + 7) & ~7)) return set_error(MVD_EALIGN, "mvd_gemv_f16: ldw must be a multiple of 8 and >= K rounded up to 8");
+  gemv_kernel<<<(N + 7) / 8, 256, 0, stream>>>(x, ldx, static_cast<const __half*>(W), ldw, bias, y, ldy, M, N, K, silu_in,
+                                              silu_out);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_timestep_embedding(const float* t_dev, const float* freqs_dev, float* out, int32_t dim,
+                                      void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!t_dev || !freqs_dev || !out || dim < 2) return set_error(MVD_EINVAL, "mvd_timestep_embedding: bad arguments");
+  timestep_embed_kernel<<<1, 256, 0, stream>>>(t_dev, freqs_dev, out, dim);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_unet_input_f16(const float* noisy, const float* cond, int32_t cond_batched, void* out,
+                                  int32_t n_views, int32_t n_img, int32_t hw, int32_t Cpad, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!noisy || !cond || !out || n_views <= 0 || (n_img != n_views && n_img != 2 * n_views) || hw <= 0 || Cpad < 10 ||
+      (Cpad & 7))
+    return set_error(MVD_EINVAL, "mvd_unet_input_f16: bad arguments");
+  unet_input_kernel<<<grid_for(static_cast<size_t>(n_img) * hw), 256, 0, stream>>>(
+      noisy, cond, cond_batched, static_cast<__half*>(out), n_views, n_img, hw, Cpad);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_cfg_ddim(const float* head, int32_t ld, int32_t two_branch, const float* coef_dev, const float* xt,
+                            const float* noise, float* eps_out, float* x_prev, float* x0_out, int32_t n_views,
+                            int32_t hw, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!head || !coef_dev || n_views <= 0 || hw <= 0 || ld < 5) return set_error(MVD_EINVAL, "mvd_cfg_ddim: bad arguments");
+  if (xt != nullptr && (x_prev == nullptr || noise == nullptr)) return set_error(MVD_EINVAL, "mvd_cfg_ddim: x_prev and noise required with xt");
+  if (xt == nullptr && eps_out == nullptr) return set_error(MVD_EINVAL, "mvd_cfg_ddim: nothing to write");
+  cfg_ddim_kernel<<<grid_for(static_cast<size_t>(n_views) * 5 * hw), 256, 0, stream>>>(
+      head, ld, two_branch, coef_dev, xt, noise, eps_out, x_prev, x0_out, n_views, hw);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_nchw_to_rows_f32(const float* x, float* y, int32_t n_img, int32_t C, int32_t hw, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !y || n_img <= 0 || C <= 0 || hw <= 0) return set_error(MVD_EINVAL, "mvd_nchw_to_rows_f32: bad arguments");
+  const size_t total = static_cast<size_t>(n_img) * C * hw;
+  nchw_to_rows_kernel<<<grid_for(total), 256, 0, stream>>>(x, y, C, hw, total);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_rows_to_nchw_f32(const float* x, float* y, int32_t n_img, int32_t C, int32_t ld, int32_t hw,
+                                    void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !y || n_img <= 0 || C <= 0 || hw <= 0 || ld < C) return set_error(MVD_EINVAL, "mvd_rows_to_nchw_f32: bad arguments");
+  const size_t total = static_cast<size_t>(n_img) * C * hw;
+  rows_to_nchw_kernel<<<grid_for(total), 256, 0, stream>>>(x, y, C, ld, hw, total);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}

@@ -35,6 +35,7 @@ struct GemmKParams {
   const float* bias;
   const float* rowbias;
   int rows_per_group;
+  const float* colscale;
   const float* residual;
   int ldr;
   int act, out_mode;
@@ -253,6 +254,10 @@ __global__ void __launch_bounds__(GEMM_THREADS)
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = silu(v[i]);
         }
+        if (p.colscale != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= (full || nc + i < p.N) ? __ldg(p.colscale + nc + i) : 0.f;
+        }
         if (lead && p.residual != nullptr) {
           const float* res = p.residual + static_cast<size_t>(grow) * p.ldr + nc;
           if (full && (p.ldr & 3) == 0) {
@@ -363,6 +368,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   p.bias = a->bias;
   p.rowbias = a->rowbias;
   p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
+  p.colscale = a->colscale;
   p.residual = a->residual;
   p.ldr = a->ldr;
   p.act = a->act;
@@ -431,7 +437,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   split = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.split_k = split;
   if (split > 1) {
-    if (a->out_mode != MVD_OUT_F32 || a->act != MVD_ACT_NONE)
+    if (a->out_mode != MVD_OUT_F32 || a->act != MVD_ACT_NONE || a->colscale != nullptr)
       return set_error(MVD_EINVAL, "mvd_gemm_f16: split_k needs F32 output and no activation");
     if (a->ldc == a->N) {
       MVD_CUDA_CHECK(cudaMemsetAsync(a->out, 0, static_cast<size_t>(a->M) * a->N * sizeof(float), stream));
