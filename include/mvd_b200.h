@@ -134,15 +134,23 @@ int mvd_gemv_f16(const float* x, int32_t ldx, const void* W, int32_t ldw, const 
 /* timestep_embedding (util.py:152-172): out[dim] = [cos(t f) | sin(t f)], t and f tables in device memory */
 int mvd_timestep_embedding(const float* t_dev, const float* freqs_dev, float* out, int32_t dim, void* stream);
 /* UNet input assembly incl. the unconditional CFG branch (mvdfusion/unet.py:153-161,173-186) -> fp16 NHWC */
-int mvd_unet_input_f16(const float* noisy, const float* cond, int32_t cond_batched, void* out, int32_t n_views,
-                       int32_t n_img, int32_t hw, int32_t Cpad, void* stream);
+/* cond_scale: optional [n_views] multiplier of the concat channels (condition drop, mvdfusion/unet.py:140-151) */
+int mvd_unet_input_f16(const float* noisy, const float* cond, int32_t cond_batched, const float* cond_scale, void* out,
+                       int32_t n_views, int32_t n_img, int32_t hw, int32_t Cpad, void* stream);
 /* CFG combine (mvdfusion/unet.py:195) + optional DDIM update (mvdfusion/sampler.py:55-65).
  * coef_dev = {a_t, a_prev, sqrt(1-a_t), sigma_t, add_noise, cfg_scale} in device memory. */
 int mvd_cfg_ddim(const float* head, int32_t ld, int32_t two_branch, const float* coef_dev, const float* xt,
                  const float* noise, float* eps_out, float* x_prev, float* x0_out, int32_t n_views, int32_t hw,
                  void* stream);
+/* out[0:row_len] = table[*idx_dev * row_len + ...]: per-step schedule constants (mvdfusion/sampler.py:55-58 indexes
+ * them on the host every step) and pre-drawn noise rows, selected by a device-resident step counter so that one
+ * captured CUDA graph replays the whole DDIM loop (mvdfusion/sampler.py:119-142); mvd_increment_i32 advances it. */
+int mvd_gather_rows_f32(const float* table, long long row_len, const int32_t* idx_dev, float* out, void* stream);
+int mvd_increment_i32(int32_t* counter_dev, int32_t delta, void* stream);
 int mvd_nchw_to_rows_f32(const float* x, float* y, int32_t n_img, int32_t C, int32_t hw, void* stream);
 int mvd_rows_to_nchw_f32(const float* x, float* y, int32_t n_img, int32_t C, int32_t ld, int32_t hw, void* stream);
+/* NCHW fp32 -> NHWC fp16 with the channel dim zero-padded to Cpad (UNetModel.forward input, mvdfusion/unet.py:524,544) */
+int mvd_nchw_to_nhwc_f16(const float* x, void* y, int32_t n_img, int32_t C, int32_t hw, int32_t Cpad, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GridAttn: depth-guided cross-view aggregation (mvdfusion/view_attn_efficient2.py:269-442).

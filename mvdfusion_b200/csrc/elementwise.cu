@@ -149,8 +149,10 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t_ptr, const flo
 // UNet input (mvdfusion/unet.py:153-161,173-186): per image, NHWC fp16 with Cpad channels:
 //   ch 0..4  = noisy latent, ch 5..8 = input latent / 0.18215, ch 9 = input depth channel, rest 0.
 //   images [n_views, 2*n_views) are the unconditional branch: concat channels zeroed.
+//   cond_scale (optional, [n_views]) multiplies the concat channels of a view (condition drop, unet.py:140-151).
 __global__ void unet_input_kernel(const float* __restrict__ noisy /*[n,5,hw]*/, const float* __restrict__ cond /*[1 or n,5,hw]*/,
-                                  int cond_batched, __half* __restrict__ out, int n_views, int n_img, int hw, int Cpad) {
+                                  int cond_batched, const float* __restrict__ cond_scale, __half* __restrict__ out,
+                                  int n_views, int n_img, int hw, int Cpad) {
   const size_t total = static_cast<size_t>(n_img) * hw;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -163,6 +165,7 @@ __global__ void unet_input_kernel(const float* __restrict__ noisy /*[n,5,hw]*/, 
     const float* cb = cond + (cond_batched ? static_cast<size_t>(view) * 5 * hw : 0);
     for (int c = 0; c < 5; ++c) {
       float v = uncond ? 0.f : cb[static_cast<size_t>(c) * hw + pix];
+      if (cond_scale != nullptr) v *= cond_scale[view];
       if (c < 4) v = v / 0.18215f;
       o[5 + c] = __float2half_rn(v);
     }
@@ -223,6 +226,30 @@ __global__ void rows_to_nchw_kernel(const float* __restrict__ x, float* __restri
     const int c = static_cast<int>((i / hw) % C);
     const size_t img = i / (static_cast<size_t>(hw) * C);
     y[i] = x[(img * hw + pix) * ld + c];
+  }
+}
+
+// out[0:row_len] = table[idx[0] * row_len + ...]: per-step constants / pre-drawn noise selected by a device-resident
+// step counter, so that one captured CUDA graph replays every DDIM iteration (mvdfusion/sampler.py:119-142).
+__global__ void gather_rows_kernel(const float* __restrict__ table, long long row_len, const int* __restrict__ idx,
+                                   float* __restrict__ out) {
+  const float* src = table + static_cast<long long>(*idx) * row_len;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < row_len;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = src[i];
+}
+__global__ void increment_kernel(int* p, int delta) { *p += delta; }
+
+// NCHW fp32 [n, C, hw] -> NHWC fp16 [n, hw, Cpad] (channels >= C zero-filled): input of the stem conv when a caller
+// hands UNetModel.forward an already-assembled tensor (mvdfusion/unet.py:524).
+__global__ void nchw_to_nhwc_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, int C, int hw, int Cpad,
+                                        size_t total) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cpad);
+    const size_t r = i / Cpad;
+    const size_t img = r / hw, pix = r % hw;
+    y[i] = __float2half_rn(c < C ? x[(img * C + c) * hw + pix] : 0.f);
   }
 }
 
@@ -304,14 +331,14 @@ extern "C" int mvd_timestep_embedding(const float* t_dev, const float* freqs_dev
   return MVD_OK;
 }
 
-extern "C" int mvd_unet_input_f16(const float* noisy, const float* cond, int32_t cond_batched, void* out,
-                                  int32_t n_views, int32_t n_img, int32_t hw, int32_t Cpad, void* stream_) {
+extern "C" int mvd_unet_input_f16(const float* noisy, const float* cond, int32_t cond_batched, const float* cond_scale,
+                                  void* out, int32_t n_views, int32_t n_img, int32_t hw, int32_t Cpad, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!noisy || !cond || !out || n_views <= 0 || (n_img != n_views && n_img != 2 * n_views) || hw <= 0 || Cpad < 10 ||
       (Cpad & 7))
     return set_error(MVD_EINVAL, "mvd_unet_input_f16: bad arguments");
   unet_input_kernel<<<grid_for(static_cast<size_t>(n_img) * hw), 256, 0, stream>>>(
-      noisy, cond, cond_batched, static_cast<__half*>(out), n_views, n_img, hw, Cpad);
+      noisy, cond, cond_batched, cond_scale, static_cast<__half*>(out), n_views, n_img, hw, Cpad);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -347,6 +374,36 @@ extern "C" int mvd_rows_to_nchw_f32(const float* x, float* y, int32_t n_img, int
   if (!x || !y || n_img <= 0 || C <= 0 || hw <= 0 || ld < C) return set_error(MVD_EINVAL, "mvd_rows_to_nchw_f32: bad arguments");
   const size_t total = static_cast<size_t>(n_img) * C * hw;
   rows_to_nchw_kernel<<<grid_for(total), 256, 0, stream>>>(x, y, C, ld, hw, total);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_gather_rows_f32(const float* table, long long row_len, const int32_t* idx_dev, float* out,
+                                   void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!table || !idx_dev || !out || row_len <= 0) return set_error(MVD_EINVAL, "mvd_gather_rows_f32: bad arguments");
+  gather_rows_kernel<<<grid_for(static_cast<size_t>(row_len)), 256, 0, stream>>>(table, row_len, idx_dev, out);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_increment_i32(int32_t* p, int32_t delta, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!p) return set_error(MVD_EINVAL, "mvd_increment_i32: null pointer");
+  increment_kernel<<<1, 1, 0, stream>>>(p, delta);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_nchw_to_nhwc_f16(const float* x, void* y, int32_t n_img, int32_t C, int32_t hw, int32_t Cpad,
+                                    void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !y || n_img <= 0 || C <= 0 || hw <= 0 || Cpad < C) return set_error(MVD_EINVAL, "mvd_nchw_to_nhwc_f16: bad arguments");
+  const size_t total = static_cast<size_t>(n_img) * hw * Cpad;
+  nchw_to_nhwc_f16_kernel<<<grid_for(total), 256, 0, stream>>>(x, static_cast<__half*>(y), C, hw, Cpad, total);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

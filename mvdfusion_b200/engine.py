@@ -1,0 +1,600 @@
+"""Host-side engine of the multi-view denoising hot path.
+
+A denoising step (GridAttn over N views -> UNet over N (x2 under CFG) view latents -> CFG combine -> DDIM
+update) is compiled ONCE per shape into a `Program`: a flat list of bound C-ABI calls (ops.BoundCall) over
+pre-allocated HBM buffers.  The program is replayed every step, either call by call or from a captured CUDA
+graph; nothing is allocated, synchronised or copied to the host inside it.
+
+Data layout in HBM: activations are "rows x channels" (NHWC flattened), the residual stream is
+fp32, every tensor-core operand is fp16; weights are packed once per state-dict version into K-major fp16
+matrices (conv kernels as [C_out, (ky,kx,c)], q/k/v fused, GEGLU value/gate rows interleaved per 128-column tile).
+
+Reference call sites each emitter replaces are cited in its docstring (paths under the reference root).
+"""
+import math
+
+import torch
+
+from .ops import ACT_GEGLU, ACT_GELU, ACT_NONE
+
+NUM_SMS = 148
+Z_CH = 256        # GridAttn z_embedder width (mvdfusion/view_attn_efficient2.py:151)
+TOKEN_LD = 736    # 723-d GridAttn token rounded up to a multiple of 16
+CTX_DIM = 768
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------------------ weights
+class PackedWeights:
+    """Kernel-side weight cache derived from a reference-named state dict (SURVEY.md §5 checkpoint contract:
+    parameter names / shapes stay the reference's; packed copies are rebuilt after load_state_dict)."""
+
+    def __init__(self, state_dict, ops, prefix=""):
+        self.sd = state_dict
+        self.ops = ops
+        self.prefix = prefix
+        self.cache = {}
+
+    def _full(self, key):
+        k = self.prefix + key
+        return k[1:] if k.startswith(".") else k  # module-level plans use an empty layer prefix
+
+    def has(self, key):
+        return self._full(key) in self.sd
+
+    def raw(self, key):
+        return self.sd[self._full(key)].detach()
+
+    def _put(self, tag, key, fn):
+        k = (tag, key)
+        if k not in self.cache:
+            self.cache[k] = fn().contiguous().to(self.ops.device)
+        return self.cache[k]
+
+    def f32(self, key):
+        return self._put("f32", key, lambda: self.raw(key).float().reshape(-1))
+
+    def f32_sum(self, key_a, key_b):
+        return self._put("f32sum", (key_a, key_b), lambda: (self.raw(key_a).float() + self.raw(key_b).float()).reshape(-1))
+
+    @staticmethod
+    def _pad_k(w):
+        n, k = w.shape
+        k8 = _round_up(k, 8)
+        if k8 != k:
+            w = torch.cat([w, w.new_zeros(n, k8 - k)], dim=1)
+        return w
+
+    def lin(self, key, k_pad=None):
+        """nn.Linear / 1x1-conv weight [N, K(,1,1)] -> fp16 [N, K8]"""
+        def f():
+            w = self.raw(key).float()
+            w = w.reshape(w.shape[0], -1)
+            if k_pad is not None and k_pad > w.shape[1]:
+                w = torch.cat([w, w.new_zeros(w.shape[0], k_pad - w.shape[1])], dim=1)
+            return self._pad_k(w).half()
+        return self._put("lin", (key, k_pad), f)
+
+    def conv3(self, key, c_pad=None):
+        """conv3x3 weight [Cout, Cin, 3, 3] -> fp16 [Cout, 9*Cin_pad], k = (ky*3 + kx)*Cin_pad + c"""
+        def f():
+            w = self.raw(key).float()
+            co, ci = w.shape[0], w.shape[1]
+            cp = c_pad if c_pad is not None else ci
+            w = w.permute(0, 2, 3, 1)  # [Cout, ky, kx, Cin]
+            if cp != ci:
+                w = torch.cat([w, w.new_zeros(co, 3, 3, cp - ci)], dim=3)
+            return w.reshape(co, 9 * cp).half()
+        return self._put("conv3", (key, c_pad), f)
+
+    def qkv(self, p):
+        """to_q | to_k | to_v fused into one [3C, C] matrix (external/sd1/ldm/modules/attention.py:161-163)"""
+        return self._put("qkv", p, lambda: self._pad_k(torch.cat([self.raw(p + ".to_q.weight"), self.raw(p + ".to_k.weight"),
+                                                                  self.raw(p + ".to_v.weight")], 0).float()).half())
+
+    def kv(self, p):
+        return self._put("kv", p, lambda: self._pad_k(torch.cat([self.raw(p + ".to_k.weight"),
+                                                                 self.raw(p + ".to_v.weight")], 0).float()).half())
+
+    def geglu(self, p, tile_n=128):
+        """GEGLU.proj [2*inner, C] with value/gate rows interleaved per output tile (include/mvd_b200.h, MVD_ACT_GEGLU)"""
+        w = self.raw(p + ".weight")
+        inner = w.shape[0] // 2
+        perm = self._put("geglu_perm", (inner, tile_n), lambda: self.ops.geglu_permutation(inner, tile_n))
+        wp = self._put("geglu_w", p, lambda: self._pad_k(self.raw(p + ".weight").float()[perm.cpu()]).half())
+        bp = self._put("geglu_b", p, lambda: self.raw(p + ".bias").float()[perm.cpu()])
+        return wp, bp
+
+
+# ------------------------------------------------------------------------------------------------ buffers
+class Arena:
+    """Scratch-buffer pool.  Calls of a Program execute in order on one stream, so a buffer may be handed out
+    again as soon as the emitter that produced its last reader has been appended."""
+
+    def __init__(self, ops):
+        self.ops = ops
+        self.free_list = []   # base uint8 tensors
+        self.base_of = {}     # data_ptr -> base
+        self.total_bytes = 0
+
+    def alloc(self, shape, dtype):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        nbytes = _round_up(max(n, 1) * torch.empty((), dtype=dtype).element_size(), 1024)
+        best = None
+        for i, b in enumerate(self.free_list):
+            if b.numel() >= nbytes and (best is None or b.numel() < self.free_list[best].numel()):
+                best = i
+        if best is not None and self.free_list[best].numel() <= 2 * nbytes:
+            base = self.free_list.pop(best)
+        else:
+            base = self.ops.empty((nbytes,), torch.uint8)
+            self.total_bytes += nbytes
+        t = base[: n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
+        self.base_of[t.data_ptr()] = base
+        return t
+
+    def free(self, *tensors):
+        for t in tensors:
+            if t is None:
+                continue
+            base = self.base_of.pop(t.data_ptr(), None)
+            if base is not None:
+                self.free_list.append(base)
+
+
+class Program:
+    """A fixed sequence of bound kernel calls."""
+
+    def __init__(self):
+        self.calls = []
+
+    def append(self, call):
+        self.calls.append(call)
+
+    def extend(self, other):
+        self.calls.extend(other.calls)
+
+    def run(self, stream):
+        for c in self.calls:
+            c(stream)
+
+    def __len__(self):
+        return len(self.calls)
+
+
+# ------------------------------------------------------------------------------------------------ emitters
+class Builder:
+    """Emits kernel-call sequences for the reference modules into a Program."""
+
+    def __init__(self, ops, weights, program=None, arena=None):
+        self.ops = ops
+        self.W = weights
+        self.prog = program if program is not None else Program()
+        self.arena = arena if arena is not None else Arena(ops)
+        self._qkv_bufs = {}
+        self._stats = None
+        self.heads = 8
+
+    # -- buffers
+    def t16(self, *shape):
+        return self.arena.alloc(shape, torch.float16)
+
+    def t32(self, *shape):
+        return self.arena.alloc(shape, torch.float32)
+
+    def free(self, *ts):
+        self.arena.free(*ts)
+
+    def stats_ws(self, n_img):
+        if self._stats is None or self._stats.numel() < n_img * 64:
+            self._stats = self.ops.zeros((max(n_img, 64) * 64,), torch.float64)
+        return self._stats
+
+    def qkv_buffers(self, n_img, seq, dpad):
+        """q, k [n_img*heads, seq, dpad] and v^T [n_img*heads, dpad, seq]; head-dim padding stays zero because
+        the QKV GEMM epilogue only ever writes the first dhead columns."""
+        key = (n_img, seq, dpad)
+        if key not in self._qkv_bufs:
+            n = n_img * self.heads * seq * dpad
+            self._qkv_bufs[key] = tuple(self.ops.zeros((n,), torch.float16) for _ in range(3))
+        return self._qkv_bufs[key]
+
+    @staticmethod
+    def split_k_for(M, N, K, tile_n=128):
+        tiles = math.ceil(M / 128) * math.ceil(N / tile_n)
+        kb = math.ceil(K / 64)
+        if tiles >= NUM_SMS or kb < 8:
+            return 1
+        return max(1, min(math.ceil(2 * NUM_SMS / tiles), kb // 4, 32))
+
+    # -- primitive emitters
+    def gemm(self, A, Wt, out, M, N, K, *, allow_split=False, **kw):
+        split = 1
+        if allow_split and out.dtype == torch.float32 and kw.get("act", ACT_NONE) == ACT_NONE and kw.get("colscale") is None:
+            split = self.split_k_for(M, N, K)
+        self.prog.append(self.ops.gemm(A, Wt, out, M, N, K, split_k=split, **kw))
+
+    def groupnorm(self, x, p, n_img, hw, C, eps, silu):
+        """GroupNorm32(32, C) (+SiLU) -> fp16 operand.  util.py:200-217 / attention.py:76-77"""
+        y = self.t16(n_img * hw, C)
+        self.prog.append(self.ops.groupnorm(x, self.W.f32(p + ".weight"), self.W.f32(p + ".bias"), y, self.stats_ws(n_img),
+                                            n_img, hw, C, eps, silu))
+        return y
+
+    def layernorm(self, x, p, rows, C):
+        y = self.t16(rows, C)
+        self.prog.append(self.ops.layernorm(x, self.W.f32(p + ".weight"), self.W.f32(p + ".bias"), y, rows, C, 1e-5))
+        return y
+
+    def conv3x3(self, a16, wkey, n_img, H, W_, Cin, Cout, *, bias, residual=None, c_pad=None, ldc=None, out=None,
+                rowbias=None, rows_per_group=1):
+        """conv_nd(2, Cin, Cout, 3, padding=1) as implicit GEMM (openaimodel.py:107,204,230; unet.py:323,499)"""
+        M = n_img * H * W_
+        cp = c_pad if c_pad is not None else Cin
+        if out is None:
+            out = self.t32(M, ldc if ldc is not None else Cout)
+        w = self.W.conv3(wkey, c_pad)
+        self.gemm(a16, w, out, M, Cout, 9 * cp, allow_split=True, conv=(n_img, H, W_, cp), bias=bias, residual=residual,
+                  rowbias=rowbias, rows_per_group=rows_per_group,
+                  ldr=(residual.shape[-1] if residual is not None else 0), ldc=(ldc if ldc is not None else Cout))
+        return out
+
+    def cast16(self, x, rows, C):
+        y = self.t16(rows, C)
+        self.prog.append(self.ops.cast(x, y, rows * C))
+        return y
+
+    # -- ResBlock
+    def resblock(self, x, p, n_img, H, Cin, Cout, emb, emb_dim):
+        """ResBlock._forward (openaimodel.py:255-275): GN-SiLU-conv, + Linear(SiLU(emb)), GN-SiLU-conv, + skip.
+        The timestep term is per-channel only (one shared t), so it rides in the first conv's bias."""
+        hw, M = H * H, n_img * H * H
+        a = self.groupnorm(x, p + ".in_layers.0", n_img, hw, Cin, 1e-5, True)
+        ne = emb.shape[0]  # 1 on the path (shared t); n_img when a caller passes per-image embeddings
+        eb = self.t32(ne, Cout)
+        self.prog.append(self.ops.gemv(emb, self.W.lin(p + ".emb_layers.1.weight"),
+                                       self.W.f32_sum(p + ".emb_layers.1.bias", p + ".in_layers.2.bias"), eb, ne, Cout,
+                                       emb_dim, silu_in=True))
+        if ne == 1:
+            h = self.conv3x3(a, p + ".in_layers.2.weight", n_img, H, H, Cin, Cout, bias=eb)
+        else:
+            h = self.conv3x3(a, p + ".in_layers.2.weight", n_img, H, H, Cin, Cout, bias=None, rowbias=eb, rows_per_group=hw)
+        self.free(a)
+        b = self.groupnorm(h, p + ".out_layers.0", n_img, hw, Cout, 1e-5, True)
+        self.free(h, eb)
+        res, s = x, None
+        if self.W.has(p + ".skip_connection.weight"):
+            x16 = self.cast16(x, M, Cin)
+            s = self.t32(M, Cout)
+            self.gemm(x16, self.W.lin(p + ".skip_connection.weight"), s, M, Cout, Cin, allow_split=True,
+                      bias=self.W.f32(p + ".skip_connection.bias"))
+            self.free(x16)
+            res = s
+        out = self.conv3x3(b, p + ".out_layers.3.weight", n_img, H, H, Cout, Cout, bias=self.W.f32(p + ".out_layers.3.bias"),
+                           residual=res)
+        self.free(b, s)
+        return out
+
+    def downsample(self, x, p, n_img, H, C):
+        """Downsample.op: conv3x3 stride 2 (openaimodel.py:151) = fp16 im2col + GEMM"""
+        Mo = n_img * (H // 2) * (H // 2)
+        col = self.t16(Mo, 9 * C)
+        self.prog.append(self.ops.im2col_s2(x, col, n_img, H, H, C))
+        out = self.t32(Mo, C)
+        self.gemm(col, self.W.conv3(p + ".op.weight"), out, Mo, C, 9 * C, allow_split=True, bias=self.W.f32(p + ".op.bias"))
+        self.free(col)
+        return out
+
+    def upsample(self, x, p, n_img, H, C):
+        """Upsample: nearest x2 then conv3x3 (openaimodel.py:107-119)"""
+        u = self.t16(n_img * 4 * H * H, C)
+        self.prog.append(self.ops.upsample2x(x, u, n_img, H, H, C))
+        out = self.conv3x3(u, p + ".conv.weight", n_img, 2 * H, 2 * H, C, C, bias=self.W.f32(p + ".conv.bias"))
+        self.free(u)
+        return out
+
+    # -- attention blocks
+    def self_attention(self, h, p, norm, n_img, seq, C, rowbias=None):
+        """x = attn1(norm1(x)) + x  [+ per-image vector]: LayerNorm -> fused QKV GEMM (heads scattered) ->
+        flash attention -> to_out GEMM with bias + residual.  attention.py:170-193,220; mvd attention.py:52"""
+        M = n_img * seq
+        d = C // self.heads
+        dpad = _round_up(d, 64)
+        ln = self.layernorm(h, norm, M, C)
+        q, k, vt = self.qkv_buffers(n_img, seq, dpad)
+        self.gemm(ln, self.W.qkv(p), q, M, 3 * C, C,
+                  qkv=dict(out_k=k, out_vt=vt, heads=self.heads, dhead=d, dpad=dpad, seq=seq))
+        ao = ln  # reuse: same shape / dtype, the QKV GEMM was its last reader
+        self.prog.append(self.ops.attn_self(q, k, vt, ao, n_img, self.heads, seq, d, dpad, C))
+        h2 = self.t32(M, C)
+        self.gemm(ao, self.W.lin(p + ".to_out.0.weight"), h2, M, C, C, allow_split=True, bias=self.W.f32(p + ".to_out.0.bias"),
+                  rowbias=rowbias, rows_per_group=seq, residual=h, ldr=C)
+        self.free(ao, h)
+        return h2
+
+    def feed_forward(self, h, p, norm, M, C):
+        """x = ff(norm3(x)) + x with the GEGLU fused into the first GEMM's epilogue.  attention.py:37-64,222"""
+        ln = self.layernorm(h, norm, M, C)
+        inner = 4 * C
+        wg, bg = self.W.geglu(p + ".net.0.proj")
+        g = self.t16(M, inner)
+        self.gemm(ln, wg, g, M, 2 * inner, C, bias=bg, act=ACT_GEGLU, tile_n=128, ldc=inner)
+        self.free(ln)
+        h2 = self.t32(M, C)
+        self.gemm(g, self.W.lin(p + ".net.2.weight"), h2, M, C, inner, allow_split=True, bias=self.W.f32(p + ".net.2.bias"),
+                  residual=h, ldr=C)
+        self.free(g, h)
+        return h2
+
+    def spatial_transformer(self, x, p, n_img, H, C, clipvec):
+        """SpatialTransformer.forward (attention.py:268-287) with BasicTransformerBlock (:219-223).
+        attn2 sees ONE CLIP token per view, so softmax == 1 and its output is the per-view vector
+        to_out(to_v(ctx)) (`clipvec`, [n_img, C]); it is added in the attn1 output GEMM's epilogue."""
+        hw, M = H * H, n_img * H * H
+        a = self.groupnorm(x, p + ".norm", n_img, hw, C, 1e-6, False)
+        h = self.t32(M, C)
+        self.gemm(a, self.W.lin(p + ".proj_in.weight"), h, M, C, C, allow_split=True, bias=self.W.f32(p + ".proj_in.bias"))
+        self.free(a)
+        tb = p + ".transformer_blocks.0"
+        h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C, rowbias=clipvec)
+        h = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C)
+        h16 = self.cast16(h, M, C)
+        self.free(h)
+        out = self.t32(M, C)
+        self.gemm(h16, self.W.lin(p + ".proj_out.weight"), out, M, C, C, allow_split=True, bias=self.W.f32(p + ".proj_out.bias"),
+                  residual=x, ldr=C)
+        self.free(h16)
+        return out
+
+    def clip_vector(self, ctx, p, n_img, C, out=None):
+        """Per-view output of the one-token CLIP cross-attention: to_out(to_v(ctx)) + bias  (attention.py:221)."""
+        tb = p + ".transformer_blocks.0.attn2"
+        v = self.t32(n_img, C)
+        self.prog.append(self.ops.gemv(ctx, self.W.lin(tb + ".to_v.weight"), None, v, n_img, C, CTX_DIM))
+        if out is None:
+            out = self.ops.empty((n_img, C), torch.float32)
+        self.prog.append(self.ops.gemv(v, self.W.lin(tb + ".to_out.0.weight"), self.W.f32(tb + ".to_out.0.bias"), out, n_img,
+                                       C, C))
+        self.free(v)
+        return out
+
+    def view_cross_attention(self, h, p, norm, ctx16, M, D, C):
+        """DualAttnetionBlock.attn2 (mvd attention.py:56-62): every pixel is one query against its D frustum keys."""
+        d = C // self.heads
+        if D == 1:  # softmax over a single key == 1: out = to_out(to_v(ctx))
+            v = self.t16(M, C)
+            self.gemm(ctx16, self.W.lin(p + ".to_v.weight"), v, M, C, CTX_DIM)
+            o = v
+        else:
+            ln = self.layernorm(h, norm, M, C)
+            q = self.t16(M, C)
+            self.gemm(ln, self.W.lin(p + ".to_q.weight"), q, M, C, C)
+            self.free(ln)
+            kv = self.t16(M * D, 2 * C)
+            self.gemm(ctx16, self.W.kv(p), kv, M * D, 2 * C, CTX_DIM)
+            o = self.t16(M, C)
+            self.prog.append(self.ops.pixel_cross_attn(q, kv, o, M, D, self.heads, d))
+            self.free(q, kv)
+        h2 = self.t32(M, C)
+        self.gemm(o, self.W.lin(p + ".to_out.0.weight"), h2, M, C, C, allow_split=True, bias=self.W.f32(p + ".to_out.0.bias"),
+                  residual=h, ldr=C)
+        self.free(o, h)
+        return h2
+
+    def view_aligned_transformer(self, x, p, n_img, H, C, ctx16, D):
+        """ViewAlignedFeatureTransformer.forward (mvd attention.py:119-145) + DualAttnetionBlock (:43-66)."""
+        hw, M = H * H, n_img * H * H
+        a = self.groupnorm(x, p + ".aligned_attn_norm", n_img, hw, C, 1e-6, False)
+        h = self.t32(M, C)
+        self.gemm(a, self.W.lin(p + ".aligned_attn_proj_in.weight"), h, M, C, C, allow_split=True,
+                  bias=self.W.f32(p + ".aligned_attn_proj_in.bias"))
+        self.free(a)
+        tb = p + ".aligned_attn_transformer_blocks.0"
+        h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C)
+        h = self.view_cross_attention(h, tb + ".attn2", tb + ".norm2", ctx16, M, D, C)
+        h = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C)
+        h16 = self.cast16(h, M, C)
+        self.free(h)
+        out = self.t32(M, C)
+        self.gemm(h16, self.W.lin(p + ".aligned_attn_proj_out.weight"), out, M, C, C, allow_split=True,
+                  bias=self.W.f32(p + ".aligned_attn_proj_out.bias"), residual=x, ldr=C)
+        self.free(h16)
+        return out
+
+    # -- timestep MLPs
+    def time_mlp(self, t_dev, freqs, dim, p0, p2, hidden, out_dim):
+        """timestep_embedding -> Linear -> SiLU -> Linear on a single t (unet.py:537-538; viewfusion...py:276-279)"""
+        te = self.t32(1, dim)
+        self.prog.append(self.ops.timestep_embedding(t_dev, freqs, te, dim))
+        e1 = self.t32(1, hidden)
+        self.prog.append(self.ops.gemv(te, self.W.lin(p0 + ".weight"), self.W.f32(p0 + ".bias"), e1, 1, hidden, dim,
+                                       silu_out=True))
+        emb = self.ops.empty((1, out_dim), torch.float32)
+        self.prog.append(self.ops.gemv(e1, self.W.lin(p2 + ".weight"), self.W.f32(p2 + ".bias"), emb, 1, out_dim, hidden))
+        self.free(te, e1)
+        return emb
+
+
+def timestep_freqs(dim, device, max_period=10000):
+    half = dim // 2
+    return torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half).to(device)
+
+
+# ------------------------------------------------------------------------------------------------ UNet
+class UNetSpec:
+    """Topology of mvdfusion.unet.UNetModel (unet.py:320-500) as a flat op list derived from its hyper-parameters."""
+
+    def __init__(self, model_channels, channel_mult, num_res_blocks, attention_resolutions, num_heads, image_size,
+                 in_channels, out_channels):
+        self.mc, self.mult, self.nres = model_channels, tuple(channel_mult), num_res_blocks
+        self.attn_res = tuple(attention_resolutions)
+        self.heads, self.image_size = num_heads, image_size
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.emb_dim = 4 * model_channels
+        self.input_blocks, self.middle, self.output_blocks = [], [], []
+        ch, ds = self.mc, 1
+        chans = [ch]
+        self.input_blocks.append([("stem", in_channels, ch)])
+        for level, m in enumerate(self.mult):
+            for _ in range(self.nres):
+                layers = [("res", ch, m * self.mc)]
+                ch = m * self.mc
+                if ds in self.attn_res:
+                    layers.append(("st", ch))
+                self.input_blocks.append(layers)
+                chans.append(ch)
+            if level != len(self.mult) - 1:
+                self.input_blocks.append([("down", ch)])
+                chans.append(ch)
+                ds *= 2
+        self.middle = [("res", ch, ch), ("st", ch), ("vaft", ch), ("res", ch, ch)]
+        for level, m in list(enumerate(self.mult))[::-1]:
+            for i in range(self.nres + 1):
+                ich = chans.pop()
+                layers = [("res", ch + ich, self.mc * m)]
+                ch = self.mc * m
+                if ds in self.attn_res:
+                    layers.append(("st", ch))
+                    layers.append(("vaft", ch))
+                if level and i == self.nres:
+                    layers.append(("up", ch))
+                    ds //= 2
+                self.output_blocks.append(layers)
+        self.final_ch = ch
+
+    def st_layers(self):
+        """(prefix, channels) of every SpatialTransformer in execution order."""
+        out = []
+        for name, blocks in (("input_blocks", self.input_blocks), ("output_blocks", self.output_blocks)):
+            if name == "output_blocks":
+                for j, l in enumerate(self.middle):
+                    if l[0] == "st":
+                        out.append((f"middle_block.{j}", l[1]))
+            for i, layers in enumerate(blocks):
+                for j, l in enumerate(layers):
+                    if l[0] == "st":
+                        out.append((f"{name}.{i}.{j}", l[1]))
+        return out
+
+
+def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c_in_pad=16):
+    """UNetModel.forward (unet.py:524-556).  x_in16: fp16 NHWC [n_img, S, S, c_in_pad]; clipvecs: dict prefix ->
+    [n_img, C] fp32; pyramid16: list of fp16 [n_img*H_l*H_l*D, 768].  Returns the head output fp32 [n_img*S*S, 8]."""
+    b.heads = spec.heads
+    emb = b.time_mlp(t_dev, freqs, spec.mc, "time_embed.0", "time_embed.2", spec.emb_dim, spec.emb_dim)
+    H = S
+    hs = []
+
+    def run_layers(h, prefix, layers, H):
+        for j, l in enumerate(layers):
+            p = f"{prefix}.{j}"
+            kind = l[0]
+            if kind == "stem":
+                new = b.conv3x3(h, p + ".weight", n_img, H, H, l[1], l[2], bias=b.W.f32(p + ".bias"), c_pad=c_in_pad)
+            elif kind == "res":
+                new = b.resblock(h, p, n_img, H, l[1], l[2], emb, spec.emb_dim)
+            elif kind == "st":
+                new = b.spatial_transformer(h, p, n_img, H, l[1], clipvecs[p])
+            elif kind == "vaft":
+                level = {spec.image_size: 0, spec.image_size // 2: 1, spec.image_size // 4: 2, spec.image_size // 8: 3}[H]
+                new = b.view_aligned_transformer(h, p, n_img, H, l[1], pyramid16[level], D)
+            elif kind == "down":
+                new = b.downsample(h, p, n_img, H, l[1])
+                H //= 2
+            elif kind == "up":
+                new = b.upsample(h, p, n_img, H, l[1])
+                H *= 2
+            else:
+                raise ValueError(kind)
+            if not any(h is s for s, _ in hs) and h is not x_in16:
+                b.free(h)
+            h = new
+        return h, H
+
+    h = x_in16
+    for i, layers in enumerate(spec.input_blocks):
+        h, H = run_layers(h, f"input_blocks.{i}", layers, H)
+        hs.append((h, layers))
+    h, H = run_layers(h, "middle_block", spec.middle, H)
+    for i, layers in enumerate(spec.output_blocks):
+        skip, _ = hs.pop()
+        c1, c2 = h.shape[-1], skip.shape[-1]
+        rows = n_img * H * H
+        cat = b.t32(rows, c1 + c2)
+        b.prog.append(b.ops.concat(h, skip, cat, rows, c1, c2))
+        b.free(h, skip)
+        h, H = run_layers(cat, f"output_blocks.{i}", layers, H)
+    a = b.groupnorm(h, "out.0", n_img, H * H, spec.final_ch, 1e-5, True)
+    b.free(h)
+    head = b.ops.empty((n_img * H * H, 8), torch.float32)
+    b.conv3x3(a, "out.2.weight", n_img, H, H, spec.final_ch, spec.out_channels, bias=b.W.f32("out.2.bias"), ldc=8, out=head)
+    b.free(a)
+    return head
+
+
+# ------------------------------------------------------------------------------------------------ GridAttn
+def emit_gridattn(b, *, noisy, input_latent, depth_override, depth_eps, scal, cams, mask, c_embed, n_views, S, D,
+                  q_first, q_count, num_layers, num_heads, depth_scale, depth_shift, frustum_out, harm_freqs, ndc_grid):
+    """GridAttn.forward + aggregate_features (mvdfusion/view_attn_efficient2.py:269-442) for query views
+    [q_first, q_first+q_count) against all n_views views.  c_embed: fp32 [1, 256] (t_embed[:1]).
+    frustum_out: fp16 [q_count*S*S*D, 768] (pyramid level 0 of the conditional images)."""
+    hw = S * S
+    V = n_views
+    P = q_count * hw * D
+    R = P * V
+    W = b.W
+    feat = b.t16((n_views + 1) * hw, Z_CH)
+    zdepth = b.t32(n_views * D * hw)
+    b.prog.append(b.ops.gridattn_prep(noisy, input_latent, depth_override, depth_eps, scal, W.f32("z_embedder.0.weight"),
+                                      W.f32("z_embedder.0.bias"), feat, zdepth, n_views, S, D, depth_scale, depth_shift))
+    tokens = b.t16(R, TOKEN_LD)
+    b.prog.append(b.ops.gridattn_tokens(feat, zdepth, cams, mask, harm_freqs, ndc_grid, tokens, n_views, S, D, q_first, q_count))
+    b.free(feat, zdepth)
+    x = b.t32(R, Z_CH)
+    b.gemm(tokens, W.lin("pre_layer_b.0.weight", k_pad=TOKEN_LD), x, R, Z_CH, TOKEN_LD, bias=W.f32("pre_layer_b.0.bias"),
+           act=ACT_GELU)
+    b.free(tokens)
+    hd = Z_CH // num_heads
+    for i in range(num_layers):
+        p = f"aggregation_transformer.layer_list.{i}"
+        mod = b.ops.empty((6 * Z_CH,), torch.float32)  # shift/scale/gate (msa), shift/scale/gate (mlp)
+        b.prog.append(b.ops.gemv(c_embed, W.lin(p + ".adaLN_modulation.1.weight"), W.f32(p + ".adaLN_modulation.1.bias"), mod,
+                                 1, 6 * Z_CH, Z_CH, ldy=6 * Z_CH, silu_in=True))
+        ch = [mod[j * Z_CH:(j + 1) * Z_CH] for j in range(6)]
+        a = b.t16(R, Z_CH)
+        b.prog.append(b.ops.ln_modulate(x, ch[0], ch[1], a, R, Z_CH, 1e-6))
+        qkv = b.t16(R, 3 * Z_CH)
+        b.gemm(a, W.lin(p + ".attn.qkv.weight"), qkv, R, 3 * Z_CH, Z_CH, bias=W.f32(p + ".attn.qkv.bias"))
+        b.prog.append(b.ops.view_attention(qkv, a, P, V, num_heads, hd))
+        b.free(qkv)
+        x2 = b.t32(R, Z_CH)
+        b.gemm(a, W.lin(p + ".attn.proj.weight"), x2, R, Z_CH, Z_CH, bias=W.f32(p + ".attn.proj.bias"), colscale=ch[2],
+               residual=x, ldr=Z_CH)
+        b.free(x)
+        b.prog.append(b.ops.ln_modulate(x2, ch[3], ch[4], a, R, Z_CH, 1e-6))
+        hid = W.raw(p + ".mlp.fc1.weight").shape[0]
+        f = b.t16(R, hid)
+        b.gemm(a, W.lin(p + ".mlp.fc1.weight"), f, R, hid, Z_CH, bias=W.f32(p + ".mlp.fc1.bias"), act=ACT_GELU)
+        b.free(a)
+        x = b.t32(R, Z_CH)
+        b.gemm(f, W.lin(p + ".mlp.fc2.weight"), x, R, Z_CH, hid, bias=W.f32(p + ".mlp.fc2.bias"), colscale=ch[5],
+               residual=x2, ldr=Z_CH)
+        b.free(f, x2)
+    pooled = b.t16(P, Z_CH)
+    b.prog.append(b.ops.view_pool(x, W.f32("aggregation_transformer.weight_layer.weight"),
+                                  W.f32("aggregation_transformer.weight_layer.bias"), pooled, P, V, Z_CH))
+    b.free(x)
+    out_dim = W.raw("final_layer_b.weight").shape[0]
+    b.gemm(pooled, W.lin("final_layer_b.weight"), frustum_out, P, out_dim, Z_CH, bias=W.f32("final_layer_b.bias"))
+    b.free(pooled)
+
+
+def emit_pyramid(b, pyramid16, n_cond, S, D, C=CTX_DIM):
+    """get_volume_feats_pyramid (unet.py:198-209): 'area' pooling of level 0 by 2, 4, 8 (conditional images only)."""
+    for l in range(1, len(pyramid16)):
+        b.prog.append(b.ops.frustum_pool(pyramid16[0], pyramid16[l], n_cond, S, D, C, 1 << l))

@@ -1,0 +1,281 @@
+"""mvdfusion/viewfusion_zero_depth_rgb.py of the reference: the ViewFusion facade (named `MVDFusion` in BASELINE.json).
+
+Owns GridAttn, the UNet wrapper, the DDPM tables, cc_projection and the time-embedding MLP under the reference's
+attribute / parameter names; `apply_model` and `sample` (through DDIMSampler) run the compiled step plan.  The frozen VAE
+and CLIP encoders sit before / after the hot path and are outside this package: when their reference
+implementations are not importable, `encode` / `decode` / `encode_clip` raise and `prepare_batch` expects pre-encoded
+inputs in the batch (`latents`, `clip_embed`).
+"""
+import torch
+import torch.nn as nn
+
+from ..config import instantiate_from_config, load_model_from_config
+from ..denoise import StepPlan
+from ..runtime import WeightCache, current_stream, get_ops
+from .cameras import PerspectiveCameras, relative_cameras
+from .embedder import timestep_embedding
+from .sampler import DDIMSampler
+from .unet import UNetWrapper
+
+
+def normalize(x):
+    return torch.clip(x * 2 - 1.0, -1.0, 1.0)
+
+
+def unnormalize(x):
+    return torch.clip((x + 1.0) / 2.0, 0.0, 1.0)
+
+
+class ViewFusion(nn.Module):
+    """mvdfusion/viewfusion_zero_depth_rgb.py:19-417"""
+
+    def __init__(self, view_attn_config, unet_config, ddpm_config, vae_config=None, unet_path="", vae_path="", clip_path="",
+                 unet_cc_path="", z_scale_factor=0.18215, vae_max_batch=8, objective="noise", loss_type="l2",
+                 embed_camera_pose=True, finetune_projection=False, finetune_unet=False, finetune_cross_attn=True,
+                 finetune_view_attn=True, feed_prev_depth=False, drop_conditions=False, ddim_num_steps=50, ddim_eta=1.0,
+                 latent_size=32, **kwargs):
+        super().__init__()
+        self.finetune_projection = finetune_projection
+        self.finetune_unet = finetune_unet
+        self.z_scale_factor = z_scale_factor
+        self.vae_max_batch = vae_max_batch
+        self.objective = objective
+        self.loss_type = loss_type
+        self.embed_camera_pose = embed_camera_pose
+        self.finetune_cross_attn = finetune_cross_attn
+        self.finetune_view_attn = finetune_view_attn
+        self.unet_path = unet_path
+        self.unet_cc_path = unet_cc_path
+        self.feed_prev_depth = feed_prev_depth
+        self.drop_conditions = drop_conditions
+        if not embed_camera_pose:
+            raise NotImplementedError("hot path: camera-pose embedding (796-d clip_v_embed), as in every reference config")
+
+        self.view_attn = instantiate_from_config(view_attn_config)
+        self.unet_model = UNetWrapper(unet_config, unet_path=unet_path or None, drop_conditions=drop_conditions,
+                                      drop_scheme="default", finetune_unet=finetune_unet,
+                                      finetune_cross_attn=finetune_cross_attn, finetune_view_attn=finetune_view_attn,
+                                      use_zero_123=True, remove_keys=["input_blocks.0.0.weight", "out.2.weight", "out.2.bias"])
+        self.scheduler = instantiate_from_config(ddpm_config)
+        self.vae = load_model_from_config(vae_config, vae_path or None, replace_key=["first_stage_model.", ""]) if vae_config else None
+        self.clip_image_encoder = None  # FrozenCLIPImageEmbedder: outside the hot path, weights not shipped
+        self.cc_projection = nn.Sequential(nn.Linear(768 + 14 * 2, 768), nn.SiLU(True), nn.Linear(768, 768), nn.SiLU(True),
+                                           nn.Linear(768, 768))
+        nn.init.eye_(list(self.cc_projection.parameters())[0][:768, :768])
+        nn.init.zeros_(list(self.cc_projection.parameters())[1])
+        self.cc_projection.requires_grad_(finetune_projection)
+        self.time_embed_dim = 256
+        self.time_embed = nn.Sequential(nn.Linear(256, 256), nn.SiLU(True), nn.Linear(256, 256))
+        self.register_buffer("_device", torch.tensor([0.0]), persistent=False)
+        if loss_type != "l2":
+            raise NotImplementedError
+        self.loss_fn = torch.nn.functional.mse_loss
+        self.ddim = DDIMSampler(self, ddim_num_steps=ddim_num_steps, ddim_discretize="uniform", ddim_eta=ddim_eta,
+                                latent_size=latent_size, z_dim=4, feed_prev_depth=feed_prev_depth)
+        assert self.finetune_view_attn is True, "must finetune new view attention layers"
+        self.view_group = None      # (process group, rank, world) when the views of a scene are sharded across GPUs
+        self._cache = WeightCache()
+
+    # ------------------------------------------------------------------ view sharding
+    def shard_views(self, group=None):
+        """Shard the N views of every scene over the ranks of `group` (default: the world group): each rank runs GridAttn
+        for its own query views against all views, the UNet on its own views, and the ranks exchange the updated
+        5-channel latents with ONE all-gather per denoising step."""
+        import torch.distributed as dist
+        self.view_group = (group, dist.get_rank(group), dist.get_world_size(group))
+
+    def gather_views(self, plan):
+        import torch.distributed as dist
+        group = self.view_group[0]
+        dist.all_gather_into_tensor(plan.x.view(-1), plan.x_local.reshape(-1), group=group)
+
+    # ------------------------------------------------------------------ plans
+    def step_plan(self, n_views, S, D, use_cfg, use_depth_override=False, use_cond_scale=False):
+        ops = get_ops(self._device.device)
+        sd = self._cache.get(self, ops)
+        q_first, q_count = 0, n_views
+        if self.view_group is not None:
+            _, rank, world = self.view_group
+            if n_views % world:
+                raise ValueError(f"{n_views} views do not shard evenly over {world} ranks")
+            q_count = n_views // world
+            q_first = rank * q_count
+        key = (n_views, S, D, use_cfg, q_first, q_count, use_depth_override, use_cond_scale)
+        if key not in self._cache.plans:
+            va = self.view_attn
+            self._cache.plans[key] = StepPlan(ops, sd, self.unet_model.unet_model.spec, n_views=n_views, S=S, D=D, use_cfg=use_cfg,
+                                              q_first=q_first, q_count=q_count, num_layers=va.num_layers,
+                                              grid_heads=va.num_heads, depth_scale=va.depth_scale, depth_shift=va.depth_shift,
+                                              use_depth_override=use_depth_override, use_cond_scale=use_cond_scale)
+        return self._cache.plans[key]
+
+    @staticmethod
+    def bind_scene(plan, batch_cameras, input_latents, input_cameras, clip_v_embed, stream):
+        bc, ic = batch_cameras, input_cameras
+        plan.set_scene(bc.R, bc.T, bc.focal_length, bc.principal_point, ic.R, ic.T, ic.focal_length, ic.principal_point,
+                       input_latents, clip_v_embed, stream)
+
+    # ------------------------------------------------------------------ frozen encoders (outside the hot path)
+    def _need(self, what, obj):
+        if obj is None:
+            raise RuntimeError(f"{what} is outside the mvdfusion_b200 hot path and its reference implementation is not importable "
+                               "here; pass pre-encoded inputs instead (batch['latents'], batch['clip_embed'])")
+        return obj
+
+    @torch.no_grad()
+    def encode_clip(self, x):
+        return self._need("CLIP image encoder", self.clip_image_encoder).encode(x)
+
+    @torch.no_grad()
+    def encode(self, x):
+        return self._need("VAE", self.vae).encode(normalize(x)).mode() * self.z_scale_factor
+
+    @torch.no_grad()
+    def decode(self, z):
+        return unnormalize(self._need("VAE", self.vae).decode(z * 1 / self.z_scale_factor)).clip(0.0, 1.0)
+
+    # ------------------------------------------------------------------ batch preparation (the step before the path)
+    def prepare_batch(self, batch, trainer_config, generator=None):
+        """mvdfusion/viewfusion_zero_depth_rgb.py:165-273.  View selection, relative cameras (R' = R_q^T R, T' = T) and the
+        796-d [clip | R_in T_in f_in | R_b T_b f_b] embedding follow the reference; image -> latent / CLIP encoding uses
+        the reference's frozen encoders when present, else `batch['latents']` (S_v,4,h,w; already x0.18215) and
+        `batch['clip_embed']` (S_v,1,768)."""
+        key = "images" if "images" in batch else "latents"
+        dev = batch[key].device
+        B = batch[key].shape[0]
+        n_in, n_tr = trainer_config["input_batch_size"], trainer_config["train_batch_size"]
+        if trainer_config["random_views"]:
+            rand = torch.randperm(B, generator=generator) if generator is not None else torch.randperm(B)
+        else:
+            rand = torch.linspace(0, B - 1, n_in + n_tr).long()
+        input_idx, batch_idx = rand[:n_in], rand[n_in:n_tr + n_in]
+        if "latents" in batch:
+            input_latents, batch_latents = batch["latents"][input_idx].float(), batch["latents"][batch_idx].float()
+        else:
+            input_latents, batch_latents = self.encode(batch["images"][input_idx]), self.encode(batch["images"][batch_idx])
+        h, w = input_latents.shape[-2:]
+        input_latents = torch.cat((input_latents, torch.zeros((n_in, 1, h, w), device=dev)), dim=1)  # input depth zeroed (:215)
+        if "depths" in batch:
+            bd = torch.nn.functional.interpolate(normalize(batch["depths"][batch_idx]).to(dev), scale_factor=0.125, mode="area")
+        else:
+            bd = torch.zeros((batch_latents.shape[0], 1, h, w), device=dev)
+        batch_latents = torch.cat((batch_latents, bd), dim=1)
+        cams = PerspectiveCameras(R=batch["R"], T=batch["T"], focal_length=batch["f"], principal_point=batch["c"], device=dev)
+        cams = relative_cameras(cams, input_idx)
+        input_cameras, batch_cameras = cams[input_idx], cams[batch_idx]
+        if "clip_embed" in batch:
+            clip_embed = batch["clip_embed"][input_idx].float()
+        else:
+            clip_embed = self.encode_clip(batch["images"][input_idx])
+        clip_embed = clip_embed.reshape(1, 1, -1).expand(n_tr, -1, -1)
+        nb = len(batch_latents)
+        in_e = torch.cat((input_cameras.R.reshape(-1, 1, 9), input_cameras.T.reshape(-1, 1, 3),
+                          input_cameras.focal_length.reshape(-1, 1, 2)), dim=-1).expand(nb, -1, -1)
+        b_e = torch.cat((batch_cameras.R.reshape(-1, 1, 9), batch_cameras.T.reshape(-1, 1, 3),
+                         batch_cameras.focal_length.reshape(-1, 1, 2)), dim=-1)
+        clip_v_embed = torch.cat((clip_embed, in_e, b_e), dim=-1)
+        return batch_latents, batch_cameras, input_latents, input_cameras, clip_v_embed
+
+    def embed_time(self, t):
+        """mvdfusion/viewfusion_zero_depth_rgb.py:276-279 as a standalone call (host-side helper: the loop computes it in-program)."""
+        ops = get_ops(self._device.device)
+        W = self._cache.pack(self, ops)
+        te = timestep_embedding(t, self.time_embed_dim).float().contiguous()
+        n = te.shape[0]
+        h = ops.empty((n, 256), torch.float32)
+        y = ops.empty((n, 256), torch.float32)
+        stream = current_stream(self._device.device)
+        ops.gemv(te, W.lin("time_embed.0.weight"), W.f32("time_embed.0.bias"), h, n, 256, 256, silu_out=True)(stream)
+        ops.gemv(h, W.lin("time_embed.2.weight"), W.f32("time_embed.2.bias"), y, n, 256, 256)(stream)
+        return y
+
+    # ------------------------------------------------------------------ the hot path
+    def apply_model(self, noisy_latents, batch_cameras, input_latents, input_cameras, clip_v_embed, t, prev_depth=None,
+                    cfg_scale=1.0, depth_eps=None, drop_random=None):
+        """mvdfusion/viewfusion_zero_depth_rgb.py:282-345 -> predicted noise (B,5,S,S).
+        depth_eps (B,D,S,S) / drop_random (B,) optionally inject the draws of GridAttn's depth jitter (:431 of
+        view_attn_efficient2.py) and of the condition-drop scheme (unet.py:120)."""
+        B, _, S, _ = noisy_latents.shape
+        dev = noisy_latents.device
+        D = self.view_attn.n_pts_per_ray
+        use_cfg = cfg_scale != 1.0
+        # reference quirk: the cfg == 1.0 branch calls the UNet wrapper with is_train=True (:324-331)
+        drop = (not use_cfg) and self.drop_conditions
+        plan = self.step_plan(B, S, D, use_cfg, use_depth_override=prev_depth is not None, use_cond_scale=drop)
+        stream = current_stream(dev)
+        q0, q = plan.q_first, plan.q
+        if depth_eps is None:
+            depth_eps = torch.randn(B, D, S, S, device=dev)
+        plan.depth_eps.copy_(depth_eps.reshape(B, D, S * S))
+        if prev_depth is not None:
+            plan.depth_override.copy_(prev_depth.reshape(B, S * S))
+        plan.x.copy_(noisy_latents.reshape(B, 5, S * S))
+        row = self.ddim.step_row(0, cfg_scale)
+        t0 = int(t.reshape(-1)[0])
+        sch = self.scheduler
+        row[0] = float(t0)
+        row[1] = float(sch.sqrt_alphas_cumprod[t0])
+        row[2] = float(sch.sqrt_one_minus_alphas_cumprod[t0] / sch.sqrt_alphas_cumprod[t0] / 10.0)
+        plan.set_step_constants(row)
+        if not drop:
+            self.bind_scene(plan, batch_cameras, input_latents, input_cameras, clip_v_embed, stream)
+            plan.run_eps(stream)
+        else:
+            r = drop_random if drop_random is not None else torch.rand(B, dtype=torch.float32, device=dev)
+            r = r.to(dev)[q0:q0 + q]
+            keep_clip = 1.0 - (((r > 0.15) & (r <= 0.2)) | (r <= 0.05)).float()
+            keep_vol = 1.0 - (((r > 0.1) & (r <= 0.15)) | (r <= 0.05)).float()
+            plan.cond_scale.copy_(1.0 - (((r > 0.05) & (r <= 0.1)) | (r <= 0.05)).float())
+            bc, ic = batch_cameras, input_cameras
+            scene = (bc.R, bc.T, bc.focal_length, bc.principal_point, ic.R, ic.T, ic.focal_length, ic.principal_point,
+                     input_latents, clip_v_embed)
+            plan.run_eps_with_drop(scene, keep_clip, keep_vol, stream)
+        return plan.eps_out.reshape(q, 5, S, S).clone()
+
+    def sample(self, batch, trainer_config, cfg_scale, return_input=False, depth=False, verbose=True):
+        """mvdfusion/viewfusion_zero_depth_rgb.py:348-359"""
+        batch_latents, batch_cameras, input_latents, input_cameras, clip_v_embed = self.prepare_batch(batch, trainer_config)
+        if return_input:
+            x, inter = self.ddim.sample(batch_cameras, input_latents, input_cameras, clip_v_embed, unconditional_scale=cfg_scale,
+                                        depth=depth, return_intermediates=True, verbose=verbose)
+            return x, batch_latents, input_latents, batch_cameras, inter
+        return self.ddim.sample(batch_cameras, input_latents, input_cameras, clip_v_embed, unconditional_scale=cfg_scale,
+                                depth=depth, verbose=verbose)
+
+    def p_losses(self, batch, trainer_config):
+        """mvdfusion/viewfusion_zero_depth_rgb.py:362-392 — forward value of the training loss (no autograd through the
+        kernels yet: SURVEY.md §7 step 8 / BASELINE config 4 is a later row)."""
+        batch_latents, batch_cameras, input_latents, input_cameras, clip_v_embed = self.prepare_batch(batch, trainer_config)
+        B = batch_latents.shape[0]
+        t = self.scheduler.sample_random_times(B, share_t=True, device=batch_latents.device)
+        noisy, noise = self.scheduler.q_sample(batch_latents.clone(), t=t)
+        kw = dict(prev_depth=input_latents[:, 4:].clone()) if self.feed_prev_depth else {}
+        pred = self.apply_model(noisy, batch_cameras, input_latents, input_cameras, clip_v_embed, t, **kw)
+        target = noise if self.objective == "noise" else batch_latents
+        return self.loss_fn(target, pred).mean()
+
+    def forward(self, batch, trainer_config):
+        return self.p_losses(batch, trainer_config)
+
+    def configure_optimizers(self, lr=None, verbose=False):
+        """mvdfusion/viewfusion_zero_depth_rgb.py:399-417"""
+        lr = self.learning_rate if lr is None else lr
+        paras = []
+        if self.finetune_projection:
+            paras.append({"params": self.cc_projection.parameters(), "lr": lr})
+        paras.append({"params": self.unet_model.get_trainable_parameters(), "lr": lr})
+        paras.append({"params": self.time_embed.parameters(), "lr": lr})
+        paras.append({"params": self.view_attn.parameters(), "lr": lr})
+        return torch.optim.AdamW(paras, lr=lr)
+
+    def _print_parameter_count(self):
+        va = sum(p.numel() for p in self.view_attn.parameters())
+        un = sum(p.numel() for p in self.unet_model.get_trainable_parameters())
+        full = sum(p.numel() for p in self.unet_model.parameters())
+        tp = sum(p.numel() for p in self.time_embed.parameters())
+        pp = sum(p.numel() for p in self.cc_projection.parameters()) if self.finetune_projection else 0
+        print(f"view_attn params: {va * 1e-6:.2f}M\nunet params: {un * 1e-6:.2f}M\ntotal params: {(va + un + tp + pp) * 1e-6:.2f}M")
+        print(f"unet full params: {full * 1e-6:.2f}M\ntotal full params: {(va + full + tp + pp) * 1e-6:.2f}M")
+
+
+MVDFusion = ViewFusion  # the name BASELINE.json uses for this class

@@ -1,0 +1,218 @@
+"""Tensor-level view of the C ABI: every method validates its torch tensors, freezes the raw pointers and sizes
+into a bound call and returns it; `call(stream)` launches the kernel(s) asynchronously on that CUDA stream.
+
+A step of the denoising loop is a fixed list of such bound calls (engine.Program), replayed either directly
+or from a captured CUDA graph.  There is exactly one implementation of this interface in the product — the
+sm_100a library — and it refuses anything that is not a CUDA tensor.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+A_ROWMAJOR, A_CONV3X3 = 0, 1
+ACT_NONE, ACT_GELU, ACT_SILU, ACT_GEGLU = 0, 1, 2, 3
+OUT_F32, OUT_F16, OUT_QKV_HEADS = 0, 1, 2
+
+
+class MvdError(RuntimeError):
+    pass
+
+
+def _ptr(t, dtype=None):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise MvdError("mvdfusion_b200 kernels take CUDA tensors only (no CPU fallback exists)")
+    if dtype is not None and t.dtype != dtype:
+        raise MvdError(f"expected {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+class BoundCall:
+    """One C-ABI call with frozen arguments.  Keeps the tensors alive that its pointers refer to."""
+
+    __slots__ = ("fn", "args", "keep", "name")
+
+    def __init__(self, name, fn, args, keep):
+        self.name, self.fn, self.args, self.keep = name, fn, args, keep
+
+    def __call__(self, stream):
+        rc = self.fn(*self.args, stream)
+        if rc != 0:
+            raise MvdError(f"{self.name} failed (rc={rc}): {_lib.last_error()}")
+
+
+class NativeOps:
+    """The sm_100a kernels of libmvd_b200.so (include/mvd_b200.h)."""
+
+    def __init__(self, device):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise MvdError("NativeOps needs a CUDA device; mvdfusion_b200 has no CPU path")
+
+    # ------------------------------------------------------------------ helpers
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def geglu_permutation(self, inner, tile_n):
+        perm = (ctypes.c_int32 * (2 * inner))()
+        rc = self.lib.mvd_geglu_row_permutation(inner, tile_n, ctypes.cast(perm, ctypes.c_void_p))
+        if rc != 0:
+            raise MvdError(_lib.last_error())
+        return torch.tensor(list(perm), dtype=torch.long)
+
+    def _bind(self, name, args, keep):
+        return BoundCall(name, getattr(self.lib, name), tuple(args), keep)
+
+    # ------------------------------------------------------------------ GEMM / conv
+    def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
+             colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0):
+        g = _lib.GemmArgs()
+        g.M, g.N, g.K = M, N, K
+        g.A = _ptr(A, torch.float16)
+        g.Wt = _ptr(Wt, torch.float16)
+        g.ldw = ldw if ldw is not None else Wt.shape[-1]
+        if conv is not None:
+            g.a_mode = A_CONV3X3
+            g.n_img, g.H, g.W, g.C = conv
+        else:
+            g.a_mode = A_ROWMAJOR
+            g.lda = lda if lda is not None else A.shape[-1]
+        g.bias = _ptr(bias, torch.float32)
+        g.rowbias = _ptr(rowbias, torch.float32)
+        g.rows_per_group = rows_per_group
+        g.colscale = _ptr(colscale, torch.float32)
+        g.residual = _ptr(residual, torch.float32)
+        g.ldr = ldr
+        g.act = act
+        g.out = _ptr(out)
+        if qkv is not None:
+            g.out_mode = OUT_QKV_HEADS
+            g.out_k = _ptr(qkv["out_k"], torch.float16)
+            g.out_vt = _ptr(qkv["out_vt"], torch.float16)
+            g.heads, g.dhead, g.dpad, g.seq = qkv["heads"], qkv["dhead"], qkv["dpad"], qkv["seq"]
+        else:
+            g.out_mode = OUT_F16 if out.dtype == torch.float16 else OUT_F32
+            g.ldc = ldc if ldc is not None else out.shape[-1]
+        g.split_k = split_k
+        g.tile_n = tile_n
+        keep = (g, A, Wt, out, bias, rowbias, colscale, residual, qkv)
+        return self._bind("mvd_gemm_f16", (ctypes.byref(g),), keep)
+
+    def attn_self(self, q, k, vt, out, n_img, heads, seq, dhead, dpad, ldo):
+        return self._bind("mvd_attn_self_f16", (_ptr(q, torch.float16), _ptr(k, torch.float16), _ptr(vt, torch.float16),
+                                                _ptr(out, torch.float16), n_img, heads, seq, dhead, dpad, ldo),
+                          (q, k, vt, out))
+
+    # ------------------------------------------------------------------ normalisation
+    def groupnorm(self, x, gamma, beta, y, stats_ws, n_img, hw, C, eps, silu):
+        return self._bind("mvd_groupnorm_f32_f16", (_ptr(x, torch.float32), _ptr(gamma, torch.float32),
+                                                    _ptr(beta, torch.float32), _ptr(y, torch.float16),
+                                                    _ptr(stats_ws, torch.float64), n_img, hw, C, eps, int(silu)),
+                          (x, gamma, beta, y, stats_ws))
+
+    def layernorm(self, x, gamma, beta, y, rows, C, eps):
+        return self._bind("mvd_layernorm_f32_f16", (_ptr(x, torch.float32), _ptr(gamma, torch.float32),
+                                                    _ptr(beta, torch.float32), _ptr(y, torch.float16), rows, C, eps),
+                          (x, gamma, beta, y))
+
+    def ln_modulate(self, x, shift, scale, y, rows, C, eps):
+        return self._bind("mvd_ln_modulate_f32_f16", (_ptr(x, torch.float32), _ptr(shift, torch.float32),
+                                                      _ptr(scale, torch.float32), _ptr(y, torch.float16), rows, C, eps),
+                          (x, shift, scale, y))
+
+    # ------------------------------------------------------------------ data movement / elementwise
+    def cast(self, x, y, n):
+        return self._bind("mvd_cast_f32_f16", (_ptr(x, torch.float32), _ptr(y, torch.float16), n), (x, y))
+
+    def concat(self, a, b, out, rows, C1, C2):
+        return self._bind("mvd_concat_f32", (_ptr(a, torch.float32), _ptr(b, torch.float32), _ptr(out, torch.float32),
+                                             rows, C1, C2), (a, b, out))
+
+    def upsample2x(self, x, y, n_img, H, W, C):
+        return self._bind("mvd_upsample2x_f32_f16", (_ptr(x, torch.float32), _ptr(y, torch.float16), n_img, H, W, C),
+                          (x, y))
+
+    def im2col_s2(self, x, y, n_img, H, W, C):
+        return self._bind("mvd_im2col_s2_f32_f16", (_ptr(x, torch.float32), _ptr(y, torch.float16), n_img, H, W, C),
+                          (x, y))
+
+    def gemv(self, x, W, bias, y, M, N, K, *, ldx=None, ldw=None, ldy=None, silu_in=False, silu_out=False):
+        return self._bind("mvd_gemv_f16", (_ptr(x, torch.float32), ldx if ldx is not None else x.shape[-1],
+                                           _ptr(W, torch.float16), ldw if ldw is not None else W.shape[-1],
+                                           _ptr(bias, torch.float32), _ptr(y, torch.float32),
+                                           ldy if ldy is not None else y.shape[-1], M, N, K, int(silu_in),
+                                           int(silu_out)), (x, W, bias, y))
+
+    def timestep_embedding(self, t_dev, freqs, out, dim):
+        return self._bind("mvd_timestep_embedding", (_ptr(t_dev, torch.float32), _ptr(freqs, torch.float32),
+                                                     _ptr(out, torch.float32), dim), (t_dev, freqs, out))
+
+    def unet_input(self, noisy, cond, cond_batched, cond_scale, out, n_views, n_img, hw, Cpad):
+        return self._bind("mvd_unet_input_f16", (_ptr(noisy, torch.float32), _ptr(cond, torch.float32),
+                                                 int(cond_batched), _ptr(cond_scale, torch.float32),
+                                                 _ptr(out, torch.float16), n_views, n_img, hw, Cpad),
+                          (noisy, cond, cond_scale, out))
+
+    def cfg_ddim(self, head, ld, two_branch, coef, xt, noise, eps_out, x_prev, x0_out, n_views, hw):
+        return self._bind("mvd_cfg_ddim", (_ptr(head, torch.float32), ld, int(two_branch), _ptr(coef, torch.float32),
+                                           _ptr(xt, torch.float32), _ptr(noise, torch.float32),
+                                           _ptr(eps_out, torch.float32), _ptr(x_prev, torch.float32),
+                                           _ptr(x0_out, torch.float32), n_views, hw),
+                          (head, coef, xt, noise, eps_out, x_prev, x0_out))
+
+    def nchw_to_rows(self, x, y, n_img, C, hw):
+        return self._bind("mvd_nchw_to_rows_f32", (_ptr(x, torch.float32), _ptr(y, torch.float32), n_img, C, hw), (x, y))
+
+    def rows_to_nchw(self, x, y, n_img, C, ld, hw):
+        return self._bind("mvd_rows_to_nchw_f32", (_ptr(x, torch.float32), _ptr(y, torch.float32), n_img, C, ld, hw),
+                          (x, y))
+
+    def nchw_to_nhwc16(self, x, y, n_img, C, hw, Cpad):
+        return self._bind("mvd_nchw_to_nhwc_f16", (_ptr(x, torch.float32), _ptr(y, torch.float16), n_img, C, hw, Cpad), (x, y))
+
+    def gather_rows(self, table, row_len, idx_dev, out):
+        return self._bind("mvd_gather_rows_f32", (_ptr(table, torch.float32), row_len, _ptr(idx_dev, torch.int32),
+                                                  _ptr(out, torch.float32)), (table, idx_dev, out))
+
+    def increment(self, counter, delta):
+        return self._bind("mvd_increment_i32", (_ptr(counter, torch.int32), delta), (counter,))
+
+    # ------------------------------------------------------------------ GridAttn
+    def gridattn_prep(self, noisy, input_latent, depth_override, depth_eps, scal, Wz, bz, feat, zdepth, n_views, S, D,
+                      depth_scale, depth_shift):
+        return self._bind("mvd_gridattn_prep", (_ptr(noisy, torch.float32), _ptr(input_latent, torch.float32),
+                                                _ptr(depth_override, torch.float32), _ptr(depth_eps, torch.float32),
+                                                _ptr(scal, torch.float32), _ptr(Wz, torch.float32),
+                                                _ptr(bz, torch.float32), _ptr(feat, torch.float16),
+                                                _ptr(zdepth, torch.float32), n_views, S, D, depth_scale, depth_shift),
+                          (noisy, input_latent, depth_override, depth_eps, scal, Wz, bz, feat, zdepth))
+
+    def gridattn_tokens(self, feat, zdepth, cams, mask, freqs, ndc_grid, tokens, n_views, S, D, q_first, q_count):
+        return self._bind("mvd_gridattn_tokens", (_ptr(feat, torch.float16), _ptr(zdepth, torch.float32),
+                                                  _ptr(cams, torch.float32), _ptr(mask, torch.float32),
+                                                  _ptr(freqs, torch.float32), _ptr(ndc_grid, torch.float32),
+                                                  _ptr(tokens, torch.float16), n_views, S, D, q_first, q_count),
+                          (feat, zdepth, cams, mask, freqs, ndc_grid, tokens))
+
+    def view_attention(self, qkv, out, P, V, heads, hd):
+        return self._bind("mvd_view_attention_f16", (_ptr(qkv, torch.float16), _ptr(out, torch.float16), P, V, heads, hd),
+                          (qkv, out))
+
+    def view_pool(self, x, w, b, out, P, V, C):
+        return self._bind("mvd_view_pool_f16", (_ptr(x, torch.float32), _ptr(w, torch.float32), _ptr(b, torch.float32),
+                                                _ptr(out, torch.float16), P, V, C), (x, w, b, out))
+
+    def frustum_pool(self, inp, out, n_img, S, D, C, factor):
+        return self._bind("mvd_frustum_pool_f16", (_ptr(inp, torch.float16), _ptr(out, torch.float16), n_img, S, D, C,
+                                                   factor), (inp, out))
+
+    def pixel_cross_attn(self, q, kv, out, M, D, heads, dhead):
+        return self._bind("mvd_pixel_cross_attn_f16", (_ptr(q, torch.float16), _ptr(kv, torch.float16),
+                                                       _ptr(out, torch.float16), M, D, heads, dhead), (q, kv, out))

@@ -1,0 +1,65 @@
+"""Per-process runtime glue: one NativeOps handle per CUDA device, weight-pack caches keyed on parameter versions.
+
+There is no CPU execution path in the product: asking for ops on a non-CUDA device raises.  (`_OPS_OVERRIDE`
+exists so that tests/ can substitute a recording / emulating double for the C library to check the host-side
+program logic on a GPU-less box; nothing in the package sets it.)
+"""
+import torch
+
+from .engine import PackedWeights
+from .ops import MvdError, NativeOps
+
+_OPS = {}
+_OPS_OVERRIDE = None
+
+
+def get_ops(device):
+    device = torch.device(device)
+    if _OPS_OVERRIDE is not None:
+        return _OPS_OVERRIDE(device)
+    if device.type != "cuda":
+        raise MvdError(
+            f"mvdfusion_b200 runs on CUDA (sm_100a) only; got tensors on '{device}'. There is no CPU fallback — "
+            "move the module and its inputs to a B200."
+        )
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _OPS:
+        _OPS[key] = NativeOps(torch.device("cuda", key))
+    return _OPS[key]
+
+
+def current_stream(device):
+    if torch.device(device).type == "cuda":
+        return torch.cuda.current_stream(device).cuda_stream
+    return None
+
+
+def params_signature(module):
+    """Changes whenever a parameter / buffer is reassigned, moved or modified in place (load_state_dict, .cuda(), optimizer step)."""
+    sig = []
+    for t in list(module.parameters()) + list(module.buffers()):
+        sig.append((t.data_ptr(), t._version))
+    return hash(tuple(sig))
+
+
+class WeightCache:
+    """PackedWeights of a module, rebuilt when the module's parameters change (packed weights are a derived cache)."""
+
+    def __init__(self):
+        self.sig = None
+        self.state = None
+
+    def get(self, module, ops):
+        sig = (params_signature(module), id(ops))
+        if sig != self.sig:
+            self.state = {k: v.detach() for k, v in module.state_dict().items()}
+            self.sig = sig
+            self.packs = {}
+            self.plans = {}
+        return self.state
+
+    def pack(self, module, ops, prefix=""):
+        sd = self.get(module, ops)
+        if prefix not in self.packs:
+            self.packs[prefix] = PackedWeights(sd, ops, prefix)
+        return self.packs[prefix]

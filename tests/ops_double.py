@@ -1,0 +1,338 @@
+"""TEST DOUBLE for mvdfusion_b200.ops.NativeOps — test infrastructure, never imported by the product.
+
+It emulates, with plain torch on CPU tensors, the documented semantics of every C-ABI entry point
+(include/mvd_b200.h), including the fp16 rounding of fp16 outputs.  Purpose: on a box without a GPU, run the
+product's host-side logic (engine emitters, weight packing, buffer arena, program order, step tables, view sharding)
+against the oracle, so that the only thing left to verify on the B200 is the kernels themselves.
+"""
+import torch
+import torch.nn.functional as F
+
+from mvdfusion_b200.ops import ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_SILU
+
+
+def geglu_permutation(inner, tile_n):
+    """mirror of mvd_geglu_row_permutation (csrc/gemm.cu); tests/test_lib_host.py checks it against the library"""
+    half = tile_n // 2
+    perm = []
+    for r in range(2 * inner):
+        tile, w = divmod(r, tile_n)
+        perm.append(tile * half + w if w < half else inner + tile * half + (w - half))
+    return torch.tensor(perm, dtype=torch.long)
+
+
+class TorchOpsDouble:
+    def __init__(self, device="cpu"):
+        self.device = torch.device(device)
+        self.calls = 0
+
+    def empty(self, shape, dtype):
+        # poison (NaN for floats, 0xFF bytes for the arena's raw buffers): catches reads of unwritten memory
+        return torch.full(shape, float("nan") if dtype.is_floating_point else 255, dtype=dtype)
+
+    def zeros(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype)
+
+    def geglu_permutation(self, inner, tile_n):
+        return geglu_permutation(inner, tile_n)
+
+    def _call(self, fn):
+        def run(stream):
+            self.calls += 1
+            fn()
+        return run
+
+    # ------------------------------------------------------------------ GEMM / conv
+    def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
+             colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0):
+        assert A.dtype == torch.float16 and Wt.dtype == torch.float16
+        ldw_ = ldw if ldw is not None else Wt.shape[-1]
+
+        def fn():
+            W = Wt.reshape(-1)[: N * ldw_].reshape(N, ldw_)[:, :K].float()
+            if conv is not None:
+                n_img, H, Wd, C = conv
+                assert K == 9 * C and M == n_img * H * Wd
+                x = A.reshape(-1)[: M * C].reshape(n_img, H, Wd, C).float()
+                xp = F.pad(x, (0, 0, 1, 1, 1, 1))
+                cols = [xp[:, ky:ky + H, kx:kx + Wd, :] for ky in range(3) for kx in range(3)]
+                a = torch.cat(cols, dim=-1).reshape(M, K)
+            else:
+                lda_ = lda if lda is not None else A.shape[-1]
+                a = A.reshape(-1)[: M * lda_].reshape(M, lda_)[:, :K].float()
+            acc = a @ W.t()
+            if bias is not None:
+                acc = acc + bias.reshape(-1)[:N]
+            if rowbias is not None:
+                groups = (M + rows_per_group - 1) // rows_per_group
+                rb = rowbias.reshape(-1)[: groups * N].reshape(groups, N)
+                acc = acc + rb.repeat_interleave(rows_per_group, dim=0)[:M]
+            if act == ACT_GELU:
+                acc = F.gelu(acc)
+            elif act == ACT_SILU:
+                acc = F.silu(acc)
+            elif act == ACT_GEGLU:
+                bn = tile_n if tile_n else (64 if N <= 64 else 128)
+                t = acc.reshape(M, N // bn, bn)
+                acc = (t[..., : bn // 2] * F.gelu(t[..., bn // 2:])).reshape(M, N // 2)
+            if colscale is not None:
+                assert act != ACT_GEGLU
+                acc = acc * colscale.reshape(-1)[:N]
+            if residual is not None:
+                acc = acc + residual.reshape(-1)[: M * ldr].reshape(M, ldr)[:, : acc.shape[1]]
+            if qkv is not None:
+                heads, d, dpad, seq = qkv["heads"], qkv["dhead"], qkv["dpad"], qkv["seq"]
+                n_img = M // seq
+                t = acc.reshape(n_img, seq, 3, heads, d).permute(2, 0, 3, 1, 4)  # [3, img, h, seq, d]
+                q = out.reshape(-1)[: n_img * heads * seq * dpad].reshape(n_img, heads, seq, dpad)
+                k = qkv["out_k"].reshape(-1)[: n_img * heads * seq * dpad].reshape(n_img, heads, seq, dpad)
+                vt = qkv["out_vt"].reshape(-1)[: n_img * heads * seq * dpad].reshape(n_img, heads, dpad, seq)
+                q[..., :d] = t[0].half()
+                k[..., :d] = t[1].half()
+                vt[:, :, :d, :] = t[2].transpose(-1, -2).half()
+                return
+            ldc_ = ldc if ldc is not None else out.shape[-1]
+            o = out.reshape(-1)[: M * ldc_].reshape(M, ldc_)
+            o[:, : acc.shape[1]] = acc.to(out.dtype)
+        return self._call(fn)
+
+    def attn_self(self, q, k, vt, out, n_img, heads, seq, dhead, dpad, ldo):
+        def fn():
+            n = n_img * heads * seq * dpad
+            Q = q.reshape(-1)[:n].reshape(n_img, heads, seq, dpad).float()
+            Kk = k.reshape(-1)[:n].reshape(n_img, heads, seq, dpad).float()
+            V = vt.reshape(-1)[:n].reshape(n_img, heads, dpad, seq).float().transpose(-1, -2)
+            kd = (dhead + 15) // 16 * 16
+            s = (Q[..., :kd] @ Kk[..., :kd].transpose(-1, -2)) * dhead ** -0.5
+            p = s.softmax(-1)
+            o = (p @ V)[..., :dhead]
+            out.reshape(-1)[: n_img * seq * ldo].reshape(n_img, seq, ldo)[:, :, : heads * dhead] = \
+                o.permute(0, 2, 1, 3).reshape(n_img, seq, heads * dhead).half()
+        return self._call(fn)
+
+    # ------------------------------------------------------------------ normalisation
+    def groupnorm(self, x, gamma, beta, y, stats_ws, n_img, hw, C, eps, silu):
+        def fn():
+            v = x.reshape(-1)[: n_img * hw * C].reshape(n_img, hw, C).permute(0, 2, 1)
+            o = F.group_norm(v, 32, gamma, beta, eps)
+            if silu:
+                o = F.silu(o)
+            y.reshape(-1)[: n_img * hw * C].copy_(o.permute(0, 2, 1).reshape(-1).half())
+        return self._call(fn)
+
+    def layernorm(self, x, gamma, beta, y, rows, C, eps):
+        def fn():
+            v = x.reshape(-1)[: rows * C].reshape(rows, C)
+            y.reshape(-1)[: rows * C].copy_(F.layer_norm(v, (C,), gamma, beta, eps).reshape(-1).half())
+        return self._call(fn)
+
+    def ln_modulate(self, x, shift, scale, y, rows, C, eps):
+        def fn():
+            v = x.reshape(-1)[: rows * C].reshape(rows, C)
+            o = F.layer_norm(v, (C,), None, None, eps) * (1 + scale.reshape(-1)[:C]) + shift.reshape(-1)[:C]
+            y.reshape(-1)[: rows * C].copy_(o.reshape(-1).half())
+        return self._call(fn)
+
+    # ------------------------------------------------------------------ data movement
+    def cast(self, x, y, n):
+        return self._call(lambda: y.reshape(-1)[:n].copy_(x.reshape(-1)[:n].half()))
+
+    def concat(self, a, b, out, rows, C1, C2):
+        def fn():
+            o = out.reshape(-1)[: rows * (C1 + C2)].reshape(rows, C1 + C2)
+            o[:, :C1] = a.reshape(-1)[: rows * C1].reshape(rows, C1)
+            o[:, C1:] = b.reshape(-1)[: rows * C2].reshape(rows, C2)
+        return self._call(fn)
+
+    def upsample2x(self, x, y, n_img, H, W, C):
+        def fn():
+            v = x.reshape(-1)[: n_img * H * W * C].reshape(n_img, H, W, C)
+            o = v.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+            y.reshape(-1)[: o.numel()].copy_(o.reshape(-1).half())
+        return self._call(fn)
+
+    def im2col_s2(self, x, y, n_img, H, W, C):
+        def fn():
+            v = x.reshape(-1)[: n_img * H * W * C].reshape(n_img, H, W, C)
+            vp = F.pad(v, (0, 0, 1, 1, 1, 1))
+            cols = [vp[:, ky:ky + H:2, kx:kx + W:2, :] for ky in range(3) for kx in range(3)]
+            o = torch.cat(cols, dim=-1)
+            y.reshape(-1)[: o.numel()].copy_(o.reshape(-1).half())
+        return self._call(fn)
+
+    def gemv(self, x, W, bias, y, M, N, K, *, ldx=None, ldw=None, ldy=None, silu_in=False, silu_out=False):
+        ldx_ = ldx if ldx is not None else x.shape[-1]
+        ldw_ = ldw if ldw is not None else W.shape[-1]
+        ldy_ = ldy if ldy is not None else y.shape[-1]
+
+        def fn():
+            a = x.reshape(-1)[: M * ldx_].reshape(M, ldx_)[:, :K]
+            if silu_in:
+                a = F.silu(a)
+            o = a @ W.reshape(-1)[: N * ldw_].reshape(N, ldw_)[:, :K].float().t()
+            if bias is not None:
+                o = o + bias.reshape(-1)[:N]
+            if silu_out:
+                o = F.silu(o)
+            y.reshape(-1)[: M * ldy_].reshape(M, ldy_)[:, :N] = o
+        return self._call(fn)
+
+    def timestep_embedding(self, t_dev, freqs, out, dim):
+        def fn():
+            a = t_dev.reshape(-1)[0] * freqs
+            out.reshape(-1)[:dim].copy_(torch.cat([torch.cos(a), torch.sin(a)])[:dim])
+        return self._call(fn)
+
+    def unet_input(self, noisy, cond, cond_batched, cond_scale, out, n_views, n_img, hw, Cpad):
+        def fn():
+            o = out.reshape(-1)[: n_img * hw * Cpad].reshape(n_img, hw, Cpad)
+            o.zero_()
+            nz = noisy.reshape(-1)[: n_views * 5 * hw].reshape(n_views, 5, hw)
+            for img in range(n_img):
+                view = img % n_views
+                o[img, :, :5] = nz[view].t().half()
+                if img < n_views:
+                    c = cond.reshape(-1, 5, hw)[view if cond_batched else 0].clone()
+                    if cond_scale is not None:
+                        c = c * cond_scale[view]
+                    c[:4] = c[:4] / 0.18215
+                    o[img, :, 5:10] = c.t().half()
+        return self._call(fn)
+
+    def cfg_ddim(self, head, ld, two_branch, coef, xt, noise, eps_out, x_prev, x0_out, n_views, hw):
+        def fn():
+            n_img = n_views * (2 if two_branch else 1)
+            h = head.reshape(-1)[: n_img * hw * ld].reshape(n_img, hw, ld)[:, :, :5].permute(0, 2, 1)
+            e = h[:n_views]
+            if two_branch:
+                e = h[n_views:] + coef[5] * (h[:n_views] - h[n_views:])
+            if eps_out is not None:
+                eps_out.reshape(-1)[: e.numel()].copy_(e.reshape(-1))
+            if xt is not None:
+                a_t, a_prev, somat, sigma = coef[0], coef[1], coef[2], coef[3]
+                x = xt.reshape(n_views, 5, hw).clone()
+                x0 = (x - somat * e) / a_t.sqrt()
+                xp = a_prev.sqrt() * x0 + torch.clamp(1.0 - a_prev - sigma * sigma, min=1e-7).sqrt() * e
+                if float(coef[4]) != 0.0:
+                    xp = xp + sigma * noise.reshape(n_views, 5, hw)
+                x_prev.reshape(n_views, 5, hw).copy_(xp)
+                if x0_out is not None:
+                    x0_out.reshape(n_views, 5, hw).copy_(x0)
+        return self._call(fn)
+
+    def nchw_to_rows(self, x, y, n_img, C, hw):
+        return self._call(lambda: y.reshape(-1)[: n_img * C * hw].copy_(x.reshape(n_img, C, hw).permute(0, 2, 1).reshape(-1)))
+
+    def rows_to_nchw(self, x, y, n_img, C, ld, hw):
+        return self._call(lambda: y.reshape(-1)[: n_img * C * hw].copy_(
+            x.reshape(-1)[: n_img * hw * ld].reshape(n_img, hw, ld)[:, :, :C].permute(0, 2, 1).reshape(-1)))
+
+    def nchw_to_nhwc16(self, x, y, n_img, C, hw, Cpad):
+        def fn():
+            o = y.reshape(-1)[: n_img * hw * Cpad].reshape(n_img, hw, Cpad)
+            o.zero_()
+            o[:, :, :C] = x.reshape(n_img, C, hw).permute(0, 2, 1).half()
+        return self._call(fn)
+
+    def gather_rows(self, table, row_len, idx_dev, out):
+        return self._call(lambda: out.reshape(-1)[:row_len].copy_(table.reshape(-1, row_len)[int(idx_dev[0])]))
+
+    def increment(self, counter, delta):
+        return self._call(lambda: counter.add_(delta))
+
+    # ------------------------------------------------------------------ GridAttn
+    def gridattn_prep(self, noisy, input_latent, depth_override, depth_eps, scal, Wz, bz, feat, zdepth, n_views, S, D,
+                      depth_scale, depth_shift):
+        def fn():
+            hw = S * S
+            lat = torch.cat([noisy.reshape(n_views, 5, hw), input_latent.reshape(-1, 5, hw)[:1]])
+            f = F.gelu(lat.permute(0, 2, 1) @ Wz.reshape(256, 5).t() + bz)
+            feat.reshape(-1)[: f.numel()].copy_(f.reshape(-1).half())
+            mean = depth_override.reshape(n_views, 1, hw) if depth_override is not None else \
+                noisy.reshape(n_views, 5, hw)[:, 4:5] / scal[0]
+            s = mean + scal[1] * depth_eps.reshape(n_views, D, hw)
+            z = torch.clip((s + 1.0) / 2.0, 0.0, 1.0) * depth_scale + depth_shift
+            zdepth.reshape(-1)[: z.numel()].copy_(z.reshape(-1))
+        return self._call(fn)
+
+    def gridattn_tokens(self, feat, zdepth, cams, mask, freqs, ndc_grid, tokens, n_views, S, D, q_first, q_count):
+        def fn():
+            hw, V = S * S, n_views
+            fm = feat.reshape(-1)[: (V + 1) * hw * 256].reshape(V + 1, S, S, 256).float().permute(0, 3, 1, 2)
+            z = zdepth.reshape(-1)[: V * D * hw].reshape(V, D, hw)[q_first:q_first + q_count]
+            cam = cams.reshape(V + 1, 16)
+            R, T, f, pp = cam[:, :9].reshape(-1, 3, 3), cam[:, 9:12], cam[:, 12:14], cam[:, 14:16]
+            ctr = -torch.einsum("bj,bij->bi", T, R)
+            gx = ndc_grid.reshape(1, S).expand(S, S).reshape(-1)
+            gy = ndc_grid.reshape(S, 1).expand(S, S).reshape(-1)
+            qi = torch.arange(q_first, q_first + q_count)
+            dv = torch.stack([(gx[None] - pp[qi, 0:1]) / f[qi, 0:1], (gy[None] - pp[qi, 1:2]) / f[qi, 1:2],
+                              torch.ones(q_count, hw)], -1)
+            dirs = dv @ R[qi].transpose(1, 2)  # (q, hw, 3)
+            X = ctr[qi][:, None, None, :] + z.permute(0, 2, 1)[..., None] * dirs[:, :, None, :]  # (q, hw, D, 3)
+            P = q_count * hw * D
+            pts = X.reshape(1, P, 3)
+
+            def sample(fmap, ci):
+                v = pts @ R[ci] + T[ci][:, None, :]
+                x = f[ci][:, None, 0] * v[..., 0] / v[..., 2] + pp[ci][:, None, 0]
+                y = f[ci][:, None, 1] * v[..., 1] / v[..., 2] + pp[ci][:, None, 1]
+                g = F.grid_sample(fmap, -torch.stack([x, y], -1).unsqueeze(2), align_corners=True, mode="bilinear",
+                                  padding_mode="border")
+                return g[..., 0].permute(0, 2, 1)  # (n, P, 256)
+
+            vi = torch.arange(V)
+            ref = sample(fm[:V], vi)
+            inp = sample(fm[V:], torch.tensor([V])).expand(V, -1, -1)
+
+            def harm(x):
+                e = (x[..., None] * freqs).reshape(*x.shape[:-1], -1)
+                return torch.cat([e.sin(), e.cos(), x], -1)
+
+            rd = pts.expand(V, -1, -1) - ctr[:V, None, :]
+            rlen = torch.linalg.norm(rd, dim=-1, keepdim=True)
+            rdn = rd / rlen.clamp_min(1e-12)
+            ref_pl = harm(torch.cat([rdn, torch.cross(ctr[:V, None, :].expand_as(rdn), rdn, dim=-1)], -1))
+            qd = dirs / torch.linalg.norm(dirs, dim=-1, keepdim=True).clamp_min(1e-12)
+            qd = qd[:, :, None, :].expand(-1, -1, D, -1).reshape(1, P, 3)
+            qo = ctr[qi][:, None, None, :].expand(-1, hw, D, -1).reshape(1, P, 3)
+            q_pl = harm(torch.cat([qd, torch.cross(qo, qd, dim=-1)], -1)).expand(V, -1, -1)
+            q_dep = harm(z.permute(0, 2, 1).reshape(1, P, 1)).expand(V, -1, -1)
+            m = mask.reshape(V, 1, 1).expand(-1, P, -1)
+            tok = torch.cat([ref, inp, ref_pl, harm(rlen), q_pl, q_dep, m], -1)  # (V, P, 723)
+            o = tokens.reshape(-1)[: P * V * 736].reshape(P, V, 736)
+            o.zero_()
+            o[:, :, :723] = tok.permute(1, 0, 2).half()
+        return self._call(fn)
+
+    def view_attention(self, qkv, out, P, V, heads, hd):
+        def fn():
+            C = heads * hd
+            t = qkv.reshape(-1)[: P * V * 3 * C].reshape(P, V, 3, heads, hd).float().permute(2, 0, 3, 1, 4)
+            a = ((t[0] * hd ** -0.5) @ t[1].transpose(-1, -2)).softmax(-1) @ t[2]
+            out.reshape(-1)[: P * V * C].copy_(a.transpose(1, 2).reshape(-1).half())
+        return self._call(fn)
+
+    def view_pool(self, x, w, b, out, P, V, C):
+        def fn():
+            v = x.reshape(-1)[: P * V * C].reshape(P, V, C)
+            wt = (v @ w.reshape(C, 1) + b.reshape(-1)[0]).softmax(dim=1)
+            out.reshape(-1)[: P * C].copy_((v * wt).sum(1).reshape(-1).half())
+        return self._call(fn)
+
+    def frustum_pool(self, inp, out, n_img, S, D, C, factor):
+        def fn():
+            v = inp.reshape(-1)[: n_img * S * S * D * C].reshape(n_img, S // factor, factor, S // factor, factor, D, C).float()
+            o = v.mean(dim=(2, 4))
+            out.reshape(-1)[: o.numel()].copy_(o.reshape(-1).half())
+        return self._call(fn)
+
+    def pixel_cross_attn(self, q, kv, out, M, D, heads, dhead):
+        def fn():
+            C = heads * dhead
+            Q = q.reshape(-1)[: M * C].reshape(M, heads, 1, dhead).float()
+            KV = kv.reshape(-1)[: M * D * 2 * C].reshape(M, D, 2, heads, dhead).float()
+            K, V = KV[:, :, 0].permute(0, 2, 1, 3), KV[:, :, 1].permute(0, 2, 1, 3)
+            a = ((Q @ K.transpose(-1, -2)) * dhead ** -0.5).softmax(-1) @ V
+            out.reshape(-1)[: M * C].copy_(a.reshape(-1).half())
+        return self._call(fn)
