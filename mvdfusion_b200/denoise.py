@@ -118,7 +118,8 @@ class StepPlan:
         self.arena_bytes = arena.total_bytes
         self._tables = None
         self._loop_prog = None
-        self._graph = None
+        self._host_prog = None
+        self._graphs = {}
         self.kernels_per_step = None
 
     # ------------------------------------------------------------------ scene / inputs
@@ -164,53 +165,67 @@ class StepPlan:
 
     # ------------------------------------------------------------------ loop (DDIMSampler.sample)
     def set_tables(self, step_rows, depth_eps_all, noise_all):
-        """step_rows [steps, 16]; depth_eps_all [steps, N, D, hw]; noise_all [steps, N, 5, hw] (device tensors)."""
+        """step_rows [steps, 16]; depth_eps_all [steps, N, D, hw]; noise_all [steps, N, 5, hw].  The device tables are
+        persistent (re-allocated only when the step count grows), so the captured loop graph stays valid across scenes."""
         steps = step_rows.shape[0]
-        dev = self.stepc.device
-        self._tables = (step_rows.to(dev).float().contiguous(), depth_eps_all.to(dev).float().reshape(steps, -1).contiguous(),
-                        noise_all.to(dev).float().reshape(steps, -1).contiguous())
         ops = self.ops
-        pro = E.Program()
-        pro.append(ops.gather_rows(self._tables[0], STEPC_LEN, self.counter, self.stepc))
-        pro.append(ops.gather_rows(self._tables[1], self.N * self.D * self.hw, self.counter, self.depth_eps))
-        pro.append(ops.gather_rows(self._tables[2], self.N * 5 * self.hw, self.counter, self.ddim_noise))
-        pro.append(ops.increment(self.counter, 1))
-        loop = E.Program()
-        loop.extend(pro)
-        loop.extend(self.core_prog)
-        loop.extend(self.ddim_prog)
-        self._loop_prog = loop
-        self._graph = None
+        if self._tables is None or self._tables[0].shape[0] < steps:
+            self._tables = (ops.zeros((steps, STEPC_LEN), torch.float32), ops.zeros((steps, self.N * self.D * self.hw), torch.float32),
+                            ops.zeros((steps, self.N * 5 * self.hw), torch.float32))
+            pro = E.Program()
+            pro.append(ops.gather_rows(self._tables[0], STEPC_LEN, self.counter, self.stepc))
+            pro.append(ops.gather_rows(self._tables[1], self.N * self.D * self.hw, self.counter, self.depth_eps))
+            pro.append(ops.gather_rows(self._tables[2], self.N * 5 * self.hw, self.counter, self.ddim_noise))
+            pro.append(ops.increment(self.counter, 1))
+            loop = E.Program()
+            loop.extend(pro)
+            loop.extend(self.core_prog)
+            loop.extend(self.ddim_prog)
+            self._loop_prog = loop
+            self._graphs.pop("loop", None)
+        self._tables[0][:steps].copy_(step_rows.float(), non_blocking=True)
+        self._tables[1][:steps].copy_(depth_eps_all.reshape(steps, -1).float(), non_blocking=True)
+        self._tables[2][:steps].copy_(noise_all.reshape(steps, -1).float(), non_blocking=True)
         self.counter.zero_()
 
-    def loop_step(self, stream, use_graph=True):
-        """One DDIM iteration for this rank's views (advances the device step counter)."""
+    def _replay(self, key, prog, stream, use_graph):
+        """Run `prog` once: call by call, or (CUDA) from a graph captured on first use."""
         if not use_graph or self.x.device.type != "cuda":
-            self._loop_prog.run(stream)
+            prog.run(stream)
             return
-        if self._graph is None:
+        if key not in self._graphs:
             # warm-up outside capture (lazy module loading, smem attribute opt-ins), then restore the loop state
-            x_keep = self.x.clone()
-            c_keep = self.counter.clone()
             from . import _lib
+            x_keep, c_keep = self.x.clone(), self.counter.clone()
             c0 = _lib.launch_count()
-            self._loop_prog.run(stream)
+            prog.run(stream)
             self.kernels_per_step = _lib.launch_count() - c0
             torch.cuda.synchronize()
             self.x.copy_(x_keep)
             self.counter.copy_(c_keep)
             g = torch.cuda.CUDAGraph()
-            cur = torch.cuda.current_stream()
-            side = torch.cuda.Stream()
-            side.wait_stream(cur)
-            with torch.cuda.graph(g, stream=side):
-                self._loop_prog.run(torch.cuda.current_stream().cuda_stream)
-            cur.wait_stream(side)
+            with torch.cuda.graph(g):
+                prog.run(torch.cuda.current_stream().cuda_stream)
             self.x.copy_(x_keep)
             self.counter.copy_(c_keep)
-            self._graph = g
-        self._graph.replay()
+            self._graphs[key] = g
+        self._graphs[key].replay()
 
+    def loop_step(self, stream, use_graph=True):
+        """One DDIM iteration for this rank's views, everything selected on the device (advances the step counter)."""
+        self._replay("loop", self._loop_prog, stream, use_graph)
+
+    def host_step(self, stream, row, depth_eps, ddim_noise, use_graph=True):
+        """One DDIM iteration whose per-step inputs come from (pinned) HOST memory: constants row [16], depth jitter
+        (N,D,hw) and DDIM noise (N,5,hw) are copied host->device on `stream` order, then the step program runs."""
+        self.stepc.copy_(row, non_blocking=True)
+        self.depth_eps.copy_(depth_eps.reshape(self.depth_eps.shape), non_blocking=True)
+        self.ddim_noise.copy_(ddim_noise.reshape(self.ddim_noise.shape), non_blocking=True)
+        if self._host_prog is None:
+            self._host_prog = E.Program()
+            self._host_prog.extend(self.core_prog)
+            self._host_prog.extend(self.ddim_prog)
+        self._replay("host", self._host_prog, stream, use_graph)
 
 
 class UNetStagePlan:

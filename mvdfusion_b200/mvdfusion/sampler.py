@@ -91,10 +91,13 @@ class DDIMSampler:
 
     @torch.no_grad()
     def sample(self, batch_cameras, input_latents, input_cameras, clip_embed, unconditional_scale=1.0, depth=False,
-               return_intermediates=False, verbose=True, x_T=None, depth_eps=None, ddim_noise=None, use_graph=True):
+               return_intermediates=False, verbose=True, x_T=None, depth_eps=None, ddim_noise=None, use_graph=True,
+               host_io=False):
         """mvdfusion/sampler.py:90-147.  Extra keyword arguments (all optional): x_T (B,5,S,S), depth_eps / ddim_noise
         (steps,B,D,S,S) / (steps,B,5,S,S) inject the random draws of iteration i (i = 0 is the largest timestep) instead of
-        drawing them here; use_graph=False replays the step program call by call."""
+        drawing them here; use_graph=False replays the step program call by call; host_io=True keeps the per-step inputs
+        (schedule constants, noise draws) in pinned HOST memory, copies them to the device every step and reads every
+        step's x_t back to the host (the end-to-end mode bench.py times)."""
         if not depth:
             raise NotImplementedError("GridAttn needs the 4+1 channel latents (view_attn_efficient2.py:440): call with depth=True")
         model = self.model
@@ -124,13 +127,25 @@ class DDIMSampler:
         stream = current_stream(device)
         model.bind_scene(plan, batch_cameras, input_latents, input_cameras, clip_embed, stream)
         plan.x.copy_(x.reshape(B, 5, S * S))
-        plan.set_tables(rows, depth_eps, ddim_noise)
         inter = []
         group = model.view_group
+        if host_io:
+            pin = (lambda t: t.pin_memory()) if device.type == "cuda" else (lambda t: t)
+            rows_h, de_h, dn_h = pin(rows.contiguous()), pin(depth_eps.float().cpu().contiguous()), pin(ddim_noise.float().cpu().contiguous())
+            x_h = pin(torch.empty(total, plan.q, 5, S, S))
+        else:
+            plan.set_tables(rows, depth_eps, ddim_noise)
         for i in range(total):
-            plan.loop_step(stream, use_graph=use_graph)
+            if host_io:
+                plan.host_step(stream, rows_h[i], de_h[i], dn_h[i], use_graph=use_graph)
+            else:
+                plan.loop_step(stream, use_graph=use_graph)
             if group is not None:
                 model.gather_views(plan)
+            if host_io:
+                x_h[i].copy_(plan.x_local.reshape(plan.q, 5, S, S), non_blocking=True)
+                if device.type == "cuda":
+                    torch.cuda.current_stream(device).synchronize()
             if return_intermediates:
                 inter.append({"t": int(self.ddim_timesteps[total - i - 1]), "xt": plan.x.reshape(B, 5, S, S).clone(),
                               "x0": plan.x0_out.reshape(-1, 5, S, S).clone()})

@@ -33,10 +33,11 @@ def _ptr(t, dtype=None):
 class BoundCall:
     """One C-ABI call with frozen arguments.  Keeps the tensors alive that its pointers refer to."""
 
-    __slots__ = ("fn", "args", "keep", "name")
+    __slots__ = ("fn", "args", "keep", "name", "meta")
 
-    def __init__(self, name, fn, args, keep):
+    def __init__(self, name, fn, args, keep, meta=None):
         self.name, self.fn, self.args, self.keep = name, fn, args, keep
+        self.meta = meta or {}  # algorithmic flops / bytes of the launch (bench.py roofline accounting)
 
     def __call__(self, stream):
         rc = self.fn(*self.args, stream)
@@ -67,8 +68,8 @@ class NativeOps:
             raise MvdError(_lib.last_error())
         return torch.tensor(list(perm), dtype=torch.long)
 
-    def _bind(self, name, args, keep):
-        return BoundCall(name, getattr(self.lib, name), tuple(args), keep)
+    def _bind(self, name, args, keep, meta=None):
+        return BoundCall(name, getattr(self.lib, name), tuple(args), keep, meta)
 
     # ------------------------------------------------------------------ GEMM / conv
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
@@ -103,12 +104,19 @@ class NativeOps:
         g.split_k = split_k
         g.tile_n = tile_n
         keep = (g, A, Wt, out, bias, rowbias, colscale, residual, qkv)
-        return self._bind("mvd_gemm_f16", (ctypes.byref(g),), keep)
+        n_out = N // 2 if act == ACT_GEGLU else N
+        a_bytes = (conv[0] * conv[1] * conv[2] * conv[3] if conv is not None else M * K) * 2
+        o_bytes = M * n_out * (4 if (qkv is None and out.dtype == torch.float32) else 2)
+        meta = {"kernel": "gemm_tc_kernel", "flops": 2.0 * M * N * K, "shape": (M, N, K, split_k),
+                "bytes": a_bytes + N * K * 2 + o_bytes + (M * n_out * 4 if residual is not None else 0)}
+        return self._bind("mvd_gemm_f16", (ctypes.byref(g),), keep, meta)
 
     def attn_self(self, q, k, vt, out, n_img, heads, seq, dhead, dpad, ldo):
         return self._bind("mvd_attn_self_f16", (_ptr(q, torch.float16), _ptr(k, torch.float16), _ptr(vt, torch.float16),
                                                 _ptr(out, torch.float16), n_img, heads, seq, dhead, dpad, ldo),
-                          (q, k, vt, out))
+                          (q, k, vt, out),
+                          {"kernel": "attn_self_kernel", "flops": 4.0 * n_img * heads * seq * seq * dhead,
+                           "bytes": 2.0 * n_img * heads * seq * (3 * dpad + dhead)})
 
     # ------------------------------------------------------------------ normalisation
     def groupnorm(self, x, gamma, beta, y, stats_ws, n_img, hw, C, eps, silu):

@@ -1,0 +1,196 @@
+"""-m gpu: every C-ABI entry point on the B200 against the CPU emulation of its documented semantics
+(tests/ops_double.py), on random inputs at the shapes the hot path uses."""
+import pytest
+import torch
+
+from mvdfusion_b200 import ops as OPS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nat():
+    return OPS.NativeOps("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def dbl():
+    from ops_double import TorchOpsDouble
+    return TorchOpsDouble()
+
+
+def run_both(nat, dbl, name, tensors, out_names, *args, tol=2e-3, **kw):
+    """tensors: dict name -> cpu tensor (inputs and pre-filled outputs).  Calls op `name` on both, compares outputs."""
+    cpu = {k: (v.clone() if v is not None else None) for k, v in tensors.items()}
+    gpu = {k: (v.cuda() if v is not None else None) for k, v in tensors.items()}
+
+    def bind(o, t):
+        a = [t[x] if isinstance(x, str) and x in t else x for x in args]
+        k = {kk: (t[vv] if isinstance(vv, str) and vv in t else vv) for kk, vv in kw.items()}
+        if "qkv" in k and k["qkv"] is not None:
+            k["qkv"] = {qq: (t[qv] if isinstance(qv, str) else qv) for qq, qv in k["qkv"].items()}
+        return getattr(o, name)(*a, **k)
+
+    bind(dbl, cpu)(None)
+    bind(nat, gpu)(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for o in out_names:
+        a, b = gpu[o].float().cpu(), cpu[o].float()
+        assert torch.isfinite(a).all(), f"{name}: non-finite values in {o}"
+        err = (a - b).abs().max().item()
+        scale = b.abs().max().item() + 1e-6
+        assert err <= tol * scale, f"{name}:{o} max err {err:.3e} vs scale {scale:.3e}"
+
+
+def rnd(*shape, dtype=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(dtype)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 320, 320), (1024, 1280, 5120), (130, 5, 2880), (2048, 768, 256)])
+def test_gemm_plain_bias_residual(nat, dbl, M, N, K):
+    t = {"A": rnd(M, K, dtype=torch.float16), "W": rnd(N, K, dtype=torch.float16, seed=1, scale=K ** -0.5),
+         "bias": rnd(N, seed=2), "res": rnd(M, N, seed=3), "out": torch.zeros(M, N)}
+    run_both(nat, dbl, "gemm", t, ["out"], "A", "W", "out", M, N, K, bias="bias", residual="res", ldr=N)
+
+
+def test_gemm_splitk_rowbias(nat, dbl):
+    M, N, K = 256, 1280, 11520
+    t = {"A": rnd(M, K, dtype=torch.float16), "W": rnd(N, K, dtype=torch.float16, seed=1, scale=K ** -0.5),
+         "rb": rnd(4, N, seed=2), "res": rnd(M, N, seed=3), "out": torch.zeros(M, N)}
+    run_both(nat, dbl, "gemm", t, ["out"], "A", "W", "out", M, N, K, rowbias="rb", rows_per_group=64, residual="res", ldr=N,
+             split_k=8)
+
+
+def test_gemm_geglu_f16(nat, dbl):
+    M, C = 512, 320
+    t = {"A": rnd(M, C, dtype=torch.float16), "W": rnd(8 * C, C, dtype=torch.float16, seed=1, scale=C ** -0.5),
+         "bias": rnd(8 * C, seed=2, scale=0.1), "out": torch.zeros(M, 4 * C, dtype=torch.float16)}
+    run_both(nat, dbl, "gemm", t, ["out"], "A", "W", "out", M, 8 * C, C, bias="bias", act=OPS.ACT_GEGLU, tile_n=128, ldc=4 * C)
+
+
+def test_gemm_gelu_colscale(nat, dbl):
+    M, N, K = 4096, 256, 512
+    t = {"A": rnd(M, K, dtype=torch.float16), "W": rnd(N, K, dtype=torch.float16, seed=1, scale=K ** -0.5),
+         "bias": rnd(N, seed=2), "cs": rnd(N, seed=4), "res": rnd(M, N, seed=3), "out": torch.zeros(M, N)}
+    run_both(nat, dbl, "gemm", t, ["out"], "A", "W", "out", M, N, K, bias="bias", colscale="cs", residual="res", ldr=N)
+    t["out"] = torch.zeros(M, N, dtype=torch.float16)
+    run_both(nat, dbl, "gemm", t, ["out"], "A", "W", "out", M, N, K, bias="bias", act=OPS.ACT_GELU)
+
+
+@pytest.mark.parametrize("n,H,Cin,Cout", [(2, 32, 320, 320), (4, 16, 640, 320), (16, 4, 1280, 1280), (3, 8, 960, 640), (2, 32, 16, 320),
+                                          (2, 32, 320, 5)])
+def test_conv3x3(nat, dbl, n, H, Cin, Cout):
+    M = n * H * H
+    ldc = 8 if Cout == 5 else Cout
+    t = {"A": rnd(M, Cin, dtype=torch.float16), "W": rnd(Cout, 9 * Cin, dtype=torch.float16, seed=1, scale=(9 * Cin) ** -0.5),
+         "bias": rnd(Cout, seed=2), "out": torch.zeros(M, ldc)}
+    run_both(nat, dbl, "gemm", t, ["out"], "A", "W", "out", M, Cout, 9 * Cin, conv=(n, H, H, Cin), bias="bias", ldc=ldc,
+             split_k=(4 if H == 4 else 1))
+
+
+@pytest.mark.parametrize("n,seq,C", [(2, 1024, 320), (2, 256, 640), (3, 64, 1280), (2, 16, 1280), (2, 1024, 64)])
+def test_qkv_and_attention(nat, dbl, n, seq, C):
+    heads = 8
+    d = C // heads
+    dpad = (d + 63) // 64 * 64
+    M = n * seq
+    nb = n * heads * seq * dpad
+    t = {"A": rnd(M, C, dtype=torch.float16), "W": rnd(3 * C, C, dtype=torch.float16, seed=1, scale=C ** -0.5),
+         "q": torch.zeros(nb, dtype=torch.float16), "k": torch.zeros(nb, dtype=torch.float16),
+         "vt": torch.zeros(nb, dtype=torch.float16), "o": torch.zeros(M, C, dtype=torch.float16)}
+    run_both(nat, dbl, "gemm", t, ["q", "k", "vt"], "A", "W", "q", M, 3 * C, C,
+             qkv=dict(out_k="k", out_vt="vt", heads=heads, dhead=d, dpad=dpad, seq=seq))
+    # attention on the (emulated) q/k/v so that both sides see identical operands
+    from ops_double import TorchOpsDouble
+    d2 = TorchOpsDouble()
+    d2.gemm(t["A"], t["W"], t["q"], M, 3 * C, C, qkv=dict(out_k=t["k"], out_vt=t["vt"], heads=heads, dhead=d, dpad=dpad, seq=seq))(None)
+    run_both(nat, dbl, "attn_self", t, ["o"], "q", "k", "vt", "o", n, heads, seq, d, dpad, C, tol=4e-3)
+
+
+@pytest.mark.parametrize("n,hw,C,silu", [(2, 1024, 320, True), (16, 16, 2560, True), (3, 256, 1920, False)])
+def test_groupnorm(nat, dbl, n, hw, C, silu):
+    t = {"x": rnd(n * hw, C) * 2 + 0.5, "g": rnd(C, seed=1), "b": rnd(C, seed=2), "y": torch.zeros(n * hw, C, dtype=torch.float16),
+         "ws": torch.zeros(max(n, 64) * 64, dtype=torch.float64)}
+    run_both(nat, dbl, "groupnorm", t, ["y"], "x", "g", "b", "y", "ws", n, hw, C, 1e-5, silu)
+
+
+def test_layernorms(nat, dbl):
+    for rows, C in ((512, 320), (100, 1280), (4096, 256)):
+        t = {"x": rnd(rows, C) * 3, "g": rnd(C, seed=1), "b": rnd(C, seed=2), "y": torch.zeros(rows, C, dtype=torch.float16)}
+        run_both(nat, dbl, "layernorm", t, ["y"], "x", "g", "b", "y", rows, C, 1e-5)
+        run_both(nat, dbl, "ln_modulate", t, ["y"], "x", "b", "g", "y", rows, C, 1e-6)
+
+
+def test_data_movement(nat, dbl):
+    n, H, C = 3, 8, 64
+    t = {"x": rnd(n * H * H, C), "y": torch.zeros(n * 4 * H * H, C, dtype=torch.float16)}
+    run_both(nat, dbl, "upsample2x", t, ["y"], "x", "y", n, H, H, C)
+    t = {"x": rnd(n * H * H, C), "y": torch.zeros(n * H * H // 4, 9 * C, dtype=torch.float16)}
+    run_both(nat, dbl, "im2col_s2", t, ["y"], "x", "y", n, H, H, C)
+    t = {"a": rnd(100, 64), "b": rnd(100, 32, seed=1), "o": torch.zeros(100, 96)}
+    run_both(nat, dbl, "concat", t, ["o"], "a", "b", "o", 100, 64, 32)
+    t = {"x": rnd(1000), "y": torch.zeros(1000, dtype=torch.float16)}
+    run_both(nat, dbl, "cast", t, ["y"], "x", "y", 1000)
+    t = {"x": rnd(2, 10, 64), "y": torch.zeros(2 * 64, 16, dtype=torch.float16), "r": torch.zeros(2 * 64, 10), "z": torch.zeros(2, 10, 64)}
+    run_both(nat, dbl, "nchw_to_nhwc16", t, ["y"], "x", "y", 2, 10, 64, 16)
+    run_both(nat, dbl, "nchw_to_rows", t, ["r"], "x", "r", 2, 10, 64)
+    t["r"] = rnd(2 * 64, 10)
+    run_both(nat, dbl, "rows_to_nchw", t, ["z"], "r", "z", 2, 10, 10, 64)
+
+
+def test_gemv_and_timestep(nat, dbl):
+    for M, N, K in ((1, 1280, 320), (8, 768, 796), (1, 1536, 256)):
+        k8 = (K + 7) // 8 * 8
+        W = torch.zeros(N, k8, dtype=torch.float16)
+        W[:, :K] = rnd(N, K, dtype=torch.float16, scale=K ** -0.5)
+        t = {"x": rnd(M, K, seed=1), "W": W, "b": rnd(N, seed=2), "y": torch.zeros(M, N)}
+        run_both(nat, dbl, "gemv", t, ["y"], "x", "W", "b", "y", M, N, K, ldx=K, ldw=k8, ldy=N, silu_in=True, silu_out=True, tol=1e-4)
+    import math
+    freqs = torch.exp(-math.log(10000) * torch.arange(160, dtype=torch.float32) / 160)
+    t = {"t": torch.tensor([981.0]), "f": freqs, "o": torch.zeros(320)}
+    run_both(nat, dbl, "timestep_embedding", t, ["o"], "t", "f", "o", 320, tol=2e-4)
+
+
+def test_unet_input_cfg_ddim_tables(nat, dbl):
+    n, hw = 3, 64
+    t = {"noisy": rnd(n, 5, hw), "cond": rnd(1, 5, hw, seed=1), "cs": torch.tensor([1.0, 0.0, 1.0]),
+         "out": torch.zeros(2 * n * hw, 16, dtype=torch.float16)}
+    run_both(nat, dbl, "unet_input", t, ["out"], "noisy", "cond", False, "cs", "out", n, 2 * n, hw, 16)
+    coef = torch.tensor([0.5, 0.6, 0.70710678, 0.2, 1.0, 2.5])
+    t = {"head": rnd(2 * n * hw, 8), "coef": coef, "xt": rnd(n, 5, hw, seed=2), "noise": rnd(n, 5, hw, seed=3),
+         "eps": torch.zeros(n, 5, hw), "xp": torch.zeros(n, 5, hw), "x0": torch.zeros(n, 5, hw)}
+    run_both(nat, dbl, "cfg_ddim", t, ["eps", "xp", "x0"], "head", 8, True, "coef", "xt", "noise", "eps", "xp", "x0", n, hw, tol=1e-5)
+    t = {"tab": rnd(7, 33), "idx": torch.tensor([4], dtype=torch.int32), "o": torch.zeros(33)}
+    run_both(nat, dbl, "gather_rows", t, ["o"], "tab", 33, "idx", "o", tol=0)
+    run_both(nat, dbl, "increment", t, ["idx"], "idx", 2, tol=0)
+
+
+@pytest.mark.parametrize("N,D,q_first,q_count", [(4, 1, 0, 4), (3, 3, 1, 2)])
+def test_gridattn_kernels(nat, dbl, N, D, q_first, q_count):
+    from mvdfusion_b200 import synthetic
+    from mvdfusion_b200.denoise import pack_cameras
+    S, hw = 32, 1024
+    R, T, f, p = synthetic.gso_rig(N)
+    cams = pack_cameras(torch.cat([R[1:], R[:1]]), torch.cat([T[1:], T[:1]]), torch.cat([f[1:], f[:1]]), torch.cat([p[1:], p[:1]]))
+    half = 1.0 / S
+    t = {"noisy": rnd(N, 5, hw), "inp": rnd(1, 5, hw, seed=1), "eps": rnd(N, D, hw, seed=2), "scal": torch.tensor([0.6, 0.13]),
+         "Wz": rnd(256 * 5, seed=3, scale=0.4), "bz": rnd(256, seed=4, scale=0.1),
+         "feat": torch.zeros((N + 1) * hw, 256, dtype=torch.float16), "z": torch.zeros(N * D * hw)}
+    run_both(nat, dbl, "gridattn_prep", t, ["feat", "z"], "noisy", "inp", None, "eps", "scal", "Wz", "bz", "feat", "z", N, S, D, 2.0, 0.5)
+    from ops_double import TorchOpsDouble
+    TorchOpsDouble().gridattn_prep(t["noisy"], t["inp"], None, t["eps"], t["scal"], t["Wz"], t["bz"], t["feat"], t["z"], N, S, D, 2.0, 0.5)(None)
+    P = q_count * hw * D
+    t.update({"cams": cams, "mask": torch.ones(N), "fr": (2.0 ** torch.arange(7, dtype=torch.float32)) * 0.1,
+              "grid": torch.linspace(1.0 - half, -1.0 + half, S), "tok": torch.zeros(P * N, 736, dtype=torch.float16)})
+    run_both(nat, dbl, "gridattn_tokens", t, ["tok"], "feat", "z", "cams", "mask", "fr", "grid", "tok", N, S, D, q_first, q_count, tol=4e-3)
+    t = {"qkv": rnd(P * N, 768, dtype=torch.float16), "o": torch.zeros(P * N, 256, dtype=torch.float16)}
+    run_both(nat, dbl, "view_attention", t, ["o"], "qkv", "o", P, N, 8, 32)
+    t = {"x": rnd(P * N, 256), "w": rnd(256, seed=1, scale=0.1), "b": torch.tensor([0.1]), "o": torch.zeros(P, 256, dtype=torch.float16)}
+    run_both(nat, dbl, "view_pool", t, ["o"], "x", "w", "b", "o", P, N, 256)
+    t = {"i": rnd(2 * hw * D, 768, dtype=torch.float16), "o": torch.zeros(2 * (hw // 16) * D, 768, dtype=torch.float16)}
+    run_both(nat, dbl, "frustum_pool", t, ["o"], "i", "o", 2, S, D, 768, 4)
+    if D > 1:
+        M, C = 512, 640
+        t = {"q": rnd(M, C, dtype=torch.float16), "kv": rnd(M * D, 2 * C, dtype=torch.float16, seed=1), "o": torch.zeros(M, C, dtype=torch.float16)}
+        run_both(nat, dbl, "pixel_cross_attn", t, ["o"], "q", "kv", "o", M, D, 8, C // 8)

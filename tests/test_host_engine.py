@@ -1,0 +1,154 @@
+"""CPU: the product's host-side logic (reference-surface modules -> engine emitters -> program of bound calls, weight
+packing, buffer arena, step tables) executed against the CPU emulation of the C ABI and compared with the oracle.
+What this does NOT test is the kernels: that is tests/test_gpu_*.py on the B200."""
+import pytest
+import torch
+
+from common import build_model, rel_l2, state_dict_cpu, synthetic, unet_cfg_of
+from mvdfusion_b200.mvdfusion.cameras import PerspectiveCameras
+from oracle import mvd_oracle as O
+
+TOL = 2e-3  # the emulation rounds fp16 tensors exactly like the kernels' outputs
+
+
+def cams_of(c):
+    return PerspectiveCameras(c["R"], c["T"], c["f"], c["p"])
+
+
+@pytest.fixture(scope="module")
+def model():
+    m = build_model(64, 8, D=1, S=32)
+    return m, state_dict_cpu(m)
+
+
+def test_state_dict_names_follow_reference(model):
+    m, sd = model
+    for k in ("view_attn.z_embedder.0.weight", "view_attn.t_embedder.mlp.0.weight", "view_attn.pre_layer_b.0.weight",
+              "view_attn.aggregation_transformer.layer_list.2.attn.qkv.bias",
+              "view_attn.aggregation_transformer.layer_list.0.adaLN_modulation.1.weight",
+              "view_attn.aggregation_transformer.weight_layer.weight", "view_attn.final_layer_b.weight",
+              "unet_model.unet_model.time_embed.0.weight", "unet_model.unet_model.input_blocks.0.0.weight",
+              "unet_model.unet_model.input_blocks.1.1.transformer_blocks.0.attn1.to_q.weight",
+              "unet_model.unet_model.input_blocks.3.0.op.weight", "unet_model.unet_model.middle_block.2.aligned_attn_proj_in.weight",
+              "unet_model.unet_model.middle_block.2.aligned_attn_transformer_blocks.0.attn2.to_k.weight",
+              "unet_model.unet_model.output_blocks.5.3.conv.weight", "unet_model.unet_model.output_blocks.11.2.aligned_attn_norm.weight",
+              "unet_model.unet_model.output_blocks.2.1.conv.weight", "unet_model.unet_model.out.2.bias",
+              "scheduler.alphas_cumprod", "cc_projection.4.weight", "time_embed.2.bias"):
+        assert k in sd, k
+    assert sd["view_attn.pre_layer_b.0.weight"].shape == (256, 723)
+    assert sd["cc_projection.0.weight"].shape == (768, 796)
+
+
+@pytest.mark.parametrize("D,cfg", [(1, 2.5), (3, 2.5), (1, 1.0)])
+def test_apply_model(ops_double, D, cfg):
+    m = build_model(64, 8, D=D, S=32)
+    sd = state_dict_cpu(m)
+    sc = synthetic.scene_inputs(2, 32)
+    de, _ = synthetic.step_noises(2, D, 32, 1)
+    t = torch.full((2,), 501, dtype=torch.long)
+    eps = m.apply_model(sc["x_T"], cams_of(sc["cams"]), sc["input_latents"], cams_of(sc["in_cams"]), sc["clip_v_embed"], t,
+                        cfg_scale=cfg, depth_eps=de[0])
+    ref = O.apply_model(sd, sc["x_T"], sc["cams"], sc["input_latents"], sc["in_cams"], sc["clip_v_embed"], t, de[0],
+                        unet_cfg=unet_cfg_of(m), D=D, cfg_scale=cfg)
+    assert torch.isfinite(eps).all()
+    assert rel_l2(eps, ref) < TOL
+
+
+def test_apply_model_condition_drop_and_prev_depth(ops_double, model):
+    m, sd = model
+    sc = synthetic.scene_inputs(2, 32)
+    de, _ = synthetic.step_noises(2, 1, 32, 1)
+    t = torch.full((2,), 501, dtype=torch.long)
+    rnd = torch.tensor([0.03, 0.12])
+    prev = torch.rand(2, 1, 32, 32) * 2 - 1
+    m.drop_conditions = True
+    try:
+        eps = m.apply_model(sc["x_T"], cams_of(sc["cams"]), sc["input_latents"], cams_of(sc["in_cams"]), sc["clip_v_embed"], t,
+                            cfg_scale=1.0, depth_eps=de[0], drop_random=rnd, prev_depth=prev)
+    finally:
+        m.drop_conditions = False
+    ref = O.apply_model(sd, sc["x_T"], sc["cams"], sc["input_latents"], sc["in_cams"], sc["clip_v_embed"], t, de[0],
+                        unet_cfg=unet_cfg_of(m), D=1, cfg_scale=1.0, drop_random=rnd, prev_depth=prev)
+    assert rel_l2(eps, ref) < TOL
+
+
+def test_ddim_loop_tables_and_counter(ops_double, model):
+    m, sd = model
+    steps = 4  # (1000 must be divisible: the reference has the same constraint, util.py:48-49)
+    m.ddim._make_schedule(steps, "uniform", 1.0)
+    sc = synthetic.scene_inputs(2, 32)
+    de, dn = synthetic.step_noises(2, 1, 32, steps)
+    x, inter = m.ddim.sample(cams_of(sc["cams"]), sc["input_latents"], cams_of(sc["in_cams"]), sc["clip_v_embed"],
+                             unconditional_scale=2.5, depth=True, return_intermediates=True, verbose=False, x_T=sc["x_T"],
+                             depth_eps=de, ddim_noise=dn)
+    ref, rinter = O.ddim_sample(sd, sc["x_T"], sc["cams"], sc["input_latents"], sc["in_cams"], sc["clip_v_embed"], de, dn,
+                                unet_cfg=unet_cfg_of(m), D=1, num_steps=steps, eta=1.0, cfg_scale=2.5, return_intermediates=True)
+    assert [a["t"] for a in inter] == [b["t"] for b in rinter]
+    for a, b in zip(inter, rinter):
+        assert rel_l2(a["xt"], b["xt"]) < TOL and rel_l2(a["x0"], b["x0"]) < TOL
+    assert rel_l2(x, ref) < TOL
+
+
+def test_module_level_forwards(ops_double, model):
+    m, sd = model
+    um = m.unet_model.unet_model
+    pre = "unet_model.unet_model."
+    g = torch.Generator().manual_seed(3)
+    # ResBlock with channel change (1x1 skip) and per-image embeddings
+    rb = um.input_blocks[4][0]
+    x = torch.randn(2, 64, 16, 16, generator=g)
+    emb = torch.randn(2, 256, generator=g)
+    assert rel_l2(rb(x, emb), O.resblock(sd, pre + "input_blocks.4.0", x, emb)) < TOL
+    # SpatialTransformer
+    st = um.input_blocks[1][1]
+    x = torch.randn(2, 64, 32, 32, generator=g)
+    ctx = torch.randn(2, 1, 768, generator=g)
+    assert rel_l2(st(x, ctx), O.spatial_transformer(sd, pre + "input_blocks.1.1", x, ctx, 8)) < TOL
+    # ViewAlignedFeatureTransformer at the 8x8 level with D = 2 keys per pixel
+    va = um.output_blocks[3][2]
+    x = torch.randn(2, 256, 8, 8, generator=g)
+    pyr = [torch.randn(2, 32 >> l, 32 >> l, 2, 768, generator=g) for l in range(4)]
+    assert rel_l2(va(x, pyr), O.view_aligned_transformer(sd, pre + "output_blocks.3.2", x, pyr, 8, 32)) < TOL
+    # self-attention
+    ca = st.transformer_blocks[0].attn1
+    x = torch.randn(2, 256, 64, generator=g)
+    assert rel_l2(ca(x), O.cross_attention(sd, pre + "input_blocks.1.1.transformer_blocks.0.attn1", x, None, 8)) < TOL
+    # whole UNet through its own forward
+    xin = torch.randn(2, 10, 32, 32, generator=g)
+    vol = torch.randn(2, 32, 32, 1, 768, generator=g)
+    y = um(xin, torch.tensor([301]), ctx, volume_feats=O.volume_pyramid(vol))
+    ref = O.unet_forward(sd, xin, torch.tensor([301]), ctx, O.volume_pyramid(vol), model_channels=64, num_heads=8, image_size=32, prefix=pre)
+    assert rel_l2(y, ref) < TOL
+
+
+def test_weight_cache_follows_parameter_updates(ops_double, model):
+    m, sd = model
+    st = m.unet_model.unet_model.input_blocks[1][1]
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(1, 64, 32, 32, generator=g)
+    ctx = torch.randn(1, 1, 768, generator=g)
+    y0 = st(x, ctx)
+    with torch.no_grad():
+        st.proj_out.weight.mul_(2.0)
+    y1 = st(x, ctx)
+    with torch.no_grad():
+        st.proj_out.weight.mul_(0.5)
+    assert rel_l2(y1 - x, 2 * (y0 - x) - st.proj_out.bias.view(1, -1, 1, 1)) < 1e-2  # packed weights were rebuilt
+
+
+def test_prepare_batch_matches_reference_layout(model):
+    m, _ = model
+    R, T, f, p = synthetic.gso_rig(8)
+    # un-relative rig: rotate the world so that view 0 is NOT the identity, prepare_batch must undo it
+    Q = torch.linalg.qr(torch.randn(3, 3, generator=torch.Generator().manual_seed(0)))[0]
+    batch = {"latents": torch.randn(9, 4, 32, 32), "clip_embed": torch.randn(9, 1, 768), "R": torch.einsum("ij,bjk->bik", Q, R),
+             "T": T, "f": f, "c": p}
+    cfg = {"input_batch_size": 1, "train_batch_size": 8, "random_views": False}
+    bl, bc, il, ic, cve = m.prepare_batch(batch, cfg)
+    assert bl.shape == (8, 5, 32, 32) and il.shape == (1, 5, 32, 32) and cve.shape == (8, 1, 796)
+    assert float(il[:, 4].abs().max()) == 0.0                         # input depth is zeroed (viewfusion…py:215)
+    assert torch.allclose(ic.R[0], torch.eye(3), atol=1e-5)           # relative to the input view
+    assert torch.allclose(bc.R, R[1:], atol=1e-5)
+    assert torch.allclose(cve[0, 0, 768:777], ic.R.reshape(-1), atol=1e-6)
+    assert torch.allclose(cve[3, 0, 782:791], bc.R[3].reshape(-1), atol=1e-6)
+    assert torch.allclose(cve[3, 0, 794:796], bc.focal_length[3], atol=1e-6)
