@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the multi-view denoising hot path (BASELINE.json metric: UNet denoising steps/sec, N-view, 256^2, DDIM).
+
+    python bench.py [--gpus N --steps K --warmup W]          # this repo's sm_100a path, one JSON line
+    python bench.py --impl reference [...]                   # the reference algorithm on the host CPUs (oracle port)
+
+One *step* = one iteration of DDIMSampler.sample's loop for one scene of `--views` views at 256^2 (32x32x(4+1) latents):
+GridAttn over all views + UNet over the views (x2: classifier-free guidance 2.5, both branches in one batch) + CFG
+combine + DDIM update.  Workload at N=1 = BASELINE.json configs[1]: N=8 views, 1xB200, full-size UNet
+(1.034 B parameters, random-init — no checkpoints offline), D = 1 depth sample per ray, synthetic GSO camera rig.
+
+Multi-GPU (`--gpus G`, one process per GPU under torchrun): `--mode shard` (default) splits the 8 views of ONE scene over
+the G ranks — every rank runs GridAttn for its own query views against all views and the UNet on its own views, then the
+ranks exchange the updated 5-channel latents with one NCCL all-gather per step (strong scaling); `--mode replicas` runs
+one independent scene per rank with no collective (what the reference's demo.py does; weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+F_UNET_GFLOP = 225.1       # per view-pass, 32x32 latents, D=1
+F_GRID_GFLOP = 3.590e-3    # x N^2 S^2 D
+METRIC = "UNet denoising steps/sec (N-view, 256^2, 50-step DDIM)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--mode", default="shard", choices=["shard", "replicas"])
+    ap.add_argument("--views", type=int, default=8)
+    ap.add_argument("--cfg", type=float, default=2.5)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-table", default="", help="write the per-kernel time table (json) here")
+    return ap.parse_args()
+
+
+def step_flops(n_views, S, D, cfg):
+    p = 1 if cfg == 1.0 else 2
+    return (F_GRID_GFLOP * n_views * n_views * S * S * D + p * n_views * F_UNET_GFLOP) * 1e9
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d["bf16_tflops_sustained"], "tflops_burst": d["bf16_tflops"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_step_sample(sd, unet_cfg, sc, de, dn, n_views, D, cfg, query, tab, index):
+    """One bounded sample of a denoising step on the CPU: the oracle (reference algorithm, fp32) for `query` views."""
+    from oracle import mvd_oracle as O
+    t = torch.full((n_views,), int(tab["timesteps"][index]), dtype=torch.long)
+    eps = O.apply_model(sd, sc["x_T"], sc["cams"], sc["input_latents"], sc["in_cams"], sc["clip_v_embed"], t, de, unet_cfg=unet_cfg,
+                        D=D, cfg_scale=cfg, query=query)
+    return O.ddim_update(sc["x_T"][query], eps, tab, index, dn[query])
+
+
+def cpu_arm(args, reps, warmup, model=None):
+    """Reference algorithm on the host cores.  Sample = 2 of the `views` query views per step (UNet x2 CFG for 2 views +
+    GridAttn of 2 query views against all views); every stage is linear in the number of query views, so
+    step time = sample time x views/2."""
+    from common import build_model, state_dict_cpu, synthetic, unet_cfg_of
+    from oracle import mvd_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    n, S, D = args.views, 32, 1
+    m = model if model is not None else build_model(320, 8, D=D, S=S)
+    sd = state_dict_cpu(m)
+    ucfg = unet_cfg_of(m)
+    sc = synthetic.scene_inputs(n, S)
+    de, dn = synthetic.step_noises(n, D, S, 1)
+    tab = O.ddim_tables(sd["scheduler.alphas_cumprod"], 50, 1.0)
+    query = [0, 1]
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + reps):
+            t0 = time.perf_counter()
+            cpu_step_sample(sd, ucfg, sc, de[0], dn[0], n, D, args.cfg, query, tab, 49 - (i % 50))
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    scale = n / len(query)
+    step_s = sum(times) / len(times) * scale
+    return {"value": 1.0 / step_s, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(query)} of {n} query views per step (UNet x2 CFG on 2 views + GridAttn of 2 query views vs all {n}); "
+                      f"step time = {scale:g} x sample time; {len(times)} timed samples, fp32, oracle/mvd_oracle.py"}, step_s
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    reps = max(1, min(args.steps, 6))
+    warm = max(0, min(args.warmup, 1))
+    cb, step_s = cpu_arm(args, reps, warm)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"N={args.views} views 256^2 DDIM step, cfg {args.cfg}, D=1, full-size UNet (BASELINE configs[1])",
+                       "timed_samples": reps, "note": "reference algorithm (CPU port, oracle/) on host cores; bounded sample per step"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 7]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], 0, set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ per-kernel timing
+def kernel_table(prog, stream):
+    """Per-launch device time of every bound call of one step, CUDA events on the launching stream; a spin kernel is
+    queued first so that the host runs ahead of the device and the events bracket back-to-back kernel execution."""
+    calls = prog.calls
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in calls]
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(1.2e8))
+    for c, (e0, e1) in zip(calls, ev):
+        e0.record()
+        c(stream)
+        e1.record()
+    torch.cuda.synchronize()
+    agg = {}
+    for c, (e0, e1) in zip(calls, ev):
+        name = c.meta.get("kernel", c.name.replace("mvd_", ""))
+        a = agg.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        a["calls"] += 1
+        a["ms"] += e0.elapsed_time(e1)
+        a["flops"] += c.meta.get("flops", 0.0)
+        a["bytes"] += c.meta.get("bytes", 0.0)
+    total = sum(a["ms"] for a in agg.values())
+    rows = []
+    for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        rows.append({"kernel": name, "calls": a["calls"], "ms": round(a["ms"], 4), "share": round(a["ms"] / total, 4),
+                     "tflops": round(a["flops"] / (a["ms"] * 1e-3) / 1e12, 2) if a["flops"] else None,
+                     "algo_gb": round(a["bytes"] / 1e9, 4) if a["bytes"] else None})
+    return rows, total
+
+
+# ------------------------------------------------------------------------------------------------ native arm
+def run_native(args):
+    import torch.distributed as dist
+    from common import build_model, synthetic
+    from mvdfusion_b200 import _lib
+    from mvdfusion_b200.mvdfusion.cameras import PerspectiveCameras
+    from mvdfusion_b200.runtime import current_stream
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n, S, D, K, Wm = args.views, 32, 1, args.steps, args.warmup
+    shard = world > 1 and args.mode == "shard"
+
+    model = build_model(320, 8, D=D, S=S, device=dev)
+    if shard:
+        model.shard_views()
+    scene_seed = 0 if (shard or world == 1) else rank
+    sc = synthetic.scene_inputs(n, S, seed=scene_seed)
+    total = K + Wm
+    de1, dn1 = synthetic.step_noises(n, D, S, min(total, 50), seed=1)
+    idx = [i % de1.shape[0] for i in range(total)]
+    de, dn = de1[idx], dn1[idx]
+    rows = torch.stack([model.ddim.step_row(49 - (i % 50), args.cfg) for i in range(total)])
+    cam = lambda c: PerspectiveCameras(c["R"], c["T"], c["f"], c["p"], device=dev)
+    cams, icams = cam(sc["cams"]), cam(sc["in_cams"])
+    plan = model.step_plan(n, S, D, use_cfg=args.cfg != 1.0)
+    stream = current_stream(dev)
+    model.bind_scene(plan, cams, sc["input_latents"].to(dev), icams, sc["clip_v_embed"].to(dev), stream)
+    plan.x.copy_(sc["x_T"].reshape(n, 5, S * S))
+    plan.set_tables(rows, de, dn)
+    use_graph = not args.no_graph
+
+    def one_step():
+        plan.loop_step(stream, use_graph=use_graph)
+        if shard:
+            model.gather_views(plan)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(Wm, 3)):
+        one_step()
+    plan.counter.fill_(Wm)
+    barrier()
+    clocks = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        one_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    finite = bool(torch.isfinite(plan.x).all())
+    scenes = 1 if (shard or world == 1) else world
+    steps_per_s = scenes * K / (ms * 1e-3)
+
+    # ---- end to end through the public sampler API with HOST buffers (pinned): per step H2D of the schedule row and the
+    #      step's noise draws, D2H of the step's x_t
+    model.ddim._make_schedule(50, "uniform", 1.0)
+    K2 = min(K, 50)
+    pin = lambda t: t.contiguous().pin_memory()
+    host = dict(x_T=pin(sc["x_T"]), de=pin(de1), dn=pin(dn1))
+    if K2 != 50:
+        model.ddim._make_schedule([s for s in (50, 25, 20, 10, 8, 5, 4, 2, 1) if s <= K2][0], "uniform", 1.0)
+    K2 = int(model.ddim.ddim_timesteps.shape[0])
+    for _ in range(2):  # warm-up incl. graph capture of the host-streamed step
+        model.ddim.sample(cams, sc["input_latents"].to(dev), icams, sc["clip_v_embed"].to(dev), unconditional_scale=args.cfg, depth=True,
+                          verbose=False, x_T=host["x_T"], depth_eps=host["de"][:K2], ddim_noise=host["dn"][:K2], host_io=True)
+    barrier()
+    t0 = time.perf_counter()
+    lat_h, clip_h = pin(sc["input_latents"]), pin(sc["clip_v_embed"])
+    x_out = model.ddim.sample(cams, lat_h.to(dev, non_blocking=True), icams, clip_h.to(dev, non_blocking=True),
+                              unconditional_scale=args.cfg, depth=True, verbose=False, x_T=host["x_T"], depth_eps=host["de"][:K2],
+                              ddim_noise=host["dn"][:K2], host_io=True)
+    x_host = x_out.cpu()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t)
+    clk = clocks.stop()
+    q = plan.q
+    h2d = 16 * 4 + n * D * S * S * 4 + n * 5 * S * S * 4
+    d2h = q * 5 * S * S * 4
+    e2e = {"value": scenes * K2 / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": K2, "api": "DDIMSampler.sample(host_io=True): pinned-host schedule row + noise draws copied in every step, x_t read back every step"}
+
+    # ---- per-kernel device times of one step (events), roofline of the dominant kernel
+    pk = peaks()
+    roof, ktab = None, None
+    if rank == 0:
+        plan.counter.zero_()
+        ktab, tot_ms = kernel_table(plan._loop_prog, stream)
+        plan.counter.zero_()
+        top = ktab[0]
+        if top["tflops"]:
+            roof = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["tflops"], "peak": pk["tflops"], "unit": "TFLOP/s",
+                    "frac": round(top["tflops"] / pk["tflops"], 4), "traffic": None, "peak_source": f"{pk['source']} (sustained bf16 cuBLAS)",
+                    "launches_per_step": top["calls"], "share_of_step": top["share"],
+                    "note": "achieved = sum of 2MNK over the kernel's launches of one step / sum of their CUDA-event durations (fp16 operands, fp32 accumulate)"}
+        if args.kernel_table:
+            json.dump({"step_ms_sum_of_kernels": tot_ms, "kernels": ktab}, open(args.kernel_table, "w"), indent=1)
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        f_step = step_flops(n, S, D, args.cfg)
+        line = {"metric": METRIC, "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (shard or world == 1) else "weak",
+                "vs_baseline": None, "dtype": "f16 operands / f32 accumulate + f32 residual stream", "data": "synthetic",
+                "config": {"workload": f"N={n} views 256^2 (32x32x5 latents) DDIM step, cfg {args.cfg} (cond+uncond batched), D=1, "
+                                       "full-size UNet 1.034B params random-init + GridAttn (BASELINE configs[1])",
+                           "mode": ("view-sharded, 1 all-gather/step" if shard else ("replicas" if world > 1 else "single GPU")),
+                           "views_per_gpu": q, "cuda_graph": use_graph,
+                           "l2": "no flush: every step streams 2.08 GB of fp16 weights (>> 126 MB L2)"},
+                "e2e": e2e, "gpu_launches": int((plan.kernels_per_step or 0) * K), "kernels_per_step": plan.kernels_per_step,
+                "clocks": clk, "roofline": roof,
+                "step_roofline": {"gflop_per_step": round(f_step / 1e9, 1), "achieved_tflops_per_gpu": round(f_step * steps_per_s / world / 1e12, 2),
+                                  "frac_of_sustained_peak": round(f_step * steps_per_s / world / 1e12 / pk["tflops"], 4)},
+                "kernels": ktab[:8] if ktab else None, "finite": finite and bool(torch.isfinite(x_host).all())}
+        if not args.no_cpu_baseline and world == 1:
+            cb, _ = cpu_arm(args, reps=2, warmup=1, model=model)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -372,13 +372,18 @@ def dit_block(sd, p, x, c, heads):
     return x + g_m.unsqueeze(1) * h
 
 
-def gridattn_tokens(sd, feat, in_feat, zdepth, cams, in_cams, predict_mask, prefix=""):
+def gridattn_tokens(sd, feat, in_feat, zdepth, cams, in_cams, predict_mask, prefix="", query=None):
     """Geometry / gather half of aggregate_features (mvdfusion/view_attn_efficient2.py:269-370).
     feat (V,256,S,S) embedded noisy latents, in_feat (1,256,S,S), zdepth (N,D,S,S).
-    Returns z (V, N, S*S*D, 723) and the world points (N,S,S,D,3)."""
+    Returns z (V, N, S*S*D, 723) and the world points (N,S,S,D,3).
+    query (optional index list): only these views shoot query rays (all V views are still attended over) — the
+    per-rank share of the view-sharded path and the bounded CPU-baseline sample; None = every view, as the reference."""
+    V = zdepth.shape[0]
+    o, d = ray_bundle(cams, zdepth.shape[2])
+    centers_all = cam_center(cams)
+    if query is not None:
+        o, d, zdepth = o[query], d[query], zdepth[query]
     N, D, S, _ = zdepth.shape
-    V = N
-    o, d = ray_bundle(cams, S)
     lengths = zdepth.permute(0, 2, 3, 1)  # (N,S,S,D)  'b n h w -> b (h w) n'
     xyz = o[..., None, :] + lengths[..., :, None] * d[..., None, :]  # (N,S,S,D,3)
     pts = xyz.reshape(1, N * S * S * D, 3)
@@ -391,7 +396,7 @@ def gridattn_tokens(sd, feat, in_feat, zdepth, cams, in_cams, predict_mask, pref
     ref_feat = sample(feat, cams)  # (V,N,HWD,256)
     inp_feat = sample(in_feat, in_cams).expand(V, -1, -1, -1)
 
-    centers = cam_center(cams)
+    centers = centers_all
     ref_dir = (pts.expand(V, -1, -1) - centers[:, None, :]).reshape(V, N, S * S * D, 3)
     ref_depth = harmonic_embedding(torch.linalg.norm(ref_dir, dim=-1, keepdim=True))
     ref_dir = F.normalize(ref_dir, dim=-1)
@@ -399,7 +404,8 @@ def gridattn_tokens(sd, feat, in_feat, zdepth, cams, in_cams, predict_mask, pref
 
     q_dir = F.normalize(d, dim=-1)  # (N,S,S,3)
     q_dir = q_dir.reshape(1, N, S * S, 1, 3).expand(1, N, S * S, D, 3).reshape(1, N, S * S * D, 3)
-    q_pl = _plucker(centers[None, :, None, :], q_dir).expand(V, -1, -1, -1)
+    q_centers = centers if query is None else centers[query]
+    q_pl = _plucker(q_centers[None, :, None, :], q_dir).expand(V, -1, -1, -1)
     q_depth = harmonic_embedding(lengths.reshape(1, N, S * S * D, 1)).expand(V, -1, -1, -1)
     z = torch.cat((ref_feat, inp_feat, ref_pl, ref_depth, q_pl, q_depth), dim=-1)
     mask = predict_mask.reshape(V, 1, 1, 1).expand(-1, N, S * S * D, -1)
@@ -407,8 +413,9 @@ def gridattn_tokens(sd, feat, in_feat, zdepth, cams, in_cams, predict_mask, pref
 
 
 def gridattn_forward(sd, noisy_latents, cams, predict_mask, t_embed, t, tables, depth_eps, input_latents, in_cams,
-                     *, D, num_heads=8, depth_scale=2.0, depth_shift=0.5, overwrite_attn_depth=None, prefix=""):
-    """GridAttn.forward + aggregate_features (mvdfusion/view_attn_efficient2.py:269-442) -> (N,S,S,D,768)."""
+                     *, D, num_heads=8, depth_scale=2.0, depth_shift=0.5, overwrite_attn_depth=None, prefix="", query=None):
+    """GridAttn.forward + aggregate_features (mvdfusion/view_attn_efficient2.py:269-442) -> (N,S,S,D,768)
+    (N = len(query) when a query subset is given, see gridattn_tokens)."""
     p = prefix
     N, _, S, _ = noisy_latents.shape
     zdepth = gridattn_depth_samples(noisy_latents, tables, t, depth_eps, D, depth_scale, depth_shift,
@@ -420,8 +427,10 @@ def gridattn_forward(sd, noisy_latents, cams, predict_mask, t_embed, t, tables, 
 
     feat = zemb(noisy_latents)
     in_feat = zemb(input_latents)
-    z, _ = gridattn_tokens(sd, feat, in_feat, zdepth, cams, in_cams, predict_mask)
+    z, _ = gridattn_tokens(sd, feat, in_feat, zdepth, cams, in_cams, predict_mask, query=query)
     V = z.shape[0]
+    if query is not None:
+        N = len(query)
     x = z.reshape(V, -1, z.shape[-1]).permute(1, 0, 2)  # (P, V, 723)
     x = F.gelu(_linear(sd, p + "pre_layer_b.0", x))
     c = t_embed[:1]
@@ -448,13 +457,16 @@ def mlp_silu(sd, p, x, idx):
 
 
 def apply_model(sd, noisy_latents, cams, input_latents, in_cams, clip_v_embed, t, depth_eps, *, unet_cfg, D,
-                cfg_scale=1.0, prev_depth=None, drop_random=None):
-    """mvdfusion/viewfusion_zero_depth_rgb.py:282-345.  sd uses the ViewFusion state-dict prefixes."""
+                cfg_scale=1.0, prev_depth=None, drop_random=None, query=None):
+    """mvdfusion/viewfusion_zero_depth_rgb.py:282-345.  sd uses the ViewFusion state-dict prefixes.
+    query: optional subset of views to denoise (GridAttn still attends over all views; UNet runs on the subset)."""
     B = noisy_latents.shape[0]
     tables = {k: sd["scheduler." + k] for k in ("sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod")}
     t_embed = mlp_silu(sd, "time_embed", timestep_embedding(t, 256), (0, 2))
     feat = gridattn_forward(sd, noisy_latents, cams, torch.ones(B), t_embed, t, tables, depth_eps, input_latents,
-                            in_cams, D=D, overwrite_attn_depth=prev_depth, prefix="view_attn.")
+                            in_cams, D=D, overwrite_attn_depth=prev_depth, prefix="view_attn.", query=query)
+    if query is not None:
+        noisy_latents, clip_v_embed, B = noisy_latents[query], clip_v_embed[query], len(query)
     x_concat = input_latents.expand(B, -1, -1, -1)
     clip_embed = mlp_silu(sd, "cc_projection", clip_v_embed, (0, 2, 4))
     pre = "unet_model.unet_model."
