@@ -52,8 +52,10 @@ long long mvd_launch_count(void);
  *        out = value * gelu(gate); external/sd1/ldm/modules/attention.py:42-44)
  *   out_mode: F32 / F16 row-major [M, ldc]; QKV_HEADS scatters q,k into [img*heads + h, seq, dpad]
  *        and v transposed into [img*heads + h, dpad, seq] for mvd_attn_self_f16.
- *   split_k > 1: partial sums are red.add'ed into an fp32 output the library zeroes first
- *        (F32 out, act NONE only).
+ *   split_k: K is cut into slices that run as separate work units; each slice parks its fp32 partial tile in
+ *        `splitk_ws`, the slice finishing last sums them and runs the epilogue (any act / out_mode except GEGLU).
+ *   The kernel is persistent (one CTA per SM walks the tile list) and keeps two accumulators in TMEM so that the
+ *   epilogue of one tile overlaps the MMAs of the next; outputs leave through swizzled smem + TMA bulk stores.
  * ---------------------------------------------------------------------------------------------- */
 enum { MVD_A_ROWMAJOR = 0, MVD_A_CONV3X3 = 1 };
 enum { MVD_ACT_NONE = 0, MVD_ACT_GELU = 1, MVD_ACT_SILU = 2, MVD_ACT_GEGLU = 3 };
@@ -81,8 +83,11 @@ typedef struct mvd_gemm_args {
   void* out_k;
   void* out_vt;
   int32_t heads, dhead, dpad, seq;
-  int32_t split_k;     /* >= 1 */
-  int32_t tile_n;      /* 0 = auto; 64, 128 or 256 */
+  int32_t split_k;     /* 0 = auto, 1 = off, > 1 = that many K slices (needs splitk_ws) */
+  int32_t tile_n;      /* 0 = auto; else a multiple of 32 in [32, 256], or a multiple of 16 >= N (GEGLU: a multiple of 64 dividing N) */
+  void* splitk_ws;     /* caller-owned split-K workspace or NULL; MUST be zero-filled once before its first use
+                          (the first 16 KB are self-resetting tile semaphores, the rest holds fp32 partial tiles) */
+  long long splitk_ws_bytes;
 } mvd_gemm_args;
 
 int mvd_gemm_f16(const mvd_gemm_args* args, void* stream);

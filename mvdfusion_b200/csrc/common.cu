@@ -51,6 +51,24 @@ static int encode(CUtensorMap* out, const void* base, int rank, const cuuint64_t
   return MVD_OK;
 }
 
+int make_tmap_2d_ex(CUtensorMap* out, const void* base, int elem_bytes, long long cols, long long rows, long long ld,
+                    int box_cols, int box_rows, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode();
+  if (fn == nullptr) return set_error(MVD_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(MVD_ECUDA, "cuTensorMapEncodeTiled(2d_ex) failed (CUresult %d, dims %lld/%lld ld %lld box %d/%d)",
+                     static_cast<int>(r), cols, rows, ld, box_cols, box_rows);
+  return MVD_OK;
+}
+
 int make_tmap_2d(CUtensorMap* out, const void* base, int cols, int rows, int ld, int box_cols, int box_rows) {
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
@@ -79,5 +97,5 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, int n, int h, int w, int 
 }  // namespace mvd
 
 extern "C" const char* mvd_last_error(void) { return mvd::g_err; }
-extern "C" int mvd_abi_version(void) { return 2; }
+extern "C" int mvd_abi_version(void) { return 3; }
 extern "C" long long mvd_launch_count(void) { return mvd::g_launches.load(std::memory_order_relaxed); }

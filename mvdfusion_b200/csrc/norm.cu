@@ -10,67 +10,111 @@
 namespace mvd {
 
 // ---------------------------------------------------------------------------- GroupNorm
-// stats[img][group] = {sum, sumsq} in double (zeroed by the host wrapper first)
+// Thread mapping shared by both passes: a block is `rows` x (C/4) threads; thread (row, cq) owns channels 4cq..4cq+3 and
+// walks pixels row, row+rows, ... of its block's pixel range, so every load is a float4 and a warp reads contiguous
+// memory.  stats[img][group] = {sum, sumsq} in double (zeroed by the host wrapper first).
 __global__ void gn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, int hw, int C, int cpg,
-                                int pix_per_block) {
-  __shared__ double s_sum[32], s_sq[32];
+                                int pix_per_block, int rows) {
+  extern __shared__ float gn_sm[];  // [rows][C] sums, then [rows][C] sums of squares
+  const int cq4 = C >> 2;
+  const int cq = threadIdx.x % cq4;
+  const int row = threadIdx.x / cq4;
   const int img = blockIdx.y;
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(hw, p0 + pix_per_block);
-  if (threadIdx.x < 32) {
-    s_sum[threadIdx.x] = 0.0;
-    s_sq[threadIdx.x] = 0.0;
-  }
-  __syncthreads();
-  const float* base = x + (static_cast<size_t>(img) * hw) * C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f, q = 0.f;
-    for (int p = p0; p < p1; ++p) {
-      const float v = __ldg(base + static_cast<size_t>(p) * C + c);
-      s += v;
-      q = fmaf(v, v, q);
+  const float4* base = reinterpret_cast<const float4*>(x + static_cast<size_t>(img) * hw * C) + cq;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  int p = p0 + row;
+  for (; p + 3 * rows < p1; p += 4 * rows) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(base + static_cast<size_t>(p + u * rows) * cq4);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
+      q[0] = fmaf(v[u].x, v[u].x, q[0]); q[1] = fmaf(v[u].y, v[u].y, q[1]);
+      q[2] = fmaf(v[u].z, v[u].z, q[2]); q[3] = fmaf(v[u].w, v[u].w, q[3]);
     }
-    const int g = c / cpg;
-    atomicAdd(&s_sum[g], static_cast<double>(s));
-    atomicAdd(&s_sq[g], static_cast<double>(q));
+  }
+  for (; p < p1; p += rows) {
+    const float4 v = __ldg(base + static_cast<size_t>(p) * cq4);
+    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
+  }
+  float* ssum = gn_sm;
+  float* ssq = gn_sm + rows * C;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    ssum[row * C + cq * 4 + k] = s[k];
+    ssq[row * C + cq * 4 + k] = q[k];
   }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    double* dst = stats + (static_cast<size_t>(img) * 32 + threadIdx.x) * 2;
-    atomicAdd(dst, s_sum[threadIdx.x]);
-    atomicAdd(dst + 1, s_sq[threadIdx.x]);
+  // 32 groups x 8 lanes: lane l of group g sums channels g*cpg + l, l+8, ... over all rows
+  const int g = threadIdx.x >> 3, l = threadIdx.x & 7;
+  if (g < 32) {
+    double a = 0.0, b = 0.0;
+    for (int c = l; c < cpg; c += 8)
+      for (int rr = 0; rr < rows; ++rr) {
+        a += static_cast<double>(ssum[rr * C + g * cpg + c]);
+        b += static_cast<double>(ssq[rr * C + g * cpg + c]);
+      }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o, 8);
+      b += __shfl_xor_sync(0xffffffffu, b, o, 8);
+    }
+    if (l == 0) {
+      double* dst = stats + (static_cast<size_t>(img) * 32 + g) * 2;
+      atomicAdd(dst, a);
+      atomicAdd(dst + 1, b);
+    }
   }
 }
 
 __global__ void gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ y,
-                                int hw, int C, int cpg, float eps, int apply_silu, size_t total4) {
-  const double inv_cnt = 1.0 / (static_cast<double>(hw) * cpg);
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t e = i * 4;
-    const int c = static_cast<int>(e % C);
-    const int img = static_cast<int>(e / (static_cast<size_t>(hw) * C));
-    const float4 v = *reinterpret_cast<const float4*>(x + e);
-    float in[4] = {v.x, v.y, v.z, v.w};
-    float out[4];
+                                int hw, int C, int cpg, float eps, int apply_silu, int pix_per_block, int rows) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int cq4 = C >> 2;
+  const int cq = threadIdx.x % cq4;
+  const int row = threadIdx.x / cq4;
+  const int img = blockIdx.y;
+  if (threadIdx.x < 32) {
+    const double inv_cnt = 1.0 / (static_cast<double>(hw) * cpg);
+    const double* st = stats + (static_cast<size_t>(img) * 32 + threadIdx.x) * 2;
+    const double mean = st[0] * inv_cnt;
+    const double var = fmax(st[1] * inv_cnt - mean * mean, 0.0);
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = rsqrtf(static_cast<float>(var) + eps);
+  }
+  __syncthreads();
+  float sc[4], sh[4];  // y = x * sc + sh
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int g = (c + k) / cpg;
-      const double* st = stats + (static_cast<size_t>(img) * 32 + g) * 2;
-      const double mean = st[0] * inv_cnt;
-      const double var = fmax(st[1] * inv_cnt - mean * mean, 0.0);
-      const float rstd = rsqrtf(static_cast<float>(var) + eps);
-      float t = (in[k] - static_cast<float>(mean)) * rstd * __ldg(gamma + c + k) + __ldg(beta + c + k);
-      if (apply_silu) t = t / (1.f + expf(-t));
-      out[k] = t;
+  for (int k = 0; k < 4; ++k) {
+    const int c = cq * 4 + k;
+    const int g = c / cpg;
+    const float ga = __ldg(gamma + c);
+    sc[k] = s_rstd[g] * ga;
+    sh[k] = __ldg(beta + c) - s_mean[g] * s_rstd[g] * ga;
+  }
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(hw, p0 + pix_per_block);
+  const size_t img_off = static_cast<size_t>(img) * hw * cq4;
+  const float4* src = reinterpret_cast<const float4*>(x) + img_off + cq;
+  uint2* dst = reinterpret_cast<uint2*>(y) + img_off + cq;
+  for (int p = p0 + row; p < p1; p += rows) {
+    const float4 v = __ldg(src + static_cast<size_t>(p) * cq4);
+    float o[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
+    if (apply_silu) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = o[k] / (1.f + __expf(-o[k]));
     }
-    __half2 h0 = __floats2half2_rn(out[0], out[1]);
-    __half2 h1 = __floats2half2_rn(out[2], out[3]);
+    __half2 h0 = __floats2half2_rn(o[0], o[1]);
+    __half2 h1 = __floats2half2_rn(o[2], o[3]);
     uint2 u;
     u.x = *reinterpret_cast<uint32_t*>(&h0);
     u.y = *reinterpret_cast<uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(y + e) = u;
+    dst[static_cast<size_t>(p) * cq4] = u;
   }
 }
 
@@ -151,20 +195,26 @@ extern "C" int mvd_groupnorm_f32_f16(const float* x, const float* gamma, const f
   if (n_img <= 0 || hw <= 0 || C <= 0 || (C % 32) != 0 || (C & 3) != 0)
     return set_error(MVD_EINVAL, "mvd_groupnorm_f32_f16: C must be a multiple of 32");
   const int cpg = C / 32;
+  if (C > 4096) return set_error(MVD_EINVAL, "mvd_groupnorm_f32_f16: C must be <= 4096");
   MVD_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, static_cast<size_t>(n_img) * 32 * 2 * sizeof(double), stream));
-  // enough blocks to cover the machine: ~ 148*4 blocks in total
+  const int cq4 = C / 4;
+  int rows = 512 / cq4;
+  if (rows < 1) rows = 1;
+  if (rows > hw) rows = hw;
+  if (rows * cq4 < 256) rows = (256 + cq4 - 1) / cq4;  // the group reduction needs 256 threads
+  const int threads = rows * cq4;
+  // enough blocks to cover the machine (~4 per SM), at least 4 pixels per thread
   int chunks = (592 + n_img - 1) / n_img;
-  if (chunks > hw) chunks = hw;
+  const int max_chunks = (hw + 4 * rows - 1) / (4 * rows);
+  if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   const int ppb = (hw + chunks - 1) / chunks;
   chunks = (hw + ppb - 1) / ppb;
-  gn_stats_kernel<<<dim3(chunks, n_img), 256, 0, stream>>>(x, static_cast<double*>(stats_ws), hw, C, cpg, ppb);
+  const size_t sm = static_cast<size_t>(2) * rows * C * sizeof(float);
+  gn_stats_kernel<<<dim3(chunks, n_img), threads, sm, stream>>>(x, static_cast<double*>(stats_ws), hw, C, cpg, ppb, rows);
   count_launch();
-  const size_t total4 = static_cast<size_t>(n_img) * hw * C / 4;
-  int blocks = static_cast<int>((total4 + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  gn_apply_kernel<<<blocks, 256, 0, stream>>>(x, static_cast<const double*>(stats_ws), gamma, beta,
-                                              static_cast<__half*>(y), hw, C, cpg, eps, apply_silu, total4);
+  gn_apply_kernel<<<dim3(chunks, n_img), threads, 0, stream>>>(x, static_cast<const double*>(stats_ws), gamma, beta,
+                                                             static_cast<__half*>(y), hw, C, cpg, eps, apply_silu, ppb, rows);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

@@ -21,6 +21,8 @@ NUM_SMS = 148
 Z_CH = 256        # GridAttn z_embedder width (mvdfusion/view_attn_efficient2.py:151)
 TOKEN_LD = 736    # 723-d GridAttn token rounded up to a multiple of 16
 CTX_DIM = 768
+SPLITK_WS_BYTES = 64 << 20
+GEGLU_TILE = 256  # value | gate column interleave period of the packed GEGLU weights (= the GEMM tile width)
 
 
 def _round_up(x, m):
@@ -178,6 +180,7 @@ class Builder:
         self.arena = arena if arena is not None else Arena(ops)
         self._qkv_bufs = {}
         self._stats = None
+        self._ws = None
         self.heads = 8
 
     # -- buffers
@@ -204,20 +207,20 @@ class Builder:
             self._qkv_bufs[key] = tuple(self.ops.zeros((n,), torch.float16) for _ in range(3))
         return self._qkv_bufs[key]
 
-    @staticmethod
-    def split_k_for(M, N, K, tile_n=128):
-        tiles = math.ceil(M / 128) * math.ceil(N / tile_n)
-        kb = math.ceil(K / 64)
-        if tiles >= NUM_SMS or kb < 8:
-            return 1
-        return max(1, min(math.ceil(2 * NUM_SMS / tiles), kb // 4, 32))
-
     # -- primitive emitters
+    def splitk_ws(self):
+        """Zero-initialised split-K workspace shared by every GEMM of the program (calls run in stream order; the tile
+        semaphores at its head reset themselves)."""
+        if self._ws is None:
+            self._ws = self.ops.zeros((SPLITK_WS_BYTES,), torch.uint8)
+        return self._ws
+
     def gemm(self, A, Wt, out, M, N, K, *, allow_split=False, **kw):
-        split = 1
-        if allow_split and out.dtype == torch.float32 and kw.get("act", ACT_NONE) == ACT_NONE and kw.get("colscale") is None:
-            split = self.split_k_for(M, N, K)
-        self.prog.append(self.ops.gemm(A, Wt, out, M, N, K, split_k=split, **kw))
+        # split_k = 0 lets the library cut K when the tile grid cannot fill the machine (small-M, weight-bound layers)
+        if allow_split and kw.get("act", ACT_NONE) != ACT_GEGLU:
+            self.prog.append(self.ops.gemm(A, Wt, out, M, N, K, split_k=0, ws=self.splitk_ws(), **kw))
+        else:
+            self.prog.append(self.ops.gemm(A, Wt, out, M, N, K, split_k=1, **kw))
 
     def groupnorm(self, x, p, n_img, hw, C, eps, silu):
         """GroupNorm32(32, C) (+SiLU) -> fp16 operand.  util.py:200-217 / attention.py:76-77"""
@@ -321,9 +324,9 @@ class Builder:
         """x = ff(norm3(x)) + x with the GEGLU fused into the first GEMM's epilogue.  attention.py:37-64,222"""
         ln = self.layernorm(h, norm, M, C)
         inner = 4 * C
-        wg, bg = self.W.geglu(p + ".net.0.proj")
+        wg, bg = self.W.geglu(p + ".net.0.proj", GEGLU_TILE)
         g = self.t16(M, inner)
-        self.gemm(ln, wg, g, M, 2 * inner, C, bias=bg, act=ACT_GEGLU, tile_n=128, ldc=inner)
+        self.gemm(ln, wg, g, M, 2 * inner, C, bias=bg, act=ACT_GEGLU, tile_n=GEGLU_TILE, ldc=inner)
         self.free(ln)
         h2 = self.t32(M, C)
         self.gemm(g, self.W.lin(p + ".net.2.weight"), h2, M, C, inner, allow_split=True, bias=self.W.f32(p + ".net.2.bias"),

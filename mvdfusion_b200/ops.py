@@ -73,7 +73,7 @@ class NativeOps:
 
     # ------------------------------------------------------------------ GEMM / conv
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
-             colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0):
+             colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None):
         g = _lib.GemmArgs()
         g.M, g.N, g.K = M, N, K
         g.A = _ptr(A, torch.float16)
@@ -103,7 +103,10 @@ class NativeOps:
             g.ldc = ldc if ldc is not None else out.shape[-1]
         g.split_k = split_k
         g.tile_n = tile_n
-        keep = (g, A, Wt, out, bias, rowbias, colscale, residual, qkv)
+        if ws is not None:
+            g.splitk_ws = _ptr(ws, torch.uint8)
+            g.splitk_ws_bytes = ws.numel()
+        keep = (g, A, Wt, out, bias, rowbias, colscale, residual, qkv, ws)
         n_out = N // 2 if act == ACT_GEGLU else N
         a_bytes = (conv[0] * conv[1] * conv[2] * conv[3] if conv is not None else M * K) * 2
         o_bytes = M * n_out * (4 if (qkv is None and out.dtype == torch.float32) else 2)

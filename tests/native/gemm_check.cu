@@ -139,6 +139,13 @@ static void run(const Case& c) {
   g.residual = dres; g.ldr = N;
   g.act = c.act; g.out_mode = c.out_mode;
   g.split_k = c.split_k; g.tile_n = c.tile_n;
+  static void* ws = nullptr;            // split-K workspace: zero-filled once, semaphores reset themselves
+  const size_t ws_bytes = 32u << 20;
+  if (ws == nullptr) {
+    CK(cudaMalloc(&ws, ws_bytes));
+    CK(cudaMemset(ws, 0, ws_bytes));
+  }
+  g.splitk_ws = ws; g.splitk_ws_bytes = static_cast<long long>(ws_bytes);
 
   double max_err = 0, max_ref = 0;
   size_t bad = 0, total = 0;
@@ -209,7 +216,7 @@ static void run(const Case& c) {
       for (size_t i = 0; i < nout; ++i) out[i] = __half2float(oh[i]);
     }
     const double tol = c.out_mode == MVD_OUT_F32 ? tol32 : tol16;
-    const int bn = c.tile_n ? c.tile_n : (N <= 64 ? 64 : 128);
+    const int bn = c.tile_n ? c.tile_n : 256;  // GEGLU default tile
     for (int m = 0; m < M; ++m)
       for (int n = 0; n < No; ++n) {
         double want;
@@ -249,7 +256,7 @@ int main(int argc, char** argv) {
   { Case c; c.name = "bn256 512x512x1280 rowbias"; c.M = 512; c.N = 512; c.K = 1280; c.tile_n = 256; c.rowbias = true; c.rows_per_group = 64; cases.push_back(c); }
   { Case c; c.name = "f16 gelu 384x256x256"; c.M = 384; c.N = 256; c.K = 256; c.bias = true; c.act = MVD_ACT_GELU; c.out_mode = MVD_OUT_F16; cases.push_back(c); }
   { Case c; c.name = "f16 silu bn64 130x64x128"; c.M = 130; c.N = 64; c.K = 128; c.act = MVD_ACT_SILU; c.out_mode = MVD_OUT_F16; cases.push_back(c); }
-  { Case c; c.name = "geglu 256x512x320"; c.M = 256; c.N = 512; c.K = 320; c.bias = true; c.act = MVD_ACT_GEGLU; c.out_mode = MVD_OUT_F16; cases.push_back(c); }
+  { Case c; c.name = "geglu bn128 256x512x320"; c.M = 256; c.N = 512; c.K = 320; c.bias = true; c.act = MVD_ACT_GEGLU; c.out_mode = MVD_OUT_F16; c.tile_n = 128; cases.push_back(c); }
   { Case c; c.name = "geglu bn256 256x1024x320"; c.M = 256; c.N = 1024; c.K = 320; c.bias = true; c.act = MVD_ACT_GEGLU; c.out_mode = MVD_OUT_F16; c.tile_n = 256; cases.push_back(c); }
   { Case c; c.name = "splitk4 128x256x2048 bias+res"; c.M = 128; c.N = 256; c.K = 2048; c.split_k = 4; c.bias = c.residual = true; cases.push_back(c); }
   { Case c; c.name = "splitk3 200x130x1000"; c.M = 200; c.N = 130; c.K = 1000; c.split_k = 3; c.lda_pad = 0; cases.push_back(c); }
@@ -262,6 +269,13 @@ int main(int argc, char** argv) {
   { Case c; c.name = "conv 1x64x64x64->64"; c.a_mode = MVD_A_CONV3X3; c.n_img = 1; c.H = c.W = 64; c.C = 64; c.N = 64; c.K = 9 * 64; c.M = 4096; cases.push_back(c); }
   { Case c; c.name = "qkv heads 2x64 d40"; c.M = 128; c.N = 3 * 8 * 40; c.K = 320; c.out_mode = MVD_OUT_QKV_HEADS; c.heads = 8; c.dhead = 40; c.dpad = 64; c.seq = 64; cases.push_back(c); }
   { Case c; c.name = "qkv heads 3x16 d160"; c.M = 48; c.N = 3 * 8 * 160; c.K = 1280; c.out_mode = MVD_OUT_QKV_HEADS; c.heads = 8; c.dhead = 160; c.dpad = 192; c.seq = 16; cases.push_back(c); }
+  { Case c; c.name = "persistent 20480x320x320 bias+res"; c.M = 20480; c.N = 320; c.K = 320; c.bias = c.residual = true; cases.push_back(c); }
+  { Case c; c.name = "persistent f16 20000x960x320"; c.M = 20000; c.N = 960; c.K = 320; c.out_mode = MVD_OUT_F16; c.bias = true; cases.push_back(c); }
+  { Case c; c.name = "auto-split 256x1280x11520 bias+res"; c.M = 256; c.N = 1280; c.K = 11520; c.split_k = 0; c.bias = c.residual = true; cases.push_back(c); }
+  { Case c; c.name = "auto-split gelu f16 1024x1280x1280"; c.M = 1024; c.N = 1280; c.K = 1280; c.split_k = 0; c.bias = true; c.act = MVD_ACT_GELU; c.out_mode = MVD_OUT_F16; cases.push_back(c); }
+  { Case c; c.name = "split16 rowbias 130x640x8192"; c.M = 130; c.N = 640; c.K = 8192; c.split_k = 16; c.rowbias = true; c.rows_per_group = 16; cases.push_back(c); }
+  { Case c; c.name = "conv 16x8x8x1280->1280 auto-split res"; c.a_mode = MVD_A_CONV3X3; c.n_img = 16; c.H = c.W = 8; c.C = 1280; c.N = 1280; c.K = 9 * 1280; c.M = 1024; c.split_k = 0; c.bias = c.residual = true; cases.push_back(c); }
+  { Case c; c.name = "geglu 4096x2560x320"; c.M = 4096; c.N = 2560; c.K = 320; c.bias = true; c.act = MVD_ACT_GEGLU; c.out_mode = MVD_OUT_F16; cases.push_back(c); }
   for (size_t i = 0; i < cases.size(); ++i)
     if (only < 0 || only == static_cast<int>(i)) run(cases[i]);
   printf("%s (%d failing)\n", g_fail ? "GEMM CHECK FAILED" : "GEMM CHECK PASSED", g_fail);

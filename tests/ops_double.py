@@ -44,7 +44,7 @@ class TorchOpsDouble:
 
     # ------------------------------------------------------------------ GEMM / conv
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
-             colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0):
+             colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None):
         assert A.dtype == torch.float16 and Wt.dtype == torch.float16
         ldw_ = ldw if ldw is not None else Wt.shape[-1]
 
@@ -72,7 +72,7 @@ class TorchOpsDouble:
             elif act == ACT_SILU:
                 acc = F.silu(acc)
             elif act == ACT_GEGLU:
-                bn = tile_n if tile_n else (64 if N <= 64 else 128)
+                bn = tile_n if tile_n else 256
                 t = acc.reshape(M, N // bn, bn)
                 acc = (t[..., : bn // 2] * F.gelu(t[..., bn // 2:])).reshape(M, N // 2)
             if colscale is not None:

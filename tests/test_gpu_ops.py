@@ -47,7 +47,8 @@ def rnd(*shape, dtype=torch.float32, seed=0, scale=1.0):
     return (torch.randn(*shape, generator=g) * scale).to(dtype)
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 320, 320), (1024, 1280, 5120), (130, 5, 2880), (2048, 768, 256)])
+@pytest.mark.parametrize("M,N,K", [(256, 320, 320), (1024, 1280, 5120), (130, 5, 2880), (2048, 768, 256), (32768, 320, 320),
+                                   (16384, 640, 2560), (300, 130, 736)])
 def test_gemm_plain_bias_residual(nat, dbl, M, N, K):
     t = {"A": rnd(M, K, dtype=torch.float16), "W": rnd(N, K, dtype=torch.float16, seed=1, scale=K ** -0.5),
          "bias": rnd(N, seed=2), "res": rnd(M, N, seed=3), "out": torch.zeros(M, N)}
@@ -57,16 +58,18 @@ def test_gemm_plain_bias_residual(nat, dbl, M, N, K):
 def test_gemm_splitk_rowbias(nat, dbl):
     M, N, K = 256, 1280, 11520
     t = {"A": rnd(M, K, dtype=torch.float16), "W": rnd(N, K, dtype=torch.float16, seed=1, scale=K ** -0.5),
-         "rb": rnd(4, N, seed=2), "res": rnd(M, N, seed=3), "out": torch.zeros(M, N)}
-    run_both(nat, dbl, "gemm", t, ["out"], "A", "W", "out", M, N, K, rowbias="rb", rows_per_group=64, residual="res", ldr=N,
-             split_k=8)
+         "rb": rnd(4, N, seed=2), "res": rnd(M, N, seed=3), "out": torch.zeros(M, N), "ws": torch.zeros(32 << 20, dtype=torch.uint8)}
+    for split in (8, 0, 15):  # explicit, automatic, and a slice count that does not divide the k-blocks
+        run_both(nat, dbl, "gemm", t, ["out"], "A", "W", "out", M, N, K, rowbias="rb", rows_per_group=64, residual="res", ldr=N,
+                 split_k=split, ws="ws")
 
 
 def test_gemm_geglu_f16(nat, dbl):
     M, C = 512, 320
     t = {"A": rnd(M, C, dtype=torch.float16), "W": rnd(8 * C, C, dtype=torch.float16, seed=1, scale=C ** -0.5),
          "bias": rnd(8 * C, seed=2, scale=0.1), "out": torch.zeros(M, 4 * C, dtype=torch.float16)}
-    run_both(nat, dbl, "gemm", t, ["out"], "A", "W", "out", M, 8 * C, C, bias="bias", act=OPS.ACT_GEGLU, tile_n=128, ldc=4 * C)
+    for tile in (256, 128):
+        run_both(nat, dbl, "gemm", t, ["out"], "A", "W", "out", M, 8 * C, C, bias="bias", act=OPS.ACT_GEGLU, tile_n=tile, ldc=4 * C)
 
 
 def test_gemm_gelu_colscale(nat, dbl):
@@ -84,9 +87,9 @@ def test_conv3x3(nat, dbl, n, H, Cin, Cout):
     M = n * H * H
     ldc = 8 if Cout == 5 else Cout
     t = {"A": rnd(M, Cin, dtype=torch.float16), "W": rnd(Cout, 9 * Cin, dtype=torch.float16, seed=1, scale=(9 * Cin) ** -0.5),
-         "bias": rnd(Cout, seed=2), "out": torch.zeros(M, ldc)}
+         "bias": rnd(Cout, seed=2), "out": torch.zeros(M, ldc), "ws": torch.zeros(32 << 20, dtype=torch.uint8)}
     run_both(nat, dbl, "gemm", t, ["out"], "A", "W", "out", M, Cout, 9 * Cin, conv=(n, H, H, Cin), bias="bias", ldc=ldc,
-             split_k=(4 if H == 4 else 1))
+             split_k=(0 if H <= 8 else 1), ws="ws")
 
 
 @pytest.mark.parametrize("n,seq,C", [(2, 1024, 320), (2, 256, 640), (3, 64, 1280), (2, 16, 1280), (2, 1024, 64)])
