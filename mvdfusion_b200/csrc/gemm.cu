@@ -3,18 +3,20 @@
 //   acc[m, n] = sum_k A[m, k] * W[n, k]     fp16 operands (K-major, 128B-swizzled smem tiles via TMA),
 //                                           fp32 accumulators in TMEM, fused epilogues.
 //
-// One CTA per SM loops over work units (output tile 128 x BN, optionally one K-slice of it):
+// One CTA (384 threads) per SM loops over work units (output tile 128 x BN, optionally one K-slice of it):
 //   warp 0      : TMA producer (one elected lane) — A tile + W tile per 64-wide k-block into a `stages`-deep ring
 //   warp 1      : TMEM allocator + UMMA issuer (one elected lane); tcgen05.commit releases ring slots and
 //                 publishes the finished accumulator.  TWO accumulators live in TMEM, so the MMA of unit j+1
 //                 overlaps the epilogue of unit j.
-//   warps 4..7  : epilogue — tcgen05.ld (warp w owns TMEM lanes 32*(w%4)..), bias / per-image row bias /
-//                 GELU / SiLU / GEGLU / adaLN gate / residual, then a 128B-swizzled smem staging tile and a
-//                 TMA bulk store (coalesced; TMA clips the M / N tails).  The residual tile is TMA-loaded
-//                 into smem two chunks ahead.  QKV mode scatters q, k, v^T per head directly.
-// Split-K (small-M, weight-bound layers): every K-slice writes its fp32 partial tile to a workspace in a
-//   lane-coalesced layout and bumps a per-tile semaphore; the slice that arrives last adds the others'
-//   partials to its own TMEM accumulator and runs the normal epilogue (no atomics on the output, no memset).
+//   warps 4..11 : two epilogue warpgroups; each owns every other 32-column chunk of a tile.  Per chunk:
+//                 phase A  tcgen05.ld (thread = tile row) -> 128B-swizzled fp32 staging tile in smem
+//                          (GEGLU multiplies value * gelu(gate) here; the v^T part of a QKV scatter leaves from here),
+//                 phase B  thread = (row, 16-byte segment): bias / per-image row bias / GELU / SiLU / adaLN gate /
+//                          residual / split-K partials, all read and written with coalesced 16-byte accesses.
+//                 The residual of the NEXT chunk is already in flight (registers) while this one is processed.
+// Split-K (small-M, weight-bound layers; all slices of a tile are co-resident): slice s parks the chunks it does not
+//   own in a workspace, bumps the tile semaphore and waits for its siblings; then every slice reduces and finishes the
+//   chunks it owns (chunk c belongs to slice c % split) — the reduction is spread over the slices, no atomics on data.
 // For MVD_A_CONV3X3 the A tile of k-block (tap, c-block) is a 4-D TMA box (64 ch, tw, th, tn) of the NHWC image
 //   shifted by (kx-1, ky-1); out-of-bounds pixels are zero-filled by TMA == zero padding; im2col never exists.
 //
@@ -27,12 +29,13 @@ namespace mvd {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int STG_BYTES = 128 * 128;  // one staging chunk: 128 rows x 32 fp32 (or 32 fp16 in the first 64 B of... see below)
+constexpr int STG_BYTES = 128 * 128;  // one staging chunk: 128 rows x 32 fp32, 128B-swizzled
 constexpr int MAX_STAGES = 8;
-constexpr int EPI_THREADS = 128;
-constexpr int WS_COUNTER_BYTES = 16384;  // 4096 tile semaphores at the head of the split-K workspace
+constexpr int WG_THREADS = 128;
+constexpr int EPI_THREADS = 256;
+constexpr int WS_COUNTER_BYTES = 16384;  // 2048 x {arrive, done} tile semaphores at the head of the split-K workspace
 
 struct GemmKParams {
   int M, N;
@@ -55,8 +58,9 @@ struct GemmKParams {
   void* out_k;
   void* out_vt;
   int heads, dhead, dpad, seq;
-  int use_out_tma, use_res_tma;
-  float4* ws;
+  int vec_bias, vec_rowbias, vec_colscale, vec_res, vec_out;  // 16-byte (8-byte for fp16 out) accesses are legal
+  int qkv_direct;                                             // QKV scatter of every chunk from phase A (generic geometry)
+  float* ws;
   int* counters;
   int acc_stride, tmem_cols;
 };
@@ -76,9 +80,6 @@ __device__ __forceinline__ void store8_f16(__half* dst, const float* v) {
 __device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ void sts_v4_u32(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -87,6 +88,31 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// 4 consecutive floats starting at p; `nvalid` of them exist (>= 4 -> all); vector access only when `vec`
+__device__ __forceinline__ float4 ldg4(const float* p, bool vec, int nvalid) {
+  if (vec && nvalid >= 4) return __ldg(reinterpret_cast<const float4*>(p));
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (nvalid > 0) r.x = __ldg(p);
+  if (nvalid > 1) r.y = __ldg(p + 1);
+  if (nvalid > 2) r.z = __ldg(p + 2);
+  if (nvalid > 3) r.w = __ldg(p + 3);
+  return r;
+}
+// same, coherent loads (the residual stream is written by earlier kernels of the same graph)
+__device__ __forceinline__ float4 ld4(const float* p, bool vec, int nvalid) {
+  if (vec && nvalid >= 4) return *reinterpret_cast<const float4*>(p);
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (nvalid > 0) r.x = p[0];
+  if (nvalid > 1) r.y = p[1];
+  if (nvalid > 2) r.z = p[2];
+  if (nvalid > 3) r.w = p[3];
+  return r;
 }
 
 struct Unit {
@@ -118,22 +144,28 @@ __device__ __forceinline__ Unit decode_unit(const GemmKParams& p, int u) {
   return t;
 }
 
+// Epilogue specialisation: ACT / OUT / RES / SPLIT >= 0 fix the activation, output mode, "has residual" and "split-K"
+// at compile time (-1 = decided at run time); VEC = every epilogue access is a full, aligned 16-byte (8-byte fp16)
+// vector, so no tails exist.  The specialised bodies are several times smaller than the generic one, which matters:
+// a warp walks its epilogue code once per chunk, and the generic body does not fit the instruction cache.
+template <int ACT, int OUT, int RES, int SPLIT, bool VEC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const GemmKParams p) {
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+  const int act = ACT >= 0 ? ACT : p.act;
+  const int out_mode = OUT >= 0 ? OUT : p.out_mode;
+  const bool has_res = RES >= 0 ? (RES != 0) : (p.residual != nullptr);
+  const bool is_split = SPLIT >= 0 ? (SPLIT != 0) : (p.split > 1);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = A_BYTES + p.BN * 128;
-  uint8_t* out_stg = smem + p.stages * stage_bytes;  // 2 x STG_BYTES
-  uint8_t* res_stg = out_stg + 2 * STG_BYTES;        // 2 x STG_BYTES (only when use_res_tma)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(res_stg + (p.use_res_tma ? 2 * STG_BYTES : 0));
+  uint8_t* out_stg = smem + p.stages * stage_bytes;                    // 2 warpgroups x 2 x STG_BYTES
+  float* bias_smem = reinterpret_cast<float*>(out_stg + 4 * STG_BYTES);  // 2 x 256 floats (GEGLU tile bias)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_smem + 512);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + MAX_STAGES;
   uint64_t* acc_full = bars + 2 * MAX_STAGES;
   uint64_t* acc_empty = acc_full + 2;
-  uint64_t* res_full = acc_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
-  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -141,8 +173,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.use_out_tma) tma_prefetch_desc(&tmO);
-    if (p.use_res_tma) tma_prefetch_desc(&tmR);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -150,7 +180,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], EPI_THREADS);
-      mbar_init(&res_full[b], 1);
     }
     mbar_fence_init();
   }
@@ -221,223 +250,283 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (128 threads, thread = output row of the tile)
-    const int et = threadIdx.x - 4 * 32;
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const bool geglu = (p.act == MVD_ACT_GEGLU);
-    const int n_out = geglu ? p.N / 2 : p.N;         // output columns
-    const int out_bn = geglu ? p.BN / 2 : p.BN;      // output columns per tile
-    const int nchunks = (out_bn + 31) / 32;  // a single narrow tile (BN < 32, N <= BN) still takes one chunk; TMA / guards clip it
-    const bool f16_out = (p.out_mode == MVD_OUT_F16);
-    const uint32_t stg_row_bytes = f16_out ? 64 : 128;
-    int res_items = 0;  // residual staging items consumed so far (buffer = item & 1, parity = (item >> 1) & 1)
-    int out_items = 0;  // out staging items issued so far
+    // ------------------------------------------------------------ epilogue: 2 warpgroups x 128 threads
+    const int wg = (warp - 4) >> 2;
+    const int q = warp & 3;              // TMEM lane quadrant this warp may read
+    const int et = q * 32 + lane;        // thread within the warpgroup == tile row in phase A
+    const int seg = et & 7;              // phase B: 16-byte segment of the 32-column chunk
+    const int rb = et >> 3;              // phase B: rows rb, rb + 16, ..., rb + 112
+    const int bar_id = 1 + wg;
+    const bool geglu = (act == MVD_ACT_GEGLU);
+    const int n_out = geglu ? p.N / 2 : p.N;       // output columns
+    const int out_bn = geglu ? p.BN / 2 : p.BN;    // output columns per tile
+    const int nchunks = (out_bn + 31) / 32;        // a narrow tile (BN < 32) still takes one chunk; guards clip it
+    const int ws_ld = nchunks * 32;                // leading dimension of one split-K partial tile
+    const uint32_t stg_base = smem_u32(out_stg) + wg * 2 * STG_BYTES;
+    float* sbias = bias_smem + wg * 256;
+    const int inner = p.heads * p.dhead;
+    int n_staged = 0;  // staging buffer toggle
+
+    // ---- phase A of one chunk: TMEM -> registers -> (GEGLU) -> swizzled staging tile, or the direct QKV scatter
+    auto phase_a = [&](const Unit& t, uint32_t taddr, int c, uint32_t stg) -> bool {
+      float v[32];
+      const int oc = t.n_tile * out_bn + c * 32;
+      if (geglu) {
+        float g[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld32(taddr + p.BN / 2 + c * 32, g);
+        tmem_ld_wait();
+        if (p.bias != nullptr) {
+          const uint32_t sv = smem_u32(sbias + c * 32), sg = smem_u32(sbias + p.BN / 2 + c * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bv = lds_v4(sv + i * 16), bg = lds_v4(sg + i * 16);
+            v[4 * i] += bv.x; v[4 * i + 1] += bv.y; v[4 * i + 2] += bv.z; v[4 * i + 3] += bv.w;
+            g[4 * i] += bg.x; g[4 * i + 1] += bg.y; g[4 * i + 2] += bg.z; g[4 * i + 3] += bg.w;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= gelu_erf(g[i]);
+      } else {
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+      }
+      if (out_mode == MVD_OUT_QKV_HEADS && (p.qkv_direct || oc >= 2 * inner)) {
+        // v^T (keys contiguous) wants thread = row: leave straight from the registers
+        const int grow = t.grow0 + et;
+        if (grow < p.M) {
+          const int img = grow / p.seq;
+          const int pos = grow - img * p.seq;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            const int n = oc + i;
+            if (n >= p.N) continue;
+            const int which = n / inner;
+            const int rem = n - which * inner;
+            const int h = rem / p.dhead;
+            const int jj = rem - h * p.dhead;
+            const size_t bh = static_cast<size_t>(img) * p.heads + h;
+            if (which < 2) {
+              __half* base = reinterpret_cast<__half*>(which == 0 ? p.out : p.out_k);
+              store8_f16(base + (bh * p.seq + pos) * p.dpad + jj, v + i);
+            } else {
+              __half* base = reinterpret_cast<__half*>(p.out_vt) + (bh * p.dpad + jj) * p.seq + pos;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) base[static_cast<size_t>(e) * p.seq] = __float2half_rn(v[i + e]);
+            }
+          }
+        }
+        return false;
+      }
+      const uint32_t srow = stg + et * 128;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sts_v4(srow + ((i ^ (et & 7)) << 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      return true;
+    };
+
+    // ---- residual of one chunk, phase-B mapping (issued one chunk ahead; consumed in phase B)
+    float4 rn[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto res_load = [&](int grow0, int oc, int i) -> float4 {
+      const int row = grow0 + rb + 16 * i;
+      const int col = oc + seg * 4;
+      if (row < p.M && col < p.N) return ld4(p.residual + static_cast<size_t>(row) * p.ldr + col, VEC || p.vec_res != 0, VEC ? 4 : p.N - col);
+      return make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+
+    // ---- phase B of one chunk.  part_tile/part_s: split-K partial tiles to add (nullptr = none); nxt_*: next chunk of
+    //      this warpgroup (residual prefetch), nxt_valid = false when there is none.
+    auto phase_b = [&](const Unit& t, int c, uint32_t stg, bool nxt_valid, int nxt_grow0, int nxt_oc) {
+      const int oc = t.n_tile * out_bn + c * 32;
+      const int col = oc + seg * 4;
+      const int nvalid = VEC ? ((n_out - col) > 0 ? 4 : 0) : (n_out - col);  // <= 0: this thread's columns do not exist
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (!geglu && p.bias != nullptr && nvalid > 0) b4 = ldg4(p.bias + col, VEC || p.vec_bias != 0, nvalid);
+      if (p.colscale != nullptr && nvalid > 0) cs4 = ldg4(p.colscale + col, VEC || p.vec_colscale != 0, nvalid);
+      // QKV (q / k part): per-thread head coordinates are fixed for the chunk
+      int qk_which = 0, qk_h = 0, qk_jj = 0;
+      if (out_mode == MVD_OUT_QKV_HEADS && nvalid > 0) {
+        qk_which = col / inner;
+        const int rem = col - qk_which * inner;
+        qk_h = rem / p.dhead;
+        qk_jj = rem - qk_h * p.dhead;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = rb + 16 * i;
+        const int grow = t.grow0 + row;
+        float4 v = lds_v4(stg + row * 128 + ((seg ^ (row & 7)) << 4));
+        const bool live = (grow < p.M) && nvalid > 0;
+        if (is_split && live) {
+          for (int s2 = 0; s2 < p.split; ++s2) {
+            if (s2 == t.s) continue;
+            const float* wp = p.ws + (static_cast<size_t>(t.tile) * p.split + s2) * (BM * ws_ld) + row * ws_ld + c * 32 + seg * 4;
+            const float4 w4 = __ldcg(reinterpret_cast<const float4*>(wp));
+            v.x += w4.x; v.y += w4.y; v.z += w4.z; v.w += w4.w;
+          }
+        }
+        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+        if (p.rowbias != nullptr && live) {
+          const float4 r4 = ldg4(p.rowbias + static_cast<size_t>(grow / p.rows_per_group) * p.N + col, VEC || p.vec_rowbias != 0, nvalid);
+          v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+        }
+        if (act == MVD_ACT_GELU) {
+          v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+        } else if (act == MVD_ACT_SILU) {
+          v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w);
+        }
+        v.x *= cs4.x; v.y *= cs4.y; v.z *= cs4.z; v.w *= cs4.w;
+        if (has_res) {
+          v.x += rn[i].x; v.y += rn[i].y; v.z += rn[i].z; v.w += rn[i].w;
+          if (nxt_valid) rn[i] = res_load(nxt_grow0, nxt_oc, i);
+        }
+        if (!live) continue;
+        if (out_mode == MVD_OUT_F32) {
+          float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(grow) * p.ldc + col;
+          if (VEC || (p.vec_out && nvalid >= 4)) {
+            *reinterpret_cast<float4*>(dst) = v;
+          } else {
+            dst[0] = v.x;
+            if (nvalid > 1) dst[1] = v.y;
+            if (nvalid > 2) dst[2] = v.z;
+            if (nvalid > 3) dst[3] = v.w;
+          }
+        } else if (out_mode == MVD_OUT_F16) {
+          __half* dst = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(grow) * p.ldc + col;
+          if (VEC || (p.vec_out && nvalid >= 4)) {
+            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
+          } else {
+            dst[0] = __float2half_rn(v.x);
+            if (nvalid > 1) dst[1] = __float2half_rn(v.y);
+            if (nvalid > 2) dst[2] = __float2half_rn(v.z);
+            if (nvalid > 3) dst[3] = __float2half_rn(v.w);
+          }
+        } else {  // q / k part of the head scatter (dhead % 8 == 0: four columns never straddle a head)
+          const int img = grow / p.seq;
+          const int pos = grow - img * p.seq;
+          __half* base = reinterpret_cast<__half*>(qk_which == 0 ? p.out : p.out_k);
+          __half* dst = base + ((static_cast<size_t>(img) * p.heads + qk_h) * p.seq + pos) * p.dpad + qk_jj;
+          *reinterpret_cast<uint2*>(dst) = make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
+        }
+      }
+    };
+
+    // chunks of unit (j, t) this warpgroup finishes: c = cfirst, cfirst + cstride, ... < valid
+    auto chunk_walk = [&](const Unit& t, int j, int& cfirst, int& cstride, int& valid) {
+      valid = min(nchunks, (n_out - t.n_tile * out_bn + 31) / 32);
+      if (is_split) {
+        cfirst = t.s + p.split * wg;
+        cstride = 2 * p.split;
+      } else {
+        cfirst = (wg ^ j) & 1;
+        cstride = 2;
+      }
+    };
+    // first chunk of this warpgroup at or after unit j (search forward); false when no work is left
+    auto find_task = [&](int j, int& jt, int& ct, int& grow0, int& oc) -> bool {
+      for (; j < n_local; ++j) {
+        const Unit t = decode_unit(p, first + j * gridDim.x);
+        int cf, cs, vc;
+        chunk_walk(t, j, cf, cs, vc);
+        if (cf < vc) {
+          jt = j; ct = cf; grow0 = t.grow0; oc = t.n_tile * out_bn + cf * 32;
+          return true;
+        }
+      }
+      return false;
+    };
+
+    if (has_res) {  // residual of the very first chunk
+      int jt, ct, g0, oc0;
+      if (find_task(0, jt, ct, g0, oc0)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rn[i] = res_load(g0, oc0, i);
+      }
+    }
 
     for (int j = 0; j < n_local; ++j) {
       const int u = first + j * gridDim.x;
       const Unit t = decode_unit(p, u);
       const int buf = j & 1;
-      const int col_base = t.n_tile * out_bn;
-      const int valid_chunks = min(nchunks, (n_out - col_base + 31) / 32);
-      const int grow = t.grow0 + r;
-      const bool valid = grow < p.M;
+      int cfirst, cstride, valid_chunks;
+      chunk_walk(t, j, cfirst, cstride, valid_chunks);
 
-      // residual tiles for the first two chunks: requested before the accumulator is even finished
-      if (p.use_res_tma && et == 0) {
-        for (int c = 0; c < min(2, valid_chunks); ++c) {
-          const int b = (res_items + c) & 1;
-          mbar_expect_tx(&res_full[b], STG_BYTES);
-          tma_load_2d(res_stg + b * STG_BYTES, &tmR, &res_full[b], col_base + c * 32, t.grow0);
-        }
+      if (geglu && p.bias != nullptr) {  // tile bias -> smem (phase A reads it as broadcast vectors)
+        for (int k = et; k < p.BN; k += WG_THREADS) sbias[k] = __ldg(p.bias + t.n_tile * p.BN + k);
+        named_bar_sync(bar_id, WG_THREADS);
       }
 
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
 
-      bool do_final = true;
-      if (p.split > 1) {
-        // ---- publish this K-slice's partial tile: ws[u][col4][row] (lanes write consecutive float4 -> coalesced)
-        const int ws_cols4 = ((p.BN + 31) / 32) * 8;  // float4 columns of one partial tile
-        float4* wsp = p.ws + static_cast<size_t>(u) * ws_cols4 * BM;
-        for (int c = 0; c < nchunks; ++c) {
-          float v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
+      if (is_split) {
+        // ---- park the chunks other slices own: ws[u][row][col] fp32, written with the coalesced phase-B mapping
+        float* wsu = p.ws + static_cast<size_t>(u) * (BM * ws_ld);
+        for (int c = wg; c < valid_chunks; c += 2) {
+          if (c % p.split == t.s) continue;
+          const uint32_t stg = stg_base + (n_staged & 1) * STG_BYTES;
+          ++n_staged;
+          phase_a(t, taddr, c, stg);
+          named_bar_sync(bar_id, WG_THREADS);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) wsp[(c * 8 + i) * BM + r] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int i = 0; i < 8; ++i) {
+            const int row = rb + 16 * i;
+            const float4 v = lds_v4(stg + row * 128 + ((seg ^ (row & 7)) << 4));
+            __stcg(reinterpret_cast<float4*>(wsu + row * ws_ld + c * 32 + seg * 4), v);
+          }
         }
         __threadfence();
-        named_bar_sync(1, EPI_THREADS);
-        if (et == 0) {
-          const int old = atomicAdd(&p.counters[t.tile], 1);
-          const int last = (old == p.split - 1) ? 1 : 0;
-          if (last) p.counters[t.tile] = 0;  // self-resetting semaphore: ready for the next launch
-          *last_flag = last;
+        named_bar_sync(3, EPI_THREADS);
+        if (wg == 0 && et == 0) {
+          atomicAdd(&p.counters[2 * t.tile], 1);
+          while (ld_acquire(&p.counters[2 * t.tile]) < p.split) {
+          }
         }
-        named_bar_sync(1, EPI_THREADS);
-        do_final = (*last_flag != 0);
-        if (do_final) __threadfence();
+        named_bar_sync(3, EPI_THREADS);
       }
 
-      if (do_final) {
-        const float* rb = nullptr;
-        if (p.rowbias != nullptr && valid) rb = p.rowbias + static_cast<size_t>(grow / p.rows_per_group) * p.N;
-        for (int c = 0; c < valid_chunks; ++c) {
-          const int oc = col_base + c * 32;  // first output column of this chunk
-          float v[32];
-          if (geglu) {
-            float g[32];
-            tmem_ld32(taddr + c * 32, v);
-            tmem_ld32(taddr + p.BN / 2 + c * 32, g);
-            tmem_ld_wait();
-            const int nv = t.n_tile * p.BN + c * 32;  // packed column of the value half
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float a = v[i], b = g[i];
-              if (p.bias != nullptr) {
-                a += __ldg(p.bias + nv + i);
-                b += __ldg(p.bias + nv + p.BN / 2 + i);
-              }
-              v[i] = a * gelu_erf(b);
-            }
+      for (int c = cfirst; c < valid_chunks; c += cstride) {
+        const uint32_t stg = stg_base + (n_staged & 1) * STG_BYTES;
+        // next chunk of this warpgroup (this unit or a later one) for the residual prefetch
+        bool nxt = false;
+        int ng0 = 0, noc = 0;
+        if (has_res) {
+          if (c + cstride < valid_chunks) {
+            nxt = true; ng0 = t.grow0; noc = t.n_tile * out_bn + (c + cstride) * 32;
           } else {
-            tmem_ld32(taddr + c * 32, v);
-            tmem_ld_wait();
-            if (p.split > 1) {
-              for (int s2 = 0; s2 < p.split; ++s2) {
-                if (s2 == t.s) continue;
-                const float4* wo = p.ws + static_cast<size_t>(t.tile * p.split + s2) * (((p.BN + 31) / 32) * 8) * BM;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float4 w4 = __ldcg(wo + (c * 8 + i) * BM + r);
-                  v[4 * i] += w4.x; v[4 * i + 1] += w4.y; v[4 * i + 2] += w4.z; v[4 * i + 3] += w4.w;
-                }
-              }
-            }
-            const bool full = (oc + 32 <= p.N);
-            if (p.bias != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] += (full || oc + i < p.N) ? __ldg(p.bias + oc + i) : 0.f;
-            }
-            if (rb != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] += (full || oc + i < p.N) ? __ldg(rb + oc + i) : 0.f;
-            }
-            if (p.act == MVD_ACT_GELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-            } else if (p.act == MVD_ACT_SILU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = silu(v[i]);
-            }
-            if (p.colscale != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= (full || oc + i < p.N) ? __ldg(p.colscale + oc + i) : 0.f;
-            }
-            if (p.use_res_tma) {
-              const int b = res_items & 1;
-              mbar_wait(&res_full[b], (res_items >> 1) & 1);
-              const uint32_t rrow = smem_u32(res_stg + b * STG_BYTES) + r * 128;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 t4 = lds_v4(rrow + ((i ^ (r & 7)) << 4));
-                v[4 * i] += t4.x; v[4 * i + 1] += t4.y; v[4 * i + 2] += t4.z; v[4 * i + 3] += t4.w;
-              }
-            } else if (p.residual != nullptr && valid) {
-              const float* res = p.residual + static_cast<size_t>(grow) * p.ldr + oc;
-              if (full && (p.ldr & 3) == 0) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  const float4 t4 = *reinterpret_cast<const float4*>(res + i);
-                  v[i] += t4.x; v[i + 1] += t4.y; v[i + 2] += t4.z; v[i + 3] += t4.w;
-                }
-              } else {
-                for (int i = 0; i < 32 && oc + i < p.N; ++i) v[i] += res[i];
-              }
-            }
+            int jt, ct;
+            nxt = find_task(j + 1, jt, ct, ng0, noc);
           }
+        }
+        const bool staged = phase_a(t, taddr, c, stg);
+        if (c + cstride >= valid_chunks) {  // last TMEM read of this unit by this thread: hand the accumulator back
+          tc_fence_before();
+          mbar_arrive(&acc_empty[buf]);
+        }
+        if (staged) {
+          ++n_staged;
+          named_bar_sync(bar_id, WG_THREADS);
+          phase_b(t, c, stg, nxt, ng0, noc);
+        }
+      }
+      if (cfirst >= valid_chunks) {  // nothing to finish in this unit: still part of the accumulator hand-shake
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf]);
+      }
 
-          if (p.use_out_tma) {
-            // ---- staged, coalesced store: registers -> swizzled smem tile -> TMA bulk store (clips the tails)
-            const int ob = out_items & 1;
-            if (et == 0) tma_store_wait_read<1>();  // the store issued two chunks ago has finished reading buffer `ob`
-            named_bar_sync(1, EPI_THREADS);
-            const uint32_t srow = smem_u32(out_stg + ob * STG_BYTES) + r * stg_row_bytes;
-            if (f16_out) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                sts_v4_u32(srow + (i << 4), pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
-                           pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) sts_v4(srow + ((i ^ (r & 7)) << 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-            fence_async_smem();
-            named_bar_sync(1, EPI_THREADS);  // staging tile complete; every thread is also done with residual buffer res_items & 1
-            if (et == 0) {
-              tma_store_2d(&tmO, out_stg + ob * STG_BYTES, oc, t.grow0);
-              tma_store_commit();
-              if (p.use_res_tma && c + 2 < valid_chunks) {
-                const int b = res_items & 1;
-                mbar_expect_tx(&res_full[b], STG_BYTES);
-                tma_load_2d(res_stg + b * STG_BYTES, &tmR, &res_full[b], col_base + (c + 2) * 32, t.grow0);
-              }
-            }
-            ++out_items;
-            if (p.use_res_tma) ++res_items;
-          } else if (valid) {
-            // ---- direct stores (QKV head scatter, or an output whose leading dimension TMA cannot address)
-            const bool full = (oc + 32 <= n_out);
-            if (p.out_mode == MVD_OUT_F32) {
-              float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(grow) * p.ldc + oc;
-              if (full && (p.ldc & 3) == 0) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                  *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-              } else {
-                for (int i = 0; i < 32 && oc + i < n_out; ++i) dst[i] = v[i];
-              }
-            } else if (p.out_mode == MVD_OUT_F16) {
-              __half* dst = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(grow) * p.ldc + oc;
-              if (full && (p.ldc & 7) == 0) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) store8_f16(dst + i, v + i);
-              } else {
-                for (int i = 0; i < 32 && oc + i < n_out; ++i) dst[i] = __float2half_rn(v[i]);
-              }
-            } else {  // MVD_OUT_QKV_HEADS
-              const int inner = p.heads * p.dhead;
-              const int img = grow / p.seq;
-              const int pos = grow - img * p.seq;
-#pragma unroll 1
-              for (int i = 0; i < 32; i += 8) {
-                const int n = oc + i;
-                if (n >= p.N) break;
-                const int which = n / inner;
-                const int rem = n - which * inner;
-                const int h = rem / p.dhead;
-                const int jj = rem - h * p.dhead;
-                const size_t bh = static_cast<size_t>(img) * p.heads + h;
-                if (which < 2) {
-                  __half* base = reinterpret_cast<__half*>(which == 0 ? p.out : p.out_k);
-                  store8_f16(base + (bh * p.seq + pos) * p.dpad + jj, v + i);
-                } else {
-                  __half* base = reinterpret_cast<__half*>(p.out_vt) + (bh * p.dpad + jj) * p.seq + pos;
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) base[static_cast<size_t>(e) * p.seq] = __float2half_rn(v[i + e]);
-                }
-              }
-            }
+      if (is_split) {
+        named_bar_sync(3, EPI_THREADS);  // every partial of this tile has been consumed by this CTA
+        if (wg == 0 && et == 0) {
+          const int old = atomicAdd(&p.counters[2 * t.tile + 1], 1);
+          if (old == p.split - 1) {  // last slice out resets the semaphores for the next launch
+            p.counters[2 * t.tile] = 0;
+            p.counters[2 * t.tile + 1] = 0;
           }
         }
       }
-      // accumulator `buf` is drained: hand it back to the MMA warp
-      tc_fence_before();
-      mbar_arrive(&acc_empty[buf]);
     }
-    if (et == 0 && p.use_out_tma) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -532,7 +621,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   }
   p.BN = bn;
 
-  CUtensorMap tmA, tmB, tmO, tmR;
+  CUtensorMap tmA, tmB;
   if (a->a_mode == MVD_A_ROWMAJOR) {
     if ((a->lda & 7) != 0 || a->lda < a->K) return set_error(MVD_EALIGN, "mvd_gemm_f16: lda must be >= K and a multiple of 8");
     p.num_kb = (a->K + BK - 1) / BK;
@@ -571,22 +660,26 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   const int tiles = p.tiles_m * p.tiles_n;
   const int sms = num_sms();
 
-  // ---- split-K
+  // ---- split-K (every slice of a tile must be co-resident: units <= SMs)
   int split = a->split_k;
   const size_t ws_avail = (a->splitk_ws != nullptr && a->splitk_ws_bytes > WS_COUNTER_BYTES) ? static_cast<size_t>(a->splitk_ws_bytes) - WS_COUNTER_BYTES : 0;
   const size_t tile_ws = static_cast<size_t>((bn + 31) / 32 * 32) * BM * sizeof(float);
+  const bool can_split = !geglu && a->out_mode != MVD_OUT_QKV_HEADS;
   if (split <= 0) {  // auto: only when the tiles cannot fill half the machine and K is deep
     split = 1;
-    if (!geglu && tiles * 2 <= sms && p.num_kb >= 8) {
+    if (can_split && tiles * 2 <= sms && p.num_kb >= 8) {
       split = sms / tiles;
       if (split > p.num_kb / 4) split = p.num_kb / 4;
       if (split > 16) split = 16;
       if (split < 1) split = 1;
     }
-    while (split > 1 && (tiles > WS_COUNTER_BYTES / 4 || static_cast<size_t>(tiles) * split * tile_ws > ws_avail)) --split;
+    while (split > 1 && (tiles > WS_COUNTER_BYTES / 8 || static_cast<size_t>(tiles) * split * tile_ws > ws_avail)) --split;
   } else if (split > 1) {
-    if (geglu) return set_error(MVD_EINVAL, "mvd_gemm_f16: split_k is not supported with GEGLU");
-    if (tiles > WS_COUNTER_BYTES / 4 || static_cast<size_t>(tiles) * split * tile_ws > ws_avail)
+    if (!can_split) return set_error(MVD_EINVAL, "mvd_gemm_f16: split_k is not supported with GEGLU / QKV_HEADS");
+    if (split > p.num_kb) split = p.num_kb;
+    if (tiles * split > sms)
+      return set_error(MVD_EINVAL, "mvd_gemm_f16: split_k=%d x %d tiles exceeds the %d SMs (slices of a tile must be co-resident)", split, tiles, sms);
+    if (tiles > WS_COUNTER_BYTES / 8 || static_cast<size_t>(tiles) * split * tile_ws > ws_avail)
       return set_error(MVD_EINVAL, "mvd_gemm_f16: split_k=%d needs a split-K workspace of %zu bytes (args.splitk_ws)", split,
                        static_cast<size_t>(tiles) * split * tile_ws + WS_COUNTER_BYTES);
   }
@@ -598,34 +691,29 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   if (split > 1) {
     if ((reinterpret_cast<uintptr_t>(a->splitk_ws) & 15) != 0) return set_error(MVD_EALIGN, "mvd_gemm_f16: splitk_ws must be 16-byte aligned");
     p.counters = reinterpret_cast<int*>(a->splitk_ws);
-    p.ws = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(a->splitk_ws) + WS_COUNTER_BYTES);
+    p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a->splitk_ws) + WS_COUNTER_BYTES);
   }
 
-  // ---- epilogue paths
-  const int out_elem = (a->out_mode == MVD_OUT_F32) ? 4 : 2;
+  // ---- epilogue access widths
   const int n_out = geglu ? a->N / 2 : a->N;
-  p.use_out_tma = (a->out_mode != MVD_OUT_QKV_HEADS) && ((static_cast<long long>(a->ldc) * out_elem) % 16 == 0) &&
-                  ((reinterpret_cast<uintptr_t>(a->out) & 15) == 0) && a->ldc >= n_out;
+  auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
   if (a->out_mode != MVD_OUT_QKV_HEADS && a->ldc < n_out) return set_error(MVD_EINVAL, "mvd_gemm_f16: ldc is smaller than the output width");
-  if (p.use_out_tma) {
-    int rc = make_tmap_2d_ex(&tmO, a->out, out_elem, n_out, a->M, a->ldc, 32, BM, out_elem == 4 ? 128 : 0);
-    if (rc != MVD_OK) return rc;
-  } else {
-    tmO = tmB;
-  }
-  p.use_res_tma = p.use_out_tma && a->residual != nullptr && split == 1 && ((static_cast<long long>(a->ldr) * 4) % 16 == 0) &&
-                  ((reinterpret_cast<uintptr_t>(a->residual) & 15) == 0) && a->ldr >= a->N;
   if (a->residual != nullptr && a->ldr < a->N) return set_error(MVD_EINVAL, "mvd_gemm_f16: ldr is smaller than N");
-  if (p.use_res_tma) {
-    int rc = make_tmap_2d_ex(&tmR, a->residual, 4, a->N, a->M, a->ldr, 32, BM, 128);
-    if (rc != MVD_OK) return rc;
-  } else {
-    tmR = tmB;
+  p.vec_bias = al16(a->bias);
+  p.vec_rowbias = al16(a->rowbias) && (a->N & 3) == 0;
+  p.vec_colscale = al16(a->colscale);
+  p.vec_res = al16(a->residual) && (a->ldr & 3) == 0;
+  if (a->out_mode == MVD_OUT_F32) p.vec_out = al16(a->out) && (a->ldc & 3) == 0;
+  else if (a->out_mode == MVD_OUT_F16) p.vec_out = (reinterpret_cast<uintptr_t>(a->out) & 7) == 0 && (a->ldc & 3) == 0;
+  else {
+    p.vec_out = 1;
+    if (!al16(a->out) || !al16(a->out_k) || !al16(a->out_vt)) return set_error(MVD_EALIGN, "mvd_gemm_f16: q / k / v^T must be 16-byte aligned");
+    p.qkv_direct = ((a->heads * a->dhead) & 31) != 0;
   }
 
   // ---- shared memory / TMEM budget
   const int stage_bytes = A_BYTES + bn * 128;
-  const int fixed = 2 * STG_BYTES + (p.use_res_tma ? 2 * STG_BYTES : 0) + 512;
+  const int fixed = 4 * STG_BYTES + 2048 + 512;
   int stages = (232448 - 1024 - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return set_error(MVD_EINVAL, "mvd_gemm_f16: tile does not fit in shared memory");
@@ -634,13 +722,43 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   p.acc_stride = bn <= 128 ? 128 : 256;
   p.tmem_cols = 2 * p.acc_stride;
 
+  // ---- pick the epilogue specialisation
+  const bool vec = (n_out % 4 == 0) && (a->bias == nullptr || p.vec_bias) && (a->rowbias == nullptr || p.vec_rowbias) &&
+                   (a->colscale == nullptr || p.vec_colscale) && (a->residual == nullptr || p.vec_res) && p.vec_out &&
+                   !(a->out_mode == MVD_OUT_QKV_HEADS && p.qkv_direct);
+  const int has_res = a->residual != nullptr ? 1 : 0;
+  const int is_split = split > 1 ? 1 : 0;
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const GemmKParams);
+  KernelFn fn = gemm_tc_kernel<-1, -1, -1, -1, false>;
+  if (vec) {
+    const int key = a->act * 1000 + a->out_mode * 100 + has_res * 10 + is_split;
+    switch (key) {
+      case MVD_ACT_NONE * 1000 + MVD_OUT_F32 * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 0, 0, true>; break;
+      case MVD_ACT_NONE * 1000 + MVD_OUT_F32 * 100 + 1: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 0, 1, true>; break;
+      case MVD_ACT_NONE * 1000 + MVD_OUT_F32 * 100 + 10: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 1, 0, true>; break;
+      case MVD_ACT_NONE * 1000 + MVD_OUT_F32 * 100 + 11: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 1, 1, true>; break;
+      case MVD_ACT_NONE * 1000 + MVD_OUT_F16 * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 0, 0, true>; break;
+      case MVD_ACT_NONE * 1000 + MVD_OUT_F16 * 100 + 10: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 1, 0, true>; break;
+      case MVD_ACT_GELU * 1000 + MVD_OUT_F16 * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_GELU, MVD_OUT_F16, 0, 0, true>; break;
+      case MVD_ACT_GELU * 1000 + MVD_OUT_F32 * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_GELU, MVD_OUT_F32, 0, 0, true>; break;
+      case MVD_ACT_GEGLU * 1000 + MVD_OUT_F16 * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_GEGLU, MVD_OUT_F16, 0, 0, true>; break;
+      case MVD_ACT_NONE * 1000 + MVD_OUT_QKV_HEADS * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_QKV_HEADS, 0, 0, true>; break;
+      default: break;
+    }
+  }
   static bool configured = false;
   if (!configured) {
-    MVD_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    KernelFn all[] = {gemm_tc_kernel<-1, -1, -1, -1, false>,
+                      gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 0, 0, true>, gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 0, 1, true>,
+                      gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 1, 0, true>, gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 1, 1, true>,
+                      gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 0, 0, true>, gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 1, 0, true>,
+                      gemm_tc_kernel<MVD_ACT_GELU, MVD_OUT_F16, 0, 0, true>, gemm_tc_kernel<MVD_ACT_GELU, MVD_OUT_F32, 0, 0, true>,
+                      gemm_tc_kernel<MVD_ACT_GEGLU, MVD_OUT_F16, 0, 0, true>, gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_QKV_HEADS, 0, 0, true>};
+    for (KernelFn f : all) MVD_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     configured = true;
   }
   const int grid = p.num_units < sms ? p.num_units : sms;
-  gemm_tc_kernel<<<grid, GEMM_THREADS, dyn, stream>>>(tmA, tmB, tmO, tmR, p);
+  fn<<<grid, GEMM_THREADS, dyn, stream>>>(tmA, tmB, p);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

@@ -110,7 +110,10 @@ class NativeOps:
         n_out = N // 2 if act == ACT_GEGLU else N
         a_bytes = (conv[0] * conv[1] * conv[2] * conv[3] if conv is not None else M * K) * 2
         o_bytes = M * n_out * (4 if (qkv is None and out.dtype == torch.float32) else 2)
-        meta = {"kernel": "gemm_tc_kernel", "flops": 2.0 * M * N * K, "shape": (M, N, K, split_k),
+        desc = (f"{'conv' if conv is not None else 'lin'} M{M} N{N} K{K} "
+                f"{'qkv' if qkv is not None else ('f32' if out.dtype == torch.float32 else 'f16')}"
+                f"{' res' if residual is not None else ''}{' act%d' % act if act else ''}{' sk' if split_k != 1 else ''}")
+        meta = {"kernel": "gemm_tc_kernel", "flops": 2.0 * M * N * K, "shape": (M, N, K, split_k), "desc": desc,
                 "bytes": a_bytes + N * K * 2 + o_bytes + (M * n_out * 4 if residual is not None else 0)}
         return self._bind("mvd_gemm_f16", (ctypes.byref(g),), keep, meta)
 
@@ -119,6 +122,7 @@ class NativeOps:
                                                 _ptr(out, torch.float16), n_img, heads, seq, dhead, dpad, ldo),
                           (q, k, vt, out),
                           {"kernel": "attn_self_kernel", "flops": 4.0 * n_img * heads * seq * seq * dhead,
+                           "desc": f"img{n_img} seq{seq} d{dhead}",
                            "bytes": 2.0 * n_img * heads * seq * (3 * dpad + dhead)})
 
     # ------------------------------------------------------------------ normalisation
@@ -126,12 +130,12 @@ class NativeOps:
         return self._bind("mvd_groupnorm_f32_f16", (_ptr(x, torch.float32), _ptr(gamma, torch.float32),
                                                     _ptr(beta, torch.float32), _ptr(y, torch.float16),
                                                     _ptr(stats_ws, torch.float64), n_img, hw, C, eps, int(silu)),
-                          (x, gamma, beta, y, stats_ws))
+                          (x, gamma, beta, y, stats_ws), {"desc": f"img{n_img} hw{hw} C{C}", "bytes": 6.0 * n_img * hw * C})
 
     def layernorm(self, x, gamma, beta, y, rows, C, eps):
         return self._bind("mvd_layernorm_f32_f16", (_ptr(x, torch.float32), _ptr(gamma, torch.float32),
                                                     _ptr(beta, torch.float32), _ptr(y, torch.float16), rows, C, eps),
-                          (x, gamma, beta, y))
+                          (x, gamma, beta, y), {"desc": f"rows{rows} C{C}", "bytes": 6.0 * rows * C})
 
     def ln_modulate(self, x, shift, scale, y, rows, C, eps):
         return self._bind("mvd_ln_modulate_f32_f16", (_ptr(x, torch.float32), _ptr(shift, torch.float32),
@@ -140,11 +144,12 @@ class NativeOps:
 
     # ------------------------------------------------------------------ data movement / elementwise
     def cast(self, x, y, n):
-        return self._bind("mvd_cast_f32_f16", (_ptr(x, torch.float32), _ptr(y, torch.float16), n), (x, y))
+        return self._bind("mvd_cast_f32_f16", (_ptr(x, torch.float32), _ptr(y, torch.float16), n), (x, y),
+                          {"desc": f"n{n}", "bytes": 6.0 * n})
 
     def concat(self, a, b, out, rows, C1, C2):
         return self._bind("mvd_concat_f32", (_ptr(a, torch.float32), _ptr(b, torch.float32), _ptr(out, torch.float32),
-                                             rows, C1, C2), (a, b, out))
+                                             rows, C1, C2), (a, b, out), {"desc": f"rows{rows} {C1}+{C2}", "bytes": 8.0 * rows * (C1 + C2)})
 
     def upsample2x(self, x, y, n_img, H, W, C):
         return self._bind("mvd_upsample2x_f32_f16", (_ptr(x, torch.float32), _ptr(y, torch.float16), n_img, H, W, C),

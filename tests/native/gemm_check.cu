@@ -246,7 +246,89 @@ static void run(const Case& c) {
   if (dres) cudaFree(dres);
 }
 
+// ---- timing mode: `gemm_check bench` — representative shapes of one denoising step (N=8 views x 2 CFG branches)
+struct BCase { const char* name; int M, N, K; int conv_img, conv_hw, conv_c; bool res; int act; int out_mode; int split; int tile_n; };
+static void bench(const BCase& c, int iters) {
+  const int ldw = (c.K + 7) / 8 * 8;
+  const size_t wbytes = static_cast<size_t>(c.N) * ldw * 2;
+  int ncopy = static_cast<int>((300ull << 20) / wbytes) + 1;  // rotate weight copies so they stream from HBM like in the real step
+  if (ncopy > 64) ncopy = 64;
+  __half* dW; CK(cudaMalloc(&dW, wbytes * ncopy)); CK(cudaMemset(dW, 0, wbytes * ncopy));
+  const size_t abytes = c.conv_img ? static_cast<size_t>(c.conv_img) * c.conv_hw * c.conv_hw * c.conv_c * 2 : static_cast<size_t>(c.M) * c.K * 2;
+  __half* dA; CK(cudaMalloc(&dA, abytes)); CK(cudaMemset(dA, 0, abytes));
+  const bool geglu = c.act == MVD_ACT_GEGLU;
+  const int No = geglu ? c.N / 2 : c.N;
+  void* dout; CK(cudaMalloc(&dout, static_cast<size_t>(c.M) * No * 4 * 3 + 1024)); 
+  float* dres = nullptr; if (c.res) { CK(cudaMalloc(&dres, static_cast<size_t>(c.M) * c.N * 4)); CK(cudaMemset(dres, 0, static_cast<size_t>(c.M) * c.N * 4)); }
+  float* db; CK(cudaMalloc(&db, c.N * 4)); CK(cudaMemset(db, 0, c.N * 4));
+  static void* ws = nullptr; const size_t ws_bytes = 64u << 20;
+  if (!ws) { CK(cudaMalloc(&ws, ws_bytes)); CK(cudaMemset(ws, 0, ws_bytes)); }
+  mvd_gemm_args g; memset(&g, 0, sizeof(g));
+  g.M = c.M; g.N = c.N; g.K = c.K; g.A = dA; g.lda = c.K; g.ldw = ldw; g.bias = db; g.residual = dres; g.ldr = c.N;
+  g.act = c.act; g.out_mode = c.out_mode; g.out = dout; g.ldc = No; g.split_k = c.split; g.tile_n = c.tile_n;
+  g.splitk_ws = ws; g.splitk_ws_bytes = ws_bytes; g.rows_per_group = 1;
+  if (c.conv_img) { g.a_mode = MVD_A_CONV3X3; g.n_img = c.conv_img; g.H = g.W = c.conv_hw; g.C = c.conv_c; }
+  if (c.out_mode == MVD_OUT_QKV_HEADS) {
+    g.heads = 8; g.dhead = c.N / 24; g.dpad = (g.dhead + 63) / 64 * 64; g.seq = c.conv_hw;  // conv_hw doubles as seq here
+    const size_t nqk = static_cast<size_t>(c.M) * 8 * g.dpad * 2;
+    CK(cudaFree(dout)); CK(cudaMalloc(&dout, nqk * 3));
+    g.out = dout; g.out_k = static_cast<char*>(dout) + nqk; g.out_vt = static_cast<char*>(dout) + 2 * nqk; g.n_img = 0;
+  }
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int rc = 0;
+  for (int i = 0; i < 3; ++i) { g.Wt = dW + (static_cast<size_t>(i % ncopy) * wbytes) / 2; rc |= mvd_gemm_f16(&g, nullptr); }
+  CK(cudaDeviceSynchronize());
+  cudaEventRecord(e0);
+  for (int i = 0; i < iters; ++i) { g.Wt = dW + (static_cast<size_t>(i % ncopy) * wbytes) / 2; rc |= mvd_gemm_f16(&g, nullptr); }
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  const double us = ms * 1e3 / iters;
+  printf("%-44s rc=%d %8.1f us  %7.1f TF/s\n", c.name, rc, us, 2.0 * c.M * c.N * c.K / (us * 1e-6) / 1e12);
+  if (rc) printf("   error: %s\n", mvd_last_error());
+  cudaFree(dW); cudaFree(dA); cudaFree(dout); cudaFree(db); if (dres) cudaFree(dres);
+}
+static int bench_main(int only) {
+  const BCase cs[] = {
+      {"lin 16384x320x320 f32 res", 16384, 320, 320, 0, 0, 0, true, 0, MVD_OUT_F32, 0, 0},
+      {"lin 16384x320x320 f32", 16384, 320, 320, 0, 0, 0, false, 0, MVD_OUT_F32, 0, 0},
+      {"lin 4096x640x640 f32 res", 4096, 640, 640, 0, 0, 0, true, 0, MVD_OUT_F32, 0, 0},
+      {"lin 1024x1280x1280 f32 res", 1024, 1280, 1280, 0, 0, 0, true, 0, MVD_OUT_F32, 0, 0},
+      {"lin 256x1280x1280 f32 res", 256, 1280, 1280, 0, 0, 0, true, 0, MVD_OUT_F32, 0, 0},
+      {"lin 16384x320x1280 f32 res", 16384, 320, 1280, 0, 0, 0, true, 0, MVD_OUT_F32, 0, 0},
+      {"lin 4096x640x2560 f32 res", 4096, 640, 2560, 0, 0, 0, true, 0, MVD_OUT_F32, 0, 0},
+      {"lin 1024x1280x5120 f32 res", 1024, 1280, 5120, 0, 0, 0, true, 0, MVD_OUT_F32, 0, 0},
+      {"lin 256x1280x5120 f32 res", 256, 1280, 5120, 0, 0, 0, true, 0, MVD_OUT_F32, 0, 0},
+      {"geglu 16384x2560x320", 16384, 2560, 320, 0, 0, 0, false, MVD_ACT_GEGLU, MVD_OUT_F16, 1, 256},
+      {"geglu 4096x5120x640", 4096, 5120, 640, 0, 0, 0, false, MVD_ACT_GEGLU, MVD_OUT_F16, 1, 256},
+      {"geglu 1024x10240x1280", 1024, 10240, 1280, 0, 0, 0, false, MVD_ACT_GEGLU, MVD_OUT_F16, 1, 256},
+      {"geglu 256x10240x1280", 256, 10240, 1280, 0, 0, 0, false, MVD_ACT_GEGLU, MVD_OUT_F16, 1, 256},
+      {"qkv 16384x960x320", 16384, 960, 320, 0, 1024, 0, false, 0, MVD_OUT_QKV_HEADS, 1, 0},
+      {"qkv 4096x1920x640", 4096, 1920, 640, 0, 256, 0, false, 0, MVD_OUT_QKV_HEADS, 1, 0},
+      {"qkv 1024x3840x1280", 1024, 3840, 1280, 0, 64, 0, false, 0, MVD_OUT_QKV_HEADS, 1, 0},
+      {"grid 65536x512x256 gelu f16", 65536, 512, 256, 0, 0, 0, false, MVD_ACT_GELU, MVD_OUT_F16, 1, 0},
+      {"grid 65536x768x256 f16", 65536, 768, 256, 0, 0, 0, false, 0, MVD_OUT_F16, 1, 0},
+      {"grid 65536x256x512 f32 res", 65536, 256, 512, 0, 0, 0, true, 0, MVD_OUT_F32, 1, 0},
+      {"grid 65536x256x256 f32 res", 65536, 256, 256, 0, 0, 0, true, 0, MVD_OUT_F32, 1, 0},
+      {"grid 65536x256x736 gelu f32", 65536, 256, 736, 0, 0, 0, false, MVD_ACT_GELU, MVD_OUT_F32, 1, 0},
+      {"conv 16x32x32x320->320 res", 16384, 320, 2880, 16, 32, 320, true, 0, MVD_OUT_F32, 0, 0},
+      {"conv 16x16x16x640->640 res", 4096, 640, 5760, 16, 16, 640, true, 0, MVD_OUT_F32, 0, 0},
+      {"conv 16x8x8x1280->1280 res", 1024, 1280, 11520, 16, 8, 1280, true, 0, MVD_OUT_F32, 0, 0},
+      {"conv 16x4x4x1280->1280 res", 256, 1280, 11520, 16, 4, 1280, true, 0, MVD_OUT_F32, 0, 0},
+      {"conv 16x4x4x2560->1280", 256, 1280, 23040, 16, 4, 2560, false, 0, MVD_OUT_F32, 0, 0},
+      {"conv 16x16x16x1280->1280 (up)", 4096, 1280, 11520, 16, 16, 1280, false, 0, MVD_OUT_F32, 0, 0},
+      {"conv 16x32x32x640->640 (up)", 16384, 640, 5760, 16, 32, 640, false, 0, MVD_OUT_F32, 0, 0},
+      {"conv 16x32x32x960->320", 16384, 320, 8640, 16, 32, 960, false, 0, MVD_OUT_F32, 0, 0},
+      {"lin 16384x320x768 f16", 16384, 320, 768, 0, 0, 0, false, 0, MVD_OUT_F16, 0, 0},
+  };
+  const int n = sizeof(cs) / sizeof(cs[0]);
+  for (int i = 0; i < n; ++i)
+    if (only < 0 || only == i) bench(cs[i], 40);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && strcmp(argv[1], "bench") == 0) return bench_main(argc > 2 ? atoi(argv[2]) : -1);
   int only = argc > 1 ? atoi(argv[1]) : -1;
   std::vector<Case> cases;
   { Case c; c.name = "plain 128x128x64"; c.M = 128; c.N = 128; c.K = 64; cases.push_back(c); }
@@ -276,6 +358,12 @@ int main(int argc, char** argv) {
   { Case c; c.name = "split16 rowbias 130x640x8192"; c.M = 130; c.N = 640; c.K = 8192; c.split_k = 16; c.rowbias = true; c.rows_per_group = 16; cases.push_back(c); }
   { Case c; c.name = "conv 16x8x8x1280->1280 auto-split res"; c.a_mode = MVD_A_CONV3X3; c.n_img = 16; c.H = c.W = 8; c.C = 1280; c.N = 1280; c.K = 9 * 1280; c.M = 1024; c.split_k = 0; c.bias = c.residual = true; cases.push_back(c); }
   { Case c; c.name = "geglu 4096x2560x320"; c.M = 4096; c.N = 2560; c.K = 320; c.bias = true; c.act = MVD_ACT_GEGLU; c.out_mode = MVD_OUT_F16; cases.push_back(c); }
+  { Case c; c.name = "f16 out tails 300x200x320 bias"; c.M = 300; c.N = 200; c.K = 320; c.bias = true; c.out_mode = MVD_OUT_F16; cases.push_back(c); }
+  { Case c; c.name = "odd N 130x37x128 bias+res"; c.M = 130; c.N = 37; c.K = 128; c.bias = c.residual = true; cases.push_back(c); }
+  { Case c; c.name = "split5 silu f16 256x320x2560 rowbias"; c.M = 256; c.N = 320; c.K = 2560; c.split_k = 5; c.bias = c.rowbias = true; c.rows_per_group = 16; c.act = MVD_ACT_SILU; c.out_mode = MVD_OUT_F16; cases.push_back(c); }
+  { Case c; c.name = "qkv heads 16x1024 d40 persistent"; c.M = 16384; c.N = 3 * 8 * 40; c.K = 320; c.out_mode = MVD_OUT_QKV_HEADS; c.heads = 8; c.dhead = 40; c.dpad = 64; c.seq = 1024; cases.push_back(c); }
+  { Case c; c.name = "qkv heads d8 (generic scatter)"; c.M = 256; c.N = 3 * 8 * 8; c.K = 64; c.out_mode = MVD_OUT_QKV_HEADS; c.heads = 8; c.dhead = 8; c.dpad = 64; c.seq = 64; cases.push_back(c); }
+  { Case c; c.name = "persistent res 40000x160x256"; c.M = 40000; c.N = 160; c.K = 256; c.bias = c.residual = true; cases.push_back(c); }
   for (size_t i = 0; i < cases.size(); ++i)
     if (only < 0 || only == static_cast<int>(i)) run(cases[i]);
   printf("%s (%d failing)\n", g_fail ? "GEMM CHECK FAILED" : "GEMM CHECK PASSED", g_fail);
