@@ -8,23 +8,25 @@
 //   Vt   : fp16 [BH, dpad, seq]  (transposed so the PV product is K-major on both operands)
 //   out  : fp16 [n_img*seq, heads*dhead]  ('b n (h d)'), the A operand of to_out.
 //
-// One CTA = 128 query rows of one (image, head).  Warps 0-3: one thread per query row (TMEM lane),
-// warp 4: control (TMA loads + tcgen05.mma issue).  S = Q K^T lives in TMEM (BKV fp32 columns),
-// O accumulates in TMEM next to it.  Exact two-pass softmax: pass 1 computes the row maxima from
-// S tiles only, pass 2 recomputes S, writes P = exp2(S*c - m*c) as fp16 into a 128B-swizzled smem
-// tile and accumulates O += P V_j and l += rowsum(P).  When the whole key range fits one tile
-// (seq <= BKV) S is computed once.
+// One CTA = 128 query rows of one (image, head); two CTAs share an SM so that one CTA's softmax overlaps the other's
+// tensor work.  Warps 0-3: one thread per query row (TMEM lane); warp 4: tcgen05.mma issue; warp 5: TMA producer
+// (Q once, K / V^T tiles through a 2-stage ring).  S = Q K^T lives in TMEM (BKV fp32 columns), O accumulates next to it.
+// Single pass over the keys with an exact online softmax: the running row maximum is only advanced (and O / l rescaled,
+// tcgen05.ld -> scale -> tcgen05.st) when it grows by more than 2^8 — P = exp2(S c - m c) stays far inside fp16 range
+// and the final O / l is exact for any reference maximum.  P goes to the tensor core as an fp16 128B-swizzled smem tile.
 #include "common.h"
 #include "ptx.cuh"
 
 namespace mvd {
 
 constexpr int ATT_BM = 128;
-constexpr int ATT_THREADS = 160;
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_MAX_STAGES = 2;
 
 struct AttnParams {
   int seq, heads, dhead, dpad, bkv;
   int n_tiles;      // key tiles
+  int stages;       // K / V ring depth
   int kd_steps;     // ceil(dhead/16): k-steps of the QK^T product
   int n_o;          // kd_steps*16: columns of O
   int tmem_cols;    // power of two >= bkv + n_o
@@ -33,6 +35,7 @@ struct AttnParams {
   int ldo;
   // smem byte offsets (from the 1024-aligned base)
   int off_k, off_v, off_p, off_bar;
+  int k_stage, v_stage;  // bytes per ring slot
 };
 
 __device__ __forceinline__ void st_shared_16(uint32_t addr, const float* v) {
@@ -46,38 +49,50 @@ __device__ __forceinline__ void st_shared_16(uint32_t addr, const float* v) {
                : "memory");
 }
 
-__global__ void __launch_bounds__(ATT_THREADS)
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// BKV = key-tile width (16 / 32 / 64 / 128): a whole score row of the tile lives in registers between the maximum
+// and the exponentiation, so S is read from TMEM once.
+template <int BKV>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
     attn_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + p.off_k;
   uint8_t* sV = smem + p.off_v;
   uint8_t* sP = smem + p.off_p;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
-  uint64_t* bar_q = bars + 0;       // TMA Q landed
-  uint64_t* bar_kv = bars + 1;      // TMA K (+V) tile landed
-  uint64_t* bar_s_full = bars + 2;  // QK^T MMA retired
-  uint64_t* bar_s_free = bars + 3;  // 128 row threads finished reading S
-  uint64_t* bar_p_ready = bars + 4; // 128 row threads wrote P
-  uint64_t* bar_pv_done = bars + 5; // PV MMA retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bar_q = bars + 0;          // TMA Q landed
+  uint64_t* bar_kv_full = bars + 1;    // [2] K + V^T tile landed
+  uint64_t* bar_kv_empty = bars + 3;   // [2] PV MMA that read the slot retired
+  uint64_t* bar_s_full = bars + 5;     // QK^T MMA retired
+  uint64_t* bar_s_free = bars + 6;     // 128 row threads finished reading S
+  uint64_t* bar_p_ready = bars + 7;    // 128 row threads wrote P (and rescaled O)
+  uint64_t* bar_pv_done = bars + 8;    // PV MMA retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * ATT_BM;
   const int bh = blockIdx.y;
-  const bool two_pass = p.n_tiles > 1;
-  const int atoms_d = p.dpad / 64;   // 64-wide k atoms of Q / K tiles
-  const int atoms_kv = (p.bkv + 63) / 64;  // 64-key atoms of the P / Vt tiles
+  const int atoms_d = p.dpad / 64;         // 64-wide k atoms of Q / K tiles
+  const int atoms_kv = (BKV + 63) / 64;  // 64-key atoms of the P / Vt tiles
 
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023) != 0) __trap();  // swizzled tiles need the 1024-byte base
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(bar_q, 1);
-    mbar_init(bar_kv, 1);
+    for (int s = 0; s < ATT_MAX_STAGES; ++s) {
+      mbar_init(&bar_kv_full[s], 1);
+      mbar_init(&bar_kv_empty[s], 1);
+    }
     mbar_init(bar_s_full, 1);
     mbar_init(bar_s_free, ATT_BM);
     mbar_init(bar_p_ready, ATT_BM);
@@ -89,108 +104,134 @@ __global__ void __launch_bounds__(ATT_THREADS)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_s = *tmem_slot;
-  const uint32_t tmem_o = tmem_s + p.bkv;
+  const uint32_t tmem_o = tmem_s + BKV;
 
-  const int total_iters = (two_pass ? 2 : 1) * p.n_tiles;
-
-  if (warp == 4) {
+  if (warp == 5) {
     if (lane == 0) {
-      // ---------------------------------------------------------------- control thread
+      // ---------------------------------------------------------------- TMA producer
       const uint32_t q_bytes = ATT_BM * p.dpad * 2;
-      const uint32_t k_bytes = p.bkv * p.dpad * 2;
-      const uint32_t v_bytes = atoms_kv * p.dpad * 128;
+      const uint32_t kv_bytes = BKV * p.dpad * 2 + atoms_kv * p.dpad * 128;
       mbar_expect_tx(bar_q, q_bytes);
       for (int a = 0; a < atoms_d; ++a) tma_load_3d(sQ + a * (ATT_BM * 128), &tmQ, bar_q, a * 64, q0, bh);
-      mbar_wait(bar_q, 0);
-      const uint32_t idesc_s = umma_idesc_f16(ATT_BM, p.bkv);
+      for (int j = 0; j < p.n_tiles; ++j) {
+        const int st = j % p.stages;
+        mbar_wait(&bar_kv_empty[st], ((j / p.stages) & 1) ^ 1);
+        mbar_expect_tx(&bar_kv_full[st], kv_bytes);
+        uint8_t* k = sK + st * p.k_stage;
+        uint8_t* v = sV + st * p.v_stage;
+        for (int a = 0; a < atoms_d; ++a) tma_load_3d(k + a * (BKV * 128), &tmK, &bar_kv_full[st], a * 64, j * BKV, bh);
+        for (int a = 0; a < atoms_kv; ++a) tma_load_3d(v + a * (p.dpad * 128), &tmV, &bar_kv_full[st], j * BKV + a * 64, 0, bh);
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- UMMA issuer
+      const uint32_t idesc_s = umma_idesc_f16(ATT_BM, BKV);
       const uint32_t idesc_o = umma_idesc_f16(ATT_BM, p.n_o);
-      int pv_count = 0;
-      for (int it = 0; it < total_iters; ++it) {
-        const bool pv_pass = !two_pass || it >= p.n_tiles;
-        const int j = two_pass ? (it % p.n_tiles) : it;
-        mbar_expect_tx(bar_kv, k_bytes + (pv_pass ? v_bytes : 0));
-        for (int a = 0; a < atoms_d; ++a) tma_load_3d(sK + a * (p.bkv * 128), &tmK, bar_kv, a * 64, j * p.bkv, bh);
-        if (pv_pass)
-          for (int a = 0; a < atoms_kv; ++a) tma_load_3d(sV + a * (p.dpad * 128), &tmV, bar_kv, j * p.bkv + a * 64, 0, bh);
-        mbar_wait(bar_kv, it & 1);
-        if (it > 0) mbar_wait(bar_s_free, (it - 1) & 1);
+      mbar_wait(bar_q, 0);
+      // QK^T of tile j+1 is issued as soon as every row thread has pulled S(j) into registers, i.e. it runs under the
+      // softmax of tile j; PV(j) follows when P(j) is in shared memory.
+      auto issue_qk = [&](int j) {
+        const int st = j % p.stages;
+        mbar_wait(&bar_kv_full[st], (j / p.stages) & 1);
+        if (j > 0) mbar_wait(bar_s_free, (j - 1) & 1);
         tc_fence_after();
+        const uint32_t k = smem_u32(sK + st * p.k_stage);
         for (int ks = 0; ks < p.kd_steps; ++ks) {
           const uint32_t aq = smem_u32(sQ) + (ks >> 2) * (ATT_BM * 128) + (ks & 3) * 32;
-          const uint32_t ak = smem_u32(sK) + (ks >> 2) * (p.bkv * 128) + (ks & 3) * 32;
+          const uint32_t ak = k + (ks >> 2) * (BKV * 128) + (ks & 3) * 32;
           umma_f16(tmem_s, umma_desc_sw128(aq), umma_desc_sw128(ak), idesc_s, ks > 0 ? 1u : 0u);
         }
         tc_commit(bar_s_full);
-        if (pv_pass) {
-          mbar_wait(bar_p_ready, pv_count & 1);
-          tc_fence_after();
-          const int ksteps = (min(p.bkv, p.seq - j * p.bkv) + 15) / 16;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t ap = smem_u32(sP) + (ks >> 2) * (ATT_BM * 128) + (ks & 3) * 32;
-            const uint32_t av = smem_u32(sV) + (ks >> 2) * (p.dpad * 128) + (ks & 3) * 32;
-            umma_f16(tmem_o, umma_desc_sw128(ap), umma_desc_sw128(av), idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-          }
-          tc_commit(bar_pv_done);
-          mbar_wait(bar_pv_done, pv_count & 1);
-          ++pv_count;
-        } else {
-          mbar_wait(bar_s_full, it & 1);  // K tile may be overwritten once the MMA has read it
+      };
+      issue_qk(0);
+      for (int j = 0; j < p.n_tiles; ++j) {
+        const int st = j % p.stages;
+        if (j + 1 < p.n_tiles) issue_qk(j + 1);
+        const uint32_t v = smem_u32(sV + st * p.v_stage);
+        mbar_wait(bar_p_ready, j & 1);
+        tc_fence_after();
+        const int ksteps = (min(BKV, p.seq - j * BKV) + 15) / 16;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t ap = smem_u32(sP) + (ks >> 2) * (ATT_BM * 128) + (ks & 3) * 32;
+          const uint32_t av = v + (ks >> 2) * (p.dpad * 128) + (ks & 3) * 32;
+          umma_f16(tmem_o, umma_desc_sw128(ap), umma_desc_sw128(av), idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
         }
+        tc_commit(&bar_kv_empty[st]);
+        tc_commit(bar_pv_done);
       }
     }
   } else {
     // ------------------------------------------------------------------ one thread per query row
     const int r = warp * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    float m = -INFINITY;  // running max of raw scores (unscaled)
+    float m = -INFINITY;  // reference maximum of the raw scores (may lag the true running maximum by <= 8 / scale_log2)
     float l = 0.f;
-    float mc = 0.f;       // m * scale_log2, fixed during the P pass
-    for (int it = 0; it < total_iters; ++it) {
-      const bool pv_pass = !two_pass || it >= p.n_tiles;
-      const int j = two_pass ? (it % p.n_tiles) : it;
-      const int kv_valid = min(p.bkv, p.seq - j * p.bkv);
-      mbar_wait(bar_s_full, it & 1);
+    constexpr int LDW = BKV >= 32 ? 32 : 16;  // columns per tcgen05.ld
+    for (int j = 0; j < p.n_tiles; ++j) {
+      const int kv_valid = min(BKV, p.seq - j * BKV);
+      mbar_wait(bar_s_full, j & 1);
       tc_fence_after();
-      if (!pv_pass || !two_pass) {
-        // row max over this tile
-        for (int c = 0; c < p.bkv; c += 16) {
-          float s[16];
-          tmem_ld16(tmem_s + lane_base + c, s);
-          tmem_ld_wait();
+      float s[BKV];
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c + i < kv_valid) m = fmaxf(m, s[i]);
-        }
+      for (int c = 0; c < BKV; c += LDW) {
+        if (LDW == 32) tmem_ld32(tmem_s + lane_base + c, s + c);
+        else tmem_ld16(tmem_s + lane_base + c, s + c);
       }
-      if (pv_pass) {
-        if (!two_pass || it == p.n_tiles) mc = m * p.scale_log2;
-        for (int c = 0; c < p.bkv; c += 16) {
-          float s[16];
-          tmem_ld16(tmem_s + lane_base + c, s);
-          tmem_ld_wait();
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_s_free);  // S is in registers: the next QK^T may overwrite it
+      if (kv_valid < BKV) {     // ragged last tile (seq is a multiple of 16)
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float e = (c + i < kv_valid) ? exp2f(fmaf(s[i], p.scale_log2, -mc)) : 0.f;
-            s[i] = e;
-            l += e;
-          }
-          // P[r, c..c+15] -> 128B-swizzled K-major tile (atom = 64 keys x 128 rows)
-          const uint32_t atom = smem_u32(sP) + (c >> 6) * (ATT_BM * 128) + r * 128;
-          const int ch = (c & 63) >> 3;
-          st_shared_16(atom + (((ch) ^ (r & 7)) << 4), s);
-          st_shared_16(atom + (((ch + 1) ^ (r & 7)) << 4), s + 8);
-        }
-        tc_fence_before();
-        fence_async_smem();
-        mbar_arrive(bar_p_ready);
+        for (int i = 0; i < BKV; ++i)
+          if (i >= kv_valid) s[i] = -INFINITY;
+      }
+      float mt = s[0];
+#pragma unroll
+      for (int i = 1; i + 1 < BKV; i += 2) mt = fmaxf(mt, fmaxf(s[i], s[i + 1]));
+      mt = fmaxf(mt, s[BKV - 1]);
+      if (j == 0) {
+        m = mt;
       } else {
-        tc_fence_before();
+        mbar_wait(bar_pv_done, (j - 1) & 1);  // P tile free again, O quiescent
+        tc_fence_after();
+        const bool grow = (mt - m) * p.scale_log2 > 8.f;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = fmaxf(m, mt);
+          const float f = exp2f((m - m_new) * p.scale_log2);
+          m = m_new;
+          l *= f;
+          for (int c = 0; c < p.n_o; c += 16) {
+            float o[16];
+            tmem_ld16(tmem_o + lane_base + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] *= f;
+            tmem_st16(tmem_o + lane_base + c, o);
+          }
+          tmem_st_wait();
+        }
       }
-      mbar_arrive(bar_s_free);
+      const float mc = m * p.scale_log2;
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < BKV; c += 8) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = ex2_fast(fmaf(s[c + i], p.scale_log2, -mc));
+        l0 += (e[0] + e[1]) + (e[2] + e[3]);
+        l1 += (e[4] + e[5]) + (e[6] + e[7]);
+        // P[r, c..c+7] -> 128B-swizzled K-major tile (atom = 64 keys x 128 rows)
+        const uint32_t atom = smem_u32(sP) + (c >> 6) * (ATT_BM * 128) + r * 128;
+        st_shared_16(atom + ((((c & 63) >> 3) ^ (r & 7)) << 4), e);
+      }
+      l += l0 + l1;
+      tc_fence_before();
+      fence_async_smem();
+      mbar_arrive(bar_p_ready);
     }
     // ---- epilogue: O / l
-    const int n_pv = p.n_tiles;
-    mbar_wait(bar_pv_done, (n_pv - 1) & 1);
+    mbar_wait(bar_pv_done, (p.n_tiles - 1) & 1);
     tc_fence_after();
     const int q = q0 + r;
     const bool valid = q < p.seq;
@@ -204,7 +245,9 @@ __global__ void __launch_bounds__(ATT_THREADS)
       if (!valid) continue;
 #pragma unroll
       for (int i = 0; i < 16; ++i) o[i] *= inv_l;
-      for (int i = 0; i < 16 && c + i < p.dhead; i += 8) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 8) {
+        if (c + i >= p.dhead) continue;
         __half2 h0 = __floats2half2_rn(o[i], o[i + 1]);
         __half2 h1 = __floats2half2_rn(o[i + 2], o[i + 3]);
         __half2 h2 = __floats2half2_rn(o[i + 4], o[i + 5]);
@@ -246,23 +289,41 @@ extern "C" int mvd_attn_self_f16(const void* q, const void* k, const void* vt, v
   p.heads = heads;
   p.dhead = dhead;
   p.dpad = dpad;
-  p.bkv = seq >= 128 ? 128 : seq;  // 16 <= bkv <= 128, multiple of 16
-  p.n_tiles = (seq + p.bkv - 1) / p.bkv;
   p.kd_steps = (dhead + 15) / 16;
   p.n_o = p.kd_steps * 16;
+  // key tile: the widest of {128, 64} (or the whole sequence) whose footprint lets two CTAs share an SM
+  // (<= 113 KB of shared memory and <= 256 TMEM columns each); otherwise the widest that fits at all.
+  auto up1k = [](int x) { return (x + 1023) & ~1023; };
+  auto layout = [&](int bkv) {
+    p.bkv = bkv;
+    p.n_tiles = (seq + bkv - 1) / bkv;
+    p.stages = p.n_tiles > 1 ? ATT_MAX_STAGES : 1;
+    const int atoms_kv = (bkv + 63) / 64;
+    p.k_stage = up1k(bkv * dpad * 2);
+    p.v_stage = up1k(atoms_kv * dpad * 128);
+    p.off_k = up1k(ATT_BM * dpad * 2);
+    p.off_v = p.off_k + p.stages * p.k_stage;
+    p.off_p = p.off_v + p.stages * p.v_stage;
+    p.off_bar = p.off_p + atoms_kv * ATT_BM * 128;
+    return p.off_bar + 128;
+  };
+  int smem_bytes = 0;
+  {
+    const int cands[4] = {128, 64, 32, 16};
+    int chosen = -1;
+    for (int i = 0; i < 4 && chosen < 0; ++i)
+      if (cands[i] <= seq && layout(cands[i]) <= 115712 && cands[i] + p.n_o <= 256) chosen = cands[i];
+    for (int i = 0; i < 4 && chosen < 0; ++i)
+      if (cands[i] <= seq && layout(cands[i]) <= 232448 && cands[i] + p.n_o <= 512) chosen = cands[i];
+    if (chosen < 0) return set_error(MVD_EINVAL, "mvd_attn_self_f16: tile does not fit in shared memory");
+    smem_bytes = layout(chosen);
+  }
   int cols = p.bkv + p.n_o;
   p.tmem_cols = 32;
   while (p.tmem_cols < cols) p.tmem_cols <<= 1;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dhead));
   p.out = static_cast<__half*>(out);
   p.ldo = ldo;
-  const int atoms_kv = (p.bkv + 63) / 64;
-  auto up1k = [](int x) { return (x + 1023) & ~1023; };
-  p.off_k = up1k(ATT_BM * dpad * 2);
-  p.off_v = p.off_k + up1k(p.bkv * dpad * 2);
-  p.off_p = p.off_v + up1k(atoms_kv * dpad * 128);
-  p.off_bar = p.off_p + atoms_kv * ATT_BM * 128;
-  const int smem_bytes = p.off_bar + 64 + 1024;
 
   const int BH = n_img * heads;
   CUtensorMap tmQ, tmK, tmV;
@@ -273,13 +334,16 @@ extern "C" int mvd_attn_self_f16(const void* q, const void* k, const void* vt, v
   rc = make_tmap_3d(&tmV, vt, seq, dpad, BH, seq, static_cast<long long>(seq) * dpad, 64, dpad, 1);
   if (rc != MVD_OK) return rc;
 
-  static int configured_smem = 0;
-  if (smem_bytes > configured_smem) {
-    MVD_CUDA_CHECK(cudaFuncSetAttribute(attn_self_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured_smem = smem_bytes;
+  typedef void (*AttnFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
+  AttnFn fn = p.bkv == 128 ? attn_self_kernel<128> : p.bkv == 64 ? attn_self_kernel<64> : p.bkv == 32 ? attn_self_kernel<32> : attn_self_kernel<16>;
+  static bool configured = false;
+  if (!configured) {
+    AttnFn all[] = {attn_self_kernel<128>, attn_self_kernel<64>, attn_self_kernel<32>, attn_self_kernel<16>};
+    for (AttnFn f : all) MVD_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    configured = true;
   }
   dim3 grid((seq + ATT_BM - 1) / ATT_BM, BH);
-  attn_self_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
+  fn<<<grid, ATT_THREADS, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

@@ -352,20 +352,43 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         qk_h = rem / p.dhead;
         qk_jj = rem - qk_h * p.dhead;
       }
+      float4 acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = rb + 16 * i;
+        acc[i] = lds_v4(stg + row * 128 + ((seg ^ (row & 7)) << 4));
+      }
+      if (is_split) {
+        // the other slices' partials of this chunk: 16 independent 16-byte loads in flight per step
+        const size_t tile_elems = static_cast<size_t>(BM) * ws_ld;
+        const float* wbase = p.ws + static_cast<size_t>(t.tile) * p.split * tile_elems + rb * ws_ld + c * 32 + seg * 4;
+        const int nother = p.split - 1;
+        for (int o = 0; o < nother; o += 2) {
+          const int sa = o < t.s ? o : o + 1;
+          const bool two = o + 1 < nother;
+          const int sb2 = two ? ((o + 1) < t.s ? o + 1 : o + 2) : sa;
+          const float* pa = wbase + sa * tile_elems;
+          const float* pb = wbase + sb2 * tile_elems;
+          float4 wa[8], wb[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            wa[i] = __ldcg(reinterpret_cast<const float4*>(pa + 16 * i * ws_ld));
+            wb[i] = __ldcg(reinterpret_cast<const float4*>(pb + 16 * i * ws_ld));
+          }
+          const float fb = two ? 1.f : 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            acc[i].x += wa[i].x + fb * wb[i].x; acc[i].y += wa[i].y + fb * wb[i].y;
+            acc[i].z += wa[i].z + fb * wb[i].z; acc[i].w += wa[i].w + fb * wb[i].w;
+          }
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = rb + 16 * i;
         const int grow = t.grow0 + row;
-        float4 v = lds_v4(stg + row * 128 + ((seg ^ (row & 7)) << 4));
+        float4 v = acc[i];
         const bool live = (grow < p.M) && nvalid > 0;
-        if (is_split && live) {
-          for (int s2 = 0; s2 < p.split; ++s2) {
-            if (s2 == t.s) continue;
-            const float* wp = p.ws + (static_cast<size_t>(t.tile) * p.split + s2) * (BM * ws_ld) + row * ws_ld + c * 32 + seg * 4;
-            const float4 w4 = __ldcg(reinterpret_cast<const float4*>(wp));
-            v.x += w4.x; v.y += w4.y; v.z += w4.z; v.w += w4.w;
-          }
-        }
         v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
         if (p.rowbias != nullptr && live) {
           const float4 r4 = ldg4(p.rowbias + static_cast<size_t>(grow / p.rows_per_group) * p.N + col, VEC || p.vec_rowbias != 0, nvalid);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstring>
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -92,7 +93,43 @@ static void run(int n_img, int heads, int seq, int dhead, int dpad, float amp) {
   cudaFree(dq); cudaFree(dk); cudaFree(dv); cudaFree(dout);
 }
 
-int main() {
+static void bench(int n_img, int heads, int seq, int dhead, int dpad) {
+  const int BH = n_img * heads;
+  const size_t nq = static_cast<size_t>(BH) * seq * dpad;
+  __half *dq, *dk, *dv, *dout;
+  CK(cudaMalloc(&dq, nq * 2)); CK(cudaMalloc(&dk, nq * 2)); CK(cudaMalloc(&dv, nq * 2));
+  CK(cudaMalloc(&dout, static_cast<size_t>(n_img) * seq * heads * dhead * 2));
+  CK(cudaMemset(dq, 0, nq * 2)); CK(cudaMemset(dk, 0, nq * 2)); CK(cudaMemset(dv, 0, nq * 2));
+  cudaStream_t st; CK(cudaStreamCreate(&st));
+  int rc = mvd_attn_self_f16(dq, dk, dv, dout, n_img, heads, seq, dhead, dpad, heads * dhead, st);
+  CK(cudaStreamSynchronize(st));
+  const int iters = 20;
+  cudaGraph_t graph; cudaGraphExec_t gexec;
+  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  for (int i = 0; i < iters; ++i) rc |= mvd_attn_self_f16(dq, dk, dv, dout, n_img, heads, seq, dhead, dpad, heads * dhead, st);
+  CK(cudaStreamEndCapture(st, &graph));
+  CK(cudaGraphInstantiate(&gexec, graph, 0));
+  CK(cudaGraphLaunch(gexec, st)); CK(cudaStreamSynchronize(st));
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, st); CK(cudaGraphLaunch(gexec, st)); cudaEventRecord(e1, st); CK(cudaStreamSynchronize(st));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  const double us = ms * 1e3 / iters;
+  printf("attn bench img=%d heads=%d seq=%d d=%d: rc=%d %.1f us  %.1f TF/s (4*seq^2*d)\n", n_img, heads, seq, dhead, rc, us,
+         4.0 * BH * seq * static_cast<double>(seq) * dhead / (us * 1e-6) / 1e12);
+  cudaFree(dq); cudaFree(dk); cudaFree(dv); cudaFree(dout);
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && strcmp(argv[1], "bench") == 0) {
+    bench(16, 8, 1024, 40, 64);
+    bench(16, 8, 256, 80, 128);
+    bench(16, 8, 64, 160, 192);
+    bench(16, 8, 16, 160, 192);
+    bench(16, 8, 4096, 40, 64);
+    return 0;
+  }
+  run(1, 2, 1024, 40, 64, 5.0f);
+  run(3, 8, 1024, 40, 64, 2.0f);
   run(1, 1, 16, 160, 192, 1.0f);
   run(2, 3, 64, 160, 192, 1.0f);
   run(1, 2, 128, 40, 64, 1.0f);

@@ -248,7 +248,7 @@ static void run(const Case& c) {
 
 // ---- timing mode: `gemm_check bench` — representative shapes of one denoising step (N=8 views x 2 CFG branches)
 struct BCase { const char* name; int M, N, K; int conv_img, conv_hw, conv_c; bool res; int act; int out_mode; int split; int tile_n; };
-static void bench(const BCase& c, int iters) {
+static double bench(const BCase& c, int iters, bool quiet = false) {
   const int ldw = (c.K + 7) / 8 * 8;
   const size_t wbytes = static_cast<size_t>(c.N) * ldw * 2;
   int ncopy = static_cast<int>((300ull << 20) / wbytes) + 1;  // rotate weight copies so they stream from HBM like in the real step
@@ -276,17 +276,30 @@ static void bench(const BCase& c, int iters) {
   }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   int rc = 0;
-  for (int i = 0; i < 3; ++i) { g.Wt = dW + (static_cast<size_t>(i % ncopy) * wbytes) / 2; rc |= mvd_gemm_f16(&g, nullptr); }
-  CK(cudaDeviceSynchronize());
-  cudaEventRecord(e0);
-  for (int i = 0; i < iters; ++i) { g.Wt = dW + (static_cast<size_t>(i % ncopy) * wbytes) / 2; rc |= mvd_gemm_f16(&g, nullptr); }
-  cudaEventRecord(e1);
-  CK(cudaDeviceSynchronize());
+  cudaStream_t st; CK(cudaStreamCreate(&st));
+  for (int i = 0; i < 3; ++i) { g.Wt = dW + (static_cast<size_t>(i % ncopy) * wbytes) / 2; rc |= mvd_gemm_f16(&g, st); }
+  CK(cudaStreamSynchronize(st));
+  // the launches are replayed from a CUDA graph, as in the real step: host-side launch cost is not part of the number
+  cudaGraph_t graph; cudaGraphExec_t gexec;
+  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  for (int i = 0; i < iters; ++i) { g.Wt = dW + (static_cast<size_t>(i % ncopy) * wbytes) / 2; rc |= mvd_gemm_f16(&g, st); }
+  CK(cudaStreamEndCapture(st, &graph));
+  CK(cudaGraphInstantiate(&gexec, graph, 0));
+  CK(cudaGraphLaunch(gexec, st));
+  CK(cudaStreamSynchronize(st));
+  cudaEventRecord(e0, st);
+  CK(cudaGraphLaunch(gexec, st));
+  cudaEventRecord(e1, st);
+  CK(cudaStreamSynchronize(st));
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  cudaGraphExecDestroy(gexec); cudaGraphDestroy(graph); cudaStreamDestroy(st);
   const double us = ms * 1e3 / iters;
-  printf("%-44s rc=%d %8.1f us  %7.1f TF/s\n", c.name, rc, us, 2.0 * c.M * c.N * c.K / (us * 1e-6) / 1e12);
-  if (rc) printf("   error: %s\n", mvd_last_error());
+  if (!quiet) {
+    printf("%-44s rc=%d %8.1f us  %7.1f TF/s\n", c.name, rc, us, 2.0 * c.M * c.N * c.K / (us * 1e-6) / 1e12);
+    if (rc) printf("   error: %s\n", mvd_last_error());
+  }
   cudaFree(dW); cudaFree(dA); cudaFree(dout); cudaFree(db); if (dres) cudaFree(dres);
+  return rc ? 1e30 : us;
 }
 static int bench_main(int only) {
   const BCase cs[] = {
@@ -327,7 +340,49 @@ static int bench_main(int only) {
   return 0;
 }
 
+// ---- `gemm_check tune`: sweep (tile_n, split_k) for the small-M / weight-bound shapes of the step; prints the best
+static int tune_main() {
+  struct T { int M, N, K, img, hw, c; bool res; };
+  const T ts[] = {
+      {256, 1280, 1280, 0, 0, 0, true},   {256, 1280, 2560, 0, 0, 0, false},  {256, 1280, 5120, 0, 0, 0, true},
+      {256, 1280, 768, 0, 0, 0, false},   {256, 1280, 11520, 16, 4, 1280, true}, {256, 1280, 23040, 16, 4, 2560, false},
+      {256, 1280, 11520, 0, 0, 0, false}, {1024, 1280, 1280, 0, 0, 0, true},  {1024, 1280, 5120, 0, 0, 0, true},
+      {1024, 1280, 2560, 0, 0, 0, false}, {1024, 1280, 1920, 0, 0, 0, false}, {1024, 1280, 640, 0, 0, 0, false},
+      {1024, 1280, 768, 0, 0, 0, false},  {1024, 640, 5760, 0, 0, 0, false},  {1024, 1280, 11520, 16, 8, 1280, true},
+      {1024, 1280, 23040, 16, 8, 2560, false}, {1024, 1280, 17280, 16, 8, 1920, false}, {1024, 1280, 5760, 16, 8, 640, false},
+      {4096, 640, 640, 0, 0, 0, true},    {4096, 640, 2560, 0, 0, 0, true},   {4096, 640, 5760, 16, 16, 640, true},
+      {4096, 640, 11520, 16, 16, 1280, false}, {4096, 1280, 11520, 16, 16, 1280, false}, {4096, 320, 2880, 0, 0, 0, false},
+      {4096, 640, 768, 0, 0, 0, false},   {16384, 320, 320, 0, 0, 0, true},   {16384, 320, 1280, 0, 0, 0, true},
+      {16384, 320, 2880, 16, 32, 320, true}, {16384, 320, 768, 0, 0, 0, false},
+  };
+  const int bns[] = {64, 96, 128, 160, 192, 256};
+  const int sps[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16};
+  for (const T& t : ts) {
+    double best = 1e30, dflt = 0; int bbn = 0, bsp = 0;
+    {
+      BCase c{"", t.M, t.N, t.K, t.img, t.hw, t.c, t.res, 0, MVD_OUT_F32, 0, 0};
+      dflt = bench(c, 20, true);
+    }
+    for (int bn : bns) {
+      if (t.N % bn != 0 && bn != 256) continue;
+      const int tiles = ((t.M + 127) / 128) * ((t.N + bn - 1) / bn);
+      for (int sp : sps) {
+        if (sp > 1 && tiles * sp > 148) continue;
+        if (sp > (t.K + 63) / 64) continue;
+        BCase c{"", t.M, t.N, t.K, t.img, t.hw, t.c, t.res, 0, MVD_OUT_F32, sp, bn};
+        const double us = bench(c, 20, true);
+        if (us < best) { best = us; bbn = bn; bsp = sp; }
+      }
+    }
+    printf("TUNE %s M=%d N=%d K=%d res=%d : default %.1f us ; best %.1f us tile_n=%d split_k=%d\n", t.img ? "conv" : "lin", t.M, t.N, t.K,
+           t.res ? 1 : 0, dflt, best, bbn, bsp);
+    fflush(stdout);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && strcmp(argv[1], "tune") == 0) return tune_main();
   if (argc > 1 && strcmp(argv[1], "bench") == 0) return bench_main(argc > 2 ? atoi(argv[2]) : -1);
   int only = argc > 1 ? atoi(argv[1]) : -1;
   std::vector<Case> cases;
