@@ -136,6 +136,12 @@ int mvd_im2col_s2_f32_f16(const float* x, void* y, int32_t n_img, int32_t H, int
  * ViewFusion.time_embed / cc_projection (viewfusion_zero_depth_rgb.py:107-132), DiT adaLN (view_attn_efficient2.py:58-61) */
 int mvd_gemv_f16(const float* x, int32_t ldx, const void* W, int32_t ldw, const float* bias, float* y, int32_t ldy,
                  int32_t M, int32_t N, int32_t K, int32_t silu_in, int32_t silu_out, void* stream);
+/* the same for a table of jobs that share ONE input row (M = 1), one launch: the 22 ResBlock.emb_layers of a UNet pass all
+ * read SiLU(emb) (openaimodel.py:218-224,266-270).  jobs_dev: int64 [n_jobs, 5] in device memory =
+ * {W (fp16 [N, ldw]), bias (fp32 [N] or 0), y (fp32 [N]), N | (int64)ldw << 32, first global column}; columns are
+ * numbered consecutively over the jobs, total_cols = sum of N; W rows must be 16-byte aligned (ldw % 8 == 0). */
+int mvd_gemv_grouped_f16(const float* x, int32_t K, int32_t silu_in, const void* jobs_dev, int32_t n_jobs,
+                         int32_t total_cols, void* stream);
 /* timestep_embedding (util.py:152-172): out[dim] = [cos(t f) | sin(t f)], t and f tables in device memory */
 int mvd_timestep_embedding(const float* t_dev, const float* freqs_dev, float* out, int32_t dim, void* stream);
 /* UNet input assembly incl. the unconditional CFG branch (mvdfusion/unet.py:153-161,173-186) -> fp16 NHWC */

@@ -9,7 +9,7 @@ from ctypes import c_char_p, c_float, c_int32, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmvd_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class GemmArgs(ctypes.Structure):
@@ -49,6 +49,7 @@ SIGNATURES = {
     "mvd_upsample2x_f32_f16": [vp, vp, i32, i32, i32, i32, vp],
     "mvd_im2col_s2_f32_f16": [vp, vp, i32, i32, i32, i32, vp],
     "mvd_gemv_f16": [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    "mvd_gemv_grouped_f16": [vp, i32, i32, vp, i32, i32, vp],
     "mvd_timestep_embedding": [vp, vp, vp, i32, vp],
     "mvd_unet_input_f16": [vp, vp, i32, vp, vp, i32, i32, i32, i32, vp],
     "mvd_cfg_ddim": [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp],

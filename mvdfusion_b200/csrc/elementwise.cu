@@ -130,6 +130,59 @@ __global__ void gemv_kernel(const float* __restrict__ x, int ldx, const __half* 
   }
 }
 
+// Grouped GEMV on one shared input row: y_j[n] = sum_k act_in(x[k]) * W_j[n, k] + b_j[n] for a table of jobs, one launch.
+// Used for the 22 ResBlock.emb_layers of a UNet pass (openaimodel.py:218-224,266-270): all of them see the same SiLU(emb).
+// jobs: int64 [n_jobs, 5] = {W ptr (fp16 [N, ldw]), bias ptr (fp32 or 0), y ptr (fp32), N | ldw << 32, first global column}.
+__global__ void gemv_grouped_kernel(const float* __restrict__ x, int K, int silu_in, const long long* __restrict__ jobs,
+                                    int n_jobs, int total_cols) {
+  extern __shared__ float gx[];  // act_in(x), K floats (zero-padded to a multiple of 8)
+  const int K8 = (K + 7) & ~7;
+  for (int k = threadIdx.x; k < K8; k += blockDim.x) {
+    float v = k < K ? x[k] : 0.f;
+    if (silu_in) v = v / (1.f + expf(-v));
+    gx[k] = v;
+  }
+  __syncthreads();
+  const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (col >= total_cols) return;
+  int j = 0;
+  while (j + 1 < n_jobs && col >= static_cast<int>(jobs[(j + 1) * 5 + 4])) ++j;
+  const long long* job = jobs + j * 5;
+  const int n = col - static_cast<int>(job[4]);
+  const int N = static_cast<int>(job[3] & 0xffffffffll);
+  const int ldw = static_cast<int>(job[3] >> 32);
+  if (n >= N) return;
+  const __half* w = reinterpret_cast<const __half*>(job[0]) + static_cast<size_t>(n) * ldw;
+  const float* bias = reinterpret_cast<const float*>(job[1]);
+  float* y = reinterpret_cast<float*>(job[2]);
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K8; k0 += 1024) {  // four independent 16-byte weight loads in flight per lane
+    uint4 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + i * 256 + lane * 8;
+      u[i] = k < K8 ? __ldg(reinterpret_cast<const uint4*>(w + k)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + i * 256 + lane * 8;
+      if (k < K8) {
+        const __half2* hp = reinterpret_cast<const __half2*>(&u[i]);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float2 f = __half22float2(hp[jj]);
+          acc = fmaf(gx[k + 2 * jj], f.x, acc);
+          acc = fmaf(gx[k + 2 * jj + 1], f.y, acc);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) y[n] = acc + (bias != nullptr ? bias[n] : 0.f);
+}
+
 // timestep_embedding (util.py:152-172 / mvdfusion/embedder.py:114-134): [cos(t*f_i) | sin(t*f_i)],
 // f_i = exp(-ln(max_period) * i / half) supplied as a host-built fp32 table (bit-identical to the
 // reference's torch.exp).  t is read from device memory (graph-replay friendly).
@@ -316,6 +369,19 @@ extern "C" int mvd_gemv_f16(const float* x, int32_t ldx, const void* W, int32_t 
   if ((ldw & 7) || ldw < ((K + 7) & ~7)) return set_error(MVD_EALIGN, "mvd_gemv_f16: ldw must be a multiple of 8 and >= K rounded up to 8");
   gemv_kernel<<<(N + 7) / 8, 256, 0, stream>>>(x, ldx, static_cast<const __half*>(W), ldw, bias, y, ldy, M, N, K, silu_in,
                                               silu_out);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_gemv_grouped_f16(const float* x, int32_t K, int32_t silu_in, const void* jobs_dev, int32_t n_jobs,
+                                    int32_t total_cols, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !jobs_dev || K <= 0 || K > 8192 || n_jobs <= 0 || total_cols <= 0)
+    return set_error(MVD_EINVAL, "mvd_gemv_grouped_f16: bad arguments");
+  const int K8 = (K + 7) & ~7;
+  gemv_grouped_kernel<<<(total_cols + 7) / 8, 256, K8 * sizeof(float), stream>>>(x, K, silu_in, static_cast<const long long*>(jobs_dev),
+                                                                             n_jobs, total_cols);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

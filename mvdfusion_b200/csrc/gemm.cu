@@ -573,16 +573,22 @@ static int num_sms() {
   return n;
 }
 
-// tile width: N <= 64 -> one tile of N rounded up to 16; else the multiple of 32 in [64, 256] that wastes the fewest
-// padded columns (ties -> wider).  (The epilogue walks 32-column chunks.)
-static int pick_bn(int N) {
+// tile width.  N <= 64: one tile of N rounded up to 16.  Otherwise the multiple of 32 in [64, 256] with the lowest
+// modelled time: rounds of the persistent loop x shared-memory rows filled per k-block (128 of A + bn of W; the
+// mainloop is bound by the L2 -> smem fill rate on this part, ~56 B/clk/SM measured) — which accounts for both the
+// wave quantisation over the SMs and the columns wasted by padding N up to a multiple of bn.
+static int pick_bn(int N, int tiles_m, int sms) {
   if (N <= 64) return (N + 15) / 16 * 16;
-  int best = 64, best_waste = 1 << 30;
+  int best = 64;
+  double best_cost = 1e300;
   for (int bn = 64; bn <= 256; bn += 32) {
-    const int waste = (N + bn - 1) / bn * bn - N;
-    if (waste <= best_waste) {
+    const int tiles = tiles_m * ((N + bn - 1) / bn);
+    const int rounds = (tiles + sms - 1) / sms;
+    // a machine that is less than half full will be split along K afterwards: compare per-tile work then
+    const double cost = (tiles * 2 <= sms) ? (128.0 + bn) * tiles / sms * 1.15 : static_cast<double>(rounds) * (128 + bn);
+    if (cost < best_cost * 0.999 || (cost <= best_cost * 1.001 && bn > best)) {
       best = bn;
-      best_waste = waste;
+      best_cost = cost;
     }
   }
   return best;
@@ -628,7 +634,10 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
 
   const bool geglu = a->act == MVD_ACT_GEGLU;
   int bn = a->tile_n;
-  if (bn == 0) bn = geglu ? 256 : pick_bn(a->N);
+  if (bn == 0) {
+    const int tm = a->a_mode == MVD_A_CONV3X3 ? (a->M + BM - 1) / BM : (a->M + BM - 1) / BM;
+    bn = geglu ? 256 : pick_bn(a->N, tm, num_sms());
+  }
   if (bn < 16 || bn > 256 || (bn & 15) != 0 || ((bn & 31) != 0 && bn < a->N))
     return set_error(MVD_EINVAL, "mvd_gemm_f16: tile_n must be 0, a multiple of 32 in [32, 256], or a multiple of 16 that covers N");
   if (geglu) {
@@ -762,6 +771,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
       case MVD_ACT_NONE * 1000 + MVD_OUT_F32 * 100 + 11: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 1, 1, true>; break;
       case MVD_ACT_NONE * 1000 + MVD_OUT_F16 * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 0, 0, true>; break;
       case MVD_ACT_NONE * 1000 + MVD_OUT_F16 * 100 + 10: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 1, 0, true>; break;
+      case MVD_ACT_NONE * 1000 + MVD_OUT_F16 * 100 + 11: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 1, 1, true>; break;
       case MVD_ACT_GELU * 1000 + MVD_OUT_F16 * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_GELU, MVD_OUT_F16, 0, 0, true>; break;
       case MVD_ACT_GELU * 1000 + MVD_OUT_F32 * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_GELU, MVD_OUT_F32, 0, 0, true>; break;
       case MVD_ACT_GEGLU * 1000 + MVD_OUT_F16 * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_GEGLU, MVD_OUT_F16, 0, 0, true>; break;
@@ -775,6 +785,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
                       gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 0, 0, true>, gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 0, 1, true>,
                       gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 1, 0, true>, gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 1, 1, true>,
                       gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 0, 0, true>, gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 1, 0, true>,
+                      gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 1, 1, true>,
                       gemm_tc_kernel<MVD_ACT_GELU, MVD_OUT_F16, 0, 0, true>, gemm_tc_kernel<MVD_ACT_GELU, MVD_OUT_F32, 0, 0, true>,
                       gemm_tc_kernel<MVD_ACT_GEGLU, MVD_OUT_F16, 0, 0, true>, gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_QKV_HEADS, 0, 0, true>};
     for (KernelFn f : all) MVD_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));

@@ -10,100 +10,100 @@
 namespace mvd {
 
 // ---------------------------------------------------------------------------- GroupNorm
-// Thread mapping shared by both passes: a block is `rows` x (C/4) threads; thread (row, cq) owns channels 4cq..4cq+3 and
-// walks pixels row, row+rows, ... of its block's pixel range, so every load is a float4 and a warp reads contiguous
-// memory.  stats[img][group] = {sum, sumsq} in double (zeroed by the host wrapper first).
-__global__ void gn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, int hw, int C, int cpg,
-                                int pix_per_block, int rows) {
-  extern __shared__ float gn_sm[];  // [rows][C] sums, then [rows][C] sums of squares
-  const int cq4 = C >> 2;
-  const int cq = threadIdx.x % cq4;
-  const int row = threadIdx.x / cq4;
+// One kernel, one pass over HBM: a CTA owns `gpc` consecutive groups (span = gpc * C/32 channels, a multiple of 8 so that
+// every pixel's slice is whole 32-byte sectors) of one image for ALL pixels.  It reads its slice once (float4, thread
+// (row, cq) owns channels 4cq..4cq+3 of pixels row, row+rows, ...), keeps it in shared memory when it fits, reduces
+// per-group sum / sum of squares (fp32 per-thread partials over a few dozen values, combined in fp64), then normalises,
+// applies gamma / beta (+SiLU) and writes the fp16 GEMM operand.  Slices too large for shared memory (C = 960 at 32x32)
+// are re-read from L2 in the second phase.
+template <bool CACHE>
+__global__ void __launch_bounds__(512)
+    gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    __half* __restrict__ y, int hw, int C, int cpg, int gpc, int rows, float eps, int apply_silu) {
+  extern __shared__ __align__(16) uint8_t gn_smem[];
+  const int span = gpc * cpg;
+  const int span4 = span >> 2;
+  float* part_s = reinterpret_cast<float*>(gn_smem);  // [rows][span]
+  float* part_q = part_s + rows * span;               // [rows][span]
+  float* s_mean = part_q + rows * span;               // [32]
+  float* s_rstd = s_mean + 32;                        // [32]
+  float4* cache = reinterpret_cast<float4*>(s_rstd + 32);  // [hw][span4] when CACHE
+
   const int img = blockIdx.y;
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(hw, p0 + pix_per_block);
-  const float4* base = reinterpret_cast<const float4*>(x + static_cast<size_t>(img) * hw * C) + cq;
+  const int c0 = blockIdx.x * span;  // first channel of this CTA's slice
+  const int cq = threadIdx.x % span4;
+  const int row = threadIdx.x / span4;
+  const bool active = row < rows;
+  const size_t pix_stride4 = static_cast<size_t>(C) >> 2;
+  const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(img) * hw * C + c0) + cq;
+
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-  int p = p0 + row;
-  for (; p + 3 * rows < p1; p += 4 * rows) {
-    float4 v[4];
+  if (active) {
+    int p = row;
+    for (; p + 3 * rows < hw; p += 4 * rows) {
+      float4 v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = __ldg(base + static_cast<size_t>(p + u * rows) * cq4);
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(src + static_cast<size_t>(p + u * rows) * pix_stride4);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
-      q[0] = fmaf(v[u].x, v[u].x, q[0]); q[1] = fmaf(v[u].y, v[u].y, q[1]);
-      q[2] = fmaf(v[u].z, v[u].z, q[2]); q[3] = fmaf(v[u].w, v[u].w, q[3]);
+      for (int u = 0; u < 4; ++u) {
+        if (CACHE) cache[(p + u * rows) * span4 + cq] = v[u];
+        s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
+        q[0] = fmaf(v[u].x, v[u].x, q[0]); q[1] = fmaf(v[u].y, v[u].y, q[1]);
+        q[2] = fmaf(v[u].z, v[u].z, q[2]); q[3] = fmaf(v[u].w, v[u].w, q[3]);
+      }
+    }
+    for (; p < hw; p += rows) {
+      const float4 v = __ldg(src + static_cast<size_t>(p) * pix_stride4);
+      if (CACHE) cache[p * span4 + cq] = v;
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      part_s[row * span + cq * 4 + k] = s[k];
+      part_q[row * span + cq * 4 + k] = q[k];
     }
   }
-  for (; p < p1; p += rows) {
-    const float4 v = __ldg(base + static_cast<size_t>(p) * cq4);
-    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-    q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
-  }
-  float* ssum = gn_sm;
-  float* ssq = gn_sm + rows * C;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    ssum[row * C + cq * 4 + k] = s[k];
-    ssq[row * C + cq * 4 + k] = q[k];
-  }
   __syncthreads();
-  // 32 groups x 8 lanes: lane l of group g sums channels g*cpg + l, l+8, ... over all rows
-  const int g = threadIdx.x >> 3, l = threadIdx.x & 7;
-  if (g < 32) {
-    double a = 0.0, b = 0.0;
-    for (int c = l; c < cpg; c += 8)
-      for (int rr = 0; rr < rows; ++rr) {
-        a += static_cast<double>(ssum[rr * C + g * cpg + c]);
-        b += static_cast<double>(ssq[rr * C + g * cpg + c]);
+  // warp w reduces local groups w, w + nwarps, ...: rows x cpg partials each, in double
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int n = rows * cpg;
+    for (int g = warp; g < gpc; g += nwarps) {
+      double a = 0.0, b = 0.0;
+      for (int i = lane; i < n; i += 32) {
+        const int rr = i / cpg, c = i - rr * cpg;
+        a += static_cast<double>(part_s[rr * span + g * cpg + c]);
+        b += static_cast<double>(part_q[rr * span + g * cpg + c]);
       }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o, 8);
-      b += __shfl_xor_sync(0xffffffffu, b, o, 8);
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (lane == 0) {
+        const double inv_cnt = 1.0 / (static_cast<double>(hw) * cpg);
+        const double mean = a * inv_cnt;
+        const double var = fmax(b * inv_cnt - mean * mean, 0.0);
+        s_mean[g] = static_cast<float>(mean);
+        s_rstd[g] = rsqrtf(static_cast<float>(var) + eps);
+      }
     }
-    if (l == 0) {
-      double* dst = stats + (static_cast<size_t>(img) * 32 + g) * 2;
-      atomicAdd(dst, a);
-      atomicAdd(dst + 1, b);
-    }
-  }
-}
-
-__global__ void gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ y,
-                                int hw, int C, int cpg, float eps, int apply_silu, int pix_per_block, int rows) {
-  __shared__ float s_mean[32], s_rstd[32];
-  const int cq4 = C >> 2;
-  const int cq = threadIdx.x % cq4;
-  const int row = threadIdx.x / cq4;
-  const int img = blockIdx.y;
-  if (threadIdx.x < 32) {
-    const double inv_cnt = 1.0 / (static_cast<double>(hw) * cpg);
-    const double* st = stats + (static_cast<size_t>(img) * 32 + threadIdx.x) * 2;
-    const double mean = st[0] * inv_cnt;
-    const double var = fmax(st[1] * inv_cnt - mean * mean, 0.0);
-    s_mean[threadIdx.x] = static_cast<float>(mean);
-    s_rstd[threadIdx.x] = rsqrtf(static_cast<float>(var) + eps);
   }
   __syncthreads();
+  if (!active) return;
   float sc[4], sh[4];  // y = x * sc + sh
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int c = cq * 4 + k;
-    const int g = c / cpg;
-    const float ga = __ldg(gamma + c);
+    const int cl = cq * 4 + k;
+    const int g = cl / cpg;
+    const float ga = __ldg(gamma + c0 + cl);
     sc[k] = s_rstd[g] * ga;
-    sh[k] = __ldg(beta + c) - s_mean[g] * s_rstd[g] * ga;
+    sh[k] = __ldg(beta + c0 + cl) - s_mean[g] * s_rstd[g] * ga;
   }
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(hw, p0 + pix_per_block);
-  const size_t img_off = static_cast<size_t>(img) * hw * cq4;
-  const float4* src = reinterpret_cast<const float4*>(x) + img_off + cq;
-  uint2* dst = reinterpret_cast<uint2*>(y) + img_off + cq;
-  for (int p = p0 + row; p < p1; p += rows) {
-    const float4 v = __ldg(src + static_cast<size_t>(p) * cq4);
+  uint2* dst = reinterpret_cast<uint2*>(y + static_cast<size_t>(img) * hw * C + c0) + cq;
+  for (int p = row; p < hw; p += rows) {
+    const float4 v = CACHE ? cache[p * span4 + cq] : __ldg(src + static_cast<size_t>(p) * pix_stride4);
     float o[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
     if (apply_silu) {
 #pragma unroll
@@ -114,7 +114,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, const double* __res
     uint2 u;
     u.x = *reinterpret_cast<uint32_t*>(&h0);
     u.y = *reinterpret_cast<uint32_t*>(&h1);
-    dst[static_cast<size_t>(p) * cq4] = u;
+    dst[static_cast<size_t>(p) * pix_stride4] = u;
   }
 }
 
@@ -196,25 +196,36 @@ extern "C" int mvd_groupnorm_f32_f16(const float* x, const float* gamma, const f
     return set_error(MVD_EINVAL, "mvd_groupnorm_f32_f16: C must be a multiple of 32");
   const int cpg = C / 32;
   if (C > 4096) return set_error(MVD_EINVAL, "mvd_groupnorm_f32_f16: C must be <= 4096");
-  MVD_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, static_cast<size_t>(n_img) * 32 * 2 * sizeof(double), stream));
-  const int cq4 = C / 4;
-  int rows = 512 / cq4;
-  if (rows < 1) rows = 1;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 7))
+    return set_error(MVD_EALIGN, "mvd_groupnorm_f32_f16: x must be 16-byte and y 8-byte aligned");
+  // groups per CTA: the smallest power of two whose channel span is a multiple of 8 (whole sectors per pixel), else of 4
+  int gpc = 0;
+  for (int g = 1; g <= 32 && gpc == 0; g <<= 1)
+    if (((g * cpg) & 7) == 0) gpc = g;
+  for (int g = 1; g <= 32 && gpc == 0; g <<= 1)
+    if (((g * cpg) & 3) == 0) gpc = g;
+  const int span = gpc * cpg;
+  const int span4 = span / 4;
+  if (span4 > 512) return set_error(MVD_EINVAL, "mvd_groupnorm_f32_f16: unsupported channel count");
+  int rows = 512 / span4;
   if (rows > hw) rows = hw;
-  if (rows * cq4 < 256) rows = (256 + cq4 - 1) / cq4;  // the group reduction needs 256 threads
-  const int threads = rows * cq4;
-  // enough blocks to cover the machine (~4 per SM), at least 4 pixels per thread
-  int chunks = (592 + n_img - 1) / n_img;
-  const int max_chunks = (hw + 4 * rows - 1) / (4 * rows);
-  if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks < 1) chunks = 1;
-  const int ppb = (hw + chunks - 1) / chunks;
-  chunks = (hw + ppb - 1) / ppb;
-  const size_t sm = static_cast<size_t>(2) * rows * C * sizeof(float);
-  gn_stats_kernel<<<dim3(chunks, n_img), threads, sm, stream>>>(x, static_cast<double*>(stats_ws), hw, C, cpg, ppb, rows);
-  count_launch();
-  gn_apply_kernel<<<dim3(chunks, n_img), threads, 0, stream>>>(x, static_cast<const double*>(stats_ws), gamma, beta,
-                                                             static_cast<__half*>(y), hw, C, cpg, eps, apply_silu, ppb, rows);
+  int threads = (rows * span4 + 31) / 32 * 32;
+  if (threads < 32 * 1) threads = 32;
+  const size_t fixed = static_cast<size_t>(2) * rows * span * sizeof(float) + 64 * sizeof(float);
+  const size_t cache_bytes = static_cast<size_t>(hw) * span * sizeof(float);
+  const bool use_cache = fixed + cache_bytes <= 200 * 1024;
+  const size_t sm = fixed + (use_cache ? cache_bytes : 0);
+  static bool configured = false;
+  if (!configured) {
+    MVD_CUDA_CHECK(cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    configured = true;
+  }
+  (void)stats_ws;
+  const dim3 grid(32 / gpc, n_img);
+  if (use_cache)
+    gn_fused_kernel<true><<<grid, threads, sm, stream>>>(x, gamma, beta, static_cast<__half*>(y), hw, C, cpg, gpc, rows, eps, apply_silu);
+  else
+    gn_fused_kernel<false><<<grid, threads, sm, stream>>>(x, gamma, beta, static_cast<__half*>(y), hw, C, cpg, gpc, rows, eps, apply_silu);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

@@ -179,6 +179,7 @@ class Builder:
         self.prog = program if program is not None else Program()
         self.arena = arena if arena is not None else Arena(ops)
         self._qkv_bufs = {}
+        self._emb_vectors = {}
         self._stats = None
         self._ws = None
         self.heads = 8
@@ -252,6 +253,19 @@ class Builder:
         self.prog.append(self.ops.cast(x, y, rows * C))
         return y
 
+    def emb_vectors(self, emb, emb_dim, blocks):
+        """emb_layers (SiLU -> Linear) of every ResBlock in `blocks` [(prefix, C_out)] on the shared timestep embedding,
+        as ONE grouped launch (openaimodel.py:218-224,266-270); the conv bias in_layers.2.bias is folded in."""
+        total = sum(c for _, c in blocks)
+        buf = self.ops.empty((total,), torch.float32)
+        jobs, off = [], 0
+        for p, c in blocks:
+            y = buf[off:off + c]
+            off += c
+            jobs.append((self.W.lin(p + ".emb_layers.1.weight"), self.W.f32_sum(p + ".emb_layers.1.bias", p + ".in_layers.2.bias"), y))
+            self._emb_vectors[p] = y.view(1, c)
+        self.prog.append(self.ops.gemv_grouped(emb, emb_dim, jobs, silu_in=True))
+
     # -- ResBlock
     def resblock(self, x, p, n_img, H, Cin, Cout, emb, emb_dim):
         """ResBlock._forward (openaimodel.py:255-275): GN-SiLU-conv, + Linear(SiLU(emb)), GN-SiLU-conv, + skip.
@@ -259,10 +273,14 @@ class Builder:
         hw, M = H * H, n_img * H * H
         a = self.groupnorm(x, p + ".in_layers.0", n_img, hw, Cin, 1e-5, True)
         ne = emb.shape[0]  # 1 on the path (shared t); n_img when a caller passes per-image embeddings
-        eb = self.t32(ne, Cout)
-        self.prog.append(self.ops.gemv(emb, self.W.lin(p + ".emb_layers.1.weight"),
-                                       self.W.f32_sum(p + ".emb_layers.1.bias", p + ".in_layers.2.bias"), eb, ne, Cout,
-                                       emb_dim, silu_in=True))
+        pre = self._emb_vectors.get(p) if ne == 1 else None
+        if pre is not None:  # computed with every other ResBlock's vector by one grouped launch (emb_vectors)
+            eb = pre
+        else:
+            eb = self.t32(ne, Cout)
+            self.prog.append(self.ops.gemv(emb, self.W.lin(p + ".emb_layers.1.weight"),
+                                           self.W.f32_sum(p + ".emb_layers.1.bias", p + ".in_layers.2.bias"), eb, ne, Cout,
+                                           emb_dim, silu_in=True))
         if ne == 1:
             h = self.conv3x3(a, p + ".in_layers.2.weight", n_img, H, H, Cin, Cout, bias=eb)
         else:
@@ -320,15 +338,16 @@ class Builder:
         self.free(ao, h)
         return h2
 
-    def feed_forward(self, h, p, norm, M, C):
-        """x = ff(norm3(x)) + x with the GEGLU fused into the first GEMM's epilogue.  attention.py:37-64,222"""
+    def feed_forward(self, h, p, norm, M, C, out16=False):
+        """x = ff(norm3(x)) + x with the GEGLU fused into the first GEMM's epilogue.  attention.py:37-64,222
+        out16: the block output only feeds proj_out, so it is written once, as that GEMM's fp16 operand."""
         ln = self.layernorm(h, norm, M, C)
         inner = 4 * C
         wg, bg = self.W.geglu(p + ".net.0.proj", GEGLU_TILE)
         g = self.t16(M, inner)
         self.gemm(ln, wg, g, M, 2 * inner, C, bias=bg, act=ACT_GEGLU, tile_n=GEGLU_TILE, ldc=inner)
         self.free(ln)
-        h2 = self.t32(M, C)
+        h2 = self.t16(M, C) if out16 else self.t32(M, C)
         self.gemm(g, self.W.lin(p + ".net.2.weight"), h2, M, C, inner, allow_split=True, bias=self.W.f32(p + ".net.2.bias"),
                   residual=h, ldr=C)
         self.free(g, h)
@@ -345,9 +364,7 @@ class Builder:
         self.free(a)
         tb = p + ".transformer_blocks.0"
         h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C, rowbias=clipvec)
-        h = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C)
-        h16 = self.cast16(h, M, C)
-        self.free(h)
+        h16 = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C, out16=True)
         out = self.t32(M, C)
         self.gemm(h16, self.W.lin(p + ".proj_out.weight"), out, M, C, C, allow_split=True, bias=self.W.f32(p + ".proj_out.bias"),
                   residual=x, ldr=C)
@@ -400,9 +417,7 @@ class Builder:
         tb = p + ".aligned_attn_transformer_blocks.0"
         h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C)
         h = self.view_cross_attention(h, tb + ".attn2", tb + ".norm2", ctx16, M, D, C)
-        h = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C)
-        h16 = self.cast16(h, M, C)
-        self.free(h)
+        h16 = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C, out16=True)
         out = self.t32(M, C)
         self.gemm(h16, self.W.lin(p + ".aligned_attn_proj_out.weight"), out, M, C, C, allow_split=True,
                   bias=self.W.f32(p + ".aligned_attn_proj_out.bias"), residual=x, ldr=C)
@@ -490,6 +505,13 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
     [n_img, C] fp32; pyramid16: list of fp16 [n_img*H_l*H_l*D, 768].  Returns the head output fp32 [n_img*S*S, 8]."""
     b.heads = spec.heads
     emb = b.time_mlp(t_dev, freqs, spec.mc, "time_embed.0", "time_embed.2", spec.emb_dim, spec.emb_dim)
+    res_blocks = []
+    for name, blocks in (("input_blocks", spec.input_blocks), ("middle_block", [spec.middle]), ("output_blocks", spec.output_blocks)):
+        for i, layers in enumerate(blocks):
+            for j, l in enumerate(layers):
+                if l[0] == "res":
+                    res_blocks.append((f"{name}.{j}" if name == "middle_block" else f"{name}.{i}.{j}", l[2]))
+    b.emb_vectors(emb, spec.emb_dim, res_blocks)
     H = S
     hs = []
 

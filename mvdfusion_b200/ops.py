@@ -166,6 +166,17 @@ class NativeOps:
                                            ldy if ldy is not None else y.shape[-1], M, N, K, int(silu_in),
                                            int(silu_out)), (x, W, bias, y))
 
+    def gemv_grouped(self, x, K, jobs, *, silu_in=False):
+        """jobs: list of (W fp16 [N, ldw], bias fp32 [N] or None, y fp32 [N]); all read the single input row x[:K]."""
+        rows, col0 = [], 0
+        for W, bias, y in jobs:
+            N = y.numel()
+            rows.append([_ptr(W, torch.float16), _ptr(bias, torch.float32) or 0, _ptr(y, torch.float32), N | (W.shape[-1] << 32), col0])
+            col0 += N
+        table = torch.tensor(rows, dtype=torch.int64).to(self.device)
+        return self._bind("mvd_gemv_grouped_f16", (_ptr(x, torch.float32), K, int(silu_in), _ptr(table, torch.int64), len(jobs), col0),
+                          (x, table, jobs), {"desc": f"jobs{len(jobs)} cols{col0} K{K}", "bytes": 2.0 * col0 * K})
+
     def timestep_embedding(self, t_dev, freqs, out, dim):
         return self._bind("mvd_timestep_embedding", (_ptr(t_dev, torch.float32), _ptr(freqs, torch.float32),
                                                      _ptr(out, torch.float32), dim), (t_dev, freqs, out))

@@ -177,6 +177,18 @@ class TorchOpsDouble:
             y.reshape(-1)[: M * ldy_].reshape(M, ldy_)[:, :N] = o
         return self._call(fn)
 
+    def gemv_grouped(self, x, K, jobs, *, silu_in=False):
+        def fn():
+            a = x.reshape(-1)[:K]
+            if silu_in:
+                a = F.silu(a)
+            for W, bias, y in jobs:
+                o = W[:, :K].float() @ a
+                if bias is not None:
+                    o = o + bias.reshape(-1)[: o.shape[0]]
+                y.reshape(-1)[: o.shape[0]].copy_(o)
+        return self._call(fn)
+
     def timestep_embedding(self, t_dev, freqs, out, dim):
         def fn():
             a = t_dev.reshape(-1)[0] * freqs

@@ -59,7 +59,7 @@ def test_gemm_splitk_rowbias(nat, dbl):
     M, N, K = 256, 1280, 11520
     t = {"A": rnd(M, K, dtype=torch.float16), "W": rnd(N, K, dtype=torch.float16, seed=1, scale=K ** -0.5),
          "rb": rnd(4, N, seed=2), "res": rnd(M, N, seed=3), "out": torch.zeros(M, N), "ws": torch.zeros(32 << 20, dtype=torch.uint8)}
-    for split in (8, 0, 15):  # explicit, automatic, and a slice count that does not divide the k-blocks
+    for split in (8, 0, 13):  # explicit, automatic, and a slice count that does not divide the k-blocks
         run_both(nat, dbl, "gemm", t, ["out"], "A", "W", "out", M, N, K, rowbias="rb", rows_per_group=64, residual="res", ldr=N,
                  split_k=split, ws="ws")
 
@@ -140,6 +140,22 @@ def test_data_movement(nat, dbl):
     run_both(nat, dbl, "nchw_to_rows", t, ["r"], "x", "r", 2, 10, 64)
     t["r"] = rnd(2 * 64, 10)
     run_both(nat, dbl, "rows_to_nchw", t, ["z"], "r", "z", 2, 10, 10, 64)
+
+
+def test_gemv_grouped(nat, dbl):
+    K = 1280
+    x = rnd(1, K, seed=5)
+    sizes = (320, 640, 1280, 40, 1280)
+    Ws = [rnd(n, K, dtype=torch.float16, seed=10 + i, scale=K ** -0.5) for i, n in enumerate(sizes)]
+    bs = [rnd(n, seed=20 + i) if i != 3 else None for i, n in enumerate(sizes)]
+    y_cpu = [torch.zeros(n) for n in sizes]
+    y_gpu = [torch.zeros(n).cuda() for n in sizes]
+    dbl.gemv_grouped(x, K, list(zip(Ws, bs, y_cpu)), silu_in=True)(None)
+    nat.gemv_grouped(x.cuda(), K, [(w.cuda(), b.cuda() if b is not None else None, y) for w, b, y in zip(Ws, bs, y_gpu)],
+                     silu_in=True)(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for a, b in zip(y_gpu, y_cpu):
+        assert (a.cpu() - b).abs().max().item() <= 1e-4 * (b.abs().max().item() + 1e-6)
 
 
 def test_gemv_and_timestep(nat, dbl):
