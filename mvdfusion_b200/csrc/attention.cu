@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   const int atoms_d = p.dpad / 64;         // 64-wide k atoms of Q / K tiles
   const int atoms_kv = (BKV + 63) / 64;  // 64-key atoms of the P / Vt tiles
 
+  pdl_trigger();
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023) != 0) __trap();  // swizzled tiles need the 1024-byte base
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   if (warp == 5) {
     if (lane == 0) {
       // ---------------------------------------------------------------- TMA producer
+      pdl_wait();  // q / k / v^T come from the QKV GEMM just before us
       const uint32_t q_bytes = ATT_BM * p.dpad * 2;
       const uint32_t kv_bytes = BKV * p.dpad * 2 + atoms_kv * p.dpad * 128;
       mbar_expect_tx(bar_q, q_bytes);
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     }
   } else {
     // ------------------------------------------------------------------ one thread per query row
+    pdl_wait();  // `out` may alias a buffer the predecessor is still reading
     const int r = warp * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
     float m = -INFINITY;  // reference maximum of the raw scores (may lag the true running maximum by <= 8 / scale_log2)
@@ -343,7 +346,7 @@ extern "C" int mvd_attn_self_f16(const void* q, const void* k, const void* vt, v
     configured = true;
   }
   dim3 grid((seq + ATT_BM - 1) / ATT_BM, BH);
-  fn<<<grid, ATT_THREADS, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
+  MVD_CUDA_CHECK(launch_kernel(fn, grid, dim3(ATT_THREADS), static_cast<size_t>(smem_bytes), stream, 1, tmQ, tmK, tmV, p));
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace mvd {
@@ -16,6 +17,11 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("MVD_NO_PDL") == nullptr;
+  return on;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

@@ -19,6 +19,38 @@ void count_launch(int n = 1);
       return ::mvd::set_error(MVD_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
   } while (0)
 
+// Launch with programmatic dependent launch enabled (MVD_NO_PDL=1 in the environment turns the attribute off) and an
+// optional thread-block cluster along x.  Works under stream capture: the edge becomes a programmatic graph dependency.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define MVD_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  MVD_CUDA_CHECK(::mvd::launch_kernel(kernel, dim3(grid), dim3(block), smem, stream, 1, __VA_ARGS__))
+
 // fp16 row-major matrix [rows, ld] of which [rows, cols] is addressable; box = box_cols x box_rows, 128B swizzle.
 int make_tmap_2d(CUtensorMap* out, const void* base, int cols, int rows, int ld, int box_cols, int box_rows);
 // fp16 3-D tensor [d2, d1, d0] with strides (ld1, ld2 elements); box (b0, b1, b2), 128B swizzle.

@@ -16,6 +16,8 @@ __device__ __forceinline__ uint2 pack4(float a, float b, float c, float d) {
 }
 
 __global__ void cast_f32_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, size_t n4) {
+  pdl_trigger();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -26,6 +28,8 @@ __global__ void cast_f32_f16_kernel(const float* __restrict__ x, __half* __restr
 // out[r, 0:C1] = a[r, :], out[r, C1:C1+C2] = b[r, :]   (torch.cat([h, hs.pop()], dim=1), mvdfusion/unet.py:550)
 __global__ void concat_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                                   int C1, int C2, size_t total4) {
+  pdl_trigger();
+  pdl_wait();
   const int C = C1 + C2;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -44,6 +48,8 @@ __global__ void concat_f32_kernel(const float* __restrict__ a, const float* __re
 // F.interpolate(scale_factor=2, mode='nearest') (openaimodel.py:116): fp32 [n,H,W,C] -> fp16 [n,2H,2W,C]
 __global__ void upsample2x_kernel(const float* __restrict__ x, __half* __restrict__ y, int H, int W, int C,
                                   size_t total4) {
+  pdl_trigger();
+  pdl_wait();
   const int W2 = 2 * W, H2 = 2 * H;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -63,6 +69,8 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, __half* __restric
 // fp32 [n,H,W,C] -> fp16 [n*(H/2)*(W/2), 9*C], k = (ky*3+kx)*C + c
 __global__ void im2col_s2_kernel(const float* __restrict__ x, __half* __restrict__ y, int H, int W, int C,
                                  size_t total4) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2, K = 9 * C;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -87,6 +95,8 @@ __global__ void im2col_s2_kernel(const float* __restrict__ x, __half* __restrict
 __global__ void gemv_kernel(const float* __restrict__ x, int ldx, const __half* __restrict__ W, int ldw,
                             const float* __restrict__ bias, float* __restrict__ y, int ldy, int M, int N, int K,
                             int silu_in, int silu_out) {
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -135,6 +145,8 @@ __global__ void gemv_kernel(const float* __restrict__ x, int ldx, const __half* 
 // jobs: int64 [n_jobs, 5] = {W ptr (fp16 [N, ldw]), bias ptr (fp32 or 0), y ptr (fp32), N | ldw << 32, first global column}.
 __global__ void gemv_grouped_kernel(const float* __restrict__ x, int K, int silu_in, const long long* __restrict__ jobs,
                                     int n_jobs, int total_cols) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float gx[];  // act_in(x), K floats (zero-padded to a multiple of 8)
   const int K8 = (K + 7) & ~7;
   for (int k = threadIdx.x; k < K8; k += blockDim.x) {
@@ -188,6 +200,8 @@ __global__ void gemv_grouped_kernel(const float* __restrict__ x, int K, int silu
 // reference's torch.exp).  t is read from device memory (graph-replay friendly).
 __global__ void timestep_embed_kernel(const float* __restrict__ t_ptr, const float* __restrict__ freqs,
                                       float* __restrict__ out, int dim) {
+  pdl_trigger();
+  pdl_wait();
   const int half = dim / 2;
   const float t = *t_ptr;
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
@@ -206,6 +220,8 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t_ptr, const flo
 __global__ void unet_input_kernel(const float* __restrict__ noisy /*[n,5,hw]*/, const float* __restrict__ cond /*[1 or n,5,hw]*/,
                                   int cond_batched, const float* __restrict__ cond_scale, __half* __restrict__ out,
                                   int n_views, int n_img, int hw, int Cpad) {
+  pdl_trigger();
+  pdl_wait();
   const size_t total = static_cast<size_t>(n_img) * hw;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -234,6 +250,8 @@ __global__ void unet_input_kernel(const float* __restrict__ noisy /*[n,5,hw]*/, 
 __global__ void cfg_ddim_kernel(const float* __restrict__ head, int ld, int two_branch, const float* __restrict__ coef,
                                 const float* __restrict__ xt, const float* __restrict__ noise, float* __restrict__ eps_out,
                                 float* __restrict__ x_prev, float* __restrict__ x0_out, int n, int hw) {
+  pdl_trigger();
+  pdl_wait();
   const size_t total = static_cast<size_t>(n) * 5 * hw;
   const float w = coef[5];
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -263,6 +281,8 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ head, int ld, int two_
 
 // NCHW fp32 <-> rows x channels fp32 (public per-module entry points only; the fused path never transposes)
 __global__ void nchw_to_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int hw, size_t total) {
+  pdl_trigger();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % C);
@@ -273,6 +293,8 @@ __global__ void nchw_to_rows_kernel(const float* __restrict__ x, float* __restri
 }
 __global__ void rows_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int ld, int hw,
                                     size_t total) {
+  pdl_trigger();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const size_t pix = i % hw;
@@ -286,17 +308,23 @@ __global__ void rows_to_nchw_kernel(const float* __restrict__ x, float* __restri
 // step counter, so that one captured CUDA graph replays every DDIM iteration (mvdfusion/sampler.py:119-142).
 __global__ void gather_rows_kernel(const float* __restrict__ table, long long row_len, const int* __restrict__ idx,
                                    float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const float* src = table + static_cast<long long>(*idx) * row_len;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < row_len;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     out[i] = src[i];
 }
-__global__ void increment_kernel(int* p, int delta) { *p += delta; }
+__global__ void increment_kernel(int* p, int delta) {
+  pdl_trigger();
+  pdl_wait(); *p += delta; }
 
 // NCHW fp32 [n, C, hw] -> NHWC fp16 [n, hw, Cpad] (channels >= C zero-filled): input of the stem conv when a caller
 // hands UNetModel.forward an already-assembled tensor (mvdfusion/unet.py:524).
 __global__ void nchw_to_nhwc_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, int C, int hw, int Cpad,
                                         size_t total) {
+  pdl_trigger();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % Cpad);
@@ -320,7 +348,7 @@ using namespace mvd;
 extern "C" int mvd_cast_f32_f16(const float* x, void* y, long long n, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !y || n <= 0 || (n & 3)) return set_error(MVD_EINVAL, "mvd_cast_f32_f16: n must be a positive multiple of 4");
-  cast_f32_f16_kernel<<<grid_for(n / 4), 256, 0, stream>>>(x, static_cast<__half*>(y), static_cast<size_t>(n / 4));
+  MVD_LAUNCH((cast_f32_f16_kernel), grid_for(n / 4), 256, 0, stream, x, static_cast<__half*>(y), static_cast<size_t>(n / 4));
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -332,7 +360,7 @@ extern "C" int mvd_concat_f32(const float* a, const float* b, float* out, long l
   if (!a || !b || !out || rows <= 0 || C1 <= 0 || C2 <= 0 || (C1 & 3) || (C2 & 3))
     return set_error(MVD_EINVAL, "mvd_concat_f32: channel counts must be multiples of 4");
   const size_t total4 = static_cast<size_t>(rows) * (C1 + C2) / 4;
-  concat_f32_kernel<<<grid_for(total4), 256, 0, stream>>>(a, b, out, C1, C2, total4);
+  MVD_LAUNCH((concat_f32_kernel), grid_for(total4), 256, 0, stream, a, b, out, C1, C2, total4);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -343,7 +371,7 @@ extern "C" int mvd_upsample2x_f32_f16(const float* x, void* y, int32_t n_img, in
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !y || n_img <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return set_error(MVD_EINVAL, "mvd_upsample2x_f32_f16: bad arguments");
   const size_t total4 = static_cast<size_t>(n_img) * H * W * 4 * C / 4;
-  upsample2x_kernel<<<grid_for(total4), 256, 0, stream>>>(x, static_cast<__half*>(y), H, W, C, total4);
+  MVD_LAUNCH((upsample2x_kernel), grid_for(total4), 256, 0, stream, x, static_cast<__half*>(y), H, W, C, total4);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -355,7 +383,7 @@ extern "C" int mvd_im2col_s2_f32_f16(const float* x, void* y, int32_t n_img, int
   if (!x || !y || n_img <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || C <= 0 || (C & 3))
     return set_error(MVD_EINVAL, "mvd_im2col_s2_f32_f16: bad arguments");
   const size_t total4 = static_cast<size_t>(n_img) * (H / 2) * (W / 2) * 9 * C / 4;
-  im2col_s2_kernel<<<grid_for(total4), 256, 0, stream>>>(x, static_cast<__half*>(y), H, W, C, total4);
+  MVD_LAUNCH((im2col_s2_kernel), grid_for(total4), 256, 0, stream, x, static_cast<__half*>(y), H, W, C, total4);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -367,7 +395,7 @@ extern "C" int mvd_gemv_f16(const float* x, int32_t ldx, const void* W, int32_t 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !W || !y || M <= 0 || N <= 0 || K <= 0) return set_error(MVD_EINVAL, "mvd_gemv_f16: bad arguments");
   if ((ldw & 7) || ldw < ((K + 7) & ~7)) return set_error(MVD_EALIGN, "mvd_gemv_f16: ldw must be a multiple of 8 and >= K rounded up to 8");
-  gemv_kernel<<<(N + 7) / 8, 256, 0, stream>>>(x, ldx, static_cast<const __half*>(W), ldw, bias, y, ldy, M, N, K, silu_in,
+  MVD_LAUNCH((gemv_kernel), (N + 7) / 8, 256, 0, stream, x, ldx, static_cast<const __half*>(W), ldw, bias, y, ldy, M, N, K, silu_in,
                                               silu_out);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
@@ -380,7 +408,7 @@ extern "C" int mvd_gemv_grouped_f16(const float* x, int32_t K, int32_t silu_in, 
   if (!x || !jobs_dev || K <= 0 || K > 8192 || n_jobs <= 0 || total_cols <= 0)
     return set_error(MVD_EINVAL, "mvd_gemv_grouped_f16: bad arguments");
   const int K8 = (K + 7) & ~7;
-  gemv_grouped_kernel<<<(total_cols + 7) / 8, 256, K8 * sizeof(float), stream>>>(x, K, silu_in, static_cast<const long long*>(jobs_dev),
+  MVD_LAUNCH((gemv_grouped_kernel), (total_cols + 7) / 8, 256, K8 * sizeof(float), stream, x, K, silu_in, static_cast<const long long*>(jobs_dev),
                                                                              n_jobs, total_cols);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
@@ -391,7 +419,7 @@ extern "C" int mvd_timestep_embedding(const float* t_dev, const float* freqs_dev
                                       void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!t_dev || !freqs_dev || !out || dim < 2) return set_error(MVD_EINVAL, "mvd_timestep_embedding: bad arguments");
-  timestep_embed_kernel<<<1, 256, 0, stream>>>(t_dev, freqs_dev, out, dim);
+  MVD_LAUNCH((timestep_embed_kernel), 1, 256, 0, stream, t_dev, freqs_dev, out, dim);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -403,7 +431,7 @@ extern "C" int mvd_unet_input_f16(const float* noisy, const float* cond, int32_t
   if (!noisy || !cond || !out || n_views <= 0 || (n_img != n_views && n_img != 2 * n_views) || hw <= 0 || Cpad < 10 ||
       (Cpad & 7))
     return set_error(MVD_EINVAL, "mvd_unet_input_f16: bad arguments");
-  unet_input_kernel<<<grid_for(static_cast<size_t>(n_img) * hw), 256, 0, stream>>>(
+  MVD_LAUNCH((unet_input_kernel), grid_for(static_cast<size_t>(n_img) * hw), 256, 0, stream, 
       noisy, cond, cond_batched, cond_scale, static_cast<__half*>(out), n_views, n_img, hw, Cpad);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
@@ -417,7 +445,7 @@ extern "C" int mvd_cfg_ddim(const float* head, int32_t ld, int32_t two_branch, c
   if (!head || !coef_dev || n_views <= 0 || hw <= 0 || ld < 5) return set_error(MVD_EINVAL, "mvd_cfg_ddim: bad arguments");
   if (xt != nullptr && (x_prev == nullptr || noise == nullptr)) return set_error(MVD_EINVAL, "mvd_cfg_ddim: x_prev and noise required with xt");
   if (xt == nullptr && eps_out == nullptr) return set_error(MVD_EINVAL, "mvd_cfg_ddim: nothing to write");
-  cfg_ddim_kernel<<<grid_for(static_cast<size_t>(n_views) * 5 * hw), 256, 0, stream>>>(
+  MVD_LAUNCH((cfg_ddim_kernel), grid_for(static_cast<size_t>(n_views) * 5 * hw), 256, 0, stream, 
       head, ld, two_branch, coef_dev, xt, noise, eps_out, x_prev, x0_out, n_views, hw);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
@@ -428,7 +456,7 @@ extern "C" int mvd_nchw_to_rows_f32(const float* x, float* y, int32_t n_img, int
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !y || n_img <= 0 || C <= 0 || hw <= 0) return set_error(MVD_EINVAL, "mvd_nchw_to_rows_f32: bad arguments");
   const size_t total = static_cast<size_t>(n_img) * C * hw;
-  nchw_to_rows_kernel<<<grid_for(total), 256, 0, stream>>>(x, y, C, hw, total);
+  MVD_LAUNCH((nchw_to_rows_kernel), grid_for(total), 256, 0, stream, x, y, C, hw, total);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -439,7 +467,7 @@ extern "C" int mvd_rows_to_nchw_f32(const float* x, float* y, int32_t n_img, int
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !y || n_img <= 0 || C <= 0 || hw <= 0 || ld < C) return set_error(MVD_EINVAL, "mvd_rows_to_nchw_f32: bad arguments");
   const size_t total = static_cast<size_t>(n_img) * C * hw;
-  rows_to_nchw_kernel<<<grid_for(total), 256, 0, stream>>>(x, y, C, ld, hw, total);
+  MVD_LAUNCH((rows_to_nchw_kernel), grid_for(total), 256, 0, stream, x, y, C, ld, hw, total);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -449,7 +477,7 @@ extern "C" int mvd_gather_rows_f32(const float* table, long long row_len, const 
                                    void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!table || !idx_dev || !out || row_len <= 0) return set_error(MVD_EINVAL, "mvd_gather_rows_f32: bad arguments");
-  gather_rows_kernel<<<grid_for(static_cast<size_t>(row_len)), 256, 0, stream>>>(table, row_len, idx_dev, out);
+  MVD_LAUNCH((gather_rows_kernel), grid_for(static_cast<size_t>(row_len)), 256, 0, stream, table, row_len, idx_dev, out);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -458,7 +486,7 @@ extern "C" int mvd_gather_rows_f32(const float* table, long long row_len, const 
 extern "C" int mvd_increment_i32(int32_t* p, int32_t delta, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!p) return set_error(MVD_EINVAL, "mvd_increment_i32: null pointer");
-  increment_kernel<<<1, 1, 0, stream>>>(p, delta);
+  MVD_LAUNCH((increment_kernel), 1, 1, 0, stream, p, delta);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -469,7 +497,7 @@ extern "C" int mvd_nchw_to_nhwc_f16(const float* x, void* y, int32_t n_img, int3
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !y || n_img <= 0 || C <= 0 || hw <= 0 || Cpad < C) return set_error(MVD_EINVAL, "mvd_nchw_to_nhwc_f16: bad arguments");
   const size_t total = static_cast<size_t>(n_img) * hw * Cpad;
-  nchw_to_nhwc_f16_kernel<<<grid_for(total), 256, 0, stream>>>(x, static_cast<__half*>(y), C, hw, Cpad, total);
+  MVD_LAUNCH((nchw_to_nhwc_f16_kernel), grid_for(total), 256, 0, stream, x, static_cast<__half*>(y), C, hw, Cpad, total);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

@@ -22,6 +22,8 @@
 //
 // Replaces the cuBLAS/cuDNN dispatch behind nn.Linear / nn.Conv2d on the reference hot path
 // (see include/mvd_b200.h for the file:line list).
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -42,6 +44,7 @@ struct GemmKParams {
   int BN, stages;
   int num_kb, split, kb_per_split;
   int tiles_m, tiles_n, num_units;
+  int tiles_m_real;  // m-tiles of the problem (tiles_m counts CTA-pair rows in pair mode)
   int a_mode;
   int kb_per_tap, C;
   int n_img, H, W;
@@ -121,12 +124,19 @@ struct Unit {
   int grow0;         // first output row of the tile
 };
 
-__device__ __forceinline__ Unit decode_unit(const GemmKParams& p, int u) {
+// pair_rank < 0: one CTA per tile.  Otherwise the unit list enumerates 256-row tile PAIRS and CTA `pair_rank` of the
+// cluster owns m-tile 2*mt + rank (which may lie beyond the problem when the m-tile count is odd: every access of such
+// a tile is clipped, the CTA still takes part in the pair's loads and barriers).
+__device__ __forceinline__ Unit decode_unit(const GemmKParams& p, int u, int pair_rank) {
   Unit t;
   t.s = u % p.split;
   t.tile = u / p.split;
   t.n_tile = t.tile / p.tiles_m;
   t.m_tile = t.tile - t.n_tile * p.tiles_m;
+  if (pair_rank >= 0) {
+    t.m_tile = 2 * t.m_tile + pair_rank;
+    t.tile = t.n_tile * p.tiles_m_real + t.m_tile;  // split-K semaphores / partials are per real tile
+  }
   t.kb0 = t.s * p.kb_per_split;
   t.kb1 = min(p.num_kb, t.kb0 + p.kb_per_split);
   t.x0 = t.y0 = t.img0 = 0;
@@ -148,7 +158,7 @@ __device__ __forceinline__ Unit decode_unit(const GemmKParams& p, int u) {
 // at compile time (-1 = decided at run time); VEC = every epilogue access is a full, aligned 16-byte (8-byte fp16)
 // vector, so no tails exist.  The specialised bodies are several times smaller than the generic one, which matters:
 // a warp walks its epilogue code once per chunk, and the generic body does not fit the instruction cache.
-template <int ACT, int OUT, int RES, int SPLIT, bool VEC>
+template <int ACT, int OUT, int RES, int SPLIT, bool VEC, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
   const int act = ACT >= 0 ? ACT : p.act;
@@ -157,7 +167,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const bool is_split = SPLIT >= 0 ? (SPLIT != 0) : (p.split > 1);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = A_BYTES + p.BN * 128;
+  const int b_rows = PAIR ? p.BN / 2 : p.BN;  // W rows this CTA stages per k-block (a pair splits the tile's columns)
+  const int stage_bytes = A_BYTES + b_rows * 128;
   uint8_t* out_stg = smem + p.stages * stage_bytes;                    // 2 warpgroups x 2 x STG_BYTES
   float* bias_smem = reinterpret_cast<float*>(out_stg + 4 * STG_BYTES);  // 2 x 256 floats (GEGLU tile bias)
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_smem + 512);
@@ -169,6 +180,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int pair_rank = PAIR ? static_cast<int>(cluster_ctarank()) : -1;
+  const bool leader = !PAIR || pair_rank == 0;
+  pdl_trigger();  // the next kernel's CTAs may take SMs as ours retire; they block in pdl_wait() until this grid is done
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -179,54 +193,90 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], EPI_THREADS);
+      mbar_init(&acc_empty[b], PAIR ? 2 * EPI_THREADS : EPI_THREADS);  // pair: the leader collects both CTAs' epilogues
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, p.tmem_cols);
+    else tmem_alloc(tmem_slot, p.tmem_cols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // both CTAs' barriers are initialised before either signals the other's
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int first = blockIdx.x;
-  const int n_local = (first < p.num_units) ? (p.num_units - first + gridDim.x - 1) / gridDim.x : 0;
+  const int first = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const int ustride = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const int n_local = (first < p.num_units) ? (p.num_units - first + ustride - 1) / ustride : 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      // The weights do not depend on the previous kernel: the W tiles of the first ring slots are pulled into L2 BEFORE
+      // the grid-dependency wait, so their HBM latency overlaps the predecessor's tail.
+      if (n_local > 0) {
+        const Unit t0 = decode_unit(p, first, pair_rank);
+        const int npre = min(p.stages, t0.kb1 - t0.kb0);
+        for (int i = 0; i < npre; ++i) {
+          const int kb = t0.kb0 + i;
+          int kcol = kb * BK;
+          if (p.a_mode == MVD_A_CONV3X3) {
+            const int tap = kb / p.kb_per_tap;
+            kcol = tap * p.C + (kb - tap * p.kb_per_tap) * BK;
+          }
+          tma_prefetch_l2_2d(&tmB, kcol, t0.n_tile * p.BN + (PAIR ? pair_rank * b_rows : 0));
+        }
+      }
+      pdl_wait();
       int it = 0;
       for (int j = 0; j < n_local; ++j) {
-        const Unit t = decode_unit(p, first + j * gridDim.x);
+        const Unit t = decode_unit(p, first + j * ustride, pair_rank);
         for (int kb = t.kb0; kb < t.kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], stage_bytes);
+          if (leader) mbar_expect_tx(&full_bar[s], PAIR ? 2 * stage_bytes : stage_bytes);
           uint8_t* sa = smem + s * stage_bytes;
           uint8_t* sb = sa + A_BYTES;
           int kcol;
-          if (p.a_mode == MVD_A_CONV3X3) {
-            const int tap = kb / p.kb_per_tap;
-            const int cb = kb - tap * p.kb_per_tap;
-            const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d(sa, &tmA, &full_bar[s], cb * BK, t.x0 + kx - 1, t.y0 + ky - 1, t.img0);
-            kcol = tap * p.C + cb * BK;
+          if (PAIR) {
+            const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
+            if (p.a_mode == MVD_A_CONV3X3) {
+              const int tap = kb / p.kb_per_tap;
+              const int cb = kb - tap * p.kb_per_tap;
+              const int ky = tap / 3, kx = tap - ky * 3;
+              tma_load_4d_pair(sa, &tmA, lbar, cb * BK, t.x0 + kx - 1, t.y0 + ky - 1, t.img0);
+              kcol = tap * p.C + cb * BK;
+            } else {
+              tma_load_2d_pair(sa, &tmA, lbar, kb * BK, t.m_tile * BM);
+              kcol = kb * BK;
+            }
+            tma_load_2d_pair(sb, &tmB, lbar, kcol, t.n_tile * p.BN + pair_rank * b_rows);
           } else {
-            tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, t.m_tile * BM);
-            kcol = kb * BK;
+            if (p.a_mode == MVD_A_CONV3X3) {
+              const int tap = kb / p.kb_per_tap;
+              const int cb = kb - tap * p.kb_per_tap;
+              const int ky = tap / 3, kx = tap - ky * 3;
+              tma_load_4d(sa, &tmA, &full_bar[s], cb * BK, t.x0 + kx - 1, t.y0 + ky - 1, t.img0);
+              kcol = tap * p.C + cb * BK;
+            } else {
+              tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, t.m_tile * BM);
+              kcol = kb * BK;
+            }
+            tma_load_2d(sb, &tmB, &full_bar[s], kcol, t.n_tile * p.BN);
           }
-          tma_load_2d(sb, &tmB, &full_bar[s], kcol, t.n_tile * p.BN);
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ UMMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(BM, p.BN);
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_idesc_f16(PAIR ? 2 * BM : BM, p.BN);
       int it = 0;
       for (int j = 0; j < n_local; ++j) {
-        const Unit t = decode_unit(p, first + j * gridDim.x);
+        const Unit t = decode_unit(p, first + j * ustride, pair_rank);
         const int buf = j & 1;
         mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -242,11 +292,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 fp16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+            else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[s]);
+          if (PAIR) tc_commit_pair(&empty_bar[s], 3);  // frees the slot in BOTH CTAs
+          else tc_commit(&empty_bar[s]);
         }
-        tc_commit(&acc_full[buf]);
+        if (PAIR) tc_commit_pair(&acc_full[buf], 3);
+        else tc_commit(&acc_full[buf]);
       }
     }
   } else if (warp >= 4) {
@@ -266,6 +319,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     float* sbias = bias_smem + wg * 256;
     const int inner = p.heads * p.dhead;
     int n_staged = 0;  // staging buffer toggle
+    pdl_wait();        // residual / split-K workspace reads and every output write come after the predecessor grid
 
     // ---- phase A of one chunk: TMEM -> registers -> (GEGLU) -> swizzled staging tile, or the direct QKV scatter
     auto phase_a = [&](const Unit& t, uint32_t taddr, int c, uint32_t stg) -> bool {
@@ -449,9 +503,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // first chunk of this warpgroup at or after unit j (search forward); false when no work is left
     auto find_task = [&](int j, int& jt, int& ct, int& grow0, int& oc) -> bool {
       for (; j < n_local; ++j) {
-        const Unit t = decode_unit(p, first + j * gridDim.x);
+        const Unit t = decode_unit(p, first + j * ustride, pair_rank);
         int cf, cs, vc;
         chunk_walk(t, j, cf, cs, vc);
+        if (PAIR && t.m_tile >= p.tiles_m_real) continue;
         if (cf < vc) {
           jt = j; ct = cf; grow0 = t.grow0; oc = t.n_tile * out_bn + cf * 32;
           return true;
@@ -469,11 +524,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
 
     for (int j = 0; j < n_local; ++j) {
-      const int u = first + j * gridDim.x;
-      const Unit t = decode_unit(p, u);
+      const Unit t = decode_unit(p, first + j * ustride, pair_rank);
+      const int u = t.tile * p.split + t.s;  // index of this slice's split-K partial tile
       const int buf = j & 1;
       int cfirst, cstride, valid_chunks;
       chunk_walk(t, j, cfirst, cstride, valid_chunks);
+      if (PAIR && t.m_tile >= p.tiles_m_real) {  // padding half of the last pair: only the accumulator hand-shake
+        mbar_wait(&acc_full[buf], (j >> 1) & 1);
+        tc_fence_before();
+        mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[buf]), 0));
+        continue;
+      }
 
       if (geglu && p.bias != nullptr) {  // tile bias -> smem (phase A reads it as broadcast vectors)
         for (int k = et; k < p.BN; k += WG_THREADS) sbias[k] = __ldg(p.bias + t.n_tile * p.BN + k);
@@ -526,7 +587,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const bool staged = phase_a(t, taddr, c, stg);
         if (c + cstride >= valid_chunks) {  // last TMEM read of this unit by this thread: hand the accumulator back
           tc_fence_before();
-          mbar_arrive(&acc_empty[buf]);
+          if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[buf]), 0));
+          else mbar_arrive(&acc_empty[buf]);
         }
         if (staged) {
           ++n_staged;
@@ -536,7 +598,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
       if (cfirst >= valid_chunks) {  // nothing to finish in this unit: still part of the accumulator hand-shake
         tc_fence_before();
-        mbar_arrive(&acc_empty[buf]);
+        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[buf]), 0));
+        else mbar_arrive(&acc_empty[buf]);
       }
 
       if (is_split) {
@@ -553,10 +616,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's shared memory and signal its barriers until the very end
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -577,15 +642,17 @@ static int num_sms() {
 // modelled time: rounds of the persistent loop x shared-memory rows filled per k-block (128 of A + bn of W; the
 // mainloop is bound by the L2 -> smem fill rate on this part, ~56 B/clk/SM measured) — which accounts for both the
 // wave quantisation over the SMs and the columns wasted by padding N up to a multiple of bn.
-static int pick_bn(int N, int tiles_m, int sms) {
-  if (N <= 64) return (N + 15) / 16 * 16;
+// tiles_m / slots count CTA pairs when `pair` (each SM of a pair stages 128 + bn/2 rows per k-block).
+static int pick_bn(int N, int tiles_m, int slots, bool pair) {
+  if (N <= 64) return pair ? (N + 31) / 32 * 32 : (N + 15) / 16 * 16;
   int best = 64;
   double best_cost = 1e300;
   for (int bn = 64; bn <= 256; bn += 32) {
     const int tiles = tiles_m * ((N + bn - 1) / bn);
-    const int rounds = (tiles + sms - 1) / sms;
+    const int rounds = (tiles + slots - 1) / slots;
+    const double rows = pair ? 128.0 + bn / 2 : 128.0 + bn;
     // a machine that is less than half full will be split along K afterwards: compare per-tile work then
-    const double cost = (tiles * 2 <= sms) ? (128.0 + bn) * tiles / sms * 1.15 : static_cast<double>(rounds) * (128 + bn);
+    const double cost = (tiles * 2 <= slots) ? rows * tiles / slots * 1.15 : rounds * rows;
     if (cost < best_cost * 0.999 || (cost <= best_cost * 1.001 && bn > best)) {
       best = bn;
       best_cost = cost;
@@ -633,13 +700,32 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   p.seq = a->seq;
 
   const bool geglu = a->act == MVD_ACT_GEGLU;
-  int bn = a->tile_n;
-  if (bn == 0) {
-    const int tm = a->a_mode == MVD_A_CONV3X3 ? (a->M + BM - 1) / BM : (a->M + BM - 1) / BM;
-    bn = geglu ? 256 : pick_bn(a->N, tm, num_sms());
+  const int sms = num_sms();
+  // m-tiles of the problem (conv tiles are whole image rows: see the geometry block below)
+  int tiles_m_real;
+  if (a->a_mode == MVD_A_CONV3X3) {
+    if (a->n_img <= 0 || a->H <= 0 || a->W <= 0 || !is_pow2(a->W) || a->W > 128) return set_error(MVD_EINVAL, "mvd_gemm_f16: bad CONV3X3 geometry");
+    int th = BM / a->W;
+    if (th > a->H) th = a->H;
+    const int tn = BM / (a->W * th);
+    tiles_m_real = (a->H / (th > 0 ? th : 1)) * ((a->n_img + tn - 1) / tn);
+  } else {
+    tiles_m_real = (a->M + BM - 1) / BM;
   }
-  if (bn < 16 || bn > 256 || (bn & 15) != 0 || ((bn & 31) != 0 && bn < a->N))
-    return set_error(MVD_EINVAL, "mvd_gemm_f16: tile_n must be 0, a multiple of 32 in [32, 256], or a multiple of 16 that covers N");
+  // CTA pairs (cta_group::2): two m-tiles share one pass over the W tile — each SM stages 128 + bn/2 rows per k-block
+  // instead of 128 + bn, which is what bounds the mainloop (L2 -> smem fill).  Used whenever the m-tiles pair up
+  // with little padding; MVD_GEMM_NO_PAIR=1 in the environment turns it off (A/B measurements).
+  static const bool no_pair = getenv("MVD_GEMM_NO_PAIR") != nullptr;
+  // Measured on B200 (profiles/r01_gemm_native_bench_*.log): the pair wins when the mainloop dominates (deep K, or K >= 1280
+  // with a wide N); short-K GEMMs are epilogue-bound and run better as independent CTAs.
+  static const bool force_pair = getenv("MVD_GEMM_FORCE_PAIR") != nullptr;
+  const bool deep = a->K >= 2048 || (a->K >= 1280 && a->N >= 2560);
+  const bool pair = !no_pair && (deep || force_pair) && tiles_m_real >= 2 && ((tiles_m_real & 1) == 0 || tiles_m_real >= 9) && (sms & 1) == 0;
+  const int tiles_mp = pair ? (tiles_m_real + 1) / 2 : tiles_m_real;
+  const int slots = pair ? sms / 2 : sms;
+  int bn = a->tile_n;
+  if (bn == 0) bn = geglu ? 256 : pick_bn(a->N, tiles_mp, slots, pair);
+  if (pair && (bn & 31) != 0) return set_error(MVD_EINVAL, "mvd_gemm_f16: tile_n must be a multiple of 32 here");
   if (geglu) {
     if ((bn & 63) != 0 || (a->N % bn) != 0) return set_error(MVD_EINVAL, "mvd_gemm_f16: GEGLU needs tile_n a multiple of 64 that divides N");
     if (a->colscale != nullptr || a->residual != nullptr || a->rowbias != nullptr || a->out_mode == MVD_OUT_QKV_HEADS)
@@ -657,7 +743,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   if (a->a_mode == MVD_A_ROWMAJOR) {
     if ((a->lda & 7) != 0 || a->lda < a->K) return set_error(MVD_EALIGN, "mvd_gemm_f16: lda must be >= K and a multiple of 8");
     p.num_kb = (a->K + BK - 1) / BK;
-    p.tiles_m = (a->M + BM - 1) / BM;
+    p.tiles_m_real = (a->M + BM - 1) / BM;
     int rc = make_tmap_2d(&tmA, a->A, /*cols=*/a->K, /*rows=*/a->M, /*ld=*/a->lda, BK, BM);
     if (rc != MVD_OK) return rc;
   } else if (a->a_mode == MVD_A_CONV3X3) {
@@ -676,7 +762,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     p.tiles_x = 1;
     p.tiles_y = a->H / p.th;
     const int tiles_z = (a->n_img + p.tn - 1) / p.tn;
-    p.tiles_m = p.tiles_x * p.tiles_y * tiles_z;
+    p.tiles_m_real = p.tiles_x * p.tiles_y * tiles_z;
     p.kb_per_tap = (a->C + BK - 1) / BK;
     p.num_kb = 9 * p.kb_per_tap;
     int rc = make_tmap_nhwc(&tmA, a->A, a->n_img, a->H, a->W, a->C, BK, p.tw, p.th, p.tn);
@@ -685,12 +771,13 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     return set_error(MVD_EINVAL, "mvd_gemm_f16: bad a_mode");
   }
   {
-    int rc = make_tmap_2d(&tmB, a->Wt, /*cols=*/a->K, /*rows=*/a->N, /*ld=*/a->ldw, BK, bn);
+    int rc = make_tmap_2d(&tmB, a->Wt, /*cols=*/a->K, /*rows=*/a->N, /*ld=*/a->ldw, BK, pair ? bn / 2 : bn);
     if (rc != MVD_OK) return rc;
   }
+  if (p.tiles_m_real != tiles_m_real) return set_error(MVD_EINVAL, "mvd_gemm_f16: internal tile count mismatch");
+  p.tiles_m = tiles_mp;
   p.tiles_n = (a->N + bn - 1) / bn;
-  const int tiles = p.tiles_m * p.tiles_n;
-  const int sms = num_sms();
+  const int tiles = p.tiles_m * p.tiles_n;  // work items per K slice: tiles, or 256-row tile pairs
 
   // ---- split-K (every slice of a tile must be co-resident: units <= SMs)
   int split = a->split_k;
@@ -699,19 +786,19 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   const bool can_split = !geglu && a->out_mode != MVD_OUT_QKV_HEADS;
   if (split <= 0) {  // auto: only when the tiles cannot fill half the machine and K is deep
     split = 1;
-    if (can_split && tiles * 2 <= sms && p.num_kb >= 8) {
-      split = sms / tiles;
+    if (can_split && tiles * 2 <= slots && p.num_kb >= 8) {
+      split = slots / tiles;
       if (split > p.num_kb / 4) split = p.num_kb / 4;
       if (split > 16) split = 16;
       if (split < 1) split = 1;
     }
-    while (split > 1 && (tiles > WS_COUNTER_BYTES / 8 || static_cast<size_t>(tiles) * split * tile_ws > ws_avail)) --split;
+    while (split > 1 && (p.tiles_m_real * p.tiles_n > WS_COUNTER_BYTES / 8 || static_cast<size_t>(p.tiles_m_real) * p.tiles_n * split * tile_ws > ws_avail)) --split;
   } else if (split > 1) {
     if (!can_split) return set_error(MVD_EINVAL, "mvd_gemm_f16: split_k is not supported with GEGLU / QKV_HEADS");
     if (split > p.num_kb) split = p.num_kb;
-    if (tiles * split > sms)
-      return set_error(MVD_EINVAL, "mvd_gemm_f16: split_k=%d x %d tiles exceeds the %d SMs (slices of a tile must be co-resident)", split, tiles, sms);
-    if (tiles > WS_COUNTER_BYTES / 8 || static_cast<size_t>(tiles) * split * tile_ws > ws_avail)
+    if (tiles * split > slots)
+      return set_error(MVD_EINVAL, "mvd_gemm_f16: split_k=%d x %d tiles exceeds the %d SMs / SM pairs (slices of a tile must be co-resident)", split, tiles, slots);
+    if (p.tiles_m_real * p.tiles_n > WS_COUNTER_BYTES / 8 || static_cast<size_t>(p.tiles_m_real) * p.tiles_n * split * tile_ws > ws_avail)
       return set_error(MVD_EINVAL, "mvd_gemm_f16: split_k=%d needs a split-K workspace of %zu bytes (args.splitk_ws)", split,
                        static_cast<size_t>(tiles) * split * tile_ws + WS_COUNTER_BYTES);
   }
@@ -744,7 +831,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   }
 
   // ---- shared memory / TMEM budget
-  const int stage_bytes = A_BYTES + bn * 128;
+  const int stage_bytes = A_BYTES + (pair ? bn / 2 : bn) * 128;
   const int fixed = 4 * STG_BYTES + 2048 + 512;
   int stages = (232448 - 1024 - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -761,38 +848,40 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   const int has_res = a->residual != nullptr ? 1 : 0;
   const int is_split = split > 1 ? 1 : 0;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const GemmKParams);
-  KernelFn fn = gemm_tc_kernel<-1, -1, -1, -1, false>;
+  struct Spec { int key; KernelFn one, two; };
+#define MVD_SPEC(ACT, OUT, RES, SPL) \
+  { (ACT) * 1000 + (OUT) * 100 + (RES) * 10 + (SPL), gemm_tc_kernel<ACT, OUT, RES, SPL, true, false>, gemm_tc_kernel<ACT, OUT, RES, SPL, true, true> }
+  static const Spec specs[] = {
+      MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 0, 0),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 0, 1),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 1, 0),
+      MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 1, 1),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F16, 0, 0),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F16, 1, 0),
+      MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F16, 1, 1),  MVD_SPEC(MVD_ACT_GELU, MVD_OUT_F16, 0, 0),  MVD_SPEC(MVD_ACT_GELU, MVD_OUT_F32, 0, 0),
+      MVD_SPEC(MVD_ACT_GEGLU, MVD_OUT_F16, 0, 0), MVD_SPEC(MVD_ACT_NONE, MVD_OUT_QKV_HEADS, 0, 0),
+  };
+#undef MVD_SPEC
+  const Spec generic = {-1, gemm_tc_kernel<-1, -1, -1, -1, false, false>, gemm_tc_kernel<-1, -1, -1, -1, false, true>};
+  const Spec* spec = &generic;
   if (vec) {
     const int key = a->act * 1000 + a->out_mode * 100 + has_res * 10 + is_split;
-    switch (key) {
-      case MVD_ACT_NONE * 1000 + MVD_OUT_F32 * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 0, 0, true>; break;
-      case MVD_ACT_NONE * 1000 + MVD_OUT_F32 * 100 + 1: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 0, 1, true>; break;
-      case MVD_ACT_NONE * 1000 + MVD_OUT_F32 * 100 + 10: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 1, 0, true>; break;
-      case MVD_ACT_NONE * 1000 + MVD_OUT_F32 * 100 + 11: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 1, 1, true>; break;
-      case MVD_ACT_NONE * 1000 + MVD_OUT_F16 * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 0, 0, true>; break;
-      case MVD_ACT_NONE * 1000 + MVD_OUT_F16 * 100 + 10: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 1, 0, true>; break;
-      case MVD_ACT_NONE * 1000 + MVD_OUT_F16 * 100 + 11: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 1, 1, true>; break;
-      case MVD_ACT_GELU * 1000 + MVD_OUT_F16 * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_GELU, MVD_OUT_F16, 0, 0, true>; break;
-      case MVD_ACT_GELU * 1000 + MVD_OUT_F32 * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_GELU, MVD_OUT_F32, 0, 0, true>; break;
-      case MVD_ACT_GEGLU * 1000 + MVD_OUT_F16 * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_GEGLU, MVD_OUT_F16, 0, 0, true>; break;
-      case MVD_ACT_NONE * 1000 + MVD_OUT_QKV_HEADS * 100 + 0: fn = gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_QKV_HEADS, 0, 0, true>; break;
-      default: break;
-    }
+    for (const Spec& sp : specs)
+      if (sp.key == key) spec = &sp;
   }
   static bool configured = false;
   if (!configured) {
-    KernelFn all[] = {gemm_tc_kernel<-1, -1, -1, -1, false>,
-                      gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 0, 0, true>, gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 0, 1, true>,
-                      gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 1, 0, true>, gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F32, 1, 1, true>,
-                      gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 0, 0, true>, gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 1, 0, true>,
-                      gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_F16, 1, 1, true>,
-                      gemm_tc_kernel<MVD_ACT_GELU, MVD_OUT_F16, 0, 0, true>, gemm_tc_kernel<MVD_ACT_GELU, MVD_OUT_F32, 0, 0, true>,
-                      gemm_tc_kernel<MVD_ACT_GEGLU, MVD_OUT_F16, 0, 0, true>, gemm_tc_kernel<MVD_ACT_NONE, MVD_OUT_QKV_HEADS, 0, 0, true>};
-    for (KernelFn f : all) MVD_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    for (const Spec& sp : specs) {
+      MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.one, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.two, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    }
+    MVD_CUDA_CHECK(cudaFuncSetAttribute(generic.one, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    MVD_CUDA_CHECK(cudaFuncSetAttribute(generic.two, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     configured = true;
   }
-  const int grid = p.num_units < sms ? p.num_units : sms;
-  fn<<<grid, GEMM_THREADS, dyn, stream>>>(tmA, tmB, p);
+  if (pair) {
+    const int grid = 2 * (p.num_units < slots ? p.num_units : slots);
+    MVD_CUDA_CHECK(launch_kernel(spec->two, dim3(grid), dim3(GEMM_THREADS), dyn, stream, 2, tmA, tmB, p));
+  } else {
+    const int grid = p.num_units < sms ? p.num_units : sms;
+    MVD_CUDA_CHECK(launch_kernel(spec->one, dim3(grid), dim3(GEMM_THREADS), dyn, stream, 1, tmA, tmB, p));
+  }
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

@@ -63,6 +63,8 @@ __global__ void gridattn_prep_kernel(const float* __restrict__ lat, const float*
                                      const float* __restrict__ bz, __half* __restrict__ feat,
                                      float* __restrict__ zdepth, int n_views, int hw, int D, float depth_scale,
                                      float depth_shift) {
+  pdl_trigger();
+  pdl_wait();
   const int pix = blockIdx.x;
   const int view = blockIdx.y;  // n_views == input view
   const float* src = (view < n_views) ? lat + static_cast<size_t>(view) * 5 * hw : inp;
@@ -146,6 +148,8 @@ __global__ void gridattn_tokens_kernel(const __half* __restrict__ feat, const fl
                                        const float* __restrict__ cams, const float* __restrict__ mask,
                                        const float* __restrict__ freqs, const float* __restrict__ ndc_grid,
                                        __half* __restrict__ tokens, int n_views, int S, int D, int q0, int nq) {
+  pdl_trigger();
+  pdl_wait();
   const int hw = S * S;
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -232,6 +236,8 @@ __global__ void gridattn_tokens_kernel(const __half* __restrict__ feat, const fl
 // One thread per (point, head, query view).
 template <int HD>
 __global__ void view_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int P, int V, int heads) {
+  pdl_trigger();
+  pdl_wait();
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t total = static_cast<size_t>(P) * heads * V;
   if (idx >= total) return;
@@ -315,6 +321,8 @@ __global__ void view_attention_kernel(const __half* __restrict__ qkv, __half* __
 // x fp32 [P*V, 256]; w = x . ww + wb; softmax over V; out[p] = sum_v softmax_v x_v  -> fp16 [P, 256]
 __global__ void view_pool_kernel(const float* __restrict__ x, const float* __restrict__ ww, const float* __restrict__ wb,
                                  __half* __restrict__ out, int P, int V) {
+  pdl_trigger();
+  pdl_wait();
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (p >= P) return;
@@ -360,6 +368,8 @@ __global__ void view_pool_kernel(const float* __restrict__ x, const float* __res
 // in fp16 [n, S, S, D, C] -> out fp16 [n, S/f, S/f, D, C], mean over f x f pixel blocks (interpolate mode='area')
 __global__ void frustum_pool_kernel(const __half* __restrict__ in, __half* __restrict__ out, int S, int D, int C, int f,
                                     size_t total8) {
+  pdl_trigger();
+  pdl_wait();
   const int So = S / f;
   const float inv = 1.f / static_cast<float>(f * f);
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
@@ -404,6 +414,8 @@ __global__ void frustum_pool_kernel(const __half* __restrict__ in, __half* __res
 // keys.  q fp16 [M, C]; kv fp16 [M*D, 2C] (k | v); out fp16 [M, C].  One thread per (pixel, head, 8-channel group).
 __global__ void pixel_cross_attn_kernel(const __half* __restrict__ q, const __half* __restrict__ kv,
                                         __half* __restrict__ out, int M, int D, int heads, int dhead) {
+  pdl_trigger();
+  pdl_wait();
   // one warp per (pixel, head): lanes stride the head dim
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -448,7 +460,7 @@ extern "C" int mvd_gridattn_prep(const float* noisy, const float* input_latent, 
   if (!noisy || !input_latent || !depth_eps || !scal_dev || !Wz || !bz || !feat_out || !zdepth_out)
     return set_error(MVD_EINVAL, "mvd_gridattn_prep: null pointer");
   if (n_views <= 0 || S <= 0 || D <= 0 || D > 32) return set_error(MVD_EINVAL, "mvd_gridattn_prep: bad sizes");
-  gridattn_prep_kernel<<<dim3(S * S, n_views + 1), 64, 0, stream>>>(noisy, input_latent, depth_override, depth_eps,
+  MVD_LAUNCH((gridattn_prep_kernel), dim3(S * S, n_views + 1), 64, 0, stream, noisy, input_latent, depth_override, depth_eps,
                                                                    scal_dev, Wz, bz, static_cast<__half*>(feat_out),
                                                                    zdepth_out, n_views, S * S, D, depth_scale,
                                                                    depth_shift);
@@ -466,7 +478,7 @@ extern "C" int mvd_gridattn_tokens(const void* feat, const float* zdepth, const 
     return set_error(MVD_EINVAL, "mvd_gridattn_tokens: bad sizes");
   const long long total = static_cast<long long>(q_count) * S * S * D * n_views;
   const int wpb = 8;
-  gridattn_tokens_kernel<<<static_cast<unsigned>((total + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+  MVD_LAUNCH((gridattn_tokens_kernel), static_cast<unsigned>((total + wpb - 1) / wpb), wpb * 32, 0, stream, 
       static_cast<const __half*>(feat), zdepth, cams, mask, freqs, ndc_grid, static_cast<__half*>(tokens), n_views, S, D,
       q_first, q_count);
   count_launch();
@@ -480,7 +492,7 @@ extern "C" int mvd_view_attention_f16(const void* qkv, void* out, int32_t P, int
   if (!qkv || !out || P <= 0 || V <= 0 || heads <= 0) return set_error(MVD_EINVAL, "mvd_view_attention_f16: bad arguments");
   if (hd != 32) return set_error(MVD_EINVAL, "mvd_view_attention_f16: head dim must be 32");
   const size_t total = static_cast<size_t>(P) * heads * V;
-  view_attention_kernel<32><<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(
+  MVD_LAUNCH((view_attention_kernel<32>), static_cast<unsigned>((total + 127) / 128), 128, 0, stream, 
       static_cast<const __half*>(qkv), static_cast<__half*>(out), P, V, heads);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
@@ -492,7 +504,7 @@ extern "C" int mvd_view_pool_f16(const float* x, const float* w, const float* b,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !w || !b || !out || P <= 0 || V <= 0) return set_error(MVD_EINVAL, "mvd_view_pool_f16: bad arguments");
   if (C != ZC) return set_error(MVD_EINVAL, "mvd_view_pool_f16: hidden size must be 256");
-  view_pool_kernel<<<(P + 7) / 8, 256, 0, stream>>>(x, w, b, static_cast<__half*>(out), P, V);
+  MVD_LAUNCH((view_pool_kernel), (P + 7) / 8, 256, 0, stream, x, w, b, static_cast<__half*>(out), P, V);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -507,7 +519,7 @@ extern "C" int mvd_frustum_pool_f16(const void* in, void* out, int32_t n_img, in
   const size_t total8 = static_cast<size_t>(n_img) * So * So * D * C / 8;
   size_t blocks = (total8 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  frustum_pool_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+  MVD_LAUNCH((frustum_pool_kernel), static_cast<unsigned>(blocks), 256, 0, stream, 
       static_cast<const __half*>(in), static_cast<__half*>(out), S, D, C, factor, total8);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
@@ -520,7 +532,7 @@ extern "C" int mvd_pixel_cross_attn_f16(const void* q, const void* kv, void* out
   if (!q || !kv || !out || M <= 0 || D <= 0 || D > 8 || heads <= 0 || dhead <= 0)
     return set_error(MVD_EINVAL, "mvd_pixel_cross_attn_f16: bad arguments (D <= 8)");
   const long long warps = static_cast<long long>(M) * heads;
-  pixel_cross_attn_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, stream>>>(
+  MVD_LAUNCH((pixel_cross_attn_kernel), static_cast<unsigned>((warps + 7) / 8), 256, 0, stream, 
       static_cast<const __half*>(q), static_cast<const __half*>(kv), static_cast<__half*>(out), M, D, heads, dhead);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());

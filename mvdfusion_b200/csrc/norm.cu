@@ -20,6 +20,8 @@ template <bool CACHE>
 __global__ void __launch_bounds__(512)
     gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                     __half* __restrict__ y, int hw, int C, int cpg, int gpc, int rows, float eps, int apply_silu) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t gn_smem[];
   const int span = gpc * cpg;
   const int span4 = span >> 2;
@@ -124,6 +126,8 @@ __global__ void __launch_bounds__(512)
 template <int MODE>
 __global__ void ln_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
                           __half* __restrict__ y, int rows, int C, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int warps_per_block = blockDim.x >> 5;
   const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -223,9 +227,9 @@ extern "C" int mvd_groupnorm_f32_f16(const float* x, const float* gamma, const f
   (void)stats_ws;
   const dim3 grid(32 / gpc, n_img);
   if (use_cache)
-    gn_fused_kernel<true><<<grid, threads, sm, stream>>>(x, gamma, beta, static_cast<__half*>(y), hw, C, cpg, gpc, rows, eps, apply_silu);
+    MVD_LAUNCH((gn_fused_kernel<true>), grid, threads, sm, stream, x, gamma, beta, static_cast<__half*>(y), hw, C, cpg, gpc, rows, eps, apply_silu);
   else
-    gn_fused_kernel<false><<<grid, threads, sm, stream>>>(x, gamma, beta, static_cast<__half*>(y), hw, C, cpg, gpc, rows, eps, apply_silu);
+    MVD_LAUNCH((gn_fused_kernel<false>), grid, threads, sm, stream, x, gamma, beta, static_cast<__half*>(y), hw, C, cpg, gpc, rows, eps, apply_silu);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -236,7 +240,7 @@ extern "C" int mvd_layernorm_f32_f16(const float* x, const float* gamma, const f
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !gamma || !beta || !y) return set_error(MVD_EINVAL, "mvd_layernorm_f32_f16: null pointer");
   if (rows <= 0 || C <= 0 || (C & 3) != 0 || C > 1280) return set_error(MVD_EINVAL, "mvd_layernorm_f32_f16: C must be a multiple of 4, <= 1280");
-  ln_kernel<0><<<(rows + 7) / 8, 256, 0, stream>>>(x, gamma, beta, static_cast<__half*>(y), rows, C, eps);
+  MVD_LAUNCH((ln_kernel<0>), (rows + 7) / 8, 256, 0, stream, x, gamma, beta, static_cast<__half*>(y), rows, C, eps);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -247,7 +251,7 @@ extern "C" int mvd_ln_modulate_f32_f16(const float* x, const float* shift, const
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !shift || !scale || !y) return set_error(MVD_EINVAL, "mvd_ln_modulate_f32_f16: null pointer");
   if (rows <= 0 || C <= 0 || (C & 3) != 0 || C > 1280) return set_error(MVD_EINVAL, "mvd_ln_modulate_f32_f16: C must be a multiple of 4, <= 1280");
-  ln_kernel<1><<<(rows + 7) / 8, 256, 0, stream>>>(x, scale, shift, static_cast<__half*>(y), rows, C, eps);
+  MVD_LAUNCH((ln_kernel<1>), (rows + 7) / 8, 256, 0, stream, x, scale, shift, static_cast<__half*>(y), rows, C, eps);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
