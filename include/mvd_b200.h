@@ -55,7 +55,9 @@ long long mvd_launch_count(void);
  *   split_k: K is cut into slices that run as separate work units; each slice parks its fp32 partial tile in
  *        `splitk_ws`, the slice finishing last sums them and runs the epilogue (any act / out_mode except GEGLU).
  *   The kernel is persistent (one CTA per SM walks the tile list) and keeps two accumulators in TMEM so that the
- *   epilogue of one tile overlaps the MMAs of the next; outputs leave through swizzled smem + TMA bulk stores.
+ *   epilogue of one tile overlaps the MMAs of the next; outputs leave through a swizzled smem staging tile as coalesced
+ *   16-byte stores.  Deep-K problems run as CTA pairs (tcgen05 cta_group::2): two m-tiles share each W tile.
+ *   tile_n / split_k / cta_pair = 0 let the library choose; mvdfusion_b200/gemm_tuning.json holds measured choices.
  * ---------------------------------------------------------------------------------------------- */
 enum { MVD_A_ROWMAJOR = 0, MVD_A_CONV3X3 = 1 };
 enum { MVD_ACT_NONE = 0, MVD_ACT_GELU = 1, MVD_ACT_SILU = 2, MVD_ACT_GEGLU = 3 };
@@ -85,6 +87,7 @@ typedef struct mvd_gemm_args {
   int32_t heads, dhead, dpad, seq;
   int32_t split_k;     /* 0 = auto, 1 = off, > 1 = that many K slices (needs splitk_ws) */
   int32_t tile_n;      /* 0 = auto; else a multiple of 32 in [32, 256], or a multiple of 16 >= N (GEGLU: a multiple of 64 dividing N) */
+  int32_t cta_pair;    /* 0 = auto, 1 = one CTA per 128-row tile, 2 = CTA pairs (cta_group::2, 256-row tiles; needs >= 2 m-tiles) */
   void* splitk_ws;     /* caller-owned split-K workspace or NULL; MUST be zero-filled once before its first use
                           (the first 16 KB are self-resetting tile semaphores, the rest holds fp32 partial tiles) */
   long long splitk_ws_bytes;

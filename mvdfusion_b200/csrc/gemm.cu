@@ -720,7 +720,10 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   // with a wide N); short-K GEMMs are epilogue-bound and run better as independent CTAs.
   static const bool force_pair = getenv("MVD_GEMM_FORCE_PAIR") != nullptr;
   const bool deep = a->K >= 2048 || (a->K >= 1280 && a->N >= 2560);
-  const bool pair = !no_pair && (deep || force_pair) && tiles_m_real >= 2 && ((tiles_m_real & 1) == 0 || tiles_m_real >= 9) && (sms & 1) == 0;
+  if (a->cta_pair < 0 || a->cta_pair > 2) return set_error(MVD_EINVAL, "mvd_gemm_f16: cta_pair must be 0, 1 or 2");
+  if (a->cta_pair == 2 && (tiles_m_real < 2 || (sms & 1) != 0)) return set_error(MVD_EINVAL, "mvd_gemm_f16: cta_pair = 2 needs at least two m-tiles");
+  const bool pair_auto = (deep || force_pair) && tiles_m_real >= 2 && ((tiles_m_real & 1) == 0 || tiles_m_real >= 9) && (sms & 1) == 0;
+  const bool pair = !no_pair && (a->cta_pair == 2 || (a->cta_pair == 0 && pair_auto));
   const int tiles_mp = pair ? (tiles_m_real + 1) / 2 : tiles_m_real;
   const int slots = pair ? sms / 2 : sms;
   int bn = a->tile_n;

@@ -41,24 +41,22 @@ __global__ void __launch_bounds__(512)
 
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   if (active) {
-    int p = row;
-    for (; p + 3 * rows < hw; p += 4 * rows) {
-      float4 v[4];
+    // eight independent 16-byte loads in flight per thread
+    for (int p0 = row; p0 < hw; p0 += 8 * rows) {
+      float4 v[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(src + static_cast<size_t>(p + u * rows) * pix_stride4);
+      for (int u = 0; u < 8; ++u) {
+        const int p = p0 + u * rows;
+        v[u] = p < hw ? __ldg(src + static_cast<size_t>(p) * pix_stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (CACHE) cache[(p + u * rows) * span4 + cq] = v[u];
+      for (int u = 0; u < 8; ++u) {
+        const int p = p0 + u * rows;
+        if (CACHE && p < hw) cache[p * span4 + cq] = v[u];
         s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
         q[0] = fmaf(v[u].x, v[u].x, q[0]); q[1] = fmaf(v[u].y, v[u].y, q[1]);
         q[2] = fmaf(v[u].z, v[u].z, q[2]); q[3] = fmaf(v[u].w, v[u].w, q[3]);
       }
-    }
-    for (; p < hw; p += rows) {
-      const float4 v = __ldg(src + static_cast<size_t>(p) * pix_stride4);
-      if (CACHE) cache[p * span4 + cq] = v;
-      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-      q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {

@@ -15,7 +15,25 @@ import math
 
 import torch
 
-from .ops import ACT_GEGLU, ACT_GELU, ACT_NONE
+import json
+import os
+
+from .ops import ACT_GEGLU, ACT_GELU, ACT_NONE, gemm_signature
+
+_TUNING = None
+
+
+def gemm_tuning():
+    """signature -> (tile_n, split_k, cta_pair), measured on a B200 by tools/tune_gemm.py (empty when the file is absent or
+    MVD_GEMM_NO_TUNING is set: the library's own heuristics then decide)."""
+    global _TUNING
+    if _TUNING is None:
+        _TUNING = {}
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gemm_tuning.json")
+        if os.path.exists(path) and not os.environ.get("MVD_GEMM_NO_TUNING"):
+            with open(path) as f:
+                _TUNING = {k: tuple(v) for k, v in json.load(f).get("choices", {}).items()}
+    return _TUNING
 
 NUM_SMS = 148
 Z_CH = 256        # GridAttn z_embedder width (mvdfusion/view_attn_efficient2.py:151)
@@ -217,8 +235,22 @@ class Builder:
         return self._ws
 
     def gemm(self, A, Wt, out, M, N, K, *, allow_split=False, **kw):
-        # split_k = 0 lets the library cut K when the tile grid cannot fill the machine (small-M, weight-bound layers)
-        if allow_split and kw.get("act", ACT_NONE) != ACT_GEGLU:
+        # split_k = 0 lets the library cut K when the tile grid cannot fill the machine (small-M, weight-bound layers);
+        # a measured (tile_n, split_k, cta_pair) choice from gemm_tuning.json overrides the library's heuristics.
+        act = kw.get("act", ACT_NONE)
+        can_split = allow_split and act != ACT_GEGLU and kw.get("qkv") is None
+        sig = gemm_signature(kw.get("conv") is not None, M, N, K,
+                             "qkv" if kw.get("qkv") is not None else str(out.dtype).split(".")[-1], kw.get("residual") is not None, act)
+        tuned = gemm_tuning().get(sig)
+        if tuned is not None and "tile_n" not in kw:
+            tn, sk, pr = tuned
+            if act == ACT_GEGLU:
+                tn = GEGLU_TILE
+            if sk > 1 and not can_split:
+                sk = 1
+            self.prog.append(self.ops.gemm(A, Wt, out, M, N, K, split_k=sk, tile_n=tn, cta_pair=pr,
+                                           ws=self.splitk_ws() if sk != 1 else None, **kw))
+        elif can_split:
             self.prog.append(self.ops.gemm(A, Wt, out, M, N, K, split_k=0, ws=self.splitk_ws(), **kw))
         else:
             self.prog.append(self.ops.gemm(A, Wt, out, M, N, K, split_k=1, **kw))

@@ -20,6 +20,11 @@ class MvdError(RuntimeError):
     pass
 
 
+def gemm_signature(is_conv, M, N, K, out_kind, has_res, act):
+    """Key of a GEMM launch in mvdfusion_b200/gemm_tuning.json (tools/tune_gemm.py)."""
+    return f"{'conv' if is_conv else 'lin'}:{M}:{N}:{K}:{out_kind}:{int(bool(has_res))}:{act}"
+
+
 def _ptr(t, dtype=None):
     if t is None:
         return None
@@ -73,7 +78,7 @@ class NativeOps:
 
     # ------------------------------------------------------------------ GEMM / conv
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
-             colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None):
+             colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None, cta_pair=0):
         g = _lib.GemmArgs()
         g.M, g.N, g.K = M, N, K
         g.A = _ptr(A, torch.float16)
@@ -103,6 +108,7 @@ class NativeOps:
             g.ldc = ldc if ldc is not None else out.shape[-1]
         g.split_k = split_k
         g.tile_n = tile_n
+        g.cta_pair = cta_pair
         if ws is not None:
             g.splitk_ws = _ptr(ws, torch.uint8)
             g.splitk_ws_bytes = ws.numel()
@@ -113,7 +119,8 @@ class NativeOps:
         desc = (f"{'conv' if conv is not None else 'lin'} M{M} N{N} K{K} "
                 f"{'qkv' if qkv is not None else ('f32' if out.dtype == torch.float32 else 'f16')}"
                 f"{' res' if residual is not None else ''}{' act%d' % act if act else ''}{' sk' if split_k != 1 else ''}")
-        meta = {"kernel": "gemm_tc_kernel", "flops": 2.0 * M * N * K, "shape": (M, N, K, split_k), "desc": desc,
+        sig = gemm_signature(conv is not None, M, N, K, "qkv" if qkv is not None else str(out.dtype).split(".")[-1], residual is not None, act)
+        meta = {"kernel": "gemm_tc_kernel", "flops": 2.0 * M * N * K, "shape": (M, N, K, split_k), "desc": desc, "sig": sig, "can_split": ws is not None,
                 "bytes": a_bytes + N * K * 2 + o_bytes + (M * n_out * 4 if residual is not None else 0)}
         return self._bind("mvd_gemm_f16", (ctypes.byref(g),), keep, meta)
 

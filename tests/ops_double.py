@@ -44,7 +44,7 @@ class TorchOpsDouble:
 
     # ------------------------------------------------------------------ GEMM / conv
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
-             colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None):
+             colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None, cta_pair=0):
         assert A.dtype == torch.float16 and Wt.dtype == torch.float16
         ldw_ = ldw if ldw is not None else Wt.shape[-1]
 
