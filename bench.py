@@ -9,10 +9,13 @@ GridAttn over all views + UNet over the views (x2: classifier-free guidance 2.5,
 combine + DDIM update.  Workload at N=1 = BASELINE.json configs[1]: N=8 views, 1xB200, full-size UNet
 (1.034 B parameters, random-init — no checkpoints offline), D = 1 depth sample per ray, synthetic GSO camera rig.
 
-Multi-GPU (`--gpus G`, one process per GPU under torchrun): `--mode shard` (default) splits the 8 views of ONE scene over
-the G ranks — every rank runs GridAttn for its own query views against all views and the UNet on its own views, then the
-ranks exchange the updated 5-channel latents with one NCCL all-gather per step (strong scaling); `--mode replicas` runs
-one independent scene per rank with no collective (what the reference's demo.py does; weak scaling).
+Multi-GPU (`--gpus G`, one process per GPU under torchrun), both of SURVEY.md §8(e)'s modes are measured in the same run:
+  * replicas (the headline `value`; weak scaling): one independent scene of `--views` views per rank, no data-path
+    collective — what the reference's demo.py does (demo.py:63-64), and the throughput mode;
+  * view-sharded (reported under `"sharded"`; strong scaling, the latency mode): the views of ONE scene are split over the
+    G ranks — every rank runs GridAttn for its own query views against all views and the UNet on its own views, then the
+    ranks exchange the updated 5-channel latents with one NCCL all-gather per step.
+`--mode shard` makes the sharded figure the headline instead.
 """
 import argparse
 import json
@@ -38,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--mode", default="shard", choices=["shard", "replicas"])
+    ap.add_argument("--mode", default="replicas", choices=["shard", "replicas"])
     ap.add_argument("--views", type=int, default=8)
     ap.add_argument("--cfg", type=float, default=2.5)
     ap.add_argument("--no-graph", action="store_true")
@@ -206,53 +209,69 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     n, S, D, K, Wm = args.views, 32, 1, args.steps, args.warmup
     shard = world > 1 and args.mode == "shard"
+    if world > 1 and n % world:
+        raise SystemExit(f"--views {n} does not shard over {world} ranks")
 
     model = build_model(320, 8, D=D, S=S, device=dev)
-    if shard:
-        model.shard_views()
-    scene_seed = 0 if (shard or world == 1) else rank
-    sc = synthetic.scene_inputs(n, S, seed=scene_seed)
     total = K + Wm
     de1, dn1 = synthetic.step_noises(n, D, S, min(total, 50), seed=1)
     idx = [i % de1.shape[0] for i in range(total)]
     de, dn = de1[idx], dn1[idx]
     rows = torch.stack([model.ddim.step_row(49 - (i % 50), args.cfg) for i in range(total)])
     cam = lambda c: PerspectiveCameras(c["R"], c["T"], c["f"], c["p"], device=dev)
-    cams, icams = cam(sc["cams"]), cam(sc["in_cams"])
-    plan = model.step_plan(n, S, D, use_cfg=args.cfg != 1.0)
     stream = current_stream(dev)
-    model.bind_scene(plan, cams, sc["input_latents"].to(dev), icams, sc["clip_v_embed"].to(dev), stream)
-    plan.x.copy_(sc["x_T"].reshape(n, 5, S * S))
-    plan.set_tables(rows, de, dn)
     use_graph = not args.no_graph
-
-    def one_step():
-        plan.loop_step(stream, use_graph=use_graph)
-        if shard:
-            model.gather_views(plan)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(Wm, 3)):
-        one_step()
-    plan.counter.fill_(Wm)
-    barrier()
+    def timed_loop(sharded):
+        """W warm-up + K timed denoising steps of one scene per rank (replicas) or of one scene over all ranks (sharded);
+        returns (max-over-ranks ms for the K steps, plan, scene, cameras)."""
+        if sharded:
+            model.shard_views()
+        else:
+            model.view_group = None
+        sc_ = synthetic.scene_inputs(n, S, seed=0 if (sharded or world == 1) else rank)
+        cams_, icams_ = cam(sc_["cams"]), cam(sc_["in_cams"])
+        plan_ = model.step_plan(n, S, D, use_cfg=args.cfg != 1.0)
+        model.bind_scene(plan_, cams_, sc_["input_latents"].to(dev), icams_, sc_["clip_v_embed"].to(dev), stream)
+        plan_.x.copy_(sc_["x_T"].reshape(n, 5, S * S))
+        plan_.set_tables(rows, de, dn)
+
+        def one_step():
+            plan_.loop_step(stream, use_graph=use_graph)
+            if sharded:
+                model.gather_views(plan_)
+
+        for _ in range(max(Wm, 3)):
+            one_step()
+        plan_.counter.fill_(Wm)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(K):
+            one_step()
+        e1.record()
+        barrier()
+        ms_ = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t)
+        return ms_, plan_, sc_, cams_, icams_
+
     clocks = ClockSampler(local)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(K):
-        one_step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t)
+    other = None
+    if world > 1:  # the non-headline mode first, so that the headline plan stays bound for the e2e / kernel-table legs
+        o_ms, o_plan, _, _, _ = timed_loop(not shard)
+        o_scenes = world if shard else 1
+        other = {"value": o_scenes * K / (o_ms * 1e-3), "unit": "steps/s", "ms_per_step": o_ms / K, "views_per_gpu": o_plan.q,
+                 "finite": bool(torch.isfinite(o_plan.x).all())}
+    ms, plan, sc, cams, icams = timed_loop(shard)
     finite = bool(torch.isfinite(plan.x).all())
     scenes = 1 if (shard or world == 1) else world
     steps_per_s = scenes * K / (ms * 1e-3)
@@ -297,9 +316,14 @@ def run_native(args):
         ktab, tot_ms = kernel_table(plan._loop_prog, stream)
         plan.counter.zero_()
         top = ktab[0]
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         if top["tflops"]:
             roof = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["tflops"], "peak": pk["tflops"], "unit": "TFLOP/s",
-                    "frac": round(top["tflops"] / pk["tflops"], 4), "traffic": None, "peak_source": f"{pk['source']} (sustained bf16 cuBLAS)",
+                    "frac": round(top["tflops"] / pk["tflops"], 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"{pk['source']} (sustained bf16 cuBLAS)",
                     "launches_per_step": top["calls"], "share_of_step": top["share"],
                     "note": "achieved = sum of 2MNK over the kernel's launches of one step / sum of their CUDA-event durations (fp16 operands, fp32 accumulate)"}
         if args.kernel_table:
@@ -322,6 +346,13 @@ def run_native(args):
                 "step_roofline": {"gflop_per_step": round(f_step / 1e9, 1), "achieved_tflops_per_gpu": round(f_step * steps_per_s / world / 1e12, 2),
                                   "frac_of_sustained_peak": round(f_step * steps_per_s / world / 1e12 / pk["tflops"], 4)},
                 "kernels": ktab[:8] if ktab else None, "finite": finite and bool(torch.isfinite(x_host).all())}
+        if other is not None:
+            if shard:
+                other["mode"] = "replicas: one independent scene per GPU, no collective (weak scaling)"
+                line["replicas"] = other
+            else:
+                other["mode"] = "ONE scene view-sharded over the GPUs, 1 NCCL all-gather of the 5-channel latents per step (strong scaling)"
+                line["sharded"] = other
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_arm(args, reps=2, warmup=1, model=model)
             line["cpu_baseline"] = cb

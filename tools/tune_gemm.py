@@ -55,6 +55,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--views", type=int, default=8)
     ap.add_argument("--reps", type=int, default=16)
+    ap.add_argument("--shards", default="1", help="comma list of GPU counts whose per-rank shapes (views/G per GPU) to tune")
+    ap.add_argument("--merge", default="", help="existing tuning file whose choices are kept for signatures not re-measured")
     ap.add_argument("--out", default=os.path.join(ROOT, "mvdfusion_b200", "gemm_tuning.json"))
     a = ap.parse_args()
     os.environ["MVD_GEMM_NO_TUNING"] = "1"  # start from the heuristics
@@ -64,45 +66,51 @@ def main():
     lib = _lib.load()
     dev = torch.device("cuda", 0)
     model = build_model(320, 8, D=1, S=32, device=dev)
-    plan = model.step_plan(a.views, 32, 1, use_cfg=True)
     stream = torch.cuda.Stream()
     seen, choices, report = {}, {}, []
-    for c in plan.core_prog.calls:
-        if c.name != "mvd_gemm_f16":
-            continue
-        sig = c.meta["sig"]
-        if sig in seen:
-            continue
-        seen[sig] = True
-        g0, Wt = c.keep[0], c.keep[2]
-        M, N, K = g0.M, g0.N, g0.K
-        wbytes = Wt.numel() * 2
-        ncopy = max(1, min(24, (256 << 20) // wbytes + 1))
-        copies = [Wt] + [Wt.clone() for _ in range(ncopy - 1)]
-        can_split = bool(c.meta["can_split"])
-        geglu = g0.act == ACT_GEGLU
-        tiles_m = (M + 127) // 128
-        base = time_candidate(lib, g0, Wt, copies, g0.tile_n, g0.split_k, 0, a.reps, stream)
-        cands = []
-        for pair in (1, 2):
-            if pair == 2 and tiles_m < 2:
+    if a.merge and os.path.exists(a.merge):
+        choices.update(json.load(open(a.merge)).get("choices", {}))
+    for world in [int(w) for w in a.shards.split(",")]:
+        model.view_group = (None, 0, world) if world > 1 else None  # rank 0's shard: shapes are the same on every rank
+        plan = model.step_plan(a.views, 32, 1, use_cfg=True)
+        print(f"---- {a.views} views over {world} GPU(s): {plan.q} views per GPU", flush=True)
+        for c in plan.core_prog.calls:
+            if c.name != "mvd_gemm_f16":
                 continue
-            for tn in ((g0.tile_n,) if geglu else (64, 96, 128, 160, 192, 224, 256)):
-                if not geglu and N <= 64:
-                    tn = 0
-                for sk in ((1, 2, 3, 4, 6, 8, 12, 16) if can_split else (1,)):
-                    cands.append((tn, sk, pair))
-        cands = sorted(set(cands))
-        best, best_c = base, None
-        for tn, sk, pair in cands:
-            t = time_candidate(lib, g0, Wt, copies, tn, sk, pair, a.reps, stream)
-            if t is not None and t < best * 0.97:  # only move off the heuristic for a clear win
-                best, best_c = t, (tn, sk, pair)
-        if best_c is not None:
-            choices[sig] = list(best_c)
-        report.append((sig, base, best, best_c))
-        print(f"{sig:44s} heuristic {base:7.1f} us   best {best:7.1f} us  {best_c}", flush=True)
-        del copies
+            sig = c.meta["sig"]
+            if sig in seen:
+                continue
+            seen[sig] = True
+            choices.pop(sig, None)
+            g0, Wt = c.keep[0], c.keep[2]
+            M, N, K = g0.M, g0.N, g0.K
+            wbytes = Wt.numel() * 2
+            ncopy = max(1, min(24, (256 << 20) // wbytes + 1))
+            copies = [Wt] + [Wt.clone() for _ in range(ncopy - 1)]
+            can_split = bool(c.meta["can_split"])
+            geglu = g0.act == ACT_GEGLU
+            tiles_m = (M + 127) // 128
+            base = time_candidate(lib, g0, Wt, copies, g0.tile_n, g0.split_k, 0, a.reps, stream)
+            cands = []
+            for pair in (1, 2):
+                if pair == 2 and tiles_m < 2:
+                    continue
+                for tn in ((g0.tile_n,) if geglu else (64, 96, 128, 160, 192, 224, 256)):
+                    if not geglu and N <= 64:
+                        tn = 0
+                    for sk in ((1, 2, 3, 4, 6, 8, 12, 16) if can_split else (1,)):
+                        cands.append((tn, sk, pair))
+            cands = sorted(set(cands))
+            best, best_c = base, None
+            for tn, sk, pair in cands:
+                t = time_candidate(lib, g0, Wt, copies, tn, sk, pair, a.reps, stream)
+                if t is not None and t < best * 0.97:  # only move off the heuristic for a clear win
+                    best, best_c = t, (tn, sk, pair)
+            if best_c is not None:
+                choices[sig] = list(best_c)
+            report.append((sig, base, best, best_c))
+            print(f"{sig:44s} heuristic {base:7.1f} us   best {best:7.1f} us  {best_c}", flush=True)
+            del copies
     gain = sum((b - t) * 1 for _, b, t, _ in report)
     json.dump({"device": torch.cuda.get_device_name(0), "views": a.views, "note": "signature -> [tile_n, split_k, cta_pair]",
                "choices": choices}, open(a.out, "w"), indent=1, sort_keys=True)
