@@ -206,6 +206,8 @@ def run_native(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which must carry exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     n, S, D, K, Wm = args.views, 32, 1, args.steps, args.warmup
     shard = world > 1 and args.mode == "shard"
