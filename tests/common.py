@@ -58,3 +58,17 @@ def unet_cfg_of(model):
     um = model.unet_model.unet_model
     return {"model_channels": um.model_channels, "num_heads": um.num_heads, "image_size": um.image_size,
             "channel_mult": list(um.channel_mult)}
+
+
+def record_parity(name, value, tol):
+    """Append a measured rel-L2 to gpurun_out/parity.jsonl (brought back from the GPU box) and echo it."""
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity.jsonl"), "a") as f:
+            f.write(json.dumps({"case": name, "rel_l2": value, "tolerance": tol}) + "\n")
+    except OSError:
+        pass
+    print(f"parity {name}: rel-L2 {value:.3e} (tolerance {tol:g})")
+    return value

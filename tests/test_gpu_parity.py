@@ -7,7 +7,7 @@ import os
 import pytest
 import torch
 
-from common import build_model, rel_l2, state_dict_cpu, synthetic, unet_cfg_of
+from common import build_model, record_parity, rel_l2, state_dict_cpu, synthetic, unet_cfg_of
 from mvdfusion_b200.mvdfusion.cameras import PerspectiveCameras
 from oracle import mvd_oracle as O
 
@@ -35,7 +35,7 @@ def test_unet_small_vs_golden_and_oracle(small):
     vol = torch.randn(2, 32, 32, 1, 768, generator=g)
     pyr = [v.cuda() for v in O.volume_pyramid(vol)]
     y = m.unet_model.unet_model(xin.cuda(), torch.tensor([gold["t"]]).cuda(), ctx.cuda(), volume_feats=pyr)
-    assert rel_l2(y, gold["out"]) < TOL
+    assert record_parity("unet_small_vs_reference_golden", rel_l2(y, gold["out"]), TOL) < TOL
 
 
 @pytest.mark.parametrize("cfg", [2.5, 1.0])
@@ -47,7 +47,7 @@ def test_apply_model_small_vs_reference_golden(small, cfg):
     t = torch.full((2,), gold["t"], dtype=torch.long, device="cuda")
     eps = m.apply_model(sc["x_T"].cuda(), cams_of(sc["cams"], "cuda"), sc["input_latents"].cuda(), cams_of(sc["in_cams"], "cuda"),
                         sc["clip_v_embed"].cuda(), t, cfg_scale=cfg, depth_eps=de[0].cuda())
-    assert rel_l2(eps, gold["eps"]) < TOL
+    assert record_parity(f"apply_model_small_cfg{cfg}_vs_reference_golden", rel_l2(eps, gold["eps"]), TOL) < TOL
 
 
 def test_apply_model_condition_drop_quirk(small):
@@ -63,7 +63,7 @@ def test_apply_model_condition_drop_quirk(small):
                             drop_random=gold["drop_random"])
     finally:
         m.drop_conditions = False
-    assert rel_l2(eps, gold["eps"]) < TOL
+    assert record_parity("apply_model_condition_drop_vs_reference_golden", rel_l2(eps, gold["eps"]), TOL) < TOL
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
@@ -79,7 +79,7 @@ def test_ddim_loop_small_vs_reference_golden(small, use_graph):
                              verbose=False, x_T=sc["x_T"], depth_eps=de, ddim_noise=dn, use_graph=use_graph)
     for a, b in zip(inter, gold["xt"]):
         assert rel_l2(a["xt"], b) < 2 * TOL
-    assert rel_l2(x, gold["x0"]) < 2 * TOL
+    assert record_parity(f"ddim4_x0_vs_reference_golden_graph{int(use_graph)}", rel_l2(x, gold["x0"]), 2 * TOL) < 2 * TOL
 
 
 @pytest.mark.parametrize("D", [1, 3])
@@ -95,7 +95,7 @@ def test_gridattn_module_vs_oracle(D):
     x = sc["x_T"] * gold["x_scale"]
     y = m.view_attn(x.cuda(), cams_of(sc["cams"], "cuda"), torch.ones(N).cuda(), t_embed.cuda(), t.cuda(), m.scheduler,
                     input_latents=sc["input_latents"].cuda(), input_cameras=cams_of(sc["in_cams"], "cuda"), depth_eps=de[0].cuda())
-    assert rel_l2(y[:, ::4, ::4, :, ::16], gold["out_sub"]) < TOL
+    assert record_parity(f"gridattn_D{D}_vs_reference_golden", rel_l2(y[:, ::4, ::4, :, ::16], gold["out_sub"]), TOL) < TOL
     assert abs(float(y.norm()) / float(gold["out_norm"]) - 1) < TOL
 
 
@@ -111,6 +111,24 @@ def test_apply_model_full_size_vs_oracle():
                         sc["clip_v_embed"].cuda(), t.cuda(), cfg_scale=2.5, depth_eps=de[0].cuda())
     ref = O.apply_model(sd, sc["x_T"], sc["cams"], sc["input_latents"], sc["in_cams"], sc["clip_v_embed"], t, de[0],
                         unet_cfg=unet_cfg_of(m), D=D, cfg_scale=2.5)
-    r = rel_l2(eps, ref)
-    print(f"full-size apply_model rel-L2 vs fp32 oracle: {r:.3e}")
+    r = record_parity("apply_model_full_size_N2_vs_oracle", rel_l2(eps, ref), TOL)
+    assert r < TOL
+
+
+def test_apply_model_full_size_n8_views_subset_vs_oracle():
+    """BASELINE configs[1] exactly (N = 8 views, full-size UNet, cfg 2.5): the CPU oracle evaluates 2 of the 8 query views
+    (every stage is independent per query view given all views' latents), the GPU runs all 8."""
+    N, S, D = 8, 32, 1
+    query = [1, 6]
+    m = build_model(320, 8, D=D, S=S, device="cuda")
+    sd = state_dict_cpu(m)
+    sc = synthetic.scene_inputs(N, S, seed=0)
+    de, _ = synthetic.step_noises(N, D, S, 1, seed=1)
+    t = torch.full((N,), 501, dtype=torch.long)
+    eps = m.apply_model(sc["x_T"].cuda(), cams_of(sc["cams"], "cuda"), sc["input_latents"].cuda(), cams_of(sc["in_cams"], "cuda"),
+                        sc["clip_v_embed"].cuda(), t.cuda(), cfg_scale=2.5, depth_eps=de[0].cuda())
+    ref = O.apply_model(sd, sc["x_T"], sc["cams"], sc["input_latents"], sc["in_cams"], sc["clip_v_embed"], t, de[0],
+                        unet_cfg=unet_cfg_of(m), D=D, cfg_scale=2.5, query=query)
+    r = record_parity("apply_model_full_size_N8_views1and6_vs_oracle", rel_l2(eps[query], ref), TOL)
+    assert torch.isfinite(eps).all()
     assert r < TOL
