@@ -68,13 +68,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   uint8_t* sP = smem + p.off_p;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* bar_q = bars + 0;          // TMA Q landed
-  uint64_t* bar_kv_full = bars + 1;    // [2] K + V^T tile landed
-  uint64_t* bar_kv_empty = bars + 3;   // [2] PV MMA that read the slot retired
-  uint64_t* bar_s_full = bars + 5;     // QK^T MMA retired
-  uint64_t* bar_s_free = bars + 6;     // 128 row threads finished reading S
-  uint64_t* bar_p_ready = bars + 7;    // 128 row threads wrote P (and rescaled O)
-  uint64_t* bar_pv_done = bars + 8;    // PV MMA retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* bar_k_full = bars + 1;     // [2] K tile landed
+  uint64_t* bar_k_empty = bars + 3;    // [2] QK^T MMA that read the slot retired (early: K(j+2) loads under softmax(j))
+  uint64_t* bar_v_full = bars + 5;     // [2] V^T tile landed
+  uint64_t* bar_v_empty = bars + 7;    // [2] PV MMA that read the slot retired
+  uint64_t* bar_s_full = bars + 9;     // QK^T MMA retired
+  uint64_t* bar_s_free = bars + 10;    // 128 row threads pulled S into registers
+  uint64_t* bar_p_ready = bars + 11;   // 128 row threads wrote P (and rescaled O)
+  uint64_t* bar_pv_done = bars + 12;   // PV MMA retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -91,8 +93,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     tma_prefetch_desc(&tmV);
     mbar_init(bar_q, 1);
     for (int s = 0; s < ATT_MAX_STAGES; ++s) {
-      mbar_init(&bar_kv_full[s], 1);
-      mbar_init(&bar_kv_empty[s], 1);
+      mbar_init(&bar_k_full[s], 1);
+      mbar_init(&bar_k_empty[s], 1);
+      mbar_init(&bar_v_full[s], 1);
+      mbar_init(&bar_v_empty[s], 1);
     }
     mbar_init(bar_s_full, 1);
     mbar_init(bar_s_free, ATT_BM);
@@ -112,17 +116,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       // ---------------------------------------------------------------- TMA producer
       pdl_wait();  // q / k / v^T come from the QKV GEMM just before us
       const uint32_t q_bytes = ATT_BM * p.dpad * 2;
-      const uint32_t kv_bytes = BKV * p.dpad * 2 + atoms_kv * p.dpad * 128;
+      const uint32_t k_bytes = BKV * p.dpad * 2;
+      const uint32_t v_bytes = atoms_kv * p.dpad * 128;
       mbar_expect_tx(bar_q, q_bytes);
       for (int a = 0; a < atoms_d; ++a) tma_load_3d(sQ + a * (ATT_BM * 128), &tmQ, bar_q, a * 64, q0, bh);
       for (int j = 0; j < p.n_tiles; ++j) {
         const int st = j % p.stages;
-        mbar_wait(&bar_kv_empty[st], ((j / p.stages) & 1) ^ 1);
-        mbar_expect_tx(&bar_kv_full[st], kv_bytes);
+        const uint32_t ph = ((j / p.stages) & 1) ^ 1;
         uint8_t* k = sK + st * p.k_stage;
         uint8_t* v = sV + st * p.v_stage;
-        for (int a = 0; a < atoms_d; ++a) tma_load_3d(k + a * (BKV * 128), &tmK, &bar_kv_full[st], a * 64, j * BKV, bh);
-        for (int a = 0; a < atoms_kv; ++a) tma_load_3d(v + a * (p.dpad * 128), &tmV, &bar_kv_full[st], j * BKV + a * 64, 0, bh);
+        mbar_wait(&bar_k_empty[st], ph);  // released as soon as QK^T(j - stages) retired
+        mbar_expect_tx(&bar_k_full[st], k_bytes);
+        for (int a = 0; a < atoms_d; ++a) tma_load_3d(k + a * (BKV * 128), &tmK, &bar_k_full[st], a * 64, j * BKV, bh);
+        mbar_wait(&bar_v_empty[st], ph);  // released when PV(j - stages) retired
+        mbar_expect_tx(&bar_v_full[st], v_bytes);
+        for (int a = 0; a < atoms_kv; ++a) tma_load_3d(v + a * (p.dpad * 128), &tmV, &bar_v_full[st], j * BKV + a * 64, 0, bh);
       }
     }
   } else if (warp == 4) {
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       // softmax of tile j; PV(j) follows when P(j) is in shared memory.
       auto issue_qk = [&](int j) {
         const int st = j % p.stages;
-        mbar_wait(&bar_kv_full[st], (j / p.stages) & 1);
+        mbar_wait(&bar_k_full[st], (j / p.stages) & 1);
         if (j > 0) mbar_wait(bar_s_free, (j - 1) & 1);
         tc_fence_after();
         const uint32_t k = smem_u32(sK + st * p.k_stage);
@@ -144,6 +152,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
           const uint32_t ak = k + (ks >> 2) * (BKV * 128) + (ks & 3) * 32;
           umma_f16(tmem_s, umma_desc_sw128(aq), umma_desc_sw128(ak), idesc_s, ks > 0 ? 1u : 0u);
         }
+        tc_commit(&bar_k_empty[st]);
         tc_commit(bar_s_full);
       };
       issue_qk(0);
@@ -151,6 +160,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         const int st = j % p.stages;
         if (j + 1 < p.n_tiles) issue_qk(j + 1);
         const uint32_t v = smem_u32(sV + st * p.v_stage);
+        mbar_wait(&bar_v_full[st], (j / p.stages) & 1);
         mbar_wait(bar_p_ready, j & 1);
         tc_fence_after();
         const int ksteps = (min(BKV, p.seq - j * BKV) + 15) / 16;
@@ -159,7 +169,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
           const uint32_t av = v + (ks >> 2) * (p.dpad * 128) + (ks & 3) * 32;
           umma_f16(tmem_o, umma_desc_sw128(ap), umma_desc_sw128(av), idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
         }
-        tc_commit(&bar_kv_empty[st]);
+        tc_commit(&bar_v_empty[st]);
         tc_commit(bar_pv_done);
       }
     }
@@ -193,17 +203,34 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
 #pragma unroll
       for (int i = 1; i + 1 < BKV; i += 2) mt = fmaxf(mt, fmaxf(s[i], s[i + 1]));
       mt = fmaxf(mt, s[BKV - 1]);
+      float f = 1.f;
+      bool rescale = false;
       if (j == 0) {
         m = mt;
       } else {
-        mbar_wait(bar_pv_done, (j - 1) & 1);  // P tile free again, O quiescent
-        tc_fence_after();
         const bool grow = (mt - m) * p.scale_log2 > 8.f;
-        if (__any_sync(0xffffffffu, grow)) {
+        rescale = __any_sync(0xffffffffu, grow);
+        if (rescale) {
           const float m_new = fmaxf(m, mt);
-          const float f = exp2f((m - m_new) * p.scale_log2);
+          f = exp2f((m - m_new) * p.scale_log2);
           m = m_new;
           l *= f;
+        }
+      }
+      const float mc = m * p.scale_log2;
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < BKV; c += 8) {  // exponentials in place, under the PV MMA of the previous tile
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[c + i] = ex2_fast(fmaf(s[c + i], p.scale_log2, -mc));
+        l0 += (s[c] + s[c + 1]) + (s[c + 2] + s[c + 3]);
+        l1 += (s[c + 4] + s[c + 5]) + (s[c + 6] + s[c + 7]);
+      }
+      l += l0 + l1;
+      if (j > 0) {
+        mbar_wait(bar_pv_done, (j - 1) & 1);  // P tile free again, O quiescent
+        tc_fence_after();
+        if (rescale) {
           for (int c = 0; c < p.n_o; c += 16) {
             float o[16];
             tmem_ld16(tmem_o + lane_base + c, o);
@@ -215,20 +242,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
           tmem_st_wait();
         }
       }
-      const float mc = m * p.scale_log2;
-      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int c = 0; c < BKV; c += 8) {
-        float e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) e[i] = ex2_fast(fmaf(s[c + i], p.scale_log2, -mc));
-        l0 += (e[0] + e[1]) + (e[2] + e[3]);
-        l1 += (e[4] + e[5]) + (e[6] + e[7]);
         // P[r, c..c+7] -> 128B-swizzled K-major tile (atom = 64 keys x 128 rows)
         const uint32_t atom = smem_u32(sP) + (c >> 6) * (ATT_BM * 128) + r * 128;
-        st_shared_16(atom + ((((c & 63) >> 3) ^ (r & 7)) << 4), e);
+        st_shared_16(atom + ((((c & 63) >> 3) ^ (r & 7)) << 4), s + c);
       }
-      l += l0 + l1;
       tc_fence_before();
       fence_async_smem();
       mbar_arrive(bar_p_ready);
@@ -308,7 +327,7 @@ extern "C" int mvd_attn_self_f16(const void* q, const void* k, const void* vt, v
     p.off_v = p.off_k + p.stages * p.k_stage;
     p.off_p = p.off_v + p.stages * p.v_stage;
     p.off_bar = p.off_p + atoms_kv * ATT_BM * 128;
-    return p.off_bar + 128;
+    return p.off_bar + 128;  // 13 barriers + the TMEM slot
   };
   int smem_bytes = 0;
   {

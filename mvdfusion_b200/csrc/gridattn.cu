@@ -317,6 +317,104 @@ __global__ void view_attention_kernel(const __half* __restrict__ qkv, __half* __
   }
 }
 
+// Staged variant (heads * V divides 256): a CTA of 256 threads owns 256 / (heads * V) consecutive points.  The q | k | v rows
+// of a point are one contiguous block of V * 3C halves, so the CTA pulls its 32 rows (48 KB) into shared memory with
+// fully coalesced 16-byte loads, every thread = (point, head, query view) then works out of shared memory (k / v reads are
+// broadcasts across the query views), and writes its 64-byte output segment.
+template <int HD>
+__global__ void __launch_bounds__(256)
+    view_attention_staged_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int P, int V, int heads) {
+  extern __shared__ __align__(16) uint8_t va_smem[];
+  pdl_trigger();
+  pdl_wait();
+  const int C = heads * HD;
+  const int ld = 3 * C;                       // halves per row
+  const int pts = 256 / (heads * V);          // points per CTA
+  const size_t p0 = static_cast<size_t>(blockIdx.x) * pts;
+  const int npts = static_cast<int>(min(static_cast<size_t>(pts), static_cast<size_t>(P) - p0));
+  const int rows = npts * V;
+  const int vec_per_row = ld / 8;             // 16-byte vectors per row
+  const uint4* src = reinterpret_cast<const uint4*>(qkv + p0 * V * ld);
+  uint4* sm = reinterpret_cast<uint4*>(va_smem);
+  const int nvec = rows * vec_per_row;
+  for (int i = threadIdx.x; i < nvec; i += 256) sm[i] = __ldg(src + i);
+  __syncthreads();
+  const int t = threadIdx.x;
+  const int qi = t % V;
+  const int h = (t / V) % heads;
+  const int pl = t / (V * heads);
+  if (pl >= npts) return;
+  const __half* base = reinterpret_cast<const __half*>(va_smem) + static_cast<size_t>(pl) * V * ld;
+  float q[HD];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(base + qi * ld + h * HD);
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      const uint4 u = qp[i];
+      const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(hp[j]);
+        q[i * 8 + 2 * j] = f.x;
+        q[i * 8 + 2 * j + 1] = f.y;
+      }
+    }
+  }
+  const float scale_log2 = rsqrtf(static_cast<float>(HD)) * 1.4426950408889634f;
+  float m = -INFINITY, l = 0.f;
+  float acc[HD];
+#pragma unroll
+  for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+  for (int kj = 0; kj < V; ++kj) {
+    const uint4* kp = reinterpret_cast<const uint4*>(base + kj * ld + C + h * HD);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      const uint4 u = kp[i];
+      const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(hp[j]);
+        s = fmaf(q[i * 8 + 2 * j], f.x, s);
+        s = fmaf(q[i * 8 + 2 * j + 1], f.y, s);
+      }
+    }
+    s *= scale_log2;
+    const float m_new = fmaxf(m, s);
+    const float corr = exp2f(m - m_new);
+    const float pexp = exp2f(s - m_new);
+    l = l * corr + pexp;
+    const uint4* vp = reinterpret_cast<const uint4*>(base + kj * ld + 2 * C + h * HD);
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      const uint4 u = vp[i];
+      const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(hp[j]);
+        acc[i * 8 + 2 * j] = acc[i * 8 + 2 * j] * corr + pexp * f.x;
+        acc[i * 8 + 2 * j + 1] = acc[i * 8 + 2 * j + 1] * corr + pexp * f.y;
+      }
+    }
+    m = m_new;
+  }
+  const float inv = 1.f / l;
+  __half* o = out + ((p0 + pl) * V + qi) * C + h * HD;
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) {
+    __half2 h0 = __floats2half2_rn(acc[i * 8 + 0] * inv, acc[i * 8 + 1] * inv);
+    __half2 h1 = __floats2half2_rn(acc[i * 8 + 2] * inv, acc[i * 8 + 3] * inv);
+    __half2 h2 = __floats2half2_rn(acc[i * 8 + 4] * inv, acc[i * 8 + 5] * inv);
+    __half2 h3 = __floats2half2_rn(acc[i * 8 + 6] * inv, acc[i * 8 + 7] * inv);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2);
+    u.w = *reinterpret_cast<uint32_t*>(&h3);
+    reinterpret_cast<uint4*>(o)[i] = u;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- view pool
 // x fp32 [P*V, 256]; w = x . ww + wb; softmax over V; out[p] = sum_v softmax_v x_v  -> fp16 [P, 256]
 __global__ void view_pool_kernel(const float* __restrict__ x, const float* __restrict__ ww, const float* __restrict__ wb,
@@ -492,6 +590,22 @@ extern "C" int mvd_view_attention_f16(const void* qkv, void* out, int32_t P, int
   if (!qkv || !out || P <= 0 || V <= 0 || heads <= 0) return set_error(MVD_EINVAL, "mvd_view_attention_f16: bad arguments");
   if (hd != 32) return set_error(MVD_EINVAL, "mvd_view_attention_f16: head dim must be 32");
   const size_t total = static_cast<size_t>(P) * heads * V;
+  if (256 % (heads * V) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const int pts = 256 / (heads * V);
+    const size_t smem = static_cast<size_t>(pts) * V * 3 * heads * 32 * sizeof(__half);
+    static bool configured = false;
+    if (!configured) {
+      MVD_CUDA_CHECK(cudaFuncSetAttribute(view_attention_staged_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      configured = true;
+    }
+    if (smem <= 64 * 1024) {
+      MVD_LAUNCH((view_attention_staged_kernel<32>), static_cast<unsigned>((P + pts - 1) / pts), 256, smem, stream,
+                 static_cast<const __half*>(qkv), static_cast<__half*>(out), P, V, heads);
+      count_launch();
+      MVD_CUDA_CHECK(cudaGetLastError());
+      return MVD_OK;
+    }
+  }
   MVD_LAUNCH((view_attention_kernel<32>), static_cast<unsigned>((total + 127) / 128), 128, 0, stream, 
       static_cast<const __half*>(qkv), static_cast<__half*>(out), P, V, heads);
   count_launch();

@@ -142,6 +142,13 @@ def test_data_movement(nat, dbl):
     run_both(nat, dbl, "rows_to_nchw", t, ["z"], "r", "z", 2, 10, 10, 64)
 
 
+@pytest.mark.parametrize("P,V", [(1030, 8), (515, 4), (129, 16), (200, 3)])
+def test_view_attention_layouts(nat, dbl, P, V):
+    """staged kernel (heads * V divides 256, ragged last CTA) and the per-thread fallback (V = 3)"""
+    t = {"qkv": rnd(P * V, 768, dtype=torch.float16, seed=3), "o": torch.zeros(P * V, 256, dtype=torch.float16)}
+    run_both(nat, dbl, "view_attention", t, ["o"], "qkv", "o", P, V, 8, 32)
+
+
 def test_gemv_grouped(nat, dbl):
     K = 1280
     x = rnd(1, K, seed=5)
