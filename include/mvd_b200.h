@@ -113,12 +113,16 @@ int mvd_attn_self_f16(const void* q, const void* k, const void* vt, void* out, i
 /* ------------------------------------------------------------------------------------------------
  * Normalisation (fp32 residual stream in, fp16 GEMM operand out).
  *   groupnorm : 32 groups over [n_img, hw, C]; optional SiLU.  util.py:200-217 (eps 1e-5, ResBlock/out),
- *               external/sd1/ldm/modules/attention.py:76-77 (eps 1e-6).  stats_ws: n_img*64 doubles.
+ *               external/sd1/ldm/modules/attention.py:76-77 (eps 1e-6).  stats_ws: unused since the single-pass kernel (may be NULL).
  *   layernorm : nn.LayerNorm(C) (external/sd1/ldm/modules/attention.py:211-213, mvdfusion/attention.py:35-37)
  *   ln_modulate : LayerNorm(no affine) then x*(1+scale)+shift (mvdfusion/view_attn_efficient2.py:15-16,65-66)
  * ---------------------------------------------------------------------------------------------- */
 int mvd_groupnorm_f32_f16(const float* x, const float* gamma, const float* beta, void* y, void* stats_ws,
                           int32_t n_img, int32_t hw, int32_t C, float eps, int32_t apply_silu, void* stream);
+/* GroupNorm of the channel concatenation [x1 | x2] (x1: [n_img, hw, C1], x2: [n_img, hw, C2]) without materialising it:
+ * `h = th.cat([h, hs.pop()], dim=1)` followed by ResBlock.in_layers[0] in the UNet's output blocks (mvdfusion/unet.py:550). */
+int mvd_groupnorm2_f32_f16(const float* x1, int32_t C1, const float* x2, int32_t C2, const float* gamma, const float* beta,
+                           void* y, int32_t n_img, int32_t hw, float eps, int32_t apply_silu, void* stream);
 int mvd_layernorm_f32_f16(const float* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t C,
                           float eps, void* stream);
 int mvd_ln_modulate_f32_f16(const float* x, const float* shift, const float* scale, void* y, int32_t rows, int32_t C,
@@ -130,6 +134,8 @@ int mvd_ln_modulate_f32_f16(const float* x, const float* shift, const float* sca
 int mvd_cast_f32_f16(const float* x, void* y, long long n, void* stream);
 /* torch.cat([h, hs.pop()], dim=1) in rows x channels form (mvdfusion/unet.py:550) */
 int mvd_concat_f32(const float* a, const float* b, float* out, long long rows, int32_t C1, int32_t C2, void* stream);
+/* the same concatenation as the fp16 operand of the ResBlock's 1x1 skip convolution (openaimodel.py:241,273) */
+int mvd_concat_f32_f16(const float* a, const float* b, void* out, long long rows, int32_t C1, int32_t C2, void* stream);
 /* F.interpolate(scale_factor=2, mode="nearest") (openaimodel.py:116); fp32 NHWC -> fp16 NHWC */
 int mvd_upsample2x_f32_f16(const float* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C, void* stream);
 /* im2col of the stride-2 Downsample conv (openaimodel.py:151): fp32 NHWC -> fp16 [n*(H/2)*(W/2), 9*C] */

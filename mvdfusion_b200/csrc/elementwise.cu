@@ -45,6 +45,27 @@ __global__ void concat_f32_kernel(const float* __restrict__ a, const float* __re
   }
 }
 
+// the same concatenation written as the fp16 operand of the ResBlock's 1x1 skip convolution (openaimodel.py:241,273)
+__global__ void concat_f16_kernel(const float* __restrict__ a, const float* __restrict__ b, __half* __restrict__ out,
+                                  int C1, int C2, size_t total4) {
+  pdl_trigger();
+  pdl_wait();
+  const int C = C1 + C2;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t e = i * 4;
+    const size_t r = e / C;
+    const int c = static_cast<int>(e - r * C);
+    const float4 v = c < C1 ? *reinterpret_cast<const float4*>(a + r * C1 + c) : *reinterpret_cast<const float4*>(b + r * C2 + (c - C1));
+    __half2 h0 = __floats2half2_rn(v.x, v.y);
+    __half2 h1 = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(out + e) = u;
+  }
+}
+
 // F.interpolate(scale_factor=2, mode='nearest') (openaimodel.py:116): fp32 [n,H,W,C] -> fp16 [n,2H,2W,C]
 __global__ void upsample2x_kernel(const float* __restrict__ x, __half* __restrict__ y, int H, int W, int C,
                                   size_t total4) {
@@ -361,6 +382,18 @@ extern "C" int mvd_concat_f32(const float* a, const float* b, float* out, long l
     return set_error(MVD_EINVAL, "mvd_concat_f32: channel counts must be multiples of 4");
   const size_t total4 = static_cast<size_t>(rows) * (C1 + C2) / 4;
   MVD_LAUNCH((concat_f32_kernel), grid_for(total4), 256, 0, stream, a, b, out, C1, C2, total4);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_concat_f32_f16(const float* a, const float* b, void* out, long long rows, int32_t C1, int32_t C2,
+                                  void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!a || !b || !out || rows <= 0 || C1 <= 0 || C2 <= 0 || (C1 & 3) || (C2 & 3))
+    return set_error(MVD_EINVAL, "mvd_concat_f32_f16: channel counts must be multiples of 4");
+  const size_t total4 = static_cast<size_t>(rows) * (C1 + C2) / 4;
+  MVD_LAUNCH((concat_f16_kernel), grid_for(total4), 256, 0, stream, a, b, static_cast<__half*>(out), C1, C2, total4);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

@@ -18,8 +18,9 @@ namespace mvd {
 // are re-read from L2 in the second phase.
 template <bool CACHE>
 __global__ void __launch_bounds__(512)
-    gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    __half* __restrict__ y, int hw, int C, int cpg, int gpc, int rows, float eps, int apply_silu) {
+    gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ x2, int C1, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, __half* __restrict__ y, int hw, int C, int cpg, int gpc, int rows, float eps,
+                    int apply_silu) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) uint8_t gn_smem[];
@@ -29,15 +30,22 @@ __global__ void __launch_bounds__(512)
   float* part_q = part_s + rows * span;               // [rows][span]
   float* s_mean = part_q + rows * span;               // [32]
   float* s_rstd = s_mean + 32;                        // [32]
-  float4* cache = reinterpret_cast<float4*>(s_rstd + 32);  // [hw][span4] when CACHE
+  float4* cache = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(s_rstd + 32) + 32 * 16 * 2 * sizeof(double));  // [hw][span4] when CACHE
 
   const int img = blockIdx.y;
   const int c0 = blockIdx.x * span;  // first channel of this CTA's slice
   const int cq = threadIdx.x % span4;
   const int row = threadIdx.x / span4;
   const bool active = row < rows;
-  const size_t pix_stride4 = static_cast<size_t>(C) >> 2;
-  const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(img) * hw * C + c0) + cq;
+  // two-source form (x2 != nullptr): channels [0, C1) live in x [.., C1], channels [C1, C) in x2 [.., C - C1] — the
+  // torch.cat([h, skip], dim=1) of the UNet's output blocks (mvdfusion/unet.py:550) is never materialised.
+  // C1 % 4 == 0, so a thread's four channels always come from one source.
+  const int cg = c0 + cq * 4;  // first global channel of this thread
+  const bool second = x2 != nullptr && cg >= C1;
+  const int Csrc = x2 == nullptr ? C : (second ? C - C1 : C1);
+  const size_t pix_stride4 = static_cast<size_t>(Csrc) >> 2;
+  const float4* src = reinterpret_cast<const float4*>((second ? x2 : x) + static_cast<size_t>(img) * hw * Csrc + (second ? cg - C1 : cg));
+  const size_t out_stride4 = static_cast<size_t>(C) >> 2;
 
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   if (active) {
@@ -65,13 +73,14 @@ __global__ void __launch_bounds__(512)
     }
   }
   __syncthreads();
-  // warp w reduces local groups w, w + nwarps, ...: rows x cpg partials each, in double
+  // every warp sums a strided share of each group's rows x cpg partials in double; one thread per group finishes
   {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    double* red = reinterpret_cast<double*>(s_rstd + 32);  // [gpc][nwarps][2], in front of the cache
     const int n = rows * cpg;
-    for (int g = warp; g < gpc; g += nwarps) {
+    for (int g = 0; g < gpc; ++g) {
       double a = 0.0, b = 0.0;
-      for (int i = lane; i < n; i += 32) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int rr = i / cpg, c = i - rr * cpg;
         a += static_cast<double>(part_s[rr * span + g * cpg + c]);
         b += static_cast<double>(part_q[rr * span + g * cpg + c]);
@@ -82,12 +91,23 @@ __global__ void __launch_bounds__(512)
         b += __shfl_xor_sync(0xffffffffu, b, o);
       }
       if (lane == 0) {
-        const double inv_cnt = 1.0 / (static_cast<double>(hw) * cpg);
-        const double mean = a * inv_cnt;
-        const double var = fmax(b * inv_cnt - mean * mean, 0.0);
-        s_mean[g] = static_cast<float>(mean);
-        s_rstd[g] = rsqrtf(static_cast<float>(var) + eps);
+        red[(g * nwarps + warp) * 2] = a;
+        red[(g * nwarps + warp) * 2 + 1] = b;
       }
+    }
+    __syncthreads();
+    if (threadIdx.x < gpc) {
+      const int g = threadIdx.x;
+      double a = 0.0, b = 0.0;
+      for (int w = 0; w < nwarps; ++w) {
+        a += red[(g * nwarps + w) * 2];
+        b += red[(g * nwarps + w) * 2 + 1];
+      }
+      const double inv_cnt = 1.0 / (static_cast<double>(hw) * cpg);
+      const double mean = a * inv_cnt;
+      const double var = fmax(b * inv_cnt - mean * mean, 0.0);
+      s_mean[g] = static_cast<float>(mean);
+      s_rstd[g] = rsqrtf(static_cast<float>(var) + eps);
     }
   }
   __syncthreads();
@@ -114,7 +134,7 @@ __global__ void __launch_bounds__(512)
     uint2 u;
     u.x = *reinterpret_cast<uint32_t*>(&h0);
     u.y = *reinterpret_cast<uint32_t*>(&h1);
-    dst[static_cast<size_t>(p) * pix_stride4] = u;
+    dst[static_cast<size_t>(p) * out_stride4] = u;
   }
 }
 
@@ -189,16 +209,16 @@ __global__ void ln_kernel(const float* __restrict__ x, const float* __restrict__
 
 using namespace mvd;
 
-extern "C" int mvd_groupnorm_f32_f16(const float* x, const float* gamma, const float* beta, void* y, void* stats_ws,
-                                     int32_t n_img, int32_t hw, int32_t C, float eps, int32_t apply_silu,
-                                     void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!x || !gamma || !beta || !y || !stats_ws) return set_error(MVD_EINVAL, "mvd_groupnorm_f32_f16: null pointer");
+static int groupnorm_launch(const float* x, const float* x2, int C1, const float* gamma, const float* beta, void* y, int32_t n_img,
+                            int32_t hw, int32_t C, float eps, int32_t apply_silu, cudaStream_t stream) {
+  if (!x || !gamma || !beta || !y) return set_error(MVD_EINVAL, "mvd_groupnorm_f32_f16: null pointer");
+  if (x2 != nullptr && (C1 <= 0 || C1 >= C || (C1 & 3) != 0 || ((C - C1) & 3) != 0))
+    return set_error(MVD_EINVAL, "mvd_groupnorm2_f32_f16: C1 and C2 must be positive multiples of 4");
   if (n_img <= 0 || hw <= 0 || C <= 0 || (C % 32) != 0 || (C & 3) != 0)
     return set_error(MVD_EINVAL, "mvd_groupnorm_f32_f16: C must be a multiple of 32");
   const int cpg = C / 32;
   if (C > 4096) return set_error(MVD_EINVAL, "mvd_groupnorm_f32_f16: C must be <= 4096");
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 7))
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(x2) & 15) || (reinterpret_cast<uintptr_t>(y) & 7))
     return set_error(MVD_EALIGN, "mvd_groupnorm_f32_f16: x must be 16-byte and y 8-byte aligned");
   // groups per CTA: the smallest power of two whose channel span is a multiple of 8 (whole sectors per pixel), else of 4
   int gpc = 0;
@@ -213,7 +233,7 @@ extern "C" int mvd_groupnorm_f32_f16(const float* x, const float* gamma, const f
   if (rows > hw) rows = hw;
   int threads = (rows * span4 + 31) / 32 * 32;
   if (threads < 32 * 1) threads = 32;
-  const size_t fixed = static_cast<size_t>(2) * rows * span * sizeof(float) + 64 * sizeof(float);
+  const size_t fixed = static_cast<size_t>(2) * rows * span * sizeof(float) + 64 * sizeof(float) + 32 * 16 * 2 * sizeof(double);
   const size_t cache_bytes = static_cast<size_t>(hw) * span * sizeof(float);
   const bool use_cache = fixed + cache_bytes <= 200 * 1024;
   const size_t sm = fixed + (use_cache ? cache_bytes : 0);
@@ -222,15 +242,28 @@ extern "C" int mvd_groupnorm_f32_f16(const float* x, const float* gamma, const f
     MVD_CUDA_CHECK(cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
     configured = true;
   }
-  (void)stats_ws;
   const dim3 grid(32 / gpc, n_img);
   if (use_cache)
-    MVD_LAUNCH((gn_fused_kernel<true>), grid, threads, sm, stream, x, gamma, beta, static_cast<__half*>(y), hw, C, cpg, gpc, rows, eps, apply_silu);
+    MVD_LAUNCH((gn_fused_kernel<true>), grid, threads, sm, stream, x, x2, C1, gamma, beta, static_cast<__half*>(y), hw, C, cpg, gpc, rows, eps, apply_silu);
   else
-    MVD_LAUNCH((gn_fused_kernel<false>), grid, threads, sm, stream, x, gamma, beta, static_cast<__half*>(y), hw, C, cpg, gpc, rows, eps, apply_silu);
+    MVD_LAUNCH((gn_fused_kernel<false>), grid, threads, sm, stream, x, x2, C1, gamma, beta, static_cast<__half*>(y), hw, C, cpg, gpc, rows, eps, apply_silu);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
+}
+
+extern "C" int mvd_groupnorm_f32_f16(const float* x, const float* gamma, const float* beta, void* y, void* stats_ws,
+                                     int32_t n_img, int32_t hw, int32_t C, float eps, int32_t apply_silu,
+                                     void* stream_) {
+  (void)stats_ws;  // the single-pass kernel keeps its statistics on chip; the argument stays for ABI stability
+  return groupnorm_launch(x, nullptr, 0, gamma, beta, y, n_img, hw, C, eps, apply_silu, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mvd_groupnorm2_f32_f16(const float* x1, int32_t C1, const float* x2, int32_t C2, const float* gamma,
+                                      const float* beta, void* y, int32_t n_img, int32_t hw, float eps, int32_t apply_silu,
+                                      void* stream_) {
+  if (!x2) return set_error(MVD_EINVAL, "mvd_groupnorm2_f32_f16: null pointer");
+  return groupnorm_launch(x1, x2, C1, gamma, beta, y, n_img, hw, C1 + C2, eps, apply_silu, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int mvd_layernorm_f32_f16(const float* x, const float* gamma, const float* beta, void* y, int32_t rows,

@@ -258,8 +258,7 @@ class Builder:
     def groupnorm(self, x, p, n_img, hw, C, eps, silu):
         """GroupNorm32(32, C) (+SiLU) -> fp16 operand.  util.py:200-217 / attention.py:76-77"""
         y = self.t16(n_img * hw, C)
-        self.prog.append(self.ops.groupnorm(x, self.W.f32(p + ".weight"), self.W.f32(p + ".bias"), y, self.stats_ws(n_img),
-                                            n_img, hw, C, eps, silu))
+        self.prog.append(self.ops.groupnorm(x, self.W.f32(p + ".weight"), self.W.f32(p + ".bias"), y, None, n_img, hw, C, eps, silu))
         return y
 
     def layernorm(self, x, p, rows, C):
@@ -299,11 +298,20 @@ class Builder:
         self.prog.append(self.ops.gemv_grouped(emb, emb_dim, jobs, silu_in=True))
 
     # -- ResBlock
-    def resblock(self, x, p, n_img, H, Cin, Cout, emb, emb_dim):
+    def resblock(self, x, p, n_img, H, Cin, Cout, emb, emb_dim, cat=None):
         """ResBlock._forward (openaimodel.py:255-275): GN-SiLU-conv, + Linear(SiLU(emb)), GN-SiLU-conv, + skip.
-        The timestep term is per-channel only (one shared t), so it rides in the first conv's bias."""
+        The timestep term is per-channel only (one shared t), so it rides in the first conv's bias.
+        cat = (h, skip): the block input is torch.cat([h, skip], dim=1) (mvdfusion/unet.py:550); it is consumed by a
+        two-source GroupNorm and written once as the fp16 operand of the 1x1 skip convolution, never in fp32."""
         hw, M = H * H, n_img * H * H
-        a = self.groupnorm(x, p + ".in_layers.0", n_img, hw, Cin, 1e-5, True)
+        if cat is not None:
+            assert x is None and self.W.has(p + ".skip_connection.weight")
+            c1, c2 = cat[0].shape[-1], cat[1].shape[-1]
+            a = self.t16(M, Cin)
+            self.prog.append(self.ops.groupnorm2(cat[0], c1, cat[1], c2, self.W.f32(p + ".in_layers.0.weight"),
+                                                 self.W.f32(p + ".in_layers.0.bias"), a, n_img, hw, 1e-5, True))
+        else:
+            a = self.groupnorm(x, p + ".in_layers.0", n_img, hw, Cin, 1e-5, True)
         ne = emb.shape[0]  # 1 on the path (shared t); n_img when a caller passes per-image embeddings
         pre = self._emb_vectors.get(p) if ne == 1 else None
         if pre is not None:  # computed with every other ResBlock's vector by one grouped launch (emb_vectors)
@@ -322,7 +330,11 @@ class Builder:
         self.free(h, eb)
         res, s = x, None
         if self.W.has(p + ".skip_connection.weight"):
-            x16 = self.cast16(x, M, Cin)
+            if cat is not None:
+                x16 = self.t16(M, Cin)
+                self.prog.append(self.ops.concat16(cat[0], cat[1], x16, M, cat[0].shape[-1], cat[1].shape[-1]))
+            else:
+                x16 = self.cast16(x, M, Cin)
             s = self.t32(M, Cout)
             self.gemm(x16, self.W.lin(p + ".skip_connection.weight"), s, M, Cout, Cin, allow_split=True,
                       bias=self.W.f32(p + ".skip_connection.bias"))
@@ -547,8 +559,10 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
     H = S
     hs = []
 
-    def run_layers(h, prefix, layers, H):
+    def run_layers(h, prefix, layers, H, start=0):
         for j, l in enumerate(layers):
+            if j < start:
+                continue
             p = f"{prefix}.{j}"
             kind = l[0]
             if kind == "stem":
@@ -582,10 +596,16 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
         skip, _ = hs.pop()
         c1, c2 = h.shape[-1], skip.shape[-1]
         rows = n_img * H * H
-        cat = b.t32(rows, c1 + c2)
-        b.prog.append(b.ops.concat(h, skip, cat, rows, c1, c2))
-        b.free(h, skip)
-        h, H = run_layers(cat, f"output_blocks.{i}", layers, H)
+        p0 = f"output_blocks.{i}.0"
+        if layers[0][0] == "res" and b.W.has(p0 + ".skip_connection.weight"):
+            new = b.resblock(None, p0, n_img, H, c1 + c2, layers[0][2], emb, spec.emb_dim, cat=(h, skip))
+            b.free(h, skip)
+            h, H = run_layers(new, f"output_blocks.{i}", layers, H, start=1)
+        else:
+            cat = b.t32(rows, c1 + c2)
+            b.prog.append(b.ops.concat(h, skip, cat, rows, c1, c2))
+            b.free(h, skip)
+            h, H = run_layers(cat, f"output_blocks.{i}", layers, H)
     a = b.groupnorm(h, "out.0", n_img, H * H, spec.final_ch, 1e-5, True)
     b.free(h)
     head = b.ops.empty((n_img * H * H, 8), torch.float32)

@@ -136,8 +136,15 @@ class NativeOps:
     def groupnorm(self, x, gamma, beta, y, stats_ws, n_img, hw, C, eps, silu):
         return self._bind("mvd_groupnorm_f32_f16", (_ptr(x, torch.float32), _ptr(gamma, torch.float32),
                                                     _ptr(beta, torch.float32), _ptr(y, torch.float16),
-                                                    _ptr(stats_ws, torch.float64), n_img, hw, C, eps, int(silu)),
+                                                    _ptr(stats_ws, torch.float64) if stats_ws is not None else None, n_img, hw, C,
+                                                    eps, int(silu)),
                           (x, gamma, beta, y, stats_ws), {"desc": f"img{n_img} hw{hw} C{C}", "bytes": 6.0 * n_img * hw * C})
+
+    def groupnorm2(self, x1, C1, x2, C2, gamma, beta, y, n_img, hw, eps, silu):
+        return self._bind("mvd_groupnorm2_f32_f16", (_ptr(x1, torch.float32), C1, _ptr(x2, torch.float32), C2, _ptr(gamma, torch.float32),
+                                                     _ptr(beta, torch.float32), _ptr(y, torch.float16), n_img, hw, eps, int(silu)),
+                          (x1, x2, gamma, beta, y), {"kernel": "groupnorm_f32_f16", "desc": f"img{n_img} hw{hw} C{C1}+{C2}",
+                                                     "bytes": 6.0 * n_img * hw * (C1 + C2)})
 
     def layernorm(self, x, gamma, beta, y, rows, C, eps):
         return self._bind("mvd_layernorm_f32_f16", (_ptr(x, torch.float32), _ptr(gamma, torch.float32),
@@ -157,6 +164,10 @@ class NativeOps:
     def concat(self, a, b, out, rows, C1, C2):
         return self._bind("mvd_concat_f32", (_ptr(a, torch.float32), _ptr(b, torch.float32), _ptr(out, torch.float32),
                                              rows, C1, C2), (a, b, out), {"desc": f"rows{rows} {C1}+{C2}", "bytes": 8.0 * rows * (C1 + C2)})
+
+    def concat16(self, a, b, out, rows, C1, C2):
+        return self._bind("mvd_concat_f32_f16", (_ptr(a, torch.float32), _ptr(b, torch.float32), _ptr(out, torch.float16),
+                                                 rows, C1, C2), (a, b, out), {"desc": f"rows{rows} {C1}+{C2}", "bytes": 6.0 * rows * (C1 + C2)})
 
     def upsample2x(self, x, y, n_img, H, W, C):
         return self._bind("mvd_upsample2x_f32_f16", (_ptr(x, torch.float32), _ptr(y, torch.float16), n_img, H, W, C),

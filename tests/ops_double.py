@@ -120,6 +120,17 @@ class TorchOpsDouble:
             y.reshape(-1)[: n_img * hw * C].copy_(o.permute(0, 2, 1).reshape(-1).half())
         return self._call(fn)
 
+    def groupnorm2(self, x1, C1, x2, C2, gamma, beta, y, n_img, hw, eps, silu):
+        def fn():
+            a = x1.reshape(-1)[: n_img * hw * C1].reshape(n_img, hw, C1)
+            b = x2.reshape(-1)[: n_img * hw * C2].reshape(n_img, hw, C2)
+            v = torch.cat([a, b], dim=2).permute(0, 2, 1)
+            o = F.group_norm(v, 32, gamma, beta, eps)
+            if silu:
+                o = F.silu(o)
+            y.reshape(-1)[: n_img * hw * (C1 + C2)].copy_(o.permute(0, 2, 1).reshape(-1).half())
+        return self._call(fn)
+
     def layernorm(self, x, gamma, beta, y, rows, C, eps):
         def fn():
             v = x.reshape(-1)[: rows * C].reshape(rows, C)
@@ -142,6 +153,13 @@ class TorchOpsDouble:
             o = out.reshape(-1)[: rows * (C1 + C2)].reshape(rows, C1 + C2)
             o[:, :C1] = a.reshape(-1)[: rows * C1].reshape(rows, C1)
             o[:, C1:] = b.reshape(-1)[: rows * C2].reshape(rows, C2)
+        return self._call(fn)
+
+    def concat16(self, a, b, out, rows, C1, C2):
+        def fn():
+            o = out.reshape(-1)[: rows * (C1 + C2)].reshape(rows, C1 + C2)
+            o[:, :C1] = a.reshape(-1)[: rows * C1].reshape(rows, C1).half()
+            o[:, C1:] = b.reshape(-1)[: rows * C2].reshape(rows, C2).half()
         return self._call(fn)
 
     def upsample2x(self, x, y, n_img, H, W, C):

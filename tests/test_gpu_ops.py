@@ -118,6 +118,15 @@ def test_groupnorm(nat, dbl, n, hw, C, silu):
     run_both(nat, dbl, "groupnorm", t, ["y"], "x", "g", "b", "y", "ws", n, hw, C, 1e-5, silu)
 
 
+@pytest.mark.parametrize("n,hw,C1,C2", [(2, 1024, 320, 320), (3, 256, 640, 320), (4, 16, 1280, 1280), (2, 64, 1280, 640)])
+def test_groupnorm_two_sources_and_concat16(nat, dbl, n, hw, C1, C2):
+    C = C1 + C2
+    t = {"a": rnd(n * hw, C1, seed=1) + 0.3, "b": rnd(n * hw, C2, seed=2) * 2.0, "g": rnd(C, seed=3), "be": rnd(C, seed=4),
+         "y": torch.zeros(n * hw, C, dtype=torch.float16), "c": torch.zeros(n * hw, C, dtype=torch.float16)}
+    run_both(nat, dbl, "groupnorm2", t, ["y"], "a", C1, "b", C2, "g", "be", "y", n, hw, 1e-5, True, tol=4e-3)
+    run_both(nat, dbl, "concat16", t, ["c"], "a", "b", "c", n * hw, C1, C2, tol=1e-3)
+
+
 def test_layernorms(nat, dbl):
     for rows, C in ((512, 320), (100, 1280), (4096, 256)):
         t = {"x": rnd(rows, C) * 3, "g": rnd(C, seed=1), "b": rnd(C, seed=2), "y": torch.zeros(rows, C, dtype=torch.float16)}

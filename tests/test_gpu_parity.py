@@ -132,3 +132,72 @@ def test_apply_model_full_size_n8_views_subset_vs_oracle():
     r = record_parity("apply_model_full_size_N8_views1and6_vs_oracle", rel_l2(eps[query], ref), TOL)
     assert torch.isfinite(eps).all()
     assert r < TOL
+
+
+def _apply_both(m, N, S, D, cfg, seed=0, t_val=641):
+    sd = state_dict_cpu(m)
+    sc = synthetic.scene_inputs(N, S, seed=seed)
+    de, _ = synthetic.step_noises(N, D, S, 1, seed=seed + 1)
+    t = torch.full((N,), t_val, dtype=torch.long)
+    eps = m.apply_model(sc["x_T"].cuda(), cams_of(sc["cams"], "cuda"), sc["input_latents"].cuda(), cams_of(sc["in_cams"], "cuda"),
+                        sc["clip_v_embed"].cuda(), t.cuda(), cfg_scale=cfg, depth_eps=de[0].cuda())
+    ref = O.apply_model(sd, sc["x_T"], sc["cams"], sc["input_latents"], sc["in_cams"], sc["clip_v_embed"], t, de[0],
+                        unet_cfg=unet_cfg_of(m), D=D, cfg_scale=cfg)
+    return eps, ref
+
+
+def test_apply_model_three_depth_samples_vs_oracle():
+    """n_pts_per_ray = 3 (configs/mvd_train.yaml:28): D keys per pixel in the view cross-attention (to_q / to_k / softmax
+    over D, mvdfusion/attention.py:56-62) and D-fold frustum pyramid."""
+    m = build_model(64, 8, D=3, S=32, device="cuda")
+    eps, ref = _apply_both(m, 2, 32, 3, 2.5, seed=5)
+    assert record_parity("apply_model_small_D3_vs_oracle", rel_l2(eps, ref), TOL) < TOL
+
+
+def test_apply_model_64x64_latents_vs_oracle():
+    """BASELINE configs[4]: 512^2 images = 64x64 latents (self-attention over 4096 tokens, 64-wide conv rows)."""
+    m = build_model(64, 8, D=1, S=64, device="cuda")
+    eps, ref = _apply_both(m, 2, 64, 1, 2.5, seed=7)
+    assert record_parity("apply_model_small_S64_vs_oracle", rel_l2(eps, ref), TOL) < TOL
+
+
+def test_apply_model_sixteen_views_vs_oracle():
+    """BASELINE configs[2]'s view count (N = 16): 16-way view attention in GridAttn, 32 UNet images under CFG."""
+    m = build_model(64, 8, D=1, S=32, device="cuda")
+    eps, ref = _apply_both(m, 16, 32, 1, 2.5, seed=9)
+    assert record_parity("apply_model_small_N16_vs_oracle", rel_l2(eps, ref), TOL) < TOL
+
+
+def test_view_shards_reproduce_the_full_batch_on_one_gpu():
+    """The per-rank programs of a 2-way and a 4-way view shard (built on this one GPU, no collective needed for a single
+    apply_model) give the rows of the unsharded result: sharding changes M of every GEMM, not the numbers beyond fp16
+    operand rounding (split-K / tile choices differ, so not bit-exact)."""
+    from mvdfusion_b200.runtime import current_stream
+    N, S, D = 8, 32, 1
+    m = build_model(64, 8, D=D, S=S, device="cuda")
+    sc = synthetic.scene_inputs(N, S, seed=2)
+    de, dn = synthetic.step_noises(N, D, S, 1, seed=3)
+    row = m.ddim.step_row(30, 2.5)
+    stream = current_stream(torch.device("cuda"))
+
+    def run(world, rank):
+        m.view_group = (None, rank, world) if world > 1 else None
+        plan = m.step_plan(N, S, D, use_cfg=True)
+        m.bind_scene(plan, cams_of(sc["cams"], "cuda"), sc["input_latents"].cuda(), cams_of(sc["in_cams"], "cuda"),
+                     sc["clip_v_embed"].cuda(), stream)
+        plan.x.copy_(sc["x_T"].reshape(N, 5, S * S))
+        plan.set_step_constants(row)
+        plan.depth_eps.copy_(de[0].reshape(plan.depth_eps.shape))
+        plan.run_eps(stream)
+        torch.cuda.synchronize()
+        return plan.eps_out.clone(), plan.q_first, plan.q
+
+    try:
+        full, _, _ = run(1, 0)
+        for world in (2, 4):
+            for rank in range(world):
+                part, q0, q = run(world, rank)
+                r = rel_l2(part, full[q0:q0 + q])
+                assert r < 1e-3, (world, rank, r)
+    finally:
+        m.view_group = None
