@@ -117,7 +117,7 @@ def run_reference(args):
                        "timed_samples": reps, "note": "reference algorithm (CPU port, oracle/) on host cores; bounded sample per step"},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -206,8 +206,6 @@ def run_native(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which must carry exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     n, S, D, K, Wm = args.views, 32, 1, args.steps, args.warmup
     shard = world > 1 and args.mode == "shard"
@@ -358,12 +356,21 @@ def run_native(args):
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_arm(args, reps=2, warmup=1, model=model)
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints there (NCCL's version banner...) was
+    re-routed to stderr at start-up."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 if __name__ == "__main__":
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)
