@@ -66,6 +66,11 @@ struct GemmKParams {
   float* ws;
   int* counters;
   int acc_stride, tmem_cols;
+  __half* out16;            // optional fp16 copy of an F32 output (the next GEMM's operand), [M, ld16]
+  int ld16, vec_out16;
+  const float* ln_colsum;   // LayerNorm folded into this GEMM (see mvd_b200.h): column sums of the gamma-scaled weights
+  float ln_eps, ln_inv_k;
+  int ln_k;                 // K of the problem (columns of a row that exist)
 };
 
 __device__ __forceinline__ void store8_f16(__half* dst, const float* v) {
@@ -177,6 +182,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* acc_full = bars + 2 * MAX_STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float2* rowstat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 512);  // [2][128] {mean, rstd}; LN mode only
+  const bool ln = p.ln_colsum != nullptr;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -189,10 +196,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], ln ? 3 : 1);  // LN mode: the two statistics warps also read the A tile
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_full[b], ln ? 1 + 64 : 1);  // LN mode: + the 64 row-statistics threads (warps 2, 3)
       mbar_init(&acc_empty[b], PAIR ? 2 * EPI_THREADS : EPI_THREADS);  // pair: the leader collects both CTAs' epilogues
     }
     mbar_fence_init();
@@ -302,7 +309,71 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         else tc_commit(&acc_full[buf]);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    // ------------------------------------------------------------ LN mode: row statistics of the A tile (warps 2, 3)
+    // Thread st owns tile rows st and st + 64.  Every k-block it sums its rows' 64 fp16 values and their squares straight
+    // from the 128B-swizzled ring slot (a row is one 128-byte line whose 16-byte chunks are permuted — irrelevant for a
+    // sum; lane l starts at chunk l & 7 so that a quarter-warp hits eight different bank groups), then frees the slot.
+    // mean / rstd of the finished tile go to rowstat[buf]; the arrival on acc_full[buf] publishes them to the epilogue.
+    if (ln && !PAIR) {
+      const int st = (warp - 2) * 32 + lane;
+      int it = 0;
+      for (int j = 0; j < n_local; ++j) {
+        const Unit t = decode_unit(p, first + j * ustride, pair_rank);
+        const int buf = j & 1;
+        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+        uint32_t piv0 = 0, piv1 = 0;  // per-row pivot (an element of the row, both halves of a half2): sums run over x - pivot
+        for (int kb = t.kb0; kb < t.kb1; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          const uint32_t r0 = smem_u32(smem + s * stage_bytes) + st * 128;
+          if (kb == t.kb0) {
+            uint32_t w0, w1;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(r0) : "memory");
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(r0 + 64 * 128) : "memory");
+            piv0 = __byte_perm(w0, w0, 0x1010);
+            piv1 = __byte_perm(w1, w1, 0x1010);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t off = static_cast<uint32_t>((c + lane) & 7) << 4;
+            uint32_t wa[4], wb[4];
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wa[0]), "=r"(wa[1]), "=r"(wa[2]), "=r"(wa[3]) : "r"(r0 + off) : "memory");
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wb[0]), "=r"(wb[1]), "=r"(wb[2]), "=r"(wb[3]) : "r"(r0 + 64 * 128 + off) : "memory");
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              // d = x - pivot as half2 (its fp16 rounding only perturbs the statistics by ~2^-11 / sqrt(K)), then the
+              // mixed-precision forms (fp16 operands, fp32 accumulator — FHADD / FHFMA on sm_100): two instructions per element
+              asm("{\n\t.reg .b32 d;\n\t.reg .b16 lo, hi;\n\t"
+                  "sub.rn.f16x2 d, %2, %3;\n\tmov.b32 {lo, hi}, d;\n\t"
+                  "add.f32.f16 %0, lo, %0;\n\tadd.f32.f16 %0, hi, %0;\n\t"
+                  "fma.rn.f32.f16 %1, lo, lo, %1;\n\tfma.rn.f32.f16 %1, hi, hi, %1;\n\t}\n" : "+f"(s0), "+f"(q0) : "r"(wa[e]), "r"(piv0));
+              asm("{\n\t.reg .b32 d;\n\t.reg .b16 lo, hi;\n\t"
+                  "sub.rn.f16x2 d, %2, %3;\n\tmov.b32 {lo, hi}, d;\n\t"
+                  "add.f32.f16 %0, lo, %0;\n\tadd.f32.f16 %0, hi, %0;\n\t"
+                  "fma.rn.f32.f16 %1, lo, lo, %1;\n\tfma.rn.f32.f16 %1, hi, hi, %1;\n\t}\n" : "+f"(s1), "+f"(q1) : "r"(wb[e]), "r"(piv1));
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+        mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);  // the epilogue of unit j - 2 has read rowstat[buf]
+        {
+          // columns beyond K are zero-filled by TMA: each contributed d = -pivot; take them out again
+          const float npad = static_cast<float>((t.kb1 - t.kb0) * BK - p.ln_k);
+          const float pv0 = __half2float(__ushort_as_half(static_cast<unsigned short>(piv0 & 0xffffu)));
+          const float pv1 = __half2float(__ushort_as_half(static_cast<unsigned short>(piv1 & 0xffffu)));
+          const float d0 = (s0 + npad * pv0) * p.ln_inv_k, d1 = (s1 + npad * pv1) * p.ln_inv_k;  // mean - pivot
+          const float v0 = fmaxf((q0 - npad * pv0 * pv0) * p.ln_inv_k - d0 * d0, 0.f);
+          const float v1 = fmaxf((q1 - npad * pv1 * pv1) * p.ln_inv_k - d1 * d1, 0.f);
+          rowstat[buf * 128 + st] = make_float2(pv0 + d0, rsqrtf(v0 + p.ln_eps));
+          rowstat[buf * 128 + st + 64] = make_float2(pv1 + d1, rsqrtf(v1 + p.ln_eps));
+        }
+        mbar_arrive(&acc_full[buf]);
+      }
+    }
+  } else {
     // ------------------------------------------------------------ epilogue: 2 warpgroups x 128 threads
     const int wg = (warp - 4) >> 2;
     const int q = warp & 3;              // TMEM lane quadrant this warp may read
@@ -321,6 +392,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     int n_staged = 0;  // staging buffer toggle
     pdl_wait();        // residual / split-K workspace reads and every output write come after the predecessor grid
 
+    // LN mode: v = rstd[row] * (acc - mean[row] * colsum[col]) — LayerNorm(x) W'^T from the raw-x product (thread = row here)
+    float ln_mu = 0.f, ln_rs = 1.f;
+    auto ln_apply = [&](float* v, int col0) {  // col0: GEMM column (packed weight row) of v[0]
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int col = col0 + 4 * i;
+        float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col < p.N) c4 = ldg4(p.ln_colsum + col, true, 4);  // N % 4 == 0 and 16-byte alignment are checked on the host
+        v[4 * i] = ln_rs * fmaf(-ln_mu, c4.x, v[4 * i]);
+        v[4 * i + 1] = ln_rs * fmaf(-ln_mu, c4.y, v[4 * i + 1]);
+        v[4 * i + 2] = ln_rs * fmaf(-ln_mu, c4.z, v[4 * i + 2]);
+        v[4 * i + 3] = ln_rs * fmaf(-ln_mu, c4.w, v[4 * i + 3]);
+      }
+    };
+
     // ---- phase A of one chunk: TMEM -> registers -> (GEGLU) -> swizzled staging tile, or the direct QKV scatter
     auto phase_a = [&](const Unit& t, uint32_t taddr, int c, uint32_t stg) -> bool {
       float v[32];
@@ -330,6 +416,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tmem_ld32(taddr + c * 32, v);
         tmem_ld32(taddr + p.BN / 2 + c * 32, g);
         tmem_ld_wait();
+        if (ln) {
+          ln_apply(v, t.n_tile * p.BN + c * 32);
+          ln_apply(g, t.n_tile * p.BN + p.BN / 2 + c * 32);
+        }
         if (p.bias != nullptr) {
           const uint32_t sv = smem_u32(sbias + c * 32), sg = smem_u32(sbias + p.BN / 2 + c * 32);
 #pragma unroll
@@ -344,6 +434,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       } else {
         tmem_ld32(taddr + c * 32, v);
         tmem_ld_wait();
+        if (ln) ln_apply(v, oc);
       }
       if (out_mode == MVD_OUT_QKV_HEADS && (p.qkv_direct || oc >= 2 * inner)) {
         // v^T (keys contiguous) wants thread = row: leave straight from the registers
@@ -355,6 +446,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           for (int i = 0; i < 32; i += 8) {
             const int n = oc + i;
             if (n >= p.N) continue;
+            if (p.bias != nullptr) {  // dhead % 8 == 0 and N = 3 * heads * dhead: eight whole columns exist
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[i + e] += __ldg(p.bias + n + e);
+            }
             const int which = n / inner;
             const int rem = n - which * inner;
             const int h = rem / p.dhead;
@@ -469,6 +564,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             if (nvalid > 2) dst[2] = v.z;
             if (nvalid > 3) dst[3] = v.w;
           }
+          if (p.out16 != nullptr) {  // the same values once more as the fp16 operand of the next GEMM
+            __half* d16 = p.out16 + static_cast<size_t>(grow) * p.ld16 + col;
+            if (p.vec_out16 && nvalid >= 4) {
+              *reinterpret_cast<uint2*>(d16) = make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
+            } else {
+              d16[0] = __float2half_rn(v.x);
+              if (nvalid > 1) d16[1] = __float2half_rn(v.y);
+              if (nvalid > 2) d16[2] = __float2half_rn(v.z);
+              if (nvalid > 3) d16[3] = __float2half_rn(v.w);
+            }
+          }
         } else if (out_mode == MVD_OUT_F16) {
           __half* dst = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(grow) * p.ldc + col;
           if (VEC || (p.vec_out && nvalid >= 4)) {
@@ -544,6 +650,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+      if (ln) {  // published by the statistics warps' arrivals on acc_full; read before this thread's acc_empty arrival
+        const float2 rs = rowstat[buf * 128 + et];
+        ln_mu = rs.x;
+        ln_rs = rs.y;
+      }
 
       if (is_split) {
         // ---- park the chunks other slices own: ws[u][row][col] fp32, written with the coalesced phase-B mapping
@@ -698,6 +809,25 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   p.dhead = a->dhead;
   p.dpad = a->dpad;
   p.seq = a->seq;
+  p.out16 = static_cast<__half*>(a->out16);
+  p.ld16 = a->ld16;
+  p.ln_colsum = a->ln_colsum;
+  p.ln_eps = a->ln_eps;
+  p.ln_inv_k = 1.0f / static_cast<float>(a->K);
+  p.ln_k = a->K;
+  const bool ln = a->ln_colsum != nullptr;
+  if (a->out16 != nullptr) {
+    if (a->out_mode != MVD_OUT_F32 || a->act == MVD_ACT_GEGLU) return set_error(MVD_EINVAL, "mvd_gemm_f16: out16 accompanies an F32 output only");
+    if (a->ld16 < a->N) return set_error(MVD_EINVAL, "mvd_gemm_f16: ld16 is smaller than N");
+    p.vec_out16 = (reinterpret_cast<uintptr_t>(a->out16) & 7) == 0 && (a->ld16 & 3) == 0;
+  }
+  if (ln) {
+    if (a->a_mode != MVD_A_ROWMAJOR) return set_error(MVD_EINVAL, "mvd_gemm_f16: ln_colsum needs a row-major A");
+    if ((a->N & 3) != 0 || (reinterpret_cast<uintptr_t>(a->ln_colsum) & 15) != 0)
+      return set_error(MVD_EALIGN, "mvd_gemm_f16: ln_colsum needs N % 4 == 0 and a 16-byte aligned vector");
+    if (a->split_k > 1 || a->cta_pair == 2) return set_error(MVD_EINVAL, "mvd_gemm_f16: ln_colsum excludes split_k and cta_pair");
+    if (!(a->ln_eps > 0.f)) return set_error(MVD_EINVAL, "mvd_gemm_f16: ln_eps must be positive");
+  }
 
   const bool geglu = a->act == MVD_ACT_GEGLU;
   const int sms = num_sms();
@@ -723,7 +853,8 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   if (a->cta_pair < 0 || a->cta_pair > 2) return set_error(MVD_EINVAL, "mvd_gemm_f16: cta_pair must be 0, 1 or 2");
   if (a->cta_pair == 2 && (tiles_m_real < 2 || (sms & 1) != 0)) return set_error(MVD_EINVAL, "mvd_gemm_f16: cta_pair = 2 needs at least two m-tiles");
   const bool pair_auto = (deep || force_pair) && tiles_m_real >= 2 && ((tiles_m_real & 1) == 0 || tiles_m_real >= 9) && (sms & 1) == 0;
-  const bool pair = !no_pair && (a->cta_pair == 2 || (a->cta_pair == 0 && pair_auto));
+  // (LN mode: the row statistics are taken from each CTA's own A tile behind its own full barrier — single CTAs only)
+  const bool pair = !no_pair && !ln && (a->cta_pair == 2 || (a->cta_pair == 0 && pair_auto));
   const int tiles_mp = pair ? (tiles_m_real + 1) / 2 : tiles_m_real;
   const int slots = pair ? sms / 2 : sms;
   int bn = a->tile_n;
@@ -786,7 +917,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   int split = a->split_k;
   const size_t ws_avail = (a->splitk_ws != nullptr && a->splitk_ws_bytes > WS_COUNTER_BYTES) ? static_cast<size_t>(a->splitk_ws_bytes) - WS_COUNTER_BYTES : 0;
   const size_t tile_ws = static_cast<size_t>((bn + 31) / 32 * 32) * BM * sizeof(float);
-  const bool can_split = !geglu && a->out_mode != MVD_OUT_QKV_HEADS;
+  const bool can_split = !geglu && a->out_mode != MVD_OUT_QKV_HEADS && !ln;
   if (split <= 0) {  // auto: only when the tiles cannot fill half the machine and K is deep
     split = 1;
     if (can_split && tiles * 2 <= slots && p.num_kb >= 8) {
@@ -835,7 +966,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
 
   // ---- shared memory / TMEM budget
   const int stage_bytes = A_BYTES + (pair ? bn / 2 : bn) * 128;
-  const int fixed = 4 * STG_BYTES + 2048 + 512;
+  const int fixed = 4 * STG_BYTES + 2048 + 512 + (ln ? 2048 : 0);  // staging, GEGLU bias, barriers, LN row statistics
   int stages = (232448 - 1024 - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return set_error(MVD_EINVAL, "mvd_gemm_f16: tile does not fit in shared memory");

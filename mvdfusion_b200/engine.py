@@ -119,6 +119,34 @@ class PackedWeights:
         return self._put("kv", p, lambda: self._pad_k(torch.cat([self.raw(p + ".to_k.weight"),
                                                                  self.raw(p + ".to_v.weight")], 0).float()).half())
 
+    # LayerNorm folded into the consuming GEMM (include/mvd_b200.h, mvd_gemm_args.ln_colsum):
+    #   LN(x) W^T + b = rstd (x W'^T - mean colsum(W')) + (b + W beta),   W' = W diag(gamma)
+    def _ln_fold(self, tag, key, w_fn, b_fn, norm):
+        """-> (W' fp16 [N, K8], colsum fp32 [N] of the ROUNDED W', bias' fp32 [N])"""
+        def f_w():
+            return self._pad_k(w_fn().float() * self.raw(norm + ".weight").float()[None, :]).half()
+        wp = self._put(tag + "_w", (key, norm), f_w)
+        cs = self._put(tag + "_cs", (key, norm), lambda: wp.float().sum(dim=1))
+        def f_b():
+            wb = w_fn().float() @ self.raw(norm + ".bias").float()
+            b = b_fn()
+            return wb if b is None else wb + b.float()
+        bp = self._put(tag + "_b", (key, norm), f_b)
+        return wp, cs, bp
+
+    def qkv_ln(self, p, norm):
+        """fused to_q | to_k | to_v behind nn.LayerNorm `norm` (attention.py:211,220; mvd attention.py:35,52)"""
+        w = lambda: torch.cat([self.raw(p + ".to_q.weight"), self.raw(p + ".to_k.weight"), self.raw(p + ".to_v.weight")], 0)
+        return self._ln_fold("qkvln", p, w, lambda: None, norm)
+
+    def geglu_ln(self, p, norm, tile_n=128):
+        """GEGLU.proj behind nn.LayerNorm `norm`, rows interleaved per output tile as in geglu()"""
+        inner = self.raw(p + ".weight").shape[0] // 2
+        perm = self._put("geglu_perm", (inner, tile_n), lambda: self.ops.geglu_permutation(inner, tile_n))
+        w = lambda: self.raw(p + ".weight")[perm.cpu()]
+        b = lambda: self.raw(p + ".bias")[perm.cpu()]
+        return self._ln_fold("gegluln", (p, tile_n), w, b, norm)
+
     def geglu(self, p, tile_n=128):
         """GEGLU.proj [2*inner, C] with value/gate rows interleaved per output tile (include/mvd_b200.h, MVD_ACT_GEGLU)"""
         w = self.raw(p + ".weight")
@@ -201,6 +229,10 @@ class Builder:
         self._stats = None
         self._ws = None
         self.heads = 8
+        # nn.LayerNorm in front of to_q/k/v and GEGLU.proj folded into those GEMMs (MVD_NO_LN_FOLD=1: separate LayerNorm passes)
+        self.ln_fold = not os.environ.get("MVD_NO_LN_FOLD")
+        # fp16 operands of the 1x1 skip convolutions written by their producers' epilogues (MVD_NO_FUSE_CAT=1: cast / concat passes)
+        self.fuse_cat = not os.environ.get("MVD_NO_FUSE_CAT")
 
     # -- buffers
     def t16(self, *shape):
@@ -238,7 +270,8 @@ class Builder:
         # split_k = 0 lets the library cut K when the tile grid cannot fill the machine (small-M, weight-bound layers);
         # a measured (tile_n, split_k, cta_pair) choice from gemm_tuning.json overrides the library's heuristics.
         act = kw.get("act", ACT_NONE)
-        can_split = allow_split and act != ACT_GEGLU and kw.get("qkv") is None
+        has_ln = kw.get("ln") is not None
+        can_split = allow_split and act != ACT_GEGLU and kw.get("qkv") is None and not has_ln
         sig = gemm_signature(kw.get("conv") is not None, M, N, K,
                              "qkv" if kw.get("qkv") is not None else str(out.dtype).split(".")[-1], kw.get("residual") is not None, act)
         tuned = gemm_tuning().get(sig)
@@ -248,6 +281,8 @@ class Builder:
                 tn = GEGLU_TILE
             if sk > 1 and not can_split:
                 sk = 1
+            if has_ln:
+                pr = 1
             self.prog.append(self.ops.gemm(A, Wt, out, M, N, K, split_k=sk, tile_n=tn, cta_pair=pr,
                                            ws=self.splitk_ws() if sk != 1 else None, **kw))
         elif can_split:
@@ -267,7 +302,7 @@ class Builder:
         return y
 
     def conv3x3(self, a16, wkey, n_img, H, W_, Cin, Cout, *, bias, residual=None, c_pad=None, ldc=None, out=None,
-                rowbias=None, rows_per_group=1):
+                rowbias=None, rows_per_group=1, out16=None):
         """conv_nd(2, Cin, Cout, 3, padding=1) as implicit GEMM (openaimodel.py:107,204,230; unet.py:323,499)"""
         M = n_img * H * W_
         cp = c_pad if c_pad is not None else Cin
@@ -276,8 +311,13 @@ class Builder:
         w = self.W.conv3(wkey, c_pad)
         self.gemm(a16, w, out, M, Cout, 9 * cp, allow_split=True, conv=(n_img, H, W_, cp), bias=bias, residual=residual,
                   rowbias=rowbias, rows_per_group=rows_per_group,
-                  ldr=(residual.shape[-1] if residual is not None else 0), ldc=(ldc if ldc is not None else Cout))
+                  ldr=(residual.shape[-1] if residual is not None else 0), ldc=(ldc if ldc is not None else Cout), **self._o16(out16))
         return out
+
+    @staticmethod
+    def _o16(out16):
+        """out16 = (fp16 tensor or column window, row pitch) -> gemm keywords: the GEMM's epilogue also writes its result there"""
+        return {} if out16 is None else {"out16": out16[0], "ld16": out16[1]}
 
     def cast16(self, x, rows, C):
         y = self.t16(rows, C)
@@ -298,11 +338,13 @@ class Builder:
         self.prog.append(self.ops.gemv_grouped(emb, emb_dim, jobs, silu_in=True))
 
     # -- ResBlock
-    def resblock(self, x, p, n_img, H, Cin, Cout, emb, emb_dim, cat=None):
+    def resblock(self, x, p, n_img, H, Cin, Cout, emb, emb_dim, cat=None, x16=None, out16=None):
         """ResBlock._forward (openaimodel.py:255-275): GN-SiLU-conv, + Linear(SiLU(emb)), GN-SiLU-conv, + skip.
         The timestep term is per-channel only (one shared t), so it rides in the first conv's bias.
         cat = (h, skip): the block input is torch.cat([h, skip], dim=1) (mvdfusion/unet.py:550); it is consumed by a
-        two-source GroupNorm and written once as the fp16 operand of the 1x1 skip convolution, never in fp32."""
+        two-source GroupNorm and written once as the fp16 operand of the 1x1 skip convolution, never in fp32.
+        x16 = (fp16 tensor / column window, row pitch): the block input as fp16, already written by its producers' epilogues
+        (out16) — the skip convolution reads it instead of a cast / concat pass.  out16: where to leave this block's output."""
         hw, M = H * H, n_img * H * H
         if cat is not None:
             assert x is None and self.W.has(p + ".skip_connection.weight")
@@ -330,88 +372,110 @@ class Builder:
         self.free(h, eb)
         res, s = x, None
         if self.W.has(p + ".skip_connection.weight"):
-            if cat is not None:
-                x16 = self.t16(M, Cin)
-                self.prog.append(self.ops.concat16(cat[0], cat[1], x16, M, cat[0].shape[-1], cat[1].shape[-1]))
-            else:
-                x16 = self.cast16(x, M, Cin)
             s = self.t32(M, Cout)
-            self.gemm(x16, self.W.lin(p + ".skip_connection.weight"), s, M, Cout, Cin, allow_split=True,
-                      bias=self.W.f32(p + ".skip_connection.bias"))
-            self.free(x16)
+            if x16 is not None:
+                self.gemm(x16[0], self.W.lin(p + ".skip_connection.weight"), s, M, Cout, Cin, allow_split=True,
+                          bias=self.W.f32(p + ".skip_connection.bias"), lda=x16[1])
+            else:
+                if cat is not None:
+                    xc = self.t16(M, Cin)
+                    self.prog.append(self.ops.concat16(cat[0], cat[1], xc, M, cat[0].shape[-1], cat[1].shape[-1]))
+                else:
+                    xc = self.cast16(x, M, Cin)
+                self.gemm(xc, self.W.lin(p + ".skip_connection.weight"), s, M, Cout, Cin, allow_split=True,
+                          bias=self.W.f32(p + ".skip_connection.bias"))
+                self.free(xc)
             res = s
         out = self.conv3x3(b, p + ".out_layers.3.weight", n_img, H, H, Cout, Cout, bias=self.W.f32(p + ".out_layers.3.bias"),
-                           residual=res)
+                           residual=res, out16=out16)
         self.free(b, s)
         return out
 
-    def downsample(self, x, p, n_img, H, C):
+    def downsample(self, x, p, n_img, H, C, out16=None):
         """Downsample.op: conv3x3 stride 2 (openaimodel.py:151) = fp16 im2col + GEMM"""
         Mo = n_img * (H // 2) * (H // 2)
         col = self.t16(Mo, 9 * C)
         self.prog.append(self.ops.im2col_s2(x, col, n_img, H, H, C))
         out = self.t32(Mo, C)
-        self.gemm(col, self.W.conv3(p + ".op.weight"), out, Mo, C, 9 * C, allow_split=True, bias=self.W.f32(p + ".op.bias"))
+        self.gemm(col, self.W.conv3(p + ".op.weight"), out, Mo, C, 9 * C, allow_split=True, bias=self.W.f32(p + ".op.bias"),
+                  **self._o16(out16))
         self.free(col)
         return out
 
-    def upsample(self, x, p, n_img, H, C):
+    def upsample(self, x, p, n_img, H, C, out16=None):
         """Upsample: nearest x2 then conv3x3 (openaimodel.py:107-119)"""
         u = self.t16(n_img * 4 * H * H, C)
         self.prog.append(self.ops.upsample2x(x, u, n_img, H, H, C))
-        out = self.conv3x3(u, p + ".conv.weight", n_img, 2 * H, 2 * H, C, C, bias=self.W.f32(p + ".conv.bias"))
+        out = self.conv3x3(u, p + ".conv.weight", n_img, 2 * H, 2 * H, C, C, bias=self.W.f32(p + ".conv.bias"), out16=out16)
         self.free(u)
         return out
 
     # -- attention blocks
-    def self_attention(self, h, p, norm, n_img, seq, C, rowbias=None):
-        """x = attn1(norm1(x)) + x  [+ per-image vector]: LayerNorm -> fused QKV GEMM (heads scattered) ->
-        flash attention -> to_out GEMM with bias + residual.  attention.py:170-193,220; mvd attention.py:52"""
+    def self_attention(self, h, p, norm, n_img, seq, C, rowbias=None, h16=None, want16=False):
+        """x = attn1(norm1(x)) + x  [+ per-image vector]: fused QKV GEMM (heads scattered) -> flash attention -> to_out GEMM
+        with bias + residual.  attention.py:170-193,220; mvd attention.py:52
+        h16: fp16 copy of h written by h's producer — norm1 is then folded into the QKV GEMM (no LayerNorm pass);
+        want16: also return an fp16 copy of the result (for the next folded LayerNorm)."""
         M = n_img * seq
         d = C // self.heads
         dpad = _round_up(d, 64)
-        ln = self.layernorm(h, norm, M, C)
         q, k, vt = self.qkv_buffers(n_img, seq, dpad)
-        self.gemm(ln, self.W.qkv(p), q, M, 3 * C, C,
-                  qkv=dict(out_k=k, out_vt=vt, heads=self.heads, dhead=d, dpad=dpad, seq=seq))
-        ao = ln  # reuse: same shape / dtype, the QKV GEMM was its last reader
+        qkv = dict(out_k=k, out_vt=vt, heads=self.heads, dhead=d, dpad=dpad, seq=seq)
+        if h16 is not None:
+            w, cs, bq = self.W.qkv_ln(p, norm)
+            self.gemm(h16, w, q, M, 3 * C, C, qkv=qkv, bias=bq, ln=(cs, 1e-5))
+            ao = h16  # reuse: same shape / dtype, the QKV GEMM was its last reader
+        else:
+            ao = self.layernorm(h, norm, M, C)
+            self.gemm(ao, self.W.qkv(p), q, M, 3 * C, C, qkv=qkv)
         self.prog.append(self.ops.attn_self(q, k, vt, ao, n_img, self.heads, seq, d, dpad, C))
         h2 = self.t32(M, C)
+        h2_16 = self.t16(M, C) if want16 else None
         self.gemm(ao, self.W.lin(p + ".to_out.0.weight"), h2, M, C, C, allow_split=True, bias=self.W.f32(p + ".to_out.0.bias"),
-                  rowbias=rowbias, rows_per_group=seq, residual=h, ldr=C)
+                  rowbias=rowbias, rows_per_group=seq, residual=h, ldr=C, out16=h2_16)
         self.free(ao, h)
-        return h2
+        return (h2, h2_16) if want16 else h2
 
-    def feed_forward(self, h, p, norm, M, C, out16=False):
+    def feed_forward(self, h, p, norm, M, C, out16=False, h16=None):
         """x = ff(norm3(x)) + x with the GEGLU fused into the first GEMM's epilogue.  attention.py:37-64,222
-        out16: the block output only feeds proj_out, so it is written once, as that GEMM's fp16 operand."""
-        ln = self.layernorm(h, norm, M, C)
+        out16: the block output only feeds proj_out, so it is written once, as that GEMM's fp16 operand.
+        h16: fp16 copy of h from its producer — norm3 is then folded into the GEGLU GEMM."""
         inner = 4 * C
-        wg, bg = self.W.geglu(p + ".net.0.proj", GEGLU_TILE)
         g = self.t16(M, inner)
-        self.gemm(ln, wg, g, M, 2 * inner, C, bias=bg, act=ACT_GEGLU, tile_n=GEGLU_TILE, ldc=inner)
-        self.free(ln)
+        if h16 is not None:
+            wg, cs, bg = self.W.geglu_ln(p + ".net.0.proj", norm, GEGLU_TILE)
+            self.gemm(h16, wg, g, M, 2 * inner, C, bias=bg, act=ACT_GEGLU, tile_n=GEGLU_TILE, ldc=inner, ln=(cs, 1e-5))
+            self.free(h16)
+        else:
+            ln = self.layernorm(h, norm, M, C)
+            wg, bg = self.W.geglu(p + ".net.0.proj", GEGLU_TILE)
+            self.gemm(ln, wg, g, M, 2 * inner, C, bias=bg, act=ACT_GEGLU, tile_n=GEGLU_TILE, ldc=inner)
+            self.free(ln)
         h2 = self.t16(M, C) if out16 else self.t32(M, C)
         self.gemm(g, self.W.lin(p + ".net.2.weight"), h2, M, C, inner, allow_split=True, bias=self.W.f32(p + ".net.2.bias"),
                   residual=h, ldr=C)
         self.free(g, h)
         return h2
 
-    def spatial_transformer(self, x, p, n_img, H, C, clipvec):
+    def spatial_transformer(self, x, p, n_img, H, C, clipvec, out16=None):
         """SpatialTransformer.forward (attention.py:268-287) with BasicTransformerBlock (:219-223).
         attn2 sees ONE CLIP token per view, so softmax == 1 and its output is the per-view vector
         to_out(to_v(ctx)) (`clipvec`, [n_img, C]); it is added in the attn1 output GEMM's epilogue."""
         hw, M = H * H, n_img * H * H
         a = self.groupnorm(x, p + ".norm", n_img, hw, C, 1e-6, False)
         h = self.t32(M, C)
-        self.gemm(a, self.W.lin(p + ".proj_in.weight"), h, M, C, C, allow_split=True, bias=self.W.f32(p + ".proj_in.bias"))
+        hx = self.t16(M, C) if self.ln_fold else None  # fp16 copy for the folded norm1 (written by proj_in's epilogue)
+        self.gemm(a, self.W.lin(p + ".proj_in.weight"), h, M, C, C, allow_split=True, bias=self.W.f32(p + ".proj_in.bias"), out16=hx)
         self.free(a)
         tb = p + ".transformer_blocks.0"
-        h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C, rowbias=clipvec)
-        h16 = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C, out16=True)
+        if self.ln_fold:
+            h, hx = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C, rowbias=clipvec, h16=hx, want16=True)
+        else:
+            h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C, rowbias=clipvec)
+        h16 = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C, out16=True, h16=hx)
         out = self.t32(M, C)
         self.gemm(h16, self.W.lin(p + ".proj_out.weight"), out, M, C, C, allow_split=True, bias=self.W.f32(p + ".proj_out.bias"),
-                  residual=x, ldr=C)
+                  residual=x, ldr=C, **self._o16(out16))
         self.free(h16)
         return out
 
@@ -427,8 +491,9 @@ class Builder:
         self.free(v)
         return out
 
-    def view_cross_attention(self, h, p, norm, ctx16, M, D, C):
-        """DualAttnetionBlock.attn2 (mvd attention.py:56-62): every pixel is one query against its D frustum keys."""
+    def view_cross_attention(self, h, p, norm, ctx16, M, D, C, want16=False):
+        """DualAttnetionBlock.attn2 (mvd attention.py:56-62): every pixel is one query against its D frustum keys.
+        want16: also return an fp16 copy of the result (for the folded norm3 of the feed-forward)."""
         d = C // self.heads
         if D == 1:  # softmax over a single key == 1: out = to_out(to_v(ctx))
             v = self.t16(M, C)
@@ -445,26 +510,32 @@ class Builder:
             self.prog.append(self.ops.pixel_cross_attn(q, kv, o, M, D, self.heads, d))
             self.free(q, kv)
         h2 = self.t32(M, C)
+        h2_16 = self.t16(M, C) if want16 else None
         self.gemm(o, self.W.lin(p + ".to_out.0.weight"), h2, M, C, C, allow_split=True, bias=self.W.f32(p + ".to_out.0.bias"),
-                  residual=h, ldr=C)
+                  residual=h, ldr=C, out16=h2_16)
         self.free(o, h)
-        return h2
+        return (h2, h2_16) if want16 else h2
 
-    def view_aligned_transformer(self, x, p, n_img, H, C, ctx16, D):
+    def view_aligned_transformer(self, x, p, n_img, H, C, ctx16, D, out16=None):
         """ViewAlignedFeatureTransformer.forward (mvd attention.py:119-145) + DualAttnetionBlock (:43-66)."""
         hw, M = H * H, n_img * H * H
         a = self.groupnorm(x, p + ".aligned_attn_norm", n_img, hw, C, 1e-6, False)
         h = self.t32(M, C)
+        hx = self.t16(M, C) if self.ln_fold else None
         self.gemm(a, self.W.lin(p + ".aligned_attn_proj_in.weight"), h, M, C, C, allow_split=True,
-                  bias=self.W.f32(p + ".aligned_attn_proj_in.bias"))
+                  bias=self.W.f32(p + ".aligned_attn_proj_in.bias"), out16=hx)
         self.free(a)
         tb = p + ".aligned_attn_transformer_blocks.0"
-        h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C)
-        h = self.view_cross_attention(h, tb + ".attn2", tb + ".norm2", ctx16, M, D, C)
-        h16 = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C, out16=True)
+        h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C, h16=hx)
+        hx = None
+        if self.ln_fold:
+            h, hx = self.view_cross_attention(h, tb + ".attn2", tb + ".norm2", ctx16, M, D, C, want16=True)
+        else:
+            h = self.view_cross_attention(h, tb + ".attn2", tb + ".norm2", ctx16, M, D, C)
+        h16 = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C, out16=True, h16=hx)
         out = self.t32(M, C)
         self.gemm(h16, self.W.lin(p + ".aligned_attn_proj_out.weight"), out, M, C, C, allow_split=True,
-                  bias=self.W.f32(p + ".aligned_attn_proj_out.bias"), residual=x, ldr=C)
+                  bias=self.W.f32(p + ".aligned_attn_proj_out.bias"), residual=x, ldr=C, **self._o16(out16))
         self.free(h16)
         return out
 
@@ -559,26 +630,61 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
     H = S
     hs = []
 
-    def run_layers(h, prefix, layers, H, start=0):
+    # The 1x1 skip convolution of output block i reads torch.cat([h, hs.pop()], dim=1) (unet.py:550) as an fp16 operand.
+    # Both halves are written straight into that buffer by the epilogues of the GEMMs that produce h and the skip
+    # (out16 windows), so no cast / concat pass runs; the channel-changing input ResBlocks read their input from the same
+    # windows (row pitch c1 + c2).
+    ch, hh, outs = spec.mc, S, []
+    for layers in spec.input_blocks:
+        for l in layers:
+            if l[0] in ("stem", "res"):
+                ch = l[2]
+            elif l[0] == "down":
+                hh //= 2
+        outs.append((ch, hh))
+    cat16 = []
+    for i, layers in enumerate(spec.output_blocks):
+        sch, sh = outs[len(outs) - 1 - i]
+        assert sh == hh
+        fused = b.fuse_cat and layers[0][0] == "res" and b.W.has(f"output_blocks.{i}.0.skip_connection.weight")
+        cat16.append((b.t16(n_img * hh * hh, ch + sch), ch, sch) if fused else None)
+        for l in layers:
+            if l[0] == "res":
+                ch = l[2]
+            elif l[0] == "up":
+                hh *= 2
+
+    def skip_window(k):
+        """fp16 home of input block k's output: the skip half of its output block's concatenation buffer"""
+        c = cat16[len(spec.input_blocks) - 1 - k]
+        return None if c is None else (c[0][:, c[1]:], c[1] + c[2])
+
+    def head_window(i):
+        """fp16 home of the tensor entering output block i (h half of its concatenation buffer)"""
+        c = cat16[i] if i < len(cat16) else None
+        return None if c is None else (c[0][:, :c[1]], c[1] + c[2])
+
+    def run_layers(h, prefix, layers, H, start=0, h16=None, last16=None):
         for j, l in enumerate(layers):
             if j < start:
                 continue
             p = f"{prefix}.{j}"
             kind = l[0]
+            o16 = last16 if j == len(layers) - 1 else None
             if kind == "stem":
-                new = b.conv3x3(h, p + ".weight", n_img, H, H, l[1], l[2], bias=b.W.f32(p + ".bias"), c_pad=c_in_pad)
+                new = b.conv3x3(h, p + ".weight", n_img, H, H, l[1], l[2], bias=b.W.f32(p + ".bias"), c_pad=c_in_pad, out16=o16)
             elif kind == "res":
-                new = b.resblock(h, p, n_img, H, l[1], l[2], emb, spec.emb_dim)
+                new = b.resblock(h, p, n_img, H, l[1], l[2], emb, spec.emb_dim, x16=h16 if j == 0 else None, out16=o16)
             elif kind == "st":
-                new = b.spatial_transformer(h, p, n_img, H, l[1], clipvecs[p])
+                new = b.spatial_transformer(h, p, n_img, H, l[1], clipvecs[p], out16=o16)
             elif kind == "vaft":
                 level = {spec.image_size: 0, spec.image_size // 2: 1, spec.image_size // 4: 2, spec.image_size // 8: 3}[H]
-                new = b.view_aligned_transformer(h, p, n_img, H, l[1], pyramid16[level], D)
+                new = b.view_aligned_transformer(h, p, n_img, H, l[1], pyramid16[level], D, out16=o16)
             elif kind == "down":
-                new = b.downsample(h, p, n_img, H, l[1])
+                new = b.downsample(h, p, n_img, H, l[1], out16=o16)
                 H //= 2
             elif kind == "up":
-                new = b.upsample(h, p, n_img, H, l[1])
+                new = b.upsample(h, p, n_img, H, l[1], out16=o16)
                 H *= 2
             else:
                 raise ValueError(kind)
@@ -589,23 +695,31 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
 
     h = x_in16
     for i, layers in enumerate(spec.input_blocks):
-        h, H = run_layers(h, f"input_blocks.{i}", layers, H)
+        # a channel-changing ResBlock needs its input as fp16 (1x1 skip convolution): the previous block left it in its window
+        prev16 = skip_window(i - 1) if i > 0 and layers[0][0] == "res" and layers[0][1] != layers[0][2] else None
+        h, H = run_layers(h, f"input_blocks.{i}", layers, H, h16=prev16, last16=skip_window(i))
         hs.append((h, layers))
-    h, H = run_layers(h, "middle_block", spec.middle, H)
+    h, H = run_layers(h, "middle_block", spec.middle, H, last16=head_window(0))
     for i, layers in enumerate(spec.output_blocks):
         skip, _ = hs.pop()
         c1, c2 = h.shape[-1], skip.shape[-1]
         rows = n_img * H * H
         p0 = f"output_blocks.{i}.0"
         if layers[0][0] == "res" and b.W.has(p0 + ".skip_connection.weight"):
-            new = b.resblock(None, p0, n_img, H, c1 + c2, layers[0][2], emb, spec.emb_dim, cat=(h, skip))
+            c16 = cat16[i]
+            assert c16 is None or (c16[1], c16[2]) == (c1, c2)
+            nxt = head_window(i + 1)
+            new = b.resblock(None, p0, n_img, H, c1 + c2, layers[0][2], emb, spec.emb_dim, cat=(h, skip),
+                             x16=None if c16 is None else (c16[0], c1 + c2), out16=nxt if len(layers) == 1 else None)
             b.free(h, skip)
-            h, H = run_layers(new, f"output_blocks.{i}", layers, H, start=1)
+            if c16 is not None:
+                b.free(c16[0])
+            h, H = run_layers(new, f"output_blocks.{i}", layers, H, start=1, last16=nxt)
         else:
             cat = b.t32(rows, c1 + c2)
             b.prog.append(b.ops.concat(h, skip, cat, rows, c1, c2))
             b.free(h, skip)
-            h, H = run_layers(cat, f"output_blocks.{i}", layers, H)
+            h, H = run_layers(cat, f"output_blocks.{i}", layers, H, last16=head_window(i + 1))
     a = b.groupnorm(h, "out.0", n_img, H * H, spec.final_ch, 1e-5, True)
     b.free(h)
     head = b.ops.empty((n_img * H * H, 8), torch.float32)

@@ -44,8 +44,11 @@ class TorchOpsDouble:
 
     # ------------------------------------------------------------------ GEMM / conv
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
-             colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None, cta_pair=0):
+             colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None, cta_pair=0,
+             out16=None, ld16=None, ln=None):
         assert A.dtype == torch.float16 and Wt.dtype == torch.float16
+        assert ln is None or (conv is None and split_k in (0, 1) and cta_pair != 2)
+        assert out16 is None or (out.dtype == torch.float32 and qkv is None and act != ACT_GEGLU)
         ldw_ = ldw if ldw is not None else Wt.shape[-1]
 
         def fn():
@@ -59,8 +62,12 @@ class TorchOpsDouble:
                 a = torch.cat(cols, dim=-1).reshape(M, K)
             else:
                 lda_ = lda if lda is not None else A.shape[-1]
-                a = A.reshape(-1)[: M * lda_].reshape(M, lda_)[:, :K].float()
+                a = torch.as_strided(A, (M, K), (lda_, 1), A.storage_offset()).float()  # A may be a column window of a wider buffer
             acc = a @ W.t()
+            if ln is not None:  # LayerNorm folded into the GEMM: statistics of the raw fp16 rows, E[x^2] - mean^2 form
+                mu = a.mean(dim=1, keepdim=True)
+                var = ((a * a).mean(dim=1, keepdim=True) - mu * mu).clamp_min(0.0)
+                acc = torch.rsqrt(var + ln[1]) * (acc - mu * ln[0].reshape(-1)[:N].float())
             if bias is not None:
                 acc = acc + bias.reshape(-1)[:N]
             if rowbias is not None:
@@ -94,6 +101,11 @@ class TorchOpsDouble:
             ldc_ = ldc if ldc is not None else out.shape[-1]
             o = out.reshape(-1)[: M * ldc_].reshape(M, ldc_)
             o[:, : acc.shape[1]] = acc.to(out.dtype)
+            if out16 is not None:
+                ld16_ = ld16 if ld16 is not None else out16.shape[-1]
+                # out16 may be a column window of a wider buffer: address it from its first element with the row pitch
+                o16 = torch.as_strided(out16, (M, N), (ld16_, 1), out16.storage_offset()) if out16.dim() else out16
+                o16.copy_(acc.half())
         return self._call(fn)
 
     def attn_self(self, q, k, vt, out, n_img, heads, seq, dhead, dpad, ldo):
