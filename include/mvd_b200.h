@@ -95,15 +95,6 @@ typedef struct mvd_gemm_args {
   void* out16;         /* optional (out_mode F32 only): the stored values once more as fp16 [M, ld16] — the operand of the
                           GEMM that consumes this output, written here instead of by a separate cast / concat pass */
   int32_t ld16;
-  const float* ln_colsum; /* optional, ROWMAJOR only: LayerNorm folded into the GEMM.  A holds the RAW rows x (fp16), Wt the
-                          gamma-scaled weights W' = W diag(gamma); ln_colsum[n] = sum_k W'[n, k] (of the fp16-rounded W'),
-                          bias must already contain W beta.  The kernel takes mean / variance of every A row (over the K
-                          columns, from the tiles it stages anyway) and forms
-                              acc' = rstd[m] * (acc - mean[m] * ln_colsum[n])  ==  (LayerNorm_noaffine(x) W'^T)[m, n]
-                          before bias / act / ....  Replaces nn.LayerNorm in front of to_q/to_k/to_v and GEGLU.proj
-                          (external/sd1/ldm/modules/attention.py:211-213,220-222; mvdfusion/attention.py:35-37,52,64).
-                          Excludes split_k > 1 and CTA pairs. */
-  float ln_eps;
 } mvd_gemm_args;
 
 int mvd_gemm_f16(const mvd_gemm_args* args, void* stream);

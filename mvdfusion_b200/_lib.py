@@ -28,7 +28,7 @@ class GemmArgs(ctypes.Structure):
         ("heads", c_int32), ("dhead", c_int32), ("dpad", c_int32), ("seq", c_int32),
         ("split_k", c_int32), ("tile_n", c_int32), ("cta_pair", c_int32),
         ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_longlong),
-        ("out16", c_void_p), ("ld16", c_int32), ("ln_colsum", c_void_p), ("ln_eps", c_float),
+        ("out16", c_void_p), ("ld16", c_int32),
     ]
 
 

@@ -31,12 +31,10 @@ namespace mvd {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 384;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int STG_BYTES = 128 * 128;  // one staging chunk: 128 rows x 32 fp32, 128B-swizzled
 constexpr int MAX_STAGES = 8;
 constexpr int WG_THREADS = 128;
-constexpr int EPI_THREADS = 256;
 constexpr int WS_COUNTER_BYTES = 16384;  // 2048 x {arrive, done} tile semaphores at the head of the split-K workspace
 
 struct GemmKParams {
@@ -68,9 +66,6 @@ struct GemmKParams {
   int acc_stride, tmem_cols;
   __half* out16;            // optional fp16 copy of an F32 output (the next GEMM's operand), [M, ld16]
   int ld16, vec_out16;
-  const float* ln_colsum;   // LayerNorm folded into this GEMM (see mvd_b200.h): column sums of the gamma-scaled weights
-  float ln_eps, ln_inv_k;
-  int ln_k;                 // K of the problem (columns of a row that exist)
 };
 
 __device__ __forceinline__ void store8_f16(__half* dst, const float* v) {
@@ -163,8 +158,12 @@ __device__ __forceinline__ Unit decode_unit(const GemmKParams& p, int u, int pai
 // at compile time (-1 = decided at run time); VEC = every epilogue access is a full, aligned 16-byte (8-byte fp16)
 // vector, so no tails exist.  The specialised bodies are several times smaller than the generic one, which matters:
 // a warp walks its epilogue code once per chunk, and the generic body does not fit the instruction cache.
-template <int ACT, int OUT, int RES, int SPLIT, bool VEC, bool PAIR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// NWG = epilogue warpgroups: 2 (384 threads, two staging tiles each) or 3 (512 threads -> 128 registers per thread, one
+// staging tile each).  Short-K GEMMs are bound by the epilogue's latency chains (TMEM -> staging -> global with only two
+// warps per scheduler); a third warpgroup is a third chunk in flight.  Used by the specialisations whose epilogue fits
+// 128 registers.
+template <int ACT, int OUT, int RES, int SPLIT, bool VEC, bool PAIR, int NWG>
+__global__ void __launch_bounds__(128 + 128 * NWG, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
   const int act = ACT >= 0 ? ACT : p.act;
   const int out_mode = OUT >= 0 ? OUT : p.out_mode;
@@ -174,16 +173,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_rows = PAIR ? p.BN / 2 : p.BN;  // W rows this CTA stages per k-block (a pair splits the tile's columns)
   const int stage_bytes = A_BYTES + b_rows * 128;
-  uint8_t* out_stg = smem + p.stages * stage_bytes;                    // 2 warpgroups x 2 x STG_BYTES
-  float* bias_smem = reinterpret_cast<float*>(out_stg + 4 * STG_BYTES);  // 2 x 256 floats (GEGLU tile bias)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_smem + 512);
+  constexpr int EPI_THREADS = NWG * WG_THREADS;
+  constexpr int STG_PER_WG = NWG == 2 ? 2 : 1;
+  uint8_t* out_stg = smem + p.stages * stage_bytes;                                      // NWG x STG_PER_WG x STG_BYTES
+  float* bias_smem = reinterpret_cast<float*>(out_stg + NWG * STG_PER_WG * STG_BYTES);   // NWG x 256 floats (GEGLU tile bias)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_smem + NWG * 256);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + MAX_STAGES;
   uint64_t* acc_full = bars + 2 * MAX_STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float2* rowstat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 512);  // [2][128] {mean, rstd}; LN mode only
-  const bool ln = p.ln_colsum != nullptr;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -196,10 +195,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], ln ? 3 : 1);  // LN mode: the two statistics warps also read the A tile
+      mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&acc_full[b], ln ? 1 + 64 : 1);  // LN mode: + the 64 row-statistics threads (warps 2, 3)
+      mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], PAIR ? 2 * EPI_THREADS : EPI_THREADS);  // pair: the leader collects both CTAs' epilogues
     }
     mbar_fence_init();
@@ -309,71 +308,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         else tc_commit(&acc_full[buf]);
       }
     }
-  } else if (warp < 4) {
-    // ------------------------------------------------------------ LN mode: row statistics of the A tile (warps 2, 3)
-    // Thread st owns tile rows st and st + 64.  Every k-block it sums its rows' 64 fp16 values and their squares straight
-    // from the 128B-swizzled ring slot (a row is one 128-byte line whose 16-byte chunks are permuted — irrelevant for a
-    // sum; lane l starts at chunk l & 7 so that a quarter-warp hits eight different bank groups), then frees the slot.
-    // mean / rstd of the finished tile go to rowstat[buf]; the arrival on acc_full[buf] publishes them to the epilogue.
-    if (ln && !PAIR) {
-      const int st = (warp - 2) * 32 + lane;
-      int it = 0;
-      for (int j = 0; j < n_local; ++j) {
-        const Unit t = decode_unit(p, first + j * ustride, pair_rank);
-        const int buf = j & 1;
-        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-        uint32_t piv0 = 0, piv1 = 0;  // per-row pivot (an element of the row, both halves of a half2): sums run over x - pivot
-        for (int kb = t.kb0; kb < t.kb1; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(&full_bar[s], ph);
-          const uint32_t r0 = smem_u32(smem + s * stage_bytes) + st * 128;
-          if (kb == t.kb0) {
-            uint32_t w0, w1;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(r0) : "memory");
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(r0 + 64 * 128) : "memory");
-            piv0 = __byte_perm(w0, w0, 0x1010);
-            piv1 = __byte_perm(w1, w1, 0x1010);
-          }
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint32_t off = static_cast<uint32_t>((c + lane) & 7) << 4;
-            uint32_t wa[4], wb[4];
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wa[0]), "=r"(wa[1]), "=r"(wa[2]), "=r"(wa[3]) : "r"(r0 + off) : "memory");
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wb[0]), "=r"(wb[1]), "=r"(wb[2]), "=r"(wb[3]) : "r"(r0 + 64 * 128 + off) : "memory");
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              // d = x - pivot as half2 (its fp16 rounding only perturbs the statistics by ~2^-11 / sqrt(K)), then the
-              // mixed-precision forms (fp16 operands, fp32 accumulator — FHADD / FHFMA on sm_100): two instructions per element
-              asm("{\n\t.reg .b32 d;\n\t.reg .b16 lo, hi;\n\t"
-                  "sub.rn.f16x2 d, %2, %3;\n\tmov.b32 {lo, hi}, d;\n\t"
-                  "add.f32.f16 %0, lo, %0;\n\tadd.f32.f16 %0, hi, %0;\n\t"
-                  "fma.rn.f32.f16 %1, lo, lo, %1;\n\tfma.rn.f32.f16 %1, hi, hi, %1;\n\t}\n" : "+f"(s0), "+f"(q0) : "r"(wa[e]), "r"(piv0));
-              asm("{\n\t.reg .b32 d;\n\t.reg .b16 lo, hi;\n\t"
-                  "sub.rn.f16x2 d, %2, %3;\n\tmov.b32 {lo, hi}, d;\n\t"
-                  "add.f32.f16 %0, lo, %0;\n\tadd.f32.f16 %0, hi, %0;\n\t"
-                  "fma.rn.f32.f16 %1, lo, lo, %1;\n\tfma.rn.f32.f16 %1, hi, hi, %1;\n\t}\n" : "+f"(s1), "+f"(q1) : "r"(wb[e]), "r"(piv1));
-            }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty_bar[s]);
-        }
-        mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);  // the epilogue of unit j - 2 has read rowstat[buf]
-        {
-          // columns beyond K are zero-filled by TMA: each contributed d = -pivot; take them out again
-          const float npad = static_cast<float>((t.kb1 - t.kb0) * BK - p.ln_k);
-          const float pv0 = __half2float(__ushort_as_half(static_cast<unsigned short>(piv0 & 0xffffu)));
-          const float pv1 = __half2float(__ushort_as_half(static_cast<unsigned short>(piv1 & 0xffffu)));
-          const float d0 = (s0 + npad * pv0) * p.ln_inv_k, d1 = (s1 + npad * pv1) * p.ln_inv_k;  // mean - pivot
-          const float v0 = fmaxf((q0 - npad * pv0 * pv0) * p.ln_inv_k - d0 * d0, 0.f);
-          const float v1 = fmaxf((q1 - npad * pv1 * pv1) * p.ln_inv_k - d1 * d1, 0.f);
-          rowstat[buf * 128 + st] = make_float2(pv0 + d0, rsqrtf(v0 + p.ln_eps));
-          rowstat[buf * 128 + st + 64] = make_float2(pv1 + d1, rsqrtf(v1 + p.ln_eps));
-        }
-        mbar_arrive(&acc_full[buf]);
-      }
-    }
-  } else {
+  } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue: 2 warpgroups x 128 threads
     const int wg = (warp - 4) >> 2;
     const int q = warp & 3;              // TMEM lane quadrant this warp may read
@@ -386,40 +321,41 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const int out_bn = geglu ? p.BN / 2 : p.BN;    // output columns per tile
     const int nchunks = (out_bn + 31) / 32;        // a narrow tile (BN < 32) still takes one chunk; guards clip it
     const int ws_ld = nchunks * 32;                // leading dimension of one split-K partial tile
-    const uint32_t stg_base = smem_u32(out_stg) + wg * 2 * STG_BYTES;
+    const uint32_t stg_base = smem_u32(out_stg) + wg * STG_PER_WG * STG_BYTES;
     float* sbias = bias_smem + wg * 256;
     const int inner = p.heads * p.dhead;
     int n_staged = 0;  // staging buffer toggle
     pdl_wait();        // residual / split-K workspace reads and every output write come after the predecessor grid
 
-    // LN mode: v = rstd[row] * (acc - mean[row] * colsum[col]) — LayerNorm(x) W'^T from the raw-x product (thread = row here)
-    float ln_mu = 0.f, ln_rs = 1.f;
-    auto ln_apply = [&](float* v, int col0) {  // col0: GEMM column (packed weight row) of v[0]
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int col = col0 + 4 * i;
-        float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col < p.N) c4 = ldg4(p.ln_colsum + col, true, 4);  // N % 4 == 0 and 16-byte alignment are checked on the host
-        v[4 * i] = ln_rs * fmaf(-ln_mu, c4.x, v[4 * i]);
-        v[4 * i + 1] = ln_rs * fmaf(-ln_mu, c4.y, v[4 * i + 1]);
-        v[4 * i + 2] = ln_rs * fmaf(-ln_mu, c4.z, v[4 * i + 2]);
-        v[4 * i + 3] = ln_rs * fmaf(-ln_mu, c4.w, v[4 * i + 3]);
-      }
-    };
-
     // ---- phase A of one chunk: TMEM -> registers -> (GEGLU) -> swizzled staging tile, or the direct QKV scatter
     auto phase_a = [&](const Unit& t, uint32_t taddr, int c, uint32_t stg) -> bool {
       float v[32];
       const int oc = t.n_tile * out_bn + c * 32;
-      if (geglu) {
+      if (geglu && NWG == 3) {
+        // three warpgroups run at 128 registers: the value / gate columns pass through in two 16-column halves
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float g[16];
+          tmem_ld16(taddr + c * 32 + hh * 16, v + hh * 16);
+          tmem_ld16(taddr + p.BN / 2 + c * 32 + hh * 16, g);
+          tmem_ld_wait();
+          if (p.bias != nullptr) {
+            const uint32_t sv = smem_u32(sbias + c * 32 + hh * 16), sg = smem_u32(sbias + p.BN / 2 + c * 32 + hh * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 bv = lds_v4(sv + i * 16), bg = lds_v4(sg + i * 16);
+              v[hh * 16 + 4 * i] += bv.x; v[hh * 16 + 4 * i + 1] += bv.y; v[hh * 16 + 4 * i + 2] += bv.z; v[hh * 16 + 4 * i + 3] += bv.w;
+              g[4 * i] += bg.x; g[4 * i + 1] += bg.y; g[4 * i + 2] += bg.z; g[4 * i + 3] += bg.w;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[hh * 16 + i] *= gelu_erf(g[i]);
+        }
+      } else if (geglu) {
         float g[32];
         tmem_ld32(taddr + c * 32, v);
         tmem_ld32(taddr + p.BN / 2 + c * 32, g);
         tmem_ld_wait();
-        if (ln) {
-          ln_apply(v, t.n_tile * p.BN + c * 32);
-          ln_apply(g, t.n_tile * p.BN + p.BN / 2 + c * 32);
-        }
         if (p.bias != nullptr) {
           const uint32_t sv = smem_u32(sbias + c * 32), sg = smem_u32(sbias + p.BN / 2 + c * 32);
 #pragma unroll
@@ -434,7 +370,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       } else {
         tmem_ld32(taddr + c * 32, v);
         tmem_ld_wait();
-        if (ln) ln_apply(v, oc);
       }
       if (out_mode == MVD_OUT_QKV_HEADS && (p.qkv_direct || oc >= 2 * inner)) {
         // v^T (keys contiguous) wants thread = row: leave straight from the registers
@@ -486,9 +421,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
     // ---- phase B of one chunk.  part_tile/part_s: split-K partial tiles to add (nullptr = none); nxt_*: next chunk of
     //      this warpgroup (residual prefetch), nxt_valid = false when there is none.
+    constexpr bool PREFETCH_RES = (NWG == 2);  // three warpgroups: a third chunk in flight hides the latency instead (and 32 registers less)
     auto phase_b = [&](const Unit& t, int c, uint32_t stg, bool nxt_valid, int nxt_grow0, int nxt_oc) {
       const int oc = t.n_tile * out_bn + c * 32;
       const int col = oc + seg * 4;
+      if (!PREFETCH_RES && has_res) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rn[i] = res_load(t.grow0, oc, i);
+      }
       const int nvalid = VEC ? ((n_out - col) > 0 ? 4 : 0) : (n_out - col);  // <= 0: this thread's columns do not exist
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(1.f, 1.f, 1.f, 1.f);
       if (!geglu && p.bias != nullptr && nvalid > 0) b4 = ldg4(p.bias + col, VEC || p.vec_bias != 0, nvalid);
@@ -551,7 +491,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         v.x *= cs4.x; v.y *= cs4.y; v.z *= cs4.z; v.w *= cs4.w;
         if (has_res) {
           v.x += rn[i].x; v.y += rn[i].y; v.z += rn[i].z; v.w += rn[i].w;
-          if (nxt_valid) rn[i] = res_load(nxt_grow0, nxt_oc, i);
+          if (PREFETCH_RES && nxt_valid) rn[i] = res_load(nxt_grow0, nxt_oc, i);
         }
         if (!live) continue;
         if (out_mode == MVD_OUT_F32) {
@@ -600,10 +540,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       valid = min(nchunks, (n_out - t.n_tile * out_bn + 31) / 32);
       if (is_split) {
         cfirst = t.s + p.split * wg;
-        cstride = 2 * p.split;
+        cstride = NWG * p.split;
       } else {
-        cfirst = (wg ^ j) & 1;
-        cstride = 2;
+        cfirst = (wg + j) % NWG;
+        cstride = NWG;
       }
     };
     // first chunk of this warpgroup at or after unit j (search forward); false when no work is left
@@ -621,7 +561,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       return false;
     };
 
-    if (has_res) {  // residual of the very first chunk
+    if (PREFETCH_RES && has_res) {  // residual of the very first chunk
       int jt, ct, g0, oc0;
       if (find_task(0, jt, ct, g0, oc0)) {
 #pragma unroll
@@ -650,19 +590,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
-      if (ln) {  // published by the statistics warps' arrivals on acc_full; read before this thread's acc_empty arrival
-        const float2 rs = rowstat[buf * 128 + et];
-        ln_mu = rs.x;
-        ln_rs = rs.y;
-      }
 
       if (is_split) {
         // ---- park the chunks other slices own: ws[u][row][col] fp32, written with the coalesced phase-B mapping
         float* wsu = p.ws + static_cast<size_t>(u) * (BM * ws_ld);
-        for (int c = wg; c < valid_chunks; c += 2) {
+        for (int c = wg; c < valid_chunks; c += NWG) {
           if (c % p.split == t.s) continue;
-          const uint32_t stg = stg_base + (n_staged & 1) * STG_BYTES;
+          const uint32_t stg = stg_base + (STG_PER_WG == 2 ? (n_staged & 1) * STG_BYTES : 0);
           ++n_staged;
+          if (STG_PER_WG == 1) named_bar_sync(bar_id, WG_THREADS);  // the previous chunk's readers are done with the tile
           phase_a(t, taddr, c, stg);
           named_bar_sync(bar_id, WG_THREADS);
 #pragma unroll
@@ -673,21 +609,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
         }
         __threadfence();
-        named_bar_sync(3, EPI_THREADS);
+        named_bar_sync(NWG + 1, EPI_THREADS);
         if (wg == 0 && et == 0) {
           atomicAdd(&p.counters[2 * t.tile], 1);
           while (ld_acquire(&p.counters[2 * t.tile]) < p.split) {
           }
         }
-        named_bar_sync(3, EPI_THREADS);
+        named_bar_sync(NWG + 1, EPI_THREADS);
       }
 
       for (int c = cfirst; c < valid_chunks; c += cstride) {
-        const uint32_t stg = stg_base + (n_staged & 1) * STG_BYTES;
+        const uint32_t stg = stg_base + (STG_PER_WG == 2 ? (n_staged & 1) * STG_BYTES : 0);
         // next chunk of this warpgroup (this unit or a later one) for the residual prefetch
         bool nxt = false;
         int ng0 = 0, noc = 0;
-        if (has_res) {
+        if (PREFETCH_RES && has_res) {
           if (c + cstride < valid_chunks) {
             nxt = true; ng0 = t.grow0; noc = t.n_tile * out_bn + (c + cstride) * 32;
           } else {
@@ -695,6 +631,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             nxt = find_task(j + 1, jt, ct, ng0, noc);
           }
         }
+        if (STG_PER_WG == 1) named_bar_sync(bar_id, WG_THREADS);  // the previous chunk's readers are done with the tile
         const bool staged = phase_a(t, taddr, c, stg);
         if (c + cstride >= valid_chunks) {  // last TMEM read of this unit by this thread: hand the accumulator back
           tc_fence_before();
@@ -714,7 +651,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
 
       if (is_split) {
-        named_bar_sync(3, EPI_THREADS);  // every partial of this tile has been consumed by this CTA
+        named_bar_sync(NWG + 1, EPI_THREADS);  // every partial of this tile has been consumed by this CTA
         if (wg == 0 && et == 0) {
           const int old = atomicAdd(&p.counters[2 * t.tile + 1], 1);
           if (old == p.split - 1) {  // last slice out resets the semaphores for the next launch
@@ -811,22 +748,10 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   p.seq = a->seq;
   p.out16 = static_cast<__half*>(a->out16);
   p.ld16 = a->ld16;
-  p.ln_colsum = a->ln_colsum;
-  p.ln_eps = a->ln_eps;
-  p.ln_inv_k = 1.0f / static_cast<float>(a->K);
-  p.ln_k = a->K;
-  const bool ln = a->ln_colsum != nullptr;
   if (a->out16 != nullptr) {
     if (a->out_mode != MVD_OUT_F32 || a->act == MVD_ACT_GEGLU) return set_error(MVD_EINVAL, "mvd_gemm_f16: out16 accompanies an F32 output only");
     if (a->ld16 < a->N) return set_error(MVD_EINVAL, "mvd_gemm_f16: ld16 is smaller than N");
     p.vec_out16 = (reinterpret_cast<uintptr_t>(a->out16) & 7) == 0 && (a->ld16 & 3) == 0;
-  }
-  if (ln) {
-    if (a->a_mode != MVD_A_ROWMAJOR) return set_error(MVD_EINVAL, "mvd_gemm_f16: ln_colsum needs a row-major A");
-    if ((a->N & 3) != 0 || (reinterpret_cast<uintptr_t>(a->ln_colsum) & 15) != 0)
-      return set_error(MVD_EALIGN, "mvd_gemm_f16: ln_colsum needs N % 4 == 0 and a 16-byte aligned vector");
-    if (a->split_k > 1 || a->cta_pair == 2) return set_error(MVD_EINVAL, "mvd_gemm_f16: ln_colsum excludes split_k and cta_pair");
-    if (!(a->ln_eps > 0.f)) return set_error(MVD_EINVAL, "mvd_gemm_f16: ln_eps must be positive");
   }
 
   const bool geglu = a->act == MVD_ACT_GEGLU;
@@ -853,8 +778,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   if (a->cta_pair < 0 || a->cta_pair > 2) return set_error(MVD_EINVAL, "mvd_gemm_f16: cta_pair must be 0, 1 or 2");
   if (a->cta_pair == 2 && (tiles_m_real < 2 || (sms & 1) != 0)) return set_error(MVD_EINVAL, "mvd_gemm_f16: cta_pair = 2 needs at least two m-tiles");
   const bool pair_auto = (deep || force_pair) && tiles_m_real >= 2 && ((tiles_m_real & 1) == 0 || tiles_m_real >= 9) && (sms & 1) == 0;
-  // (LN mode: the row statistics are taken from each CTA's own A tile behind its own full barrier — single CTAs only)
-  const bool pair = !no_pair && !ln && (a->cta_pair == 2 || (a->cta_pair == 0 && pair_auto));
+  const bool pair = !no_pair && (a->cta_pair == 2 || (a->cta_pair == 0 && pair_auto));
   const int tiles_mp = pair ? (tiles_m_real + 1) / 2 : tiles_m_real;
   const int slots = pair ? sms / 2 : sms;
   int bn = a->tile_n;
@@ -917,7 +841,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   int split = a->split_k;
   const size_t ws_avail = (a->splitk_ws != nullptr && a->splitk_ws_bytes > WS_COUNTER_BYTES) ? static_cast<size_t>(a->splitk_ws_bytes) - WS_COUNTER_BYTES : 0;
   const size_t tile_ws = static_cast<size_t>((bn + 31) / 32 * 32) * BM * sizeof(float);
-  const bool can_split = !geglu && a->out_mode != MVD_OUT_QKV_HEADS && !ln;
+  const bool can_split = !geglu && a->out_mode != MVD_OUT_QKV_HEADS;
   if (split <= 0) {  // auto: only when the tiles cannot fill half the machine and K is deep
     split = 1;
     if (can_split && tiles * 2 <= slots && p.num_kb >= 8) {
@@ -964,9 +888,62 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     p.qkv_direct = ((a->heads * a->dhead) & 31) != 0;
   }
 
-  // ---- shared memory / TMEM budget
+  // ---- pick the epilogue specialisation
+  const bool vec = (n_out % 4 == 0) && (a->bias == nullptr || p.vec_bias) && (a->rowbias == nullptr || p.vec_rowbias) &&
+                   (a->colscale == nullptr || p.vec_colscale) && (a->residual == nullptr || p.vec_res) && p.vec_out &&
+                   !(a->out_mode == MVD_OUT_QKV_HEADS && p.qkv_direct);
+  const int has_res = a->residual != nullptr ? 1 : 0;
+  const int is_split = split > 1 ? 1 : 0;
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const GemmKParams);
+  struct Spec { int key; int nwg; KernelFn one, two; };
+#define MVD_SPEC(ACT, OUT, RES, SPL, NWG) \
+  { (ACT) * 1000 + (OUT) * 100 + (RES) * 10 + (SPL), NWG, gemm_tc_kernel<ACT, OUT, RES, SPL, true, false, NWG>, gemm_tc_kernel<ACT, OUT, RES, SPL, true, true, NWG> }
+  // three epilogue warpgroups where the epilogue fits 128 registers (ptxas -v: <= 110 with two warpgroups), two elsewhere
+  static const Spec specs[] = {
+      MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 0, 0, 3),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 0, 1, 2),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 1, 0, 3),
+      MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 1, 1, 2),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F16, 0, 0, 3),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F16, 1, 0, 3),
+      MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F16, 1, 1, 2),  MVD_SPEC(MVD_ACT_GELU, MVD_OUT_F16, 0, 0, 3),  MVD_SPEC(MVD_ACT_GELU, MVD_OUT_F32, 0, 0, 3),
+      MVD_SPEC(MVD_ACT_GEGLU, MVD_OUT_F16, 0, 0, 3), MVD_SPEC(MVD_ACT_NONE, MVD_OUT_QKV_HEADS, 0, 0, 3),
+  };
+  // the same keys with two warpgroups (MVD_GEMM_WG2=1 in the environment: A/B measurements)
+  static const Spec specs_wg2[] = {
+      MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 0, 0, 2),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F16, 0, 0, 2),  MVD_SPEC(MVD_ACT_GELU, MVD_OUT_F16, 0, 0, 2),
+      MVD_SPEC(MVD_ACT_GELU, MVD_OUT_F32, 0, 0, 2),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_QKV_HEADS, 0, 0, 2),
+      MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 1, 0, 2),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F16, 1, 0, 2),  MVD_SPEC(MVD_ACT_GEGLU, MVD_OUT_F16, 0, 0, 2),
+  };
+#undef MVD_SPEC
+  static const Spec generic = {-1, 2, gemm_tc_kernel<-1, -1, -1, -1, false, false, 2>, gemm_tc_kernel<-1, -1, -1, -1, false, true, 2>};
+  static const bool force_wg2 = getenv("MVD_GEMM_WG2") != nullptr;
+  const Spec* spec = &generic;
+  if (vec) {
+    const int key = a->act * 1000 + a->out_mode * 100 + has_res * 10 + is_split;
+    for (const Spec& sp : specs)
+      if (sp.key == key) spec = &sp;
+    if (force_wg2 && spec->nwg != 2)
+      for (const Spec& sp : specs_wg2)
+        if (sp.key == key) spec = &sp;
+  }
+  static bool configured = false;
+  if (!configured) {
+    for (const Spec& sp : specs) {
+      MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.one, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.two, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    }
+    for (const Spec& sp : specs_wg2) {
+      MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.one, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.two, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    }
+    MVD_CUDA_CHECK(cudaFuncSetAttribute(generic.one, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    MVD_CUDA_CHECK(cudaFuncSetAttribute(generic.two, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    configured = true;
+  }
+  const int nwg = spec->nwg;
+  const int threads = 128 + 128 * nwg;
+
+  // ---- shared memory / TMEM budget: ring stages + staging tiles (2 per warpgroup with two warpgroups, 1 with three) +
+  //      GEGLU tile bias (256 floats per warpgroup) + barriers
   const int stage_bytes = A_BYTES + (pair ? bn / 2 : bn) * 128;
-  const int fixed = 4 * STG_BYTES + 2048 + 512 + (ln ? 2048 : 0);  // staging, GEGLU bias, barriers, LN row statistics
+  const int fixed = (nwg == 2 ? 4 : 3) * STG_BYTES + nwg * 1024 + 512;
   int stages = (232448 - 1024 - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return set_error(MVD_EINVAL, "mvd_gemm_f16: tile does not fit in shared memory");
@@ -975,46 +952,12 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   p.acc_stride = bn <= 128 ? 128 : 256;
   p.tmem_cols = 2 * p.acc_stride;
 
-  // ---- pick the epilogue specialisation
-  const bool vec = (n_out % 4 == 0) && (a->bias == nullptr || p.vec_bias) && (a->rowbias == nullptr || p.vec_rowbias) &&
-                   (a->colscale == nullptr || p.vec_colscale) && (a->residual == nullptr || p.vec_res) && p.vec_out &&
-                   !(a->out_mode == MVD_OUT_QKV_HEADS && p.qkv_direct);
-  const int has_res = a->residual != nullptr ? 1 : 0;
-  const int is_split = split > 1 ? 1 : 0;
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const GemmKParams);
-  struct Spec { int key; KernelFn one, two; };
-#define MVD_SPEC(ACT, OUT, RES, SPL) \
-  { (ACT) * 1000 + (OUT) * 100 + (RES) * 10 + (SPL), gemm_tc_kernel<ACT, OUT, RES, SPL, true, false>, gemm_tc_kernel<ACT, OUT, RES, SPL, true, true> }
-  static const Spec specs[] = {
-      MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 0, 0),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 0, 1),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 1, 0),
-      MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 1, 1),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F16, 0, 0),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F16, 1, 0),
-      MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F16, 1, 1),  MVD_SPEC(MVD_ACT_GELU, MVD_OUT_F16, 0, 0),  MVD_SPEC(MVD_ACT_GELU, MVD_OUT_F32, 0, 0),
-      MVD_SPEC(MVD_ACT_GEGLU, MVD_OUT_F16, 0, 0), MVD_SPEC(MVD_ACT_NONE, MVD_OUT_QKV_HEADS, 0, 0),
-  };
-#undef MVD_SPEC
-  const Spec generic = {-1, gemm_tc_kernel<-1, -1, -1, -1, false, false>, gemm_tc_kernel<-1, -1, -1, -1, false, true>};
-  const Spec* spec = &generic;
-  if (vec) {
-    const int key = a->act * 1000 + a->out_mode * 100 + has_res * 10 + is_split;
-    for (const Spec& sp : specs)
-      if (sp.key == key) spec = &sp;
-  }
-  static bool configured = false;
-  if (!configured) {
-    for (const Spec& sp : specs) {
-      MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.one, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-      MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.two, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    }
-    MVD_CUDA_CHECK(cudaFuncSetAttribute(generic.one, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    MVD_CUDA_CHECK(cudaFuncSetAttribute(generic.two, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    configured = true;
-  }
   if (pair) {
     const int grid = 2 * (p.num_units < slots ? p.num_units : slots);
-    MVD_CUDA_CHECK(launch_kernel(spec->two, dim3(grid), dim3(GEMM_THREADS), dyn, stream, 2, tmA, tmB, p));
+    MVD_CUDA_CHECK(launch_kernel(spec->two, dim3(grid), dim3(threads), dyn, stream, 2, tmA, tmB, p));
   } else {
     const int grid = p.num_units < sms ? p.num_units : sms;
-    MVD_CUDA_CHECK(launch_kernel(spec->one, dim3(grid), dim3(GEMM_THREADS), dyn, stream, 1, tmA, tmB, p));
+    MVD_CUDA_CHECK(launch_kernel(spec->one, dim3(grid), dim3(threads), dyn, stream, 1, tmA, tmB, p));
   }
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());

@@ -119,34 +119,6 @@ class PackedWeights:
         return self._put("kv", p, lambda: self._pad_k(torch.cat([self.raw(p + ".to_k.weight"),
                                                                  self.raw(p + ".to_v.weight")], 0).float()).half())
 
-    # LayerNorm folded into the consuming GEMM (include/mvd_b200.h, mvd_gemm_args.ln_colsum):
-    #   LN(x) W^T + b = rstd (x W'^T - mean colsum(W')) + (b + W beta),   W' = W diag(gamma)
-    def _ln_fold(self, tag, key, w_fn, b_fn, norm):
-        """-> (W' fp16 [N, K8], colsum fp32 [N] of the ROUNDED W', bias' fp32 [N])"""
-        def f_w():
-            return self._pad_k(w_fn().float() * self.raw(norm + ".weight").float()[None, :]).half()
-        wp = self._put(tag + "_w", (key, norm), f_w)
-        cs = self._put(tag + "_cs", (key, norm), lambda: wp.float().sum(dim=1))
-        def f_b():
-            wb = w_fn().float() @ self.raw(norm + ".bias").float()
-            b = b_fn()
-            return wb if b is None else wb + b.float()
-        bp = self._put(tag + "_b", (key, norm), f_b)
-        return wp, cs, bp
-
-    def qkv_ln(self, p, norm):
-        """fused to_q | to_k | to_v behind nn.LayerNorm `norm` (attention.py:211,220; mvd attention.py:35,52)"""
-        w = lambda: torch.cat([self.raw(p + ".to_q.weight"), self.raw(p + ".to_k.weight"), self.raw(p + ".to_v.weight")], 0)
-        return self._ln_fold("qkvln", p, w, lambda: None, norm)
-
-    def geglu_ln(self, p, norm, tile_n=128):
-        """GEGLU.proj behind nn.LayerNorm `norm`, rows interleaved per output tile as in geglu()"""
-        inner = self.raw(p + ".weight").shape[0] // 2
-        perm = self._put("geglu_perm", (inner, tile_n), lambda: self.ops.geglu_permutation(inner, tile_n))
-        w = lambda: self.raw(p + ".weight")[perm.cpu()]
-        b = lambda: self.raw(p + ".bias")[perm.cpu()]
-        return self._ln_fold("gegluln", (p, tile_n), w, b, norm)
-
     def geglu(self, p, tile_n=128):
         """GEGLU.proj [2*inner, C] with value/gate rows interleaved per output tile (include/mvd_b200.h, MVD_ACT_GEGLU)"""
         w = self.raw(p + ".weight")
@@ -229,8 +201,6 @@ class Builder:
         self._stats = None
         self._ws = None
         self.heads = 8
-        # nn.LayerNorm in front of to_q/k/v and GEGLU.proj folded into those GEMMs (MVD_NO_LN_FOLD=1: separate LayerNorm passes)
-        self.ln_fold = not os.environ.get("MVD_NO_LN_FOLD")
         # fp16 operands of the 1x1 skip convolutions written by their producers' epilogues (MVD_NO_FUSE_CAT=1: cast / concat passes)
         self.fuse_cat = not os.environ.get("MVD_NO_FUSE_CAT")
 
@@ -270,8 +240,7 @@ class Builder:
         # split_k = 0 lets the library cut K when the tile grid cannot fill the machine (small-M, weight-bound layers);
         # a measured (tile_n, split_k, cta_pair) choice from gemm_tuning.json overrides the library's heuristics.
         act = kw.get("act", ACT_NONE)
-        has_ln = kw.get("ln") is not None
-        can_split = allow_split and act != ACT_GEGLU and kw.get("qkv") is None and not has_ln
+        can_split = allow_split and act != ACT_GEGLU and kw.get("qkv") is None
         sig = gemm_signature(kw.get("conv") is not None, M, N, K,
                              "qkv" if kw.get("qkv") is not None else str(out.dtype).split(".")[-1], kw.get("residual") is not None, act)
         tuned = gemm_tuning().get(sig)
@@ -281,8 +250,6 @@ class Builder:
                 tn = GEGLU_TILE
             if sk > 1 and not can_split:
                 sk = 1
-            if has_ln:
-                pr = 1
             self.prog.append(self.ops.gemm(A, Wt, out, M, N, K, split_k=sk, tile_n=tn, cta_pair=pr,
                                            ws=self.splitk_ws() if sk != 1 else None, **kw))
         elif can_split:
@@ -411,46 +378,33 @@ class Builder:
         return out
 
     # -- attention blocks
-    def self_attention(self, h, p, norm, n_img, seq, C, rowbias=None, h16=None, want16=False):
-        """x = attn1(norm1(x)) + x  [+ per-image vector]: fused QKV GEMM (heads scattered) -> flash attention -> to_out GEMM
-        with bias + residual.  attention.py:170-193,220; mvd attention.py:52
-        h16: fp16 copy of h written by h's producer — norm1 is then folded into the QKV GEMM (no LayerNorm pass);
-        want16: also return an fp16 copy of the result (for the next folded LayerNorm)."""
+    def self_attention(self, h, p, norm, n_img, seq, C, rowbias=None):
+        """x = attn1(norm1(x)) + x  [+ per-image vector]: LayerNorm -> fused QKV GEMM (heads scattered) ->
+        flash attention -> to_out GEMM with bias + residual.  attention.py:170-193,220; mvd attention.py:52"""
         M = n_img * seq
         d = C // self.heads
         dpad = _round_up(d, 64)
+        ln = self.layernorm(h, norm, M, C)
         q, k, vt = self.qkv_buffers(n_img, seq, dpad)
-        qkv = dict(out_k=k, out_vt=vt, heads=self.heads, dhead=d, dpad=dpad, seq=seq)
-        if h16 is not None:
-            w, cs, bq = self.W.qkv_ln(p, norm)
-            self.gemm(h16, w, q, M, 3 * C, C, qkv=qkv, bias=bq, ln=(cs, 1e-5))
-            ao = h16  # reuse: same shape / dtype, the QKV GEMM was its last reader
-        else:
-            ao = self.layernorm(h, norm, M, C)
-            self.gemm(ao, self.W.qkv(p), q, M, 3 * C, C, qkv=qkv)
+        self.gemm(ln, self.W.qkv(p), q, M, 3 * C, C,
+                  qkv=dict(out_k=k, out_vt=vt, heads=self.heads, dhead=d, dpad=dpad, seq=seq))
+        ao = ln  # reuse: same shape / dtype, the QKV GEMM was its last reader
         self.prog.append(self.ops.attn_self(q, k, vt, ao, n_img, self.heads, seq, d, dpad, C))
         h2 = self.t32(M, C)
-        h2_16 = self.t16(M, C) if want16 else None
         self.gemm(ao, self.W.lin(p + ".to_out.0.weight"), h2, M, C, C, allow_split=True, bias=self.W.f32(p + ".to_out.0.bias"),
-                  rowbias=rowbias, rows_per_group=seq, residual=h, ldr=C, out16=h2_16)
+                  rowbias=rowbias, rows_per_group=seq, residual=h, ldr=C)
         self.free(ao, h)
-        return (h2, h2_16) if want16 else h2
+        return h2
 
-    def feed_forward(self, h, p, norm, M, C, out16=False, h16=None):
+    def feed_forward(self, h, p, norm, M, C, out16=False):
         """x = ff(norm3(x)) + x with the GEGLU fused into the first GEMM's epilogue.  attention.py:37-64,222
-        out16: the block output only feeds proj_out, so it is written once, as that GEMM's fp16 operand.
-        h16: fp16 copy of h from its producer — norm3 is then folded into the GEGLU GEMM."""
+        out16: the block output only feeds proj_out, so it is written once, as that GEMM's fp16 operand."""
+        ln = self.layernorm(h, norm, M, C)
         inner = 4 * C
+        wg, bg = self.W.geglu(p + ".net.0.proj", GEGLU_TILE)
         g = self.t16(M, inner)
-        if h16 is not None:
-            wg, cs, bg = self.W.geglu_ln(p + ".net.0.proj", norm, GEGLU_TILE)
-            self.gemm(h16, wg, g, M, 2 * inner, C, bias=bg, act=ACT_GEGLU, tile_n=GEGLU_TILE, ldc=inner, ln=(cs, 1e-5))
-            self.free(h16)
-        else:
-            ln = self.layernorm(h, norm, M, C)
-            wg, bg = self.W.geglu(p + ".net.0.proj", GEGLU_TILE)
-            self.gemm(ln, wg, g, M, 2 * inner, C, bias=bg, act=ACT_GEGLU, tile_n=GEGLU_TILE, ldc=inner)
-            self.free(ln)
+        self.gemm(ln, wg, g, M, 2 * inner, C, bias=bg, act=ACT_GEGLU, tile_n=GEGLU_TILE, ldc=inner)
+        self.free(ln)
         h2 = self.t16(M, C) if out16 else self.t32(M, C)
         self.gemm(g, self.W.lin(p + ".net.2.weight"), h2, M, C, inner, allow_split=True, bias=self.W.f32(p + ".net.2.bias"),
                   residual=h, ldr=C)
@@ -464,15 +418,11 @@ class Builder:
         hw, M = H * H, n_img * H * H
         a = self.groupnorm(x, p + ".norm", n_img, hw, C, 1e-6, False)
         h = self.t32(M, C)
-        hx = self.t16(M, C) if self.ln_fold else None  # fp16 copy for the folded norm1 (written by proj_in's epilogue)
-        self.gemm(a, self.W.lin(p + ".proj_in.weight"), h, M, C, C, allow_split=True, bias=self.W.f32(p + ".proj_in.bias"), out16=hx)
+        self.gemm(a, self.W.lin(p + ".proj_in.weight"), h, M, C, C, allow_split=True, bias=self.W.f32(p + ".proj_in.bias"))
         self.free(a)
         tb = p + ".transformer_blocks.0"
-        if self.ln_fold:
-            h, hx = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C, rowbias=clipvec, h16=hx, want16=True)
-        else:
-            h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C, rowbias=clipvec)
-        h16 = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C, out16=True, h16=hx)
+        h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C, rowbias=clipvec)
+        h16 = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C, out16=True)
         out = self.t32(M, C)
         self.gemm(h16, self.W.lin(p + ".proj_out.weight"), out, M, C, C, allow_split=True, bias=self.W.f32(p + ".proj_out.bias"),
                   residual=x, ldr=C, **self._o16(out16))
@@ -491,9 +441,8 @@ class Builder:
         self.free(v)
         return out
 
-    def view_cross_attention(self, h, p, norm, ctx16, M, D, C, want16=False):
-        """DualAttnetionBlock.attn2 (mvd attention.py:56-62): every pixel is one query against its D frustum keys.
-        want16: also return an fp16 copy of the result (for the folded norm3 of the feed-forward)."""
+    def view_cross_attention(self, h, p, norm, ctx16, M, D, C):
+        """DualAttnetionBlock.attn2 (mvd attention.py:56-62): every pixel is one query against its D frustum keys."""
         d = C // self.heads
         if D == 1:  # softmax over a single key == 1: out = to_out(to_v(ctx))
             v = self.t16(M, C)
@@ -510,29 +459,23 @@ class Builder:
             self.prog.append(self.ops.pixel_cross_attn(q, kv, o, M, D, self.heads, d))
             self.free(q, kv)
         h2 = self.t32(M, C)
-        h2_16 = self.t16(M, C) if want16 else None
         self.gemm(o, self.W.lin(p + ".to_out.0.weight"), h2, M, C, C, allow_split=True, bias=self.W.f32(p + ".to_out.0.bias"),
-                  residual=h, ldr=C, out16=h2_16)
+                  residual=h, ldr=C)
         self.free(o, h)
-        return (h2, h2_16) if want16 else h2
+        return h2
 
     def view_aligned_transformer(self, x, p, n_img, H, C, ctx16, D, out16=None):
         """ViewAlignedFeatureTransformer.forward (mvd attention.py:119-145) + DualAttnetionBlock (:43-66)."""
         hw, M = H * H, n_img * H * H
         a = self.groupnorm(x, p + ".aligned_attn_norm", n_img, hw, C, 1e-6, False)
         h = self.t32(M, C)
-        hx = self.t16(M, C) if self.ln_fold else None
         self.gemm(a, self.W.lin(p + ".aligned_attn_proj_in.weight"), h, M, C, C, allow_split=True,
-                  bias=self.W.f32(p + ".aligned_attn_proj_in.bias"), out16=hx)
+                  bias=self.W.f32(p + ".aligned_attn_proj_in.bias"))
         self.free(a)
         tb = p + ".aligned_attn_transformer_blocks.0"
-        h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C, h16=hx)
-        hx = None
-        if self.ln_fold:
-            h, hx = self.view_cross_attention(h, tb + ".attn2", tb + ".norm2", ctx16, M, D, C, want16=True)
-        else:
-            h = self.view_cross_attention(h, tb + ".attn2", tb + ".norm2", ctx16, M, D, C)
-        h16 = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C, out16=True, h16=hx)
+        h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C)
+        h = self.view_cross_attention(h, tb + ".attn2", tb + ".norm2", ctx16, M, D, C)
+        h16 = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C, out16=True)
         out = self.t32(M, C)
         self.gemm(h16, self.W.lin(p + ".aligned_attn_proj_out.weight"), out, M, C, C, allow_split=True,
                   bias=self.W.f32(p + ".aligned_attn_proj_out.bias"), residual=x, ldr=C, **self._o16(out16))

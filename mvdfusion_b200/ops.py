@@ -79,10 +79,8 @@ class NativeOps:
     # ------------------------------------------------------------------ GEMM / conv
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
              colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None, cta_pair=0,
-             out16=None, ld16=None, ln=None):
-        """out16: optional fp16 tensor that receives a copy of an fp32 output ([M, ld16]).
-        ln = (colsum fp32 [N], eps): LayerNorm folded into the GEMM — A holds the raw rows, Wt the gamma-scaled weights
-        (include/mvd_b200.h, mvd_gemm_args.ln_colsum)."""
+             out16=None, ld16=None):
+        """out16: optional fp16 tensor (or column window of a wider one, row pitch ld16) that receives a copy of an fp32 output."""
         g = _lib.GemmArgs()
         g.M, g.N, g.K = M, N, K
         g.A = _ptr(A, torch.float16)
@@ -119,17 +117,14 @@ class NativeOps:
         if out16 is not None:
             g.out16 = _ptr(out16, torch.float16)
             g.ld16 = ld16 if ld16 is not None else out16.shape[-1]
-        if ln is not None:
-            g.ln_colsum = _ptr(ln[0], torch.float32)
-            g.ln_eps = float(ln[1])
-        keep = (g, A, Wt, out, bias, rowbias, colscale, residual, qkv, ws, out16, ln)
+        keep = (g, A, Wt, out, bias, rowbias, colscale, residual, qkv, ws, out16)
         n_out = N // 2 if act == ACT_GEGLU else N
         a_bytes = (conv[0] * conv[1] * conv[2] * conv[3] if conv is not None else M * K) * 2
         o_bytes = M * n_out * (4 if (qkv is None and out.dtype == torch.float32) else 2)
         desc = (f"{'conv' if conv is not None else 'lin'} M{M} N{N} K{K} "
                 f"{'qkv' if qkv is not None else ('f32' if out.dtype == torch.float32 else 'f16')}"
                 f"{' res' if residual is not None else ''}{' act%d' % act if act else ''}{' sk' if split_k != 1 else ''}"
-                f"{' +f16' if out16 is not None else ''}{' ln' if ln is not None else ''}")
+                f"{' +f16' if out16 is not None else ''}")
         sig = gemm_signature(conv is not None, M, N, K, "qkv" if qkv is not None else str(out.dtype).split(".")[-1], residual is not None, act)
         meta = {"kernel": "gemm_tc_kernel", "flops": 2.0 * M * N * K, "shape": (M, N, K, split_k), "desc": desc, "sig": sig, "can_split": ws is not None,
                 "bytes": a_bytes + N * K * 2 + o_bytes + (M * n_out * 4 if residual is not None else 0) + (M * n_out * 2 if out16 is not None else 0)}

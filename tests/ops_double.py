@@ -45,9 +45,8 @@ class TorchOpsDouble:
     # ------------------------------------------------------------------ GEMM / conv
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
              colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None, cta_pair=0,
-             out16=None, ld16=None, ln=None):
+             out16=None, ld16=None):
         assert A.dtype == torch.float16 and Wt.dtype == torch.float16
-        assert ln is None or (conv is None and split_k in (0, 1) and cta_pair != 2)
         assert out16 is None or (out.dtype == torch.float32 and qkv is None and act != ACT_GEGLU)
         ldw_ = ldw if ldw is not None else Wt.shape[-1]
 
@@ -64,10 +63,6 @@ class TorchOpsDouble:
                 lda_ = lda if lda is not None else A.shape[-1]
                 a = torch.as_strided(A, (M, K), (lda_, 1), A.storage_offset()).float()  # A may be a column window of a wider buffer
             acc = a @ W.t()
-            if ln is not None:  # LayerNorm folded into the GEMM: statistics of the raw fp16 rows, E[x^2] - mean^2 form
-                mu = a.mean(dim=1, keepdim=True)
-                var = ((a * a).mean(dim=1, keepdim=True) - mu * mu).clamp_min(0.0)
-                acc = torch.rsqrt(var + ln[1]) * (acc - mu * ln[0].reshape(-1)[:N].float())
             if bias is not None:
                 acc = acc + bias.reshape(-1)[:N]
             if rowbias is not None:
