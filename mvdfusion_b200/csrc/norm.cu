@@ -4,86 +4,94 @@
 //                             external/sd1/ldm/modules/attention.py:76-77
 //   nn.LayerNorm            : external/sd1/ldm/modules/attention.py:211-213, mvdfusion/attention.py:35-37
 //   DiT LayerNorm+modulate  : mvdfusion/view_attn_efficient2.py:15-16,51,53,65-66
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
 namespace mvd {
 
 // ---------------------------------------------------------------------------- GroupNorm
-// One kernel, one pass over HBM: a CTA owns `gpc` consecutive groups (span = gpc * C/32 channels, a multiple of 8 so that
-// every pixel's slice is whole 32-byte sectors) of one image for ALL pixels.  It reads its slice once (float4, thread
-// (row, cq) owns channels 4cq..4cq+3 of pixels row, row+rows, ...), keeps it in shared memory when it fits, reduces
-// per-group sum / sum of squares (fp32 per-thread partials over a few dozen values, combined in fp64), then normalises,
-// applies gamma / beta (+SiLU) and writes the fp16 GEMM operand.  Slices too large for shared memory (C = 960 at 32x32)
-// are re-read from L2 in the second phase.
-template <bool CACHE>
-__global__ void __launch_bounds__(512)
-    gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ x2, int C1, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, __half* __restrict__ y, int hw, int C, int cpg, int gpc, int rows, float eps,
-                    int apply_silu) {
+// One kernel, one pass over HBM/L2, statistics exchanged inside a thread-block cluster.
+//   slice   = `gpc` consecutive groups of one image (span = gpc * C/32 channels; a multiple of 8 channels when possible,
+//             so that every pixel's part of the slice is whole 32-byte sectors)
+//   cluster = the CTAs that share one slice; CTA r of `csplit` owns pixels r, r + csplit, ... (interleaved)
+//   thread (row, cq) owns channels 4cq .. 4cq+3 of the CTA's pixels row, row + rows, ...: at most MAXP pixels, which
+//             stay in REGISTERS between the statistics and the normalisation (all loads of a thread are issued at once:
+//             one memory latency per CTA; several small CTAs per SM overlap each other's phases).
+//   per-thread fp32 partial sums -> smem [row][span] -> one warp per group sums them in fp64 -> cluster barrier ->
+//   every CTA adds up its peers' group sums through distributed shared memory -> normalise, gamma / beta (+SiLU), fp16.
+template <int MAXP>
+__global__ void __launch_bounds__(256)
+    gn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ x2, int C1, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, __half* __restrict__ y, int hw, int C, int cpg, int gpc, int rows, int csplit,
+                      float eps, int apply_silu) {
   pdl_trigger();
-  pdl_wait();
   extern __shared__ __align__(16) uint8_t gn_smem[];
   const int span = gpc * cpg;
   const int span4 = span >> 2;
-  float* part_s = reinterpret_cast<float*>(gn_smem);  // [rows][span]
-  float* part_q = part_s + rows * span;               // [rows][span]
-  float* s_mean = part_q + rows * span;               // [32]
-  float* s_rstd = s_mean + 32;                        // [32]
-  float4* cache = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(s_rstd + 32) + 32 * 16 * 2 * sizeof(double));  // [hw][span4] when CACHE
+  double* gsum = reinterpret_cast<double*>(gn_smem);      // [32][2] group sums of this CTA (read by the cluster peers)
+  float* s_mean = reinterpret_cast<float*>(gsum + 64);    // [32]
+  float* s_rstd = s_mean + 32;                            // [32]
+  float* part_s = s_rstd + 32;                            // [rows][span]
+  float* part_q = part_s + rows * span;                   // [rows][span]
 
   const int img = blockIdx.y;
-  const int c0 = blockIdx.x * span;  // first channel of this CTA's slice
+  const int slice = blockIdx.x / csplit;
+  const int rank = blockIdx.x - slice * csplit;  // == %cluster_ctarank (cluster dims (csplit, 1, 1))
+  const int c0 = slice * span;
   const int cq = threadIdx.x % span4;
   const int row = threadIdx.x / span4;
   const bool active = row < rows;
   // two-source form (x2 != nullptr): channels [0, C1) live in x [.., C1], channels [C1, C) in x2 [.., C - C1] — the
   // torch.cat([h, skip], dim=1) of the UNet's output blocks (mvdfusion/unet.py:550) is never materialised.
   // C1 % 4 == 0, so a thread's four channels always come from one source.
-  const int cg = c0 + cq * 4;  // first global channel of this thread
+  const int cg = c0 + cq * 4;
   const bool second = x2 != nullptr && cg >= C1;
   const int Csrc = x2 == nullptr ? C : (second ? C - C1 : C1);
   const size_t pix_stride4 = static_cast<size_t>(Csrc) >> 2;
   const float4* src = reinterpret_cast<const float4*>((second ? x2 : x) + static_cast<size_t>(img) * hw * Csrc + (second ? cg - C1 : cg));
-  const size_t out_stride4 = static_cast<size_t>(C) >> 2;
+  const int pstep = rows * csplit;         // pixel stride of one thread
+  const int p_first = row * csplit + rank;  // its first pixel
 
+  pdl_wait();
+  constexpr int NV = MAXP > 0 ? MAXP : 8;  // MAXP == 0: any number of pixels per thread, eight at a time, re-read for the output
+  float4 v[NV];
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   if (active) {
-    // eight independent 16-byte loads in flight per thread
-    for (int p0 = row; p0 < hw; p0 += 8 * rows) {
-      float4 v[8];
+    for (int pb = p_first; pb < (MAXP > 0 ? p_first + 1 : hw); pb += NV * pstep) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int p = p0 + u * rows;
+      for (int u = 0; u < NV; ++u) {
+        const int p = pb + u * pstep;
         v[u] = p < hw ? __ldg(src + static_cast<size_t>(p) * pix_stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int p = p0 + u * rows;
-        if (CACHE && p < hw) cache[p * span4 + cq] = v[u];
+      for (int u = 0; u < NV; ++u) {
         s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
         q[0] = fmaf(v[u].x, v[u].x, q[0]); q[1] = fmaf(v[u].y, v[u].y, q[1]);
         q[2] = fmaf(v[u].z, v[u].z, q[2]); q[3] = fmaf(v[u].w, v[u].w, q[3]);
       }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      part_s[row * span + cq * 4 + k] = s[k];
-      part_q[row * span + cq * 4 + k] = q[k];
-    }
+    *reinterpret_cast<float4*>(part_s + row * span + cq * 4) = make_float4(s[0], s[1], s[2], s[3]);
+    *reinterpret_cast<float4*>(part_q + row * span + cq * 4) = make_float4(q[0], q[1], q[2], q[3]);
   }
   __syncthreads();
-  // every warp sums a strided share of each group's rows x cpg partials in double; one thread per group finishes
   {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    double* red = reinterpret_cast<double*>(s_rstd + 32);  // [gpc][nwarps][2], in front of the cache
-    const int n = rows * cpg;
-    for (int g = 0; g < gpc; ++g) {
+    // warp w sums group w, w + 8, ...: lane = row, cpg contiguous fp32 partials each, accumulated in double
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = warp; g < gpc; g += 8) {
       double a = 0.0, b = 0.0;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int rr = i / cpg, c = i - rr * cpg;
-        a += static_cast<double>(part_s[rr * span + g * cpg + c]);
-        b += static_cast<double>(part_q[rr * span + g * cpg + c]);
+      for (int rr = lane; rr < rows; rr += 32) {
+        const float* ps = part_s + rr * span + g * cpg;
+        const float* pq = part_q + rr * span + g * cpg;
+        float fa = 0.f, fb = 0.f;  // <= 128 values of one row: fp32 is ample, the cross-row / cross-CTA sums are double
+        for (int c = 0; c < cpg; ++c) {
+          fa += ps[c];
+          fb += pq[c];
+        }
+        a += static_cast<double>(fa);
+        b += static_cast<double>(fb);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -91,51 +99,85 @@ __global__ void __launch_bounds__(512)
         b += __shfl_xor_sync(0xffffffffu, b, o);
       }
       if (lane == 0) {
-        red[(g * nwarps + warp) * 2] = a;
-        red[(g * nwarps + warp) * 2 + 1] = b;
+        gsum[2 * g] = a;
+        gsum[2 * g + 1] = b;
       }
-    }
-    __syncthreads();
-    if (threadIdx.x < gpc) {
-      const int g = threadIdx.x;
-      double a = 0.0, b = 0.0;
-      for (int w = 0; w < nwarps; ++w) {
-        a += red[(g * nwarps + w) * 2];
-        b += red[(g * nwarps + w) * 2 + 1];
-      }
-      const double inv_cnt = 1.0 / (static_cast<double>(hw) * cpg);
-      const double mean = a * inv_cnt;
-      const double var = fmax(b * inv_cnt - mean * mean, 0.0);
-      s_mean[g] = static_cast<float>(mean);
-      s_rstd[g] = rsqrtf(static_cast<float>(var) + eps);
     }
   }
+  // publish the group sums to the cluster, then add up every CTA's (own included) in rank order: all CTAs get identical bits
+  if (csplit > 1) cluster_sync_all();
+  else __syncthreads();
+  if (threadIdx.x < gpc) {
+    const int g = threadIdx.x;
+    double a = 0.0, b = 0.0;
+    if (csplit > 1) {
+      const uint32_t local = smem_u32(gsum + 2 * g);
+      double ra[8], rb[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {  // all remote loads in flight together
+        ra[r] = rb[r] = 0.0;
+        if (r < csplit) {
+          const uint32_t remote = mapa_u32(local, static_cast<uint32_t>(r));
+          asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(ra[r]), "=d"(rb[r]) : "r"(remote) : "memory");
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        a += ra[r];
+        b += rb[r];
+      }
+    } else {
+      a = gsum[2 * g];
+      b = gsum[2 * g + 1];
+    }
+    const double inv_cnt = 1.0 / (static_cast<double>(hw) * cpg);
+    const double mean = a * inv_cnt;
+    const double var = fmax(b * inv_cnt - mean * mean, 0.0);
+    s_mean[g] = static_cast<float>(mean);
+    s_rstd[g] = rsqrtf(static_cast<float>(var) + eps);
+  }
+  // peers may still be reading this CTA's gsum: arrive now, wait just before exit (the normalisation runs in between)
+  if (csplit > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   __syncthreads();
-  if (!active) return;
-  float sc[4], sh[4];  // y = x * sc + sh
+  if (active) {
+    float sc[4], sh[4];  // y = x * sc + sh
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int cl = cq * 4 + k;
-    const int g = cl / cpg;
-    const float ga = __ldg(gamma + c0 + cl);
-    sc[k] = s_rstd[g] * ga;
-    sh[k] = __ldg(beta + c0 + cl) - s_mean[g] * s_rstd[g] * ga;
-  }
-  uint2* dst = reinterpret_cast<uint2*>(y + static_cast<size_t>(img) * hw * C + c0) + cq;
-  for (int p = row; p < hw; p += rows) {
-    const float4 v = CACHE ? cache[p * span4 + cq] : __ldg(src + static_cast<size_t>(p) * pix_stride4);
-    float o[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
-    if (apply_silu) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = o[k] / (1.f + __expf(-o[k]));
+    for (int k = 0; k < 4; ++k) {
+      const int cl = cq * 4 + k;
+      const int g = cl / cpg;
+      const float ga = __ldg(gamma + c0 + cl);
+      sc[k] = s_rstd[g] * ga;
+      sh[k] = __ldg(beta + c0 + cl) - s_mean[g] * s_rstd[g] * ga;
     }
-    __half2 h0 = __floats2half2_rn(o[0], o[1]);
-    __half2 h1 = __floats2half2_rn(o[2], o[3]);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&h0);
-    u.y = *reinterpret_cast<uint32_t*>(&h1);
-    dst[static_cast<size_t>(p) * out_stride4] = u;
+    uint2* dst = reinterpret_cast<uint2*>(y + static_cast<size_t>(img) * hw * C + c0) + cq;
+    const size_t out_stride4 = static_cast<size_t>(C) >> 2;
+    for (int pb = p_first; pb < (MAXP > 0 ? p_first + 1 : hw); pb += NV * pstep) {
+      if (MAXP == 0) {  // the registers hold the last batch only: read this one again (L2)
+#pragma unroll
+        for (int u = 0; u < NV; ++u) {
+          const int p = pb + u * pstep;
+          if (p < hw) v[u] = __ldg(src + static_cast<size_t>(p) * pix_stride4);
+        }
+      }
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int p = pb + u * pstep;
+      if (p >= hw) continue;
+      float o[4] = {fmaf(v[u].x, sc[0], sh[0]), fmaf(v[u].y, sc[1], sh[1]), fmaf(v[u].z, sc[2], sh[2]), fmaf(v[u].w, sc[3], sh[3])};
+      if (apply_silu) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = __fdividef(o[k], 1.f + __expf(-o[k]));
+      }
+      __half2 h0 = __floats2half2_rn(o[0], o[1]);
+      __half2 h1 = __floats2half2_rn(o[2], o[3]);
+      uint2 w;
+      w.x = *reinterpret_cast<uint32_t*>(&h0);
+      w.y = *reinterpret_cast<uint32_t*>(&h1);
+      dst[static_cast<size_t>(p) * out_stride4] = w;
+    }
+    }
   }
+  if (csplit > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------- LayerNorm family
@@ -220,33 +262,51 @@ static int groupnorm_launch(const float* x, const float* x2, int C1, const float
   if (C > 4096) return set_error(MVD_EINVAL, "mvd_groupnorm_f32_f16: C must be <= 4096");
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(x2) & 15) || (reinterpret_cast<uintptr_t>(y) & 7))
     return set_error(MVD_EALIGN, "mvd_groupnorm_f32_f16: x must be 16-byte and y 8-byte aligned");
-  // groups per CTA: the smallest power of two whose channel span is a multiple of 8 (whole sectors per pixel), else of 4
-  int gpc = 0;
-  for (int g = 1; g <= 32 && gpc == 0; g <<= 1)
-    if (((g * cpg) & 7) == 0) gpc = g;
-  for (int g = 1; g <= 32 && gpc == 0; g <<= 1)
-    if (((g * cpg) & 3) == 0) gpc = g;
-  const int span = gpc * cpg;
-  const int span4 = span / 4;
-  if (span4 > 512) return set_error(MVD_EINVAL, "mvd_groupnorm_f32_f16: unsupported channel count");
-  int rows = 512 / span4;
-  if (rows > hw) rows = hw;
-  int threads = (rows * span4 + 31) / 32 * 32;
-  if (threads < 32 * 1) threads = 32;
-  const size_t fixed = static_cast<size_t>(2) * rows * span * sizeof(float) + 64 * sizeof(float) + 32 * 16 * 2 * sizeof(double);
-  const size_t cache_bytes = static_cast<size_t>(hw) * span * sizeof(float);
-  const bool use_cache = fixed + cache_bytes <= 200 * 1024;
-  const size_t sm = fixed + (use_cache ? cache_bytes : 0);
-  static bool configured = false;
-  if (!configured) {
-    MVD_CUDA_CHECK(cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-    configured = true;
+  // Geometry.  Candidates: groups per CTA = 1, 2, 4, ... with a span of whole float4s (span % 4 == 0) and at most 256
+  // channel quads; pixels of a slice are split over a cluster of 1, 2, 4 or 8 CTAs until a thread keeps <= 16 pixels
+  // (the cluster exchange costs more than a longer thread: measured on B200 with MVD_GN_GEOMETRY, tests/native/norm_bench).
+  // Preferred: whole 32-byte sectors per pixel (span % 8 == 0) and <= 16 pixels per thread; the first candidate that meets
+  // both wins, else the one with the fewest pixels per thread.
+  int best_gpc = 0, best_split = 1, best_pp = 1 << 30, best_rows = 0;
+  bool best_pref = false;
+  for (int gpc = 1; gpc <= 32; gpc <<= 1) {
+    const int span = gpc * cpg;
+    if ((span & 3) != 0 || span / 4 > 256) continue;
+    int rows = 256 / (span / 4);
+    if (rows > hw) rows = hw;
+    int split = 1;
+    while (split < 8 && (hw + rows * split - 1) / (rows * split) > 16) split <<= 1;
+    const int pp = (hw + rows * split - 1) / (rows * split);
+    const bool pref = (span & 7) == 0 && pp <= 16;
+    if (best_gpc == 0 || (pref && !best_pref) || (pref == best_pref && pp < best_pp)) {
+      best_gpc = gpc; best_split = split; best_pp = pp; best_rows = rows; best_pref = pref;
+    }
+    if (pref) break;
   }
-  const dim3 grid(32 / gpc, n_img);
-  if (use_cache)
-    MVD_LAUNCH((gn_fused_kernel<true>), grid, threads, sm, stream, x, x2, C1, gamma, beta, static_cast<__half*>(y), hw, C, cpg, gpc, rows, eps, apply_silu);
+  if (best_gpc == 0) return set_error(MVD_EINVAL, "mvd_groupnorm_f32_f16: unsupported shape (hw %d, C %d)", hw, C);
+  if (const char* ov = getenv("MVD_GN_GEOMETRY")) {  // "gpc,split": measurement override (tests/native/norm_bench)
+    int og = 0, os = 0;
+    if (sscanf(ov, "%d,%d", &og, &os) == 2 && og >= 1 && og <= 32 && 32 % og == 0 && ((og * cpg) & 3) == 0 && og * cpg / 4 <= 256 &&
+        (os == 1 || os == 2 || os == 4 || os == 8)) {
+      best_gpc = og;
+      best_split = os;
+      best_rows = 256 / (og * cpg / 4);
+      if (best_rows > hw) best_rows = hw;
+      best_pp = (hw + best_rows * os - 1) / (best_rows * os);
+    }
+  }
+  const int gpc = best_gpc, csplit = best_split, rows = best_rows, span = gpc * cpg;
+  const size_t sm = 64 * sizeof(double) + 64 * sizeof(float) + static_cast<size_t>(2) * rows * span * sizeof(float);
+  const dim3 grid((32 / gpc) * csplit, n_img);
+  __half* yh = static_cast<__half*>(y);
+  if (best_pp <= 4)
+    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<4>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu));
+  else if (best_pp <= 8)
+    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<8>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu));
+  else if (best_pp > 16)  // large images (64x64 latents and up): pixels stream through in batches and are read twice
+    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<0>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu));
   else
-    MVD_LAUNCH((gn_fused_kernel<false>), grid, threads, sm, stream, x, x2, C1, gamma, beta, static_cast<__half*>(y), hw, C, cpg, gpc, rows, eps, apply_silu);
+    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<16>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu));
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

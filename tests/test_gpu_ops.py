@@ -134,7 +134,9 @@ def test_qkv_and_attention(nat, dbl, n, seq, C):
     run_both(nat, dbl, "attn_self", t, ["o"], "q", "k", "vt", "o", n, heads, seq, d, dpad, C, tol=4e-3)
 
 
-@pytest.mark.parametrize("n,hw,C,silu", [(2, 1024, 320, True), (16, 16, 2560, True), (3, 256, 1920, False)])
+@pytest.mark.parametrize("n,hw,C,silu", [(2, 1024, 320, True), (16, 16, 2560, True), (3, 256, 1920, False), (2, 1024, 960, True),
+                                         (2, 4096, 320, True), (1, 4096, 960, False), (3, 64, 1280, True), (2, 256, 640, True),
+                                         (1, 100, 64, True), (2, 16384, 32, False)])
 def test_groupnorm(nat, dbl, n, hw, C, silu):
     t = {"x": rnd(n * hw, C) * 2 + 0.5, "g": rnd(C, seed=1), "b": rnd(C, seed=2), "y": torch.zeros(n * hw, C, dtype=torch.float16),
          "ws": torch.zeros(max(n, 64) * 64, dtype=torch.float64)}
