@@ -333,6 +333,8 @@ extern "C" int mvd_attn_self_f16(const void* q, const void* k, const void* vt, v
   {
     const int cands[4] = {128, 64, 32, 16};
     int chosen = -1;
+    // a sequence of one or two 32-key tiles runs as two tiles, so that softmax(0) overlaps QK^T(1) (seq 64: 6.5 -> 5.3 us on B200)
+    if (seq == 64 && layout(32) <= 115712 && 32 + p.n_o <= 256) chosen = 32;
     for (int i = 0; i < 4 && chosen < 0; ++i)
       if (cands[i] <= seq && layout(cands[i]) <= 115712 && cands[i] + p.n_o <= 256) chosen = cands[i];
     for (int i = 0; i < 4 && chosen < 0; ++i)
