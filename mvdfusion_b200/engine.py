@@ -694,12 +694,14 @@ def emit_gridattn(b, *, noisy, input_latent, depth_override, depth_eps, scal, ca
            act=ACT_GELU)
     b.free(tokens)
     hd = Z_CH // num_heads
+    # adaLN_modulation (SiLU -> Linear(256, 6*256)) of every DiT block reads the same t embedding: one grouped launch
+    mods = [b.ops.empty((6 * Z_CH,), torch.float32) for _ in range(num_layers)]  # shift/scale/gate (msa), shift/scale/gate (mlp)
+    b.prog.append(b.ops.gemv_grouped(c_embed, Z_CH, [(W.lin(f"aggregation_transformer.layer_list.{i}.adaLN_modulation.1.weight"),
+                                                      W.f32(f"aggregation_transformer.layer_list.{i}.adaLN_modulation.1.bias"), mods[i])
+                                                     for i in range(num_layers)], silu_in=True))
     for i in range(num_layers):
         p = f"aggregation_transformer.layer_list.{i}"
-        mod = b.ops.empty((6 * Z_CH,), torch.float32)  # shift/scale/gate (msa), shift/scale/gate (mlp)
-        b.prog.append(b.ops.gemv(c_embed, W.lin(p + ".adaLN_modulation.1.weight"), W.f32(p + ".adaLN_modulation.1.bias"), mod,
-                                 1, 6 * Z_CH, Z_CH, ldy=6 * Z_CH, silu_in=True))
-        ch = [mod[j * Z_CH:(j + 1) * Z_CH] for j in range(6)]
+        ch = [mods[i][j * Z_CH:(j + 1) * Z_CH] for j in range(6)]
         a = b.t16(R, Z_CH)
         b.prog.append(b.ops.ln_modulate(x, ch[0], ch[1], a, R, Z_CH, 1e-6))
         qkv = b.t16(R, 3 * Z_CH)
