@@ -319,7 +319,18 @@ __global__ void view_attention_kernel(const __half* __restrict__ qkv, __half* __
   }
 }
 
-// Staged variant (heads * V divides 256): a CTA of 256 threads owns 256 / (heads * V) consecutive points.  The q | k | v rows
+// acc += a.lo * b.lo + a.hi * b.hi   (half2 operands, fp32 accumulator; two FHFMA)
+__device__ __forceinline__ void dot2_f16(float& acc, uint32_t a2, uint32_t b2) {
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"
+      "fma.rn.f32.f16 %0, al, bl, %0;\n\tfma.rn.f32.f16 %0, ah, bh, %0;\n\t}\n" : "+f"(acc) : "r"(a2), "r"(b2));
+}
+// acc0 += p * v.lo ; acc1 += p * v.hi   (p duplicated in both halves of p2)
+__device__ __forceinline__ void axpy2_f16(float& acc0, float& acc1, uint32_t p2, uint32_t v2) {
+  asm("{\n\t.reg .b16 pl, ph, vl, vh;\n\tmov.b32 {pl, ph}, %2;\n\tmov.b32 {vl, vh}, %3;\n\t"
+      "fma.rn.f32.f16 %0, pl, vl, %0;\n\tfma.rn.f32.f16 %1, ph, vh, %1;\n\t}\n" : "+f"(acc0), "+f"(acc1) : "r"(p2), "r"(v2));
+}
+
+// Staged variant (heads * V divides 256, V <= 16): a CTA of 256 threads owns 256 / (heads * V) consecutive points.  The q | k | v rows
 // of a point are one contiguous block of V * 3C halves, so the CTA pulls its 32 rows (48 KB) into shared memory with
 // fully coalesced 16-byte loads, every thread = (point, head, query view) then works out of shared memory (k / v reads are
 // broadcasts across the query views), and writes its 64-byte output segment.
@@ -347,58 +358,63 @@ __global__ void __launch_bounds__(256)
   const int pl = t / (V * heads);
   if (pl >= npts) return;
   const __half* base = reinterpret_cast<const __half*>(va_smem) + static_cast<size_t>(pl) * V * ld;
-  float q[HD];
+  // q stays packed (half2); products run on sm_100's mixed-precision FMA (fp16 x fp16 -> exact, accumulated in fp32: FHFMA),
+  // so no operand is ever converted.  Two passes over the <= 16 keys: scores -> maximum -> P = exp2(s - m) rounded to fp16
+  // (as in the tensor-core attention; l is the sum of the rounded values) -> P V.
+  uint32_t qh[HD / 2];
   {
     const uint4* qp = reinterpret_cast<const uint4*>(base + qi * ld + h * HD);
 #pragma unroll
     for (int i = 0; i < HD / 8; ++i) {
       const uint4 u = qp[i];
-      const __half2* hp = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(hp[j]);
-        q[i * 8 + 2 * j] = f.x;
-        q[i * 8 + 2 * j + 1] = f.y;
-      }
+      qh[i * 4] = u.x; qh[i * 4 + 1] = u.y; qh[i * 4 + 2] = u.z; qh[i * 4 + 3] = u.w;
     }
   }
   const float scale_log2 = rsqrtf(static_cast<float>(HD)) * 1.4426950408889634f;
-  float m = -INFINITY, l = 0.f;
+  constexpr int MAXV = 16;
+  float sc[MAXV];
+  float m = -INFINITY;
+#pragma unroll
+  for (int kj = 0; kj < MAXV; ++kj) {
+    if (kj < V) {
+      const uint4* kp = reinterpret_cast<const uint4*>(base + kj * ld + C + h * HD);
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) {
+        const uint4 u = kp[i];
+        dot2_f16(s0, qh[i * 4], u.x);
+        dot2_f16(s1, qh[i * 4 + 1], u.y);
+        dot2_f16(s0, qh[i * 4 + 2], u.z);
+        dot2_f16(s1, qh[i * 4 + 3], u.w);
+      }
+      sc[kj] = (s0 + s1) * scale_log2;
+      m = fmaxf(m, sc[kj]);
+    } else {
+      sc[kj] = -INFINITY;
+    }
+  }
+  float l = 0.f;
   float acc[HD];
 #pragma unroll
   for (int i = 0; i < HD; ++i) acc[i] = 0.f;
-  for (int kj = 0; kj < V; ++kj) {
-    const uint4* kp = reinterpret_cast<const uint4*>(base + kj * ld + C + h * HD);
-    float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < HD / 8; ++i) {
-      const uint4 u = kp[i];
-      const __half2* hp = reinterpret_cast<const __half2*>(&u);
+  for (int kj = 0; kj < MAXV; ++kj) {
+    if (kj < V) {
+      float pe;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(sc[kj] - m));
+      const __half ph = __float2half_rn(pe);
+      l += __half2float(ph);
+      const uint32_t p2 = static_cast<uint32_t>(__half_as_ushort(ph)) * 0x10001u;
+      const uint4* vp = reinterpret_cast<const uint4*>(base + kj * ld + 2 * C + h * HD);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(hp[j]);
-        s = fmaf(q[i * 8 + 2 * j], f.x, s);
-        s = fmaf(q[i * 8 + 2 * j + 1], f.y, s);
+      for (int i = 0; i < HD / 8; ++i) {
+        const uint4 u = vp[i];
+        axpy2_f16(acc[i * 8 + 0], acc[i * 8 + 1], p2, u.x);
+        axpy2_f16(acc[i * 8 + 2], acc[i * 8 + 3], p2, u.y);
+        axpy2_f16(acc[i * 8 + 4], acc[i * 8 + 5], p2, u.z);
+        axpy2_f16(acc[i * 8 + 6], acc[i * 8 + 7], p2, u.w);
       }
     }
-    s *= scale_log2;
-    const float m_new = fmaxf(m, s);
-    const float corr = exp2f(m - m_new);
-    const float pexp = exp2f(s - m_new);
-    l = l * corr + pexp;
-    const uint4* vp = reinterpret_cast<const uint4*>(base + kj * ld + 2 * C + h * HD);
-#pragma unroll
-    for (int i = 0; i < HD / 8; ++i) {
-      const uint4 u = vp[i];
-      const __half2* hp = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(hp[j]);
-        acc[i * 8 + 2 * j] = acc[i * 8 + 2 * j] * corr + pexp * f.x;
-        acc[i * 8 + 2 * j + 1] = acc[i * 8 + 2 * j + 1] * corr + pexp * f.y;
-      }
-    }
-    m = m_new;
   }
   const float inv = 1.f / l;
   __half* o = out + ((p0 + pl) * V + qi) * C + h * HD;
@@ -592,7 +608,7 @@ extern "C" int mvd_view_attention_f16(const void* qkv, void* out, int32_t P, int
   if (!qkv || !out || P <= 0 || V <= 0 || heads <= 0) return set_error(MVD_EINVAL, "mvd_view_attention_f16: bad arguments");
   if (hd != 32) return set_error(MVD_EINVAL, "mvd_view_attention_f16: head dim must be 32");
   const size_t total = static_cast<size_t>(P) * heads * V;
-  if (256 % (heads * V) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+  if (256 % (heads * V) == 0 && V <= 16 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     const int pts = 256 / (heads * V);
     const size_t smem = static_cast<size_t>(pts) * V * 3 * heads * 32 * sizeof(__half);
     static bool configured = false;

@@ -183,68 +183,109 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------- LayerNorm family
 // One warp per row, C <= 1280 and a multiple of 4.  mode 0: affine (gamma, beta); mode 1: adaLN
 // modulate y = n * (1 + scale[c]) + shift[c] (no affine).
-template <int MODE>
+// NV = float4 slots per lane (covers C <= 128 * NV): sized to the row so that narrow rows do not pay for 10 slots of registers
+template <int MODE, int RPW, int NV>
 __global__ void ln_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
                           __half* __restrict__ y, int rows, int C, float eps) {
   pdl_trigger();
   pdl_wait();
   const int warps_per_block = blockDim.x >> 5;
-  const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int row0 = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * RPW;  // RPW consecutive rows per warp: all their loads in flight together
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float* xr = x + static_cast<size_t>(row) * C;
-  float4 v[10];
-  float s = 0.f;
+  if (row0 >= rows) return;
+  float4 v[RPW][NV];
+  float s[RPW];
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    if (c < C) {
-      v[i] = *reinterpret_cast<const float4*>(xr + c);
-      s += v[i].x + v[i].y + v[i].z + v[i].w;
+  for (int r = 0; r < RPW; ++r) {
+    s[r] = 0.f;
+    const float* xr = x + static_cast<size_t>(min(row0 + r, rows - 1)) * C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) v[r][i] = *reinterpret_cast<const float4*>(xr + c);
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / C;
-  float q = 0.f;
+  for (int r = 0; r < RPW; ++r) {
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    if (c < C) {
-      const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
-      q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) s[r] += v[r][i].x + v[r][i].y + v[r][i].z + v[r][i].w;
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / C + eps);
-  __half* yr = y + static_cast<size_t>(row) * C;
+  for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+    for (int r = 0; r < RPW; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+  }
+  float mean[RPW], q[RPW];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    mean[r] = s[r] / C;
+    q[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) {
+        const float d0 = v[r][i].x - mean[r], d1 = v[r][i].y - mean[r], d2 = v[r][i].z - mean[r], d3 = v[r][i].w - mean[r];
+        q[r] += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < C) {
       const float4 ga = *reinterpret_cast<const float4*>(a + c);
       const float4 be = *reinterpret_cast<const float4*>(b + c);
-      float o0, o1, o2, o3;
-      if (MODE == 0) {
-        o0 = (v[i].x - mean) * rstd * ga.x + be.x;
-        o1 = (v[i].y - mean) * rstd * ga.y + be.y;
-        o2 = (v[i].z - mean) * rstd * ga.z + be.z;
-        o3 = (v[i].w - mean) * rstd * ga.w + be.w;
-      } else {  // a = scale, b = shift
-        o0 = (v[i].x - mean) * rstd * (1.f + ga.x) + be.x;
-        o1 = (v[i].y - mean) * rstd * (1.f + ga.y) + be.y;
-        o2 = (v[i].z - mean) * rstd * (1.f + ga.z) + be.z;
-        o3 = (v[i].w - mean) * rstd * (1.f + ga.w) + be.w;
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        if (row0 + r >= rows) continue;
+        const float rstd = rsqrtf(q[r] / C + eps);
+        float o0, o1, o2, o3;
+        if (MODE == 0) {
+          o0 = (v[r][i].x - mean[r]) * rstd * ga.x + be.x;
+          o1 = (v[r][i].y - mean[r]) * rstd * ga.y + be.y;
+          o2 = (v[r][i].z - mean[r]) * rstd * ga.z + be.z;
+          o3 = (v[r][i].w - mean[r]) * rstd * ga.w + be.w;
+        } else {  // a = scale, b = shift
+          o0 = (v[r][i].x - mean[r]) * rstd * (1.f + ga.x) + be.x;
+          o1 = (v[r][i].y - mean[r]) * rstd * (1.f + ga.y) + be.y;
+          o2 = (v[r][i].z - mean[r]) * rstd * (1.f + ga.z) + be.z;
+          o3 = (v[r][i].w - mean[r]) * rstd * (1.f + ga.w) + be.w;
+        }
+        __half2 h0 = __floats2half2_rn(o0, o1);
+        __half2 h1 = __floats2half2_rn(o2, o3);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(y + static_cast<size_t>(row0 + r) * C + c) = u;
       }
-      __half2 h0 = __floats2half2_rn(o0, o1);
-      __half2 h1 = __floats2half2_rn(o2, o3);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&h0);
-      u.y = *reinterpret_cast<uint32_t*>(&h1);
-      *reinterpret_cast<uint2*>(yr + c) = u;
     }
   }
+}
+
+// one row per warp; register slots sized to the row width (C = 320: 6.0 us instead of 10.0 us at 16384 rows, occupancy)
+template <int MODE>
+static cudaError_t ln_launch(const float* x, const float* a, const float* b, __half* y, int rows, int C, float eps, cudaStream_t stream) {
+  static const int force = getenv("MVD_LN_RPW") ? atoi(getenv("MVD_LN_RPW")) : 0;  // measurement override
+  const int rpw = force ? force : 1;  // measured on B200: one row per warp wins at every shape of the step (tests/native/norm_bench)
+  const dim3 grid2((rows + 15) / 16), grid1((rows + 7) / 8), block(256);
+  if (C <= 384) {
+    if (rpw == 2) return launch_kernel(ln_kernel<MODE, 2, 3>, grid2, block, 0, stream, 1, x, a, b, y, rows, C, eps);
+    return launch_kernel(ln_kernel<MODE, 1, 3>, grid1, block, 0, stream, 1, x, a, b, y, rows, C, eps);
+  }
+  if (C <= 640) {
+    if (rpw == 2) return launch_kernel(ln_kernel<MODE, 2, 5>, grid2, block, 0, stream, 1, x, a, b, y, rows, C, eps);
+    return launch_kernel(ln_kernel<MODE, 1, 5>, grid1, block, 0, stream, 1, x, a, b, y, rows, C, eps);
+  }
+  if (rpw == 2) return launch_kernel(ln_kernel<MODE, 2, 10>, grid2, block, 0, stream, 1, x, a, b, y, rows, C, eps);
+  return launch_kernel(ln_kernel<MODE, 1, 10>, grid1, block, 0, stream, 1, x, a, b, y, rows, C, eps);
 }
 
 }  // namespace mvd
@@ -331,7 +372,7 @@ extern "C" int mvd_layernorm_f32_f16(const float* x, const float* gamma, const f
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !gamma || !beta || !y) return set_error(MVD_EINVAL, "mvd_layernorm_f32_f16: null pointer");
   if (rows <= 0 || C <= 0 || (C & 3) != 0 || C > 1280) return set_error(MVD_EINVAL, "mvd_layernorm_f32_f16: C must be a multiple of 4, <= 1280");
-  MVD_LAUNCH((ln_kernel<0>), (rows + 7) / 8, 256, 0, stream, x, gamma, beta, static_cast<__half*>(y), rows, C, eps);
+  MVD_CUDA_CHECK(ln_launch<0>(x, gamma, beta, static_cast<__half*>(y), rows, C, eps, stream));
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -342,7 +383,7 @@ extern "C" int mvd_ln_modulate_f32_f16(const float* x, const float* shift, const
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !shift || !scale || !y) return set_error(MVD_EINVAL, "mvd_ln_modulate_f32_f16: null pointer");
   if (rows <= 0 || C <= 0 || (C & 3) != 0 || C > 1280) return set_error(MVD_EINVAL, "mvd_ln_modulate_f32_f16: C must be a multiple of 4, <= 1280");
-  MVD_LAUNCH((ln_kernel<1>), (rows + 7) / 8, 256, 0, stream, x, scale, shift, static_cast<__half*>(y), rows, C, eps);
+  MVD_CUDA_CHECK(ln_launch<1>(x, scale, shift, static_cast<__half*>(y), rows, C, eps, stream));
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
