@@ -23,7 +23,7 @@ namespace mvd {
 //   per-thread fp32 partial sums -> smem [row][span] -> one warp per group sums them in fp64 -> cluster barrier ->
 //   every CTA adds up its peers' group sums through distributed shared memory -> normalise, gamma / beta (+SiLU), fp16.
 template <int MAXP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MAXP == 16 ? 2 : (MAXP == 4 ? 4 : 3))  // register budget sized to the pixels a thread keeps: occupancy is what hides the latency here
     gn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ x2, int C1, const float* __restrict__ gamma,
                       const float* __restrict__ beta, __half* __restrict__ y, int hw, int C, int cpg, int gpc, int rows, int csplit,
                       float eps, int apply_silu) {
@@ -55,6 +55,14 @@ __global__ void __launch_bounds__(256)
   const int pstep = rows * csplit;         // pixel stride of one thread
   const int p_first = row * csplit + rank;  // its first pixel
 
+  // gamma / beta do not depend on the predecessor kernel: they are in flight before the dependency wait and long before the
+  // statistics are done (fetched after the cluster barrier they cost one more memory round trip per launch)
+  float ga[4], be[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    ga[k] = active ? __ldg(gamma + c0 + cq * 4 + k) : 0.f;
+    be[k] = active ? __ldg(beta + c0 + cq * 4 + k) : 0.f;
+  }
   pdl_wait();
   constexpr int NV = MAXP > 0 ? MAXP : 8;  // MAXP == 0: any number of pixels per thread, eight at a time, re-read for the output
   float4 v[NV];
@@ -145,9 +153,8 @@ __global__ void __launch_bounds__(256)
     for (int k = 0; k < 4; ++k) {
       const int cl = cq * 4 + k;
       const int g = cl / cpg;
-      const float ga = __ldg(gamma + c0 + cl);
-      sc[k] = s_rstd[g] * ga;
-      sh[k] = __ldg(beta + c0 + cl) - s_mean[g] * s_rstd[g] * ga;
+      sc[k] = s_rstd[g] * ga[k];
+      sh[k] = be[k] - s_mean[g] * s_rstd[g] * ga[k];
     }
     uint2* dst = reinterpret_cast<uint2*>(y + static_cast<size_t>(img) * hw * C + c0) + cq;
     const size_t out_stride4 = static_cast<size_t>(C) >> 2;
@@ -205,6 +212,20 @@ __global__ void ln_kernel(const float* __restrict__ x, const float* __restrict__
       if (c < C) v[r][i] = *reinterpret_cast<const float4*>(xr + c);
     }
   }
+  // wide rows run as a few latency-bound blocks: their gamma / beta loads go out together with the row instead of after the
+  // two reductions (narrow rows keep the registers for occupancy: those launches are bandwidth-bound)
+  constexpr bool EARLY_AFFINE = NV >= 10;
+  float4 ga_[EARLY_AFFINE ? NV : 1], be_[EARLY_AFFINE ? NV : 1];
+  if (EARLY_AFFINE) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) {
+        ga_[i] = __ldg(reinterpret_cast<const float4*>(a + c));
+        be_[i] = __ldg(reinterpret_cast<const float4*>(b + c));
+      }
+    }
+  }
 #pragma unroll
   for (int r = 0; r < RPW; ++r) {
 #pragma unroll
@@ -237,16 +258,19 @@ __global__ void ln_kernel(const float* __restrict__ x, const float* __restrict__
 #pragma unroll
     for (int r = 0; r < RPW; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
   }
+  float rstd_[RPW];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) rstd_[r] = rsqrtf(q[r] / C + eps);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < C) {
-      const float4 ga = *reinterpret_cast<const float4*>(a + c);
-      const float4 be = *reinterpret_cast<const float4*>(b + c);
+      const float4 ga = EARLY_AFFINE ? ga_[i] : *reinterpret_cast<const float4*>(a + c);
+      const float4 be = EARLY_AFFINE ? be_[i] : *reinterpret_cast<const float4*>(b + c);
 #pragma unroll
       for (int r = 0; r < RPW; ++r) {
         if (row0 + r >= rows) continue;
-        const float rstd = rsqrtf(q[r] / C + eps);
+        const float rstd = rstd_[r];
         float o0, o1, o2, o3;
         if (MODE == 0) {
           o0 = (v[r][i].x - mean[r]) * rstd * ga.x + be.x;
@@ -344,6 +368,8 @@ static int groupnorm_launch(const float* x, const float* x2, int C1, const float
     MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<4>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu));
   else if (best_pp <= 8)
     MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<8>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu));
+  else if (best_pp <= 12)
+    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<12>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu));
   else if (best_pp > 16)  // large images (64x64 latents and up): pixels stream through in batches and are read twice
     MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<0>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu));
   else
