@@ -135,6 +135,7 @@ class DDIMSampler:
             x_h = pin(torch.empty(total, plan.q, 5, S, S))
         else:
             plan.set_tables(rows, depth_eps, ddim_noise)
+        copied = None
         for i in range(total):
             if host_io:
                 plan.host_step(stream, rows_h[i], de_h[i], dn_h[i], use_graph=use_graph)
@@ -143,12 +144,22 @@ class DDIMSampler:
             if group is not None:
                 model.gather_views(plan)
             if host_io:
+                # the step's x_t lands in pinned host memory on the stream; the host only waits for the PREVIOUS step's
+                # copy, so that it has step i+1 (H2D of its inputs + graph launch) queued while step i still runs
                 x_h[i].copy_(plan.x_local.reshape(plan.q, 5, S, S), non_blocking=True)
                 if device.type == "cuda":
-                    torch.cuda.current_stream(device).synchronize()
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream(device))
+                    if copied is not None:
+                        copied.synchronize()
+                    copied = ev
             if return_intermediates:
                 inter.append({"t": int(self.ddim_timesteps[total - i - 1]), "xt": plan.x.reshape(B, 5, S, S).clone(),
                               "x0": plan.x0_out.reshape(-1, 5, S, S).clone()})
+        if copied is not None:
+            copied.synchronize()
+        if host_io:
+            self.host_trajectory = x_h  # (steps, views, 5, S, S): every step's x_t as it arrived in pinned host memory
         out = plan.x.reshape(B, 5, S, S).clone()
         return (out, inter) if return_intermediates else out
 

@@ -82,6 +82,24 @@ def test_ddim_loop_small_vs_reference_golden(small, use_graph):
     assert record_parity(f"ddim4_x0_vs_reference_golden_graph{int(use_graph)}", rel_l2(x, gold["x0"]), 2 * TOL) < 2 * TOL
 
 
+def test_ddim_loop_host_streamed_inputs_match_the_device_tables(small):
+    """host_io=True (per-step inputs copied from pinned host memory, every x_t read back into pinned host memory, the host
+    running one step ahead of the read-back) gives the same trajectory as the device-table loop, bit for bit"""
+    m, _ = small
+    m.ddim._make_schedule(4, "uniform", 1.0)
+    sc = synthetic.scene_inputs(2, 32, seed=0)
+    de, dn = synthetic.step_noises(2, 1, 32, 4, seed=1)
+    args = (cams_of(sc["cams"], "cuda"), sc["input_latents"].cuda(), cams_of(sc["in_cams"], "cuda"), sc["clip_v_embed"].cuda())
+    kw = dict(unconditional_scale=2.5, depth=True, verbose=False, x_T=sc["x_T"], depth_eps=de, ddim_noise=dn)
+    x_dev, inter = m.ddim.sample(*args, return_intermediates=True, **kw)
+    x_host = m.ddim.sample(*args, host_io=True, **kw)
+    assert torch.equal(x_dev, x_host)
+    traj = m.ddim.host_trajectory
+    assert traj.is_pinned() and traj.shape[0] == 4
+    for i, it in enumerate(inter):
+        assert torch.equal(traj[i], it["xt"].cpu())
+
+
 @pytest.mark.parametrize("D", [1, 3])
 def test_gridattn_module_vs_oracle(D):
     N, S = 3, 32
