@@ -68,7 +68,7 @@ typedef struct mvd_gemm_args {
   int32_t a_mode;
   const void* A;       /* fp16 */
   int32_t lda;         /* elements; ROWMAJOR only (multiple of 8) */
-  int32_t n_img, H, W, C; /* CONV3X3 only; C multiple of 8, W a power of two <= 128 */
+  int32_t n_img, H, W, C; /* CONV3X3 only; C multiple of 8, W a power of two (rows wider than 128 pixels are tiled in 128-pixel segments) */
   const void* Wt;      /* fp16 [N, ldw] */
   int32_t ldw;         /* elements, multiple of 8, >= K */
   const float* bias;   /* [N] or NULL */
@@ -131,6 +131,10 @@ int mvd_layernorm_f32_f16(const float* x, const float* gamma, const float* beta,
                           float eps, void* stream);
 int mvd_ln_modulate_f32_f16(const float* x, const float* shift, const float* scale, void* y, int32_t rows, int32_t C,
                             float eps, void* stream);
+/* p[r, :cols] = softmax(scale * s[r, :cols]) as fp16: the VAE decoder's single-head attention weights
+ * (external/sd1/ldm/modules/diffusionmodules/model.py:186-190, w_ = softmax(q k^T c^-1/2)); s fp32 [rows, ld_in], p fp16 [rows, ld_out] */
+int mvd_softmax_rows_f32_f16(const float* s, void* p, int32_t rows, int32_t cols, int32_t ld_in, int32_t ld_out, float scale,
+                             void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Data movement / elementwise.

@@ -9,7 +9,7 @@ from ctypes import c_char_p, c_float, c_int32, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmvd_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class GemmArgs(ctypes.Structure):
@@ -46,6 +46,7 @@ SIGNATURES = {
     "mvd_groupnorm2_f32_f16": [vp, i32, vp, i32, vp, vp, vp, i32, i32, f32, i32, vp],
     "mvd_layernorm_f32_f16": [vp, vp, vp, vp, i32, i32, f32, vp],
     "mvd_ln_modulate_f32_f16": [vp, vp, vp, vp, i32, i32, f32, vp],
+    "mvd_softmax_rows_f32_f16": [vp, vp, i32, i32, i32, i32, f32, vp],
     "mvd_cast_f32_f16": [vp, vp, i64, vp],
     "mvd_concat_f32": [vp, vp, vp, i64, i32, i32, vp],
     "mvd_concat_f32_f16": [vp, vp, vp, i64, i32, i32, vp],

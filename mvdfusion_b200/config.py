@@ -2,8 +2,9 @@
 
 `target:` strings written for the reference (`mvdfusion.viewfusion_zero_depth_rgb.ViewFusion`, `mvdfusion.unet.UNetModel`,
 …) resolve to this package's mirror modules, so the reference's configs/*.yaml load unchanged.
-Targets outside the hot path (the VAE under external.sd1…, CLIP) resolve to None unless the reference package itself is
-importable: those components are out of scope and the facade reports them as absent.
+`external.sd1.ldm.models.autoencoder.AutoencoderKL` resolves to this package's decode-side VAE.  Other targets outside the hot
+path (CLIP, ...) resolve to None unless the reference package itself is importable: those components are out of scope
+ and the facade reports them as absent.
 """
 import importlib
 from collections import OrderedDict
@@ -11,7 +12,9 @@ from collections import OrderedDict
 import torch
 import yaml
 
-_ALIASES = {"mvdfusion.": "mvdfusion_b200.mvdfusion."}
+_ALIASES = {"mvdfusion.": "mvdfusion_b200.mvdfusion.",
+            # the VAE (decode side): configs/mvd_gso.yaml:53-54
+            "external.sd1.ldm.models.autoencoder.": "mvdfusion_b200.mvdfusion.autoencoder."}
 _OUT_OF_SCOPE_PREFIXES = ("external.sd1.",)
 
 
@@ -24,7 +27,7 @@ def get_obj_from_str(string):
     module, cls = string.rsplit(".", 1)
     for src, dst in _ALIASES.items():
         if module.startswith(src) or module + "." == src:
-            module = dst + module[len(src):]
+            module = (dst + module[len(src):]).rstrip(".")
             break
     return getattr(importlib.import_module(module), cls)
 
@@ -33,7 +36,7 @@ def instantiate_from_config(config):
     if "target" not in config:
         raise KeyError("Expected key `target` to instantiate.")
     target = config["target"]
-    if target.startswith(_OUT_OF_SCOPE_PREFIXES):
+    if target.startswith(_OUT_OF_SCOPE_PREFIXES) and not any(target.startswith(a) for a in _ALIASES):
         try:
             module, cls = target.rsplit(".", 1)
             return getattr(importlib.import_module(module), cls)(**(config.get("params") or {}))

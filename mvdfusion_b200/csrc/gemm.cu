@@ -147,7 +147,7 @@ __device__ __forceinline__ Unit decode_unit(const GemmKParams& p, int u, int pai
     t.x0 = tx * p.tw;
     t.y0 = ty * p.th;
     t.img0 = tz * p.tn;
-    t.grow0 = (t.img0 * p.H + t.y0) * p.W + t.x0;  // tiles are full-width rows of whole images: 128 contiguous output rows
+    t.grow0 = (t.img0 * p.H + t.y0) * p.W + t.x0;  // full-width rows of whole images, or a 128-pixel row segment: 128 contiguous output rows
   } else {
     t.grow0 = t.m_tile * BM;
   }
@@ -759,11 +759,12 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   // m-tiles of the problem (conv tiles are whole image rows: see the geometry block below)
   int tiles_m_real;
   if (a->a_mode == MVD_A_CONV3X3) {
-    if (a->n_img <= 0 || a->H <= 0 || a->W <= 0 || !is_pow2(a->W) || a->W > 128) return set_error(MVD_EINVAL, "mvd_gemm_f16: bad CONV3X3 geometry");
-    int th = BM / a->W;
+    if (a->n_img <= 0 || a->H <= 0 || a->W <= 0 || !is_pow2(a->W) || a->W > 4096) return set_error(MVD_EINVAL, "mvd_gemm_f16: bad CONV3X3 geometry");
+    const int tw = a->W < BM ? a->W : BM;  // rows wider than a tile are cut into 128-pixel segments
+    int th = BM / tw;
     if (th > a->H) th = a->H;
-    const int tn = BM / (a->W * th);
-    tiles_m_real = (a->H / (th > 0 ? th : 1)) * ((a->n_img + tn - 1) / tn);
+    const int tn = BM / (tw * th);
+    tiles_m_real = (a->W / tw) * (a->H / th) * ((a->n_img + tn - 1) / tn);
   } else {
     tiles_m_real = (a->M + BM - 1) / BM;
   }
@@ -805,19 +806,19 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     int rc = make_tmap_2d(&tmA, a->A, /*cols=*/a->K, /*rows=*/a->M, /*ld=*/a->lda, BK, BM);
     if (rc != MVD_OK) return rc;
   } else if (a->a_mode == MVD_A_CONV3X3) {
-    if (a->n_img <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || (a->C & 7) != 0 || !is_pow2(a->W) || a->W > 128 ||
-        a->K != 9 * a->C || a->M != a->n_img * a->H * a->W)
+    if (a->n_img <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || (a->C & 7) != 0 || !is_pow2(a->W) || a->W > 4096 ||
+        a->K != 9 * a->C || static_cast<long long>(a->M) != static_cast<long long>(a->n_img) * a->H * a->W)
       return set_error(MVD_EINVAL, "mvd_gemm_f16: bad CONV3X3 geometry");
     p.n_img = a->n_img;
     p.H = a->H;
     p.W = a->W;
     p.C = a->C;
-    p.tw = a->W;
+    p.tw = a->W < BM ? a->W : BM;  // W > 128 (the VAE decoder's 256-wide maps): a tile is a 128-pixel segment of one image row
     p.th = BM / p.tw;
     if (p.th > a->H) p.th = a->H;
     if (!is_pow2(p.th) || (a->H % p.th) != 0) return set_error(MVD_EINVAL, "mvd_gemm_f16: CONV3X3 needs H a multiple of the tile height");
     p.tn = BM / (p.tw * p.th);
-    p.tiles_x = 1;
+    p.tiles_x = a->W / p.tw;
     p.tiles_y = a->H / p.th;
     const int tiles_z = (a->n_img + p.tn - 1) / p.tn;
     p.tiles_m_real = p.tiles_x * p.tiles_y * tiles_z;

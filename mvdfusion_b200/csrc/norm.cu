@@ -312,6 +312,48 @@ static cudaError_t ln_launch(const float* x, const float* a, const float* b, __h
   return launch_kernel(ln_kernel<MODE, 1, 10>, grid1, block, 0, stream, 1, x, a, b, y, rows, C, eps);
 }
 
+// ---------------------------------------------------------------------------- row softmax
+// p[r, :] = softmax(scale * s[r, :]) as fp16 (the P operand of the P V product).  One warp per row; the row is read three
+// times (maximum, sum, output) — it is L2-resident, and this runs once per scene, in the VAE decoder's single-head 512-wide
+// attention block (external/sd1/ldm/modules/diffusionmodules/model.py:186-190), not in the denoising loop.
+__global__ void softmax_rows_kernel(const float* __restrict__ s, __half* __restrict__ p, int rows, int cols, int ld_in, int ld_out,
+                                    float scale_log2) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* src = reinterpret_cast<const float4*>(s + static_cast<size_t>(row) * ld_in);
+  const int n4 = cols >> 2;
+  float m = -INFINITY;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = src[i];
+    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const float mc = m * scale_log2;
+  float l = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = src[i];
+    l += exp2f(fmaf(v.x, scale_log2, -mc)) + exp2f(fmaf(v.y, scale_log2, -mc)) + exp2f(fmaf(v.z, scale_log2, -mc)) +
+         exp2f(fmaf(v.w, scale_log2, -mc));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  const float inv = 1.f / l;
+  uint2* dst = reinterpret_cast<uint2*>(p + static_cast<size_t>(row) * ld_out);
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = src[i];
+    __half2 h0 = __floats2half2_rn(exp2f(fmaf(v.x, scale_log2, -mc)) * inv, exp2f(fmaf(v.y, scale_log2, -mc)) * inv);
+    __half2 h1 = __floats2half2_rn(exp2f(fmaf(v.z, scale_log2, -mc)) * inv, exp2f(fmaf(v.w, scale_log2, -mc)) * inv);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    dst[i] = u;
+  }
+}
+
 }  // namespace mvd
 
 using namespace mvd;
@@ -349,6 +391,22 @@ static int groupnorm_launch(const float* x, const float* x2, int C1, const float
     if (pref) break;
   }
   if (best_gpc == 0) return set_error(MVD_EINVAL, "mvd_groupnorm_f32_f16: unsupported shape (hw %d, C %d)", hw, C);
+  if (!best_pref && best_pp > 16) {
+    // large images (the VAE decoder's 128^2 / 256^2 maps) stream through whatever the slice: take the WIDEST slice of whole
+    // sectors that still gives a couple of CTAs per SM, so that a pixel contributes a long contiguous run instead of 16 bytes
+    for (int gpc = 32; gpc >= 1; gpc >>= 1) {
+      const int span = gpc * cpg;
+      if ((span & 7) != 0 || span / 4 > 256) continue;
+      if ((32 / gpc) * 8 * n_img >= 256 || gpc == 1) {
+        best_gpc = gpc;
+        best_split = 8;
+        best_rows = 256 / (span / 4);
+        if (best_rows > hw) best_rows = hw;
+        best_pp = (hw + best_rows * 8 - 1) / (best_rows * 8);
+        break;
+      }
+    }
+  }
   if (const char* ov = getenv("MVD_GN_GEOMETRY")) {  // "gpc,split": measurement override (tests/native/norm_bench)
     int og = 0, os = 0;
     if (sscanf(ov, "%d,%d", &og, &os) == 2 && og >= 1 && og <= 32 && 32 % og == 0 && ((og * cpg) & 3) == 0 && og * cpg / 4 <= 256 &&
@@ -410,6 +468,21 @@ extern "C" int mvd_ln_modulate_f32_f16(const float* x, const float* shift, const
   if (!x || !shift || !scale || !y) return set_error(MVD_EINVAL, "mvd_ln_modulate_f32_f16: null pointer");
   if (rows <= 0 || C <= 0 || (C & 3) != 0 || C > 1280) return set_error(MVD_EINVAL, "mvd_ln_modulate_f32_f16: C must be a multiple of 4, <= 1280");
   MVD_CUDA_CHECK(ln_launch<1>(x, scale, shift, static_cast<__half*>(y), rows, C, eps, stream));
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_softmax_rows_f32_f16(const float* s, void* p, int32_t rows, int32_t cols, int32_t ld_in, int32_t ld_out, float scale,
+                                        void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!s || !p) return set_error(MVD_EINVAL, "mvd_softmax_rows_f32_f16: null pointer");
+  if (rows <= 0 || cols <= 0 || (cols & 3) != 0 || ld_in < cols || ld_out < cols || (ld_in & 3) != 0 || (ld_out & 3) != 0)
+    return set_error(MVD_EINVAL, "mvd_softmax_rows_f32_f16: cols and the leading dimensions must be multiples of 4, ld >= cols");
+  if ((reinterpret_cast<uintptr_t>(s) & 15) || (reinterpret_cast<uintptr_t>(p) & 7))
+    return set_error(MVD_EALIGN, "mvd_softmax_rows_f32_f16: s must be 16-byte and p 8-byte aligned");
+  MVD_LAUNCH(softmax_rows_kernel, (rows + 7) / 8, 256, 0, stream, s, static_cast<__half*>(p), rows, cols, ld_in, ld_out,
+             scale * 1.4426950408889634f);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

@@ -734,3 +734,86 @@ def emit_pyramid(b, pyramid16, n_cond, S, D, C=CTX_DIM):
     """get_volume_feats_pyramid (unet.py:198-209): 'area' pooling of level 0 by 2, 4, 8 (conditional images only)."""
     for l in range(1, len(pyramid16)):
         b.prog.append(b.ops.frustum_pool(pyramid16[0], pyramid16[l], n_cond, S, D, C, 1 << l))
+
+
+# ------------------------------------------------------------------------------------------------ VAE decoder
+def _vae_resnet(b, x, p, n, H, Cin, Cout):
+    """ResnetBlock.forward with temb = None (external/sd1/ldm/modules/diffusionmodules/model.py:122-141):
+    GN(eps 1e-6)-swish-conv3x3, GN-swish-conv3x3, + x (through the 1x1 nin_shortcut when the width changes)."""
+    W, hw, M = b.W, H * H, n * H * H
+    a = b.groupnorm(x, p + ".norm1", n, hw, Cin, 1e-6, True)
+    h = b.conv3x3(a, p + ".conv1.weight", n, H, H, Cin, Cout, bias=W.f32(p + ".conv1.bias"))
+    b.free(a)
+    a = b.groupnorm(h, p + ".norm2", n, hw, Cout, 1e-6, True)
+    b.free(h)
+    res, s = x, None
+    if W.has(p + ".nin_shortcut.weight"):
+        x16 = b.cast16(x, M, Cin)
+        s = b.t32(M, Cout)
+        b.gemm(x16, W.lin(p + ".nin_shortcut.weight"), s, M, Cout, Cin, allow_split=True, bias=W.f32(p + ".nin_shortcut.bias"))
+        b.free(x16)
+        res = s
+    out = b.conv3x3(a, p + ".conv2.weight", n, H, H, Cout, Cout, bias=W.f32(p + ".conv2.bias"), residual=res)
+    b.free(a, s, x)
+    return out
+
+
+def _vae_attn(b, x, p, n, S, C):
+    """AttnBlock.forward (model.py:176-202): one head of width C over the S*S pixels of each image.  q | k | v are one fused
+    GEMM whose epilogue leaves q, k as [n, seq, C] and v transposed as [n, C, seq]; per image S = q k^T (fp32), row softmax
+    with the c^-1/2 scale, O = P V; proj_out adds the residual."""
+    W, seq = b.W, S * S
+    M = n * seq
+    a = b.groupnorm(x, p + ".norm", n, seq, C, 1e-6, False)
+    wqkv = W._put("vae_qkv_w", p, lambda: W._pad_k(torch.cat([W.raw(p + ".q.weight"), W.raw(p + ".k.weight"), W.raw(p + ".v.weight")], 0)
+                                                 .float().reshape(3 * C, C)).half())
+    bqkv = W._put("vae_qkv_b", p, lambda: torch.cat([W.raw(p + ".q.bias"), W.raw(p + ".k.bias"), W.raw(p + ".v.bias")], 0).float())
+    q, k, vt = b.t16(M, C), b.t16(M, C), b.t16(n * C, seq)
+    b.gemm(a, wqkv, q, M, 3 * C, C, bias=bqkv, qkv=dict(out_k=k, out_vt=vt, heads=1, dhead=C, dpad=C, seq=seq))
+    b.free(a)
+    sc, pr, o = b.t32(seq, seq), b.t16(seq, seq), b.t16(M, C)
+    for i in range(n):
+        b.gemm(q[i * seq:(i + 1) * seq], k[i * seq:(i + 1) * seq], sc, seq, seq, C)
+        b.prog.append(b.ops.softmax_rows(sc, pr, seq, seq, float(C) ** -0.5))
+        b.gemm(pr, vt[i * C:(i + 1) * C], o[i * seq:(i + 1) * seq], seq, C, seq)
+    b.free(q, k, vt, sc, pr)
+    out = b.t32(M, C)
+    b.gemm(o, W.lin(p + ".proj_out.weight"), out, M, C, C, allow_split=True, bias=W.f32(p + ".proj_out.bias"), residual=x, ldr=C)
+    b.free(o, x)
+    return out
+
+
+def emit_vae_decoder(b, z_nchw, n, S, ch, ch_mult, num_res_blocks, z_channels=4, out_ch=3):
+    """AutoencoderKL.decode (external/sd1/ldm/models/autoencoder.py:331-334) = post_quant_conv (1x1) -> Decoder.forward
+    (model.py:541-577).  z_nchw: fp32 [n, z_channels, S*S].  Returns (fp32 rows [n*(S*2^(L-1))^2, 4] of which out_ch columns are
+    written, output side).  The reference rounds the final normalised activation to fp16 before swish + conv_out
+    (model.py:563-569); here GroupNorm + swish are one kernel that writes the fp16 conv operand, which differs from that
+    by one fp16 rounding of an fp16-rounded value."""
+    W, ops = b.W, b.ops
+    M = n * S * S
+    z16 = ops.zeros((M, 16), torch.float16)   # NHWC with the channel dim padded to 16 (padding stays zero)
+    zq16 = ops.zeros((M, 16), torch.float16)
+    b.prog.append(ops.nchw_to_nhwc16(z_nchw, z16, n, z_channels, S * S, 16))
+    b.gemm(z16, W.lin("post_quant_conv.weight", k_pad=16), zq16, M, z_channels, 16, bias=W.f32("post_quant_conv.bias"), ldc=16)
+    C = ch * ch_mult[-1]
+    h = b.conv3x3(zq16, "decoder.conv_in.weight", n, S, S, z_channels, C, bias=W.f32("decoder.conv_in.bias"), c_pad=16)
+    h = _vae_resnet(b, h, "decoder.mid.block_1", n, S, C, C)
+    h = _vae_attn(b, h, "decoder.mid.attn_1", n, S, C)
+    h = _vae_resnet(b, h, "decoder.mid.block_2", n, S, C, C)
+    H = S
+    for lvl in reversed(range(len(ch_mult))):
+        Cout = ch * ch_mult[lvl]
+        for j in range(num_res_blocks + 1):
+            h = _vae_resnet(b, h, f"decoder.up.{lvl}.block.{j}", n, H, C, Cout)
+            C = Cout
+        if lvl != 0:
+            u = b.upsample(h, f"decoder.up.{lvl}.upsample", n, H, C)
+            b.free(h)
+            h = u
+            H *= 2
+    a = b.groupnorm(h, "decoder.norm_out", n, H * H, C, 1e-6, True)
+    b.free(h)
+    out = ops.empty((n * H * H, 4), torch.float32)
+    b.conv3x3(a, "decoder.conv_out.weight", n, H, H, C, out_ch, bias=W.f32("decoder.conv_out.bias"), ldc=4, out=out)
+    b.free(a)
+    return out, H

@@ -162,6 +162,11 @@ class NativeOps:
                                                       _ptr(scale, torch.float32), _ptr(y, torch.float16), rows, C, eps),
                           (x, shift, scale, y))
 
+    def softmax_rows(self, s, p, rows, cols, scale, ld_in=None, ld_out=None):
+        return self._bind("mvd_softmax_rows_f32_f16", (_ptr(s, torch.float32), _ptr(p, torch.float16), rows, cols,
+                                                       ld_in if ld_in is not None else cols, ld_out if ld_out is not None else cols,
+                                                       float(scale)), (s, p), {"desc": f"rows{rows} cols{cols}", "bytes": 6.0 * rows * cols})
+
     # ------------------------------------------------------------------ data movement / elementwise
     def cast(self, x, y, n):
         return self._bind("mvd_cast_f32_f16", (_ptr(x, torch.float32), _ptr(y, torch.float16), n), (x, y),

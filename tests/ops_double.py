@@ -144,6 +144,14 @@ class TorchOpsDouble:
             y.reshape(-1)[: rows * C].copy_(F.layer_norm(v, (C,), gamma, beta, eps).reshape(-1).half())
         return self._call(fn)
 
+    def softmax_rows(self, s, p, rows, cols, scale, ld_in=None, ld_out=None):
+        li, lo = ld_in if ld_in is not None else cols, ld_out if ld_out is not None else cols
+
+        def fn():
+            x = s.reshape(-1)[: rows * li].reshape(rows, li)[:, :cols].float()
+            p.reshape(-1)[: rows * lo].reshape(rows, lo)[:, :cols] = torch.softmax(x * scale, dim=-1).half()
+        return self._call(fn)
+
     def ln_modulate(self, x, shift, scale, y, rows, C, eps):
         def fn():
             v = x.reshape(-1)[: rows * C].reshape(rows, C)
