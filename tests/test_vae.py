@@ -71,6 +71,28 @@ def test_decode_host_logic_vs_oracle(ops_double):
     assert rel_l2(((y + 1.0) / 2.0).clip(0.0, 1.0), img) < TOL
 
 
+def test_viewfusion_decode_through_the_facade(ops_double):
+    """ViewFusion(vae_config=...) builds the VAE from the reference's yaml section; .decode(z) = unnormalize(vae.decode(z / 0.18215))"""
+    from common import model_config
+    from mvdfusion_b200.config import instantiate_from_config
+    e = torch.load(GOLD)["small"]
+    dd = e["ddconfig"]
+    cfg = model_config(64, 8, D=1, S=8)
+    cfg["params"]["vae_config"] = {"target": "external.sd1.ldm.models.autoencoder.AutoencoderKL",
+                                   "params": {"embed_dim": 4, "monitor": "val/rec_loss", "ddconfig": dd,
+                                              "lossconfig": {"target": "torch.nn.Identity"}}}
+    m = instantiate_from_config(cfg).eval()
+    assert m.vae is not None
+    synthetic.randomize_parameters(m.vae, e["seed"])
+    z = e["z"] * 0.18215
+    img = m.decode(z)
+    with torch.no_grad():
+        ref = V.viewfusion_decode(sd_of(m.vae), z, ch_mult=dd["ch_mult"], num_res_blocks=dd["num_res_blocks"])
+    assert img.shape == ref.shape and float(img.min()) >= 0.0 and float(img.max()) <= 1.0
+    assert rel_l2(img, ref) < TOL
+    assert any(k.startswith("vae.decoder.mid.attn_1.") for k in m.state_dict())
+
+
 @pytest.mark.gpu
 def test_softmax_rows_and_wide_convolution_kernels():
     from mvdfusion_b200 import ops as OPS

@@ -19,6 +19,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--views", type=int, default=8)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--table", action="store_true", help="per-kernel device times of one decode (CUDA events, eager)")
+    ap.add_argument("--cpu", action="store_true", help="also time the reference algorithm (oracle/vae_oracle.py, fp32) on the host cores, 1 view")
     a = ap.parse_args()
     from mvdfusion_b200 import _lib, synthetic
     from mvdfusion_b200.mvdfusion.autoencoder import AutoencoderKL
@@ -41,8 +43,44 @@ def main():
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     gflop = 622.0 * a.views  # 622 GFLOP per 256^2 decode
-    print(json.dumps({"what": "AutoencoderKL.decode", "views": a.views, "ms": round(best, 3), "launches": launches,
-                      "tflops": round(gflop / best, 1), "finite": bool(torch.isfinite(y).all())}))
+    line = {"what": "AutoencoderKL.decode", "views": a.views, "ms": round(best, 3), "launches": launches,
+            "tflops": round(gflop / best, 1), "finite": bool(torch.isfinite(y).all())}
+    if a.table:
+        plan = m.__dict__["_mvd_cache"].plans[("decode", a.views, 32)]
+        calls = plan.prog.calls
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in calls]
+        st = torch.cuda.current_stream().cuda_stream
+        torch.cuda.synchronize()
+        torch.cuda._sleep(int(1.0e8))
+        for c, (e0, e1) in zip(calls, ev):
+            e0.record()
+            c(st)
+            e1.record()
+        torch.cuda.synchronize()
+        agg = {}
+        for c, (e0, e1) in zip(calls, ev):
+            key = (c.meta.get("kernel", c.name.replace("mvd_", "")), str(c.meta.get("desc", "")))
+            g = agg.setdefault(key, [0, 0.0, 0.0])
+            g[0] += 1
+            g[1] += e0.elapsed_time(e1)
+            g[2] += c.meta.get("flops", 0.0)
+        for (k, d), (cnt, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:24]:
+            print(f"{k:22s} {d:48s} x{cnt:3d} {ms * 1e3 / cnt:9.1f} us/call {ms:8.3f} ms  {fl / (ms * 1e-3) / 1e12 if fl else 0:7.1f} TF/s", file=sys.stderr)
+    if a.cpu:
+        import time
+        sys.path.insert(0, ROOT)
+        from oracle import vae_oracle as V
+        sd = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
+        torch.set_num_threads(os.cpu_count())
+        z1 = z[:1].cpu()
+        with torch.no_grad():
+            V.vae_decode(sd, z1[:, :, :8, :8])  # warm-up on a small map
+            t0 = time.perf_counter()
+            V.vae_decode(sd, z1)
+            dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"ms_per_view": round(dt * 1e3, 1), "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "1 view, fp32, oracle/vae_oracle.py", "ms_for_these_views": round(dt * 1e3 * a.views, 1)}
+    print(json.dumps(line))
 
 
 if __name__ == "__main__":
