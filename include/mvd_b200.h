@@ -148,6 +148,9 @@ int mvd_concat_f32_f16(const float* a, const float* b, void* out, long long rows
 int mvd_upsample2x_f32_f16(const float* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C, void* stream);
 /* im2col of the stride-2 Downsample conv (openaimodel.py:151): fp32 NHWC -> fp16 [n*(H/2)*(W/2), 9*C] */
 int mvd_im2col_s2_f32_f16(const float* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C, void* stream);
+/* the same with the low-side padding selectable: pad_lo = 0 is the VAE encoder's Downsample, F.pad(x, (0,1,0,1)) + conv3x3 stride 2
+ * padding 0 (external/sd1/ldm/modules/diffusionmodules/model.py:65-76); pad_lo = 1 is the call above */
+int mvd_im2col_s2_pad_f32_f16(const float* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t pad_lo, void* stream);
 /* small-M linear: y = act_out(act_in(x) W^T + b); x fp32 [M, ldx], W fp16 [N, ldw], y fp32 [M, ldy].
  * t-only MLPs: ResBlock.emb_layers (openaimodel.py:218-224), UNetModel.time_embed (unet.py:310-314),
  * ViewFusion.time_embed / cc_projection (viewfusion_zero_depth_rgb.py:107-132), DiT adaLN (view_attn_efficient2.py:58-61) */

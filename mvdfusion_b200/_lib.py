@@ -52,6 +52,7 @@ SIGNATURES = {
     "mvd_concat_f32_f16": [vp, vp, vp, i64, i32, i32, vp],
     "mvd_upsample2x_f32_f16": [vp, vp, i32, i32, i32, i32, vp],
     "mvd_im2col_s2_f32_f16": [vp, vp, i32, i32, i32, i32, vp],
+    "mvd_im2col_s2_pad_f32_f16": [vp, vp, i32, i32, i32, i32, i32, vp],
     "mvd_gemv_f16": [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "mvd_gemv_grouped_f16": [vp, i32, i32, vp, i32, i32, vp],
     "mvd_timestep_embedding": [vp, vp, vp, i32, vp],

@@ -2,7 +2,7 @@
 
 `target:` strings written for the reference (`mvdfusion.viewfusion_zero_depth_rgb.ViewFusion`, `mvdfusion.unet.UNetModel`,
 …) resolve to this package's mirror modules, so the reference's configs/*.yaml load unchanged.
-`external.sd1.ldm.models.autoencoder.AutoencoderKL` resolves to this package's decode-side VAE.  Other targets outside the hot
+`external.sd1.ldm.models.autoencoder.AutoencoderKL` resolves to this package's VAE (encode / decode).  Other targets outside the hot
 path (CLIP, ...) resolve to None unless the reference package itself is importable: those components are out of scope
  and the facade reports them as absent.
 """
@@ -13,7 +13,7 @@ import torch
 import yaml
 
 _ALIASES = {"mvdfusion.": "mvdfusion_b200.mvdfusion.",
-            # the VAE (decode side): configs/mvd_gso.yaml:53-54
+            # the VAE: configs/mvd_gso.yaml:53-54
             "external.sd1.ldm.models.autoencoder.": "mvdfusion_b200.mvdfusion.autoencoder."}
 _OUT_OF_SCOPE_PREFIXES = ("external.sd1.",)
 

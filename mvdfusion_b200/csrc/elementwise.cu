@@ -86,10 +86,12 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, __half* __restric
   }
 }
 
-// im2col for conv3x3 stride 2 pad 1 (Downsample.op, openaimodel.py:151):
-// fp32 [n,H,W,C] -> fp16 [n*(H/2)*(W/2), 9*C], k = (ky*3+kx)*C + c
+// im2col for conv3x3 stride 2: fp32 [n,H,W,C] -> fp16 [n*(H/2)*(W/2), 9*C], k = (ky*3+kx)*C + c.
+// pad_lo = 1: padding 1 on every side (Downsample.op of the UNet, openaimodel.py:151);
+// pad_lo = 0: zero padding on the right / bottom only — the VAE encoder pads (0,1,0,1) by hand in front of a padding-0 conv
+//             (external/sd1/ldm/modules/diffusionmodules/model.py:65-76).
 __global__ void im2col_s2_kernel(const float* __restrict__ x, __half* __restrict__ y, int H, int W, int C,
-                                 size_t total4) {
+                                 size_t total4, int pad_lo) {
   pdl_trigger();
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2, K = 9 * C;
@@ -104,7 +106,7 @@ __global__ void im2col_s2_kernel(const float* __restrict__ x, __half* __restrict
     row /= Wo;
     const int oy = static_cast<int>(row % Ho);
     const size_t img = row / Ho;
-    const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
+    const int iy = 2 * oy - pad_lo + ky, ix = 2 * ox - pad_lo + kx;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = *reinterpret_cast<const float4*>(x + ((img * H + iy) * W + ix) * C + c);
     *reinterpret_cast<uint2*>(y + e) = pack4(v.x, v.y, v.z, v.w);
@@ -410,16 +412,21 @@ extern "C" int mvd_upsample2x_f32_f16(const float* x, void* y, int32_t n_img, in
   return MVD_OK;
 }
 
-extern "C" int mvd_im2col_s2_f32_f16(const float* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C,
-                                     void* stream_) {
+extern "C" int mvd_im2col_s2_pad_f32_f16(const float* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t pad_lo,
+                                         void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!x || !y || n_img <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || C <= 0 || (C & 3))
-    return set_error(MVD_EINVAL, "mvd_im2col_s2_f32_f16: bad arguments");
+  if (!x || !y || n_img <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || C <= 0 || (C & 3) || pad_lo < 0 || pad_lo > 1)
+    return set_error(MVD_EINVAL, "mvd_im2col_s2_pad_f32_f16: bad arguments");
   const size_t total4 = static_cast<size_t>(n_img) * (H / 2) * (W / 2) * 9 * C / 4;
-  MVD_LAUNCH((im2col_s2_kernel), grid_for(total4), 256, 0, stream, x, static_cast<__half*>(y), H, W, C, total4);
+  MVD_LAUNCH((im2col_s2_kernel), grid_for(total4), 256, 0, stream, x, static_cast<__half*>(y), H, W, C, total4, pad_lo);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
+}
+
+extern "C" int mvd_im2col_s2_f32_f16(const float* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                                     void* stream_) {
+  return mvd_im2col_s2_pad_f32_f16(x, y, n_img, H, W, C, 1, stream_);
 }
 
 extern "C" int mvd_gemv_f16(const float* x, int32_t ldx, const void* W, int32_t ldw, const float* bias, float* y,

@@ -817,3 +817,45 @@ def emit_vae_decoder(b, z_nchw, n, S, ch, ch_mult, num_res_blocks, z_channels=4,
     b.conv3x3(a, "decoder.conv_out.weight", n, H, H, C, out_ch, bias=W.f32("decoder.conv_out.bias"), ldc=4, out=out)
     b.free(a)
     return out, H
+
+
+def emit_vae_encoder(b, x_nchw, n, R, ch, ch_mult, num_res_blocks, in_channels=3, z_channels=4, embed_dim=4):
+    """AutoencoderKL.encode up to the moments (external/sd1/ldm/models/autoencoder.py:325-329) = Encoder.forward
+    (model.py:440-460; double_z) -> quant_conv (1x1).  x_nchw: fp32 [n, in_channels, R*R] in [-1, 1].  Returns
+    (fp32 rows [n*S*S, 8] = mean | logvar of the posterior, S)."""
+    W, ops = b.W, b.ops
+    x16 = ops.zeros((n * R * R, 16), torch.float16)  # NHWC, channel dim padded to 16 (padding stays zero)
+    b.prog.append(ops.nchw_to_nhwc16(x_nchw, x16, n, in_channels, R * R, 16))
+    h = b.conv3x3(x16, "encoder.conv_in.weight", n, R, R, in_channels, ch, bias=W.f32("encoder.conv_in.bias"), c_pad=16)
+    C, H = ch, R
+    for lvl in range(len(ch_mult)):
+        Cout = ch * ch_mult[lvl]
+        for j in range(num_res_blocks):
+            h = _vae_resnet(b, h, f"encoder.down.{lvl}.block.{j}", n, H, C, Cout)
+            C = Cout
+        if lvl != len(ch_mult) - 1:
+            # Downsample: F.pad(x, (0,1,0,1)) then conv3x3 stride 2 padding 0 (model.py:65-76) = im2col without low-side padding + GEMM
+            p = f"encoder.down.{lvl}.downsample.conv"
+            Mo = n * (H // 2) * (H // 2)
+            col = b.t16(Mo, 9 * C)
+            b.prog.append(ops.im2col_s2(h, col, n, H, H, C, pad_lo=0))
+            b.free(h)
+            h = b.t32(Mo, C)
+            b.gemm(col, W.conv3(p + ".weight"), h, Mo, C, 9 * C, allow_split=True, bias=W.f32(p + ".bias"))
+            b.free(col)
+            H //= 2
+    h = _vae_resnet(b, h, "encoder.mid.block_1", n, H, C, C)
+    h = _vae_attn(b, h, "encoder.mid.attn_1", n, H, C)
+    h = _vae_resnet(b, h, "encoder.mid.block_2", n, H, C, C)
+    a = b.groupnorm(h, "encoder.norm_out", n, H * H, C, 1e-6, True)
+    b.free(h)
+    M, Nz = n * H * H, 2 * z_channels
+    mom = b.t32(M, Nz)
+    b.conv3x3(a, "encoder.conv_out.weight", n, H, H, C, Nz, bias=W.f32("encoder.conv_out.bias"), out=mom)
+    b.free(a)
+    m16 = b.cast16(mom, M, Nz)
+    b.free(mom)
+    out = ops.empty((M, 2 * embed_dim), torch.float32)
+    b.gemm(m16, W.lin("quant_conv.weight"), out, M, 2 * embed_dim, Nz, bias=W.f32("quant_conv.bias"))
+    b.free(m16)
+    return out, H

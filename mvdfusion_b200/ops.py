@@ -184,8 +184,8 @@ class NativeOps:
         return self._bind("mvd_upsample2x_f32_f16", (_ptr(x, torch.float32), _ptr(y, torch.float16), n_img, H, W, C),
                           (x, y))
 
-    def im2col_s2(self, x, y, n_img, H, W, C):
-        return self._bind("mvd_im2col_s2_f32_f16", (_ptr(x, torch.float32), _ptr(y, torch.float16), n_img, H, W, C),
+    def im2col_s2(self, x, y, n_img, H, W, C, pad_lo=1):
+        return self._bind("mvd_im2col_s2_pad_f32_f16", (_ptr(x, torch.float32), _ptr(y, torch.float16), n_img, H, W, C, pad_lo),
                           (x, y))
 
     def gemv(self, x, W, bias, y, M, N, K, *, ldx=None, ldw=None, ldy=None, silu_in=False, silu_out=False):

@@ -1,9 +1,9 @@
 """Pins oracle/vae_oracle.py against the reference's OWN VAE decoder and writes tests/golden/vae_decoder_outputs.pt.
 
 Runs only in the build container (needs /root/reference):   python tests/golden/make_golden_vae.py
-Imports the unmodified `external.sd1.ldm.modules.diffusionmodules.model.Decoder` (the reference's AutoencoderKL wrapper
+Imports the unmodified `external.sd1.ldm.modules.diffusionmodules.model.Decoder` / `.Encoder` (the reference's AutoencoderKL wrapper
 additionally needs `taming`, which is not installed; its decode() is `decoder(post_quant_conv(z))`, autoencoder.py:331-334,
-restated here with a plain nn.Conv2d), loads the product's seeded state dict into it with strict=True — which proves the
+restated here with a plain nn.Conv2d; likewise encode() = quant_conv(encoder(x)), :325-329), loads the product's seeded state dict into it with strict=True — which proves the
 parameter names and shapes of mvdfusion_b200.mvdfusion.autoencoder match the reference — and compares on seeded latents.
 """
 import os
@@ -21,7 +21,7 @@ from mvdfusion_b200 import synthetic  # noqa: E402
 from mvdfusion_b200.mvdfusion.autoencoder import AutoencoderKL  # noqa: E402
 from oracle import vae_oracle as V  # noqa: E402
 
-from external.sd1.ldm.modules.diffusionmodules.model import Decoder as RefDecoder  # noqa: E402  (the reference)
+from external.sd1.ldm.modules.diffusionmodules.model import Decoder as RefDecoder, Encoder as RefEncoder  # noqa: E402  (the reference)
 
 SMALL = dict(double_z=True, z_channels=4, resolution=64, in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2, 4, 4], num_res_blocks=2,
              attn_resolutions=[], dropout=0.0)
@@ -44,7 +44,19 @@ def run(dd, n, seed):
     r = rel_l2(y_orc, y_ref)
     print(f"vae decode ch={dd['ch']} res={dd['resolution']} n={n}: oracle vs reference rel-L2 = {r:.3e}, |y| max {y_ref.abs().max():.3f}")
     assert r < 2e-5, r
-    return {"ddconfig": dd, "seed": seed, "z": z, "y": y_ref}
+    # encode side: Encoder -> quant_conv -> moments (autoencoder.py:325-329); images in [-1, 1]
+    enc = RefEncoder(**dd).eval()
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}, strict=True)
+    qc = torch.nn.Conv2d(2 * dd["z_channels"], 8, 1)
+    qc.load_state_dict({"weight": sd["quant_conv.weight"], "bias": sd["quant_conv.bias"]}, strict=True)
+    img = torch.rand(n, 3, dd["resolution"], dd["resolution"], generator=torch.Generator().manual_seed(seed + 2)) * 2 - 1
+    with torch.no_grad():
+        m_ref = qc(enc(img))
+        m_orc = V.vae_encode_moments(sd, img, ch_mult=dd["ch_mult"], num_res_blocks=dd["num_res_blocks"])
+    r = rel_l2(m_orc, m_ref)
+    print(f"vae encode ch={dd['ch']} res={dd['resolution']} n={n}: oracle vs reference rel-L2 = {r:.3e}, |moments| max {m_ref.abs().max():.3f}")
+    assert r < 2e-5, r
+    return {"ddconfig": dd, "seed": seed, "z": z, "y": y_ref, "img_seed": seed + 2, "moments": m_ref}
 
 
 if __name__ == "__main__":

@@ -184,10 +184,10 @@ class TorchOpsDouble:
             y.reshape(-1)[: o.numel()].copy_(o.reshape(-1).half())
         return self._call(fn)
 
-    def im2col_s2(self, x, y, n_img, H, W, C):
+    def im2col_s2(self, x, y, n_img, H, W, C, pad_lo=1):
         def fn():
             v = x.reshape(-1)[: n_img * H * W * C].reshape(n_img, H, W, C)
-            vp = F.pad(v, (0, 0, 1, 1, 1, 1))
+            vp = F.pad(v, (0, 0, pad_lo, 2 - pad_lo, pad_lo, 2 - pad_lo))
             cols = [vp[:, ky:ky + H:2, kx:kx + W:2, :] for ky in range(3) for kx in range(3)]
             o = torch.cat(cols, dim=-1)
             y.reshape(-1)[: o.numel()].copy_(o.reshape(-1).half())

@@ -1,4 +1,4 @@
-"""VAE decode: oracle vs the reference golden, product host logic vs oracle (CPU emulation of the C ABI),
+"""VAE decode / encode: oracle vs the reference golden, product host logic vs oracle (CPU emulation of the C ABI),
 and — on the B200 — the kernels themselves."""
 import os
 
@@ -42,7 +42,35 @@ def test_oracle_matches_the_reference_decoder_goldens():
         assert rel_l2(y, ref) < 2e-5, name
 
 
-def test_yaml_target_resolves_to_the_decode_side_vae():
+def golden_image(e):
+    dd = e["ddconfig"]
+    n = e["z"].shape[0]
+    return torch.rand(n, 3, dd["resolution"], dd["resolution"], generator=torch.Generator().manual_seed(e["img_seed"])) * 2 - 1
+
+
+def test_oracle_matches_the_reference_encoder_goldens():
+    g = torch.load(GOLD)
+    for name in ("small", "full"):
+        e = g[name]
+        dd = e["ddconfig"]
+        if name == "full" and os.environ.get("MVD_FAST_TESTS"):
+            continue
+        m = build_vae(dd, e["seed"])
+        with torch.no_grad():
+            mom = V.vae_encode_moments(sd_of(m), golden_image(e), ch_mult=dd["ch_mult"], num_res_blocks=dd["num_res_blocks"])
+        assert rel_l2(mom, e["moments"]) < 2e-5, name
+
+
+def test_encode_host_logic_vs_oracle(ops_double):
+    e = torch.load(GOLD)["small"]
+    m = build_vae(e["ddconfig"], e["seed"])
+    post = m.encode(golden_image(e))
+    assert post.parameters.shape == e["moments"].shape and torch.isfinite(post.parameters).all()
+    assert rel_l2(post.parameters, e["moments"]) < TOL
+    assert torch.equal(post.mode(), post.parameters[:, :4]) and post.sample().shape == post.mean.shape
+
+
+def test_yaml_target_resolves_to_this_package_vae():
     from mvdfusion_b200.config import instantiate_from_config
     from mvdfusion_b200.mvdfusion.autoencoder import AutoencoderKL
     dd = torch.load(GOLD)["small"]["ddconfig"]
@@ -54,8 +82,7 @@ def test_yaml_target_resolves_to_the_decode_side_vae():
     for k in ("post_quant_conv.weight", "decoder.conv_in.bias", "decoder.mid.attn_1.proj_out.weight", "decoder.up.3.upsample.conv.weight",
               "decoder.up.1.block.0.nin_shortcut.weight", "decoder.up.0.block.2.conv2.bias", "decoder.norm_out.weight", "decoder.conv_out.weight"):
         assert k in keys, k
-    with pytest.raises(NotImplementedError):
-        m.encode(torch.zeros(1, 3, 64, 64))
+    assert "encoder.down.2.downsample.conv.weight" in keys and "quant_conv.bias" in keys
 
 
 def test_decode_host_logic_vs_oracle(ops_double):
@@ -91,6 +118,12 @@ def test_viewfusion_decode_through_the_facade(ops_double):
     assert img.shape == ref.shape and float(img.min()) >= 0.0 and float(img.max()) <= 1.0
     assert rel_l2(img, ref) < TOL
     assert any(k.startswith("vae.decoder.mid.attn_1.") for k in m.state_dict())
+    # ViewFusion.encode (viewfusion_zero_depth_rgb.py:158-159): images in [0, 1] -> scaled latents
+    pic = (golden_image(e) + 1) / 2
+    lat = m.encode(pic)
+    with torch.no_grad():
+        lat_ref = V.viewfusion_encode(sd_of(m.vae), pic, ch_mult=dd["ch_mult"], num_res_blocks=dd["num_res_blocks"])
+    assert lat.shape == lat_ref.shape and rel_l2(lat, lat_ref) < TOL
 
 
 @pytest.mark.gpu
@@ -119,6 +152,34 @@ def test_softmax_rows_and_wide_convolution_kernels():
         nat.gemm(A.cuda(), Wt.cuda(), o_gpu, M, Cout, 9 * Cin, conv=(n, H, Wd, Cin), bias=bias.cuda(), ldc=ldc)(st)
         torch.cuda.synchronize()
         assert (o_gpu.cpu() - o_cpu).abs().max() < 2e-3 * o_cpu.abs().max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["small", "full"])
+def test_encode_on_the_gpu_vs_reference_golden(name):
+    from common import record_parity
+    e = torch.load(GOLD)[name]
+    m = build_vae(e["ddconfig"], e["seed"], device="cuda")
+    post = m.encode(golden_image(e).cuda())
+    torch.cuda.synchronize()
+    assert torch.isfinite(post.parameters).all()
+    assert record_parity(f"vae_encode_{name}_vs_reference_golden", rel_l2(post.parameters, e["moments"]), TOL) < TOL
+
+
+@pytest.mark.gpu
+def test_stride2_im2col_without_low_padding():
+    from mvdfusion_b200 import ops as OPS
+    from ops_double import TorchOpsDouble
+    nat, dbl = OPS.NativeOps("cuda:0"), TorchOpsDouble()
+    n, H, C = 2, 16, 32
+    x = torch.randn(n * H * H, C, generator=torch.Generator().manual_seed(3))
+    for pad_lo in (0, 1):
+        y_cpu = torch.zeros(n * (H // 2) ** 2, 9 * C, dtype=torch.float16)
+        y_gpu = torch.zeros_like(y_cpu, device="cuda")
+        dbl.im2col_s2(x, y_cpu, n, H, H, C, pad_lo=pad_lo)(None)
+        nat.im2col_s2(x.cuda(), y_gpu, n, H, H, C, pad_lo=pad_lo)(torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert torch.equal(y_gpu.cpu(), y_cpu)
 
 
 @pytest.mark.gpu

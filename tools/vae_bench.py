@@ -45,6 +45,20 @@ def main():
     gflop = 622.0 * a.views  # 622 GFLOP per 256^2 decode
     line = {"what": "AutoencoderKL.decode", "views": a.views, "ms": round(best, 3), "launches": launches,
             "tflops": round(gflop / best, 1), "finite": bool(torch.isfinite(y).all())}
+    # encode: the scene's input image(s) before the loop (viewfusion_zero_depth_rgb.py:158-159); 273 GFLOP per 256^2 image
+    img = torch.rand(a.views, 3, 256, 256, device="cuda") * 2 - 1
+    post = m.encode(img)
+    torch.cuda.synchronize()
+    best_e = 1e30
+    for _ in range(a.reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        post = m.encode(img)
+        e1.record()
+        torch.cuda.synchronize()
+        best_e = min(best_e, e0.elapsed_time(e1))
+    line["encode"] = {"views": a.views, "ms": round(best_e, 3), "tflops": round(273.0 * a.views / best_e, 1),
+                      "finite": bool(torch.isfinite(post.parameters).all())}
     if a.table:
         plan = m.__dict__["_mvd_cache"].plans[("decode", a.views, 32)]
         calls = plan.prog.calls
