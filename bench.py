@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--mode", default="replicas", choices=["shard", "replicas"])
     ap.add_argument("--views", type=int, default=8)
+    ap.add_argument("--latent", type=int, default=32, choices=[32, 64],
+                    help="latent side: 32 = 256^2 images (the headline workload), 64 = 512^2 (BASELINE configs[4], HBM-bandwidth stress)")
     ap.add_argument("--cfg", type=float, default=2.5)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -52,7 +54,8 @@ def parse():
 
 def step_flops(n_views, S, D, cfg):
     p = 1 if cfg == 1.0 else 2
-    return (F_GRID_GFLOP * n_views * n_views * S * S * D + p * n_views * F_UNET_GFLOP) * 1e9
+    f_unet = F_UNET_GFLOP if S == 32 else 1047.1  # F_U(64, 1)
+    return (F_GRID_GFLOP * n_views * n_views * S * S * D + p * n_views * f_unet) * 1e9
 
 
 def peaks():
@@ -80,7 +83,7 @@ def cpu_arm(args, reps, warmup, model=None):
     from common import build_model, state_dict_cpu, synthetic, unet_cfg_of
     from oracle import mvd_oracle as O
     torch.set_num_threads(os.cpu_count())
-    n, S, D = args.views, 32, 1
+    n, S, D = args.views, args.latent, 1
     m = model if model is not None else build_model(320, 8, D=D, S=S)
     sd = state_dict_cpu(m)
     ucfg = unet_cfg_of(m)
@@ -113,7 +116,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"N={args.views} views 256^2 DDIM step, cfg {args.cfg}, D=1, full-size UNet (BASELINE configs[1])",
+            "config": {"workload": f"N={args.views} views {8 * args.latent}^2 DDIM step, cfg {args.cfg}, D=1, full-size UNet (BASELINE configs[{1 if args.latent == 32 else 4}])",
                        "timed_samples": reps, "note": "reference algorithm (CPU port, oracle/) on host cores; bounded sample per step"},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -235,7 +238,7 @@ def run_native(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    n, S, D, K, Wm = args.views, 32, 1, args.steps, args.warmup
+    n, S, D, K, Wm = args.views, args.latent, 1, args.steps, args.warmup
     shard = world > 1 and args.mode == "shard"
     if world > 1 and n % world:
         raise SystemExit(f"--views {n} does not shard over {world} ranks")
@@ -372,8 +375,8 @@ def run_native(args):
         line = {"metric": METRIC, "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (shard or world == 1) else "weak",
                 "vs_baseline": None, "dtype": "f16 operands / f32 accumulate + f32 residual stream", "data": "synthetic",
-                "config": {"workload": f"N={n} views 256^2 (32x32x5 latents) DDIM step, cfg {args.cfg} (cond+uncond batched), D=1, "
-                                       "full-size UNet 1.034B params random-init + GridAttn (BASELINE configs[1])",
+                "config": {"workload": f"N={n} views {8 * S}^2 ({S}x{S}x5 latents) DDIM step, cfg {args.cfg} (cond+uncond batched), D=1, "
+                                       f"full-size UNet 1.034B params random-init + GridAttn (BASELINE configs[{1 if S == 32 else 4}])",
                            "mode": ("view-sharded, 1 all-gather/step" if shard else ("replicas" if world > 1 else "single GPU")),
                            "views_per_gpu": q, "cuda_graph": use_graph,
                            "l2": "no flush: every step streams 2.08 GB of fp16 weights (>> 126 MB L2)"},
