@@ -121,6 +121,31 @@ def test_module_level_forwards(ops_double, model):
     assert rel_l2(y, ref) < TOL
 
 
+def test_step_program_has_no_cast_or_concat_passes(ops_double, model, monkeypatch):
+    """The fp16 operands of the 1x1 skip convolutions are written by their producers' epilogues (mvd_gemm_args.out16 windows of
+    one [rows, c1+c2] buffer per output block): the step program contains no cast / concat launch, the MVD_NO_FUSE_CAT path does,
+    and both give the same result."""
+    import mvdfusion_b200.engine as E
+    m, _ = model
+    sc = synthetic.scene_inputs(2, 32)
+    de, _ = synthetic.step_noises(2, 1, 32, 1)
+    t = torch.full((2,), 501, dtype=torch.long)
+    args = (sc["x_T"], cams_of(sc["cams"]), sc["input_latents"], cams_of(sc["in_cams"]), sc["clip_v_embed"], t)
+
+    def names(plan):
+        return [getattr(c, "__name__", None) or getattr(c, "name", "") for c in plan.core_prog.calls]
+
+    eps_fused = m.apply_model(*args, cfg_scale=2.5, depth_eps=de[0])
+    plan = m.step_plan(2, 32, 1, use_cfg=True)
+    n_fused = len(plan.core_prog)
+    monkeypatch.setenv("MVD_NO_FUSE_CAT", "1")
+    m2 = build_model(64, 8, D=1, S=32)
+    eps_plain = m2.apply_model(*args, cfg_scale=2.5, depth_eps=de[0])
+    n_plain = len(m2.step_plan(2, 32, 1, use_cfg=True).core_prog)
+    assert n_plain - n_fused == 14  # 12 skip concatenations + 2 casts in front of the channel-changing input ResBlocks
+    assert torch.equal(eps_fused, eps_plain)
+
+
 def test_weight_cache_follows_parameter_updates(ops_double, model):
     m, sd = model
     st = m.unet_model.unet_model.input_blocks[1][1]
