@@ -55,6 +55,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--views", type=int, default=8)
     ap.add_argument("--reps", type=int, default=16)
+    ap.add_argument("--latent", type=int, default=32, help="latent side (32 = 256^2 images, 64 = 512^2)")
     ap.add_argument("--shards", default="1", help="comma list of GPU counts whose per-rank shapes (views/G per GPU) to tune")
     ap.add_argument("--merge", default="", help="existing tuning file whose choices are kept for signatures not re-measured")
     ap.add_argument("--out", default=os.path.join(ROOT, "mvdfusion_b200", "gemm_tuning.json"))
@@ -65,14 +66,14 @@ def main():
     from mvdfusion_b200.ops import ACT_GEGLU
     lib = _lib.load()
     dev = torch.device("cuda", 0)
-    model = build_model(320, 8, D=1, S=32, device=dev)
+    model = build_model(320, 8, D=1, S=a.latent, device=dev)
     stream = torch.cuda.Stream()
     seen, choices, report = {}, {}, []
     if a.merge and os.path.exists(a.merge):
         choices.update(json.load(open(a.merge)).get("choices", {}))
     for world in [int(w) for w in a.shards.split(",")]:
         model.view_group = (None, 0, world) if world > 1 else None  # rank 0's shard: shapes are the same on every rank
-        plan = model.step_plan(a.views, 32, 1, use_cfg=True)
+        plan = model.step_plan(a.views, a.latent, 1, use_cfg=True)
         print(f"---- {a.views} views over {world} GPU(s): {plan.q} views per GPU", flush=True)
         for c in plan.core_prog.calls:
             if c.name != "mvd_gemm_f16":
