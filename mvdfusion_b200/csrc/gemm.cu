@@ -3,17 +3,22 @@
 //   acc[m, n] = sum_k A[m, k] * W[n, k]     fp16 operands (K-major, 128B-swizzled smem tiles via TMA),
 //                                           fp32 accumulators in TMEM, fused epilogues.
 //
-// One CTA (384 threads) per SM loops over work units (output tile 128 x BN, optionally one K-slice of it):
+// One CTA (384 or 512 threads) per SM loops over work units (output tile 128 x BN, optionally one K-slice of it):
 //   warp 0      : TMA producer (one elected lane) — A tile + W tile per 64-wide k-block into a `stages`-deep ring
 //   warp 1      : TMEM allocator + UMMA issuer (one elected lane); tcgen05.commit releases ring slots and
 //                 publishes the finished accumulator.  TWO accumulators live in TMEM, so the MMA of unit j+1
 //                 overlaps the epilogue of unit j.
-//   warps 4..11 : two epilogue warpgroups; each owns every other 32-column chunk of a tile.  Per chunk:
+//   warps 4..   : two or three epilogue warpgroups (template NWG) that take turns over the 32-column chunks of a tile.
+//                 Three (512 threads, 128 registers per thread) for every non-split specialisation: the short-K GEMMs of the
+//                 step are bound by the epilogue's latency chains, and a third chunk in flight is worth 13-22 % there; the
+//                 split-K bodies need more registers and keep two.  Per chunk:
 //                 phase A  tcgen05.ld (thread = tile row) -> 128B-swizzled fp32 staging tile in smem
 //                          (GEGLU multiplies value * gelu(gate) here; the v^T part of a QKV scatter leaves from here),
 //                 phase B  thread = (row, 16-byte segment): bias / per-image row bias / GELU / SiLU / adaLN gate /
-//                          residual / split-K partials, all read and written with coalesced 16-byte accesses.
-//                 The residual of the NEXT chunk is already in flight (registers) while this one is processed.
+//                          residual / split-K partials, all read and written with coalesced 16-byte accesses; an fp32
+//                          output can be stored a second time as fp16 (out16: the next GEMM's operand).
+//                 With two warpgroups each owns two staging tiles and the residual of the NEXT chunk is already in flight
+//                 (registers) while this one is processed; with three, one staging tile each and no prefetch.
 // Split-K (small-M, weight-bound layers; all slices of a tile are co-resident): slice s parks the chunks it does not
 //   own in a workspace, bumps the tile semaphore and waits for its siblings; then every slice reduces and finishes the
 //   chunks it owns (chunk c belongs to slice c % split) — the reduction is spread over the slices, no atomics on data.
