@@ -11,12 +11,11 @@ matrices (conv kernels as [C_out, (ky,kx,c)], q/k/v fused, GEGLU value/gate rows
 
 Reference call sites each emitter replaces are cited in its docstring (paths under the reference root).
 """
+import json
 import math
+import os
 
 import torch
-
-import json
-import os
 
 from .ops import ACT_GEGLU, ACT_GELU, ACT_NONE, gemm_signature
 
