@@ -13,6 +13,11 @@ from oracle import mvd_oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL = 2e-3
+# BASELINE.json's north star asks for 1e-3 rel-L2 on the reference's own architecture: the full-size (320-channel, 1.03 B parameter)
+# cases are gated at exactly that (measured 9.4e-4 .. 9.5e-4, profiles/r01_parity_v8.jsonl; the kernels are deterministic, so the
+# figure does not move between runs); the 64-channel test models have fewer terms per dot product to average the fp16 operand
+# rounding over and keep the 2e-3 gate (measured 5.8e-4 .. 1.08e-3).
+TOL_FULL = 1e-3
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_outputs.pt")
 
 
@@ -129,8 +134,8 @@ def test_apply_model_full_size_vs_oracle():
                         sc["clip_v_embed"].cuda(), t.cuda(), cfg_scale=2.5, depth_eps=de[0].cuda())
     ref = O.apply_model(sd, sc["x_T"], sc["cams"], sc["input_latents"], sc["in_cams"], sc["clip_v_embed"], t, de[0],
                         unet_cfg=unet_cfg_of(m), D=D, cfg_scale=2.5)
-    r = record_parity("apply_model_full_size_N2_vs_oracle", rel_l2(eps, ref), TOL)
-    assert r < TOL
+    r = record_parity("apply_model_full_size_N2_vs_oracle", rel_l2(eps, ref), TOL_FULL)
+    assert r < TOL_FULL
 
 
 def test_apply_model_full_size_n8_views_subset_vs_oracle():
@@ -147,9 +152,9 @@ def test_apply_model_full_size_n8_views_subset_vs_oracle():
                         sc["clip_v_embed"].cuda(), t.cuda(), cfg_scale=2.5, depth_eps=de[0].cuda())
     ref = O.apply_model(sd, sc["x_T"], sc["cams"], sc["input_latents"], sc["in_cams"], sc["clip_v_embed"], t, de[0],
                         unet_cfg=unet_cfg_of(m), D=D, cfg_scale=2.5, query=query)
-    r = record_parity("apply_model_full_size_N8_views1and6_vs_oracle", rel_l2(eps[query], ref), TOL)
+    r = record_parity("apply_model_full_size_N8_views1and6_vs_oracle", rel_l2(eps[query], ref), TOL_FULL)
     assert torch.isfinite(eps).all()
-    assert r < TOL
+    assert r < TOL_FULL
 
 
 def _apply_both(m, N, S, D, cfg, seed=0, t_val=641):
