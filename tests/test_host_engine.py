@@ -177,3 +177,38 @@ def test_prepare_batch_matches_reference_layout(model):
     assert torch.allclose(cve[0, 0, 768:777], ic.R.reshape(-1), atol=1e-6)
     assert torch.allclose(cve[3, 0, 782:791], bc.R[3].reshape(-1), atol=1e-6)
     assert torch.allclose(cve[3, 0, 794:796], bc.focal_length[3], atol=1e-6)
+
+
+def test_sample_and_forward_through_the_facade_baseline_config0(ops_double):
+    """BASELINE.json configs[0] plumbing (demo.py:85 -> ViewFusion.sample): one input view, N = 4 target views, 10 DDIM steps,
+    cfg 2.5, random-init (64-channel) UNet; the facade draws x_T and the per-step noises itself, in the reference's order
+    (sampler.py:107,128 / view_attn_efficient2.py:431), so seeding torch reproduces them for the oracle.  Also the training
+    facade: ViewFusion.forward(batch, cfg) = mean squared error of the predicted noise (viewfusion_zero_depth_rgb.py:362-392)."""
+    N, S, steps = 4, 32, 10
+    m = build_model(64, 8, D=1, S=S, ddim_steps=steps)
+    sd = state_dict_cpu(m)
+    R, T, f, p = synthetic.gso_rig(N)
+    g = torch.Generator().manual_seed(11)
+    batch = {"latents": torch.randn(N + 1, 4, S, S, generator=g) * 0.8, "clip_embed": torch.randn(N + 1, 1, 768, generator=g),
+             "R": R, "T": T, "f": f, "c": p}
+    cfg = {"input_batch_size": 1, "train_batch_size": N, "random_views": False}
+    torch.manual_seed(123)
+    x, bl, il, bc, inter = m.sample(batch, cfg, cfg_scale=2.5, return_input=True, depth=True, verbose=False)
+    assert x.shape == (N, 5, S, S) and len(inter) == steps and bl.shape == (N, 5, S, S)
+    # the same draws for the oracle
+    torch.manual_seed(123)
+    x_T = torch.randn([N, 5, S, S])
+    de, dn = [], []
+    for _ in range(steps):
+        de.append(torch.randn(N, 1, S, S))
+        dn.append(torch.randn(N, 5, S, S))
+    _, bc2, il2, ic2, cve = m.prepare_batch(batch, cfg)
+    cams = {"R": bc2.R, "T": bc2.T, "f": bc2.focal_length, "p": bc2.principal_point}
+    icams = {"R": ic2.R, "T": ic2.T, "f": ic2.focal_length, "p": ic2.principal_point}
+    ref, _ = O.ddim_sample(sd, x_T, cams, il2, icams, cve, torch.stack(de), torch.stack(dn), unet_cfg=unet_cfg_of(m), D=1,
+                           num_steps=steps, eta=1.0, cfg_scale=2.5, return_intermediates=True)
+    assert rel_l2(x, ref) < 3 * TOL  # ten chained steps
+
+    torch.manual_seed(7)
+    loss = m(batch, cfg)
+    assert loss.dim() == 0 and torch.isfinite(loss) and 0.1 < float(loss) < 10.0
