@@ -67,57 +67,69 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
-def cpu_step_sample(sd, unet_cfg, sc, de, dn, n_views, D, cfg, query, tab, index):
-    """One bounded sample of a denoising step on the CPU: the oracle (reference algorithm, fp32) for `query` views."""
-    from oracle import mvd_oracle as O
-    t = torch.full((n_views,), int(tab["timesteps"][index]), dtype=torch.long)
-    eps = O.apply_model(sd, sc["x_T"], sc["cams"], sc["input_latents"], sc["in_cams"], sc["clip_v_embed"], t, de, unet_cfg=unet_cfg,
-                        D=D, cfg_scale=cfg, query=query)
-    return O.ddim_update(sc["x_T"][query], eps, tab, index, dn[query])
+def workload_string(args):
+    """`config.workload`, identical in both arms (the driver compares the strings)."""
+    S = args.latent
+    return (f"N={args.views} views {8 * S}^2 ({S}x{S}x5 latents) DDIM step, cfg {args.cfg} (cond+uncond), D=1, full-size UNet 1.034B params "
+            f"random-init + GridAttn (BASELINE configs[{1 if S == 32 else 4}])")
 
 
-def cpu_arm(args, reps, warmup, model=None):
-    """Reference algorithm on the host cores.  Sample = 2 of the `views` query views per step (UNet x2 CFG for 2 views +
-    GridAttn of 2 query views against all views); every stage is linear in the number of query views, so
-    step time = sample time x views/2."""
-    from common import build_model, state_dict_cpu, synthetic, unet_cfg_of
-    from oracle import mvd_oracle as O
+def cpu_arm(args, steps, warmup, budget_s):
+    """The reference's CPU implementation of the path on the host cores, all threads: `steps` timed + `warmup` untimed FULL
+    denoising steps (all `views` views, both CFG passes, GridAttn, DDIM update) of the same workload as the native arm.
+    kind "reference": the reference's own modules (sourceless bytecode in oracle/_ref, built by oracle/build_ref.py from
+    /root/reference) through oracle/ref_shims; kind "port": oracle/mvd_oracle.py when oracle/_ref is absent.
+    Returns (cpu_baseline dict, seconds per step, steps actually timed)."""
+    from common import build_model, model_config, state_dict_cpu, synthetic, unet_cfg_of
+    from oracle import ref_runner as RR
     torch.set_num_threads(os.cpu_count())
     n, S, D = args.views, args.latent, 1
-    m = model if model is not None else build_model(320, 8, D=D, S=S)
-    sd = state_dict_cpu(m)
-    ucfg = unet_cfg_of(m)
     sc = synthetic.scene_inputs(n, S)
-    de, dn = synthetic.step_noises(n, D, S, 1)
-    tab = O.ddim_tables(sd["scheduler.alphas_cumprod"], 50, 1.0)
-    query = [0, 1]
-    times = []
-    with torch.no_grad():
-        for i in range(warmup + reps):
-            t0 = time.perf_counter()
-            cpu_step_sample(sd, ucfg, sc, de[0], dn[0], n, D, args.cfg, query, tab, 49 - (i % 50))
-            dt = time.perf_counter() - t0
-            if i >= warmup:
-                times.append(dt)
-    scale = n / len(query)
-    step_s = sum(times) / len(times) * scale
-    return {"value": 1.0 / step_s, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{len(query)} of {n} query views per step (UNet x2 CFG on 2 views + GridAttn of 2 query views vs all {n}); "
-                      f"step time = {scale:g} x sample time; {len(times)} timed samples, fp32, oracle/mvd_oracle.py"}, step_s
+    if RR.available():
+        kind = "reference"
+        m = RR.build_reference_model(model_config(320, 8, D, S)["params"])
+        torch.manual_seed(1)
+        times, _ = RR.time_denoising_steps(m, sc, args.cfg, steps, warmup, budget_s=budget_s)
+        how = "the reference's own ViewFusion / DDIMSampler.denoise_apply (oracle/_ref bytecode through oracle/ref_shims)"
+    else:
+        from oracle import mvd_oracle as O
+        kind = "port"
+        m = build_model(320, 8, D=D, S=S)
+        sd, ucfg = state_dict_cpu(m), unet_cfg_of(m)
+        de, dn = synthetic.step_noises(n, D, S, 1)
+        tab = O.ddim_tables(sd["scheduler.alphas_cumprod"], 50, 1.0)
+        times, t_start = [], time.perf_counter()
+        with torch.no_grad():
+            for i in range(warmup + steps):
+                index = 49 - (i % 50)
+                t0 = time.perf_counter()
+                t = torch.full((n,), int(tab["timesteps"][index]), dtype=torch.long)
+                eps = O.apply_model(sd, sc["x_T"], sc["cams"], sc["input_latents"], sc["in_cams"], sc["clip_v_embed"], t, de[0],
+                                    unet_cfg=ucfg, D=D, cfg_scale=args.cfg)
+                O.ddim_update(sc["x_T"], eps, tab, index, dn[0])
+                if i >= warmup:
+                    times.append(time.perf_counter() - t0)
+                    if time.perf_counter() - t_start > budget_s:
+                        break
+        how = "oracle/mvd_oracle.py (CPU port of the reference algorithm; oracle/_ref was not built)"
+    step_s = sum(times) / len(times)
+    return {"value": 1.0 / step_s, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{len(times)} full denoising steps (all {n} views, {'2 UNet passes' if args.cfg != 1.0 else '1 UNet pass'} + GridAttn + DDIM "
+                      f"update) after {warmup} warm-up, fp32, {how}"}, step_s, len(times)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    reps = max(1, min(args.steps, 6))
-    warm = max(0, min(args.warmup, 1))
-    cb, step_s = cpu_arm(args, reps, warm)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+    budget = float(os.environ.get("MVD_REF_BUDGET_S", "300"))
+    cb, step_s, timed = cpu_arm(args, max(1, args.steps), max(0, args.warmup), budget)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "steps/s", "n_gpus": args.gpus, "steps": timed,
+            "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"N={args.views} views {8 * args.latent}^2 DDIM step, cfg {args.cfg}, D=1, full-size UNet (BASELINE configs[{1 if args.latent == 32 else 4}])",
-                       "timed_samples": reps, "note": "reference algorithm (CPU port, oracle/) on host cores; bounded sample per step"},
+            "config": {"workload": workload_string(args), "steps_requested": args.steps,
+                       "note": "the reference's CPU implementation on the host cores of this box (rank 0 only); `steps` = the steps "
+                               f"actually timed (stops early once {budget:g} s of wall time are spent)"},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -375,8 +387,7 @@ def run_native(args):
         line = {"metric": METRIC, "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (shard or world == 1) else "weak",
                 "vs_baseline": None, "dtype": "f16 operands / f32 accumulate + f32 residual stream", "data": "synthetic",
-                "config": {"workload": f"N={n} views {8 * S}^2 ({S}x{S}x5 latents) DDIM step, cfg {args.cfg} (cond+uncond batched), D=1, "
-                                       f"full-size UNet 1.034B params random-init + GridAttn (BASELINE configs[{1 if S == 32 else 4}])",
+                "config": {"workload": workload_string(args),
                            "mode": ("view-sharded, 1 all-gather/step" if shard else ("replicas" if world > 1 else "single GPU")),
                            "views_per_gpu": q, "cuda_graph": use_graph,
                            "l2": "no flush: every step streams 2.08 GB of fp16 weights (>> 126 MB L2)"},
@@ -393,7 +404,9 @@ def run_native(args):
                 other["mode"] = "ONE scene view-sharded over the GPUs, 1 NCCL all-gather of the 5-channel latents per step (strong scaling)"
                 line["sharded"] = other
         if not args.no_cpu_baseline and world == 1:
-            cb, _ = cpu_arm(args, reps=2, warmup=1, model=model)
+            del model, plan
+            torch.cuda.empty_cache()
+            cb, _, _ = cpu_arm(args, steps=3, warmup=1, budget_s=60.0)
             line["cpu_baseline"] = cb
         emit(line)
     if world > 1:

@@ -95,6 +95,16 @@ typedef struct mvd_gemm_args {
   void* out16;         /* optional (out_mode F32 only): the stored values once more as fp16 [M, ld16] — the operand of the
                           GEMM that consumes this output, written here instead of by a separate cast / concat pass */
   int32_t ld16;
+  /* ABI 9: split-precision ("hi/lo") operands for the few GEMMs whose fp16 operand rounding dominates the end-to-end error
+   * (the stem / head convolutions and the ResBlock 1x1 skip convolutions: they sit on the residual trunk, not on a branch).
+   * hilo = 1: A holds [A_hi | A_lo] (ROWMAJOR: columns [0,K) and [K,2K), lda >= 2K; CONV3X3: 2C channels per pixel) and Wt holds
+   *   [W_hi | W_lo] ([N, 2K], ldw >= 2K) with x_hi = fp16(x), x_lo = fp16(x - x_hi); the kernel accumulates
+   *   A_hi W_hi + A_lo W_hi + A_hi W_lo (three passes over K in one launch; K, C multiples of 64).
+   * out16_lo > 0: next to the fp16 copy `out16` of the output, its rounding residual fp16(v - fp16(v)) is stored out16_lo
+   *   columns to the right (the [hi | lo] operand of a consuming hilo GEMM). */
+  int32_t hilo;
+  int32_t out16_lo;
+  int32_t a_lo_off;    /* ROWMAJOR + hilo: column of A_lo (0 = K); > K when A is a column window of a wider [hi | lo] buffer */
 } mvd_gemm_args;
 
 int mvd_gemm_f16(const mvd_gemm_args* args, void* stream);
@@ -123,6 +133,11 @@ int mvd_attn_self_f16(const void* q, const void* k, const void* vt, void* out, i
  * ---------------------------------------------------------------------------------------------- */
 int mvd_groupnorm_f32_f16(const float* x, const float* gamma, const float* beta, void* y, void* stats_ws,
                           int32_t n_img, int32_t hw, int32_t C, float eps, int32_t apply_silu, void* stream);
+/* the same, written as a split-precision operand y fp16 [n_img*hw, 2C] = [hi | lo], hi = fp16(v), lo = fp16(v - hi): the A operand of a
+ * `hilo` GEMM (the UNet head, GroupNorm32-SiLU-conv 320->5, mvdfusion/unet.py:496-500, whose operand rounding would otherwise land on
+ * the output unattenuated) */
+int mvd_groupnorm_hilo_f32_f16(const float* x, const float* gamma, const float* beta, void* y, int32_t n_img, int32_t hw, int32_t C,
+                               float eps, int32_t apply_silu, void* stream);
 /* GroupNorm of the channel concatenation [x1 | x2] (x1: [n_img, hw, C1], x2: [n_img, hw, C2]) without materialising it:
  * `h = th.cat([h, hs.pop()], dim=1)` followed by ResBlock.in_layers[0] in the UNet's output blocks (mvdfusion/unet.py:550). */
 int mvd_groupnorm2_f32_f16(const float* x1, int32_t C1, const float* x2, int32_t C2, const float* gamma, const float* beta,
@@ -166,8 +181,10 @@ int mvd_gemv_grouped_f16(const float* x, int32_t K, int32_t silu_in, const void*
 int mvd_timestep_embedding(const float* t_dev, const float* freqs_dev, float* out, int32_t dim, void* stream);
 /* UNet input assembly incl. the unconditional CFG branch (mvdfusion/unet.py:153-161,173-186) -> fp16 NHWC */
 /* cond_scale: optional [n_views] multiplier of the concat channels (condition drop, mvdfusion/unet.py:140-151) */
+/* hilo = 1 (Cpad >= 32): channels [0,10) hold fp16(v), [10,20) fp16(v - fp16(v)), [20,30) fp16(v) again — the three K segments of a
+ * split-precision stem convolution laid out as plain input channels (weights [W_hi | W_hi | W_lo]) */
 int mvd_unet_input_f16(const float* noisy, const float* cond, int32_t cond_batched, const float* cond_scale, void* out,
-                       int32_t n_views, int32_t n_img, int32_t hw, int32_t Cpad, void* stream);
+                       int32_t n_views, int32_t n_img, int32_t hw, int32_t Cpad, int32_t hilo, void* stream);
 /* CFG combine (mvdfusion/unet.py:195) + optional DDIM update (mvdfusion/sampler.py:55-65).
  * coef_dev = {a_t, a_prev, sqrt(1-a_t), sigma_t, add_noise, cfg_scale} in device memory. */
 int mvd_cfg_ddim(const float* head, int32_t ld, int32_t two_branch, const float* coef_dev, const float* xt,

@@ -9,7 +9,7 @@ from ctypes import c_char_p, c_float, c_int32, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmvd_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class GemmArgs(ctypes.Structure):
@@ -28,7 +28,7 @@ class GemmArgs(ctypes.Structure):
         ("heads", c_int32), ("dhead", c_int32), ("dpad", c_int32), ("seq", c_int32),
         ("split_k", c_int32), ("tile_n", c_int32), ("cta_pair", c_int32),
         ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_longlong),
-        ("out16", c_void_p), ("ld16", c_int32),
+        ("out16", c_void_p), ("ld16", c_int32), ("hilo", c_int32), ("out16_lo", c_int32), ("a_lo_off", c_int32),
     ]
 
 
@@ -43,6 +43,7 @@ SIGNATURES = {
     "mvd_geglu_row_permutation": [i32, i32, vp],
     "mvd_attn_self_f16": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "mvd_groupnorm_f32_f16": [vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp],
+    "mvd_groupnorm_hilo_f32_f16": [vp, vp, vp, vp, i32, i32, i32, f32, i32, vp],
     "mvd_groupnorm2_f32_f16": [vp, i32, vp, i32, vp, vp, vp, i32, i32, f32, i32, vp],
     "mvd_layernorm_f32_f16": [vp, vp, vp, vp, i32, i32, f32, vp],
     "mvd_ln_modulate_f32_f16": [vp, vp, vp, vp, i32, i32, f32, vp],
@@ -56,7 +57,7 @@ SIGNATURES = {
     "mvd_gemv_f16": [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "mvd_gemv_grouped_f16": [vp, i32, i32, vp, i32, i32, vp],
     "mvd_timestep_embedding": [vp, vp, vp, i32, vp],
-    "mvd_unet_input_f16": [vp, vp, i32, vp, vp, i32, i32, i32, i32, vp],
+    "mvd_unet_input_f16": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp],
     "mvd_cfg_ddim": [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp],
     "mvd_nchw_to_rows_f32": [vp, vp, i32, i32, i32, vp],
     "mvd_rows_to_nchw_f32": [vp, vp, i32, i32, i32, i32, vp],

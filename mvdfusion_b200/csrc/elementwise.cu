@@ -242,7 +242,7 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t_ptr, const flo
 //   cond_scale (optional, [n_views]) multiplies the concat channels of a view (condition drop, unet.py:140-151).
 __global__ void unet_input_kernel(const float* __restrict__ noisy /*[n,5,hw]*/, const float* __restrict__ cond /*[1 or n,5,hw]*/,
                                   int cond_batched, const float* __restrict__ cond_scale, __half* __restrict__ out,
-                                  int n_views, int n_img, int hw, int Cpad) {
+                                  int n_views, int n_img, int hw, int Cpad, int hilo) {
   pdl_trigger();
   pdl_wait();
   const size_t total = static_cast<size_t>(n_img) * hw;
@@ -253,15 +253,24 @@ __global__ void unet_input_kernel(const float* __restrict__ noisy /*[n,5,hw]*/, 
     const int view = img % n_views;
     const bool uncond = img >= n_views;
     __half* o = out + i * Cpad;
-    for (int c = 0; c < 5; ++c) o[c] = __float2half_rn(noisy[(static_cast<size_t>(view) * 5 + c) * hw + pix]);
+    float val[10];
+    for (int c = 0; c < 5; ++c) val[c] = noisy[(static_cast<size_t>(view) * 5 + c) * hw + pix];
     const float* cb = cond + (cond_batched ? static_cast<size_t>(view) * 5 * hw : 0);
     for (int c = 0; c < 5; ++c) {
       float v = uncond ? 0.f : cb[static_cast<size_t>(c) * hw + pix];
       if (cond_scale != nullptr) v *= cond_scale[view];
       if (c < 4) v = v / 0.18215f;
-      o[5 + c] = __float2half_rn(v);
+      val[5 + c] = v;
     }
-    for (int c = 10; c < Cpad; ++c) o[c] = __float2half_rn(0.f);
+    for (int c = 0; c < 10; ++c) {
+      const __half h = __float2half_rn(val[c]);
+      o[c] = h;
+      if (hilo) {
+        o[10 + c] = __float2half_rn(val[c] - __half2float(h));
+        o[20 + c] = h;
+      }
+    }
+    for (int c = hilo ? 30 : 10; c < Cpad; ++c) o[c] = __float2half_rn(0.f);
   }
 }
 
@@ -466,13 +475,13 @@ extern "C" int mvd_timestep_embedding(const float* t_dev, const float* freqs_dev
 }
 
 extern "C" int mvd_unet_input_f16(const float* noisy, const float* cond, int32_t cond_batched, const float* cond_scale,
-                                  void* out, int32_t n_views, int32_t n_img, int32_t hw, int32_t Cpad, void* stream_) {
+                                  void* out, int32_t n_views, int32_t n_img, int32_t hw, int32_t Cpad, int32_t hilo, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!noisy || !cond || !out || n_views <= 0 || (n_img != n_views && n_img != 2 * n_views) || hw <= 0 || Cpad < 10 ||
+  if (!noisy || !cond || !out || n_views <= 0 || (n_img != n_views && n_img != 2 * n_views) || hw <= 0 || Cpad < (hilo ? 32 : 10) ||
       (Cpad & 7))
     return set_error(MVD_EINVAL, "mvd_unet_input_f16: bad arguments");
   MVD_LAUNCH((unet_input_kernel), grid_for(static_cast<size_t>(n_img) * hw), 256, 0, stream, 
-      noisy, cond, cond_batched, cond_scale, static_cast<__half*>(out), n_views, n_img, hw, Cpad);
+      noisy, cond, cond_batched, cond_scale, static_cast<__half*>(out), n_views, n_img, hw, Cpad, hilo ? 1 : 0);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

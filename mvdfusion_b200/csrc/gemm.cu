@@ -71,6 +71,10 @@ struct GemmKParams {
   int acc_stride, tmem_cols;
   __half* out16;            // optional fp16 copy of an F32 output (the next GEMM's operand), [M, ld16]
   int ld16, vec_out16;
+  int out16_lo;             // > 0: the fp16 rounding residual v - fp16(v) is stored too, out16_lo columns to the right
+  // hi/lo split operands (args.hilo): A = [A_hi | A_lo], W = [W_hi | W_lo]; the k-blocks run over three segments
+  // A_hi W_hi, A_lo W_hi, A_hi W_lo (kb_seg k-blocks each).  a_lo_off / w_lo_off: column (channel) offsets of the lo halves.
+  int hilo, kb_seg, a_lo_off, w_lo_off;
 };
 
 __device__ __forceinline__ void store8_f16(__half* dst, const float* v) {
@@ -122,6 +126,56 @@ __device__ __forceinline__ float4 ld4(const float* p, bool vec, int nvalid) {
   if (nvalid > 3) r.w = p[3];
   return r;
 }
+
+// k-block iterator of the TMA producer: the coordinates of the next k-block are kept in registers and advanced with adds and
+// compares only.  (A division per k-block sits on the producer's critical path: the deep-K convolutions lost 12 % when the
+// coordinate code grew by one more runtime division — profiles/r02_gemm_ab_producer.md.)
+// Plain: A column kb*BK (conv: tap (ky, kx), channel block) and the same W column.  hilo: segments 0 / 1 / 2 read
+// (A_hi, W_hi) / (A_lo, W_hi) / (A_hi, W_lo), kb_seg k-blocks each.
+struct KbIter {
+  int a_col, w_col, kx, ky;   // what the TMA loads take
+  int cb, tap, seg, left;     // position: channel block in the tap (plain: k-block in the segment), tap, segment
+  __device__ __forceinline__ void seek(const GemmKParams& p, int kb) {  // the only divisions: once per work unit
+    seg = 0;
+    if (p.hilo) {
+      seg = kb / p.kb_seg;
+      kb -= seg * p.kb_seg;
+    }
+    if (p.a_mode == MVD_A_CONV3X3) {
+      tap = kb / p.kb_per_tap;
+      cb = kb - tap * p.kb_per_tap;
+      ky = tap / 3;
+      kx = tap - ky * 3;
+    } else {
+      tap = 0; ky = 0; kx = 0;
+      cb = kb;
+    }
+    place(p);
+  }
+  __device__ __forceinline__ void place(const GemmKParams& p) {
+    const int a_off = seg == 1 ? p.a_lo_off : 0, w_off = seg == 2 ? p.w_lo_off : 0;
+    a_col = cb * BK + a_off;
+    w_col = (p.a_mode == MVD_A_CONV3X3 ? tap * p.C : 0) + cb * BK + w_off;
+  }
+  __device__ __forceinline__ void next(const GemmKParams& p) {
+    ++cb;
+    a_col += BK;
+    w_col += BK;
+    if (p.a_mode == MVD_A_CONV3X3) {
+      if (cb == p.kb_per_tap) {
+        cb = 0;
+        ++tap;
+        if (++kx == 3) { kx = 0; ++ky; }
+        if (tap == 9) { tap = 0; kx = 0; ky = 0; ++seg; }
+        place(p);
+      }
+    } else if (cb == p.kb_seg) {  // plain GEMM: only the hilo form ever gets here before the unit ends
+      cb = 0;
+      ++seg;
+      place(p);
+    }
+  }
+};
 
 struct Unit {
   int tile, s, m_tile, n_tile, kb0, kb1;
@@ -230,54 +284,37 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
       if (n_local > 0) {
         const Unit t0 = decode_unit(p, first, pair_rank);
         const int npre = min(p.stages, t0.kb1 - t0.kb0);
+        KbIter ki;
+        ki.seek(p, t0.kb0);
         for (int i = 0; i < npre; ++i) {
-          const int kb = t0.kb0 + i;
-          int kcol = kb * BK;
-          if (p.a_mode == MVD_A_CONV3X3) {
-            const int tap = kb / p.kb_per_tap;
-            kcol = tap * p.C + (kb - tap * p.kb_per_tap) * BK;
-          }
-          tma_prefetch_l2_2d(&tmB, kcol, t0.n_tile * p.BN + (PAIR ? pair_rank * b_rows : 0));
+          tma_prefetch_l2_2d(&tmB, ki.w_col, t0.n_tile * p.BN + (PAIR ? pair_rank * b_rows : 0));
+          ki.next(p);
         }
       }
       pdl_wait();
-      int it = 0;
+      int s = 0;          // ring slot and its phase, advanced without divisions
+      uint32_t ph = 0;
       for (int j = 0; j < n_local; ++j) {
         const Unit t = decode_unit(p, first + j * ustride, pair_rank);
-        for (int kb = t.kb0; kb < t.kb1; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        KbIter ki;
+        ki.seek(p, t.kb0);
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (leader) mbar_expect_tx(&full_bar[s], PAIR ? 2 * stage_bytes : stage_bytes);
           uint8_t* sa = smem + s * stage_bytes;
           uint8_t* sb = sa + A_BYTES;
-          int kcol;
           if (PAIR) {
             const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
-            if (p.a_mode == MVD_A_CONV3X3) {
-              const int tap = kb / p.kb_per_tap;
-              const int cb = kb - tap * p.kb_per_tap;
-              const int ky = tap / 3, kx = tap - ky * 3;
-              tma_load_4d_pair(sa, &tmA, lbar, cb * BK, t.x0 + kx - 1, t.y0 + ky - 1, t.img0);
-              kcol = tap * p.C + cb * BK;
-            } else {
-              tma_load_2d_pair(sa, &tmA, lbar, kb * BK, t.m_tile * BM);
-              kcol = kb * BK;
-            }
-            tma_load_2d_pair(sb, &tmB, lbar, kcol, t.n_tile * p.BN + pair_rank * b_rows);
+            if (p.a_mode == MVD_A_CONV3X3) tma_load_4d_pair(sa, &tmA, lbar, ki.a_col, t.x0 + ki.kx - 1, t.y0 + ki.ky - 1, t.img0);
+            else tma_load_2d_pair(sa, &tmA, lbar, ki.a_col, t.m_tile * BM);
+            tma_load_2d_pair(sb, &tmB, lbar, ki.w_col, t.n_tile * p.BN + pair_rank * b_rows);
           } else {
-            if (p.a_mode == MVD_A_CONV3X3) {
-              const int tap = kb / p.kb_per_tap;
-              const int cb = kb - tap * p.kb_per_tap;
-              const int ky = tap / 3, kx = tap - ky * 3;
-              tma_load_4d(sa, &tmA, &full_bar[s], cb * BK, t.x0 + kx - 1, t.y0 + ky - 1, t.img0);
-              kcol = tap * p.C + cb * BK;
-            } else {
-              tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, t.m_tile * BM);
-              kcol = kb * BK;
-            }
-            tma_load_2d(sb, &tmB, &full_bar[s], kcol, t.n_tile * p.BN);
+            if (p.a_mode == MVD_A_CONV3X3) tma_load_4d(sa, &tmA, &full_bar[s], ki.a_col, t.x0 + ki.kx - 1, t.y0 + ki.ky - 1, t.img0);
+            else tma_load_2d(sa, &tmA, &full_bar[s], ki.a_col, t.m_tile * BM);
+            tma_load_2d(sb, &tmB, &full_bar[s], ki.w_col, t.n_tile * p.BN);
           }
+          ki.next(p);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -285,16 +322,15 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
     // ------------------------------------------------------------ UMMA issuer
     if (lane == 0 && leader) {
       const uint32_t idesc = umma_idesc_f16(PAIR ? 2 * BM : BM, p.BN);
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < n_local; ++j) {
         const Unit t = decode_unit(p, first + j * ustride, pair_rank);
         const int buf = j & 1;
         mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * p.acc_stride;
-        for (int kb = t.kb0; kb < t.kb1; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * stage_bytes);
@@ -308,6 +344,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
           }
           if (PAIR) tc_commit_pair(&empty_bar[s], 3);  // frees the slot in BOTH CTAs
           else tc_commit(&empty_bar[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         if (PAIR) tc_commit_pair(&acc_full[buf], 3);
         else tc_commit(&acc_full[buf]);
@@ -519,6 +556,19 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
               if (nvalid > 2) d16[2] = __float2half_rn(v.z);
               if (nvalid > 3) d16[3] = __float2half_rn(v.w);
             }
+            if (p.out16_lo > 0) {  // what the fp16 rounding dropped, as a second fp16 (hi/lo operand of a split-precision GEMM)
+              const float lx = v.x - __half2float(__float2half_rn(v.x)), ly = v.y - __half2float(__float2half_rn(v.y));
+              const float lz = v.z - __half2float(__float2half_rn(v.z)), lw = v.w - __half2float(__float2half_rn(v.w));
+              __half* dl = d16 + p.out16_lo;
+              if (p.vec_out16 && nvalid >= 4) {
+                *reinterpret_cast<uint2*>(dl) = make_uint2(pack_h2(lx, ly), pack_h2(lz, lw));
+              } else {
+                dl[0] = __float2half_rn(lx);
+                if (nvalid > 1) dl[1] = __float2half_rn(ly);
+                if (nvalid > 2) dl[2] = __float2half_rn(lz);
+                if (nvalid > 3) dl[3] = __float2half_rn(lw);
+              }
+            }
           }
         } else if (out_mode == MVD_OUT_F16) {
           __half* dst = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(grow) * p.ldc + col;
@@ -724,7 +774,10 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error(MVD_EINVAL, "mvd_gemm_f16: M, N, K must be positive");
   if (a->A == nullptr || a->Wt == nullptr || a->out == nullptr)
     return set_error(MVD_EINVAL, "mvd_gemm_f16: null A / Wt / out");
-  if ((a->ldw & 7) != 0 || a->ldw < a->K) return set_error(MVD_EALIGN, "mvd_gemm_f16: ldw must be >= K and a multiple of 8");
+  const int hilo = a->hilo ? 1 : 0;
+  if (hilo && ((a->K & 63) != 0 || (a->a_mode == MVD_A_CONV3X3 && (a->C & 63) != 0)))
+    return set_error(MVD_EINVAL, "mvd_gemm_f16: hilo needs K (CONV3X3: C) to be a multiple of 64");
+  if ((a->ldw & 7) != 0 || a->ldw < (hilo ? 2 * a->K : a->K)) return set_error(MVD_EALIGN, "mvd_gemm_f16: ldw must be >= K (2K with hilo) and a multiple of 8");
   if ((reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->Wt) & 15))
     return set_error(MVD_EALIGN, "mvd_gemm_f16: A and Wt must be 16-byte aligned");
   if (a->act < MVD_ACT_NONE || a->act > MVD_ACT_GEGLU) return set_error(MVD_EINVAL, "mvd_gemm_f16: bad act");
@@ -753,6 +806,9 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   p.seq = a->seq;
   p.out16 = static_cast<__half*>(a->out16);
   p.ld16 = a->ld16;
+  p.out16_lo = a->out16 != nullptr ? a->out16_lo : 0;
+  if (p.out16_lo < 0 || (p.out16_lo > 0 && (p.out16_lo < a->N || (p.out16_lo & 3) != 0)))
+    return set_error(MVD_EINVAL, "mvd_gemm_f16: out16_lo must be 0 or a multiple of 4 that is >= N");
   if (a->out16 != nullptr) {
     if (a->out_mode != MVD_OUT_F32 || a->act == MVD_ACT_GEGLU) return set_error(MVD_EINVAL, "mvd_gemm_f16: out16 accompanies an F32 output only");
     if (a->ld16 < a->N) return set_error(MVD_EINVAL, "mvd_gemm_f16: ld16 is smaller than N");
@@ -805,10 +861,14 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
 
   CUtensorMap tmA, tmB;
   if (a->a_mode == MVD_A_ROWMAJOR) {
-    if ((a->lda & 7) != 0 || a->lda < a->K) return set_error(MVD_EALIGN, "mvd_gemm_f16: lda must be >= K and a multiple of 8");
+    if ((a->lda & 7) != 0 || a->lda < (hilo ? 2 * a->K : a->K)) return set_error(MVD_EALIGN, "mvd_gemm_f16: lda must be >= K (2K with hilo) and a multiple of 8");
     p.num_kb = (a->K + BK - 1) / BK;
     p.tiles_m_real = (a->M + BM - 1) / BM;
-    int rc = make_tmap_2d(&tmA, a->A, /*cols=*/a->K, /*rows=*/a->M, /*ld=*/a->lda, BK, BM);
+    p.a_lo_off = a->a_lo_off > 0 ? a->a_lo_off : a->K;  // A_lo may sit further right (a column window of a wider [hi | lo] buffer)
+    p.w_lo_off = a->K;
+    if (hilo && (p.a_lo_off < a->K || (p.a_lo_off & 7) != 0 || a->lda < p.a_lo_off + a->K))
+      return set_error(MVD_EINVAL, "mvd_gemm_f16: a_lo_off must be a multiple of 8 with K <= a_lo_off <= lda - K");
+    int rc = make_tmap_2d(&tmA, a->A, /*cols=*/hilo ? p.a_lo_off + a->K : a->K, /*rows=*/a->M, /*ld=*/a->lda, BK, BM);
     if (rc != MVD_OK) return rc;
   } else if (a->a_mode == MVD_A_CONV3X3) {
     if (a->n_img <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || (a->C & 7) != 0 || !is_pow2(a->W) || a->W > 4096 ||
@@ -829,15 +889,20 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     p.tiles_m_real = p.tiles_x * p.tiles_y * tiles_z;
     p.kb_per_tap = (a->C + BK - 1) / BK;
     p.num_kb = 9 * p.kb_per_tap;
-    int rc = make_tmap_nhwc(&tmA, a->A, a->n_img, a->H, a->W, a->C, BK, p.tw, p.th, p.tn);
+    p.a_lo_off = a->C;       // the image batch holds 2C channels: [hi | lo]
+    p.w_lo_off = 9 * a->C;
+    int rc = make_tmap_nhwc(&tmA, a->A, a->n_img, a->H, a->W, hilo ? 2 * a->C : a->C, BK, p.tw, p.th, p.tn);
     if (rc != MVD_OK) return rc;
   } else {
     return set_error(MVD_EINVAL, "mvd_gemm_f16: bad a_mode");
   }
   {
-    int rc = make_tmap_2d(&tmB, a->Wt, /*cols=*/a->K, /*rows=*/a->N, /*ld=*/a->ldw, BK, pair ? bn / 2 : bn);
+    int rc = make_tmap_2d(&tmB, a->Wt, /*cols=*/hilo ? 2 * a->K : a->K, /*rows=*/a->N, /*ld=*/a->ldw, BK, pair ? bn / 2 : bn);
     if (rc != MVD_OK) return rc;
   }
+  p.hilo = hilo;
+  p.kb_seg = p.num_kb;
+  if (hilo) p.num_kb *= 3;  // A_hi W_hi + A_lo W_hi + A_hi W_lo
   if (p.tiles_m_real != tiles_m_real) return set_error(MVD_EINVAL, "mvd_gemm_f16: internal tile count mismatch");
   p.tiles_m = tiles_mp;
   p.tiles_n = (a->N + bn - 1) / bn;

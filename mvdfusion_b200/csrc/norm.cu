@@ -26,7 +26,7 @@ template <int MAXP>
 __global__ void __launch_bounds__(256, MAXP == 16 ? 2 : (MAXP == 4 ? 4 : 3))  // register budget sized to the pixels a thread keeps: occupancy is what hides the latency here
     gn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ x2, int C1, const float* __restrict__ gamma,
                       const float* __restrict__ beta, __half* __restrict__ y, int hw, int C, int cpg, int gpc, int rows, int csplit,
-                      float eps, int apply_silu) {
+                      float eps, int apply_silu, int ldy, int lo_off) {
   pdl_trigger();
   extern __shared__ __align__(16) uint8_t gn_smem[];
   const int span = gpc * cpg;
@@ -156,8 +156,9 @@ __global__ void __launch_bounds__(256, MAXP == 16 ? 2 : (MAXP == 4 ? 4 : 3))  //
       sc[k] = s_rstd[g] * ga[k];
       sh[k] = be[k] - s_mean[g] * s_rstd[g] * ga[k];
     }
-    uint2* dst = reinterpret_cast<uint2*>(y + static_cast<size_t>(img) * hw * C + c0) + cq;
-    const size_t out_stride4 = static_cast<size_t>(C) >> 2;
+    // ldy = row pitch of y (C, or 2C for the [hi | lo] split-precision form: lo_off > 0 stores fp16(o - fp16(o)) lo_off columns right)
+    uint2* dst = reinterpret_cast<uint2*>(y + static_cast<size_t>(img) * hw * ldy + c0) + cq;
+    const size_t out_stride4 = static_cast<size_t>(ldy) >> 2;
     for (int pb = p_first; pb < (MAXP > 0 ? p_first + 1 : hw); pb += NV * pstep) {
       if (MAXP == 0) {  // the registers hold the last batch only: read this one again (L2)
 #pragma unroll
@@ -181,6 +182,15 @@ __global__ void __launch_bounds__(256, MAXP == 16 ? 2 : (MAXP == 4 ? 4 : 3))  //
       w.x = *reinterpret_cast<uint32_t*>(&h0);
       w.y = *reinterpret_cast<uint32_t*>(&h1);
       dst[static_cast<size_t>(p) * out_stride4] = w;
+      if (lo_off > 0) {
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        __half2 l0 = __floats2half2_rn(o[0] - f0.x, o[1] - f0.y);
+        __half2 l1 = __floats2half2_rn(o[2] - f1.x, o[3] - f1.y);
+        uint2 wl;
+        wl.x = *reinterpret_cast<uint32_t*>(&l0);
+        wl.y = *reinterpret_cast<uint32_t*>(&l1);
+        dst[static_cast<size_t>(p) * out_stride4 + (lo_off >> 2)] = wl;
+      }
     }
     }
   }
@@ -359,7 +369,8 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, __half* __restr
 using namespace mvd;
 
 static int groupnorm_launch(const float* x, const float* x2, int C1, const float* gamma, const float* beta, void* y, int32_t n_img,
-                            int32_t hw, int32_t C, float eps, int32_t apply_silu, cudaStream_t stream) {
+                            int32_t hw, int32_t C, float eps, int32_t apply_silu, cudaStream_t stream, int hilo = 0) {
+  const int ldy = hilo ? 2 * C : C, lo_off = hilo ? C : 0;
   if (!x || !gamma || !beta || !y) return set_error(MVD_EINVAL, "mvd_groupnorm_f32_f16: null pointer");
   if (x2 != nullptr && (C1 <= 0 || C1 >= C || (C1 & 3) != 0 || ((C - C1) & 3) != 0))
     return set_error(MVD_EINVAL, "mvd_groupnorm2_f32_f16: C1 and C2 must be positive multiples of 4");
@@ -423,15 +434,15 @@ static int groupnorm_launch(const float* x, const float* x2, int C1, const float
   const dim3 grid((32 / gpc) * csplit, n_img);
   __half* yh = static_cast<__half*>(y);
   if (best_pp <= 4)
-    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<4>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu));
+    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<4>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu, ldy, lo_off));
   else if (best_pp <= 8)
-    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<8>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu));
+    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<8>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu, ldy, lo_off));
   else if (best_pp <= 12)
-    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<12>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu));
+    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<12>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu, ldy, lo_off));
   else if (best_pp > 16)  // large images (64x64 latents and up): pixels stream through in batches and are read twice
-    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<0>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu));
+    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<0>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu, ldy, lo_off));
   else
-    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<16>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu));
+    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<16>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu, ldy, lo_off));
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -442,6 +453,11 @@ extern "C" int mvd_groupnorm_f32_f16(const float* x, const float* gamma, const f
                                      void* stream_) {
   (void)stats_ws;  // the single-pass kernel keeps its statistics on chip; the argument stays for ABI stability
   return groupnorm_launch(x, nullptr, 0, gamma, beta, y, n_img, hw, C, eps, apply_silu, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mvd_groupnorm_hilo_f32_f16(const float* x, const float* gamma, const float* beta, void* y, int32_t n_img, int32_t hw,
+                                          int32_t C, float eps, int32_t apply_silu, void* stream_) {
+  return groupnorm_launch(x, nullptr, 0, gamma, beta, y, n_img, hw, C, eps, apply_silu, static_cast<cudaStream_t>(stream_), 1);
 }
 
 extern "C" int mvd_groupnorm2_f32_f16(const float* x1, int32_t C1, const float* x2, int32_t C2, const float* gamma,

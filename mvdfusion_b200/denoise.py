@@ -13,6 +13,8 @@ Differences from the reference's schedule of work (results are the same):
   * per-step scalars (t, alpha tables, sigma) and the step's pre-drawn noise are selected on the device from
     tables by a device-resident step counter, so the whole step is one CUDA-graph replay with no host traffic.
 """
+import os
+
 import torch
 
 from . import engine as E
@@ -64,7 +66,9 @@ class StepPlan:
         self.t_dev, self.scal, self.coef = self.stepc[0:1], self.stepc[1:3], self.stepc[4:10]
         self.x_local = self.x[q_first:q_first + q]
         self.noise_local = self.ddim_noise[q_first:q_first + q]
-        self.x_in16 = ops.zeros((n_unet * hw, 16), torch.float16)
+        self.stem_hilo = int(os.environ.get("MVD_HILO", "2")) >= 1
+        self.c_in_pad = 32 if self.stem_hilo else 16
+        self.x_in16 = ops.zeros((n_unet * hw, self.c_in_pad), torch.float16)
         self.pyramid16 = [ops.zeros((n_unet * (S >> l) * (S >> l) * D, E.CTX_DIM), torch.float16)
                           for l in range(len(unet_spec.mult))]
         self.freqs_unet = E.timestep_freqs(unet_spec.mc, dev)
@@ -104,9 +108,10 @@ class StepPlan:
         self.grid_calls = len(b.prog)
         b.W = self.W_unet
         cond = self.input_latent[q_first:q_first + q] if cond_batched else self.input_latent
-        b.prog.append(ops.unet_input(self.x_local, cond, cond_batched, self.cond_scale, self.x_in16, q, n_unet, hw, 16))
+        b.prog.append(ops.unet_input(self.x_local, cond, cond_batched, self.cond_scale, self.x_in16, q, n_unet, hw, self.c_in_pad,
+                                     hilo=self.stem_hilo))
         self.head = E.emit_unet(b, unet_spec, self.x_in16, n_unet, S, D, self.t_dev, self.freqs_unet, self.clipvecs,
-                                self.pyramid16)
+                                self.pyramid16, c_in_pad=self.c_in_pad, stem_hilo=self.stem_hilo)
         self.core_prog = b.prog
 
         # ---- epilogues
@@ -247,7 +252,9 @@ class UNetStagePlan:
         self.stepc = z32(STEPC_LEN)
         self.t_dev, self.coef = self.stepc[0:1], self.stepc[4:10]
         self.eps_out = z32(q, 5, hw)
-        self.x_in16 = ops.zeros((n_unet * hw, 16), torch.float16)
+        self.stem_hilo = int(os.environ.get("MVD_HILO", "2")) >= 1
+        self.c_in_pad = 32 if self.stem_hilo else 16
+        self.x_in16 = ops.zeros((n_unet * hw, self.c_in_pad), torch.float16)
         self.pyramid16 = [ops.zeros((n_unet * (S >> l) * (S >> l) * D, E.CTX_DIM), torch.float16)
                           for l in range(len(unet_spec.mult))]
         self.freqs = E.timestep_freqs(unet_spec.mc, ops.device)
@@ -255,8 +262,9 @@ class UNetStagePlan:
         clipvecs = {p: b.clip_vector(self.clip_ctx, p, n_unet, C) for p, C in unet_spec.st_layers()}
         b.prog.append(ops.cast(self.vol32, self.pyramid16[0], q * hw * D * E.CTX_DIM))
         E.emit_pyramid(b, self.pyramid16, q, S, D)
-        b.prog.append(ops.unet_input(self.x, self.cond, True, self.cond_scale, self.x_in16, q, n_unet, hw, 16))
-        self.head = E.emit_unet(b, unet_spec, self.x_in16, n_unet, S, D, self.t_dev, self.freqs, clipvecs, self.pyramid16)
+        b.prog.append(ops.unet_input(self.x, self.cond, True, self.cond_scale, self.x_in16, q, n_unet, hw, self.c_in_pad, hilo=self.stem_hilo))
+        self.head = E.emit_unet(b, unet_spec, self.x_in16, n_unet, S, D, self.t_dev, self.freqs, clipvecs, self.pyramid16,
+                                c_in_pad=self.c_in_pad, stem_hilo=self.stem_hilo)
         b.prog.append(ops.cfg_ddim(self.head, 8, use_cfg, self.coef, None, None, self.eps_out, None, None, q, hw))
         self.prog = b.prog
 

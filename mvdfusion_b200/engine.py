@@ -109,6 +109,41 @@ class PackedWeights:
             return w.reshape(co, 9 * cp).half()
         return self._put("conv3", (key, c_pad), f)
 
+    @staticmethod
+    def _hilo(w):
+        """fp32 -> (fp16 hi, fp16 lo) with hi + lo == w to ~2^-22 relative (include/mvd_b200.h, mvd_gemm_args.hilo)"""
+        hi = w.half()
+        return hi, (w - hi.float()).half()
+
+    def lin_hilo(self, key):
+        """nn.Linear / 1x1-conv weight [N, K] -> fp16 [N, 2K] = [W_hi | W_lo] (K a multiple of 64)"""
+        def f():
+            w = self.raw(key).float()
+            w = w.reshape(w.shape[0], -1)
+            assert w.shape[1] % 64 == 0
+            return torch.cat(self._hilo(w), dim=1)
+        return self._put("lin_hilo", key, f)
+
+    def conv3_hilo(self, key):
+        """conv3x3 weight [Cout, Cin, 3, 3] -> fp16 [Cout, 2*9*Cin] = [W_hi | W_lo], each half in the implicit-GEMM k order"""
+        def f():
+            w = self.raw(key).float()
+            co, ci = w.shape[0], w.shape[1]
+            assert ci % 64 == 0
+            return torch.cat(self._hilo(w.permute(0, 2, 3, 1).reshape(co, 9 * ci)), dim=1)
+        return self._put("conv3_hilo", key, f)
+
+    def conv3_stem_hilo(self, key, c_pad=32):
+        """stem conv3x3 weight [Cout, Cin <= 10, 3, 3] -> fp16 [Cout, 9*c_pad] for input channels laid out [x_hi | x_lo | x_hi | 0]
+        (mvd_unet_input_f16 with hilo = 1): per tap [W_hi | W_hi | W_lo | 0]"""
+        def f():
+            w = self.raw(key).float()
+            co, ci = w.shape[0], w.shape[1]
+            assert 3 * ci <= c_pad
+            hi, lo = self._hilo(w.permute(0, 2, 3, 1))  # [Cout, ky, kx, Cin]
+            return torch.cat([hi, hi, lo, hi.new_zeros(co, 3, 3, c_pad - 3 * ci)], dim=3).reshape(co, 9 * c_pad)
+        return self._put("conv3_stem_hilo", (key, c_pad), f)
+
     def qkv(self, p):
         """to_q | to_k | to_v fused into one [3C, C] matrix (external/sd1/ldm/modules/attention.py:161-163)"""
         return self._put("qkv", p, lambda: self._pad_k(torch.cat([self.raw(p + ".to_q.weight"), self.raw(p + ".to_k.weight"),
@@ -202,6 +237,9 @@ class Builder:
         self.heads = 8
         # fp16 operands of the 1x1 skip convolutions written by their producers' epilogues (MVD_NO_FUSE_CAT=1: cast / concat passes)
         self.fuse_cat = not os.environ.get("MVD_NO_FUSE_CAT")
+        # split-precision (hi/lo fp16) operands where operand rounding lands on the residual trunk:
+        # level 1 = stem + head convolutions, 2 = also the ResBlock 1x1 skip convolutions; MVD_HILO=0 turns it off (A/B)
+        self.hilo = int(os.environ.get("MVD_HILO", "2"))
 
     # -- buffers
     def t16(self, *shape):
@@ -240,7 +278,7 @@ class Builder:
         # a measured (tile_n, split_k, cta_pair) choice from gemm_tuning.json overrides the library's heuristics.
         act = kw.get("act", ACT_NONE)
         can_split = allow_split and act != ACT_GEGLU and kw.get("qkv") is None
-        sig = gemm_signature(kw.get("conv") is not None, M, N, K,
+        sig = gemm_signature(kw.get("conv") is not None, M, N, K * (3 if kw.get("hilo") else 1),  # hi/lo operands: three passes over K
                              "qkv" if kw.get("qkv") is not None else str(out.dtype).split(".")[-1], kw.get("residual") is not None, act)
         tuned = gemm_tuning().get(sig)
         if tuned is not None and "tile_n" not in kw:
@@ -268,22 +306,27 @@ class Builder:
         return y
 
     def conv3x3(self, a16, wkey, n_img, H, W_, Cin, Cout, *, bias, residual=None, c_pad=None, ldc=None, out=None,
-                rowbias=None, rows_per_group=1, out16=None):
-        """conv_nd(2, Cin, Cout, 3, padding=1) as implicit GEMM (openaimodel.py:107,204,230; unet.py:323,499)"""
+                rowbias=None, rows_per_group=1, out16=None, hilo=False, w=None):
+        """conv_nd(2, Cin, Cout, 3, padding=1) as implicit GEMM (openaimodel.py:107,204,230; unet.py:323,499).
+        hilo: a16 holds 2*Cin channels [hi | lo] and the weights are packed [W_hi | W_lo] (split-precision operands)."""
         M = n_img * H * W_
         cp = c_pad if c_pad is not None else Cin
         if out is None:
             out = self.t32(M, ldc if ldc is not None else Cout)
-        w = self.W.conv3(wkey, c_pad)
+        if w is None:
+            w = self.W.conv3_hilo(wkey) if hilo else self.W.conv3(wkey, c_pad)
         self.gemm(a16, w, out, M, Cout, 9 * cp, allow_split=True, conv=(n_img, H, W_, cp), bias=bias, residual=residual,
-                  rowbias=rowbias, rows_per_group=rows_per_group,
+                  rowbias=rowbias, rows_per_group=rows_per_group, hilo=hilo,
                   ldr=(residual.shape[-1] if residual is not None else 0), ldc=(ldc if ldc is not None else Cout), **self._o16(out16))
         return out
 
     @staticmethod
     def _o16(out16):
-        """out16 = (fp16 tensor or column window, row pitch) -> gemm keywords: the GEMM's epilogue also writes its result there"""
-        return {} if out16 is None else {"out16": out16[0], "ld16": out16[1]}
+        """out16 = (fp16 tensor or column window, row pitch[, column offset of the lo half]) -> gemm keywords: the GEMM's epilogue
+        also writes its result there (and, for a [hi | lo] buffer, the fp16 rounding residual)"""
+        if out16 is None:
+            return {}
+        return {"out16": out16[0], "ld16": out16[1], "out16_lo": out16[2] if len(out16) > 2 else 0}
 
     def cast16(self, x, rows, C):
         y = self.t16(rows, C)
@@ -339,7 +382,10 @@ class Builder:
         res, s = x, None
         if self.W.has(p + ".skip_connection.weight"):
             s = self.t32(M, Cout)
-            if x16 is not None:
+            if x16 is not None and len(x16) > 2 and x16[2]:  # [hi | lo] operand: split-precision skip convolution
+                self.gemm(x16[0], self.W.lin_hilo(p + ".skip_connection.weight"), s, M, Cout, Cin, allow_split=True,
+                          bias=self.W.f32(p + ".skip_connection.bias"), lda=x16[1], hilo=True, a_lo_off=x16[2])
+            elif x16 is not None:
                 self.gemm(x16[0], self.W.lin(p + ".skip_connection.weight"), s, M, Cout, Cin, allow_split=True,
                           bias=self.W.f32(p + ".skip_connection.bias"), lda=x16[1])
             else:
@@ -557,10 +603,13 @@ class UNetSpec:
         return out
 
 
-def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c_in_pad=16):
+def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c_in_pad=16, stem_hilo=False):
     """UNetModel.forward (unet.py:524-556).  x_in16: fp16 NHWC [n_img, S, S, c_in_pad]; clipvecs: dict prefix ->
-    [n_img, C] fp32; pyramid16: list of fp16 [n_img*H_l*H_l*D, 768].  Returns the head output fp32 [n_img*S*S, 8]."""
+    [n_img, C] fp32; pyramid16: list of fp16 [n_img*H_l*H_l*D, 768].  Returns the head output fp32 [n_img*S*S, 8].
+    stem_hilo: x_in16 carries [x_hi | x_lo | x_hi | 0] channels (mvd_unet_input_f16 hilo) for a split-precision stem."""
     b.heads = spec.heads
+    skip_hilo = b.hilo >= 2
+    head_hilo = b.hilo >= 1 and spec.final_ch % 64 == 0
     emb = b.time_mlp(t_dev, freqs, spec.mc, "time_embed.0", "time_embed.2", spec.emb_dim, spec.emb_dim)
     res_blocks = []
     for name, blocks in (("input_blocks", spec.input_blocks), ("middle_block", [spec.middle]), ("output_blocks", spec.output_blocks)):
@@ -589,7 +638,8 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
         sch, sh = outs[len(outs) - 1 - i]
         assert sh == hh
         fused = b.fuse_cat and layers[0][0] == "res" and b.W.has(f"output_blocks.{i}.0.skip_connection.weight")
-        cat16.append((b.t16(n_img * hh * hh, ch + sch), ch, sch) if fused else None)
+        wide = 2 if (skip_hilo and (ch + sch) % 64 == 0 and sch % 64 == 0) else 1  # [hi | lo]: the lo half starts at column ch + sch
+        cat16.append((b.t16(n_img * hh * hh, wide * (ch + sch)), ch, sch, wide) if fused else None)
         for l in layers:
             if l[0] == "res":
                 ch = l[2]
@@ -599,12 +649,12 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
     def skip_window(k):
         """fp16 home of input block k's output: the skip half of its output block's concatenation buffer"""
         c = cat16[len(spec.input_blocks) - 1 - k]
-        return None if c is None else (c[0][:, c[1]:], c[1] + c[2])
+        return None if c is None else (c[0][:, c[1]:], c[3] * (c[1] + c[2]), (c[1] + c[2]) if c[3] == 2 else 0)
 
     def head_window(i):
         """fp16 home of the tensor entering output block i (h half of its concatenation buffer)"""
         c = cat16[i] if i < len(cat16) else None
-        return None if c is None else (c[0][:, :c[1]], c[1] + c[2])
+        return None if c is None else (c[0][:, :c[1]], c[3] * (c[1] + c[2]), (c[1] + c[2]) if c[3] == 2 else 0)
 
     def run_layers(h, prefix, layers, H, start=0, h16=None, last16=None):
         for j, l in enumerate(layers):
@@ -614,7 +664,8 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
             kind = l[0]
             o16 = last16 if j == len(layers) - 1 else None
             if kind == "stem":
-                new = b.conv3x3(h, p + ".weight", n_img, H, H, l[1], l[2], bias=b.W.f32(p + ".bias"), c_pad=c_in_pad, out16=o16)
+                new = b.conv3x3(h, p + ".weight", n_img, H, H, l[1], l[2], bias=b.W.f32(p + ".bias"), c_pad=c_in_pad, out16=o16,
+                                w=b.W.conv3_stem_hilo(p + ".weight", c_in_pad) if stem_hilo else None)
             elif kind == "res":
                 new = b.resblock(h, p, n_img, H, l[1], l[2], emb, spec.emb_dim, x16=h16 if j == 0 else None, out16=o16)
             elif kind == "st":
@@ -652,7 +703,8 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
             assert c16 is None or (c16[1], c16[2]) == (c1, c2)
             nxt = head_window(i + 1)
             new = b.resblock(None, p0, n_img, H, c1 + c2, layers[0][2], emb, spec.emb_dim, cat=(h, skip),
-                             x16=None if c16 is None else (c16[0], c1 + c2), out16=nxt if len(layers) == 1 else None)
+                             x16=None if c16 is None else (c16[0], c16[3] * (c1 + c2), (c1 + c2) if c16[3] == 2 else 0),
+                             out16=nxt if len(layers) == 1 else None)
             b.free(h, skip)
             if c16 is not None:
                 b.free(c16[0])
@@ -662,10 +714,15 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
             b.prog.append(b.ops.concat(h, skip, cat, rows, c1, c2))
             b.free(h, skip)
             h, H = run_layers(cat, f"output_blocks.{i}", layers, H, last16=head_window(i + 1))
-    a = b.groupnorm(h, "out.0", n_img, H * H, spec.final_ch, 1e-5, True)
+    if head_hilo:  # the head's operand rounding would reach the output unattenuated: split-precision operands
+        a = b.t16(n_img * H * H, 2 * spec.final_ch)
+        b.prog.append(b.ops.groupnorm_hilo(h, b.W.f32("out.0.weight"), b.W.f32("out.0.bias"), a, n_img, H * H, spec.final_ch, 1e-5, True))
+    else:
+        a = b.groupnorm(h, "out.0", n_img, H * H, spec.final_ch, 1e-5, True)
     b.free(h)
     head = b.ops.empty((n_img * H * H, 8), torch.float32)
-    b.conv3x3(a, "out.2.weight", n_img, H, H, spec.final_ch, spec.out_channels, bias=b.W.f32("out.2.bias"), ldc=8, out=head)
+    b.conv3x3(a, "out.2.weight", n_img, H, H, spec.final_ch, spec.out_channels, bias=b.W.f32("out.2.bias"), ldc=8, out=head,
+              hilo=head_hilo)
     b.free(a)
     return head
 

@@ -79,13 +79,18 @@ class NativeOps:
     # ------------------------------------------------------------------ GEMM / conv
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
              colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None, cta_pair=0,
-             out16=None, ld16=None):
-        """out16: optional fp16 tensor (or column window of a wider one, row pitch ld16) that receives a copy of an fp32 output."""
+             out16=None, ld16=None, hilo=False, out16_lo=0, a_lo_off=0):
+        """out16: optional fp16 tensor (or column window of a wider one, row pitch ld16) that receives a copy of an fp32 output
+        (out16_lo > 0: and its fp16 rounding residual, out16_lo columns to the right).
+        hilo: split-precision operands A = [A_hi | A_lo], Wt = [W_hi | W_lo] (include/mvd_b200.h, ABI 9); K stays the logical K."""
         g = _lib.GemmArgs()
         g.M, g.N, g.K = M, N, K
         g.A = _ptr(A, torch.float16)
         g.Wt = _ptr(Wt, torch.float16)
         g.ldw = ldw if ldw is not None else Wt.shape[-1]
+        g.hilo = int(bool(hilo))
+        g.out16_lo = int(out16_lo)
+        g.a_lo_off = int(a_lo_off)
         if conv is not None:
             g.a_mode = A_CONV3X3
             g.n_img, g.H, g.W, g.C = conv
@@ -124,9 +129,9 @@ class NativeOps:
         desc = (f"{'conv' if conv is not None else 'lin'} M{M} N{N} K{K} "
                 f"{'qkv' if qkv is not None else ('f32' if out.dtype == torch.float32 else 'f16')}"
                 f"{' res' if residual is not None else ''}{' act%d' % act if act else ''}{' sk' if split_k != 1 else ''}"
-                f"{' +f16' if out16 is not None else ''}")
+                f"{' +f16' if out16 is not None else ''}{' hilo' if hilo else ''}")
         sig = gemm_signature(conv is not None, M, N, K, "qkv" if qkv is not None else str(out.dtype).split(".")[-1], residual is not None, act)
-        meta = {"kernel": "gemm_tc_kernel", "flops": 2.0 * M * N * K, "shape": (M, N, K, split_k), "desc": desc, "sig": sig, "can_split": ws is not None,
+        meta = {"kernel": "gemm_tc_kernel", "flops": 2.0 * M * N * K * (3 if hilo else 1), "shape": (M, N, K, split_k), "desc": desc, "sig": sig, "can_split": ws is not None,
                 "bytes": a_bytes + N * K * 2 + o_bytes + (M * n_out * 4 if residual is not None else 0) + (M * n_out * 2 if out16 is not None else 0)}
         return self._bind("mvd_gemm_f16", (ctypes.byref(g),), keep, meta)
 
@@ -145,6 +150,12 @@ class NativeOps:
                                                     _ptr(stats_ws, torch.float64) if stats_ws is not None else None, n_img, hw, C,
                                                     eps, int(silu)),
                           (x, gamma, beta, y, stats_ws), {"desc": f"img{n_img} hw{hw} C{C}", "bytes": 6.0 * n_img * hw * C})
+
+    def groupnorm_hilo(self, x, gamma, beta, y, n_img, hw, C, eps, silu):
+        """y fp16 [n_img*hw, 2C] = [hi | lo] (split-precision operand)"""
+        return self._bind("mvd_groupnorm_hilo_f32_f16", (_ptr(x, torch.float32), _ptr(gamma, torch.float32), _ptr(beta, torch.float32),
+                                                         _ptr(y, torch.float16), n_img, hw, C, eps, int(silu)),
+                          (x, gamma, beta, y), {"kernel": "groupnorm_f32_f16", "desc": f"img{n_img} hw{hw} C{C} hilo", "bytes": 8.0 * n_img * hw * C})
 
     def groupnorm2(self, x1, C1, x2, C2, gamma, beta, y, n_img, hw, eps, silu):
         return self._bind("mvd_groupnorm2_f32_f16", (_ptr(x1, torch.float32), C1, _ptr(x2, torch.float32), C2, _ptr(gamma, torch.float32),
@@ -210,10 +221,10 @@ class NativeOps:
         return self._bind("mvd_timestep_embedding", (_ptr(t_dev, torch.float32), _ptr(freqs, torch.float32),
                                                      _ptr(out, torch.float32), dim), (t_dev, freqs, out))
 
-    def unet_input(self, noisy, cond, cond_batched, cond_scale, out, n_views, n_img, hw, Cpad):
+    def unet_input(self, noisy, cond, cond_batched, cond_scale, out, n_views, n_img, hw, Cpad, hilo=False):
         return self._bind("mvd_unet_input_f16", (_ptr(noisy, torch.float32), _ptr(cond, torch.float32),
                                                  int(cond_batched), _ptr(cond_scale, torch.float32),
-                                                 _ptr(out, torch.float16), n_views, n_img, hw, Cpad),
+                                                 _ptr(out, torch.float16), n_views, n_img, hw, Cpad, int(hilo)),
                           (noisy, cond, cond_scale, out))
 
     def cfg_ddim(self, head, ld, two_branch, coef, xt, noise, eps_out, x_prev, x0_out, n_views, hw):

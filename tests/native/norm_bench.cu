@@ -67,7 +67,8 @@ static double bench(const Case& c, int iters) {
   return us * c.calls;
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const int iters = argc > 1 ? atoi(argv[1]) : 30;  // `norm_bench 1` under compute-sanitizer
   const Case cs[] = {
       {"gn img16 hw1024 C320 silu", 0, 16, 1024, 320, 1, 16}, {"gn img16 hw256 C640 silu", 0, 16, 256, 640, 1, 14},
       {"gn img16 hw64 C1280 silu", 0, 16, 64, 1280, 1, 14},   {"gn img16 hw16 C1280 silu", 0, 16, 16, 1280, 1, 13},
@@ -80,7 +81,7 @@ int main() {
       {"ln rows65536 C256", 1, 64, 1024, 256, 0, 0},
   };
   double total = 0;
-  for (const Case& c : cs) total += bench(c, 30);
+  for (const Case& c : cs) total += bench(c, iters);
   printf("sum over one step: %.1f us\n", total);
   return 0;
 }

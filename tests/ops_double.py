@@ -45,24 +45,33 @@ class TorchOpsDouble:
     # ------------------------------------------------------------------ GEMM / conv
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
              colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None, cta_pair=0,
-             out16=None, ld16=None):
+             out16=None, ld16=None, hilo=False, out16_lo=0, a_lo_off=0):
         assert A.dtype == torch.float16 and Wt.dtype == torch.float16
         assert out16 is None or (out.dtype == torch.float32 and qkv is None and act != ACT_GEGLU)
         ldw_ = ldw if ldw is not None else Wt.shape[-1]
 
         def fn():
-            W = Wt.reshape(-1)[: N * ldw_].reshape(N, ldw_)[:, :K].float()
+            Wfull = Wt.reshape(-1)[: N * ldw_].reshape(N, ldw_)
+            W = Wfull[:, :K].float()
             if conv is not None:
                 n_img, H, Wd, C = conv
                 assert K == 9 * C and M == n_img * H * Wd
-                x = A.reshape(-1)[: M * C].reshape(n_img, H, Wd, C).float()
-                xp = F.pad(x, (0, 0, 1, 1, 1, 1))
-                cols = [xp[:, ky:ky + H, kx:kx + Wd, :] for ky in range(3) for kx in range(3)]
-                a = torch.cat(cols, dim=-1).reshape(M, K)
+                Ct = 2 * C if hilo else C
+
+                def im2col(x):
+                    xp = F.pad(x, (0, 0, 1, 1, 1, 1))
+                    return torch.cat([xp[:, ky:ky + H, kx:kx + Wd, :] for ky in range(3) for kx in range(3)], dim=-1).reshape(M, K)
+                xall = A.reshape(-1)[: M * Ct].reshape(n_img, H, Wd, Ct).float()
+                a = im2col(xall[..., :C])
+                a_lo = im2col(xall[..., C:]) if hilo else None
             else:
                 lda_ = lda if lda is not None else A.shape[-1]
                 a = torch.as_strided(A, (M, K), (lda_, 1), A.storage_offset()).float()  # A may be a column window of a wider buffer
+                a_lo = torch.as_strided(A, (M, K), (lda_, 1), A.storage_offset() + (a_lo_off or K)).float() if hilo else None
             acc = a @ W.t()
+            if hilo:  # A_hi W_hi + A_lo W_hi + A_hi W_lo
+                assert K % 64 == 0
+                acc = acc + a_lo @ W.t() + a @ Wfull[:, K:2 * K].float().t()
             if bias is not None:
                 acc = acc + bias.reshape(-1)[:N]
             if rowbias is not None:
@@ -101,6 +110,9 @@ class TorchOpsDouble:
                 # out16 may be a column window of a wider buffer: address it from its first element with the row pitch
                 o16 = torch.as_strided(out16, (M, N), (ld16_, 1), out16.storage_offset()) if out16.dim() else out16
                 o16.copy_(acc.half())
+                if out16_lo:
+                    lo = torch.as_strided(out16, (M, N), (ld16_, 1), out16.storage_offset() + out16_lo)
+                    lo.copy_((acc - acc.half().float()).half())
         return self._call(fn)
 
     def attn_self(self, q, k, vt, out, n_img, heads, seq, dhead, dpad, ldo):
@@ -125,6 +137,18 @@ class TorchOpsDouble:
             if silu:
                 o = F.silu(o)
             y.reshape(-1)[: n_img * hw * C].copy_(o.permute(0, 2, 1).reshape(-1).half())
+        return self._call(fn)
+
+    def groupnorm_hilo(self, x, gamma, beta, y, n_img, hw, C, eps, silu):
+        def fn():
+            v = x.reshape(-1)[: n_img * hw * C].reshape(n_img, hw, C).permute(0, 2, 1)
+            o = F.group_norm(v, 32, gamma, beta, eps)
+            if silu:
+                o = F.silu(o)
+            o = o.permute(0, 2, 1).reshape(n_img * hw, C)
+            yy = y.reshape(-1)[: n_img * hw * 2 * C].reshape(n_img * hw, 2 * C)
+            yy[:, :C] = o.half()
+            yy[:, C:] = (o - o.half().float()).half()
         return self._call(fn)
 
     def groupnorm2(self, x1, C1, x2, C2, gamma, beta, y, n_img, hw, eps, silu):
@@ -228,20 +252,25 @@ class TorchOpsDouble:
             out.reshape(-1)[:dim].copy_(torch.cat([torch.cos(a), torch.sin(a)])[:dim])
         return self._call(fn)
 
-    def unet_input(self, noisy, cond, cond_batched, cond_scale, out, n_views, n_img, hw, Cpad):
+    def unet_input(self, noisy, cond, cond_batched, cond_scale, out, n_views, n_img, hw, Cpad, hilo=False):
         def fn():
             o = out.reshape(-1)[: n_img * hw * Cpad].reshape(n_img, hw, Cpad)
             o.zero_()
             nz = noisy.reshape(-1)[: n_views * 5 * hw].reshape(n_views, 5, hw)
             for img in range(n_img):
                 view = img % n_views
-                o[img, :, :5] = nz[view].t().half()
+                v = torch.zeros(hw, 10)
+                v[:, :5] = nz[view].t()
                 if img < n_views:
                     c = cond.reshape(-1, 5, hw)[view if cond_batched else 0].clone()
                     if cond_scale is not None:
                         c = c * cond_scale[view]
                     c[:4] = c[:4] / 0.18215
-                    o[img, :, 5:10] = c.t().half()
+                    v[:, 5:10] = c.t()
+                o[img, :, :10] = v.half()
+                if hilo:  # [hi | lo | hi]: the three K segments of the split-precision stem conv as plain channels
+                    o[img, :, 10:20] = (v - v.half().float()).half()
+                    o[img, :, 20:30] = v.half()
         return self._call(fn)
 
     def cfg_ddim(self, head, ld, two_branch, coef, xt, noise, eps_out, x_prev, x0_out, n_views, hw):

@@ -100,6 +100,76 @@ def test_gemm_fp16_copy_of_the_output(nat, dbl, M, N, K, split):
     assert (gpu_w.cpu().float() - cpu_w.float()).abs().max() <= 2e-3 * cpu_w.float().abs().max()
 
 
+def _hilo16(x):
+    hi = x.half()
+    return hi, (x - hi.float()).half()
+
+
+@pytest.mark.parametrize("M,N,K,split", [(2048, 320, 640, 1), (512, 1280, 2560, 3), (4096, 640, 960, 1), (300, 200, 128, 1)])
+def test_gemm_split_precision_operands(nat, dbl, M, N, K, split):
+    """hilo (ABI 9): A = [A_hi | A_lo], W = [W_hi | W_lo]; the result follows the fp32 operands to ~1e-6 instead of fp16's 5e-4,
+    also when A is a column window of a wider [hi | lo] buffer (a_lo_off > K) and the rounding residual of the output is stored
+    next to its fp16 copy (out16_lo)."""
+    a32, w32 = rnd(M, K), rnd(N, K, seed=1, scale=K ** -0.5)
+    ahi, alo = _hilo16(a32)
+    whi, wlo = _hilo16(w32)
+    pad = 192  # A as a window: columns [pad, pad + K) of a [M, 2 * (pad + K)] buffer, lo half pad + K further right
+    wide = torch.zeros(M, 2 * (pad + K), dtype=torch.float16)
+    wide[:, pad:pad + K], wide[:, 2 * pad + K:] = ahi, alo
+    t = {"A": torch.cat([ahi, alo], 1), "W": torch.cat([whi, wlo], 1), "bias": rnd(N, seed=2), "out": torch.zeros(M, N),
+         "o16": torch.zeros(M, 2 * N + 8, dtype=torch.float16), "ws": torch.zeros(32 << 20, dtype=torch.uint8)}
+    # (o16 is compared as hi + lo below: a 1e-6 difference of the accumulators may move the fp16 rounding of a single value)
+    run_both(nat, dbl, "gemm", t, ["out"], "A", "W", "out", M, N, K, bias="bias", hilo=True, out16="o16", ld16=2 * N + 8,
+             out16_lo=N + 8, split_k=split, ws="ws", tol=2e-5)
+    g = {k: v.cuda() for k, v in t.items()}
+    out_w = torch.zeros(M, N, device="cuda")
+    gw = wide.cuda()
+    nat.gemm(gw[:, pad:], g["W"], out_w, M, N, K, bias=g["bias"], hilo=True, lda=2 * (pad + K), a_lo_off=pad + K)(
+        torch.cuda.current_stream().cuda_stream)
+    nat.gemm(g["A"], g["W"], g["out"], M, N, K, bias=g["bias"], hilo=True, out16=g["o16"], ld16=2 * N + 8, out16_lo=N + 8)(
+        torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    exact = (a32.double() @ w32.double().t() + t["bias"].double()).float()
+    assert (out_w.cpu() - exact).norm() / exact.norm() < 2e-5  # fp16 subnormal granularity of W_lo (2^-24 absolute) bounds it
+    assert (g["out"].cpu() - exact).norm() / exact.norm() < 2e-5  # fp16 subnormal granularity of W_lo (2^-24 absolute) bounds it
+    o16 = g["o16"].cpu().float()
+    assert ((o16[:, :N] + o16[:, N + 8:]) - exact).norm() / exact.norm() < 2e-5  # fp16 subnormal granularity of W_lo (2^-24 absolute) bounds it  # hi + lo of the stored output
+
+
+@pytest.mark.parametrize("n,H,C,Cout", [(2, 32, 320, 5), (3, 16, 128, 64)])
+def test_conv3x3_split_precision(nat, dbl, n, H, C, Cout):
+    """the UNet head (GroupNorm-SiLU-conv 320 -> 5) with [hi | lo] channels and [W_hi | W_lo] weights"""
+    import torch.nn.functional as F
+    M = n * H * H
+    ldc = 8 if Cout == 5 else Cout
+    a32, w32 = rnd(M, C), rnd(Cout, 9 * C, seed=1, scale=(9 * C) ** -0.5)
+    t = {"A": torch.cat(_hilo16(a32), 1), "W": torch.cat(_hilo16(w32), 1), "bias": rnd(Cout, seed=2), "out": torch.zeros(M, ldc),
+         "ws": torch.zeros(32 << 20, dtype=torch.uint8)}
+    run_both(nat, dbl, "gemm", t, ["out"], "A", "W", "out", M, Cout, 9 * C, conv=(n, H, H, C), bias="bias", ldc=ldc, hilo=True,
+             split_k=1, tol=2e-5)
+    g = {k: v.cuda() for k, v in t.items()}
+    nat.gemm(g["A"], g["W"], g["out"], M, Cout, 9 * C, conv=(n, H, H, C), bias=g["bias"], ldc=ldc, hilo=True)(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    x = a32.reshape(n, H, H, C).permute(0, 3, 1, 2).double()
+    w = w32.reshape(Cout, 3, 3, C).permute(0, 3, 1, 2).double()
+    exact = F.conv2d(x, w, t["bias"].double(), padding=1).permute(0, 2, 3, 1).reshape(M, Cout).float()
+    assert (g["out"].cpu()[:, :Cout] - exact).norm() / exact.norm() < 2e-5  # fp16 subnormal granularity of W_lo (2^-24 absolute) bounds it
+
+
+@pytest.mark.parametrize("n,hw,C", [(2, 1024, 320), (3, 4096, 64), (16, 1024, 320)])
+def test_groupnorm_split_precision_output(nat, dbl, n, hw, C):
+    t = {"x": rnd(n * hw, C) * 2 + 0.5, "g": rnd(C, seed=1), "b": rnd(C, seed=2), "y": torch.zeros(n * hw, 2 * C, dtype=torch.float16)}
+    run_both(nat, dbl, "groupnorm_hilo", t, ["y"], "x", "g", "b", "y", n, hw, C, 1e-5, True)
+    y = nat.empty((n * hw, 2 * C), torch.float16)
+    nat.groupnorm_hilo(t["x"].cuda(), t["g"].cuda(), t["b"].cuda(), y, n, hw, C, 1e-5, True)(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    import torch.nn.functional as F
+    exact = F.silu(F.group_norm(t["x"].double().reshape(n, hw, C).permute(0, 2, 1), 32, t["g"].double(), t["b"].double(), 1e-5))
+    exact = exact.permute(0, 2, 1).reshape(n * hw, C).float()
+    got = y.cpu().float()
+    assert ((got[:, :C] + got[:, C:]) - exact).norm() / exact.norm() < 5e-6
+
+
 @pytest.mark.parametrize("n,H,Cin,Cout", [(2, 32, 320, 320), (4, 16, 640, 320), (16, 4, 1280, 1280), (3, 8, 960, 640), (2, 32, 16, 320),
                                           (2, 32, 320, 5)])
 def test_conv3x3(nat, dbl, n, H, Cin, Cout):
@@ -217,6 +287,8 @@ def test_unet_input_cfg_ddim_tables(nat, dbl):
     t = {"noisy": rnd(n, 5, hw), "cond": rnd(1, 5, hw, seed=1), "cs": torch.tensor([1.0, 0.0, 1.0]),
          "out": torch.zeros(2 * n * hw, 16, dtype=torch.float16)}
     run_both(nat, dbl, "unet_input", t, ["out"], "noisy", "cond", False, "cs", "out", n, 2 * n, hw, 16)
+    t32 = dict(t, out=torch.zeros(2 * n * hw, 32, dtype=torch.float16))  # [hi | lo | hi | 0] channels of the split-precision stem
+    run_both(nat, dbl, "unet_input", t32, ["out"], "noisy", "cond", False, "cs", "out", n, 2 * n, hw, 32, hilo=True, tol=0)
     coef = torch.tensor([0.5, 0.6, 0.70710678, 0.2, 1.0, 2.5])
     t = {"head": rnd(2 * n * hw, 8), "coef": coef, "xt": rnd(n, 5, hw, seed=2), "noise": rnd(n, 5, hw, seed=3),
          "eps": torch.zeros(n, 5, hw), "xp": torch.zeros(n, 5, hw), "x0": torch.zeros(n, 5, hw)}

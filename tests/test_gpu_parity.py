@@ -191,6 +191,79 @@ def test_apply_model_sixteen_views_vs_oracle():
     assert record_parity("apply_model_small_N16_vs_oracle", rel_l2(eps, ref), TOL) < TOL
 
 
+# ------------------------------------------------------------------------------------------------ full-size hardening (round 2)
+@pytest.fixture(scope="module")
+def full():
+    """The reference architecture (320 channels, 1.03 B parameters, configs/mvd_gso.yaml:30-46), built once per module."""
+    m = build_model(320, 8, D=1, S=32, device="cuda")
+    return m, state_dict_cpu(m)
+
+
+def _full_apply(m, sd, N, S, D, seed, t_val, query=None, cfg=2.5):
+    sc = synthetic.scene_inputs(N, S, seed=seed)
+    de, _ = synthetic.step_noises(N, D, S, 1, seed=seed + 1)
+    t = torch.full((N,), t_val, dtype=torch.long)
+    eps = m.apply_model(sc["x_T"].cuda(), cams_of(sc["cams"], "cuda"), sc["input_latents"].cuda(), cams_of(sc["in_cams"], "cuda"),
+                        sc["clip_v_embed"].cuda(), t.cuda(), cfg_scale=cfg, depth_eps=de[0].cuda())
+    ref = O.apply_model(sd, sc["x_T"], sc["cams"], sc["input_latents"], sc["in_cams"], sc["clip_v_embed"], t, de[0],
+                        unet_cfg=unet_cfg_of(m), D=D, cfg_scale=cfg, query=query)
+    assert torch.isfinite(eps).all()
+    return (eps if query is None else eps[query]), ref
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+@pytest.mark.parametrize("t_val", [981, 501, 21])
+def test_apply_model_full_size_seed_timestep_sweep(full, seed, t_val):
+    """3 seeds x the first / middle / last DDIM timestep: the 1e-3 gate must hold with margin, not on one lucky draw."""
+    m, sd = full
+    eps, ref = _full_apply(m, sd, 2, 32, 1, seed, t_val)
+    assert record_parity(f"apply_model_full_size_N2_seed{seed}_t{t_val}_vs_oracle", rel_l2(eps, ref), TOL_FULL) < TOL_FULL
+
+
+def test_ddim_loop_full_size_ten_steps_vs_oracle(full):
+    """SURVEY.md §8(d) parity gate: x_0 after the full loop with injected noise.  Full-size model, N = 2, 10-step DDIM
+    (mvdfusion/sampler.py:119-142 via _make_schedule(10)), cfg 2.5; every x_t and x_0 against O.ddim_sample."""
+    m, sd = full
+    steps, N, S, D = 10, 2, 32, 1
+    m.ddim._make_schedule(steps, "uniform", 1.0)
+    try:
+        sc = synthetic.scene_inputs(N, S, seed=21)
+        de, dn = synthetic.step_noises(N, D, S, steps, seed=22)
+        x, inter = m.ddim.sample(cams_of(sc["cams"], "cuda"), sc["input_latents"].cuda(), cams_of(sc["in_cams"], "cuda"),
+                                 sc["clip_v_embed"].cuda(), unconditional_scale=2.5, depth=True, return_intermediates=True,
+                                 verbose=False, x_T=sc["x_T"], depth_eps=de, ddim_noise=dn)
+        ref, rinter = O.ddim_sample(sd, sc["x_T"], sc["cams"], sc["input_latents"], sc["in_cams"], sc["clip_v_embed"], de, dn,
+                                    unet_cfg=unet_cfg_of(m), D=D, num_steps=steps, eta=1.0, cfg_scale=2.5, return_intermediates=True)
+    finally:
+        m.ddim._make_schedule(50, "uniform", 1.0)
+    worst = max(rel_l2(a["xt"], b["xt"]) for a, b in zip(inter, rinter))
+    record_parity("ddim10_full_size_worst_xt_vs_oracle", worst, TOL_FULL)
+    assert worst < TOL_FULL
+    assert record_parity("ddim10_full_size_x0_vs_oracle", rel_l2(x, ref), TOL_FULL) < TOL_FULL
+
+
+def test_apply_model_full_size_three_depth_samples_vs_oracle():
+    """configs/mvd_train.yaml:28 (n_pts_per_ray = 3) on the full-size architecture: 3-key per-pixel view cross-attention."""
+    m = build_model(320, 8, D=3, S=32, device="cuda")
+    eps, ref = _full_apply(m, state_dict_cpu(m), 2, 32, 3, 31, 641)
+    assert record_parity("apply_model_full_size_D3_vs_oracle", rel_l2(eps, ref), TOL_FULL) < TOL_FULL
+
+
+def test_apply_model_full_size_64x64_latents_vs_oracle():
+    """BASELINE configs[4] on the full-size architecture: 64x64 latents (4096-token self-attention, M = 8192 rows per view pair)."""
+    m = build_model(320, 8, D=1, S=64, device="cuda")
+    eps, ref = _full_apply(m, state_dict_cpu(m), 1, 64, 1, 41, 441)
+    assert record_parity("apply_model_full_size_S64_vs_oracle", rel_l2(eps, ref), TOL_FULL) < TOL_FULL
+
+
+def test_apply_model_full_size_sixteen_views_subset_vs_oracle(full):
+    """BASELINE configs[2]'s view count on the full-size architecture: 16-way view attention (262 144 token rows), 32 UNet
+    images; the CPU oracle evaluates query views 3 and 12."""
+    m, sd = full
+    eps, ref = _full_apply(m, sd, 16, 32, 1, 51, 301, query=[3, 12])
+    assert record_parity("apply_model_full_size_N16_views3and12_vs_oracle", rel_l2(eps, ref), TOL_FULL) < TOL_FULL
+
+
 def test_view_shards_reproduce_the_full_batch_on_one_gpu():
     """The per-rank programs of a 2-way and a 4-way view shard (built on this one GPU, no collective needed for a single
     apply_model) give the rows of the unsharded result: sharding changes M of every GEMM, not the numbers beyond fp16
