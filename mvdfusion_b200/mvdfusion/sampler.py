@@ -129,6 +129,10 @@ class DDIMSampler:
         plan.x.copy_(x.reshape(B, 5, S * S))
         inter = []
         group = model.view_group
+        if group is not None and x_T is None:
+            # every rank drew its own x_T: the owning rank's rows are the authoritative ones (GridAttn of step 0 must see the
+            # latents the owners denoise), so exchange them once before the loop
+            model.gather_views(plan)
         if host_io:
             pin = (lambda t: t.pin_memory()) if device.type == "cuda" else (lambda t: t)
             rows_h, de_h, dn_h = pin(rows.contiguous()), pin(depth_eps.float().cpu().contiguous()), pin(ddim_noise.float().cpu().contiguous())
@@ -175,14 +179,26 @@ class DDIMSampler:
         total = self.ddim_timesteps.shape[0]
         B = x.shape[0]
         prev_depth, inter = None, []
+        model = self.model
+        sharded = model.view_group is not None
+        if sharded:  # rank-local rows of the initial latents are authoritative (each rank may have drawn its own x_T)
+            x = model.all_gather_rows(model.local_rows(x))
         for i, step in enumerate(np.flip(self.ddim_timesteps)):
             index = total - i - 1
             t = torch.full((B,), int(step), device=x.device, dtype=torch.long)
             if self.overwrite_x_noisy:
                 x[0] = input_latents[0].clone()
-            x, x0 = self.denoise_apply(x, batch_cameras, input_latents, input_cameras, clip_embed, t, index,
-                                       is_step0=index == 0, prev_depth=prev_depth if self.feed_prev_depth else None,
-                                       cfg_scale=cfg_scale)
+            if not sharded:
+                x, x0 = self.denoise_apply(x, batch_cameras, input_latents, input_cameras, clip_embed, t, index,
+                                           is_step0=index == 0, prev_depth=prev_depth if self.feed_prev_depth else None,
+                                           cfg_scale=cfg_scale)
+            else:
+                # view-sharded: apply_model returns the predicted noise of THIS rank's views only; update those rows and
+                # exchange the updated latents (and x_0, which feeds prev_depth) with one all-gather each
+                kw = dict(prev_depth=prev_depth) if self.feed_prev_depth else {}
+                eps = model.apply_model(x, batch_cameras, input_latents, input_cameras, clip_embed, t, cfg_scale=cfg_scale, **kw)
+                xl, x0l = self.denoise_apply_impl(model.local_rows(x), index, eps, is_step0=index == 0)
+                x, x0 = model.all_gather_rows(xl), model.all_gather_rows(x0l)
             prev_depth = x0[:, 4:].clone()
             inter.append({"t": int(step), "xt": x, "x0": x0})
         return (x, inter) if return_intermediates else x

@@ -9,7 +9,8 @@ import torch
 import torch.nn as nn
 
 from .. import engine as E
-from ..runtime import WeightCache, current_stream, get_ops
+from .. import runtime
+from ..runtime import WeightCache, current_stream
 
 
 def zero_module(module):
@@ -44,7 +45,7 @@ class NativeModule(nn.Module):
         return next(self.parameters()).device
 
     def _plan(self, key, make):
-        ops = get_ops(self._device())
+        ops = runtime.get_ops(self._device())
         cache = self.__dict__.setdefault("_mvd_cache", WeightCache())
         cache.get(self, ops)
         if key not in cache.plans:

@@ -4,6 +4,8 @@ Parameter containers with the reference's names (`input_blocks.i.j…`, `middle_
 `time_embed.*`) and native forwards: the whole UNet pass is one compiled program of sm_100a kernel calls
 (engine.emit_unet), never a layer-by-layer PyTorch walk.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -93,6 +95,13 @@ class UNetModel(NativeModule):
             raise NotImplementedError("UNetModel.forward: square latents, one context token, one shared timestep")
         D = volume_feats[0].shape[3]
         spec = self.spec
+        # split-precision stem (engine.PackedWeights.conv3_stem_hilo): the input goes in as [x_hi | x_lo | x_hi] channels, each exactly
+        # representable in fp16 — boundary glue in torch, the denoising loop does the same inside mvd_unet_input_f16
+        stem_hilo = int(os.environ.get("MVD_HILO", "2")) >= 1 and 3 * C <= 32
+        if stem_hilo:
+            hi = x.float().half().float()
+            x = torch.cat([hi, (x.float() - hi).half().float(), hi], dim=1)
+            C = 3 * C
         cpad = E._round_up(C, 16)
 
         def make(plan, b):
@@ -113,7 +122,7 @@ class UNetModel(NativeModule):
                 v16 = b.ops.empty((n * h * h * D, E.CTX_DIM), torch.float16)
                 b.prog.append(b.ops.cast(v32, v16, v32.numel()))
                 pyr.append(v16)
-            head = E.emit_unet(b, spec, x16, n, S, D, t_dev, E.timestep_freqs(spec.mc, b.ops.device), clipvecs, pyr, c_in_pad=cpad)
+            head = E.emit_unet(b, spec, x16, n, S, D, t_dev, E.timestep_freqs(spec.mc, b.ops.device), clipvecs, pyr, c_in_pad=cpad, stem_hilo=stem_hilo)
             out = b.ops.empty((n, spec.out_channels, S * S), torch.float32)
             b.prog.append(b.ops.rows_to_nchw(head, out, n, spec.out_channels, 8, S * S))
             plan.outputs["y"] = out
@@ -121,7 +130,7 @@ class UNetModel(NativeModule):
         feeds = {"x": x, "ctx": context, "t": torch.tensor([t0])}
         for l, v in enumerate(volume_feats):
             feeds[f"vol{l}"] = v
-        return self._execute(self._plan(("fwd", n, S, D), make), feeds).reshape(n, spec.out_channels, S, S)
+        return self._execute(self._plan(("fwd", n, S, D, stem_hilo), make), feeds).reshape(n, spec.out_channels, S, S)
 
     def get_cross_attn_parameters(self, finetune_cross_attn, finetune_view_attn):
         """mvdfusion/unet.py:558-571"""
@@ -183,8 +192,9 @@ class UNetWrapper(nn.Module):
 
     def _stage(self, n, S, D, use_cfg):
         um = self.unet_model
-        from ..runtime import WeightCache, get_ops
-        ops = get_ops(um._device())
+        from .. import runtime
+        from ..runtime import WeightCache
+        ops = runtime.get_ops(um._device())
         cache = um.__dict__.setdefault("_mvd_cache", WeightCache())
         cache.get(um, ops)
         key = ("stage", n, S, D, use_cfg)
@@ -214,8 +224,8 @@ class UNetWrapper(nn.Module):
 
     def get_volume_feats_pyramid(self, volume_feats):
         """mvdfusion/unet.py:198-209 as a standalone call: (b,h,w,d,c) -> list of 'area'-pooled levels."""
-        from ..runtime import get_ops
-        ops = get_ops(volume_feats.device)
+        from .. import runtime
+        ops = runtime.get_ops(volume_feats.device)
         b, h, w, d, c = volume_feats.shape
         v16 = ops.empty((b * h * w * d, c), torch.float16)
         stream = current_stream(volume_feats.device)

@@ -11,7 +11,8 @@ import torch.nn as nn
 
 from ..config import instantiate_from_config, load_model_from_config
 from ..denoise import StepPlan
-from ..runtime import WeightCache, current_stream, get_ops
+from .. import runtime
+from ..runtime import WeightCache, current_stream
 from .cameras import PerspectiveCameras, relative_cameras
 from .embedder import timestep_embedding
 from .sampler import DDIMSampler
@@ -89,9 +90,27 @@ class ViewFusion(nn.Module):
         group = self.view_group[0]
         dist.all_gather_into_tensor(plan.x.view(-1), plan.x_local.reshape(-1), group=group)
 
+    def local_rows(self, t):
+        """rows (views) of a full-batch tensor that this rank owns under view sharding (all rows when not sharded)"""
+        if self.view_group is None:
+            return t
+        _, rank, world = self.view_group
+        q = t.shape[0] // world
+        return t[rank * q:(rank + 1) * q]
+
+    def all_gather_rows(self, t_local):
+        """inverse of local_rows: concatenate every rank's rows (one all-gather)"""
+        if self.view_group is None:
+            return t_local
+        import torch.distributed as dist
+        group, _, world = self.view_group
+        out = t_local.new_empty((world * t_local.shape[0],) + tuple(t_local.shape[1:]))
+        dist.all_gather_into_tensor(out.view(-1), t_local.contiguous().view(-1), group=group)
+        return out
+
     # ------------------------------------------------------------------ plans
     def step_plan(self, n_views, S, D, use_cfg, use_depth_override=False, use_cond_scale=False):
-        ops = get_ops(self._device.device)
+        ops = runtime.get_ops(self._device.device)
         sd = self._cache.get(self, ops)
         q_first, q_count = 0, n_views
         if self.view_group is not None:
@@ -178,7 +197,7 @@ class ViewFusion(nn.Module):
 
     def embed_time(self, t):
         """mvdfusion/viewfusion_zero_depth_rgb.py:276-279 as a standalone call (host-side helper: the loop computes it in-program)."""
-        ops = get_ops(self._device.device)
+        ops = runtime.get_ops(self._device.device)
         W = self._cache.pack(self, ops)
         te = timestep_embedding(t, self.time_embed_dim).float().contiguous()
         n = te.shape[0]
@@ -192,7 +211,8 @@ class ViewFusion(nn.Module):
     # ------------------------------------------------------------------ the hot path
     def apply_model(self, noisy_latents, batch_cameras, input_latents, input_cameras, clip_v_embed, t, prev_depth=None,
                     cfg_scale=1.0, depth_eps=None, drop_random=None):
-        """mvdfusion/viewfusion_zero_depth_rgb.py:282-345 -> predicted noise (B,5,S,S).
+        """mvdfusion/viewfusion_zero_depth_rgb.py:282-345 -> predicted noise (B,5,S,S); under view sharding (shard_views) the
+        predicted noise of THIS rank's views only, (B/world,5,S,S) — callers slice with local_rows / all_gather_rows.
         depth_eps (B,D,S,S) / drop_random (B,) optionally inject the draws of GridAttn's depth jitter (:431 of
         view_attn_efficient2.py) and of the condition-drop scheme (unet.py:120)."""
         B, _, S, _ = noisy_latents.shape
@@ -252,7 +272,8 @@ class ViewFusion(nn.Module):
         kw = dict(prev_depth=input_latents[:, 4:].clone()) if self.feed_prev_depth else {}
         pred = self.apply_model(noisy, batch_cameras, input_latents, input_cameras, clip_v_embed, t, **kw)
         target = noise if self.objective == "noise" else batch_latents
-        return self.loss_fn(target, pred).mean()
+        # under view sharding apply_model returns this rank's views only: the loss is the mean over the local rows
+        return self.loss_fn(self.local_rows(target), pred).mean()
 
     def forward(self, batch, trainer_config):
         return self.p_losses(batch, trainer_config)

@@ -1,8 +1,8 @@
 """Per-process runtime glue: one NativeOps handle per CUDA device, weight-pack caches keyed on parameter versions.
 
-There is no CPU execution path in the product: asking for ops on a non-CUDA device raises.  (`_OPS_OVERRIDE`
-exists so that tests/ can substitute a recording / emulating double for the C library to check the host-side
-program logic on a GPU-less box; nothing in the package sets it.)
+There is no CPU execution path in the product: asking for ops on a non-CUDA device raises.  (The modules call
+`runtime.get_ops(...)` through the module attribute, so tests/ can monkeypatch that one function with an emulating double of
+the C library to check the host-side program logic on a GPU-less box; the package itself has no dispatch seam.)
 """
 import torch
 
@@ -10,13 +10,10 @@ from .engine import PackedWeights
 from .ops import MvdError, NativeOps
 
 _OPS = {}
-_OPS_OVERRIDE = None
 
 
 def get_ops(device):
     device = torch.device(device)
-    if _OPS_OVERRIDE is not None:
-        return _OPS_OVERRIDE(device)
     if device.type != "cuda":
         raise MvdError(
             f"mvdfusion_b200 runs on CUDA (sm_100a) only; got tensors on '{device}'. There is no CPU fallback — "

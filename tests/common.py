@@ -72,3 +72,48 @@ def record_parity(name, value, tol):
         pass
     print(f"parity {name}: rel-L2 {value:.3e} (tolerance {tol:g})")
     return value
+
+
+# ---- deterministic stand-ins for the frozen encoders (outside the hot path; weights not available offline), shared by
+#      tests/golden/make_golden_prepare_batch.py (patched onto the REFERENCE's ViewFusion) and tests/test_boundary.py
+def standin_vae_encode(images, z_scale=0.18215):
+    """(S,3,H,W) in [0,1] -> (S,4,H/8,W/8): 8x8 area pooling of the normalised image + a 4th channel (their mean), x z_scale"""
+    x = torch.clip(images * 2 - 1.0, -1.0, 1.0)
+    p = torch.nn.functional.avg_pool2d(x, 8)
+    return torch.cat([p, p.mean(dim=1, keepdim=True)], dim=1) * z_scale
+
+
+def standin_clip_encode(images):
+    """(S,3,H,W) -> (S,1,768)"""
+    m = images.mean(dim=(1, 2, 3)).reshape(-1, 1, 1)
+    return torch.sin(torch.linspace(0.0, 20.0, 768).reshape(1, 1, 768) * (1.0 + m))
+
+
+def synthetic_dataset_batch(n_views=9, side=64, seed=0):
+    """A dataset-style batch (README.md:87-96 of the reference): images, depths, R, T, f, c of `n_views` look-at cameras in an
+    arbitrarily rotated world frame (so that the relative-camera step has something to undo)."""
+    g = torch.Generator().manual_seed(seed)
+    R, T, f, p = synthetic.gso_rig(n_views - 1)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    if torch.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return {"images": torch.rand(n_views, 3, side, side, generator=g), "depths": torch.rand(n_views, 1, side, side, generator=g),
+            "R": torch.einsum("ij,bjk->bik", q, R).contiguous(), "T": T.clone(), "f": f.clone(), "c": p.clone()}
+
+
+class fast_init:
+    """Context manager: parameter initialisers become no-ops (shapes / names are what a structural test needs; drawing 1.1 B random
+    numbers takes most of a minute on the CPU)."""
+    NAMES = ("kaiming_uniform_", "kaiming_normal_", "uniform_", "normal_", "trunc_normal_", "xavier_uniform_", "xavier_normal_")
+
+    def __enter__(self):
+        import torch.nn.init as I
+        self.saved = {n: getattr(I, n) for n in self.NAMES}
+        for n in self.NAMES:
+            setattr(I, n, lambda t, *a, **k: t)
+        return self
+
+    def __exit__(self, *exc):
+        import torch.nn.init as I
+        for n, f in self.saved.items():
+            setattr(I, n, f)

@@ -1,7 +1,9 @@
-"""-m gpu: the product (sm_100a kernels through the C ABI) against the oracle on identical latents / cameras / timesteps /
-noise.  Tolerance: rel-L2 <= 2e-3 per denoiser call for fp16 tensor-core operands with fp32 accumulation and an fp32
-residual stream (north star asks 1e-3 at "a stated fp16/bf16 tolerance"; SURVEY.md §7 measured 1.35e-3 for the
-reference itself under fp16 autocast); geometry / schedule scalars are fp32 and checked tighter."""
+"""-m gpu: the product (sm_100a kernels through the C ABI) against the oracle / the reference goldens on identical latents, cameras,
+timesteps and noise.  Gate: rel-L2 <= 1e-3 per denoiser call — BASELINE.json's north-star figure — for EVERY case (fp16 tensor-core
+operands, fp32 accumulation, fp32 residual stream, split-precision stem / head / skip convolutions).  Measured on B200 (round 2,
+profiles/r02_parity.jsonl): 6.7e-4 .. 7.1e-4 at full size over 3 seeds x 3 timesteps and at D=3 / 64x64 latents / 16 views,
+3.1e-4 for x_0 after a 10-step full-size DDIM loop, 3.9e-4 .. 9.2e-4 for the 64-channel test models.  Geometry / schedule
+scalars are fp32 and checked tighter in tests/test_gpu_ops.py."""
 import os
 
 import pytest
@@ -12,12 +14,8 @@ from mvdfusion_b200.mvdfusion.cameras import PerspectiveCameras
 from oracle import mvd_oracle as O
 
 pytestmark = pytest.mark.gpu
-TOL = 2e-3
-# BASELINE.json's north star asks for 1e-3 rel-L2 on the reference's own architecture: the full-size (320-channel, 1.03 B parameter)
-# cases are gated at exactly that (measured 9.4e-4 .. 9.5e-4, profiles/r01_parity_v8.jsonl; the kernels are deterministic, so the
-# figure does not move between runs); the 64-channel test models have fewer terms per dot product to average the fp16 operand
-# rounding over and keep the 2e-3 gate (measured 5.8e-4 .. 1.08e-3).
-TOL_FULL = 1e-3
+TOL = 1e-3        # the 64-channel test models
+TOL_FULL = 1e-3   # the reference architecture (320 channels, 1.03 B parameters); the kernels are deterministic (no atomics on data)
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_outputs.pt")
 
 
@@ -83,8 +81,8 @@ def test_ddim_loop_small_vs_reference_golden(small, use_graph):
                              sc["clip_v_embed"].cuda(), unconditional_scale=gold["cfg"], depth=True, return_intermediates=True,
                              verbose=False, x_T=sc["x_T"], depth_eps=de, ddim_noise=dn, use_graph=use_graph)
     for a, b in zip(inter, gold["xt"]):
-        assert rel_l2(a["xt"], b) < 2 * TOL
-    assert record_parity(f"ddim4_x0_vs_reference_golden_graph{int(use_graph)}", rel_l2(x, gold["x0"]), 2 * TOL) < 2 * TOL
+        assert rel_l2(a["xt"], b) < TOL
+    assert record_parity(f"ddim4_x0_vs_reference_golden_graph{int(use_graph)}", rel_l2(x, gold["x0"]), TOL) < TOL
 
 
 def test_ddim_loop_host_streamed_inputs_match_the_device_tables(small):
