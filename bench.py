@@ -271,7 +271,7 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(sharded):
+    def timed_loop(sharded, model=model, n=n, S=S, rows=rows, de=de, dn=dn, K=K, min_ms=2000.0):
         """W warm-up + K timed denoising steps of one scene per rank (replicas) or of one scene over all ranks (sharded);
         returns (max-over-ranks ms for the K steps, plan, scene, cameras)."""
         if sharded:
@@ -286,17 +286,17 @@ def run_native(args):
         plan_.set_tables(rows, de, dn)
 
         def one_step():
-            plan_.loop_step(stream, use_graph=use_graph)
-            if sharded:
-                model.gather_views(plan_)
+            plan_.loop_step(stream, use_graph=use_graph)  # sharded: the all-gather of the latents is the last call of the step graph
 
         for _ in range(max(Wm, 3)):
             one_step()
         # EXACTLY K steps per repetition between barrier + synchronize, CUDA events on the launching stream, max over ranks;
         # repeated (>= 3 times, >= 2 s of timed work) and the MEDIAN repetition is the reported one
         reps_ms, reps = [], args.reps
+        x_start = plan_.x.clone()  # every repetition denoises the same latents from the same schedule position
         while True:
             plan_.counter.fill_(Wm)
+            plan_.x.copy_(x_start)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
@@ -311,7 +311,7 @@ def run_native(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ms_ = float(t)
             reps_ms.append(ms_)
-            done = len(reps_ms) >= reps if reps > 0 else (len(reps_ms) >= 3 and sum(reps_ms) >= 2000.0)
+            done = len(reps_ms) >= reps if reps > 0 else (len(reps_ms) >= 3 and sum(reps_ms) >= min_ms)
             if world > 1:  # one decision for all ranks
                 flag = torch.tensor([1 if done else 0], device=dev)
                 dist.broadcast(flag, 0)
@@ -329,6 +329,45 @@ def run_native(args):
         o_scenes = world if shard else 1
         other = {"value": o_scenes * K / (o_ms * 1e-3), "unit": "steps/s", "ms_per_step": o_ms / K, "views_per_gpu": o_plan.q,
                  "finite": bool(torch.isfinite(o_plan.x).all())}
+    extra = {}
+    if world > 1:
+        # ---- the view-sharded trajectory against the single-GPU one, on hardware: 4 DDIM steps from the same x_T / noise through
+        #      the public sampler, once with the views sharded over the ranks (NCCL all-gather inside the step graph), once unsharded
+        sc4 = synthetic.scene_inputs(n, S, seed=0)
+        de4, dn4 = synthetic.step_noises(n, D, S, 4, seed=1)
+        model.ddim._make_schedule(4, "uniform", 1.0)
+        outs = []
+        for sharded_ in (True, False):
+            if sharded_:
+                model.shard_views()
+            else:
+                model.view_group = None
+            outs.append(model.ddim.sample(cam(sc4["cams"]), sc4["input_latents"].to(dev), cam(sc4["in_cams"]), sc4["clip_v_embed"].to(dev),
+                                          unconditional_scale=args.cfg, depth=True, verbose=False, x_T=sc4["x_T"], depth_eps=de4, ddim_noise=dn4))
+        model.ddim._make_schedule(50, "uniform", 1.0)
+        rel = ((outs[0] - outs[1]).norm() / outs[1].norm()).reshape(1)
+        dist.all_reduce(rel, op=dist.ReduceOp.MAX)
+        extra["rel_l2_vs_unsharded"] = float(rel)
+        if other is not None and not shard:
+            other["rel_l2_vs_unsharded"] = float(rel)
+            other["rel_l2_note"] = "x_0 of a 4-step DDIM loop, views sharded over the ranks vs all views on one GPU (max over ranks); differs only by fp16 rounding of differently shaped GEMM batches"
+    if world == 8 and os.environ.get("MVD_BENCH_EXTRA", "1") != "0" and S == 32 and n == 8:
+        # ---- BASELINE configs[2] (N = 16 views, 2 views per GPU) and configs[4] (N = 8 views at 512^2 = 64x64 latents, 1 view per GPU),
+        #      both view-sharded over the 8 GPUs with the in-graph all-gather; fewer steps, 3 repetitions each
+        Kx = min(K, 20)
+        def extra_cfg(nx, Sx, mdl):
+            dex1, dnx1 = synthetic.step_noises(nx, D, Sx, Kx + Wm, seed=1)
+            rowsx = torch.stack([mdl.ddim.step_row(49 - (i % 50), args.cfg) for i in range(Kx + Wm)])
+            ms_x, plan_x, _, _, _ = timed_loop(True, model=mdl, n=nx, S=Sx, rows=rowsx, de=dex1, dn=dnx1, K=Kx, min_ms=0.0)
+            fx = step_flops(nx, Sx, D, args.cfg)
+            return {"workload": f"N={nx} views {8 * Sx}^2 view-sharded over {world} GPUs ({plan_x.q} views per GPU), one NCCL all-gather per step inside the step graph",
+                    "value": Kx / (ms_x * 1e-3), "unit": "steps/s", "ms_per_step": ms_x / Kx, "steps": Kx, "gflop_per_step": round(fx / 1e9, 1),
+                    "achieved_tflops_per_gpu": round(fx * Kx / (ms_x * 1e-3) / world / 1e12, 2), "finite": bool(torch.isfinite(plan_x.x).all())}
+        extra["configs2_n16_sharded"] = extra_cfg(16, 32, model)
+        model64 = build_model(320, 8, D=D, S=64, device=dev)
+        extra["configs4_s64_sharded"] = extra_cfg(8, 64, model64)
+        del model64
+        torch.cuda.empty_cache()
     ms, plan, sc, cams, icams = timed_loop(shard)
     finite = bool(torch.isfinite(plan.x).all())
     scenes = 1 if (shard or world == 1) else world
@@ -427,8 +466,9 @@ def run_native(args):
                 other["mode"] = "replicas: one independent scene per GPU, no collective (weak scaling)"
                 line["replicas"] = other
             else:
-                other["mode"] = "ONE scene view-sharded over the GPUs, 1 NCCL all-gather of the 5-channel latents per step (strong scaling)"
+                other["mode"] = "ONE scene view-sharded over the GPUs, 1 NCCL all-gather of the 5-channel latents per step, captured inside the step's CUDA graph (strong scaling)"
                 line["sharded"] = other
+        line.update({k: v for k, v in extra.items() if k != "rel_l2_vs_unsharded" or shard})
         if not args.no_cpu_baseline and world == 1:
             del model, plan
             torch.cuda.empty_cache()
@@ -436,7 +476,12 @@ def run_native(args):
             line["cpu_baseline"] = cb
         emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        # the step graphs hold captured NCCL kernels: tearing the communicator down under them can block, so every rank leaves
+        # through a last barrier + a hard exit instead of destroy_process_group()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def emit(line):

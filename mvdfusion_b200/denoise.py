@@ -121,6 +121,9 @@ class StepPlan:
         self.ddim_prog.append(ops.cfg_ddim(self.head, 8, use_cfg, self.coef, self.x_local, self.noise_local, self.eps_out,
                                            self.x_local, self.x0_out, q, hw))
         self.arena_bytes = arena.total_bytes
+        # view-sharded mode: the exchange of the updated latents (mvdfusion_b200.mvdfusion.viewfusion_zero_depth_rgb.ViewFusion.gather_views)
+        # is the LAST call of the step program, so that it is captured into the step's CUDA graph with the kernels
+        self.after_step = None
         self._tables = None
         self._loop_prog = None
         self._host_prog = None
@@ -186,6 +189,8 @@ class StepPlan:
             loop.extend(pro)
             loop.extend(self.core_prog)
             loop.extend(self.ddim_prog)
+            if self.after_step is not None:
+                loop.append(self.after_step)
             self._loop_prog = loop
             self._graphs.pop("loop", None)
         self._tables[0][:steps].copy_(step_rows.float(), non_blocking=True)
@@ -209,7 +214,8 @@ class StepPlan:
             self.x.copy_(x_keep)
             self.counter.copy_(c_keep)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: the NCCL watchdog thread of a view-sharded run must not invalidate the capture
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 prog.run(torch.cuda.current_stream().cuda_stream)
             self.x.copy_(x_keep)
             self.counter.copy_(c_keep)
@@ -230,6 +236,8 @@ class StepPlan:
             self._host_prog = E.Program()
             self._host_prog.extend(self.core_prog)
             self._host_prog.extend(self.ddim_prog)
+            if self.after_step is not None:
+                self._host_prog.append(self.after_step)
         self._replay("host", self._host_prog, stream, use_graph)
 
 

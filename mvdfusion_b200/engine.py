@@ -201,6 +201,18 @@ class Arena:
                 self.free_list.append(base)
 
 
+class HostCall:
+    """A host-side step of a Program that is not a C-ABI kernel call (e.g. the NCCL all-gather of the view-sharded mode,
+    issued through torch.distributed on the current stream — capturable into the step's CUDA graph like the kernels)."""
+
+    def __init__(self, name, fn):
+        self.name, self.fn = name, fn
+        self.meta = {"kernel": name}
+
+    def __call__(self, stream):
+        self.fn(stream)
+
+
 class Program:
     """A fixed sequence of bound kernel calls."""
 

@@ -151,8 +151,7 @@ class DDIMSampler:
                 plan.host_step(stream, rows_h[i], de_h[i], dn_h[i], use_graph=use_graph)
             else:
                 plan.loop_step(stream, use_graph=use_graph)
-            if group is not None:
-                model.gather_views(plan)
+            # (view-sharded: the all-gather of the updated latents is the last call of the step program — inside the graph)
             if host_io:
                 # the step's x_t lands in pinned host memory on the stream; the host only waits for the PREVIOUS step's
                 # copy, so that it has step i+1 (H2D of its inputs + graph launch) queued while step i still runs

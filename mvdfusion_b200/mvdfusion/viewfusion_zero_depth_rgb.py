@@ -126,6 +126,10 @@ class ViewFusion(nn.Module):
                                               q_first=q_first, q_count=q_count, num_layers=va.num_layers,
                                               grid_heads=va.num_heads, depth_scale=va.depth_scale, depth_shift=va.depth_shift,
                                               use_depth_override=use_depth_override, use_cond_scale=use_cond_scale)
+            if self.view_group is not None:
+                from ..engine import HostCall
+                plan = self._cache.plans[key]
+                plan.after_step = HostCall("all_gather_latents", lambda stream, plan=plan: self.gather_views(plan))
         return self._cache.plans[key]
 
     @staticmethod
