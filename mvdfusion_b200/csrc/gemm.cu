@@ -42,6 +42,29 @@ constexpr int MAX_STAGES = 8;
 constexpr int WG_THREADS = 128;
 constexpr int WS_COUNTER_BYTES = 16384;  // 2048 x {arrive, done} tile semaphores at the head of the split-K workspace
 
+// Division by a run-time constant as multiply-high + shift (the persistent loops decode a work unit per tile in every warp
+// role, and the QKV / row-bias epilogues divide per chunk: a hardware-emulated integer division is ~20 dependent instructions).
+// Exact for 0 <= n < 2^31, 1 <= d < 2^31.
+struct FastDiv {
+  uint32_t mul, shr, d;
+  __device__ __forceinline__ int div(int n) const { return d == 1 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul) >> shr); }
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const {
+    q = div(n);
+    r = n - q * static_cast<int>(d);
+  }
+};
+static FastDiv make_fastdiv(int d) {
+  FastDiv f{0u, 0u, static_cast<uint32_t>(d < 1 ? 1 : d)};
+  if (f.d > 1) {
+    uint32_t lg = 0;
+    while ((1ull << lg) < f.d) ++lg;                       // ceil(log2 d)
+    const unsigned long long pw = 1ull << (31 + lg);       // n < 2^31: one extra bit of the quotient estimate is enough
+    f.mul = static_cast<uint32_t>((pw + f.d - 1) / f.d);
+    f.shr = lg - 1;                                        // (n * mul) >> (31 + lg) == umulhi(n, mul) >> (lg - 1)
+  }
+  return f;
+}
+
 struct GemmKParams {
   int M, N;
   int BN, stages;
@@ -75,6 +98,7 @@ struct GemmKParams {
   // hi/lo split operands (args.hilo): A = [A_hi | A_lo], W = [W_hi | W_lo]; the k-blocks run over three segments
   // A_hi W_hi, A_lo W_hi, A_hi W_lo (kb_seg k-blocks each).  a_lo_off / w_lo_off: column (channel) offsets of the lo halves.
   int hilo, kb_seg, a_lo_off, w_lo_off;
+  FastDiv fd_split, fd_tiles_m, fd_tiles_x, fd_tiles_y, fd_seq, fd_inner, fd_dhead, fd_rpg;
 };
 
 __device__ __forceinline__ void store8_f16(__half* dst, const float* v) {
@@ -188,10 +212,8 @@ struct Unit {
 // a tile is clipped, the CTA still takes part in the pair's loads and barriers).
 __device__ __forceinline__ Unit decode_unit(const GemmKParams& p, int u, int pair_rank) {
   Unit t;
-  t.s = u % p.split;
-  t.tile = u / p.split;
-  t.n_tile = t.tile / p.tiles_m;
-  t.m_tile = t.tile - t.n_tile * p.tiles_m;
+  p.fd_split.divmod(u, t.tile, t.s);
+  p.fd_tiles_m.divmod(t.tile, t.n_tile, t.m_tile);
   if (pair_rank >= 0) {
     t.m_tile = 2 * t.m_tile + pair_rank;
     t.tile = t.n_tile * p.tiles_m_real + t.m_tile;  // split-K semaphores / partials are per real tile
@@ -200,9 +222,9 @@ __device__ __forceinline__ Unit decode_unit(const GemmKParams& p, int u, int pai
   t.kb1 = min(p.num_kb, t.kb0 + p.kb_per_split);
   t.x0 = t.y0 = t.img0 = 0;
   if (p.a_mode == MVD_A_CONV3X3) {
-    const int tx = t.m_tile % p.tiles_x;
-    const int ty = (t.m_tile / p.tiles_x) % p.tiles_y;
-    const int tz = t.m_tile / (p.tiles_x * p.tiles_y);
+    int tx, ty, tz, rest;
+    p.fd_tiles_x.divmod(t.m_tile, rest, tx);
+    p.fd_tiles_y.divmod(rest, tz, ty);
     t.x0 = tx * p.tw;
     t.y0 = ty * p.th;
     t.img0 = tz * p.tn;
@@ -417,8 +439,8 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
         // v^T (keys contiguous) wants thread = row: leave straight from the registers
         const int grow = t.grow0 + et;
         if (grow < p.M) {
-          const int img = grow / p.seq;
-          const int pos = grow - img * p.seq;
+          int img, pos;
+          p.fd_seq.divmod(grow, img, pos);
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             const int n = oc + i;
@@ -427,10 +449,9 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[i + e] += __ldg(p.bias + n + e);
             }
-            const int which = n / inner;
-            const int rem = n - which * inner;
-            const int h = rem / p.dhead;
-            const int jj = rem - h * p.dhead;
+            int which, rem, h, jj;
+            p.fd_inner.divmod(n, which, rem);
+            p.fd_dhead.divmod(rem, h, jj);
             const size_t bh = static_cast<size_t>(img) * p.heads + h;
             if (which < 2) {
               __half* base = reinterpret_cast<__half*>(which == 0 ? p.out : p.out_k);
@@ -478,10 +499,9 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
       // QKV (q / k part): per-thread head coordinates are fixed for the chunk
       int qk_which = 0, qk_h = 0, qk_jj = 0;
       if (out_mode == MVD_OUT_QKV_HEADS && nvalid > 0) {
-        qk_which = col / inner;
-        const int rem = col - qk_which * inner;
-        qk_h = rem / p.dhead;
-        qk_jj = rem - qk_h * p.dhead;
+        int rem;
+        p.fd_inner.divmod(col, qk_which, rem);
+        p.fd_dhead.divmod(rem, qk_h, qk_jj);
       }
       float4 acc[8];
 #pragma unroll
@@ -522,7 +542,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
         const bool live = (grow < p.M) && nvalid > 0;
         v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
         if (p.rowbias != nullptr && live) {
-          const float4 r4 = ldg4(p.rowbias + static_cast<size_t>(grow / p.rows_per_group) * p.N + col, VEC || p.vec_rowbias != 0, nvalid);
+          const float4 r4 = ldg4(p.rowbias + static_cast<size_t>(p.fd_rpg.div(grow)) * p.N + col, VEC || p.vec_rowbias != 0, nvalid);
           v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
         }
         if (act == MVD_ACT_GELU) {
@@ -581,8 +601,8 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
             if (nvalid > 3) dst[3] = __float2half_rn(v.w);
           }
         } else {  // q / k part of the head scatter (dhead % 8 == 0: four columns never straddle a head)
-          const int img = grow / p.seq;
-          const int pos = grow - img * p.seq;
+          int img, pos;
+          p.fd_seq.divmod(grow, img, pos);
           __half* base = reinterpret_cast<__half*>(qk_which == 0 ? p.out : p.out_k);
           __half* dst = base + ((static_cast<size_t>(img) * p.heads + qk_h) * p.seq + pos) * p.dpad + qk_jj;
           *reinterpret_cast<uint2*>(dst) = make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
@@ -936,6 +956,14 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   split = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.split = split;
   p.num_units = tiles * split;
+  p.fd_split = make_fastdiv(split);
+  p.fd_tiles_m = make_fastdiv(p.tiles_m);
+  p.fd_tiles_x = make_fastdiv(p.tiles_x > 0 ? p.tiles_x : 1);
+  p.fd_tiles_y = make_fastdiv(p.tiles_y > 0 ? p.tiles_y : 1);
+  p.fd_seq = make_fastdiv(p.seq > 0 ? p.seq : 1);
+  p.fd_inner = make_fastdiv(p.heads * p.dhead > 0 ? p.heads * p.dhead : 1);
+  p.fd_dhead = make_fastdiv(p.dhead > 0 ? p.dhead : 1);
+  p.fd_rpg = make_fastdiv(p.rows_per_group);
   if (split > 1) {
     if ((reinterpret_cast<uintptr_t>(a->splitk_ws) & 15) != 0) return set_error(MVD_EALIGN, "mvd_gemm_f16: splitk_ws must be 16-byte aligned");
     p.counters = reinterpret_cast<int*>(a->splitk_ws);
