@@ -41,7 +41,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--mode", default="replicas", choices=["shard", "replicas"])
+    ap.add_argument("--mode", default="replicas", choices=["shard", "replicas", "train"],
+                    help="train: BASELINE configs[3] — forward + backward + AdamW of one scene per rank per step under DDP (not the headline metric)")
     ap.add_argument("--views", type=int, default=8)
     ap.add_argument("--latent", type=int, default=32, choices=[32, 64],
                     help="latent side: 32 = 256^2 images (the headline workload), 64 = 512^2 (BASELINE configs[4], HBM-bandwidth stress)")
@@ -484,6 +485,84 @@ def run_native(args):
         os._exit(0)
 
 
+# ------------------------------------------------------------------------------------------------ training mode (configs[3])
+def run_train(args):
+    """BASELINE configs[3] (train.py forward + backward, N = 8 views, D = 3 — configs/mvd_train.yaml:28 — DDP over the GPUs, one
+    scene per rank per step as train.py:55 asserts; "batch = 4 scenes" = 4 such steps): ViewFusion.forward -> loss.backward() ->
+    AdamW.step().  The contractions (forward, dgrad, wgrad) run on the library's tcgen05 GEMM (mvdfusion_b200/training.py); gradients
+    are all-reduced by torch DDP with bf16 compression.  Prints its own JSON line (metric: training scenes/sec)."""
+    import torch.distributed as dist
+    from common import build_model, standin_clip_encode, standin_vae_encode, synthetic_dataset_batch
+    from mvdfusion_b200 import _lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n, S, D, K, Wm = args.views, args.latent, 3, args.steps, max(args.warmup, 1)
+    model = build_model(320, 8, D=D, S=S, device=dev)
+    model.finetune_unet = True
+    for p_ in model.parameters():
+        p_.requires_grad_(True)
+    for p_ in model.view_attn.t_embedder.parameters():   # never read by forward (SURVEY.md §2.3: find_unused_parameters=True in train.py:38)
+        p_.requires_grad_(False)
+    n_train = sum(p_.numel() for p_ in model.parameters() if p_.requires_grad)
+    net = model
+    if world > 1:
+        from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+        net.register_comm_hook(state=None, hook=default_hooks.bf16_compress_hook)
+    opt = torch.optim.AdamW([p_ for p_ in model.parameters() if p_.requires_grad], lr=1e-5)
+    tc = {"input_batch_size": 1, "train_batch_size": n, "random_views": False}
+    batch = synthetic_dataset_batch(n + 1, 8 * S, seed=rank)
+    images = batch.pop("images")
+    batch["latents"] = standin_vae_encode(images, model.z_scale_factor) * 4.0
+    batch["clip_embed"] = standin_clip_encode(images)
+    batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    model.train()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = net(batch, tc)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(Wm):
+        loss = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    c0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    launches = _lib.launch_count() - c0
+    if rank == 0:
+        f_fwd = (F_GRID_GFLOP * n * n * S * S * D + n * 235.8) * 1e9   # SURVEY.md §8d: F_U(32, D=3) = 235.8 GFLOP per view
+        emit({"metric": "training scenes/sec (forward + backward + AdamW, one scene of N views per rank per step)", "value": world * K / (ms * 1e-3),
+              "unit": "scenes/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "f16 operands / f32 accumulate, f32 master weights + gradients, bf16-compressed all-reduce", "data": "synthetic",
+              "config": {"workload": f"BASELINE configs[3]: train fwd+bwd, N={n} views {8 * S}^2, D=3, all {n_train / 1e6:.1f} M parameters trainable, DDP x{world}",
+                         "native": "contractions (forward, dgrad, wgrad) on mvd_gemm_f16; norms / softmax / gather backward via ATen (first slice)"},
+              "gpu_launches": int(launches), "loss": float(loss), "finite": bool(torch.isfinite(loss)),
+              "achieved_tflops_per_gpu": round(3 * f_fwd * K / (ms * 1e-3) / 1e12, 2)})
+    if world > 1:
+        dist.barrier()
+        os._exit(0)
+
+
 def emit(line):
     """The ONE JSON line goes to the real stdout; everything else any library prints there (NCCL's version banner...) was
     re-routed to stderr at start-up."""
@@ -497,5 +576,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.mode == "train":
+        run_train(a)
     else:
         run_native(a)

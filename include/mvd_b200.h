@@ -67,7 +67,7 @@ typedef struct mvd_gemm_args {
   int32_t M, N, K;
   int32_t a_mode;
   const void* A;       /* fp16 */
-  int32_t lda;         /* elements; ROWMAJOR only (multiple of 8) */
+  int32_t lda;         /* elements (multiple of 8); ROWMAJOR: row pitch; CONV3X3: pixel pitch, 0 = C */
   int32_t n_img, H, W, C; /* CONV3X3 only; C multiple of 8, W a power of two (rows wider than 128 pixels are tiled in 128-pixel segments) */
   const void* Wt;      /* fp16 [N, ldw] */
   int32_t ldw;         /* elements, multiple of 8, >= K */
@@ -105,6 +105,13 @@ typedef struct mvd_gemm_args {
   int32_t hilo;
   int32_t out16_lo;
   int32_t a_lo_off;    /* ROWMAJOR + hilo: column of A_lo (0 = K); > K when A is a column window of a wider [hi | lo] buffer */
+  /* ABI 10: strided implicit-GEMM convolution — Downsample.op, conv3x3 stride 2 padding 1 (openaimodel.py:151), reads its taps
+   * straight from the full-resolution image through a TMA box with element strides 2 (no im2col).  conv_stride = 2: H, W are the
+   * OUTPUT extent, A is the fp16 NHWC image [n_img, 2H, 2W, C].  conv_no_pad_lo = 1: pad the high side only (the VAE encoder's
+   * F.pad(x, (0,1,0,1)) + stride-2 conv, external/sd1/ldm/modules/diffusionmodules/model.py:65-76).  In CONV3X3 mode `lda`, when
+   * non-zero, is the pixel pitch of A in elements (the image may be a column window of a wider buffer). */
+  int32_t conv_stride;
+  int32_t conv_no_pad_lo;
 } mvd_gemm_args;
 
 int mvd_gemm_f16(const mvd_gemm_args* args, void* stream);

@@ -9,7 +9,7 @@ from ctypes import c_char_p, c_float, c_int32, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmvd_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class GemmArgs(ctypes.Structure):
@@ -28,7 +28,7 @@ class GemmArgs(ctypes.Structure):
         ("heads", c_int32), ("dhead", c_int32), ("dpad", c_int32), ("seq", c_int32),
         ("split_k", c_int32), ("tile_n", c_int32), ("cta_pair", c_int32),
         ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_longlong),
-        ("out16", c_void_p), ("ld16", c_int32), ("hilo", c_int32), ("out16_lo", c_int32), ("a_lo_off", c_int32),
+        ("out16", c_void_p), ("ld16", c_int32), ("hilo", c_int32), ("out16_lo", c_int32), ("a_lo_off", c_int32), ("conv_stride", c_int32), ("conv_no_pad_lo", c_int32),
     ]
 
 

@@ -43,10 +43,11 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, const cuuint32_t* estr_in = nullptr) {
   EncodeTiledFn fn = get_encode();
   if (fn == nullptr) return set_error(MVD_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; estr_in != nullptr && i < rank; ++i) estr[i] = estr_in[i];
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -90,18 +91,23 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int d0, int d1, int d2, lon
   return encode(out, base, 3, dims, strides, box);
 }
 
-int make_tmap_nhwc(CUtensorMap* out, const void* base, int n, int h, int w, int c, int bc, int bw, int bh, int bn) {
+int make_tmap_nhwc(CUtensorMap* out, const void* base, int n, int h, int w, int c, int bc, int bw, int bh, int bn, int pitch,
+                   int stride) {
+  // pitch: elements between consecutive pixels (>= c: the image may be a column window of a wider buffer); stride: the box visits
+  // every `stride`-th pixel in x and y (a strided convolution reads its taps straight from the full-resolution image)
+  const cuuint64_t pp = static_cast<cuuint64_t>(pitch > 0 ? pitch : c);
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
                         static_cast<cuuint64_t>(n)};
-  cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w) * c * 2,
-                           static_cast<cuuint64_t>(h) * w * c * 2};
-  cuuint32_t box[4] = {static_cast<cuuint32_t>(bc), static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh),
+  cuuint64_t strides[3] = {pp * 2, static_cast<cuuint64_t>(w) * pp * 2, static_cast<cuuint64_t>(h) * w * pp * 2};
+  const cuuint32_t es = static_cast<cuuint32_t>(stride > 1 ? stride : 1);
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(bc), static_cast<cuuint32_t>(bw) * es, static_cast<cuuint32_t>(bh) * es,
                        static_cast<cuuint32_t>(bn)};
-  return encode(out, base, 4, dims, strides, box);
+  cuuint32_t estr[4] = {1, es, es, 1};
+  return encode(out, base, 4, dims, strides, box, estr);
 }
 
 }  // namespace mvd
 
 extern "C" const char* mvd_last_error(void) { return mvd::g_err; }
-extern "C" int mvd_abi_version(void) { return 9; }
+extern "C" int mvd_abi_version(void) { return 10; }
 extern "C" long long mvd_launch_count(void) { return mvd::g_launches.load(std::memory_order_relaxed); }

@@ -56,8 +56,10 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int cols, int rows, int ld,
 // fp16 3-D tensor [d2, d1, d0] with strides (ld1, ld2 elements); box (b0, b1, b2), 128B swizzle.
 int make_tmap_3d(CUtensorMap* out, const void* base, int d0, int d1, int d2, long long ld1, long long ld2, int b0,
                  int b1, int b2);
-// fp16 NHWC image batch [n, h, w, c]; box (bc, bw, bh, bn), 128B swizzle, OOB -> 0.
-int make_tmap_nhwc(CUtensorMap* out, const void* base, int n, int h, int w, int c, int bc, int bw, int bh, int bn);
+// fp16 NHWC image batch [n, h, w, c] with `pitch` elements between pixels (0 = c); box = (bc channels, bw, bh, bn) PIXELS VISITED,
+// every `stride`-th pixel in x and y (element strides; 0 / 1 = dense); 128B swizzle, OOB -> 0.
+int make_tmap_nhwc(CUtensorMap* out, const void* base, int n, int h, int w, int c, int bc, int bw, int bh, int bn, int pitch = 0,
+                   int stride = 1);
 
 // generic 2-D map: `elem_bytes` 2 (fp16) or 4 (fp32); swizzle_bytes 0 / 128.  Used for epilogue TMA stores / residual loads.
 int make_tmap_2d_ex(CUtensorMap* out, const void* base, int elem_bytes, long long cols, long long rows, long long ld,

@@ -98,6 +98,7 @@ struct GemmKParams {
   // hi/lo split operands (args.hilo): A = [A_hi | A_lo], W = [W_hi | W_lo]; the k-blocks run over three segments
   // A_hi W_hi, A_lo W_hi, A_hi W_lo (kb_seg k-blocks each).  a_lo_off / w_lo_off: column (channel) offsets of the lo halves.
   int hilo, kb_seg, a_lo_off, w_lo_off;
+  int cstride, cpad;        // CONV3X3: stride (1 / 2) and low-side padding (1, or 0 for the VAE encoder's pad-high-only downsample)
   FastDiv fd_split, fd_tiles_m, fd_tiles_x, fd_tiles_y, fd_seq, fd_inner, fd_dhead, fd_rpg;
 };
 
@@ -327,11 +328,11 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
           uint8_t* sb = sa + A_BYTES;
           if (PAIR) {
             const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
-            if (p.a_mode == MVD_A_CONV3X3) tma_load_4d_pair(sa, &tmA, lbar, ki.a_col, t.x0 + ki.kx - 1, t.y0 + ki.ky - 1, t.img0);
+            if (p.a_mode == MVD_A_CONV3X3) tma_load_4d_pair(sa, &tmA, lbar, ki.a_col, t.x0 * p.cstride + ki.kx - p.cpad, t.y0 * p.cstride + ki.ky - p.cpad, t.img0);
             else tma_load_2d_pair(sa, &tmA, lbar, ki.a_col, t.m_tile * BM);
             tma_load_2d_pair(sb, &tmB, lbar, ki.w_col, t.n_tile * p.BN + pair_rank * b_rows);
           } else {
-            if (p.a_mode == MVD_A_CONV3X3) tma_load_4d(sa, &tmA, &full_bar[s], ki.a_col, t.x0 + ki.kx - 1, t.y0 + ki.ky - 1, t.img0);
+            if (p.a_mode == MVD_A_CONV3X3) tma_load_4d(sa, &tmA, &full_bar[s], ki.a_col, t.x0 * p.cstride + ki.kx - p.cpad, t.y0 * p.cstride + ki.ky - p.cpad, t.img0);
             else tma_load_2d(sa, &tmA, &full_bar[s], ki.a_col, t.m_tile * BM);
             tma_load_2d(sb, &tmB, &full_bar[s], ki.w_col, t.n_tile * p.BN);
           }
@@ -911,7 +912,13 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     p.num_kb = 9 * p.kb_per_tap;
     p.a_lo_off = a->C;       // the image batch holds 2C channels: [hi | lo]
     p.w_lo_off = 9 * a->C;
-    int rc = make_tmap_nhwc(&tmA, a->A, a->n_img, a->H, a->W, hilo ? 2 * a->C : a->C, BK, p.tw, p.th, p.tn);
+    if (a->conv_stride != 0 && a->conv_stride != 1 && a->conv_stride != 2) return set_error(MVD_EINVAL, "mvd_gemm_f16: conv_stride must be 1 or 2");
+    p.cstride = a->conv_stride == 2 ? 2 : 1;
+    p.cpad = a->conv_no_pad_lo ? 0 : 1;
+    const int c_img = hilo ? 2 * a->C : a->C;
+    if (a->lda != 0 && (a->lda < c_img || (a->lda & 7) != 0)) return set_error(MVD_EALIGN, "mvd_gemm_f16: CONV3X3 pixel pitch (lda) must be 0 or a multiple of 8 >= C");
+    // H, W are the OUTPUT extent; the image holds (stride H) x (stride W) pixels
+    int rc = make_tmap_nhwc(&tmA, a->A, a->n_img, a->H * p.cstride, a->W * p.cstride, c_img, BK, p.tw, p.th, p.tn, a->lda, p.cstride);
     if (rc != MVD_OK) return rc;
   } else {
     return set_error(MVD_EINVAL, "mvd_gemm_f16: bad a_mode");

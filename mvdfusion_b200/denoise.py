@@ -97,6 +97,7 @@ class StepPlan:
 
         # ---- per-step core: GridAttn -> pyramid -> UNet
         b = E.Builder(ops, self.W_top, arena=arena)
+        b.prog.mark("time_embed")
         c_embed = b.time_mlp(self.t_dev, self.freqs_grid, 256, "time_embed.0", "time_embed.2", 256, 256)
         b.W = self.W_grid
         E.emit_gridattn(b, noisy=self.x, input_latent=self.input_latent[:1], depth_override=self.depth_override,
@@ -104,6 +105,7 @@ class StepPlan:
                         n_views=N, S=S, D=D, q_first=q_first, q_count=q, num_layers=num_layers, num_heads=grid_heads,
                         depth_scale=depth_scale, depth_shift=depth_shift, frustum_out=self.pyramid16[0],
                         harm_freqs=self.harm_freqs, ndc_grid=self.ndc_grid)
+        b.prog.mark("frustum_pyramid")
         E.emit_pyramid(b, self.pyramid16, q, S, D)
         self.grid_calls = len(b.prog)
         b.W = self.W_unet
@@ -118,8 +120,10 @@ class StepPlan:
         self.eps_prog = E.Program()
         self.eps_prog.append(ops.cfg_ddim(self.head, 8, use_cfg, self.coef, None, None, self.eps_out, None, None, q, hw))
         self.ddim_prog = E.Program()
+        self.ddim_prog.mark("cfg_ddim_update")
         self.ddim_prog.append(ops.cfg_ddim(self.head, 8, use_cfg, self.coef, self.x_local, self.noise_local, self.eps_out,
                                            self.x_local, self.x0_out, q, hw))
+        self.ddim_prog.mark("end")
         self.arena_bytes = arena.total_bytes
         # view-sharded mode: the exchange of the updated latents (mvdfusion_b200.mvdfusion.viewfusion_zero_depth_rgb.ViewFusion.gather_views)
         # is the LAST call of the step program, so that it is captured into the step's CUDA graph with the kernels

@@ -213,11 +213,41 @@ class HostCall:
         self.fn(stream)
 
 
+_NVTX = bool(os.environ.get("MVD_NVTX"))
+
+
+class StageMark:
+    """Stage boundary inside a Program.  With MVD_NVTX=1 in the environment every stage of an eager (non-graph) replay is an NVTX
+    range (`ncu --nvtx --nvtx-include "unet.middle_block/"`, or a timeline tool); otherwise a no-op.  Not a kernel launch."""
+
+    _open = False
+
+    def __init__(self, name):
+        self.name = "stage:" + name
+        self.stage = name
+        self.meta = {"kernel": "stage_mark"}
+
+    def __call__(self, stream):
+        if not _NVTX:
+            return
+        if StageMark._open:
+            torch.cuda.nvtx.range_pop()
+        StageMark._open = self.stage != "end"
+        if StageMark._open:
+            torch.cuda.nvtx.range_push(self.stage)
+
+
 class Program:
     """A fixed sequence of bound kernel calls."""
 
     def __init__(self):
         self.calls = []
+
+    def mark(self, stage):
+        """start a named stage (NVTX range when MVD_NVTX=1); only recorded when the instrumentation is on, so that the default
+        program is the bare launch list"""
+        if _NVTX:
+            self.calls.append(StageMark(stage))
 
     def append(self, call):
         self.calls.append(call)
@@ -252,6 +282,8 @@ class Builder:
         # split-precision (hi/lo fp16) operands where operand rounding lands on the residual trunk:
         # level 1 = stem + head convolutions, 2 = also the ResBlock 1x1 skip convolutions; MVD_HILO=0 turns it off (A/B)
         self.hilo = int(os.environ.get("MVD_HILO", "2"))
+        # data movement folded into TMA addressing: strided implicit-GEMM Downsample; MVD_NO_FOLD_K8=1 = im2col (A/B)
+        self.fold_k8 = not os.environ.get("MVD_NO_FOLD_K8")
 
     # -- buffers
     def t16(self, *shape):
@@ -415,9 +447,16 @@ class Builder:
         self.free(b, s)
         return out
 
-    def downsample(self, x, p, n_img, H, C, out16=None):
-        """Downsample.op: conv3x3 stride 2 (openaimodel.py:151) = fp16 im2col + GEMM"""
+    def downsample(self, x, p, n_img, H, C, out16=None, x16=None):
+        """Downsample.op: conv3x3 stride 2 (openaimodel.py:151).  With the input available as fp16 (x16 = (tensor / column window,
+        pixel pitch[, lo offset]) written by its producer's epilogue) it is a strided implicit GEMM: the taps come straight from the
+        full-resolution image through a TMA box with element strides 2 — no im2col pass, no [M, 9C] matrix.  Otherwise fp16 im2col + GEMM."""
         Mo = n_img * (H // 2) * (H // 2)
+        if x16 is not None and self.fold_k8:
+            out = self.t32(Mo, C)
+            self.gemm(x16[0], self.W.conv3(p + ".op.weight"), out, Mo, C, 9 * C, allow_split=True, conv=(n_img, H // 2, H // 2, C),
+                      conv_stride=2, lda=x16[1], bias=self.W.f32(p + ".op.bias"), **self._o16(out16))
+            return out
         col = self.t16(Mo, 9 * C)
         self.prog.append(self.ops.im2col_s2(x, col, n_img, H, H, C))
         out = self.t32(Mo, C)
@@ -620,6 +659,7 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
     [n_img, C] fp32; pyramid16: list of fp16 [n_img*H_l*H_l*D, 768].  Returns the head output fp32 [n_img*S*S, 8].
     stem_hilo: x_in16 carries [x_hi | x_lo | x_hi | 0] channels (mvd_unet_input_f16 hilo) for a split-precision stem."""
     b.heads = spec.heads
+    b.prog.mark("unet.time_embed")
     skip_hilo = b.hilo >= 2
     head_hilo = b.hilo >= 1 and spec.final_ch % 64 == 0
     emb = b.time_mlp(t_dev, freqs, spec.mc, "time_embed.0", "time_embed.2", spec.emb_dim, spec.emb_dim)
@@ -686,7 +726,7 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
                 level = {spec.image_size: 0, spec.image_size // 2: 1, spec.image_size // 4: 2, spec.image_size // 8: 3}[H]
                 new = b.view_aligned_transformer(h, p, n_img, H, l[1], pyramid16[level], D, out16=o16)
             elif kind == "down":
-                new = b.downsample(h, p, n_img, H, l[1], out16=o16)
+                new = b.downsample(h, p, n_img, H, l[1], out16=o16, x16=h16 if j == 0 else None)
                 H //= 2
             elif kind == "up":
                 new = b.upsample(h, p, n_img, H, l[1], out16=o16)
@@ -700,12 +740,16 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
 
     h = x_in16
     for i, layers in enumerate(spec.input_blocks):
+        b.prog.mark(f"unet.input_blocks.{i}")
         # a channel-changing ResBlock needs its input as fp16 (1x1 skip convolution): the previous block left it in its window
-        prev16 = skip_window(i - 1) if i > 0 and layers[0][0] == "res" and layers[0][1] != layers[0][2] else None
+        needs16 = (layers[0][0] == "res" and layers[0][1] != layers[0][2]) or layers[0][0] == "down"
+        prev16 = skip_window(i - 1) if i > 0 and needs16 else None
         h, H = run_layers(h, f"input_blocks.{i}", layers, H, h16=prev16, last16=skip_window(i))
         hs.append((h, layers))
+    b.prog.mark("unet.middle_block")
     h, H = run_layers(h, "middle_block", spec.middle, H, last16=head_window(0))
     for i, layers in enumerate(spec.output_blocks):
+        b.prog.mark(f"unet.output_blocks.{i}")
         skip, _ = hs.pop()
         c1, c2 = h.shape[-1], skip.shape[-1]
         rows = n_img * H * H
@@ -726,6 +770,7 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
             b.prog.append(b.ops.concat(h, skip, cat, rows, c1, c2))
             b.free(h, skip)
             h, H = run_layers(cat, f"output_blocks.{i}", layers, H, last16=head_window(i + 1))
+    b.prog.mark("unet.out")
     if head_hilo:  # the head's operand rounding would reach the output unattenuated: split-precision operands
         a = b.t16(n_img * H * H, 2 * spec.final_ch)
         b.prog.append(b.ops.groupnorm_hilo(h, b.W.f32("out.0.weight"), b.W.f32("out.0.bias"), a, n_img, H * H, spec.final_ch, 1e-5, True))
@@ -750,6 +795,7 @@ def emit_gridattn(b, *, noisy, input_latent, depth_override, depth_eps, scal, ca
     P = q_count * hw * D
     R = P * V
     W = b.W
+    b.prog.mark("gridattn.geometry")
     feat = b.t16((n_views + 1) * hw, Z_CH)
     zdepth = b.t32(n_views * D * hw)
     b.prog.append(b.ops.gridattn_prep(noisy, input_latent, depth_override, depth_eps, scal, W.f32("z_embedder.0.weight"),
@@ -757,6 +803,7 @@ def emit_gridattn(b, *, noisy, input_latent, depth_override, depth_eps, scal, ca
     tokens = b.t16(R, TOKEN_LD)
     b.prog.append(b.ops.gridattn_tokens(feat, zdepth, cams, mask, harm_freqs, ndc_grid, tokens, n_views, S, D, q_first, q_count))
     b.free(feat, zdepth)
+    b.prog.mark("gridattn.transformer")
     x = b.t32(R, Z_CH)
     b.gemm(tokens, W.lin("pre_layer_b.0.weight", k_pad=TOKEN_LD), x, R, Z_CH, TOKEN_LD, bias=W.f32("pre_layer_b.0.bias"),
            act=ACT_GELU)

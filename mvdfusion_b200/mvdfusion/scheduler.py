@@ -30,8 +30,9 @@ class DDPMScheduler(nn.Module):
         t = torch.randint(0, self.num_timesteps, (b,), device=device).long()
         return torch.zeros_like(t) + t[0] if share_t else t
 
-    def q_sample(self, x_start, t):
-        noise = torch.randn_like(x_start)
+    def q_sample(self, x_start, t, noise=None):
+        """mvdfusion/scheduler.py:55-64 (noise: optional injected draw instead of randn_like)"""
+        noise = torch.randn_like(x_start) if noise is None else noise
         shape = (x_start.shape[0],) + (1,) * (x_start.dim() - 1)
         return self.sqrt_alphas_cumprod[t].view(shape) * x_start + self.sqrt_one_minus_alphas_cumprod[t].view(shape) * noise, noise
 

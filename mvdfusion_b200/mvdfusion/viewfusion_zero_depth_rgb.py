@@ -266,14 +266,30 @@ class ViewFusion(nn.Module):
         return self.ddim.sample(batch_cameras, input_latents, input_cameras, clip_v_embed, unconditional_scale=cfg_scale,
                                 depth=depth, verbose=verbose)
 
-    def p_losses(self, batch, trainer_config):
-        """mvdfusion/viewfusion_zero_depth_rgb.py:362-392 — forward value of the training loss (no autograd through the
-        kernels yet: SURVEY.md §7 step 8 / BASELINE config 4 is a later row)."""
+    def p_losses(self, batch, trainer_config, t=None, noise=None, depth_eps=None, drop_random=None):
+        """mvdfusion/viewfusion_zero_depth_rgb.py:362-392.  With autograd enabled and trainable parameters (train.py:90-95) the
+        prediction comes from mvdfusion_b200.training (differentiable: tcgen05 GEMM / implicit-GEMM forward, dgrad and wgrad behind
+        autograd Functions), so `loss.backward()` works; under torch.no_grad() it is the forward value from the inference kernels.
+        t / noise / depth_eps / drop_random optionally inject the random draws (shared timestep, q_sample noise, GridAttn depth
+        jitter, condition-drop scheme) for parity tests."""
         batch_latents, batch_cameras, input_latents, input_cameras, clip_v_embed = self.prepare_batch(batch, trainer_config)
         B = batch_latents.shape[0]
-        t = self.scheduler.sample_random_times(B, share_t=True, device=batch_latents.device)
-        noisy, noise = self.scheduler.q_sample(batch_latents.clone(), t=t)
+        if t is None:
+            t = self.scheduler.sample_random_times(B, share_t=True, device=batch_latents.device)
+        noisy, noise = self.scheduler.q_sample(batch_latents.clone(), t=t, noise=noise)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if self.view_group is not None or self.feed_prev_depth:
+                raise NotImplementedError("training runs scene-parallel (DDP, train.py:38), without view sharding / feed_prev_depth")
+            from .. import training
+            pred = training.apply_model_train(self, noisy, batch_cameras, input_latents, input_cameras, clip_v_embed, t,
+                                              depth_eps=depth_eps, drop_random=drop_random)
+            target = noise if self.objective == "noise" else batch_latents
+            return self.loss_fn(target, pred).mean()
         kw = dict(prev_depth=input_latents[:, 4:].clone()) if self.feed_prev_depth else {}
+        if depth_eps is not None:
+            kw["depth_eps"] = depth_eps
+        if drop_random is not None:
+            kw["drop_random"] = drop_random
         pred = self.apply_model(noisy, batch_cameras, input_latents, input_cameras, clip_v_embed, t, **kw)
         target = noise if self.objective == "noise" else batch_latents
         # under view sharding apply_model returns this rank's views only: the loss is the mean over the local rows

@@ -79,10 +79,12 @@ class NativeOps:
     # ------------------------------------------------------------------ GEMM / conv
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
              colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None, cta_pair=0,
-             out16=None, ld16=None, hilo=False, out16_lo=0, a_lo_off=0):
+             out16=None, ld16=None, hilo=False, out16_lo=0, a_lo_off=0, conv_stride=1, conv_no_pad_lo=False):
         """out16: optional fp16 tensor (or column window of a wider one, row pitch ld16) that receives a copy of an fp32 output
         (out16_lo > 0: and its fp16 rounding residual, out16_lo columns to the right).
-        hilo: split-precision operands A = [A_hi | A_lo], Wt = [W_hi | W_lo] (include/mvd_b200.h, ABI 9); K stays the logical K."""
+        hilo: split-precision operands A = [A_hi | A_lo], Wt = [W_hi | W_lo] (include/mvd_b200.h, ABI 9); K stays the logical K.
+        conv = (n_img, H, W, C) with conv_stride = 2: H, W are the OUTPUT extent and A is the [n_img, 2H, 2W, C] image (ABI 10);
+        in conv mode `lda` is the pixel pitch of A when it is a column window of a wider buffer."""
         g = _lib.GemmArgs()
         g.M, g.N, g.K = M, N, K
         g.A = _ptr(A, torch.float16)
@@ -94,6 +96,9 @@ class NativeOps:
         if conv is not None:
             g.a_mode = A_CONV3X3
             g.n_img, g.H, g.W, g.C = conv
+            g.lda = lda if lda is not None else 0
+            g.conv_stride = conv_stride
+            g.conv_no_pad_lo = int(bool(conv_no_pad_lo))
         else:
             g.a_mode = A_ROWMAJOR
             g.lda = lda if lda is not None else A.shape[-1]
@@ -124,12 +129,12 @@ class NativeOps:
             g.ld16 = ld16 if ld16 is not None else out16.shape[-1]
         keep = (g, A, Wt, out, bias, rowbias, colscale, residual, qkv, ws, out16)
         n_out = N // 2 if act == ACT_GEGLU else N
-        a_bytes = (conv[0] * conv[1] * conv[2] * conv[3] if conv is not None else M * K) * 2
+        a_bytes = (conv[0] * conv[1] * conv[2] * conv[3] * conv_stride * conv_stride if conv is not None else M * K) * 2
         o_bytes = M * n_out * (4 if (qkv is None and out.dtype == torch.float32) else 2)
         desc = (f"{'conv' if conv is not None else 'lin'} M{M} N{N} K{K} "
                 f"{'qkv' if qkv is not None else ('f32' if out.dtype == torch.float32 else 'f16')}"
                 f"{' res' if residual is not None else ''}{' act%d' % act if act else ''}{' sk' if split_k != 1 else ''}"
-                f"{' +f16' if out16 is not None else ''}{' hilo' if hilo else ''}")
+                f"{' +f16' if out16 is not None else ''}{' hilo' if hilo else ''}{' s2' if conv_stride == 2 else ''}")
         sig = gemm_signature(conv is not None, M, N, K, "qkv" if qkv is not None else str(out.dtype).split(".")[-1], residual is not None, act)
         meta = {"kernel": "gemm_tc_kernel", "flops": 2.0 * M * N * K * (3 if hilo else 1), "shape": (M, N, K, split_k), "desc": desc, "sig": sig, "can_split": ws is not None,
                 "bytes": a_bytes + N * K * 2 + o_bytes + (M * n_out * 4 if residual is not None else 0) + (M * n_out * 2 if out16 is not None else 0)}

@@ -45,7 +45,7 @@ class TorchOpsDouble:
     # ------------------------------------------------------------------ GEMM / conv
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
              colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None, cta_pair=0,
-             out16=None, ld16=None, hilo=False, out16_lo=0, a_lo_off=0):
+             out16=None, ld16=None, hilo=False, out16_lo=0, a_lo_off=0, conv_stride=1, conv_no_pad_lo=False):
         assert A.dtype == torch.float16 and Wt.dtype == torch.float16
         assert out16 is None or (out.dtype == torch.float32 and qkv is None and act != ACT_GEGLU)
         ldw_ = ldw if ldw is not None else Wt.shape[-1]
@@ -57,11 +57,15 @@ class TorchOpsDouble:
                 n_img, H, Wd, C = conv
                 assert K == 9 * C and M == n_img * H * Wd
                 Ct = 2 * C if hilo else C
+                st = conv_stride
+                Hi, Wi = H * st, Wd * st           # H, Wd are the OUTPUT extent; the image holds (st H) x (st Wd) pixels
+                pitch = lda if lda else Ct
+                lo_pad, hi_pad = (0 if conv_no_pad_lo else 1), 2
 
                 def im2col(x):
-                    xp = F.pad(x, (0, 0, 1, 1, 1, 1))
-                    return torch.cat([xp[:, ky:ky + H, kx:kx + Wd, :] for ky in range(3) for kx in range(3)], dim=-1).reshape(M, K)
-                xall = A.reshape(-1)[: M * Ct].reshape(n_img, H, Wd, Ct).float()
+                    xp = F.pad(x, (0, 0, lo_pad, hi_pad, lo_pad, hi_pad))
+                    return torch.cat([xp[:, ky:ky + Hi:st, kx:kx + Wi:st, :][:, :H, :Wd] for ky in range(3) for kx in range(3)], dim=-1).reshape(M, K)
+                xall = torch.as_strided(A, (n_img, Hi, Wi, Ct), (Hi * Wi * pitch, Wi * pitch, pitch, 1), A.storage_offset()).float()
                 a = im2col(xall[..., :C])
                 a_lo = im2col(xall[..., C:]) if hilo else None
             else:
