@@ -130,6 +130,11 @@ int mvd_geglu_row_permutation(int32_t inner_dim, int32_t tile_n, int32_t* perm_o
  * ---------------------------------------------------------------------------------------------- */
 int mvd_attn_self_f16(const void* q, const void* k, const void* vt, void* out, int32_t n_img, int32_t heads,
                       int32_t seq, int32_t dhead, int32_t dpad, int32_t ldo, void* stream);
+/* the same with keys [seq_valid, seq) masked out: a sequence whose length is not a multiple of 16 lives in a padded layout
+ * (CLIP ViT-L/14: 257 tokens in 272 rows; nn.MultiheadAttention of clip.model.ResidualAttentionBlock, called from
+ * external/sd1/ldm/modules/encoders/modules.py:431-436 through model.encode_image) */
+int mvd_attn_self_masked_f16(const void* q, const void* k, const void* vt, void* out, int32_t n_img, int32_t heads, int32_t seq,
+                             int32_t seq_valid, int32_t dhead, int32_t dpad, int32_t ldo, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Normalisation (fp32 residual stream in, fp16 GEMM operand out).
@@ -151,6 +156,10 @@ int mvd_groupnorm2_f32_f16(const float* x1, int32_t C1, const float* x2, int32_t
                            void* y, int32_t n_img, int32_t hw, float eps, int32_t apply_silu, void* stream);
 int mvd_layernorm_f32_f16(const float* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t C,
                           float eps, void* stream);
+/* nn.LayerNorm with fp32 output and explicit row pitches (x: [rows, ldx], y: [rows, ldy]; in place allowed): CLIP's ln_pre (the
+ * normalised tokens ARE the residual stream) and ln_post on the class-token rows (clip/model.py VisionTransformer.forward) */
+int mvd_layernorm_f32_f32(const float* x, long long ldx, const float* gamma, const float* beta, float* y, long long ldy, int32_t rows,
+                          int32_t C, float eps, void* stream);
 int mvd_ln_modulate_f32_f16(const float* x, const float* shift, const float* scale, void* y, int32_t rows, int32_t C,
                             float eps, void* stream);
 /* p[r, :cols] = softmax(scale * s[r, :cols]) as fp16: the VAE decoder's single-head attention weights

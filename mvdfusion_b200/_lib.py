@@ -9,7 +9,7 @@ from ctypes import c_char_p, c_float, c_int32, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmvd_b200.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 
 class GemmArgs(ctypes.Structure):
@@ -42,10 +42,12 @@ SIGNATURES = {
     "mvd_gemm_f16": [ctypes.POINTER(GemmArgs), vp],
     "mvd_geglu_row_permutation": [i32, i32, vp],
     "mvd_attn_self_f16": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    "mvd_attn_self_masked_f16": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "mvd_groupnorm_f32_f16": [vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp],
     "mvd_groupnorm_hilo_f32_f16": [vp, vp, vp, vp, i32, i32, i32, f32, i32, vp],
     "mvd_groupnorm2_f32_f16": [vp, i32, vp, i32, vp, vp, vp, i32, i32, f32, i32, vp],
     "mvd_layernorm_f32_f16": [vp, vp, vp, vp, i32, i32, f32, vp],
+    "mvd_layernorm_f32_f32": [vp, i64, vp, vp, vp, i64, i32, i32, f32, vp],
     "mvd_ln_modulate_f32_f16": [vp, vp, vp, vp, i32, i32, f32, vp],
     "mvd_softmax_rows_f32_f16": [vp, vp, i32, i32, i32, i32, f32, vp],
     "mvd_cast_f32_f16": [vp, vp, i64, vp],

@@ -14,7 +14,9 @@ import yaml
 
 _ALIASES = {"mvdfusion.": "mvdfusion_b200.mvdfusion.",
             # the VAE: configs/mvd_gso.yaml:53-54
-            "external.sd1.ldm.models.autoencoder.": "mvdfusion_b200.mvdfusion.autoencoder."}
+            "external.sd1.ldm.models.autoencoder.": "mvdfusion_b200.mvdfusion.autoencoder.",
+            # the CLIP image embedder: viewfusion_zero_depth_rgb.py:103-105
+            "external.sd1.ldm.modules.encoders.modules.": "mvdfusion_b200.mvdfusion.clip_encoder."}
 _OUT_OF_SCOPE_PREFIXES = ("external.sd1.",)
 
 

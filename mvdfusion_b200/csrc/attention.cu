@@ -25,6 +25,7 @@ constexpr int ATT_MAX_STAGES = 2;
 
 struct AttnParams {
   int seq, heads, dhead, dpad, bkv;
+  int seq_valid;    // keys >= seq_valid are masked out (rows / keys [seq_valid, seq) are layout padding: CLIP's 257 tokens in 272 rows)
   int n_tiles;      // key tiles
   int stages;       // K / V ring depth
   int kd_steps;     // ceil(dhead/16): k-steps of the QK^T product
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     float l = 0.f;
     constexpr int LDW = BKV >= 32 ? 32 : 16;  // columns per tcgen05.ld
     for (int j = 0; j < p.n_tiles; ++j) {
-      const int kv_valid = min(BKV, p.seq - j * BKV);
+      const int kv_valid = min(BKV, p.seq_valid - j * BKV);
       mbar_wait(bar_s_full, j & 1);
       tc_fence_after();
       float s[BKV];
@@ -298,7 +299,13 @@ using namespace mvd;
 
 extern "C" int mvd_attn_self_f16(const void* q, const void* k, const void* vt, void* out, int32_t n_img, int32_t heads,
                                  int32_t seq, int32_t dhead, int32_t dpad, int32_t ldo, void* stream_) {
+  return mvd_attn_self_masked_f16(q, k, vt, out, n_img, heads, seq, seq, dhead, dpad, ldo, stream_);
+}
+
+extern "C" int mvd_attn_self_masked_f16(const void* q, const void* k, const void* vt, void* out, int32_t n_img, int32_t heads,
+                                        int32_t seq, int32_t seq_valid, int32_t dhead, int32_t dpad, int32_t ldo, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (seq_valid <= 0 || seq_valid > seq) return set_error(MVD_EINVAL, "mvd_attn_self_masked_f16: seq_valid must be in [1, seq]");
   if (q == nullptr || k == nullptr || vt == nullptr || out == nullptr) return set_error(MVD_EINVAL, "mvd_attn_self_f16: null pointer");
   if (n_img <= 0 || heads <= 0 || seq <= 0 || dhead <= 0) return set_error(MVD_EINVAL, "mvd_attn_self_f16: bad sizes");
   if ((dhead & 7) || (dpad & 63) || dpad < dhead || dpad > 192)
@@ -308,6 +315,7 @@ extern "C" int mvd_attn_self_f16(const void* q, const void* k, const void* vt, v
 
   AttnParams p{};
   p.seq = seq;
+  p.seq_valid = seq_valid;
   p.heads = heads;
   p.dhead = dhead;
   p.dpad = dpad;
@@ -318,7 +326,7 @@ extern "C" int mvd_attn_self_f16(const void* q, const void* k, const void* vt, v
   auto up1k = [](int x) { return (x + 1023) & ~1023; };
   auto layout = [&](int bkv) {
     p.bkv = bkv;
-    p.n_tiles = (seq + bkv - 1) / bkv;
+    p.n_tiles = (seq_valid + bkv - 1) / bkv;  // fully masked key tiles are never visited
     p.stages = p.n_tiles > 1 ? ATT_MAX_STAGES : 1;
     const int atoms_kv = (bkv + 63) / 64;
     p.k_stage = up1k(bkv * dpad * 2);

@@ -322,6 +322,43 @@ static cudaError_t ln_launch(const float* x, const float* a, const float* b, __h
   return launch_kernel(ln_kernel<MODE, 1, 10>, grid1, block, 0, stream, 1, x, a, b, y, rows, C, eps);
 }
 
+// LayerNorm fp32 -> fp32 with row pitches: one warp per row, any C % 4 == 0 (two passes over the row, L1 / L2 resident).  For the few
+// places where the normalised values stay on the fp32 residual stream or feed a GEMV (CLIP's ln_pre / ln_post on strided rows).
+__global__ void ln_f32_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ g, const float* __restrict__ b,
+                              float* __restrict__ y, long long ldy, int rows, int C, float eps) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx);
+  const int n4 = C >> 2;
+  float s = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = xr[i];
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = xr[i];
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+  float4* yr = reinterpret_cast<float4*>(y + static_cast<size_t>(row) * ldy);
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = xr[i];
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(g) + i), be = __ldg(reinterpret_cast<const float4*>(b) + i);
+    yr[i] = make_float4((v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y, (v.z - mean) * rstd * ga.z + be.z,
+                        (v.w - mean) * rstd * ga.w + be.w);
+  }
+}
+
 // ---------------------------------------------------------------------------- row softmax
 // p[r, :] = softmax(scale * s[r, :]) as fp16 (the P operand of the P V product).  One warp per row; the row is read three
 // times (maximum, sum, output) — it is L2-resident, and this runs once per scene, in the VAE decoder's single-head 512-wide
@@ -473,6 +510,21 @@ extern "C" int mvd_layernorm_f32_f16(const float* x, const float* gamma, const f
   if (!x || !gamma || !beta || !y) return set_error(MVD_EINVAL, "mvd_layernorm_f32_f16: null pointer");
   if (rows <= 0 || C <= 0 || (C & 3) != 0 || C > 1280) return set_error(MVD_EINVAL, "mvd_layernorm_f32_f16: C must be a multiple of 4, <= 1280");
   MVD_CUDA_CHECK(ln_launch<0>(x, gamma, beta, static_cast<__half*>(y), rows, C, eps, stream));
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_layernorm_f32_f32(const float* x, long long ldx, const float* gamma, const float* beta, float* y, long long ldy,
+                                     int32_t rows, int32_t C, float eps, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !gamma || !beta || !y) return set_error(MVD_EINVAL, "mvd_layernorm_f32_f32: null pointer");
+  if (rows <= 0 || C <= 0 || (C & 3) != 0 || ldx < C || ldy < C || (ldx & 3) != 0 || (ldy & 3) != 0)
+    return set_error(MVD_EINVAL, "mvd_layernorm_f32_f32: C and the row pitches must be multiples of 4, pitches >= C");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(gamma) & 15) ||
+      (reinterpret_cast<uintptr_t>(beta) & 15))
+    return set_error(MVD_EALIGN, "mvd_layernorm_f32_f32: pointers must be 16-byte aligned");
+  MVD_LAUNCH(ln_f32_kernel, (rows + 7) / 8, 256, 0, stream, x, ldx, gamma, beta, y, ldy, rows, C, eps);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

@@ -17,7 +17,7 @@ import os
 
 import torch
 
-from .ops import ACT_GEGLU, ACT_GELU, ACT_NONE, gemm_signature
+from .ops import ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_SILU, gemm_signature
 
 _TUNING = None
 
@@ -974,3 +974,63 @@ def emit_vae_encoder(b, x_nchw, n, R, ch, ch_mult, num_res_blocks, in_channels=3
     b.gemm(m16, W.lin("quant_conv.weight"), out, M, 2 * embed_dim, Nz, bias=W.f32("quant_conv.bias"))
     b.free(m16)
     return out, H
+
+
+# ------------------------------------------------------------------------------------------------ CLIP ViT image encoder
+class ClipPlan:
+    """OpenAI CLIP VisionTransformer.forward (clip/model.py; called through FrozenCLIPImageEmbedder, external/sd1/ldm/modules/
+    encoders/modules.py:402-441) for B pre-processed images as one program.  Token layout: `seq` = T rounded up to a multiple of 16
+    rows per image (ViT-L/14: T = 257 in 272 rows); rows [T, seq) are padding that the masked attention never reads as keys.
+    W: PackedWeights over the `model.visual.` prefix.  Inputs: self.patches fp16 [B*(T-1), kp]; output: self.out fp32 [B, out_dim]."""
+
+    def __init__(self, ops, W, B, width, layers, heads, T, kp, out_dim):
+        self.ops = ops
+        seq = _round_up(T, 16)
+        d = width // heads
+        dpad = _round_up(d, 64)
+        b = Builder(ops, W)
+        b.heads = heads
+        self.patches = ops.zeros((B * (T - 1), kp), torch.float16)
+        self.out = ops.empty((B, out_dim), torch.float32)
+        M = B * seq
+        # [class_embedding ; patches] + positional_embedding: the patch GEMM adds the positional rows as its residual and writes
+        # straight into the token buffer (one launch per image: rows b*seq + 1 ..); row 0 of every image is a constant
+        x = ops.zeros((M, width), torch.float32)
+        pos = W.raw("positional_embedding").float()
+        cls_row = (W.raw("class_embedding").float() + pos[0]).to(ops.device)
+        pos_rest = pos[1:T].contiguous().to(ops.device)
+        wconv = W._put("clip_conv1", kp, lambda: torch.nn.functional.pad(W.raw("conv1.weight").float().reshape(width, -1), (0, kp - 3 * W.raw("conv1.weight").shape[-1] ** 2)).half())
+        x.view(B, seq, width)[:, 0].copy_(cls_row)
+        self._keep = (cls_row, pos_rest)
+        for i in range(B):
+            b.gemm(self.patches[i * (T - 1):(i + 1) * (T - 1)], wconv, x[i * seq + 1:i * seq + T], T - 1, width, kp, residual=pos_rest, ldr=width)
+        h = b.t32(M, width)
+        b.prog.append(ops.layernorm_f32(x, W.f32("ln_pre.weight"), W.f32("ln_pre.bias"), h, M, width, 1e-5))
+        self._x = x
+        q, k, vt = b.qkv_buffers(B, seq, dpad)
+        for l in range(layers):
+            p = f"transformer.resblocks.{l}"
+            ln = b.layernorm(h, p + ".ln_1", M, width)
+            b.gemm(ln, W.lin(p + ".attn.in_proj_weight"), q, M, 3 * width, width, bias=W.f32(p + ".attn.in_proj_bias"),
+                   qkv=dict(out_k=k, out_vt=vt, heads=heads, dhead=d, dpad=dpad, seq=seq))
+            b.prog.append(ops.attn_self(q, k, vt, ln, B, heads, seq, d, dpad, width, seq_valid=T))
+            h2 = b.t32(M, width)
+            b.gemm(ln, W.lin(p + ".attn.out_proj.weight"), h2, M, width, width, bias=W.f32(p + ".attn.out_proj.bias"), residual=h, ldr=width)
+            b.free(ln, h)
+            ln = b.layernorm(h2, p + ".ln_2", M, width)
+            # QuickGELU(u) = u sigmoid(1.702 u) = silu(1.702 u) / 1.702: c_fc is packed scaled by 1.702 (SiLU epilogue), c_proj by 1 / 1.702
+            wfc = W._put("clip_fc", p, lambda p=p: (W.raw(p + ".mlp.c_fc.weight").float() * 1.702).half())
+            bfc = W._put("clip_fc_b", p, lambda p=p: W.raw(p + ".mlp.c_fc.bias").float() * 1.702)
+            wpr = W._put("clip_proj", p, lambda p=p: (W.raw(p + ".mlp.c_proj.weight").float() / 1.702).half())
+            f = b.t16(M, 4 * width)
+            b.gemm(ln, wfc, f, M, 4 * width, width, bias=bfc, act=ACT_SILU)
+            b.free(ln)
+            h = b.t32(M, width)
+            b.gemm(f, wpr, h, M, width, 4 * width, bias=W.f32(p + ".mlp.c_proj.bias"), residual=h2, ldr=width)
+            b.free(f, h2)
+        # ln_post on the class tokens (row 0 of every image), then @ proj
+        cls32 = b.t32(B, width)
+        b.prog.append(ops.layernorm_f32(h, W.f32("ln_post.weight"), W.f32("ln_post.bias"), cls32, B, width, 1e-5, ldx=seq * width))
+        wproj = W._put("clip_vproj", 0, lambda: W.raw("proj").float().t().contiguous().half())
+        b.prog.append(ops.gemv(cls32, wproj, None, self.out, B, out_dim, width))
+        self.prog = b.prog

@@ -59,7 +59,12 @@ class ViewFusion(nn.Module):
                                       use_zero_123=True, remove_keys=["input_blocks.0.0.weight", "out.2.weight", "out.2.bias"])
         self.scheduler = instantiate_from_config(ddpm_config)
         self.vae = load_model_from_config(vae_config, vae_path or None, replace_key=["first_stage_model.", ""]) if vae_config else None
-        self.clip_image_encoder = None  # FrozenCLIPImageEmbedder: outside the hot path, weights not shipped
+        # FrozenCLIPImageEmbedder (viewfusion_zero_depth_rgb.py:103-105): built when a checkpoint path is configured (the weights are not
+        # shipped; the reference's clip.load would download them); otherwise callers pass batch['clip_embed'] / the embedding itself
+        self.clip_image_encoder = None
+        if clip_path:
+            from .clip_encoder import FrozenCLIPImageEmbedder
+            self.clip_image_encoder = FrozenCLIPImageEmbedder(model=clip_path).eval().requires_grad_(False)
         self.cc_projection = nn.Sequential(nn.Linear(768 + 14 * 2, 768), nn.SiLU(True), nn.Linear(768, 768), nn.SiLU(True),
                                            nn.Linear(768, 768))
         nn.init.eye_(list(self.cc_projection.parameters())[0][:768, :768])

@@ -136,15 +136,17 @@ class NativeOps:
                 f"{' res' if residual is not None else ''}{' act%d' % act if act else ''}{' sk' if split_k != 1 else ''}"
                 f"{' +f16' if out16 is not None else ''}{' hilo' if hilo else ''}{' s2' if conv_stride == 2 else ''}")
         sig = gemm_signature(conv is not None, M, N, K, "qkv" if qkv is not None else str(out.dtype).split(".")[-1], residual is not None, act)
-        meta = {"kernel": "gemm_tc_kernel", "flops": 2.0 * M * N * K * (3 if hilo else 1), "shape": (M, N, K, split_k), "desc": desc, "sig": sig, "can_split": ws is not None,
+        meta = {"kernel": "gemm_tc_kernel", "flops": 2.0 * M * N * K, "executed_flops": 2.0 * M * N * K * (3 if hilo else 1), "shape": (M, N, K, split_k), "desc": desc, "sig": sig, "can_split": ws is not None,
                 "bytes": a_bytes + N * K * 2 + o_bytes + (M * n_out * 4 if residual is not None else 0) + (M * n_out * 2 if out16 is not None else 0)}
         return self._bind("mvd_gemm_f16", (ctypes.byref(g),), keep, meta)
 
-    def attn_self(self, q, k, vt, out, n_img, heads, seq, dhead, dpad, ldo):
-        return self._bind("mvd_attn_self_f16", (_ptr(q, torch.float16), _ptr(k, torch.float16), _ptr(vt, torch.float16),
-                                                _ptr(out, torch.float16), n_img, heads, seq, dhead, dpad, ldo),
+    def attn_self(self, q, k, vt, out, n_img, heads, seq, dhead, dpad, ldo, seq_valid=None):
+        """seq_valid < seq: keys [seq_valid, seq) are masked (padded layout of a sequence that is not a multiple of 16)"""
+        sv = seq if seq_valid is None else seq_valid
+        return self._bind("mvd_attn_self_masked_f16", (_ptr(q, torch.float16), _ptr(k, torch.float16), _ptr(vt, torch.float16),
+                                                       _ptr(out, torch.float16), n_img, heads, seq, sv, dhead, dpad, ldo),
                           (q, k, vt, out),
-                          {"kernel": "attn_self_kernel", "flops": 4.0 * n_img * heads * seq * seq * dhead,
+                          {"kernel": "attn_self_kernel", "flops": 4.0 * n_img * heads * seq * sv * dhead,
                            "desc": f"img{n_img} seq{seq} d{dhead}",
                            "bytes": 2.0 * n_img * heads * seq * (3 * dpad + dhead)})
 
@@ -172,6 +174,12 @@ class NativeOps:
         return self._bind("mvd_layernorm_f32_f16", (_ptr(x, torch.float32), _ptr(gamma, torch.float32),
                                                     _ptr(beta, torch.float32), _ptr(y, torch.float16), rows, C, eps),
                           (x, gamma, beta, y), {"desc": f"rows{rows} C{C}", "bytes": 6.0 * rows * C})
+
+    def layernorm_f32(self, x, gamma, beta, y, rows, C, eps, ldx=None, ldy=None):
+        """fp32 -> fp32 LayerNorm over rows with pitches ldx / ldy (defaults C)"""
+        return self._bind("mvd_layernorm_f32_f32", (_ptr(x, torch.float32), ldx if ldx is not None else C, _ptr(gamma, torch.float32),
+                                                    _ptr(beta, torch.float32), _ptr(y, torch.float32), ldy if ldy is not None else C, rows, C, eps),
+                          (x, gamma, beta, y), {"kernel": "layernorm_f32_f32", "desc": f"rows{rows} C{C}", "bytes": 8.0 * rows * C})
 
     def ln_modulate(self, x, shift, scale, y, rows, C, eps):
         return self._bind("mvd_ln_modulate_f32_f16", (_ptr(x, torch.float32), _ptr(shift, torch.float32),

@@ -14,12 +14,12 @@ import time
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF_DIR = os.path.join(HERE, "_ref")
+REF_DIR = os.path.join(HERE, "_ref", "ref_bytecode.zip")   # sourceless bytecode archive (oracle/build_ref.py), imported by zipimport
 SHIMS = os.path.join(HERE, "ref_shims")
 
 
 def available():
-    return os.path.exists(os.path.join(REF_DIR, "mvdfusion", "viewfusion_zero_depth_rgb.pyc"))
+    return os.path.exists(REF_DIR)
 
 
 def import_reference():

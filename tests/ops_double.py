@@ -119,7 +119,7 @@ class TorchOpsDouble:
                     lo.copy_((acc - acc.half().float()).half())
         return self._call(fn)
 
-    def attn_self(self, q, k, vt, out, n_img, heads, seq, dhead, dpad, ldo):
+    def attn_self(self, q, k, vt, out, n_img, heads, seq, dhead, dpad, ldo, seq_valid=None):
         def fn():
             n = n_img * heads * seq * dpad
             Q = q.reshape(-1)[:n].reshape(n_img, heads, seq, dpad).float()
@@ -127,6 +127,8 @@ class TorchOpsDouble:
             V = vt.reshape(-1)[:n].reshape(n_img, heads, dpad, seq).float().transpose(-1, -2)
             kd = (dhead + 15) // 16 * 16
             s = (Q[..., :kd] @ Kk[..., :kd].transpose(-1, -2)) * dhead ** -0.5
+            if seq_valid is not None and seq_valid < seq:
+                s[..., seq_valid:] = float("-inf")
             p = s.softmax(-1)
             o = (p @ V)[..., :dhead]
             out.reshape(-1)[: n_img * seq * ldo].reshape(n_img, seq, ldo)[:, :, : heads * dhead] = \
@@ -170,6 +172,14 @@ class TorchOpsDouble:
         def fn():
             v = x.reshape(-1)[: rows * C].reshape(rows, C)
             y.reshape(-1)[: rows * C].copy_(F.layer_norm(v, (C,), gamma, beta, eps).reshape(-1).half())
+        return self._call(fn)
+
+    def layernorm_f32(self, x, gamma, beta, y, rows, C, eps, ldx=None, ldy=None):
+        lx, ly = ldx if ldx is not None else C, ldy if ldy is not None else C
+
+        def fn():
+            v = torch.as_strided(x, (rows, C), (lx, 1), x.storage_offset()).clone()
+            torch.as_strided(y, (rows, C), (ly, 1), y.storage_offset()).copy_(F.layer_norm(v, (C,), gamma, beta, eps))
         return self._call(fn)
 
     def softmax_rows(self, s, p, rows, cols, scale, ld_in=None, ld_out=None):
