@@ -326,3 +326,61 @@ def test_gridattn_kernels(nat, dbl, N, D, q_first, q_count):
         M, C = 512, 640
         t = {"q": rnd(M, C, dtype=torch.float16), "kv": rnd(M * D, 2 * C, dtype=torch.float16, seed=1), "o": torch.zeros(M, C, dtype=torch.float16)}
         run_both(nat, dbl, "pixel_cross_attn", t, ["o"], "q", "kv", "o", M, D, 8, C // 8)
+
+
+@pytest.mark.parametrize("n,H,C,Cout,no_pad_lo,window", [(2, 16, 320, 320, False, False), (16, 4, 1280, 1280, False, True), (3, 8, 128, 64, True, False),
+                                                          (2, 32, 64, 128, False, True)])
+def test_conv3x3_stride2_implicit(nat, dbl, n, H, C, Cout, no_pad_lo, window):
+    """ABI 10: Downsample.op as a strided implicit GEMM (TMA element strides 2) on the full-resolution fp16 image — dense, or a column
+    window of a wider buffer (pixel pitch); H is the OUTPUT side"""
+    M = n * H * H
+    pitch = C + 192 if window else C
+    img = rnd(n * 4 * H * H, pitch, dtype=torch.float16)
+    t = {"A": img, "W": rnd(Cout, 9 * C, dtype=torch.float16, seed=1, scale=(9 * C) ** -0.5), "bias": rnd(Cout, seed=2), "out": torch.zeros(M, Cout),
+         "ws": torch.zeros(32 << 20, dtype=torch.uint8)}
+    cpu, gpu = {k: v.clone() for k, v in t.items()}, {k: v.cuda() for k, v in t.items()}
+    off = 64 if window else 0
+    kw = dict(conv=(n, H, H, C), conv_stride=2, conv_no_pad_lo=no_pad_lo, lda=pitch if window else None)
+    dbl.gemm(cpu["A"][:, off:], cpu["W"], cpu["out"], M, Cout, 9 * C, bias=cpu["bias"], **kw)(None)
+    nat.gemm(gpu["A"][:, off:], gpu["W"], gpu["out"], M, Cout, 9 * C, bias=gpu["bias"], split_k=(0 if H <= 8 else 1), ws=gpu["ws"], **kw)(
+        torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    err = (gpu["out"].cpu() - cpu["out"]).abs().max().item()
+    assert err <= 2e-3 * cpu["out"].abs().max().item(), err
+    # and against torch's strided convolution on the same fp16-rounded operands
+    import torch.nn.functional as F
+    x = img[:, off:off + C].float().reshape(n, 2 * H, 2 * H, C).permute(0, 3, 1, 2)
+    w = t["W"].float().reshape(Cout, 3, 3, C).permute(0, 3, 1, 2)
+    ref = F.conv2d(F.pad(x, (0, 1, 0, 1)) if no_pad_lo else x, w, t["bias"], stride=2, padding=0 if no_pad_lo else 1)
+    assert rel(gpu["out"].cpu(), ref.permute(0, 2, 3, 1).reshape(M, Cout)) < 1e-3
+
+
+def rel(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm())
+
+
+def test_attention_with_masked_key_padding(nat, dbl):
+    """mvd_attn_self_masked_f16: CLIP's 257 tokens in a 272-row layout — keys [257, 272) never contribute"""
+    n, heads, seq, valid, d = 2, 16, 272, 257, 64
+    g = torch.Generator().manual_seed(3)
+    q, k = torch.randn(n * heads, seq, d, generator=g).half(), torch.randn(n * heads, seq, d, generator=g).half()
+    v = torch.randn(n * heads, seq, d, generator=g).half()
+    k[:, valid:] = 50.0   # poison: huge scores if the padding keys were read
+    v[:, valid:] = 100.0
+    vt = v.transpose(1, 2).contiguous()
+    t = {"q": q, "k": k, "vt": vt, "out": torch.zeros(n * seq, heads * d, dtype=torch.float16)}
+    run_both(nat, dbl, "attn_self", t, ["out"], "q", "k", "vt", "out", n, heads, seq, d, 64, heads * d, seq_valid=valid, tol=4e-3)
+    want = torch.softmax((q[:, :, None, :].float() * k[:, None, :valid].float()).sum(-1) * d ** -0.5, -1) @ v[:, :valid].float()
+    out = nat.zeros((n * seq, heads * d), torch.float16)
+    nat.attn_self(q.cuda(), k.cuda(), vt.cuda(), out, n, heads, seq, d, 64, heads * d, seq_valid=valid)(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = out.cpu().float().reshape(n, seq, heads, d).permute(0, 2, 1, 3).reshape(n * heads, seq, d)
+    assert rel(got[:, :valid], want[:, :valid]) < 2e-3
+
+
+def test_layernorm_f32_with_row_pitch(nat, dbl):
+    rows, C, pitch = 5, 1024, 272 * 1024
+    t = {"x": rnd(rows * pitch // 1024, 1024) * 3 + 1, "g": rnd(C, seed=1), "b": rnd(C, seed=2), "y": torch.zeros(rows, C)}
+    run_both(nat, dbl, "layernorm_f32", t, ["y"], "x", "g", "b", "y", rows, C, 1e-5, ldx=pitch, tol=1e-5)
+    t2 = {"x": rnd(300, 64), "g": rnd(64, seed=1), "b": rnd(64, seed=2), "y": torch.zeros(300, 64)}
+    run_both(nat, dbl, "layernorm_f32", t2, ["y"], "x", "g", "b", "y", 300, 64, 1e-5, tol=1e-5)
