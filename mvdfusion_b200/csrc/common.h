@@ -61,7 +61,7 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int d0, int d1, int d2, lon
 int make_tmap_nhwc(CUtensorMap* out, const void* base, int n, int h, int w, int c, int bc, int bw, int bh, int bn, int pitch = 0,
                    int stride = 1);
 
-// generic 2-D map: `elem_bytes` 2 (fp16) or 4 (fp32); swizzle_bytes 0 / 128.  Used for epilogue TMA stores / residual loads.
+// generic 2-D map: `elem_bytes` 2 (fp16) or 4 (fp32); swizzle_bytes 0 / 64 / 128.  Used for epilogue TMA stores / residual loads.
 int make_tmap_2d_ex(CUtensorMap* out, const void* base, int elem_bytes, long long cols, long long rows, long long ld,
                     int box_cols, int box_rows, int swizzle_bytes);
 

@@ -28,6 +28,7 @@
 // Replaces the cuBLAS/cuDNN dispatch behind nn.Linear / nn.Conv2d on the reference hot path
 // (see include/mvd_b200.h for the file:line list).
 #include <cstdlib>
+#include <cstring>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -41,6 +42,27 @@ constexpr int STG_BYTES = 128 * 128;  // one staging chunk: 128 rows x 32 fp32, 
 constexpr int MAX_STAGES = 8;
 constexpr int WG_THREADS = 128;
 constexpr int WS_COUNTER_BYTES = 16384;  // 2048 x {arrive, done} tile semaphores at the head of the split-K workspace
+
+// ---- optional in-kernel timeline (-DMVD_GEMM_TRACE; tools/gemm_trace.py): every CTA leaves one record with the SM clock at the
+//      hand-over points of its warp roles plus the global timer at entry / exit.  Not compiled into the product library.
+#ifdef MVD_GEMM_TRACE
+struct TraceRec {
+  unsigned long long gt_entry, gt_exit;
+  unsigned int st[12];
+  int bid, grid, M, N, num_kb, BN, split, n_local, flags, pad;
+};
+constexpr unsigned TRACE_CAP = 1u << 17;
+__device__ TraceRec g_trace[TRACE_CAP];
+__device__ unsigned int g_trace_n;
+__device__ __forceinline__ unsigned long long trace_gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define MVD_TR(i) do { tr_s[i] = static_cast<unsigned int>(clock64()); } while (0)
+#else
+#define MVD_TR(i) do { } while (0)
+#endif
 
 // Division by a run-time constant as multiply-high + shift (the persistent loops decode a work unit per tile in every warp
 // role, and the QKV / row-bias epilogues divide per chunk: a hardware-emulated integer division is ~20 dependent instructions).
@@ -99,6 +121,9 @@ struct GemmKParams {
   // A_hi W_hi, A_lo W_hi, A_hi W_lo (kb_seg k-blocks each).  a_lo_off / w_lo_off: column (channel) offsets of the lo halves.
   int hilo, kb_seg, a_lo_off, w_lo_off;
   int cstride, cpad;        // CONV3X3: stride (1 / 2) and low-side padding (1, or 0 for the VAE encoder's pad-high-only downsample)
+  // TMA epilogue (template TMAE): per-warpgroup chunk slots [32 fp32 columns x 128 rows | fp16 copy | fp16 lo] that the residual
+  // is loaded into and the finished chunk is stored from, both by TMA
+  int spw, slot_bytes, slot_h16, slot_lo;  // slots per warpgroup (1 / 2), bytes per slot, offsets of the fp16 tiles inside a slot
   FastDiv fd_split, fd_tiles_m, fd_tiles_x, fd_tiles_y, fd_seq, fd_inner, fd_dhead, fd_rpg;
 };
 
@@ -116,6 +141,20 @@ __device__ __forceinline__ void store8_f16(__half* dst, const float* v) {
 }
 __device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void sts_v4u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// TMA tile load / store with the shared-memory side given as a shared-window address
+__device__ __forceinline__ void tma_load_2d_raw(uint32_t dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_raw(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   float4 v;
@@ -244,9 +283,19 @@ __device__ __forceinline__ Unit decode_unit(const GemmKParams& p, int u, int pai
 // staging tile each).  Short-K GEMMs are bound by the epilogue's latency chains (TMEM -> staging -> global with only two
 // warps per scheduler); a third warpgroup is a third chunk in flight.  Used by the specialisations whose epilogue fits
 // 128 registers.
-template <int ACT, int OUT, int RES, int SPLIT, bool VEC, bool PAIR, int NWG>
+//
+// TMAE ("TMA epilogue", unsplit F32 / F16 outputs): the in-kernel timeline (tools/gemm_trace.py, profiles/r02_gemm_trace_v2.txt)
+// shows the short-K GEMMs of the step waiting on their epilogue — 3-6 us per 128 x 160..256 tile of per-thread global loads /
+// stores chained behind their latencies, against 1.3 us of MMAs.  With TMAE no epilogue thread touches global memory for data:
+// warp 2 TMA-loads the fp32 residual chunk (128 rows x 32 columns, 128B-swizzled) into the slot of the warpgroup that will
+// finish that chunk, one or two chunks ahead; thread = row reads its accumulator row from TMEM, adds bias / row bias / residual
+// (from the slot), applies the activation, writes the result back into the slot (and optional fp16 copies next to it), and one
+// thread per warpgroup issues the TMA store of the chunk.  TMA clips the M and N tails.
+template <int ACT, int OUT, int RES, int SPLIT, bool VEC, bool PAIR, int NWG, bool TMAE>
 __global__ void __launch_bounds__(128 + 128 * NWG, 1)
-    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                   const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmO16, const __grid_constant__ CUtensorMap tmO16lo,
+                   const GemmKParams p) {
   const int act = ACT >= 0 ? ACT : p.act;
   const int out_mode = OUT >= 0 ? OUT : p.out_mode;
   const bool has_res = RES >= 0 ? (RES != 0) : (p.residual != nullptr);
@@ -257,19 +306,30 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
   const int stage_bytes = A_BYTES + b_rows * 128;
   constexpr int EPI_THREADS = NWG * WG_THREADS;
   constexpr int STG_PER_WG = NWG == 2 ? 2 : 1;
-  uint8_t* out_stg = smem + p.stages * stage_bytes;                                      // NWG x STG_PER_WG x STG_BYTES
-  float* bias_smem = reinterpret_cast<float*>(out_stg + NWG * STG_PER_WG * STG_BYTES);   // NWG x 256 floats (GEGLU tile bias)
+  uint8_t* out_stg = smem + p.stages * stage_bytes;                                      // NWG x STG_PER_WG x STG_BYTES, or the TMAE slots
+  float* bias_smem = reinterpret_cast<float*>(out_stg + (TMAE ? NWG * p.spw * p.slot_bytes : NWG * STG_PER_WG * STG_BYTES));   // NWG x 256 floats (GEGLU tile bias)
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_smem + NWG * 256);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + MAX_STAGES;
   uint64_t* acc_full = bars + 2 * MAX_STAGES;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* res_full = acc_empty + 2;     // TMAE: one per slot (<= 6)
+  uint64_t* res_empty = res_full + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int pair_rank = PAIR ? static_cast<int>(cluster_ctarank()) : -1;
   const bool leader = !PAIR || pair_rank == 0;
+#ifdef MVD_GEMM_TRACE
+  unsigned int* tr_s = tmem_slot + 4;  // inside the 512-byte barrier block of the dynamic shared memory
+  unsigned long long tr_gt0 = 0;
+  if (threadIdx.x == 0) {
+    tr_gt0 = trace_gtimer();
+    for (int i = 0; i < 12; ++i) tr_s[i] = 0;
+    MVD_TR(0);
+  }
+#endif
   pdl_trigger();  // the next kernel's CTAs may take SMs as ours retire; they block in pdl_wait() until this grid is done
 
   if (warp == 0 && lane == 0) {
@@ -283,6 +343,14 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], PAIR ? 2 * EPI_THREADS : EPI_THREADS);  // pair: the leader collects both CTAs' epilogues
     }
+    if (TMAE) {
+      tma_prefetch_desc(&tmOut);
+      if (has_res) tma_prefetch_desc(&tmRes);
+      for (int b = 0; b < 6; ++b) {
+        mbar_init(&res_full[b], 1);
+        mbar_init(&res_empty[b], 1);
+      }
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -294,6 +362,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) MVD_TR(1);
 
   const int first = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
   const int ustride = PAIR ? (gridDim.x >> 1) : gridDim.x;
@@ -315,12 +384,14 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
         }
       }
       pdl_wait();
+      MVD_TR(2);
       int s = 0;          // ring slot and its phase, advanced without divisions
       uint32_t ph = 0;
       for (int j = 0; j < n_local; ++j) {
         const Unit t = decode_unit(p, first + j * ustride, pair_rank);
         KbIter ki;
         ki.seek(p, t.kb0);
+        if (j == 1) MVD_TR(3);  // every load of the first unit has been issued
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (leader) mbar_expect_tx(&full_bar[s], PAIR ? 2 * stage_bytes : stage_bytes);
@@ -356,6 +427,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (j == 0 && kb == t.kb0) MVD_TR(4);
           const uint32_t sa = smem_u32(smem + s * stage_bytes);
           const uint64_t da = umma_desc_sw128(sa);
           const uint64_t db = umma_desc_sw128(sa + A_BYTES);
@@ -371,9 +443,212 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
         }
         if (PAIR) tc_commit_pair(&acc_full[buf], 3);
         else tc_commit(&acc_full[buf]);
+        if (j == 0) MVD_TR(5);
+        if (j == n_local - 1) MVD_TR(6);
       }
     }
-  } else if (warp >= 4) {
+  } else if (TMAE && warp == 2) {
+    // ------------------------------------------------------------ TMAE: residual chunks -> slots, in the order the warpgroups take them
+    if (lane == 0 && has_res) {
+      const int n_out = p.N, out_bn = p.BN;
+      const int nchunks = (out_bn + 31) / 32;
+      const uint32_t slots = smem_u32(out_stg);
+      pdl_wait();
+      int gbase = 0;  // chunks of this CTA before unit j; chunk g goes to warpgroup g % NWG as its (g / NWG)-th
+      for (int j = 0; j < n_local; ++j) {
+        const Unit t = decode_unit(p, first + j * ustride, pair_rank);
+        if (PAIR && t.m_tile >= p.tiles_m_real) continue;
+        const int valid = min(nchunks, (n_out - t.n_tile * out_bn + 31) / 32);
+        for (int c = 0; c < valid; ++c) {
+          const int g = gbase + c;
+          const int w = g % NWG, k = g / NWG;
+          const int sl = w * p.spw + (p.spw == 2 ? (k & 1) : 0);
+          const int nth = p.spw == 2 ? (k >> 1) : k;  // how many times this slot has been filled before
+          if (nth >= 1) mbar_wait(&res_empty[sl], (nth - 1) & 1);
+          mbar_expect_tx(&res_full[sl], 128 * 128);
+          tma_load_2d_raw(slots + sl * p.slot_bytes, &tmRes, &res_full[sl], t.n_tile * out_bn + c * 32, t.grow0);
+        }
+        gbase += valid;
+      }
+    }
+  } else if (TMAE && warp >= 4) {
+    // ------------------------------------------------------------ TMAE epilogue: thread = tile row, chunks of 32 columns
+    const int wg = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int et = q * 32 + lane;
+    const int bar_id = 1 + wg;
+    const bool geglu = (act == MVD_ACT_GEGLU);
+    const bool f16out = (out_mode == MVD_OUT_F16);
+    const int n_out = geglu ? p.N / 2 : p.N;
+    const int out_bn = geglu ? p.BN / 2 : p.BN;
+    const int nchunks = (out_bn + 31) / 32;
+    const uint32_t slot_wg = smem_u32(out_stg) + wg * p.spw * p.slot_bytes;
+    const uint32_t sw128 = static_cast<uint32_t>(et & 7), sw64 = static_cast<uint32_t>((et >> 1) & 3);
+    const uint32_t row128 = et * 128, row64 = et * 64;
+    const uint32_t f16_off = (f16out && !has_res) ? 0u : static_cast<uint32_t>(p.slot_h16);  // where the fp16 tile of a slot lives
+    pdl_wait();
+    if (warp == 4 && lane == 0) MVD_TR(7);
+    int gbase = 0;
+    for (int j = 0; j < n_local; ++j) {
+      const Unit t = decode_unit(p, first + j * ustride, pair_rank);
+      const int buf = j & 1;
+      if (PAIR && t.m_tile >= p.tiles_m_real) {  // padding half of the last pair: only the accumulator hand-shake
+        mbar_wait(&acc_full[buf], (j >> 1) & 1);
+        tc_fence_before();
+        mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[buf]), 0));
+        continue;
+      }
+      const int valid = min(nchunks, (n_out - t.n_tile * out_bn + 31) / 32);
+      mbar_wait(&acc_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      if (j == 0 && warp == 4 && lane == 0) MVD_TR(8);
+      if (j == n_local - 1 && warp == 4 && lane == 0) MVD_TR(9);
+      const uint32_t taddr = tmem_base + buf * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+      const int grow = t.grow0 + et;
+      int c0 = (wg - gbase) % NWG;
+      if (c0 < 0) c0 += NWG;
+      for (int c = c0; c < valid; c += NWG) {
+        const int k = (gbase + c) / NWG;  // this warpgroup's chunk counter
+        const int sl = p.spw == 2 ? (k & 1) : 0;
+        const uint32_t slot = slot_wg + sl * p.slot_bytes;
+        const int oc = t.n_tile * out_bn + c * 32;
+        float v[32];
+        if (geglu) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float g[16];
+            tmem_ld16(taddr + c * 32 + hh * 16, v + hh * 16);
+            tmem_ld16(taddr + p.BN / 2 + c * 32 + hh * 16, g);
+            tmem_ld_wait();
+            if (p.bias != nullptr) {
+              const float* bv = p.bias + t.n_tile * p.BN + c * 32 + hh * 16;
+              const float* bg = bv + p.BN / 2;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(bv) + i), g4 = __ldg(reinterpret_cast<const float4*>(bg) + i);
+                v[hh * 16 + 4 * i] += a4.x; v[hh * 16 + 4 * i + 1] += a4.y; v[hh * 16 + 4 * i + 2] += a4.z; v[hh * 16 + 4 * i + 3] += a4.w;
+                g[4 * i] += g4.x; g[4 * i + 1] += g4.y; g[4 * i + 2] += g4.z; g[4 * i + 3] += g4.w;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[hh * 16 + i] *= gelu_erf(g[i]);
+          }
+        } else {
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+        }
+        if (c + NWG >= valid) {  // last TMEM read of this unit by this thread: hand the accumulator back
+          tc_fence_before();
+          if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[buf]), 0));
+          else mbar_arrive(&acc_empty[buf]);
+        }
+        if (!geglu) {
+          const bool full = oc + 32 <= n_out;
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (full || oc + 4 * i + 4 <= n_out) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + oc) + i);
+                v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+              }
+            }
+          }
+          if (p.rowbias != nullptr && grow < p.M) {
+            const float* rbp = p.rowbias + static_cast<size_t>(p.fd_rpg.div(grow)) * p.N + oc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (full || oc + 4 * i + 4 <= n_out) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(rbp) + i);
+                v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+              }
+            }
+          }
+          if (act == MVD_ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          } else if (act == MVD_ACT_SILU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = silu(v[i]);
+          }
+          if (p.colscale != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (full || oc + 4 * i + 4 <= n_out) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.colscale + oc) + i);
+                v[4 * i] *= c4.x; v[4 * i + 1] *= c4.y; v[4 * i + 2] *= c4.z; v[4 * i + 3] *= c4.w;
+              }
+            }
+          }
+        }
+        if (has_res) {
+          mbar_wait(&res_full[wg * p.spw + sl], (p.spw == 2 ? (k >> 1) : k) & 1);  // the residual chunk has landed (and the slot was free)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 r4 = lds_v4(slot + row128 + ((static_cast<uint32_t>(i) ^ sw128) << 4));
+            v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
+          }
+        } else {
+          // the TMA store that last read this slot is done (one more may still be in flight with two slots)
+          if (et == 0) {
+            if (p.spw == 2) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+          }
+          named_bar_sync(bar_id, WG_THREADS);
+        }
+        if (!f16out) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sts_v4(slot + row128 + ((static_cast<uint32_t>(i) ^ sw128) << 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        if (f16out || p.out16 != nullptr) {
+          const uint32_t hrow = slot + f16_off + row64;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            sts_v4u(hrow + ((static_cast<uint32_t>(i) ^ sw64) << 4), pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
+                    pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
+          if (p.out16_lo > 0) {  // what the fp16 rounding dropped, as a second fp16 tile
+            const uint32_t lrow = slot + p.slot_lo + row64;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] -= __half2float(__float2half_rn(v[i]));
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              sts_v4u(lrow + ((static_cast<uint32_t>(i) ^ sw64) << 4), pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
+                      pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
+          }
+        }
+        fence_async_smem();
+        named_bar_sync(bar_id, WG_THREADS);
+        if (et == 0) {
+          if (f16out) {
+            tma_store_2d_raw(&tmOut, slot + f16_off, oc, t.grow0);
+          } else {
+            tma_store_2d_raw(&tmOut, slot, oc, t.grow0);
+            if (p.out16 != nullptr) tma_store_2d_raw(&tmO16, slot + f16_off, oc, t.grow0);
+            if (p.out16_lo > 0) tma_store_2d_raw(&tmO16lo, slot + p.slot_lo, oc, t.grow0);
+          }
+          tma_store_commit();
+          if (has_res) {  // hand the slot whose store has finished reading back to the residual loader
+            if (p.spw == 2) {
+              if (k >= 1) {
+                tma_store_wait_read<1>();
+                mbar_arrive(&res_empty[wg * 2 + ((k - 1) & 1)]);
+              }
+            } else {
+              tma_store_wait_read<0>();
+              mbar_arrive(&res_empty[wg]);
+            }
+          }
+        }
+      }
+      if (c0 >= valid) {  // nothing to finish in this unit: still part of the accumulator hand-shake
+        tc_fence_before();
+        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[buf]), 0));
+        else mbar_arrive(&acc_empty[buf]);
+      }
+      gbase += valid;
+    }
+    if (et == 0) tma_store_wait_all<0>();
+    if (lane == 0 && (warp & 3) == 0) MVD_TR(10);
+  } else if (!TMAE && warp >= 4) {
     // ------------------------------------------------------------ epilogue: 2 warpgroups x 128 threads
     const int wg = (warp - 4) >> 2;
     const int q = warp & 3;              // TMEM lane quadrant this warp may read
@@ -391,6 +666,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
     const int inner = p.heads * p.dhead;
     int n_staged = 0;  // staging buffer toggle
     pdl_wait();        // residual / split-K workspace reads and every output write come after the predecessor grid
+    if (warp == 4 && lane == 0) MVD_TR(7);
 
     // ---- phase A of one chunk: TMEM -> registers -> (GEGLU) -> swizzled staging tile, or the direct QKV scatter
     auto phase_a = [&](const Unit& t, uint32_t taddr, int c, uint32_t stg) -> bool {
@@ -665,6 +941,8 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
 
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
+      if (j == 0 && warp == 4 && lane == 0) MVD_TR(8);
+      if (j == n_local - 1 && warp == 4 && lane == 0) MVD_TR(9);
       const uint32_t taddr = tmem_base + buf * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
 
       if (is_split) {
@@ -737,6 +1015,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
         }
       }
     }
+    if (lane == 0 && (warp & 3) == 0) MVD_TR(10);  // last warpgroup to get here wins: end of this CTA's epilogue work
   }
 
   tc_fence_before();
@@ -747,6 +1026,21 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
     if (PAIR) tmem_dealloc_pair(tmem_base, p.tmem_cols);
     else tmem_dealloc(tmem_base, p.tmem_cols);
   }
+#ifdef MVD_GEMM_TRACE
+  if (threadIdx.x == 0) {
+    MVD_TR(11);
+    const unsigned idx = atomicAdd(&g_trace_n, 1u);
+    if (idx < TRACE_CAP) {
+      TraceRec& r = g_trace[idx];
+      r.gt_entry = tr_gt0;
+      r.gt_exit = trace_gtimer();
+      for (int i = 0; i < 12; ++i) r.st[i] = tr_s[i];
+      r.bid = blockIdx.x; r.grid = gridDim.x; r.M = p.M; r.N = p.N; r.num_kb = p.num_kb; r.BN = p.BN; r.split = p.split; r.n_local = n_local;
+      r.flags = (PAIR ? 1 : 0) | (has_res ? 2 : 0) | (act << 4) | (out_mode << 8) | (p.a_mode << 12) | (NWG << 16);
+      r.pad = 0;
+    }
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -1000,16 +1294,24 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
                    !(a->out_mode == MVD_OUT_QKV_HEADS && p.qkv_direct);
   const int has_res = a->residual != nullptr ? 1 : 0;
   const int is_split = split > 1 ? 1 : 0;
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const GemmKParams);
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmKParams);
   struct Spec { int key; int nwg; KernelFn one, two; };
 #define MVD_SPEC(ACT, OUT, RES, SPL, NWG) \
-  { (ACT) * 1000 + (OUT) * 100 + (RES) * 10 + (SPL), NWG, gemm_tc_kernel<ACT, OUT, RES, SPL, true, false, NWG>, gemm_tc_kernel<ACT, OUT, RES, SPL, true, true, NWG> }
+  { (ACT) * 1000 + (OUT) * 100 + (RES) * 10 + (SPL), NWG, gemm_tc_kernel<ACT, OUT, RES, SPL, true, false, NWG, false>, gemm_tc_kernel<ACT, OUT, RES, SPL, true, true, NWG, false> }
+#define MVD_SPEC_TMAE(ACT, OUT, RES) \
+  { (ACT) * 1000 + (OUT) * 100 + (RES) * 10, 3, gemm_tc_kernel<ACT, OUT, RES, 0, true, false, 3, true>, gemm_tc_kernel<ACT, OUT, RES, 0, true, true, 3, true> }
   // three epilogue warpgroups where the epilogue fits 128 registers (ptxas -v: <= 110 with two warpgroups), two elsewhere
   static const Spec specs[] = {
       MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 0, 0, 3),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 0, 1, 2),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 1, 0, 3),
       MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 1, 1, 2),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F16, 0, 0, 3),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F16, 1, 0, 3),
       MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F16, 1, 1, 2),  MVD_SPEC(MVD_ACT_GELU, MVD_OUT_F16, 0, 0, 3),  MVD_SPEC(MVD_ACT_GELU, MVD_OUT_F32, 0, 0, 3),
       MVD_SPEC(MVD_ACT_GEGLU, MVD_OUT_F16, 0, 0, 3), MVD_SPEC(MVD_ACT_NONE, MVD_OUT_QKV_HEADS, 0, 0, 3),
+  };
+  // the unsplit F32 / F16 forms with the TMA epilogue (MVD_GEMM_NO_TMAE=1 in the environment keeps the thread-store one: A/B measurements)
+  static const Spec specs_tmae[] = {
+      MVD_SPEC_TMAE(MVD_ACT_NONE, MVD_OUT_F32, 0), MVD_SPEC_TMAE(MVD_ACT_NONE, MVD_OUT_F32, 1), MVD_SPEC_TMAE(MVD_ACT_NONE, MVD_OUT_F16, 0),
+      MVD_SPEC_TMAE(MVD_ACT_NONE, MVD_OUT_F16, 1), MVD_SPEC_TMAE(MVD_ACT_GELU, MVD_OUT_F16, 0), MVD_SPEC_TMAE(MVD_ACT_GELU, MVD_OUT_F32, 0),
+      MVD_SPEC_TMAE(MVD_ACT_GEGLU, MVD_OUT_F16, 0),
   };
   // the same keys with two warpgroups (MVD_GEMM_WG2=1 in the environment: A/B measurements)
   static const Spec specs_wg2[] = {
@@ -1018,9 +1320,12 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
       MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 1, 0, 2),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F16, 1, 0, 2),  MVD_SPEC(MVD_ACT_GEGLU, MVD_OUT_F16, 0, 0, 2),
   };
 #undef MVD_SPEC
-  static const Spec generic = {-1, 2, gemm_tc_kernel<-1, -1, -1, -1, false, false, 2>, gemm_tc_kernel<-1, -1, -1, -1, false, true, 2>};
+#undef MVD_SPEC_TMAE
+  static const Spec generic = {-1, 2, gemm_tc_kernel<-1, -1, -1, -1, false, false, 2, false>, gemm_tc_kernel<-1, -1, -1, -1, false, true, 2, false>};
   static const bool force_wg2 = getenv("MVD_GEMM_WG2") != nullptr;
+  static const bool no_tmae = getenv("MVD_GEMM_NO_TMAE") != nullptr;
   const Spec* spec = &generic;
+  bool tmae = false;
   if (vec) {
     const int key = a->act * 1000 + a->out_mode * 100 + has_res * 10 + is_split;
     for (const Spec& sp : specs)
@@ -1028,10 +1333,25 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     if (force_wg2 && spec->nwg != 2)
       for (const Spec& sp : specs_wg2)
         if (sp.key == key) spec = &sp;
+    // TMA epilogue: every tile the TMA engine touches must be describable — 16-byte aligned bases and row pitches
+    const bool tma_ok = !is_split && a->out_mode != MVD_OUT_QKV_HEADS && al16(a->out) &&
+                        ((static_cast<long long>(a->ldc) * (a->out_mode == MVD_OUT_F32 ? 4 : 2)) & 15) == 0 &&
+                        (a->residual == nullptr || (al16(a->residual) && (a->ldr & 3) == 0)) &&
+                        (a->out16 == nullptr || (al16(a->out16) && (a->ld16 & 7) == 0 && (p.out16_lo & 7) == 0));
+    if (!no_tmae && !force_wg2 && tma_ok)
+      for (const Spec& sp : specs_tmae)
+        if (sp.key == key) {
+          spec = &sp;
+          tmae = true;
+        }
   }
   static bool configured = false;
   if (!configured) {
     for (const Spec& sp : specs) {
+      MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.one, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.two, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    }
+    for (const Spec& sp : specs_tmae) {
       MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.one, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
       MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.two, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     }
@@ -1046,10 +1366,44 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   const int nwg = spec->nwg;
   const int threads = 128 + 128 * nwg;
 
-  // ---- shared memory / TMEM budget: ring stages + staging tiles (2 per warpgroup with two warpgroups, 1 with three) +
-  //      GEGLU tile bias (256 floats per warpgroup) + barriers
+  // ---- shared memory / TMEM budget: ring stages + staging tiles (2 per warpgroup with two warpgroups, 1 with three; TMAE: the chunk
+  //      slots) + GEGLU tile bias (256 floats per warpgroup) + barriers
   const int stage_bytes = A_BYTES + (pair ? bn / 2 : bn) * 128;
-  const int fixed = (nwg == 2 ? 4 : 3) * STG_BYTES + nwg * 1024 + 512;
+  CUtensorMap tmOut, tmRes, tmO16, tmO16lo;
+  memset(&tmOut, 0, sizeof(tmOut));
+  memset(&tmRes, 0, sizeof(tmRes));
+  memset(&tmO16, 0, sizeof(tmO16));
+  memset(&tmO16lo, 0, sizeof(tmO16lo));
+  int stg_bytes_total = (nwg == 2 ? 4 : 3) * STG_BYTES;
+  if (tmae) {
+    const bool f16out = a->out_mode == MVD_OUT_F16;
+    // slot: [fp32 chunk 128 x 32 (residual in, F32 result out) | fp16 chunk | fp16 lo chunk]; an F16 output without residual needs the fp16 chunk only
+    p.slot_h16 = (f16out && !has_res) ? 0 : 16384;
+    p.slot_lo = p.slot_h16 + 8192;
+    p.slot_bytes = (f16out && !has_res) ? 8192 : 16384 + ((f16out || a->out16 != nullptr) ? 8192 : 0) + (p.out16_lo > 0 ? 8192 : 0);
+    // two slots per warpgroup (a store draining / the next residual chunk arriving while this chunk is worked on) where the epilogue is
+    // what the tile waits for — short K — or where they are cheap (fp16 chunks); deeper K wants the shared memory as ring stages
+    // (measured: 65536x256x736 GELU at 2 ring stages 49 us, at 3 stages 41 us)
+    p.spw = (p.kb_per_split <= 10 || p.slot_bytes <= 8192) ? 2 : 1;
+    if (p.spw == 2 && (232448 - 1024 - (6 * p.slot_bytes + nwg * 1024 + 512)) / stage_bytes < 3) p.spw = 1;
+    stg_bytes_total = 3 * p.spw * p.slot_bytes;
+    int rc = f16out ? make_tmap_2d_ex(&tmOut, a->out, 2, n_out, a->M, a->ldc, 32, BM, 64)
+                    : make_tmap_2d_ex(&tmOut, a->out, 4, n_out, a->M, a->ldc, 32, BM, 128);
+    if (rc != MVD_OK) return rc;
+    if (has_res) {
+      rc = make_tmap_2d_ex(&tmRes, a->residual, 4, a->N, a->M, a->ldr, 32, BM, 128);
+      if (rc != MVD_OK) return rc;
+    }
+    if (a->out16 != nullptr) {
+      rc = make_tmap_2d_ex(&tmO16, a->out16, 2, a->N, a->M, a->ld16, 32, BM, 64);
+      if (rc != MVD_OK) return rc;
+      if (p.out16_lo > 0) {
+        rc = make_tmap_2d_ex(&tmO16lo, static_cast<const __half*>(a->out16) + p.out16_lo, 2, a->N, a->M, a->ld16, 32, BM, 64);
+        if (rc != MVD_OK) return rc;
+      }
+    }
+  }
+  const int fixed = stg_bytes_total + nwg * 1024 + 512;
   int stages = (232448 - 1024 - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return set_error(MVD_EINVAL, "mvd_gemm_f16: tile does not fit in shared memory");
@@ -1060,15 +1414,29 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
 
   if (pair) {
     const int grid = 2 * (p.num_units < slots ? p.num_units : slots);
-    MVD_CUDA_CHECK(launch_kernel(spec->two, dim3(grid), dim3(threads), dyn, stream, 2, tmA, tmB, p));
+    MVD_CUDA_CHECK(launch_kernel(spec->two, dim3(grid), dim3(threads), dyn, stream, 2, tmA, tmB, tmOut, tmRes, tmO16, tmO16lo, p));
   } else {
     const int grid = p.num_units < sms ? p.num_units : sms;
-    MVD_CUDA_CHECK(launch_kernel(spec->one, dim3(grid), dim3(threads), dyn, stream, 1, tmA, tmB, p));
+    MVD_CUDA_CHECK(launch_kernel(spec->one, dim3(grid), dim3(threads), dyn, stream, 1, tmA, tmB, tmOut, tmRes, tmO16, tmO16lo, p));
   }
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
 }
+
+#ifdef MVD_GEMM_TRACE
+// debug build only: copies the CTA records gathered so far to `dst` (<= max_rec records of 96 bytes) and restarts the log
+extern "C" int mvd_debug_gemm_trace(void* dst, int max_rec) {
+  unsigned n = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n)) != cudaSuccess) return -1;
+  if (n > TRACE_CAP) n = TRACE_CAP;
+  if (static_cast<int>(n) > max_rec) n = static_cast<unsigned>(max_rec);
+  if (n > 0 && cudaMemcpyFromSymbol(dst, g_trace, static_cast<size_t>(n) * sizeof(TraceRec)) != cudaSuccess) return -1;
+  const unsigned zero = 0;
+  if (cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero)) != cudaSuccess) return -1;
+  return static_cast<int>(n);
+}
+#endif
 
 extern "C" int mvd_geglu_row_permutation(int32_t inner, int32_t tile_n, int32_t* perm) {
   if (inner <= 0 || perm == nullptr || tile_n < 64 || tile_n > 256 || (tile_n & 63) != 0 || (2 * inner) % tile_n != 0)

@@ -131,7 +131,7 @@ static void run(const Case& c) {
   mvd_gemm_args g;
   memset(&g, 0, sizeof(g));
   g.M = M; g.N = N; g.K = K; g.a_mode = c.a_mode;
-  g.A = dA; g.lda = lda;
+  g.A = dA; g.lda = c.a_mode == MVD_A_CONV3X3 ? 0 : lda;  // CONV3X3: lda is the pixel pitch (0 = dense)
   g.n_img = c.n_img; g.H = c.H; g.W = c.W; g.C = c.C;
   g.Wt = dW; g.ldw = ldw;
   g.bias = c.bias ? db : nullptr;
@@ -264,7 +264,7 @@ static double bench(const BCase& c, int iters, bool quiet = false) {
   static void* ws = nullptr; const size_t ws_bytes = 64u << 20;
   if (!ws) { CK(cudaMalloc(&ws, ws_bytes)); CK(cudaMemset(ws, 0, ws_bytes)); }
   mvd_gemm_args g; memset(&g, 0, sizeof(g));
-  g.M = c.M; g.N = c.N; g.K = c.K; g.A = dA; g.lda = c.K; g.ldw = ldw; g.bias = db; g.residual = dres; g.ldr = c.N;
+  g.M = c.M; g.N = c.N; g.K = c.K; g.A = dA; g.lda = c.conv_img ? 0 : c.K; g.ldw = ldw; g.bias = db; g.residual = dres; g.ldr = c.N;
   g.act = c.act; g.out_mode = c.out_mode; g.out = dout; g.ldc = No; g.split_k = c.split; g.tile_n = c.tile_n;
   g.splitk_ws = ws; g.splitk_ws_bytes = ws_bytes; g.rows_per_group = 1;
   if (c.conv_img) { g.a_mode = MVD_A_CONV3X3; g.n_img = c.conv_img; g.H = g.W = c.conv_hw; g.C = c.conv_c; }
