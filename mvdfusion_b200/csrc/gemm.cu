@@ -308,14 +308,15 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
   constexpr int STG_PER_WG = NWG == 2 ? 2 : 1;
   uint8_t* out_stg = smem + p.stages * stage_bytes;                                      // NWG x STG_PER_WG x STG_BYTES, or the TMAE slots
   float* bias_smem = reinterpret_cast<float*>(out_stg + (TMAE ? NWG * p.spw * p.slot_bytes : NWG * STG_PER_WG * STG_BYTES));   // NWG x 256 floats (GEGLU tile bias)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_smem + NWG * 256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_smem + NWG * (TMAE ? 512 : 256));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + MAX_STAGES;
   uint64_t* acc_full = bars + 2 * MAX_STAGES;
   uint64_t* acc_empty = acc_full + 2;
-  uint64_t* res_full = acc_empty + 2;     // TMAE: one per slot (<= 6)
-  uint64_t* res_empty = res_full + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 6);
+  uint64_t* res_full = acc_empty + 2;     // TMAE, one per slot (<= 6): the residual chunk has landed in the slot
+  uint64_t* res_empty = res_full + 6;     //       the slot's last store has read it: free for the next residual / result
+  uint64_t* out_ready = res_empty + 6;    //       the warpgroup has written the finished chunk into the slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_ready + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -349,6 +350,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
       for (int b = 0; b < 6; ++b) {
         mbar_init(&res_full[b], 1);
         mbar_init(&res_empty[b], 1);
+        mbar_init(&out_ready[b], WG_THREADS);
       }
     }
     mbar_fence_init();
@@ -471,6 +473,53 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
         gbase += valid;
       }
     }
+  } else if (TMAE && warp == 3) {
+    // ------------------------------------------------------------ TMAE: finished chunks -> global memory (TMA stores), slots handed back
+    if (lane == 0) {
+      const bool geglu = (act == MVD_ACT_GEGLU);
+      const bool f16out = (out_mode == MVD_OUT_F16);
+      const int n_out = geglu ? p.N / 2 : p.N;
+      const int out_bn = geglu ? p.BN / 2 : p.BN;
+      const int nchunks = (out_bn + 31) / 32;
+      const uint32_t slots = smem_u32(out_stg);
+      const uint32_t f16_off = (f16out && !has_res) ? 0u : static_cast<uint32_t>(p.slot_h16);
+      pdl_wait();
+      int gbase = 0, prev_sl = -1;  // prev_sl: slot of the store committed last, not yet handed back
+      for (int j = 0; j < n_local; ++j) {
+        const Unit t = decode_unit(p, first + j * ustride, pair_rank);
+        if (PAIR && t.m_tile >= p.tiles_m_real) continue;
+        const int valid = min(nchunks, (n_out - t.n_tile * out_bn + 31) / 32);
+        for (int c = 0; c < valid; ++c) {
+          const int g = gbase + c;
+          const int w = g % NWG, k = g / NWG;
+          const int sl = w * p.spw + (p.spw == 2 ? (k & 1) : 0);
+          const uint32_t par = static_cast<uint32_t>((p.spw == 2 ? (k >> 1) : k) & 1);
+          if (prev_sl >= 0 && !mbar_try_wait(&out_ready[sl], par)) {  // nothing to store yet: hand the last slot back right away
+            tma_store_wait_read<0>();
+            mbar_arrive(&res_empty[prev_sl]);
+            prev_sl = -1;
+          }
+          mbar_wait(&out_ready[sl], par);
+          const uint32_t slot = slots + sl * p.slot_bytes;
+          const int oc = t.n_tile * out_bn + c * 32;
+          if (f16out) {
+            tma_store_2d_raw(&tmOut, slot + f16_off, oc, t.grow0);
+          } else {
+            tma_store_2d_raw(&tmOut, slot, oc, t.grow0);
+            if (p.out16 != nullptr) tma_store_2d_raw(&tmO16, slot + f16_off, oc, t.grow0);
+            if (p.out16_lo > 0) tma_store_2d_raw(&tmO16lo, slot + p.slot_lo, oc, t.grow0);
+          }
+          tma_store_commit();
+          if (prev_sl >= 0) {  // the store before this one has read its slot
+            tma_store_wait_read<1>();
+            mbar_arrive(&res_empty[prev_sl]);
+          }
+          prev_sl = sl;
+        }
+        gbase += valid;
+      }
+      tma_store_wait_read<0>();  // shared memory stays valid until the stores have read it; the writes complete with the grid
+    }
   } else if (TMAE && warp >= 4) {
     // ------------------------------------------------------------ TMAE epilogue: thread = tile row, chunks of 32 columns
     const int wg = (warp - 4) >> 2;
@@ -486,6 +535,20 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
     const uint32_t sw128 = static_cast<uint32_t>(et & 7), sw64 = static_cast<uint32_t>((et >> 1) & 3);
     const uint32_t row128 = et * 128, row64 = et * 64;
     const uint32_t f16_off = (f16out && !has_res) ? 0u : static_cast<uint32_t>(p.slot_h16);  // where the fp16 tile of a slot lives
+    float* sbias = bias_smem + wg * 512;   // [bias of the tile's BN columns | column scale]
+    const bool use_sb = (p.bias != nullptr || p.colscale != nullptr) && out_mode != MVD_OUT_QKV_HEADS;
+    int sb_tile = -1;
+    if (use_sb && n_local > 0) {            // bias and gate vectors are parameters: they may be fetched before the grid dependency resolves
+      const Unit t = decode_unit(p, first, pair_rank);
+      const int nb = t.n_tile * p.BN;
+      for (int kk = et; kk < p.BN; kk += WG_THREADS) {
+        const bool in = nb + kk < p.N;
+        if (p.bias != nullptr) sbias[kk] = in ? __ldg(p.bias + nb + kk) : 0.f;
+        if (p.colscale != nullptr) sbias[256 + kk] = in ? __ldg(p.colscale + nb + kk) : 1.f;
+      }
+      sb_tile = t.n_tile;
+      named_bar_sync(bar_id, WG_THREADS);
+    }
     pdl_wait();
     if (warp == 4 && lane == 0) MVD_TR(7);
     int gbase = 0;
@@ -499,6 +562,19 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
         continue;
       }
       const int valid = min(nchunks, (n_out - t.n_tile * out_bn + 31) / 32);
+      // the unit's bias (and adaLN gate) columns -> this warpgroup's shared vector while the MMAs are still running: a first-touch
+      // global load in front of the first chunk costs ~0.8 us on the critical path of every short GEMM
+      if (use_sb && t.n_tile != sb_tile) {
+        named_bar_sync(bar_id, WG_THREADS);  // everybody is done with the previous unit's vector
+        const int nb = t.n_tile * p.BN;
+        for (int kk = et; kk < p.BN; kk += WG_THREADS) {
+          const bool in = nb + kk < p.N;
+          if (p.bias != nullptr) sbias[kk] = in ? __ldg(p.bias + nb + kk) : 0.f;
+          if (p.colscale != nullptr) sbias[256 + kk] = in ? __ldg(p.colscale + nb + kk) : 1.f;
+        }
+        sb_tile = t.n_tile;
+        named_bar_sync(bar_id, WG_THREADS);
+      }
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
       if (j == 0 && warp == 4 && lane == 0) MVD_TR(8);
@@ -510,6 +586,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
       for (int c = c0; c < valid; c += NWG) {
         const int k = (gbase + c) / NWG;  // this warpgroup's chunk counter
         const int sl = p.spw == 2 ? (k & 1) : 0;
+        const int nth = p.spw == 2 ? (k >> 1) : k;  // how often this slot has been used before
         const uint32_t slot = slot_wg + sl * p.slot_bytes;
         const int oc = t.n_tile * out_bn + c * 32;
         float v[32];
@@ -521,11 +598,10 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
             tmem_ld16(taddr + p.BN / 2 + c * 32 + hh * 16, g);
             tmem_ld_wait();
             if (p.bias != nullptr) {
-              const float* bv = p.bias + t.n_tile * p.BN + c * 32 + hh * 16;
-              const float* bg = bv + p.BN / 2;
+              const uint32_t sv = smem_u32(sbias + c * 32 + hh * 16), sg = smem_u32(sbias + p.BN / 2 + c * 32 + hh * 16);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float4 a4 = __ldg(reinterpret_cast<const float4*>(bv) + i), g4 = __ldg(reinterpret_cast<const float4*>(bg) + i);
+                const float4 a4 = lds_v4(sv + i * 16), g4 = lds_v4(sg + i * 16);
                 v[hh * 16 + 4 * i] += a4.x; v[hh * 16 + 4 * i + 1] += a4.y; v[hh * 16 + 4 * i + 2] += a4.z; v[hh * 16 + 4 * i + 3] += a4.w;
                 g[4 * i] += g4.x; g[4 * i + 1] += g4.y; g[4 * i + 2] += g4.z; g[4 * i + 3] += g4.w;
               }
@@ -545,12 +621,11 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
         if (!geglu) {
           const bool full = oc + 32 <= n_out;
           if (p.bias != nullptr) {
+            const uint32_t sv = smem_u32(sbias + c * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              if (full || oc + 4 * i + 4 <= n_out) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + oc) + i);
-                v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-              }
+              const float4 b4 = lds_v4(sv + i * 16);
+              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
             }
           }
           if (p.rowbias != nullptr && grow < p.M) {
@@ -571,29 +646,23 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
             for (int i = 0; i < 32; ++i) v[i] = silu(v[i]);
           }
           if (p.colscale != nullptr) {
+            const uint32_t sv = smem_u32(sbias + 256 + c * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              if (full || oc + 4 * i + 4 <= n_out) {
-                const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.colscale + oc) + i);
-                v[4 * i] *= c4.x; v[4 * i + 1] *= c4.y; v[4 * i + 2] *= c4.z; v[4 * i + 3] *= c4.w;
-              }
+              const float4 c4 = lds_v4(sv + i * 16);
+              v[4 * i] *= c4.x; v[4 * i + 1] *= c4.y; v[4 * i + 2] *= c4.z; v[4 * i + 3] *= c4.w;
             }
           }
         }
         if (has_res) {
-          mbar_wait(&res_full[wg * p.spw + sl], (p.spw == 2 ? (k >> 1) : k) & 1);  // the residual chunk has landed (and the slot was free)
+          mbar_wait(&res_full[wg * p.spw + sl], nth & 1);  // the residual chunk has landed (and the slot was free)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 r4 = lds_v4(slot + row128 + ((static_cast<uint32_t>(i) ^ sw128) << 4));
             v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
           }
-        } else {
-          // the TMA store that last read this slot is done (one more may still be in flight with two slots)
-          if (et == 0) {
-            if (p.spw == 2) tma_store_wait_read<1>();
-            else tma_store_wait_read<0>();
-          }
-          named_bar_sync(bar_id, WG_THREADS);
+        } else if (nth >= 1) {
+          mbar_wait(&res_empty[wg * p.spw + sl], (nth - 1) & 1);  // the store that last used this slot has read it
         }
         if (!f16out) {
 #pragma unroll
@@ -615,29 +684,8 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
                       pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
           }
         }
-        fence_async_smem();
-        named_bar_sync(bar_id, WG_THREADS);
-        if (et == 0) {
-          if (f16out) {
-            tma_store_2d_raw(&tmOut, slot + f16_off, oc, t.grow0);
-          } else {
-            tma_store_2d_raw(&tmOut, slot, oc, t.grow0);
-            if (p.out16 != nullptr) tma_store_2d_raw(&tmO16, slot + f16_off, oc, t.grow0);
-            if (p.out16_lo > 0) tma_store_2d_raw(&tmO16lo, slot + p.slot_lo, oc, t.grow0);
-          }
-          tma_store_commit();
-          if (has_res) {  // hand the slot whose store has finished reading back to the residual loader
-            if (p.spw == 2) {
-              if (k >= 1) {
-                tma_store_wait_read<1>();
-                mbar_arrive(&res_empty[wg * 2 + ((k - 1) & 1)]);
-              }
-            } else {
-              tma_store_wait_read<0>();
-              mbar_arrive(&res_empty[wg]);
-            }
-          }
-        }
+        fence_async_smem();                          // generic-proxy writes -> visible to the TMA store
+        mbar_arrive(&out_ready[wg * p.spw + sl]);    // warp 3 stores the chunk and hands the slot back; no warpgroup barrier per chunk
       }
       if (c0 >= valid) {  // nothing to finish in this unit: still part of the accumulator hand-shake
         tc_fence_before();
@@ -646,7 +694,6 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
       }
       gbase += valid;
     }
-    if (et == 0) tma_store_wait_all<0>();
     if (lane == 0 && (warp & 3) == 0) MVD_TR(10);
   } else if (!TMAE && warp >= 4) {
     // ------------------------------------------------------------ epilogue: 2 warpgroups x 128 threads
@@ -1334,7 +1381,11 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
       for (const Spec& sp : specs_wg2)
         if (sp.key == key) spec = &sp;
     // TMA epilogue: every tile the TMA engine touches must be describable — 16-byte aligned bases and row pitches
-    const bool tma_ok = !is_split && a->out_mode != MVD_OUT_QKV_HEADS && al16(a->out) &&
+    // (A TMA form of the QKV head scatter — 8-column boxes per (q | k | v, head) — was measured and dropped: 16-byte-wide boxes
+    // make the TMA engine write 128 separate 16-byte rows per box; 16384x960x320 went from 22.0 to 23.2 us.)
+    // Deep-K GEMMs hide their epilogue behind the mainloop and lose 5-6 % with the TMA stores in flight (conv 16384x640x5760
+    // 75.5 -> 80.7 us): they keep the thread-store epilogue.
+    const bool tma_ok = !is_split && a->out_mode != MVD_OUT_QKV_HEADS && p.kb_per_split <= 24 && al16(a->out) &&
                         ((static_cast<long long>(a->ldc) * (a->out_mode == MVD_OUT_F32 ? 4 : 2)) & 15) == 0 &&
                         (a->residual == nullptr || (al16(a->residual) && (a->ldr & 3) == 0)) &&
                         (a->out16 == nullptr || (al16(a->out16) && (a->ld16 & 7) == 0 && (p.out16_lo & 7) == 0));
@@ -1385,7 +1436,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     // what the tile waits for — short K — or where they are cheap (fp16 chunks); deeper K wants the shared memory as ring stages
     // (measured: 65536x256x736 GELU at 2 ring stages 49 us, at 3 stages 41 us)
     p.spw = (p.kb_per_split <= 10 || p.slot_bytes <= 8192) ? 2 : 1;
-    if (p.spw == 2 && (232448 - 1024 - (6 * p.slot_bytes + nwg * 1024 + 512)) / stage_bytes < 3) p.spw = 1;
+    if (p.spw == 2 && (232448 - 1024 - (6 * p.slot_bytes + nwg * 2048 + 512)) / stage_bytes < 3) p.spw = 1;
     stg_bytes_total = 3 * p.spw * p.slot_bytes;
     int rc = f16out ? make_tmap_2d_ex(&tmOut, a->out, 2, n_out, a->M, a->ldc, 32, BM, 64)
                     : make_tmap_2d_ex(&tmOut, a->out, 4, n_out, a->M, a->ldc, 32, BM, 128);
@@ -1403,7 +1454,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
       }
     }
   }
-  const int fixed = stg_bytes_total + nwg * 1024 + 512;
+  const int fixed = stg_bytes_total + nwg * (tmae ? 2048 : 1024) + 512;
   int stages = (232448 - 1024 - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return set_error(MVD_EINVAL, "mvd_gemm_f16: tile does not fit in shared memory");
