@@ -200,10 +200,24 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         for (int i = 0; i < BKV; ++i)
           if (i >= kv_valid) s[i] = -INFINITY;
       }
-      float mt = s[0];
+      // row maximum as four independent chains (one chain of BKV / 2 dependent maxima is ~300 cycles of latency per tile that the
+      // two warps per scheduler cannot cover)
+      float mt;
+      if (BKV >= 16) {
+        float m0 = s[0], m1 = s[1], m2 = s[2], m3 = s[3];
 #pragma unroll
-      for (int i = 1; i + 1 < BKV; i += 2) mt = fmaxf(mt, fmaxf(s[i], s[i + 1]));
-      mt = fmaxf(mt, s[BKV - 1]);
+        for (int i = 4; i < BKV; i += 4) {
+          m0 = fmaxf(m0, s[i]);
+          m1 = fmaxf(m1, s[i + 1]);
+          m2 = fmaxf(m2, s[i + 2]);
+          m3 = fmaxf(m3, s[i + 3]);
+        }
+        mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      } else {
+        mt = s[0];
+#pragma unroll
+        for (int i = 1; i < BKV; ++i) mt = fmaxf(mt, s[i]);
+      }
       float f = 1.f;
       bool rescale = false;
       if (j == 0) {

@@ -206,14 +206,17 @@ def test_qkv_and_attention(nat, dbl, n, seq, C):
 
 @pytest.mark.parametrize("n,hw,C,silu", [(2, 1024, 320, True), (16, 16, 2560, True), (3, 256, 1920, False), (2, 1024, 960, True),
                                          (2, 4096, 320, True), (1, 4096, 960, False), (3, 64, 1280, True), (2, 256, 640, True),
-                                         (1, 100, 64, True), (2, 16384, 32, False)])
+                                         (1, 100, 64, True), (2, 16384, 32, False),
+                                         # enough images for the slab form (a cluster of 8 slabs per image held in shared memory)
+                                         (16, 1024, 320, True), (16, 256, 640, True), (16, 64, 1280, True), (16, 16, 1280, True), (12, 256, 1280, False)])
 def test_groupnorm(nat, dbl, n, hw, C, silu):
     t = {"x": rnd(n * hw, C) * 2 + 0.5, "g": rnd(C, seed=1), "b": rnd(C, seed=2), "y": torch.zeros(n * hw, C, dtype=torch.float16),
          "ws": torch.zeros(max(n, 64) * 64, dtype=torch.float64)}
     run_both(nat, dbl, "groupnorm", t, ["y"], "x", "g", "b", "y", "ws", n, hw, C, 1e-5, silu)
 
 
-@pytest.mark.parametrize("n,hw,C1,C2", [(2, 1024, 320, 320), (3, 256, 640, 320), (4, 16, 1280, 1280), (2, 64, 1280, 640)])
+@pytest.mark.parametrize("n,hw,C1,C2", [(2, 1024, 320, 320), (3, 256, 640, 320), (4, 16, 1280, 1280), (2, 64, 1280, 640),
+                                        (16, 256, 320, 320), (16, 64, 640, 640), (16, 16, 640, 640), (16, 256, 640, 320)])
 def test_groupnorm_two_sources_and_concat16(nat, dbl, n, hw, C1, C2):
     C = C1 + C2
     t = {"a": rnd(n * hw, C1, seed=1) + 0.3, "b": rnd(n * hw, C2, seed=2) * 2.0, "g": rnd(C, seed=3), "be": rnd(C, seed=4),
