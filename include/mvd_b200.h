@@ -241,6 +241,44 @@ int mvd_frustum_pool_f16(const void* in, void* out, int32_t n_img, int32_t S, in
 int mvd_pixel_cross_attn_f16(const void* q, const void* kv, void* out, int32_t M, int32_t D, int32_t heads,
                              int32_t dhead, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * GridAttn aggregation transformer as ONE kernel (SURVEY.md kernel K10): pre_layer_b (Linear 723 -> 256 + GELU), the adaLN-Zero DiT
+ * blocks over the view axis and the view-softmax pooling (mvdfusion/view_attn_efficient2.py:365-410, :45-70 DiTBlock,
+ * :83-97 weight_layer / pooling).  A persistent CTA per SM takes 128 token rows (128 / V points x V views, rows = point * V + view),
+ * keeps their fp32 residual stream in TMEM through every block — LayerNorm-modulate, the per-head q | k | v projections, the V x V
+ * attention, proj, fc1-GELU-fc2 all run out of shared memory / TMEM — and writes only the pooled fp16 [P, 256] features.
+ * Replaces 1 + 7 * layers + 1 launches and the fp32 [P*V, 256] stream round trips of the unfused program.
+ *
+ * Weights are fp16 [out, in] row-major (nn.Linear), biases / vectors fp32:
+ *   w_qkv rows in HEAD order: head h -> rows [96h, 96h + 96) = q_h (32) | k_h (32) | v_h (32); b_qkv likewise
+ *   w_proj, w_fc2 (and b_proj, b_fc2) carry the adaLN gate of this step: W' = diag(gate) W, b' = gate * b  (mvd_dit_fold_gates),
+ *   so that x += gate * (a W^T + b) is a plain accumulation into the resident stream
+ *   shift / scale: the adaLN modulate vectors of norm1 (msa) and norm2 (mlp)
+ * 128 % V == 0, V <= 32; hidden 256, 8 heads x 32, mlp 512 (the reference's only configuration).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mvd_dit_layer {
+  const void* w_qkv;   const float* b_qkv;    /* [768, 256], [768]  (head order) */
+  const void* w_proj;  const float* b_proj;   /* [256, 256], [256]  (gate folded) */
+  const void* w_fc1;   const float* b_fc1;    /* [512, 256], [512] */
+  const void* w_fc2;   const float* b_fc2;    /* [256, 512], [256]  (gate folded) */
+  const float* shift_msa; const float* scale_msa; const float* shift_mlp; const float* scale_mlp;  /* [256] each */
+} mvd_dit_layer;
+typedef struct mvd_dit_args {
+  int32_t R, V, layers;          /* token rows (= P * V), views per point, DiT blocks (1..4) */
+  int32_t token_k, token_ld;     /* token width (K of pre_layer_b) and row pitch, both multiples of 8 */
+  const void* tokens;            /* fp16 [R, token_ld] */
+  const void* w_pre; int32_t w_pre_ld; const float* b_pre;   /* fp16 [256, w_pre_ld >= token_k], fp32 [256] */
+  mvd_dit_layer layer[4];
+  const float* pool_w; const float* pool_b;   /* weight_layer: fp32 [256], [1] */
+  void* pooled;                  /* fp16 [R / V, 256] */
+  float* x_out;                  /* optional fp32 [R, 256]: the stream after the last block (parity tests); NULL in the product */
+  float eps;                     /* LayerNorm eps (1e-6) */
+} mvd_dit_args;
+int mvd_gridattn_dit_f16(const mvd_dit_args* args, void* stream);
+/* W_out[n, :] = fp16(gate[n] * W[n, :]), b_out[n] = gate[n] * b[n] for up to 8 (W, b) pairs in one launch */
+typedef struct mvd_fold_job { const void* w; const float* gate; const float* bias; void* w_out; float* b_out; int32_t N, K; } mvd_fold_job;
+int mvd_dit_fold_gates(const mvd_fold_job* jobs, int32_t n_jobs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_float, c_int32, c_longlong, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # MVD_B200_LIB: another build of the same library (e.g. the instrumented `make trace` one); it must exist — there is no fallback
 LIB_PATH = os.environ.get("MVD_B200_LIB") or os.path.join(_HERE, "libmvd_b200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 
 class GemmArgs(ctypes.Structure):
@@ -33,6 +33,30 @@ class GemmArgs(ctypes.Structure):
     ]
 
 
+class DitLayer(ctypes.Structure):
+    """struct mvd_dit_layer (include/mvd_b200.h)"""
+
+    _fields_ = [(n, c_void_p) for n in ("w_qkv", "b_qkv", "w_proj", "b_proj", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
+                                        "shift_msa", "scale_msa", "shift_mlp", "scale_mlp")]
+
+
+class DitArgs(ctypes.Structure):
+    """struct mvd_dit_args (include/mvd_b200.h)"""
+
+    _fields_ = [
+        ("R", c_int32), ("V", c_int32), ("layers", c_int32), ("token_k", c_int32), ("token_ld", c_int32),
+        ("tokens", c_void_p), ("w_pre", c_void_p), ("w_pre_ld", c_int32), ("b_pre", c_void_p),
+        ("layer", DitLayer * 4),
+        ("pool_w", c_void_p), ("pool_b", c_void_p), ("pooled", c_void_p), ("x_out", c_void_p), ("eps", c_float),
+    ]
+
+
+class FoldJob(ctypes.Structure):
+    """struct mvd_fold_job (include/mvd_b200.h)"""
+
+    _fields_ = [("w", c_void_p), ("gate", c_void_p), ("bias", c_void_p), ("w_out", c_void_p), ("b_out", c_void_p), ("N", c_int32), ("K", c_int32)]
+
+
 i32, vp, f32, i64 = c_int32, c_void_p, c_float, c_longlong
 
 # name -> argtypes (every entry returns int unless listed in _RESTYPE)
@@ -42,6 +66,8 @@ SIGNATURES = {
     "mvd_launch_count": [],
     "mvd_gemm_f16": [ctypes.POINTER(GemmArgs), vp],
     "mvd_geglu_row_permutation": [i32, i32, vp],
+    "mvd_gridattn_dit_f16": [ctypes.POINTER(DitArgs), vp],
+    "mvd_dit_fold_gates": [ctypes.POINTER(FoldJob), i32, vp],
     "mvd_attn_self_f16": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "mvd_attn_self_masked_f16": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "mvd_groupnorm_f32_f16": [vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp],

@@ -97,6 +97,20 @@ class PackedWeights:
             return self._pad_k(w).half()
         return self._put("lin", (key, k_pad), f)
 
+    @staticmethod
+    def _head_order(heads, hd):
+        """row permutation of a timm qkv Linear ([q | k | v] x heads x hd) into head-major [q_h | k_h | v_h] blocks
+        (mvd_gridattn_dit_f16 computes one head's q, k, v as one 96-column product)"""
+        C = heads * hd
+        idx = torch.arange(3 * C).reshape(3, heads, hd).permute(1, 0, 2).reshape(-1)
+        return idx
+
+    def qkv_heads(self, key, heads, hd):
+        return self._put("qkv_heads", key, lambda: self.raw(key).float()[self._head_order(heads, hd)].half())
+
+    def f32_heads(self, key, heads, hd):
+        return self._put("f32_heads", key, lambda: self.raw(key).float().reshape(-1)[self._head_order(heads, hd)])
+
     def conv3(self, key, c_pad=None):
         """conv3x3 weight [Cout, Cin, 3, 3] -> fp16 [Cout, 9*Cin_pad], k = (ky*3 + kx)*Cin_pad + c"""
         def f():
@@ -804,6 +818,39 @@ def emit_gridattn(b, *, noisy, input_latent, depth_override, depth_eps, scal, ca
     b.prog.append(b.ops.gridattn_tokens(feat, zdepth, cams, mask, harm_freqs, ndc_grid, tokens, n_views, S, D, q_first, q_count))
     b.free(feat, zdepth)
     b.prog.mark("gridattn.transformer")
+    hid0 = W.raw("aggregation_transformer.layer_list.0.mlp.fc1.weight").shape[0]
+    # One kernel for pre_layer_b + the DiT blocks + the view pooling (csrc/dit.cu) whenever the tile geometry allows it: the V rows of
+    # a point must sit inside one 128-row tile.  MVD_NO_DIT_FUSION=1 keeps the unfused program (A/B measurements).
+    fused = (V & (V - 1)) == 0 and V <= 16 and num_heads == 8 and Z_CH == 256 and hid0 == 512 and 1 <= num_layers <= 4 and \
+        not os.environ.get("MVD_NO_DIT_FUSION")
+    if fused:
+        mods = [b.ops.empty((6 * Z_CH,), torch.float32) for _ in range(num_layers)]
+        b.prog.append(b.ops.gemv_grouped(c_embed, Z_CH, [(W.lin(f"aggregation_transformer.layer_list.{i}.adaLN_modulation.1.weight"),
+                                                          W.f32(f"aggregation_transformer.layer_list.{i}.adaLN_modulation.1.bias"), mods[i])
+                                                         for i in range(num_layers)], silu_in=True))
+        layers, jobs = [], []
+        for i in range(num_layers):
+            p = f"aggregation_transformer.layer_list.{i}"
+            ch = [mods[i][j * Z_CH:(j + 1) * Z_CH] for j in range(6)]  # shift / scale / gate (msa), shift / scale / gate (mlp)
+            wp, wf = W.lin(p + ".attn.proj.weight"), W.lin(p + ".mlp.fc2.weight")
+            wp_g, wf_g = b.ops.empty(tuple(wp.shape), torch.float16), b.ops.empty(tuple(wf.shape), torch.float16)
+            bp_g, bf_g = b.ops.empty((Z_CH,), torch.float32), b.ops.empty((Z_CH,), torch.float32)
+            jobs += [(wp, ch[2], W.f32(p + ".attn.proj.bias"), wp_g, bp_g), (wf, ch[5], W.f32(p + ".mlp.fc2.bias"), wf_g, bf_g)]
+            layers.append({"w_qkv": W.qkv_heads(p + ".attn.qkv.weight", num_heads, Z_CH // num_heads),
+                           "b_qkv": W.f32_heads(p + ".attn.qkv.bias", num_heads, Z_CH // num_heads),
+                           "w_proj": wp_g, "b_proj": bp_g, "w_fc1": W.lin(p + ".mlp.fc1.weight"), "b_fc1": W.f32(p + ".mlp.fc1.bias"),
+                           "w_fc2": wf_g, "b_fc2": bf_g, "shift_msa": ch[0], "scale_msa": ch[1], "shift_mlp": ch[3], "scale_mlp": ch[4]})
+        for j0 in range(0, len(jobs), 8):
+            b.prog.append(b.ops.dit_fold_gates(jobs[j0:j0 + 8]))
+        pooled = b.t16(P, Z_CH)
+        b.prog.append(b.ops.gridattn_dit(tokens, TOKEN_LD, W.lin("pre_layer_b.0.weight", k_pad=TOKEN_LD), W.f32("pre_layer_b.0.bias"), layers,
+                                         W.f32("aggregation_transformer.weight_layer.weight"), W.f32("aggregation_transformer.weight_layer.bias"),
+                                         pooled, R, V, 1e-6))
+        b.free(tokens)
+        out_dim = W.raw("final_layer_b.weight").shape[0]
+        b.gemm(pooled, W.lin("final_layer_b.weight"), frustum_out, P, out_dim, Z_CH, bias=W.f32("final_layer_b.bias"))
+        b.free(pooled)
+        return
     x = b.t32(R, Z_CH)
     b.gemm(tokens, W.lin("pre_layer_b.0.weight", k_pad=TOKEN_LD), x, R, Z_CH, TOKEN_LD, bias=W.f32("pre_layer_b.0.bias"),
            act=ACT_GELU)

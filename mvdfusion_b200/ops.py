@@ -285,6 +285,31 @@ class NativeOps:
         return self._bind("mvd_view_attention_f16", (_ptr(qkv, torch.float16), _ptr(out, torch.float16), P, V, heads, hd),
                           (qkv, out))
 
+    def dit_fold_gates(self, jobs):
+        """jobs: list of (W fp16 [N, K], gate fp32 [N], bias fp32 [N], W_out fp16 [N, K], b_out fp32 [N]): W_out = gate[:, None] * W, b_out = gate * b"""
+        arr = (_lib.FoldJob * len(jobs))()
+        for j, (W, gate, bias, Wo, bo) in zip(arr, jobs):
+            j.w, j.gate, j.bias, j.w_out, j.b_out = (_ptr(W, torch.float16), _ptr(gate, torch.float32), _ptr(bias, torch.float32),
+                                                     _ptr(Wo, torch.float16), _ptr(bo, torch.float32))
+            j.N, j.K = W.shape[0], W.shape[1]
+        return self._bind("mvd_dit_fold_gates", (arr, len(jobs)), (arr, jobs))
+
+    def gridattn_dit(self, tokens, token_k, w_pre, b_pre, layers, pool_w, pool_b, pooled, R, V, eps, x_out=None):
+        """The aggregation transformer as one kernel (include/mvd_b200.h, mvd_gridattn_dit_f16).  layers: list of dicts with the
+        mvd_dit_layer field names (w_qkv in head order, w_proj / w_fc2 / b_proj / b_fc2 gate-folded)."""
+        a = _lib.DitArgs()
+        a.R, a.V, a.layers, a.token_k, a.token_ld = R, V, len(layers), token_k, tokens.shape[-1]
+        a.tokens, a.w_pre, a.w_pre_ld, a.b_pre = _ptr(tokens, torch.float16), _ptr(w_pre, torch.float16), w_pre.shape[-1], _ptr(b_pre, torch.float32)
+        for i, lay in enumerate(layers):
+            for name, _ in _lib.DitLayer._fields_:
+                setattr(a.layer[i], name, _ptr(lay[name], torch.float16 if name.startswith("w_") else torch.float32))
+        a.pool_w, a.pool_b, a.pooled, a.x_out, a.eps = (_ptr(pool_w, torch.float32), _ptr(pool_b, torch.float32), _ptr(pooled, torch.float16),
+                                                         _ptr(x_out, torch.float32), eps)
+        nl = len(layers)
+        flops = 2.0 * R * (token_k * 256 + nl * (768 * 256 + 256 * 256 + 2 * 512 * 256))
+        return self._bind("mvd_gridattn_dit_f16", (ctypes.byref(a),), (a, tokens, w_pre, b_pre, layers, pool_w, pool_b, pooled, x_out),
+                          {"kernel": "gridattn_dit", "desc": f"rows{R} V{V} layers{nl}", "flops": flops, "bytes": 2.0 * R * tokens.shape[-1]})
+
     def view_pool(self, x, w, b, out, P, V, C):
         return self._bind("mvd_view_pool_f16", (_ptr(x, torch.float32), _ptr(w, torch.float32), _ptr(b, torch.float32),
                                                 _ptr(out, torch.float16), P, V, C), (x, w, b, out))

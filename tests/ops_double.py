@@ -401,6 +401,34 @@ class TorchOpsDouble:
             out.reshape(-1)[: P * V * C].copy_(a.transpose(1, 2).reshape(-1).half())
         return self._call(fn)
 
+    def dit_fold_gates(self, jobs):
+        def fn():
+            for W, gate, bias, Wo, bo in jobs:
+                Wo.copy_((W.float() * gate.reshape(-1, 1)).half())
+                bo.copy_(gate * bias)
+        return self._call(fn)
+
+    def gridattn_dit(self, tokens, token_k, w_pre, b_pre, layers, pool_w, pool_b, pooled, R, V, eps, x_out=None):
+        """mvd_gridattn_dit_f16: fp16 operands (tokens, LayerNorm output, q / k / v, attention output, fc1 output), fp32 stream"""
+        def fn():
+            h = lambda t: t.half().float()
+            x = F.gelu(tokens[:R, :token_k].float() @ w_pre[:, :token_k].float().t() + b_pre)
+            for lay in layers:
+                a = h(F.layer_norm(x, (256,), None, None, eps) * (1 + lay["scale_msa"]) + lay["shift_msa"])
+                qkv = h(a @ lay["w_qkv"].float().t() + lay["b_qkv"]).reshape(R // V, V, 8, 3, 32)   # head order: q_h | k_h | v_h
+                q, k, v = (qkv[:, :, :, i].permute(0, 2, 1, 3) for i in range(3))
+                att = h(((q * 32 ** -0.5) @ k.transpose(-1, -2)).softmax(-1) @ v).permute(0, 2, 1, 3).reshape(R, 256)
+                x = x + att @ lay["w_proj"].float().t() + lay["b_proj"]
+                a = h(F.layer_norm(x, (256,), None, None, eps) * (1 + lay["scale_mlp"]) + lay["shift_mlp"])
+                f = h(F.gelu(a @ lay["w_fc1"].float().t() + lay["b_fc1"]))
+                x = x + f @ lay["w_fc2"].float().t() + lay["b_fc2"]
+            if x_out is not None:
+                x_out.reshape(-1)[: R * 256].copy_(x.reshape(-1))
+            v3 = x.reshape(R // V, V, 256)
+            wt = (v3 @ pool_w.reshape(256, 1) + pool_b.reshape(-1)[0]).softmax(dim=1)
+            pooled.reshape(-1)[: (R // V) * 256].copy_((v3 * wt).sum(1).reshape(-1).half())
+        return self._call(fn)
+
     def view_pool(self, x, w, b, out, P, V, C):
         def fn():
             v = x.reshape(-1)[: P * V * C].reshape(P, V, C)

@@ -387,3 +387,47 @@ def test_layernorm_f32_with_row_pitch(nat, dbl):
     run_both(nat, dbl, "layernorm_f32", t, ["y"], "x", "g", "b", "y", rows, C, 1e-5, ldx=pitch, tol=1e-5)
     t2 = {"x": rnd(300, 64), "g": rnd(64, seed=1), "b": rnd(64, seed=2), "y": torch.zeros(300, 64)}
     run_both(nat, dbl, "layernorm_f32", t2, ["y"], "x", "g", "b", "y", 300, 64, 1e-5, tol=1e-5)
+
+
+def _dit_inputs(R, V, nl, token_k=736, seed=0):
+    g = torch.Generator().manual_seed(100 + seed)
+    r = lambda *s, scale=1.0: torch.randn(*s, generator=g) * scale
+    t = {"tokens": r(R, token_k).half(), "w_pre": r(256, token_k, scale=token_k ** -0.5).half(), "b_pre": r(256, scale=0.1),
+         "pool_w": r(256, scale=0.1), "pool_b": r(1), "pooled": torch.zeros(R // V, 256, dtype=torch.float16), "x_out": torch.zeros(R, 256)}
+    layers = []
+    for i in range(nl):
+        lay = {"w_qkv": r(768, 256, scale=1 / 16).half(), "b_qkv": r(768, scale=0.1), "w_proj": r(256, 256, scale=1 / 32).half(), "b_proj": r(256, scale=0.1),
+               "w_fc1": r(512, 256, scale=1 / 16).half(), "b_fc1": r(512, scale=0.1), "w_fc2": r(256, 512, scale=1 / 45).half(), "b_fc2": r(256, scale=0.1),
+               "shift_msa": r(256, scale=0.2), "scale_msa": r(256, scale=0.2), "shift_mlp": r(256, scale=0.2), "scale_mlp": r(256, scale=0.2)}
+        layers.append(lay)
+    return t, layers
+
+
+@pytest.mark.parametrize("R,V,nl", [(384, 8, 1), (384, 8, 3), (160, 8, 3), (1024, 16, 3), (512, 4, 2), (128 * 150 + 64, 8, 3), (256, 1, 1)])
+def test_gridattn_dit_kernel(nat, dbl, R, V, nl):
+    """mvd_gridattn_dit_f16 (pre_layer_b + DiT blocks + view pooling in one kernel) against the per-op emulation: ragged last tile,
+    several tiles per CTA (150 tiles + a tail on 148 SMs), V = 1 / 4 / 8 / 16"""
+    t, layers = _dit_inputs(R, V, nl)
+    cpu_l, gpu_l = [dict(l) for l in layers], [{k: v.cuda() for k, v in l.items()} for l in layers]
+    cpu, gpu = {k: v.clone() for k, v in t.items()}, {k: v.cuda() for k, v in t.items()}
+    args = lambda d, ls: (d["tokens"], 736, d["w_pre"], d["b_pre"], ls, d["pool_w"], d["pool_b"], d["pooled"], R, V, 1e-6)
+    dbl.gridattn_dit(*args(cpu, cpu_l), x_out=cpu["x_out"])(None)
+    nat.gridattn_dit(*args(gpu, gpu_l), x_out=gpu["x_out"])(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for name, tol in (("x_out", 3e-3), ("pooled", 3e-3)):
+        a, b = gpu[name].float().cpu(), cpu[name].float()
+        assert torch.isfinite(a).all(), name
+        assert float((a - b).norm() / b.norm()) < tol, (name, float((a - b).norm() / b.norm()), float((a - b).abs().max()))
+
+
+def test_dit_fold_gates(nat, dbl):
+    W1, W2 = rnd(256, 256, dtype=torch.float16), rnd(256, 512, dtype=torch.float16, seed=1)
+    t = {"w1": W1, "w2": W2, "g1": rnd(256, seed=2), "g2": rnd(256, seed=3), "b1": rnd(256, seed=4), "b2": rnd(256, seed=5),
+         "o1": torch.zeros_like(W1), "o2": torch.zeros_like(W2), "c1": torch.zeros(256), "c2": torch.zeros(256)}
+    cpu, gpu = {k: v.clone() for k, v in t.items()}, {k: v.cuda() for k, v in t.items()}
+    jobs = lambda d: [(d["w1"], d["g1"], d["b1"], d["o1"], d["c1"]), (d["w2"], d["g2"], d["b2"], d["o2"], d["c2"])]
+    dbl.dit_fold_gates(jobs(cpu))(None)
+    nat.dit_fold_gates(jobs(gpu))(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for k in ("o1", "o2", "c1", "c2"):
+        assert torch.equal(gpu[k].cpu(), cpu[k]), k
