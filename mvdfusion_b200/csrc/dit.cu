@@ -123,6 +123,8 @@ __device__ unsigned int g_dit_trace[160 * 64];
 #define DT_TR(i) do { } while (0)
 #endif
 
+// VT = views per point (compile time: the attention loops unroll exactly, without predicated tails)
+template <int VT>
 __global__ void __launch_bounds__(DT_THREADS, 1) dit_kernel(const __grid_constant__ DitMaps maps, const DitParams p) {
   extern __shared__ __align__(1024) uint8_t dt_smem[];
   uint8_t* smem = dt_smem;
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dit_kernel(const __grid_constan
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t xaddr = tmem_x + lane_base + wg * 128;   // this thread's half of its X row
     const uint32_t sw = static_cast<uint32_t>(r & 7);
-    const int V = p.V;
+    constexpr int V = VT;
     const int j0 = r & ~(V - 1);                             // first row of this row's point
     uint32_t n_xready = 0, n_xdone = 0, n_awrite = 0;
     uint32_t qacc_uses = 0;
@@ -339,71 +341,79 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dit_kernel(const __grid_constan
     facc.init(); fbuf.init();
     pdl_wait();
 
-    auto exchange = [&](float v) -> float {  // sum of the two warpgroups' partials of row r (identical bits in both)
-      xch[wg * 128 + r] = v;
+    auto exchange2 = [&](float a, float b2, float& ra, float& rb) {  // sums of the two warpgroups' partials of row r (identical bits in both)
+      float2* x2 = reinterpret_cast<float2*>(xch);
+      x2[wg * 128 + r] = make_float2(a, b2);
       named_bar_sync(3, 256);
-      const float o = xch[(wg ^ 1) * 128 + r];
+      const float2 o = x2[(wg ^ 1) * 128 + r];
       named_bar_sync(3, 256);
-      return v + o;
+      ra = a + o.x;
+      rb = b2 + o.y;
     };
     // LayerNorm(no affine) * (1 + scale) + shift of the resident row -> fp16 A tile.  `pend`: a bias still owed to X (the folded
-    // proj / fc2 bias of the product that was just accumulated) is added and written back first.
-    auto ln_modulate = [&](const float* pend, const float* shift, const float* scale) {
-      float s = 0.f;
+    // proj / fc2 bias of the product that was just accumulated) is added and written back first.  Two passes over this thread's
+    // 128 columns, 64 at a time (a TMEM read costs a few hundred cycles of latency that two warps per scheduler cannot hide):
+    // sum and sum of squares (fp32 over 256 values of O(1) magnitude), then the normalisation.  have_stats: the caller already
+    // holds this thread's partial sums (the pre_layer GELU pass).
+    auto ln_modulate = [&](const float* pend, const float* shift, const float* scale, bool have_stats, float s, float q2) {
+      if (!have_stats) {
+        s = 0.f;
+        q2 = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld32(xaddr + c * 32, v);
-        tmem_ld_wait();
-        if (pend != nullptr) {
-          const float4* pb = reinterpret_cast<const float4*>(pend + wg * 128 + c * 32);
+        for (int c = 0; c < 2; ++c) {
+          float v[64];
+          tmem_ld32(xaddr + c * 64, v);
+          tmem_ld32(xaddr + c * 64 + 32, v + 32);
+          tmem_ld_wait();
+          if (pend != nullptr) {
+            const float4* pb = reinterpret_cast<const float4*>(pend + wg * 128 + c * 64);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b4 = __ldg(pb + i);
-            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            for (int i = 0; i < 16; ++i) {
+              const float4 b4 = __ldg(pb + i);
+              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            }
+            tmem_st32(xaddr + c * 64, v);
+            tmem_st32(xaddr + c * 64 + 32, v + 32);
           }
-          tmem_st32(xaddr + c * 32, v);
-        }
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s += v[i];
-      }
-      if (pend != nullptr) tmem_st_wait();
-      const float mean = exchange(s) * (1.f / DT_C);
-      float q2 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld32(xaddr + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float d = v[i] - mean;
-          q2 = fmaf(d, d, q2);
+          for (int i = 0; i < 64; i += 2) {
+            s0 += v[i]; s1 += v[i + 1];
+            q0 = fmaf(v[i], v[i], q0); q1 = fmaf(v[i + 1], v[i + 1], q1);
+          }
+          s += s0 + s1;
+          q2 += q0 + q1;
         }
+        if (pend != nullptr) tmem_st_wait();
       }
-      const float rstd = rsqrtf(exchange(q2) * (1.f / DT_C) + p.eps);
+      float ts, tq;
+      exchange2(s, q2, ts, tq);
+      const float mean = ts * (1.f / DT_C);
+      const float rstd = rsqrtf(fmaxf(tq * (1.f / DT_C) - mean * mean, 0.f) + p.eps);
       // the A tile may be rewritten once the products that read the previous one have retired
       if (n_awrite > 0) mbar_wait(&bars[BAR_A_FREE], (n_awrite - 1) & 1);
       ++n_awrite;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld32(xaddr + c * 32, v);
+      for (int c = 0; c < 2; ++c) {
+        float v[64];
+        tmem_ld32(xaddr + c * 64, v);
+        tmem_ld32(xaddr + c * 64 + 32, v + 32);
         tmem_ld_wait();
-        const float4* sc4 = reinterpret_cast<const float4*>(scale + wg * 128 + c * 32);
-        const float4* sh4 = reinterpret_cast<const float4*>(shift + wg * 128 + c * 32);
+        const float4* sc4 = reinterpret_cast<const float4*>(scale + wg * 128 + c * 64);
+        const float4* sh4 = reinterpret_cast<const float4*>(shift + wg * 128 + c * 64);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 16; ++i) {
           const float4 a = __ldg(sc4 + i), b = __ldg(sh4 + i);
           v[4 * i] = fmaf((v[4 * i] - mean) * rstd, 1.f + a.x, b.x);
           v[4 * i + 1] = fmaf((v[4 * i + 1] - mean) * rstd, 1.f + a.y, b.y);
           v[4 * i + 2] = fmaf((v[4 * i + 2] - mean) * rstd, 1.f + a.z, b.z);
           v[4 * i + 3] = fmaf((v[4 * i + 3] - mean) * rstd, 1.f + a.w, b.w);
         }
-        const uint32_t rowaddr = sA + (wg * 2 + (c >> 1)) * DT_SLOT + r * 128;
+        // 64 columns = k-block (2 wg + c) of the A tile
+        const uint32_t rowaddr = sA + (wg * 2 + c) * DT_SLOT + r * 128;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          dt_sts16(rowaddr + (((static_cast<uint32_t>((c & 1) * 4 + i)) ^ sw) << 4), dt_pack(v[8 * i], v[8 * i + 1]), dt_pack(v[8 * i + 2], v[8 * i + 3]),
+        for (int i = 0; i < 8; ++i)
+          dt_sts16(rowaddr + ((static_cast<uint32_t>(i) ^ sw) << 4), dt_pack(v[8 * i], v[8 * i + 1]), dt_pack(v[8 * i + 2], v[8 * i + 3]),
                    dt_pack(v[8 * i + 4], v[8 * i + 5]), dt_pack(v[8 * i + 6], v[8 * i + 7]));
       }
       tc_fence_before();
@@ -420,19 +430,28 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dit_kernel(const __grid_constan
       ++n_xready;
       tc_fence_after();
       DT_TR(1);
+      float pre_s = 0.f, pre_q = 0.f;  // norm1 statistics of block 0 come out of this pass
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld32(xaddr + c * 32, v);
+      for (int c = 0; c < 2; ++c) {
+        float v[64];
+        tmem_ld32(xaddr + c * 64, v);
+        tmem_ld32(xaddr + c * 64 + 32, v + 32);
         tmem_ld_wait();
-        const float4* pb = reinterpret_cast<const float4*>(p.b_pre + wg * 128 + c * 32);
+        const float4* pb = reinterpret_cast<const float4*>(p.b_pre + wg * 128 + c * 64);
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 16; ++i) {
           const float4 b4 = __ldg(pb + i);
           v[4 * i] = gelu_erf(v[4 * i] + b4.x); v[4 * i + 1] = gelu_erf(v[4 * i + 1] + b4.y);
           v[4 * i + 2] = gelu_erf(v[4 * i + 2] + b4.z); v[4 * i + 3] = gelu_erf(v[4 * i + 3] + b4.w);
+          s0 += v[4 * i] + v[4 * i + 2]; s1 += v[4 * i + 1] + v[4 * i + 3];
+          q0 = fmaf(v[4 * i], v[4 * i], q0); q1 = fmaf(v[4 * i + 1], v[4 * i + 1], q1);
+          q0 = fmaf(v[4 * i + 2], v[4 * i + 2], q0); q1 = fmaf(v[4 * i + 3], v[4 * i + 3], q1);
         }
-        tmem_st32(xaddr + c * 32, v);
+        pre_s += s0 + s1;
+        pre_q += q0 + q1;
+        tmem_st32(xaddr + c * 64, v);
+        tmem_st32(xaddr + c * 64 + 32, v + 32);
       }
       tmem_st_wait();
       DT_TR(2);
@@ -447,7 +466,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dit_kernel(const __grid_constan
           tc_fence_after();
         }
         DT_TR(4 + 8 * l);
-        ln_modulate(l > 0 ? p.L[l - 1].b_fc2 : nullptr, P.shift_msa, P.scale_msa);
+        ln_modulate(l > 0 ? p.L[l - 1].b_fc2 : nullptr, P.shift_msa, P.scale_msa, l == 0, pre_s, pre_q);
         DT_TR(5 + 8 * l);
 
         // ---- attention over the V views of each point, heads wg, wg + 2, wg + 4, wg + 6
@@ -497,62 +516,66 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dit_kernel(const __grid_constan
           }
           named_bar_sync(1 + wg, 128);
           const float scale_log2 = rsqrtf(static_cast<float>(DT_HD)) * 1.4426950408889634f;
-          float sc[DT_MAXV];
+          // scores of this row against the V rows of its point (k rows are broadcast reads); four independent accumulators
+          float sc[VT];
           float m = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < DT_MAXV; ++j) {
-            if (j < V) {
+          for (int j = 0; j < VT; ++j) {
+            {
               const int jr = j0 + j;
               const uint32_t ja = kv + jr * 128;
               const uint32_t jsw = static_cast<uint32_t>((jr >> 3) & 7);
-              float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 u = dt_lds16(ja + ((static_cast<uint32_t>(i) ^ jsw) << 4));
-                dt_dot2(s0, qh[i * 4], u.x);
-                dt_dot2(s1, qh[i * 4 + 1], u.y);
-                dt_dot2(s0, qh[i * 4 + 2], u.z);
-                dt_dot2(s1, qh[i * 4 + 3], u.w);
-              }
-              sc[j] = (s0 + s1) * scale_log2;
+              float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+              const uint4 u0 = dt_lds16(ja + ((0u ^ jsw) << 4)), u1 = dt_lds16(ja + ((1u ^ jsw) << 4));
+              const uint4 u2 = dt_lds16(ja + ((2u ^ jsw) << 4)), u3 = dt_lds16(ja + ((3u ^ jsw) << 4));
+              dt_dot2(a0, qh[0], u0.x); dt_dot2(a1, qh[1], u0.y); dt_dot2(a2, qh[2], u0.z); dt_dot2(a3, qh[3], u0.w);
+              dt_dot2(a0, qh[4], u1.x); dt_dot2(a1, qh[5], u1.y); dt_dot2(a2, qh[6], u1.z); dt_dot2(a3, qh[7], u1.w);
+              dt_dot2(a0, qh[8], u2.x); dt_dot2(a1, qh[9], u2.y); dt_dot2(a2, qh[10], u2.z); dt_dot2(a3, qh[11], u2.w);
+              dt_dot2(a0, qh[12], u3.x); dt_dot2(a1, qh[13], u3.y); dt_dot2(a2, qh[14], u3.z); dt_dot2(a3, qh[15], u3.w);
+              sc[j] = ((a0 + a1) + (a2 + a3)) * scale_log2;
               m = fmaxf(m, sc[j]);
-            } else {
-              sc[j] = -INFINITY;
             }
           }
+          // P = exp2(s - m) rounded to fp16 (as the tensor-core attention does; l sums the rounded values), kept packed in sc[]
           float lsum = 0.f;
-          float o[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = 0.f;
-#pragma unroll
-          for (int j = 0; j < DT_MAXV; ++j) {
-            if (j < V) {
+          for (int j = 0; j < VT; ++j) {
+            {
               float pe;
               asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(sc[j] - m));
               const __half ph = __float2half_rn(pe);
               lsum += __half2float(ph);
-              const uint32_t p2 = static_cast<uint32_t>(__half_as_ushort(ph)) * 0x10001u;
-              const int jr = j0 + j;
-              const uint32_t ja = kv + jr * 128;
-              const uint32_t jsw = static_cast<uint32_t>((jr >> 3) & 7);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 u = dt_lds16(ja + ((static_cast<uint32_t>(4 + i) ^ jsw) << 4));
-                dt_axpy2(o[i * 8 + 0], o[i * 8 + 1], p2, u.x);
-                dt_axpy2(o[i * 8 + 2], o[i * 8 + 3], p2, u.y);
-                dt_axpy2(o[i * 8 + 4], o[i * 8 + 5], p2, u.z);
-                dt_axpy2(o[i * 8 + 6], o[i * 8 + 7], p2, u.w);
-              }
+              sc[j] = __uint_as_float(static_cast<uint32_t>(__half_as_ushort(ph)) * 0x10001u);
             }
           }
           const float inv = 1.f / lsum;
-          // head h -> columns [32h, 32h + 32) of the B tile (k-block h / 2, chunks 4 (h & 1) .. + 3)
+          // P V in two halves of 16 dims (16 accumulators live at a time); head h -> columns [32h, 32h + 32) of the B tile
+          // (k-block h / 2, chunks 4 (h & 1) .. + 3)
           const uint32_t brow = sB + (h >> 1) * DT_SLOT + r * 128;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            dt_sts16(brow + ((static_cast<uint32_t>((h & 1) * 4 + i) ^ sw) << 4), dt_pack(o[8 * i] * inv, o[8 * i + 1] * inv),
-                     dt_pack(o[8 * i + 2] * inv, o[8 * i + 3] * inv), dt_pack(o[8 * i + 4] * inv, o[8 * i + 5] * inv),
-                     dt_pack(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
+          for (int half = 0; half < 2; ++half) {
+            float o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < VT; ++j) {
+              {
+                const int jr = j0 + j;
+                const uint32_t ja = kv + jr * 128;
+                const uint32_t jsw = static_cast<uint32_t>((jr >> 3) & 7);
+                const uint32_t p2 = __float_as_uint(sc[j]);
+                const uint4 u0 = dt_lds16(ja + ((static_cast<uint32_t>(4 + 2 * half) ^ jsw) << 4));
+                const uint4 u1 = dt_lds16(ja + ((static_cast<uint32_t>(5 + 2 * half) ^ jsw) << 4));
+                dt_axpy2(o[0], o[1], p2, u0.x); dt_axpy2(o[2], o[3], p2, u0.y); dt_axpy2(o[4], o[5], p2, u0.z); dt_axpy2(o[6], o[7], p2, u0.w);
+                dt_axpy2(o[8], o[9], p2, u1.x); dt_axpy2(o[10], o[11], p2, u1.y); dt_axpy2(o[12], o[13], p2, u1.z); dt_axpy2(o[14], o[15], p2, u1.w);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              dt_sts16(brow + ((static_cast<uint32_t>((h & 1) * 4 + 2 * half + i) ^ sw) << 4), dt_pack(o[8 * i] * inv, o[8 * i + 1] * inv),
+                       dt_pack(o[8 * i + 2] * inv, o[8 * i + 3] * inv), dt_pack(o[8 * i + 4] * inv, o[8 * i + 5] * inv),
+                       dt_pack(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
+          }
           named_bar_sync(1 + wg, 128);  // every row of the warpgroup is done with this head's k | v
         }
         fence_async_smem();
@@ -564,7 +587,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dit_kernel(const __grid_constan
         ++n_xdone;
         tc_fence_after();
         DT_TR(7 + 8 * l);
-        ln_modulate(P.b_proj, P.shift_mlp, P.scale_mlp);
+        ln_modulate(P.b_proj, P.shift_mlp, P.scale_mlp, false, 0.f, 0.f);
         DT_TR(8 + 8 * l);
 
         // ---- fc1 quarter -> GELU -> fp16 F buffer (this warpgroup writes k-block `wg` of the quarter)
@@ -610,28 +633,31 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dit_kernel(const __grid_constan
       const float* pend = p.L[L - 1].b_fc2;
       float dot = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld32(xaddr + c * 32, v);
+      for (int c = 0; c < 2; ++c) {
+        float v[64];
+        tmem_ld32(xaddr + c * 64, v);
+        tmem_ld32(xaddr + c * 64 + 32, v + 32);
         tmem_ld_wait();
-        const float4* pb = reinterpret_cast<const float4*>(pend + wg * 128 + c * 32);
-        const float4* pw = reinterpret_cast<const float4*>(p.pool_w + wg * 128 + c * 32);
+        const float4* pb = reinterpret_cast<const float4*>(pend + wg * 128 + c * 64);
+        const float4* pw = reinterpret_cast<const float4*>(p.pool_w + wg * 128 + c * 64);
+        float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 16; ++i) {
           const float4 b4 = __ldg(pb + i), w4 = __ldg(pw + i);
           v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-          dot = fmaf(v[4 * i], w4.x, dot); dot = fmaf(v[4 * i + 1], w4.y, dot);
-          dot = fmaf(v[4 * i + 2], w4.z, dot); dot = fmaf(v[4 * i + 3], w4.w, dot);
+          d0 = fmaf(v[4 * i], w4.x, d0); d1 = fmaf(v[4 * i + 1], w4.y, d1);
+          d0 = fmaf(v[4 * i + 2], w4.z, d0); d1 = fmaf(v[4 * i + 3], w4.w, d1);
         }
-        tmem_st32(xaddr + c * 32, v);
+        dot += d0 + d1;
         if (p.x_out != nullptr && row_g < p.R) {
-          float4* dst = reinterpret_cast<float4*>(p.x_out + row_g * DT_C + wg * 128 + c * 32);
+          float4* dst = reinterpret_cast<float4*>(p.x_out + row_g * DT_C + wg * 128 + c * 64);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int i = 0; i < 16; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
       }
-      tmem_st_wait();
-      const float score = exchange(dot) + __ldg(p.pool_b);
+      float score, unused;
+      exchange2(dot, 0.f, score, unused);
+      score += __ldg(p.pool_b);
       // softmax over the V rows of the point: the V lanes are consecutive lanes of this warp
       float mx = score;
       for (int o = 1; o < V; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -644,8 +670,13 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dit_kernel(const __grid_constan
         float v[32];
         tmem_ld32(xaddr + c * 32, v);
         tmem_ld_wait();
+        const float4* pb = reinterpret_cast<const float4*>(pend + wg * 128 + c * 32);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= wt;
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = __ldg(pb + i);
+          v[4 * i] = (v[4 * i] + b4.x) * wt; v[4 * i + 1] = (v[4 * i + 1] + b4.y) * wt;
+          v[4 * i + 2] = (v[4 * i + 2] + b4.z) * wt; v[4 * i + 3] = (v[4 * i + 3] + b4.w) * wt;
+        }
         for (int o = 1; o < V; o <<= 1) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
@@ -772,15 +803,19 @@ extern "C" int mvd_gridattn_dit_f16(const mvd_dit_args* a, void* stream_) {
     if (rc == MVD_OK) rc = make_tmap_2d(&maps.fc2[l], s.w_fc2, DT_HID, DT_C, DT_HID, 64, 128);
   }
   if (rc != MVD_OK) return rc;
+  typedef void (*DitFn)(const DitMaps, const DitParams);
+  static const DitFn fns[5] = {dit_kernel<1>, dit_kernel<2>, dit_kernel<4>, dit_kernel<8>, dit_kernel<16>};
   static bool configured = false;
   if (!configured) {
-    MVD_CUDA_CHECK(cudaFuncSetAttribute(dit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
+    for (DitFn f : fns) MVD_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
     configured = true;
   }
+  int vi = 0;
+  while ((1 << vi) < a->V) ++vi;
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-  MVD_CUDA_CHECK(launch_kernel(dit_kernel, dim3(grid), dim3(DT_THREADS), DT_SMEM, stream, 1, maps, p));
+  MVD_CUDA_CHECK(launch_kernel(fns[vi], dim3(grid), dim3(DT_THREADS), DT_SMEM, stream, 1, maps, p));
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

@@ -32,6 +32,8 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     print(f"kernel: {e0.elapsed_time(e1) * 1e3:.1f} us for {R} rows ({R // 128} tiles)")
+    if not hasattr(lib, "mvd_debug_dit_trace"):
+        return
     buf = np.zeros(160 * 64, dtype=np.uint32)
     lib.mvd_debug_dit_trace.argtypes = [ctypes.c_void_p]
     lib.mvd_debug_dit_trace(ctypes.c_void_p(buf.ctypes.data))
