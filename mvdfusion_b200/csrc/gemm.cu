@@ -124,6 +124,9 @@ struct GemmKParams {
   // TMA epilogue (template TMAE): per-warpgroup chunk slots [32 fp32 columns x 128 rows | fp16 copy | fp16 lo] that the residual
   // is loaded into and the finished chunk is stored from, both by TMA
   int spw, slot_bytes, slot_h16, slot_lo;  // slots per warpgroup (1 / 2), bytes per slot, offsets of the fp16 tiles inside a slot
+  // wide pair tiles (256 < BN <= 320, TMAE only): the tile is two N = BN / 2 MMAs into ONE accumulator of BN columns (single-buffered);
+  // each CTA of the pair stages rows [rank q, rank q + q) and [BN / 2 + rank q, ...) of the W tile, q = BN / 4
+  int wide;
   FastDiv fd_split, fd_tiles_m, fd_tiles_x, fd_tiles_y, fd_seq, fd_inner, fd_dhead, fd_rpg;
 };
 
@@ -291,7 +294,10 @@ __device__ __forceinline__ Unit decode_unit(const GemmKParams& p, int u, int pai
 // finish that chunk, one or two chunks ahead; thread = row reads its accumulator row from TMEM, adds bias / row bias / residual
 // (from the slot), applies the activation, writes the result back into the slot (and optional fp16 copies next to it), and one
 // thread per warpgroup issues the TMA store of the chunk.  TMA clips the M and N tails.
-template <int ACT, int OUT, int RES, int SPLIT, bool VEC, bool PAIR, int NWG, bool TMAE>
+// WIDE: 320-column pair tile (two N = BN / 2 MMAs, one accumulator).  A template parameter rather than a run-time flag: the producer and
+// issuer loops are single threads whose instruction stream is latency-critical — a run-time branch in them (and the code it adds
+// to the instruction cache the epilogue warps share) cost the ordinary deep-K convolutions 6 %.
+template <int ACT, int OUT, int RES, int SPLIT, bool VEC, bool PAIR, int NWG, bool TMAE, bool WIDE = false>
 __global__ void __launch_bounds__(128 + 128 * NWG, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                    const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmO16, const __grid_constant__ CUtensorMap tmO16lo,
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
   constexpr int STG_PER_WG = NWG == 2 ? 2 : 1;
   uint8_t* out_stg = smem + p.stages * stage_bytes;                                      // NWG x STG_PER_WG x STG_BYTES, or the TMAE slots
   float* bias_smem = reinterpret_cast<float*>(out_stg + (TMAE ? NWG * p.spw * p.slot_bytes : NWG * STG_PER_WG * STG_BYTES));   // NWG x 256 floats (GEGLU tile bias)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_smem + NWG * (TMAE ? 512 : 256));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_smem + NWG * (TMAE ? 640 : 256));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + MAX_STAGES;
   uint64_t* acc_full = bars + 2 * MAX_STAGES;
@@ -381,7 +387,12 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
         KbIter ki;
         ki.seek(p, t0.kb0);
         for (int i = 0; i < npre; ++i) {
-          tma_prefetch_l2_2d(&tmB, ki.w_col, t0.n_tile * p.BN + (PAIR ? pair_rank * b_rows : 0));
+          if (PAIR && WIDE) {
+            tma_prefetch_l2_2d(&tmB, ki.w_col, t0.n_tile * p.BN + pair_rank * (p.BN / 4));
+            tma_prefetch_l2_2d(&tmB, ki.w_col, t0.n_tile * p.BN + p.BN / 2 + pair_rank * (p.BN / 4));
+          } else {
+            tma_prefetch_l2_2d(&tmB, ki.w_col, t0.n_tile * p.BN + (PAIR ? pair_rank * b_rows : 0));
+          }
           ki.next(p);
         }
       }
@@ -389,6 +400,12 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
       MVD_TR(2);
       int s = 0;          // ring slot and its phase, advanced without divisions
       uint32_t ph = 0;
+      // W rows this CTA of a pair stages: [rank b_rows, +b_rows), or for a wide tile two boxes of BN / 4 rows (loop constants: the
+      // per-k-block path of this thread is latency-critical — deep-K convolutions lost 7 % to one more branch with divisions here)
+      constexpr bool w_wide = PAIR && WIDE;
+      const int w_row0 = PAIR ? (w_wide ? pair_rank * (p.BN >> 2) : pair_rank * b_rows) : 0;
+      const int w_row1 = (p.BN >> 1) + pair_rank * (p.BN >> 2);
+      const int w_half_bytes = (p.BN >> 2) * 128;
       for (int j = 0; j < n_local; ++j) {
         const Unit t = decode_unit(p, first + j * ustride, pair_rank);
         KbIter ki;
@@ -403,7 +420,8 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
             const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
             if (p.a_mode == MVD_A_CONV3X3) tma_load_4d_pair(sa, &tmA, lbar, ki.a_col, t.x0 * p.cstride + ki.kx - p.cpad, t.y0 * p.cstride + ki.ky - p.cpad, t.img0);
             else tma_load_2d_pair(sa, &tmA, lbar, ki.a_col, t.m_tile * BM);
-            tma_load_2d_pair(sb, &tmB, lbar, ki.w_col, t.n_tile * p.BN + pair_rank * b_rows);
+            tma_load_2d_pair(sb, &tmB, lbar, ki.w_col, t.n_tile * p.BN + w_row0);
+            if (w_wide) tma_load_2d_pair(sb + w_half_bytes, &tmB, lbar, ki.w_col, t.n_tile * p.BN + w_row1);
           } else {
             if (p.a_mode == MVD_A_CONV3X3) tma_load_4d(sa, &tmA, &full_bar[s], ki.a_col, t.x0 * p.cstride + ki.kx - p.cpad, t.y0 * p.cstride + ki.ky - p.cpad, t.img0);
             else tma_load_2d(sa, &tmA, &full_bar[s], ki.a_col, t.m_tile * BM);
@@ -417,31 +435,49 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
   } else if (warp == 1) {
     // ------------------------------------------------------------ UMMA issuer
     if (lane == 0 && leader) {
-      const uint32_t idesc = umma_idesc_f16(PAIR ? 2 * BM : BM, p.BN);
+      constexpr bool wide = PAIR && WIDE;
+      const uint32_t idesc = umma_idesc_f16(PAIR ? 2 * BM : BM, wide ? p.BN / 2 : p.BN);
+      const uint32_t wide_b = static_cast<uint32_t>((p.BN / 4) * 128) >> 4;  // descriptor offset of the W rows of the second MMA
       int s = 0;
       uint32_t ph = 0;
+      const uint64_t da0 = umma_desc_sw128(smem_u32(smem));
+      const uint64_t stage16 = static_cast<uint64_t>(stage_bytes >> 4);
+      uint64_t da_cur = da0;
       for (int j = 0; j < n_local; ++j) {
         const Unit t = decode_unit(p, first + j * ustride, pair_rank);
         const int buf = j & 1;
         mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);
+        // one accumulator only: the epilogue of the previous unit must have read it (it alternates the two barrier pairs all the same)
+        if (wide && j >= 1) mbar_wait(&acc_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * p.acc_stride;
+        // The issue loop is one thread whose instruction latencies add up against ~450 clk of MMA per k-block: operand descriptors advance
+        // by adds (a stage is stage_bytes >> 4 in the descriptor's address field), the accumulate flag is a register
+        uint32_t accum = 0u;
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           if (j == 0 && kb == t.kb0) MVD_TR(4);
-          const uint32_t sa = smem_u32(smem + s * stage_bytes);
-          const uint64_t da = umma_desc_sw128(sa);
-          const uint64_t db = umma_desc_sw128(sa + A_BYTES);
+          const uint64_t da = da_cur, db = da_cur + (A_BYTES >> 4);
+          if (PAIR && wide) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 fp16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
-            if (PAIR) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
-            else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, k == 0 ? accum : 1u);
+              umma_f16_pair(d_tmem + p.BN / 2, da + 2 * k, db + 2 * k + wide_b, idesc, k == 0 ? accum : 1u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 fp16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
+              if (PAIR) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, k == 0 ? accum : 1u);
+              else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, k == 0 ? accum : 1u);
+            }
           }
+          accum = 1u;
           if (PAIR) tc_commit_pair(&empty_bar[s], 3);  // frees the slot in BOTH CTAs
           else tc_commit(&empty_bar[s]);
-          if (++s == p.stages) { s = 0; ph ^= 1; }
+          da_cur += stage16;
+          if (++s == p.stages) { s = 0; ph ^= 1; da_cur = da0; }
         }
         if (PAIR) tc_commit_pair(&acc_full[buf], 3);
         else tc_commit(&acc_full[buf]);
@@ -535,7 +571,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
     const uint32_t sw128 = static_cast<uint32_t>(et & 7), sw64 = static_cast<uint32_t>((et >> 1) & 3);
     const uint32_t row128 = et * 128, row64 = et * 64;
     const uint32_t f16_off = (f16out && !has_res) ? 0u : static_cast<uint32_t>(p.slot_h16);  // where the fp16 tile of a slot lives
-    float* sbias = bias_smem + wg * 512;   // [bias of the tile's BN columns | column scale]
+    float* sbias = bias_smem + wg * 640;   // [bias of the tile's BN (<= 320) columns | column scale]
     const bool use_sb = (p.bias != nullptr || p.colscale != nullptr) && out_mode != MVD_OUT_QKV_HEADS;
     int sb_tile = -1;
     if (use_sb && n_local > 0) {            // bias and gate vectors are parameters: they may be fetched before the grid dependency resolves
@@ -544,7 +580,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
       for (int kk = et; kk < p.BN; kk += WG_THREADS) {
         const bool in = nb + kk < p.N;
         if (p.bias != nullptr) sbias[kk] = in ? __ldg(p.bias + nb + kk) : 0.f;
-        if (p.colscale != nullptr) sbias[256 + kk] = in ? __ldg(p.colscale + nb + kk) : 1.f;
+        if (p.colscale != nullptr) sbias[320 + kk] = in ? __ldg(p.colscale + nb + kk) : 1.f;
       }
       sb_tile = t.n_tile;
       named_bar_sync(bar_id, WG_THREADS);
@@ -570,7 +606,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
         for (int kk = et; kk < p.BN; kk += WG_THREADS) {
           const bool in = nb + kk < p.N;
           if (p.bias != nullptr) sbias[kk] = in ? __ldg(p.bias + nb + kk) : 0.f;
-          if (p.colscale != nullptr) sbias[256 + kk] = in ? __ldg(p.colscale + nb + kk) : 1.f;
+          if (p.colscale != nullptr) sbias[320 + kk] = in ? __ldg(p.colscale + nb + kk) : 1.f;
         }
         sb_tile = t.n_tile;
         named_bar_sync(bar_id, WG_THREADS);
@@ -646,7 +682,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
             for (int i = 0; i < 32; ++i) v[i] = silu(v[i]);
           }
           if (p.colscale != nullptr) {
-            const uint32_t sv = smem_u32(sbias + 256 + c * 32);
+            const uint32_t sv = smem_u32(sbias + 320 + c * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 c4 = lds_v4(sv + i * 16);
@@ -1208,6 +1244,10 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   int bn = a->tile_n;
   if (bn == 0) bn = geglu ? 256 : pick_bn(a->N, tiles_mp, slots, pair);
   if (pair && (bn & 31) != 0) return set_error(MVD_EINVAL, "mvd_gemm_f16: tile_n must be a multiple of 32 here");
+  const bool wide = bn > 256;
+  if (wide && (!pair || bn > 320 || (bn & 63) != 0 || geglu || a->out_mode == MVD_OUT_QKV_HEADS))
+    return set_error(MVD_EINVAL, "mvd_gemm_f16: tile_n > 256 needs cta_pair = 2, tile_n in {320}, a plain F32 / F16 output");
+  p.wide = wide ? 1 : 0;
   if (geglu) {
     if ((bn & 63) != 0 || (a->N % bn) != 0) return set_error(MVD_EINVAL, "mvd_gemm_f16: GEGLU needs tile_n a multiple of 64 that divides N");
     if (a->colscale != nullptr || a->residual != nullptr || a->rowbias != nullptr || a->out_mode == MVD_OUT_QKV_HEADS)
@@ -1265,7 +1305,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     return set_error(MVD_EINVAL, "mvd_gemm_f16: bad a_mode");
   }
   {
-    int rc = make_tmap_2d(&tmB, a->Wt, /*cols=*/hilo ? 2 * a->K : a->K, /*rows=*/a->N, /*ld=*/a->ldw, BK, pair ? bn / 2 : bn);
+    int rc = make_tmap_2d(&tmB, a->Wt, /*cols=*/hilo ? 2 * a->K : a->K, /*rows=*/a->N, /*ld=*/a->ldw, BK, pair ? (wide ? bn / 4 : bn / 2) : bn);
     if (rc != MVD_OK) return rc;
   }
   p.hilo = hilo;
@@ -1342,11 +1382,12 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   const int has_res = a->residual != nullptr ? 1 : 0;
   const int is_split = split > 1 ? 1 : 0;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmKParams);
-  struct Spec { int key; int nwg; KernelFn one, two; };
+  struct Spec { int key; int nwg; KernelFn one, two, wide; };
 #define MVD_SPEC(ACT, OUT, RES, SPL, NWG) \
-  { (ACT) * 1000 + (OUT) * 100 + (RES) * 10 + (SPL), NWG, gemm_tc_kernel<ACT, OUT, RES, SPL, true, false, NWG, false>, gemm_tc_kernel<ACT, OUT, RES, SPL, true, true, NWG, false> }
+  { (ACT) * 1000 + (OUT) * 100 + (RES) * 10 + (SPL), NWG, gemm_tc_kernel<ACT, OUT, RES, SPL, true, false, NWG, false>, gemm_tc_kernel<ACT, OUT, RES, SPL, true, true, NWG, false>, nullptr }
 #define MVD_SPEC_TMAE(ACT, OUT, RES) \
-  { (ACT) * 1000 + (OUT) * 100 + (RES) * 10, 3, gemm_tc_kernel<ACT, OUT, RES, 0, true, false, 3, true>, gemm_tc_kernel<ACT, OUT, RES, 0, true, true, 3, true> }
+  { (ACT) * 1000 + (OUT) * 100 + (RES) * 10, 3, gemm_tc_kernel<ACT, OUT, RES, 0, true, false, 3, true>, gemm_tc_kernel<ACT, OUT, RES, 0, true, true, 3, true>, \
+    ((ACT) == MVD_ACT_NONE ? static_cast<KernelFn>(gemm_tc_kernel<MVD_ACT_NONE, OUT, RES, 0, true, true, 3, true, true>) : nullptr) }
   // three epilogue warpgroups where the epilogue fits 128 registers (ptxas -v: <= 110 with two warpgroups), two elsewhere
   static const Spec specs[] = {
       MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 0, 0, 3),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 0, 1, 2),  MVD_SPEC(MVD_ACT_NONE, MVD_OUT_F32, 1, 0, 3),
@@ -1368,7 +1409,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   };
 #undef MVD_SPEC
 #undef MVD_SPEC_TMAE
-  static const Spec generic = {-1, 2, gemm_tc_kernel<-1, -1, -1, -1, false, false, 2, false>, gemm_tc_kernel<-1, -1, -1, -1, false, true, 2, false>};
+  static const Spec generic = {-1, 2, gemm_tc_kernel<-1, -1, -1, -1, false, false, 2, false>, gemm_tc_kernel<-1, -1, -1, -1, false, true, 2, false>, nullptr};
   static const bool force_wg2 = getenv("MVD_GEMM_WG2") != nullptr;
   static const bool no_tmae = getenv("MVD_GEMM_NO_TMAE") != nullptr;
   const Spec* spec = &generic;
@@ -1385,7 +1426,8 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     // make the TMA engine write 128 separate 16-byte rows per box; 16384x960x320 went from 22.0 to 23.2 us.)
     // Deep-K GEMMs hide their epilogue behind the mainloop and lose 5-6 % with the TMA stores in flight (conv 16384x640x5760
     // 75.5 -> 80.7 us): they keep the thread-store epilogue.
-    const bool tma_ok = !is_split && a->out_mode != MVD_OUT_QKV_HEADS && p.kb_per_split <= 24 && al16(a->out) &&
+    // (a wide pair tile runs one tile per CTA pair with nothing to overlap: it takes the TMA epilogue whatever its K)
+    const bool tma_ok = !is_split && a->out_mode != MVD_OUT_QKV_HEADS && (p.kb_per_split <= 24 || wide) && al16(a->out) &&
                         ((static_cast<long long>(a->ldc) * (a->out_mode == MVD_OUT_F32 ? 4 : 2)) & 15) == 0 &&
                         (a->residual == nullptr || (al16(a->residual) && (a->ldr & 3) == 0)) &&
                         (a->out16 == nullptr || (al16(a->out16) && (a->ld16 & 7) == 0 && (p.out16_lo & 7) == 0));
@@ -1396,6 +1438,8 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
           tmae = true;
         }
   }
+  if (wide && (!tmae || spec->wide == nullptr))
+    return set_error(MVD_EINVAL, "mvd_gemm_f16: tile_n > 256 is only available with the TMA epilogue (unsplit, aligned F32 / F16 output, no activation)");
   static bool configured = false;
   if (!configured) {
     for (const Spec& sp : specs) {
@@ -1405,6 +1449,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     for (const Spec& sp : specs_tmae) {
       MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.one, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
       MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.two, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      if (sp.wide != nullptr) MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     }
     for (const Spec& sp : specs_wg2) {
       MVD_CUDA_CHECK(cudaFuncSetAttribute(sp.one, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -1436,7 +1481,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     // what the tile waits for — short K — or where they are cheap (fp16 chunks); deeper K wants the shared memory as ring stages
     // (measured: 65536x256x736 GELU at 2 ring stages 49 us, at 3 stages 41 us)
     p.spw = (p.kb_per_split <= 10 || p.slot_bytes <= 8192) ? 2 : 1;
-    if (p.spw == 2 && (232448 - 1024 - (6 * p.slot_bytes + nwg * 2048 + 512)) / stage_bytes < 3) p.spw = 1;
+    if (p.spw == 2 && (232448 - 1024 - (6 * p.slot_bytes + nwg * 2560 + 512)) / stage_bytes < 3) p.spw = 1;
     stg_bytes_total = 3 * p.spw * p.slot_bytes;
     int rc = f16out ? make_tmap_2d_ex(&tmOut, a->out, 2, n_out, a->M, a->ldc, 32, BM, 64)
                     : make_tmap_2d_ex(&tmOut, a->out, 4, n_out, a->M, a->ldc, 32, BM, 128);
@@ -1454,18 +1499,18 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
       }
     }
   }
-  const int fixed = stg_bytes_total + nwg * (tmae ? 2048 : 1024) + 512;
+  const int fixed = stg_bytes_total + nwg * (tmae ? 2560 : 1024) + 512;
   int stages = (232448 - 1024 - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return set_error(MVD_EINVAL, "mvd_gemm_f16: tile does not fit in shared memory");
   p.stages = stages;
   const int dyn = stages * stage_bytes + fixed + 1024;
-  p.acc_stride = bn <= 128 ? 128 : 256;
-  p.tmem_cols = 2 * p.acc_stride;
+  p.acc_stride = wide ? 0 : (bn <= 128 ? 128 : 256);
+  p.tmem_cols = wide ? 512 : 2 * p.acc_stride;
 
   if (pair) {
     const int grid = 2 * (p.num_units < slots ? p.num_units : slots);
-    MVD_CUDA_CHECK(launch_kernel(spec->two, dim3(grid), dim3(threads), dyn, stream, 2, tmA, tmB, tmOut, tmRes, tmO16, tmO16lo, p));
+    MVD_CUDA_CHECK(launch_kernel(wide ? spec->wide : spec->two, dim3(grid), dim3(threads), dyn, stream, 2, tmA, tmB, tmOut, tmRes, tmO16, tmO16lo, p));
   } else {
     const int grid = p.num_units < sms ? p.num_units : sms;
     MVD_CUDA_CHECK(launch_kernel(spec->one, dim3(grid), dim3(threads), dyn, stream, 1, tmA, tmB, tmOut, tmRes, tmO16, tmO16lo, p));

@@ -49,6 +49,7 @@ struct Case {
   int tile_n = 0;
   int heads = 0, dhead = 0, dpad = 0, seq = 0;
   int lda_pad = 0;
+  int cta_pair = 0;
 };
 
 static int g_fail = 0;
@@ -138,7 +139,7 @@ static void run(const Case& c) {
   g.rowbias = drb; g.rows_per_group = c.rows_per_group;
   g.residual = dres; g.ldr = N;
   g.act = c.act; g.out_mode = c.out_mode;
-  g.split_k = c.split_k; g.tile_n = c.tile_n;
+  g.split_k = c.split_k; g.tile_n = c.tile_n; g.cta_pair = c.cta_pair;
   static void* ws = nullptr;            // split-K workspace: zero-filled once, semaphores reset themselves
   const size_t ws_bytes = 32u << 20;
   if (ws == nullptr) {
@@ -247,7 +248,7 @@ static void run(const Case& c) {
 }
 
 // ---- timing mode: `gemm_check bench` — representative shapes of one denoising step (N=8 views x 2 CFG branches)
-struct BCase { const char* name; int M, N, K; int conv_img, conv_hw, conv_c; bool res; int act; int out_mode; int split; int tile_n; };
+struct BCase { const char* name; int M, N, K; int conv_img, conv_hw, conv_c; bool res; int act; int out_mode; int split; int tile_n; int pair = 0; };
 static double bench(const BCase& c, int iters, bool quiet = false) {
   const int ldw = (c.K + 7) / 8 * 8;
   const size_t wbytes = static_cast<size_t>(c.N) * ldw * 2;
@@ -265,7 +266,7 @@ static double bench(const BCase& c, int iters, bool quiet = false) {
   if (!ws) { CK(cudaMalloc(&ws, ws_bytes)); CK(cudaMemset(ws, 0, ws_bytes)); }
   mvd_gemm_args g; memset(&g, 0, sizeof(g));
   g.M = c.M; g.N = c.N; g.K = c.K; g.A = dA; g.lda = c.conv_img ? 0 : c.K; g.ldw = ldw; g.bias = db; g.residual = dres; g.ldr = c.N;
-  g.act = c.act; g.out_mode = c.out_mode; g.out = dout; g.ldc = No; g.split_k = c.split; g.tile_n = c.tile_n;
+  g.act = c.act; g.out_mode = c.out_mode; g.out = dout; g.ldc = No; g.split_k = c.split; g.tile_n = c.tile_n; g.cta_pair = c.pair;
   g.splitk_ws = ws; g.splitk_ws_bytes = ws_bytes; g.rows_per_group = 1;
   if (c.conv_img) { g.a_mode = MVD_A_CONV3X3; g.n_img = c.conv_img; g.H = g.W = c.conv_hw; g.C = c.conv_c; }
   if (c.out_mode == MVD_OUT_QKV_HEADS) {
@@ -333,6 +334,12 @@ static int bench_main(int only) {
       {"conv 16x32x32x640->640 (up)", 16384, 640, 5760, 16, 32, 640, false, 0, MVD_OUT_F32, 0, 0},
       {"conv 16x32x32x960->320", 16384, 320, 8640, 16, 32, 960, false, 0, MVD_OUT_F32, 0, 0},
       {"lin 16384x320x768 f16", 16384, 320, 768, 0, 0, 0, false, 0, MVD_OUT_F16, 0, 0},
+      // N = 320 outputs as one wave of 320-column pair tiles vs the heuristic's choice (the lines above)
+      {"wide320 lin 16384x320x320 f32 res", 16384, 320, 320, 0, 0, 0, true, 0, MVD_OUT_F32, 1, 320, 2},
+      {"wide320 lin 16384x320x1280 f32 res", 16384, 320, 1280, 0, 0, 0, true, 0, MVD_OUT_F32, 1, 320, 2},
+      {"wide320 conv 16x32x32x320->320 res", 16384, 320, 2880, 16, 32, 320, true, 0, MVD_OUT_F32, 1, 320, 2},
+      {"wide320 conv 16x32x32x960->320", 16384, 320, 8640, 16, 32, 960, false, 0, MVD_OUT_F32, 1, 320, 2},
+      {"wide320 lin 16384x320x768 f16", 16384, 320, 768, 0, 0, 0, false, 0, MVD_OUT_F16, 1, 320, 2},
   };
   const int n = sizeof(cs) / sizeof(cs[0]);
   for (int i = 0; i < n; ++i)
@@ -419,6 +426,12 @@ int main(int argc, char** argv) {
   { Case c; c.name = "qkv heads 16x1024 d40 persistent"; c.M = 16384; c.N = 3 * 8 * 40; c.K = 320; c.out_mode = MVD_OUT_QKV_HEADS; c.heads = 8; c.dhead = 40; c.dpad = 64; c.seq = 1024; cases.push_back(c); }
   { Case c; c.name = "qkv heads d8 (generic scatter)"; c.M = 256; c.N = 3 * 8 * 8; c.K = 64; c.out_mode = MVD_OUT_QKV_HEADS; c.heads = 8; c.dhead = 8; c.dpad = 64; c.seq = 64; cases.push_back(c); }
   { Case c; c.name = "persistent res 40000x160x256"; c.M = 40000; c.N = 160; c.K = 256; c.bias = c.residual = true; cases.push_back(c); }
+  // 320-column pair tiles (two N = 160 MMAs into one single-buffered accumulator, TMA epilogue)
+  { Case c; c.name = "wide320 512x320x1280 bias+res"; c.M = 512; c.N = 320; c.K = 1280; c.tile_n = 320; c.cta_pair = 2; c.bias = c.residual = true; cases.push_back(c); }
+  { Case c; c.name = "wide320 odd tiles 384x320x320 f16"; c.M = 384; c.N = 320; c.K = 320; c.tile_n = 320; c.cta_pair = 2; c.bias = true; c.out_mode = MVD_OUT_F16; cases.push_back(c); }
+  { Case c; c.name = "wide320 40960x320x320 res (3 units per pair)"; c.M = 40960; c.N = 320; c.K = 320; c.tile_n = 320; c.cta_pair = 2; c.bias = c.residual = true; cases.push_back(c); }
+  { Case c; c.name = "wide320 conv 16x32x32x320->320 res"; c.a_mode = MVD_A_CONV3X3; c.n_img = 16; c.H = c.W = 32; c.C = 320; c.N = 320; c.K = 9 * 320; c.M = 16384; c.tile_n = 320; c.cta_pair = 2; c.bias = c.residual = true; cases.push_back(c); }
+  { Case c; c.name = "wide320 N tail 300x300x640"; c.M = 300; c.N = 300; c.K = 640; c.tile_n = 320; c.cta_pair = 2; c.bias = true; cases.push_back(c); }
   for (size_t i = 0; i < cases.size(); ++i)
     if (only < 0 || only == static_cast<int>(i)) run(cases[i]);
   printf("%s (%d failing)\n", g_fail ? "GEMM CHECK FAILED" : "GEMM CHECK PASSED", g_fail);

@@ -101,6 +101,8 @@ def main():
                         tn = 0
                     for sk in ((1, 2, 3, 4, 6, 8, 12, 16) if can_split else (1,)):
                         cands.append((tn, sk, pair))
+            if not geglu and N % 320 == 0 and tiles_m >= 2:
+                cands.append((320, 1, 2))  # one 320-column pair tile per two m-tiles (two N = 160 MMAs, single accumulator, TMA epilogue)
             cands = sorted(set(cands))
             best, best_c = base, None
             for tn, sk, pair in cands:
