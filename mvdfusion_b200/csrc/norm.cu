@@ -22,8 +22,9 @@ namespace mvd {
 //             one memory latency per CTA; several small CTAs per SM overlap each other's phases).
 //   per-thread fp32 partial sums -> smem [row][span] -> one warp per group sums them in fp64 -> cluster barrier ->
 //   every CTA adds up its peers' group sums through distributed shared memory -> normalise, gamma / beta (+SiLU), fp16.
-template <int MAXP>
-__global__ void __launch_bounds__(256, MAXP == 16 ? 2 : (MAXP == 4 ? 4 : 3))  // register budget sized to the pixels a thread keeps: occupancy is what hides the latency here
+// NT = threads per CTA: 256, or 320 for the one geometry where 256 leaves a second partial wave (16 x 32^2 x 320: see the host code)
+template <int MAXP, int NT = 256>
+__global__ void __launch_bounds__(NT, MAXP == 16 ? 2 : (MAXP == 4 ? 4 : 3))  // register budget sized to the pixels a thread keeps: occupancy is what hides the latency here
     gn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ x2, int C1, const float* __restrict__ gamma,
                       const float* __restrict__ beta, __half* __restrict__ y, int hw, int C, int cpg, int gpc, int rows, int csplit,
                       float eps, int apply_silu, int ldy, int lo_off) {
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(256, MAXP == 16 ? 2 : (MAXP == 4 ? 4 : 3))  //
   {
     // warp w sums group w, w + 8, ...: lane = row, cpg contiguous fp32 partials each, accumulated in double
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int g = warp; g < gpc; g += 8) {
+    for (int g = warp; g < gpc; g += NT / 32) {
       double a = 0.0, b = 0.0;
       for (int rr = lane; rr < rows; rr += 32) {
         const float* ps = part_s + rr * span + g * cpg;
@@ -466,11 +467,32 @@ static int groupnorm_launch(const float* x, const float* x2, int C1, const float
       best_pp = (hw + best_rows * os - 1) / (best_rows * os);
     }
   }
+  // One more candidate: when the chosen geometry does not fit the machine in one wave (16 x 32^2 x 320: 512 CTAs of 256 threads
+  // on 3 x 148 slots = a full wave and a 15 % one, 14.8 us), 320-thread CTAs that keep 16 pixels per thread halve the cluster split:
+  // 256 CTAs on 2 x 148 slots, one wave.  MVD_GN_NT320=0 keeps the 256-thread form (A/B measurements).
+  bool nt320 = false;
+  {
+    static const bool off = getenv("MVD_GN_NT320") != nullptr && atoi(getenv("MVD_GN_NT320")) == 0;
+    const long long ctas = static_cast<long long>(32 / best_gpc) * best_split * n_img;
+    const int span4 = best_gpc * cpg / 4;
+    if (!off && getenv("MVD_GN_GEOMETRY") == nullptr && best_pp <= 16 && best_split >= 2 && ctas > 3 * 148 && (320 % span4) == 0) {
+      const int rows320 = 320 / span4, split2 = best_split / 2;
+      const int pp2 = (hw + rows320 * split2 - 1) / (rows320 * split2);
+      if (rows320 <= hw && pp2 <= 16 && static_cast<long long>(32 / best_gpc) * split2 * n_img <= 2 * 148) {
+        nt320 = true;
+        best_split = split2;
+        best_rows = rows320;
+        best_pp = pp2;
+      }
+    }
+  }
   const int gpc = best_gpc, csplit = best_split, rows = best_rows, span = gpc * cpg;
   const size_t sm = 64 * sizeof(double) + 64 * sizeof(float) + static_cast<size_t>(2) * rows * span * sizeof(float);
   const dim3 grid((32 / gpc) * csplit, n_img);
   __half* yh = static_cast<__half*>(y);
-  if (best_pp <= 4)
+  if (nt320)
+    MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<16, 320>, grid, dim3(320), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu, ldy, lo_off));
+  else if (best_pp <= 4)
     MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<4>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu, ldy, lo_off));
   else if (best_pp <= 8)
     MVD_CUDA_CHECK(launch_kernel(gn_cluster_kernel<8>, grid, dim3(256), sm, stream, csplit, x, x2, C1, gamma, beta, yh, hw, C, cpg, gpc, rows, csplit, eps, apply_silu, ldy, lo_off));
