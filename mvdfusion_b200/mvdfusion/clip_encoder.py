@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 from .. import engine as E
 from .. import runtime
-from ..runtime import WeightCache, current_stream
+from ..runtime import PlanCache, WeightCache, current_stream
 
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
@@ -69,7 +69,7 @@ class FrozenCLIPImageEmbedder(nn.Module):
         self.register_buffer("mean", torch.tensor(CLIP_MEAN), persistent=False)
         self.register_buffer("std", torch.tensor(CLIP_STD), persistent=False)
         self._cache = WeightCache()
-        self._plans = {}
+        self._plans = PlanCache(2)
         if isinstance(model, str) and model not in self.ARCH and model:
             self._load(model)
 

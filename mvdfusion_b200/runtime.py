@@ -39,6 +39,29 @@ def params_signature(module):
     return hash(tuple(sig))
 
 
+class PlanCache(dict):
+    """A handful of compiled plans, least recently used first out.  A plan owns its arena, operand buffers, split-K workspace and a
+    captured CUDA graph: calling sample() / apply_model() with ever-changing view counts or flags must not grow GPU memory without
+    bound.  MVD_PLAN_CACHE in the environment sets the size (default 6)."""
+
+    def __init__(self, capacity=None):
+        super().__init__()
+        import os
+        self.capacity = capacity or int(os.environ.get("MVD_PLAN_CACHE", "6"))
+
+    def __getitem__(self, key):
+        value = super().pop(key)       # re-insert: dicts keep insertion order, so the first key is the least recently used one
+        super().__setitem__(key, value)
+        return value
+
+    def __setitem__(self, key, value):
+        if key in self:
+            super().pop(key)
+        super().__setitem__(key, value)
+        while len(self) > self.capacity:
+            super().pop(next(iter(self)))
+
+
 class WeightCache:
     """PackedWeights of a module, rebuilt when the module's parameters change (packed weights are a derived cache)."""
 
@@ -52,7 +75,7 @@ class WeightCache:
             self.state = {k: v.detach() for k, v in module.state_dict().items()}
             self.sig = sig
             self.packs = {}
-            self.plans = {}
+            self.plans = PlanCache()
         return self.state
 
     def pack(self, module, ops, prefix=""):

@@ -218,3 +218,17 @@ def test_sample_and_forward_through_the_facade_baseline_config0(ops_double):
     torch.manual_seed(7)
     loss = m(batch, cfg)
     assert loss.dim() == 0 and torch.isfinite(loss) and 0.1 < float(loss) < 10.0
+
+
+def test_plan_cache_is_bounded_lru():
+    """plans own arenas / graphs; the cache keeps the most recently used few"""
+    from mvdfusion_b200.runtime import PlanCache
+    c = PlanCache(3)
+    for k in "abc":
+        c[k] = k.upper()
+    assert c["a"] == "A"          # touch: 'b' is now the oldest
+    c["d"] = "D"
+    assert list(c) == ["c", "a", "d"] and "b" not in c
+    c["c"] = "C2"
+    c["e"] = "E"
+    assert list(c) == ["d", "c", "e"] and c["c"] == "C2"
