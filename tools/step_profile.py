@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--cfg", type=float, default=2.5)
     ap.add_argument("--out", default="")
+    ap.add_argument("--world", type=int, default=1, help="profile rank 0's step of a scene view-sharded over this many GPUs (no collective; one GPU suffices)")
     a = ap.parse_args()
     from common import build_model, synthetic
     from mvdfusion_b200.mvdfusion.cameras import PerspectiveCameras
@@ -31,12 +32,45 @@ def main():
     de, dn = synthetic.step_noises(n, D, S, 4, seed=1)
     rows = torch.stack([model.ddim.step_row(49 - i, a.cfg) for i in range(4)])
     cam = lambda c: PerspectiveCameras(c["R"], c["T"], c["f"], c["p"], device=dev)
+    if a.world > 1:
+        model.view_group = (None, 0, a.world)  # rank 0's shard: the shapes are the same on every rank
     plan = model.step_plan(n, S, D, use_cfg=a.cfg != 1.0)
     stream = current_stream(dev)
     model.bind_scene(plan, cam(sc["cams"]), sc["input_latents"].to(dev), cam(sc["in_cams"]), sc["clip_v_embed"].to(dev), stream)
     plan.x.copy_(sc["x_T"].reshape(n, 5, S * S))
     plan.set_tables(rows, de, dn)
-    calls = plan._loop_prog.calls
+    calls = [c for c in plan._loop_prog.calls if getattr(c, "name", "") != "all_gather_latents"]
+    # the whole step from its CUDA graph (what the sampler replays), without the collective
+    if a.world == 1:
+        for _ in range(3):
+            plan.loop_step(stream)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        plan.counter.zero_()
+        g0.record()
+        for _ in range(4):
+            plan.loop_step(stream)
+        g1.record()
+        torch.cuda.synchronize()
+        print(f"graph replay: {g0.elapsed_time(g1) / 4:.3f} ms per step")
+    else:
+        gr = torch.cuda.CUDAGraph()
+        for c in calls:
+            c(stream)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(gr):
+            for c in calls:
+                c(torch.cuda.current_stream().cuda_stream)
+        gr.replay()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        plan.counter.zero_()
+        g0.record()
+        for _ in range(4):
+            gr.replay()
+        g1.record()
+        torch.cuda.synchronize()
+        print(f"graph replay of rank 0's {len(calls)} kernels (1/{a.world} of the views, no all-gather): {g0.elapsed_time(g1) / 4:.3f} ms per step")
     acc = [0.0] * len(calls)
     for rep in range(a.reps + 1):
         plan.counter.zero_()
