@@ -96,7 +96,8 @@ def main():
             for pair in (1, 2):
                 if pair == 2 and tiles_m < 2:
                     continue
-                for tn in ((g0.tile_n,) if geglu else (64, 96, 128, 160, 192, 224, 256)):
+                # narrow tiles for the one / two m-tile layers: more CTAs stream the weight matrix in parallel
+                for tn in ((g0.tile_n,) if geglu else ((32, 48) if (tiles_m <= 2 and pair == 1) else ()) + (64, 96, 128, 160, 192, 224, 256)):
                     if not geglu and N <= 64:
                         tn = 0
                     for sk in ((1, 2, 3, 4, 6, 8, 12, 16) if can_split else (1,)):
