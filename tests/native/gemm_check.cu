@@ -426,6 +426,10 @@ int main(int argc, char** argv) {
   { Case c; c.name = "qkv heads 16x1024 d40 persistent"; c.M = 16384; c.N = 3 * 8 * 40; c.K = 320; c.out_mode = MVD_OUT_QKV_HEADS; c.heads = 8; c.dhead = 40; c.dpad = 64; c.seq = 1024; cases.push_back(c); }
   { Case c; c.name = "qkv heads d8 (generic scatter)"; c.M = 256; c.N = 3 * 8 * 8; c.K = 64; c.out_mode = MVD_OUT_QKV_HEADS; c.heads = 8; c.dhead = 8; c.dpad = 64; c.seq = 64; cases.push_back(c); }
   { Case c; c.name = "persistent res 40000x160x256"; c.M = 40000; c.N = 160; c.K = 256; c.bias = c.residual = true; cases.push_back(c); }
+  // narrow tiles for the one / two m-tile layers (tools/tune_gemm.py picks them for 256x1280x1280)
+  { Case c; c.name = "bn32 256x1280x1280 bias+res"; c.M = 256; c.N = 1280; c.K = 1280; c.tile_n = 32; c.bias = c.residual = true; cases.push_back(c); }
+  { Case c; c.name = "bn48 200x1280x768 f16"; c.M = 200; c.N = 1280; c.K = 768; c.tile_n = 48; c.bias = true; c.out_mode = MVD_OUT_F16; cases.push_back(c); }
+  { Case c; c.name = "bn32 split4 256x1280x2560"; c.M = 256; c.N = 1280; c.K = 2560; c.tile_n = 32; c.split_k = 3; c.bias = true; cases.push_back(c); }
   // 320-column pair tiles (two N = 160 MMAs into one single-buffered accumulator, TMA epilogue)
   { Case c; c.name = "wide320 512x320x1280 bias+res"; c.M = 512; c.N = 320; c.K = 1280; c.tile_n = 320; c.cta_pair = 2; c.bias = c.residual = true; cases.push_back(c); }
   { Case c; c.name = "wide320 odd tiles 384x320x320 f16"; c.M = 384; c.N = 320; c.K = 320; c.tile_n = 320; c.cta_pair = 2; c.bias = true; c.out_mode = MVD_OUT_F16; cases.push_back(c); }
