@@ -112,6 +112,20 @@ typedef struct mvd_gemm_args {
    * non-zero, is the pixel pitch of A in elements (the image may be a column window of a wider buffer). */
   int32_t conv_stride;
   int32_t conv_no_pad_lo;
+  /* ABI 13: nn.LayerNorm between two GEMMs without a pass of its own (external/sd1/ldm/modules/attention.py:211-213,220-222 norm1 / norm3
+   * in front of to_q|to_k|to_v and GEGLU.proj; mvdfusion/attention.py:35-37,52,64).
+   *   producer side — ln_stats_out: fp32 pairs [N/32][M][2]; for every output row and every 32-column chunk the epilogue stores
+   *     (sum, sum of squares) of the values it writes (F32 output through the TMA epilogue: unsplit, K <= 1536, N % 32 == 0; the call
+   *     fails otherwise).  Together with out16 (the raw rows as fp16) this is everything the consumer needs.
+   *   consumer side — ln_stats (what a producer wrote: [K/32][M][2], K % 32 == 0), ln_colsum, ln_eps: A holds the RAW rows x (fp16),
+   *     Wt the gamma-scaled weights W' = W diag(gamma), ln_colsum[n] = sum_k W'[n, k] (of the fp16-rounded W'), bias already contains
+   *     W beta.  Per row: mean = sum / K, rstd = rsqrt(sumsq / K - mean^2 + ln_eps), and the accumulator becomes
+   *         acc' = rstd[m] * (acc - mean[m] * ln_colsum[n])  ==  (LayerNorm_noaffine(x) W'^T)[m, n]
+   *     before bias / activation.  ROWMAJOR A, QKV_HEADS or GEGLU output, unsplit. */
+  float* ln_stats_out;
+  const float* ln_stats;
+  const float* ln_colsum;
+  float ln_eps;
 } mvd_gemm_args;
 
 int mvd_gemm_f16(const mvd_gemm_args* args, void* stream);

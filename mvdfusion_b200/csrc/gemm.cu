@@ -127,6 +127,13 @@ struct GemmKParams {
   // wide pair tiles (256 < BN <= 320, TMAE only): the tile is two N = BN / 2 MMAs into ONE accumulator of BN columns (single-buffered);
   // each CTA of the pair stages rows [rank q, rank q + q) and [BN / 2 + rank q, ...) of the W tile, q = BN / 4
   int wide;
+  // LayerNorm between two GEMMs (mvd_b200.h, ABI 13).  Producer: (sum, sum of squares) per row and 32-column chunk -> ln_stats_out
+  // [N/32][M] float2.  Consumer: ln_stats [ln_parts][M] float2 of its A rows, ln_colsum[n] = column sums of the gamma-scaled weights.
+  float2* ln_stats_out;
+  const float2* ln_stats;
+  const float* ln_colsum;
+  float ln_eps, ln_inv_k;
+  int ln_parts;
   FastDiv fd_split, fd_tiles_m, fd_tiles_x, fd_tiles_y, fd_seq, fd_inner, fd_dhead, fd_rpg;
 };
 
@@ -323,6 +330,11 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
   uint64_t* res_empty = res_full + 6;     //       the slot's last store has read it: free for the next residual / result
   uint64_t* out_ready = res_empty + 6;    //       the warpgroup has written the finished chunk into the slot
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_ready + 6);
+  // LayerNorm fold (p.ln_stats): warp 2 reduces the chunk statistics of the NEXT unit's rows to {rstd, -mean * rstd} one unit ahead
+  uint64_t* st_full = bars + 48;          // [2] the helper has written rowstat[b] (32 lanes arrive)
+  uint64_t* st_empty = bars + 50;         // [2] every epilogue thread has read rowstat[b]
+  float2* rowstat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 512);  // [2][128], behind the 512-byte barrier block
+  float* lnvec = reinterpret_cast<float*>(rowstat + 256);  // [2][column sums of the unit's BN (<= 256) weight rows | their bias] (QKV form only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -350,6 +362,12 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], PAIR ? 2 * EPI_THREADS : EPI_THREADS);  // pair: the leader collects both CTAs' epilogues
     }
+    if (p.ln_stats != nullptr) {
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&st_full[b], 32);
+        mbar_init(&st_empty[b], EPI_THREADS / 32);
+      }
+    }
     if (TMAE) {
       tma_prefetch_desc(&tmOut);
       if (has_res) tma_prefetch_desc(&tmRes);
@@ -375,6 +393,67 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
   const int first = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
   const int ustride = PAIR ? (gridDim.x >> 1) : gridDim.x;
   const int n_local = (first < p.num_units) ? (p.num_units - first + ustride - 1) / ustride : 0;
+
+  // ---- LayerNorm fold, statistics helper (one warp; lane owns tile rows lane, lane + 32, lane + 64, lane + 96): sums the per-chunk
+  //      (sum, sum of squares) the producing GEMM left for the unit's rows — `ln_parts` coalesced 8-byte loads per row, 16 in flight per
+  //      lane — and leaves {rstd, -mean * rstd} in rowstat[b] one unit ahead of the epilogue, so that no epilogue thread waits on L2.
+  auto ln_helper = [&](const bool stage_vec) {
+    pdl_wait();  // the statistics come from the kernel before us
+    int k = 0;
+    for (int j = 0; j < n_local; ++j) {
+      const Unit t = decode_unit(p, first + j * ustride, pair_rank);
+      if (PAIR && t.m_tile >= p.tiles_m_real) continue;
+      const int b = k & 1;
+      if (k >= 2) mbar_wait(&st_empty[b], ((k >> 1) - 1) & 1);
+      if (stage_vec) {  // the unit's column sums and bias: loaded here, one unit ahead, so that no epilogue thread waits on a global load
+        const int nb = t.n_tile * p.BN;
+        float cvv[8], bvv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int kk = lane + 32 * i;
+          const bool in = kk < p.BN && nb + kk < p.N;
+          cvv[i] = in ? __ldg(p.ln_colsum + nb + kk) : 0.f;
+          bvv[i] = (in && p.bias != nullptr) ? __ldg(p.bias + nb + kk) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          lnvec[b * 512 + lane + 32 * i] = cvv[i];
+          lnvec[b * 512 + 256 + lane + 32 * i] = bvv[i];
+        }
+      }
+      float sm[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+      // 32 loads in flight per lane (64 registers; this warp has nothing else to hold): two L2 round trips for a 320-wide row, three for
+      // 640, five for 1280, all of them one unit ahead of the epilogue
+      constexpr int LNB = 8;
+      for (int c = 0; c < p.ln_parts; c += LNB) {
+        float2 v[LNB][4];
+#pragma unroll
+        for (int cc = 0; cc < LNB; ++cc) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int row = t.grow0 + lane + 32 * r;
+            v[cc][r] = (c + cc < p.ln_parts && row < p.M) ? __ldcg(p.ln_stats + static_cast<size_t>(c + cc) * p.M + row) : make_float2(0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int cc = 0; cc < LNB; ++cc) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            sm[r] += v[cc][r].x;
+            sq[r] += v[cc][r].y;
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float mu = sm[r] * p.ln_inv_k;
+        const float rs = rsqrtf(fmaxf(sq[r] * p.ln_inv_k - mu * mu, 0.f) + p.ln_eps);
+        rowstat[b * 128 + lane + 32 * r] = make_float2(rs, -mu * rs);
+      }
+      mbar_arrive(&st_full[b]);
+      ++k;
+    }
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -508,6 +587,8 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
         }
         gbase += valid;
       }
+    } else if (!has_res && act == MVD_ACT_GEGLU && p.ln_stats != nullptr) {
+      ln_helper(false);  // (a GEGLU GEMM has no residual to load: the warp is free; its vectors ride in the bias staging)
     }
   } else if (TMAE && warp == 3) {
     // ------------------------------------------------------------ TMAE: finished chunks -> global memory (TMA stores), slots handed back
@@ -572,20 +653,40 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
     const uint32_t row128 = et * 128, row64 = et * 64;
     const uint32_t f16_off = (f16out && !has_res) ? 0u : static_cast<uint32_t>(p.slot_h16);  // where the fp16 tile of a slot lives
     float* sbias = bias_smem + wg * 640;   // [bias of the tile's BN (<= 320) columns | column scale]
-    const bool use_sb = (p.bias != nullptr || p.colscale != nullptr) && out_mode != MVD_OUT_QKV_HEADS;
+    const bool ln_in = geglu && p.ln_stats != nullptr;  // LayerNorm folded into this GEMM: its column sums ride in the column-scale half
+    const bool use_sb = (p.bias != nullptr || p.colscale != nullptr || ln_in) && out_mode != MVD_OUT_QKV_HEADS;
     int sb_tile = -1;
+    // the tile's bias / gate (or LayerNorm column-sum) columns -> shared vector; every load is issued before the first store, so a
+    // restaged tile costs ONE L2 round trip (load - store - load - store chains cost the folded GEGLU GEMM ~1 us per unit)
+    auto stage_vectors = [&](int n_tile) {
+      const int nb = n_tile * p.BN;
+      const float* second = ln_in ? p.ln_colsum : p.colscale;
+      float bv[3], cv[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int kk = et + i * WG_THREADS;
+        const bool in = kk < p.BN && nb + kk < p.N;
+        bv[i] = (p.bias != nullptr && in) ? __ldg(p.bias + nb + kk) : 0.f;
+        cv[i] = (second != nullptr && in) ? __ldg(second + nb + kk) : (ln_in ? 0.f : 1.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int kk = et + i * WG_THREADS;
+        if (kk < p.BN) {
+          if (p.bias != nullptr) sbias[kk] = bv[i];
+          if (second != nullptr) sbias[320 + kk] = cv[i];
+        }
+      }
+    };
     if (use_sb && n_local > 0) {            // bias and gate vectors are parameters: they may be fetched before the grid dependency resolves
       const Unit t = decode_unit(p, first, pair_rank);
-      const int nb = t.n_tile * p.BN;
-      for (int kk = et; kk < p.BN; kk += WG_THREADS) {
-        const bool in = nb + kk < p.N;
-        if (p.bias != nullptr) sbias[kk] = in ? __ldg(p.bias + nb + kk) : 0.f;
-        if (p.colscale != nullptr) sbias[320 + kk] = in ? __ldg(p.colscale + nb + kk) : 1.f;
-      }
+      stage_vectors(t.n_tile);
       sb_tile = t.n_tile;
       named_bar_sync(bar_id, WG_THREADS);
     }
     pdl_wait();
+    float ln_rs = 1.f, ln_nm = 0.f;  // rstd and -mean * rstd of this thread's row (ln_in)
+    int kln = 0;                     // units whose statistics have been consumed
     if (warp == 4 && lane == 0) MVD_TR(7);
     int gbase = 0;
     for (int j = 0; j < n_local; ++j) {
@@ -602,21 +703,26 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
       // global load in front of the first chunk costs ~0.8 us on the critical path of every short GEMM
       if (use_sb && t.n_tile != sb_tile) {
         named_bar_sync(bar_id, WG_THREADS);  // everybody is done with the previous unit's vector
-        const int nb = t.n_tile * p.BN;
-        for (int kk = et; kk < p.BN; kk += WG_THREADS) {
-          const bool in = nb + kk < p.N;
-          if (p.bias != nullptr) sbias[kk] = in ? __ldg(p.bias + nb + kk) : 0.f;
-          if (p.colscale != nullptr) sbias[320 + kk] = in ? __ldg(p.colscale + nb + kk) : 1.f;
-        }
+        stage_vectors(t.n_tile);
         sb_tile = t.n_tile;
         named_bar_sync(bar_id, WG_THREADS);
+      }
+      const int grow = t.grow0 + et;
+      if (ln_in) {  // {rstd, -mean * rstd} of this thread's row, reduced by warp 2 while the previous unit was being finished
+        const int b = kln & 1;
+        mbar_wait(&st_full[b], (kln >> 1) & 1);
+        const float2 rsn = rowstat[b * 128 + et];
+        ln_rs = rsn.x;
+        ln_nm = rsn.y;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&st_empty[b]);  // one arrival per warp: its 32 reads were issued before it (shared-memory accesses of a warp stay in order)
+        ++kln;
       }
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
       if (j == 0 && warp == 4 && lane == 0) MVD_TR(8);
       if (j == n_local - 1 && warp == 4 && lane == 0) MVD_TR(9);
       const uint32_t taddr = tmem_base + buf * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
-      const int grow = t.grow0 + et;
       int c0 = (wg - gbase) % NWG;
       if (c0 < 0) c0 += NWG;
       for (int c = c0; c < valid; c += NWG) {
@@ -633,7 +739,23 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
             tmem_ld16(taddr + c * 32 + hh * 16, v + hh * 16);
             tmem_ld16(taddr + p.BN / 2 + c * 32 + hh * 16, g);
             tmem_ld_wait();
-            if (p.bias != nullptr) {
+            if (ln_in) {  // LayerNorm(x) W'^T + b' from the raw-x product: rstd * acc + (-mean * rstd * colsum + b'), two FMAs per element
+              const uint32_t cv = smem_u32(sbias + 320 + c * 32 + hh * 16), cg = smem_u32(sbias + 320 + p.BN / 2 + c * 32 + hh * 16);
+              const uint32_t sv = smem_u32(sbias + c * 32 + hh * 16), sg = smem_u32(sbias + p.BN / 2 + c * 32 + hh * 16);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 a4 = lds_v4(cv + i * 16), g4 = lds_v4(cg + i * 16);
+                float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+                if (p.bias != nullptr) {
+                  ba = lds_v4(sv + i * 16);
+                  bg = lds_v4(sg + i * 16);
+                }
+                v[hh * 16 + 4 * i] = fmaf(ln_rs, v[hh * 16 + 4 * i], fmaf(ln_nm, a4.x, ba.x)); v[hh * 16 + 4 * i + 1] = fmaf(ln_rs, v[hh * 16 + 4 * i + 1], fmaf(ln_nm, a4.y, ba.y));
+                v[hh * 16 + 4 * i + 2] = fmaf(ln_rs, v[hh * 16 + 4 * i + 2], fmaf(ln_nm, a4.z, ba.z)); v[hh * 16 + 4 * i + 3] = fmaf(ln_rs, v[hh * 16 + 4 * i + 3], fmaf(ln_nm, a4.w, ba.w));
+                g[4 * i] = fmaf(ln_rs, g[4 * i], fmaf(ln_nm, g4.x, bg.x)); g[4 * i + 1] = fmaf(ln_rs, g[4 * i + 1], fmaf(ln_nm, g4.y, bg.y));
+                g[4 * i + 2] = fmaf(ln_rs, g[4 * i + 2], fmaf(ln_nm, g4.z, bg.z)); g[4 * i + 3] = fmaf(ln_rs, g[4 * i + 3], fmaf(ln_nm, g4.w, bg.w));
+              }
+            } else if (p.bias != nullptr) {
               const uint32_t sv = smem_u32(sbias + c * 32 + hh * 16), sg = smem_u32(sbias + p.BN / 2 + c * 32 + hh * 16);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -700,6 +822,15 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
         } else if (nth >= 1) {
           mbar_wait(&res_empty[wg * p.spw + sl], (nth - 1) & 1);  // the store that last used this slot has read it
         }
+        if (!f16out && p.ln_stats_out != nullptr) {  // what the LayerNorm behind this output needs: (sum, sum of squares) of the chunk
+          float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            s4[i & 3] += v[i];
+            q4[i & 3] = fmaf(v[i], v[i], q4[i & 3]);
+          }
+          if (grow < p.M) p.ln_stats_out[static_cast<size_t>(oc >> 5) * p.M + grow] = make_float2((s4[0] + s4[1]) + (s4[2] + s4[3]), (q4[0] + q4[1]) + (q4[2] + q4[3]));
+        }
         if (!f16out) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) sts_v4(slot + row128 + ((static_cast<uint32_t>(i) ^ sw128) << 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -731,6 +862,8 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
       gbase += valid;
     }
     if (lane == 0 && (warp & 3) == 0) MVD_TR(10);
+  } else if (!TMAE && warp == 2) {
+    if (out_mode == MVD_OUT_QKV_HEADS && p.ln_stats != nullptr) ln_helper(true);
   } else if (!TMAE && warp >= 4) {
     // ------------------------------------------------------------ epilogue: 2 warpgroups x 128 threads
     const int wg = (warp - 4) >> 2;
@@ -750,6 +883,10 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
     int n_staged = 0;  // staging buffer toggle
     pdl_wait();        // residual / split-K workspace reads and every output write come after the predecessor grid
     if (warp == 4 && lane == 0) MVD_TR(7);
+    // LayerNorm folded into this GEMM (QKV head scatter): rstd and -mean * rstd of this thread's tile row, set per unit below
+    const bool ln_in = out_mode == MVD_OUT_QKV_HEADS && p.ln_stats != nullptr;
+    float ln_rs = 1.f, ln_nm = 0.f;
+    int kln = 0, ln_b = 0;
 
     // ---- phase A of one chunk: TMEM -> registers -> (GEGLU) -> swizzled staging tile, or the direct QKV scatter
     auto phase_a = [&](const Unit& t, uint32_t taddr, int c, uint32_t stg) -> bool {
@@ -794,6 +931,15 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
       } else {
         tmem_ld32(taddr + c * 32, v);
         tmem_ld_wait();
+        if (ln_in) {  // LayerNorm(x) W'^T + b' from the raw-x product: rstd * acc + (-mean * rstd * colsum + b') (N % 32 == 0: whole chunks)
+          const uint32_t cv = smem_u32(lnvec + ln_b * 512 + c * 32), bv = cv + 256 * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 c4 = lds_v4(cv + i * 16), b4 = lds_v4(bv + i * 16);
+            v[4 * i] = fmaf(ln_rs, v[4 * i], fmaf(ln_nm, c4.x, b4.x)); v[4 * i + 1] = fmaf(ln_rs, v[4 * i + 1], fmaf(ln_nm, c4.y, b4.y));
+            v[4 * i + 2] = fmaf(ln_rs, v[4 * i + 2], fmaf(ln_nm, c4.z, b4.z)); v[4 * i + 3] = fmaf(ln_rs, v[4 * i + 3], fmaf(ln_nm, c4.w, b4.w));
+          }
+        }
       }
       if (out_mode == MVD_OUT_QKV_HEADS && (p.qkv_direct || oc >= 2 * inner)) {
         // v^T (keys contiguous) wants thread = row: leave straight from the registers
@@ -805,9 +951,15 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
           for (int i = 0; i < 32; i += 8) {
             const int n = oc + i;
             if (n >= p.N) continue;
-            if (p.bias != nullptr) {  // dhead % 8 == 0 and N = 3 * heads * dhead: eight whole columns exist
+            if (p.bias != nullptr && !ln_in) {  // dhead % 8 == 0 and N = 3 * heads * dhead: eight whole columns exist (ln_in: added above)
+              if (p.vec_bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + 1);
+                v[i] += b0.x; v[i + 1] += b0.y; v[i + 2] += b0.z; v[i + 3] += b0.w;
+                v[i + 4] += b1.x; v[i + 5] += b1.y; v[i + 6] += b1.z; v[i + 7] += b1.w;
+              } else {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[i + e] += __ldg(p.bias + n + e);
+                for (int e = 0; e < 8; ++e) v[i + e] += __ldg(p.bias + n + e);
+              }
             }
             int which, rem, h, jj;
             p.fd_inner.divmod(n, which, rem);
@@ -854,7 +1006,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
       }
       const int nvalid = VEC ? ((n_out - col) > 0 ? 4 : 0) : (n_out - col);  // <= 0: this thread's columns do not exist
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (!geglu && p.bias != nullptr && nvalid > 0) b4 = ldg4(p.bias + col, VEC || p.vec_bias != 0, nvalid);
+      if (!geglu && p.bias != nullptr && nvalid > 0 && !ln_in) b4 = ldg4(p.bias + col, VEC || p.vec_bias != 0, nvalid);
       if (p.colscale != nullptr && nvalid > 0) cs4 = ldg4(p.colscale + col, VEC || p.vec_colscale != 0, nvalid);
       // QKV (q / k part): per-thread head coordinates are fixed for the chunk
       int qk_which = 0, qk_h = 0, qk_jj = 0;
@@ -1022,6 +1174,15 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
         named_bar_sync(bar_id, WG_THREADS);
       }
 
+      if (ln_in) {  // {rstd, -mean * rstd} of this thread's row, reduced by warp 2 while the previous unit was being finished
+        const int b = kln & 1;
+        mbar_wait(&st_full[b], (kln >> 1) & 1);
+        const float2 rsn = rowstat[b * 128 + et];
+        ln_b = b;
+        ln_rs = rsn.x;
+        ln_nm = rsn.y;
+        ++kln;  // (rowstat[b] / lnvec[b] are handed back after this unit's last chunk: phase A reads the vectors)
+      }
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
       if (j == 0 && warp == 4 && lane == 0) MVD_TR(8);
@@ -1085,6 +1246,10 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
         tc_fence_before();
         if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[buf]), 0));
         else mbar_arrive(&acc_empty[buf]);
+      }
+      if (ln_in) {  // one arrival per warp: its reads of rowstat[b] / lnvec[b] were issued before it (a warp's shared-memory accesses stay in order)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&st_empty[ln_b]);
       }
 
       if (is_split) {
@@ -1211,6 +1376,28 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     if (a->out_mode != MVD_OUT_F32 || a->act == MVD_ACT_GEGLU) return set_error(MVD_EINVAL, "mvd_gemm_f16: out16 accompanies an F32 output only");
     if (a->ld16 < a->N) return set_error(MVD_EINVAL, "mvd_gemm_f16: ld16 is smaller than N");
     p.vec_out16 = (reinterpret_cast<uintptr_t>(a->out16) & 7) == 0 && (a->ld16 & 3) == 0;
+  }
+
+  p.ln_stats_out = reinterpret_cast<float2*>(a->ln_stats_out);
+  p.ln_stats = reinterpret_cast<const float2*>(a->ln_stats);
+  p.ln_colsum = a->ln_colsum;
+  p.ln_eps = a->ln_eps;
+  p.ln_inv_k = 1.0f / static_cast<float>(a->K);
+  p.ln_parts = a->K / 32;
+  if (a->ln_stats_out != nullptr) {
+    if (a->out_mode != MVD_OUT_F32 || a->act == MVD_ACT_GEGLU || (a->N & 31) != 0 || (reinterpret_cast<uintptr_t>(a->ln_stats_out) & 7) != 0)
+      return set_error(MVD_EINVAL, "mvd_gemm_f16: ln_stats_out accompanies an F32 output with N a multiple of 32 (8-byte aligned buffer)");
+    if (a->split_k > 1) return set_error(MVD_EINVAL, "mvd_gemm_f16: ln_stats_out excludes split_k");
+  }
+  if (a->ln_stats != nullptr) {
+    if (a->ln_colsum == nullptr || !(a->ln_eps > 0.f)) return set_error(MVD_EINVAL, "mvd_gemm_f16: ln_stats needs ln_colsum and a positive ln_eps");
+    if (a->a_mode != MVD_A_ROWMAJOR || hilo || (a->K & 31) != 0 || (a->N & 31) != 0 ||
+        !(a->out_mode == MVD_OUT_QKV_HEADS || (a->act == MVD_ACT_GEGLU && a->out_mode == MVD_OUT_F16)))
+      return set_error(MVD_EINVAL, "mvd_gemm_f16: ln_stats needs a row-major A, K and N multiples of 32 and a QKV_HEADS or GEGLU output");
+    if ((reinterpret_cast<uintptr_t>(a->ln_stats) & 7) != 0 || (reinterpret_cast<uintptr_t>(a->ln_colsum) & 15) != 0)
+      return set_error(MVD_EALIGN, "mvd_gemm_f16: ln_stats / ln_colsum must be 8 / 16-byte aligned");
+    if (a->out_mode == MVD_OUT_QKV_HEADS && ((a->heads * a->dhead) & 31) != 0)
+      return set_error(MVD_EINVAL, "mvd_gemm_f16: ln_stats with QKV_HEADS needs heads * dhead to be a multiple of 32");
   }
 
   const bool geglu = a->act == MVD_ACT_GEGLU;
@@ -1438,6 +1625,12 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
           tmae = true;
         }
   }
+  if (a->ln_stats_out != nullptr && !tmae)
+    return set_error(MVD_EINVAL, "mvd_gemm_f16: ln_stats_out is only available with the TMA epilogue (unsplit, K <= 1536, aligned F32 output)");
+  if (a->ln_stats != nullptr && geglu && !tmae)
+    return set_error(MVD_EINVAL, "mvd_gemm_f16: ln_stats with GEGLU is only available with the TMA epilogue (K <= 1536, aligned F16 output)");
+  if (a->ln_stats != nullptr && !geglu && (spec == &generic || split > 1))
+    return set_error(MVD_EINVAL, "mvd_gemm_f16: ln_stats with QKV_HEADS needs aligned, unsplit operands");
   if (wide && (!tmae || spec->wide == nullptr))
     return set_error(MVD_EINVAL, "mvd_gemm_f16: tile_n > 256 is only available with the TMA epilogue (unsplit, aligned F32 / F16 output, no activation)");
   static bool configured = false;
@@ -1499,7 +1692,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
       }
     }
   }
-  const int fixed = stg_bytes_total + nwg * (tmae ? 2560 : 1024) + 512;
+  const int fixed = stg_bytes_total + nwg * (tmae ? 2560 : 1024) + 512 + (a->ln_stats != nullptr ? 2048 + (tmae ? 0 : 4096) : 0);  // + rowstat[2][128] (+ lnvec[2][512])
   int stages = (232448 - 1024 - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return set_error(MVD_EINVAL, "mvd_gemm_f16: tile does not fit in shared memory");

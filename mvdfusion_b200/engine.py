@@ -163,6 +163,33 @@ class PackedWeights:
         return self._put("qkv", p, lambda: self._pad_k(torch.cat([self.raw(p + ".to_q.weight"), self.raw(p + ".to_k.weight"),
                                                                   self.raw(p + ".to_v.weight")], 0).float()).half())
 
+    # nn.LayerNorm folded into the consuming GEMM (include/mvd_b200.h ABI 13):
+    #   LN(x) W^T + b = rstd (x W'^T - mean colsum(W')) + (b + W beta),   W' = W diag(gamma)
+    def _ln_fold(self, tag, key, w_fn, b_fn, norm):
+        """-> (W' fp16 [N, K8], colsum fp32 [N] of the ROUNDED W', bias' fp32 [N])"""
+        wp = self._put(tag + "_w", (key, norm), lambda: self._pad_k(w_fn().float() * self.raw(norm + ".weight").float()[None, :]).half())
+        cs = self._put(tag + "_cs", (key, norm), lambda: wp.float().sum(dim=1))
+
+        def f_b():
+            wb = w_fn().double() @ self.raw(norm + ".bias").double()
+            b = b_fn()
+            return (wb if b is None else wb + b.double()).float()
+        bp = self._put(tag + "_b", (key, norm), f_b)
+        return wp, cs, bp
+
+    def qkv_ln(self, p, norm):
+        """fused to_q | to_k | to_v behind nn.LayerNorm `norm` (attention.py:211,220; mvd attention.py:35,52)"""
+        w = lambda: torch.cat([self.raw(p + ".to_q.weight"), self.raw(p + ".to_k.weight"), self.raw(p + ".to_v.weight")], 0)
+        return self._ln_fold("qkvln", p, w, lambda: None, norm)
+
+    def geglu_ln(self, p, norm, tile_n=128):
+        """GEGLU.proj behind nn.LayerNorm `norm`, rows interleaved per output tile as in geglu()"""
+        inner = self.raw(p + ".weight").shape[0] // 2
+        perm = self._put("geglu_perm", (inner, tile_n), lambda: self.ops.geglu_permutation(inner, tile_n))
+        w = lambda: self.raw(p + ".weight")[perm.cpu()]
+        b = lambda: self.raw(p + ".bias")[perm.cpu()]
+        return self._ln_fold("gegluln", (p, tile_n), w, b, norm)
+
     def kv(self, p):
         return self._put("kv", p, lambda: self._pad_k(torch.cat([self.raw(p + ".to_k.weight"),
                                                                  self.raw(p + ".to_v.weight")], 0).float()).half())
@@ -298,6 +325,9 @@ class Builder:
         self.hilo = int(os.environ.get("MVD_HILO", "2"))
         # data movement folded into TMA addressing: strided implicit-GEMM Downsample; MVD_NO_FOLD_K8=1 = im2col (A/B)
         self.fold_k8 = not os.environ.get("MVD_NO_FOLD_K8")
+        # nn.LayerNorm (norm1 / norm3 of the transformer blocks) without a pass of its own: the GEMM that produces the rows leaves their
+        # fp16 copy and per-chunk (sum, sum of squares), the QKV / GEGLU GEMM folds the normalisation (ABI 13); MVD_NO_LN_FOLD=1: ln_kernel
+        self.ln_fold = not os.environ.get("MVD_NO_LN_FOLD")
 
     # -- buffers
     def t16(self, *shape):
@@ -335,10 +365,13 @@ class Builder:
         # split_k = 0 lets the library cut K when the tile grid cannot fill the machine (small-M, weight-bound layers);
         # a measured (tile_n, split_k, cta_pair) choice from gemm_tuning.json overrides the library's heuristics.
         act = kw.get("act", ACT_NONE)
-        can_split = allow_split and act != ACT_GEGLU and kw.get("qkv") is None
+        can_split = allow_split and act != ACT_GEGLU and kw.get("qkv") is None and kw.get("ln_stats_out") is None
         sig = gemm_signature(kw.get("conv") is not None, M, N, K * (3 if kw.get("hilo") else 1),  # hi/lo operands: three passes over K
-                             "qkv" if kw.get("qkv") is not None else str(out.dtype).split(".")[-1], kw.get("residual") is not None, act)
+                             "qkv" if kw.get("qkv") is not None else str(out.dtype).split(".")[-1], kw.get("residual") is not None, act,
+                             "+st" if kw.get("ln_stats_out") is not None else ("+ln" if kw.get("ln") is not None else ""))
         tuned = gemm_tuning().get(sig)
+        if tuned is None and sig[-3:] in ("+st", "+ln"):  # not measured in this form yet: the choice of the plain form
+            tuned = gemm_tuning().get(sig[:-3])
         if tuned is not None and "tile_n" not in kw:
             tn, sk, pr = tuned
             if act == ACT_GEGLU:
@@ -488,33 +521,56 @@ class Builder:
         return out
 
     # -- attention blocks
-    def self_attention(self, h, p, norm, n_img, seq, C, rowbias=None):
+    def ln_ok(self, M, C):
+        """can the LayerNorm over rows [M, C] ride in its neighbours' epilogues?  (ABI 13: whole 32-column chunks, the TMA epilogue)"""
+        return self.ln_fold and C % 32 == 0 and C <= 1536 and (C // self.heads) % 8 == 0
+
+    def ln_pair(self, M, C):
+        """-> keywords for the GEMM that produces rows a folded LayerNorm will read: their fp16 copy + the per-chunk statistics"""
+        h16, st = self.t16(M, C), self.t32(C // 32, M, 2)
+        return (h16, st), {"out16": h16, "ld16": C, "ln_stats_out": st}
+
+    def self_attention(self, h, p, norm, n_img, seq, C, rowbias=None, h_ln=None, want_ln=False):
         """x = attn1(norm1(x)) + x  [+ per-image vector]: LayerNorm -> fused QKV GEMM (heads scattered) ->
-        flash attention -> to_out GEMM with bias + residual.  attention.py:170-193,220; mvd attention.py:52"""
+        flash attention -> to_out GEMM with bias + residual.  attention.py:170-193,220; mvd attention.py:52
+        h_ln = (fp16 copy of h, chunk statistics) left by h's producer: norm1 is folded into the QKV GEMM (no LayerNorm pass);
+        want_ln: also return such a pair for the result (for the next folded LayerNorm)."""
         M = n_img * seq
         d = C // self.heads
         dpad = _round_up(d, 64)
-        ln = self.layernorm(h, norm, M, C)
         q, k, vt = self.qkv_buffers(n_img, seq, dpad)
-        self.gemm(ln, self.W.qkv(p), q, M, 3 * C, C,
-                  qkv=dict(out_k=k, out_vt=vt, heads=self.heads, dhead=d, dpad=dpad, seq=seq))
-        ao = ln  # reuse: same shape / dtype, the QKV GEMM was its last reader
+        qkv = dict(out_k=k, out_vt=vt, heads=self.heads, dhead=d, dpad=dpad, seq=seq)
+        if h_ln is not None:
+            w, cs, bq = self.W.qkv_ln(p, norm)
+            self.gemm(h_ln[0], w, q, M, 3 * C, C, qkv=qkv, bias=bq, ln=(h_ln[1], cs, 1e-5))
+            self.free(h_ln[1])
+            ao = h_ln[0]  # reuse: same shape / dtype, the QKV GEMM was its last reader
+        else:
+            ao = self.layernorm(h, norm, M, C)
+            self.gemm(ao, self.W.qkv(p), q, M, 3 * C, C, qkv=qkv)
         self.prog.append(self.ops.attn_self(q, k, vt, ao, n_img, self.heads, seq, d, dpad, C))
         h2 = self.t32(M, C)
+        pair, kw = self.ln_pair(M, C) if want_ln else (None, {})
         self.gemm(ao, self.W.lin(p + ".to_out.0.weight"), h2, M, C, C, allow_split=True, bias=self.W.f32(p + ".to_out.0.bias"),
-                  rowbias=rowbias, rows_per_group=seq, residual=h, ldr=C)
+                  rowbias=rowbias, rows_per_group=seq, residual=h, ldr=C, **kw)
         self.free(ao, h)
-        return h2
+        return (h2, pair) if want_ln else h2
 
-    def feed_forward(self, h, p, norm, M, C, out16=False):
+    def feed_forward(self, h, p, norm, M, C, out16=False, h_ln=None):
         """x = ff(norm3(x)) + x with the GEGLU fused into the first GEMM's epilogue.  attention.py:37-64,222
-        out16: the block output only feeds proj_out, so it is written once, as that GEMM's fp16 operand."""
-        ln = self.layernorm(h, norm, M, C)
+        out16: the block output only feeds proj_out, so it is written once, as that GEMM's fp16 operand.
+        h_ln = (fp16 copy of h, chunk statistics) left by h's producer: norm3 is folded into the GEGLU GEMM."""
         inner = 4 * C
-        wg, bg = self.W.geglu(p + ".net.0.proj", GEGLU_TILE)
         g = self.t16(M, inner)
-        self.gemm(ln, wg, g, M, 2 * inner, C, bias=bg, act=ACT_GEGLU, tile_n=GEGLU_TILE, ldc=inner)
-        self.free(ln)
+        if h_ln is not None:
+            wg, cs, bg = self.W.geglu_ln(p + ".net.0.proj", norm, GEGLU_TILE)
+            self.gemm(h_ln[0], wg, g, M, 2 * inner, C, bias=bg, act=ACT_GEGLU, tile_n=GEGLU_TILE, ldc=inner, ln=(h_ln[1], cs, 1e-5))
+            self.free(*h_ln)
+        else:
+            ln = self.layernorm(h, norm, M, C)
+            wg, bg = self.W.geglu(p + ".net.0.proj", GEGLU_TILE)
+            self.gemm(ln, wg, g, M, 2 * inner, C, bias=bg, act=ACT_GEGLU, tile_n=GEGLU_TILE, ldc=inner)
+            self.free(ln)
         h2 = self.t16(M, C) if out16 else self.t32(M, C)
         self.gemm(g, self.W.lin(p + ".net.2.weight"), h2, M, C, inner, allow_split=True, bias=self.W.f32(p + ".net.2.bias"),
                   residual=h, ldr=C)
@@ -528,11 +584,16 @@ class Builder:
         hw, M = H * H, n_img * H * H
         a = self.groupnorm(x, p + ".norm", n_img, hw, C, 1e-6, False)
         h = self.t32(M, C)
-        self.gemm(a, self.W.lin(p + ".proj_in.weight"), h, M, C, C, allow_split=True, bias=self.W.f32(p + ".proj_in.bias"))
+        fold = self.ln_ok(M, C)
+        pair, kw = self.ln_pair(M, C) if fold else (None, {})
+        self.gemm(a, self.W.lin(p + ".proj_in.weight"), h, M, C, C, allow_split=True, bias=self.W.f32(p + ".proj_in.bias"), **kw)
         self.free(a)
         tb = p + ".transformer_blocks.0"
-        h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C, rowbias=clipvec)
-        h16 = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C, out16=True)
+        if fold:
+            h, pair = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C, rowbias=clipvec, h_ln=pair, want_ln=True)
+        else:
+            h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C, rowbias=clipvec)
+        h16 = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C, out16=True, h_ln=pair)
         out = self.t32(M, C)
         self.gemm(h16, self.W.lin(p + ".proj_out.weight"), out, M, C, C, allow_split=True, bias=self.W.f32(p + ".proj_out.bias"),
                   residual=x, ldr=C, **self._o16(out16))
@@ -551,8 +612,9 @@ class Builder:
         self.free(v)
         return out
 
-    def view_cross_attention(self, h, p, norm, ctx16, M, D, C):
-        """DualAttnetionBlock.attn2 (mvd attention.py:56-62): every pixel is one query against its D frustum keys."""
+    def view_cross_attention(self, h, p, norm, ctx16, M, D, C, want_ln=False):
+        """DualAttnetionBlock.attn2 (mvd attention.py:56-62): every pixel is one query against its D frustum keys.
+        want_ln: also return (fp16 copy, chunk statistics) of the result for a folded LayerNorm behind it."""
         d = C // self.heads
         if D == 1:  # softmax over a single key == 1: out = to_out(to_v(ctx))
             v = self.t16(M, C)
@@ -569,23 +631,29 @@ class Builder:
             self.prog.append(self.ops.pixel_cross_attn(q, kv, o, M, D, self.heads, d))
             self.free(q, kv)
         h2 = self.t32(M, C)
+        pair, kw = self.ln_pair(M, C) if want_ln else (None, {})
         self.gemm(o, self.W.lin(p + ".to_out.0.weight"), h2, M, C, C, allow_split=True, bias=self.W.f32(p + ".to_out.0.bias"),
-                  residual=h, ldr=C)
+                  residual=h, ldr=C, **kw)
         self.free(o, h)
-        return h2
+        return (h2, pair) if want_ln else h2
 
     def view_aligned_transformer(self, x, p, n_img, H, C, ctx16, D, out16=None):
         """ViewAlignedFeatureTransformer.forward (mvd attention.py:119-145) + DualAttnetionBlock (:43-66)."""
         hw, M = H * H, n_img * H * H
         a = self.groupnorm(x, p + ".aligned_attn_norm", n_img, hw, C, 1e-6, False)
         h = self.t32(M, C)
+        fold = self.ln_ok(M, C)
+        pair, kw = self.ln_pair(M, C) if fold else (None, {})
         self.gemm(a, self.W.lin(p + ".aligned_attn_proj_in.weight"), h, M, C, C, allow_split=True,
-                  bias=self.W.f32(p + ".aligned_attn_proj_in.bias"))
+                  bias=self.W.f32(p + ".aligned_attn_proj_in.bias"), **kw)
         self.free(a)
         tb = p + ".aligned_attn_transformer_blocks.0"
-        h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C)
-        h = self.view_cross_attention(h, tb + ".attn2", tb + ".norm2", ctx16, M, D, C)
-        h16 = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C, out16=True)
+        h = self.self_attention(h, tb + ".attn1", tb + ".norm1", n_img, hw, C, h_ln=pair)
+        if fold:
+            h, pair = self.view_cross_attention(h, tb + ".attn2", tb + ".norm2", ctx16, M, D, C, want_ln=True)
+        else:
+            h = self.view_cross_attention(h, tb + ".attn2", tb + ".norm2", ctx16, M, D, C)
+        h16 = self.feed_forward(h, tb + ".ff", tb + ".norm3", M, C, out16=True, h_ln=pair)
         out = self.t32(M, C)
         self.gemm(h16, self.W.lin(p + ".aligned_attn_proj_out.weight"), out, M, C, C, allow_split=True,
                   bias=self.W.f32(p + ".aligned_attn_proj_out.bias"), residual=x, ldr=C, **self._o16(out16))

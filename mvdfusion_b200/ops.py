@@ -20,9 +20,10 @@ class MvdError(RuntimeError):
     pass
 
 
-def gemm_signature(is_conv, M, N, K, out_kind, has_res, act):
-    """Key of a GEMM launch in mvdfusion_b200/gemm_tuning.json (tools/tune_gemm.py)."""
-    return f"{'conv' if is_conv else 'lin'}:{M}:{N}:{K}:{out_kind}:{int(bool(has_res))}:{act}"
+def gemm_signature(is_conv, M, N, K, out_kind, has_res, act, extra=""):
+    """Key of a GEMM launch in mvdfusion_b200/gemm_tuning.json (tools/tune_gemm.py).  extra: "+st" for a producer that also leaves the
+    fp16 copy and LayerNorm statistics of its rows, "+ln" for a consumer with the LayerNorm folded in (their epilogues cost differently)."""
+    return f"{'conv' if is_conv else 'lin'}:{M}:{N}:{K}:{out_kind}:{int(bool(has_res))}:{act}{extra}"
 
 
 def _ptr(t, dtype=None):
@@ -79,8 +80,12 @@ class NativeOps:
     # ------------------------------------------------------------------ GEMM / conv
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
              colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None, cta_pair=0,
-             out16=None, ld16=None, hilo=False, out16_lo=0, a_lo_off=0, conv_stride=1, conv_no_pad_lo=False):
-        """out16: optional fp16 tensor (or column window of a wider one, row pitch ld16) that receives a copy of an fp32 output
+             out16=None, ld16=None, hilo=False, out16_lo=0, a_lo_off=0, conv_stride=1, conv_no_pad_lo=False,
+             ln_stats_out=None, ln=None):
+        """ln_stats_out: fp32 [N/32, M, 2] — the epilogue leaves (sum, sum of squares) per row and 32-column chunk of an fp32 output;
+        ln = (stats, colsum, eps): nn.LayerNorm folded into this GEMM — A holds the raw rows, Wt the gamma-scaled weights, stats what the
+        GEMM that produced A's rows wrote (include/mvd_b200.h, ABI 13).
+        out16: optional fp16 tensor (or column window of a wider one, row pitch ld16) that receives a copy of an fp32 output
         (out16_lo > 0: and its fp16 rounding residual, out16_lo columns to the right).
         hilo: split-precision operands A = [A_hi | A_lo], Wt = [W_hi | W_lo] (include/mvd_b200.h, ABI 9); K stays the logical K.
         conv = (n_img, H, W, C) with conv_stride = 2: H, W are the OUTPUT extent and A is the [n_img, 2H, 2W, C] image (ABI 10);
@@ -127,17 +132,26 @@ class NativeOps:
         if out16 is not None:
             g.out16 = _ptr(out16, torch.float16)
             g.ld16 = ld16 if ld16 is not None else out16.shape[-1]
-        keep = (g, A, Wt, out, bias, rowbias, colscale, residual, qkv, ws, out16)
+        if ln_stats_out is not None:
+            g.ln_stats_out = _ptr(ln_stats_out, torch.float32)
+        if ln is not None:
+            g.ln_stats = _ptr(ln[0], torch.float32)
+            g.ln_colsum = _ptr(ln[1], torch.float32)
+            g.ln_eps = float(ln[2])
+        keep = (g, A, Wt, out, bias, rowbias, colscale, residual, qkv, ws, out16, ln_stats_out, ln)
         n_out = N // 2 if act == ACT_GEGLU else N
         a_bytes = (conv[0] * conv[1] * conv[2] * conv[3] * conv_stride * conv_stride if conv is not None else M * K) * 2
         o_bytes = M * n_out * (4 if (qkv is None and out.dtype == torch.float32) else 2)
         desc = (f"{'conv' if conv is not None else 'lin'} M{M} N{N} K{K} "
                 f"{'qkv' if qkv is not None else ('f32' if out.dtype == torch.float32 else 'f16')}"
                 f"{' res' if residual is not None else ''}{' act%d' % act if act else ''}{' sk' if split_k != 1 else ''}"
-                f"{' +f16' if out16 is not None else ''}{' hilo' if hilo else ''}{' s2' if conv_stride == 2 else ''}")
-        sig = gemm_signature(conv is not None, M, N, K, "qkv" if qkv is not None else str(out.dtype).split(".")[-1], residual is not None, act)
+                f"{' +f16' if out16 is not None else ''}{' hilo' if hilo else ''}{' s2' if conv_stride == 2 else ''}"
+                f"{' +st' if ln_stats_out is not None else ''}{' ln' if ln is not None else ''}")
+        sig = gemm_signature(conv is not None, M, N, K, "qkv" if qkv is not None else str(out.dtype).split(".")[-1], residual is not None, act,
+                             "+st" if ln_stats_out is not None else ("+ln" if ln is not None else ""))
         meta = {"kernel": "gemm_tc_kernel", "flops": 2.0 * M * N * K, "executed_flops": 2.0 * M * N * K * (3 if hilo else 1), "shape": (M, N, K, split_k), "desc": desc, "sig": sig, "can_split": ws is not None,
-                "bytes": a_bytes + N * K * 2 + o_bytes + (M * n_out * 4 if residual is not None else 0) + (M * n_out * 2 if out16 is not None else 0)}
+                "bytes": a_bytes + N * K * 2 + o_bytes + (M * n_out * 4 if residual is not None else 0) + (M * n_out * 2 if out16 is not None else 0)
+                + (M * N // 4 if ln_stats_out is not None else 0) + (M * K // 4 if ln is not None else 0)}
         return self._bind("mvd_gemm_f16", (ctypes.byref(g),), keep, meta)
 
     def attn_self(self, q, k, vt, out, n_img, heads, seq, dhead, dpad, ldo, seq_valid=None):

@@ -5,6 +5,8 @@ It emulates, with plain torch on CPU tensors, the documented semantics of every 
 product's host-side logic (engine emitters, weight packing, buffer arena, program order, step tables, view sharding)
 against the oracle, so that the only thing left to verify on the B200 is the kernels themselves.
 """
+import sys
+
 import torch
 import torch.nn.functional as F
 
@@ -40,13 +42,20 @@ class TorchOpsDouble:
         def run(stream):
             self.calls += 1
             fn()
+        run.name = sys._getframe(1).f_code.co_name  # the emulated op (program-structure tests count launches by kind)
         return run
 
     # ------------------------------------------------------------------ GEMM / conv
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
              colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None, cta_pair=0,
-             out16=None, ld16=None, hilo=False, out16_lo=0, a_lo_off=0, conv_stride=1, conv_no_pad_lo=False):
+             out16=None, ld16=None, hilo=False, out16_lo=0, a_lo_off=0, conv_stride=1, conv_no_pad_lo=False,
+             ln_stats_out=None, ln=None):
         assert A.dtype == torch.float16 and Wt.dtype == torch.float16
+        # ABI 13 (LayerNorm between two GEMMs): the producer leaves per-chunk (sum, sum of squares), the consumer folds the normalisation
+        assert ln_stats_out is None or (out.dtype == torch.float32 and qkv is None and act != ACT_GEGLU and N % 32 == 0 and split_k in (0, 1)
+                                        and K <= 1536 and ln_stats_out.numel() >= (N // 32) * M * 2)
+        assert ln is None or (conv is None and not hilo and K % 32 == 0 and N % 32 == 0 and (qkv is not None or act == ACT_GEGLU)
+                              and split_k in (0, 1) and ln[0].numel() >= (K // 32) * M * 2)
         assert out16 is None or (out.dtype == torch.float32 and qkv is None and act != ACT_GEGLU)
         ldw_ = ldw if ldw is not None else Wt.shape[-1]
 
@@ -76,6 +85,11 @@ class TorchOpsDouble:
             if hilo:  # A_hi W_hi + A_lo W_hi + A_hi W_lo
                 assert K % 64 == 0
                 acc = acc + a_lo @ W.t() + a @ Wfull[:, K:2 * K].float().t()
+            if ln is not None:  # statistics from the producer's chunk sums, E[x^2] - mean^2 form, as the kernel does
+                st = ln[0].reshape(-1)[: (K // 32) * M * 2].reshape(K // 32, M, 2).sum(dim=0)
+                mu = st[:, 0:1] / K
+                var = (st[:, 1:2] / K - mu * mu).clamp_min(0.0)
+                acc = torch.rsqrt(var + ln[2]) * (acc - mu * ln[1].reshape(-1)[:N].float())
             if bias is not None:
                 acc = acc + bias.reshape(-1)[:N]
             if rowbias is not None:
@@ -109,6 +123,10 @@ class TorchOpsDouble:
             ldc_ = ldc if ldc is not None else out.shape[-1]
             o = out.reshape(-1)[: M * ldc_].reshape(M, ldc_)
             o[:, : acc.shape[1]] = acc.to(out.dtype)
+            if ln_stats_out is not None:
+                ch = acc.reshape(M, N // 32, 32)
+                ln_stats_out.reshape(-1)[: (N // 32) * M * 2].reshape(N // 32, M, 2).copy_(
+                    torch.stack([ch.sum(-1), (ch * ch).sum(-1)], dim=-1).permute(1, 0, 2))
             if out16 is not None:
                 ld16_ = ld16 if ld16 is not None else out16.shape[-1]
                 # out16 may be a column window of a wider buffer: address it from its first element with the row pitch

@@ -181,6 +181,114 @@ def test_conv3x3(nat, dbl, n, H, Cin, Cout):
              split_k=(0 if H <= 8 else 1), ws="ws")
 
 
+def _close(a, b, tol, what):
+    a, b = a.float().cpu(), b.float().cpu()
+    assert torch.isfinite(a).all(), f"{what}: non-finite values"
+    err, scale = (a - b).abs().max().item(), b.abs().max().item() + 1e-6
+    assert err <= tol * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("M,C,res,tile,pair", [(4096, 320, True, 0, 0), (4096, 320, False, 320, 2), (2048, 320, True, 160, 1), (1000, 640, True, 0, 0),
+                                               (512, 1280, True, 96, 1), (256, 1280, False, 32, 1), (130, 64, True, 0, 0), (16384, 320, True, 320, 2)])
+def test_gemm_layernorm_statistics_from_the_epilogue(nat, dbl, M, C, res, tile, pair):
+    """ABI 13, producer side: next to the fp32 rows and their fp16 copy the epilogue leaves (sum, sum of squares) per row and
+    32-column chunk — every tile geometry the step uses for the C x C products (single CTAs, pairs, 320-column pair tiles, M tails)"""
+    t = {"A": rnd(M, C, dtype=torch.float16), "W": rnd(C, C, dtype=torch.float16, seed=1, scale=C ** -0.5), "bias": rnd(C, seed=2),
+         "rb": rnd((M + 255) // 256, C, seed=4), "res": rnd(M, C, seed=3, scale=3.0) + 0.7}
+    outs = {}
+    for side, ops, dev in (("cpu", dbl, "cpu"), ("gpu", nat, "cuda")):
+        g = {k: v.to(dev) for k, v in t.items()}
+        o = {"out": torch.zeros(M, C, device=dev), "o16": torch.zeros(M, C, dtype=torch.float16, device=dev),
+             "st": torch.full((C // 32, M, 2), float("nan"), device=dev)}
+        kw = dict(bias=g["bias"], rowbias=g["rb"], rows_per_group=256, out16=o["o16"], ld16=C, ln_stats_out=o["st"])
+        if res:
+            kw.update(residual=g["res"], ldr=C)
+        if side == "gpu":
+            kw.update(tile_n=tile, cta_pair=pair)
+        ops.gemm(g["A"], g["W"], o["out"], M, C, C, **kw)(torch.cuda.current_stream().cuda_stream if side == "gpu" else None)
+        outs[side] = o
+    torch.cuda.synchronize()
+    _close(outs["gpu"]["out"], outs["cpu"]["out"], 2e-3, "out")
+    _close(outs["gpu"]["o16"], outs["cpu"]["o16"], 2e-3, "out16")
+    _close(outs["gpu"]["st"][..., 0], outs["cpu"]["st"][..., 0], 2e-3, "chunk sums")
+    _close(outs["gpu"]["st"][..., 1], outs["cpu"]["st"][..., 1], 2e-3, "chunk sums of squares")
+    # the statistics describe the rows that were written (not the accumulators): mean / variance from them == those of `out`
+    x = outs["gpu"]["out"].double().cpu()
+    st = outs["gpu"]["st"].double().cpu().sum(0)
+    mu = st[:, 0] / C
+    var = st[:, 1] / C - mu * mu
+    assert (mu - x.mean(1)).abs().max() < 1e-5 * (1 + x.abs().max())
+    assert ((var - x.var(1, unbiased=False)).abs() / x.var(1, unbiased=False)).max() < 1e-4
+
+
+@pytest.mark.parametrize("n,seq,C,pair", [(2, 1024, 320, 0), (2, 256, 640, 2), (3, 64, 1280, 0), (2, 16, 1280, 1), (1, 200, 64, 0), (16, 1024, 320, 0)])
+def test_gemm_layernorm_folded_into_qkv_and_geglu(nat, dbl, n, seq, C, pair):
+    """ABI 13, consumer side: raw fp16 rows + their chunk statistics in, LayerNorm(x) W^T (+ b) out — the QKV head scatter and the
+    GEGLU epilogue, against the emulation and against nn.LayerNorm followed by the plain products in fp32"""
+    heads = 8
+    d = C // heads
+    dpad = (d + 63) // 64 * 64
+    M = n * seq
+    nb = n * heads * seq * dpad
+    x = rnd(M, C, seed=11, scale=2.5) + 0.9 * rnd(M, 1, seed=12)
+    gamma, beta = 1.0 + 0.3 * rnd(C, seed=13), 0.2 * rnd(C, seed=14)
+    ch = x.reshape(M, C // 32, 32)
+    st = torch.stack([ch.sum(-1), (ch * ch).sum(-1)], dim=-1).permute(1, 0, 2).contiguous()
+    x16 = x.half()
+    ln = torch.nn.functional.layer_norm(x, (C,), gamma, beta, 1e-5)
+    stream = lambda side: torch.cuda.current_stream().cuda_stream if side == "gpu" else None
+    # --- QKV
+    Wq = rnd(3 * C, C, seed=1, scale=C ** -0.5)
+    wq = (Wq * gamma[None, :]).half()
+    cs, bq = wq.float().sum(1), Wq @ beta
+    got = {}
+    for side, ops, dev in (("cpu", dbl, "cpu"), ("gpu", nat, "cuda")):
+        q, k, vt = (torch.zeros(nb, dtype=torch.float16, device=dev) for _ in range(3))
+        kw = dict(cta_pair=pair) if side == "gpu" else {}
+        ops.gemm(x16.to(dev), wq.to(dev), q, M, 3 * C, C, bias=bq.to(dev), ln=(st.to(dev), cs.to(dev), 1e-5),
+                 qkv=dict(out_k=k, out_vt=vt, heads=heads, dhead=d, dpad=dpad, seq=seq), **kw)(stream(side))
+        got[side] = (q, k, vt)
+    torch.cuda.synchronize()
+    for a, b, nm in zip(got["gpu"], got["cpu"], "q k vt".split()):
+        _close(a, b, 2e-3, "folded QKV " + nm)
+    ref = (ln @ Wq.t()).reshape(n, seq, 3, heads, d).permute(2, 0, 3, 1, 4)
+    qg = got["gpu"][0].reshape(n, heads, seq, dpad)[..., :d].float().cpu()
+    vg = got["gpu"][2].reshape(n, heads, dpad, seq)[:, :, :d].float().cpu().transpose(-1, -2)
+    assert rel(qg, ref[0]) < 2e-3 and rel(vg, ref[2]) < 2e-3
+    # --- GEGLU
+    from ops_double import geglu_permutation
+    tile = 256
+    Wg, bg = rnd(8 * C, C, seed=2, scale=C ** -0.5), rnd(8 * C, seed=3, scale=0.1)
+    perm = geglu_permutation(4 * C, tile)
+    wg = (Wg[perm] * gamma[None, :]).half()
+    csg, bgp = wg.float().sum(1), (Wg @ beta + bg)[perm]
+    outs = {}
+    for side, ops, dev in (("cpu", dbl, "cpu"), ("gpu", nat, "cuda")):
+        o = torch.zeros(M, 4 * C, dtype=torch.float16, device=dev)
+        kw = dict(cta_pair=pair) if side == "gpu" else {}
+        ops.gemm(x16.to(dev), wg.to(dev), o, M, 8 * C, C, bias=bgp.to(dev), act=OPS.ACT_GEGLU, tile_n=tile, ldc=4 * C,
+                 ln=(st.to(dev), csg.to(dev), 1e-5), **kw)(stream(side))
+        outs[side] = o
+    torch.cuda.synchronize()
+    _close(outs["gpu"], outs["cpu"], 3e-3, "folded GEGLU")
+    y = ln @ Wg.t() + bg
+    assert rel(outs["gpu"].float().cpu(), y[:, :4 * C] * torch.nn.functional.gelu(y[:, 4 * C:])) < 3e-3
+
+
+def test_gemm_layernorm_arguments_are_checked(nat):
+    M, C = 256, 320
+    dev = "cuda"
+    A, W = torch.zeros(M, C, dtype=torch.float16, device=dev), torch.zeros(C, C, dtype=torch.float16, device=dev)
+    st = torch.zeros(C // 32, M, 2, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    with pytest.raises(OPS.MvdError):  # statistics need the TMA epilogue: no split-K
+        nat.gemm(A, W, torch.zeros(M, C, device=dev), M, C, C, ln_stats_out=st, split_k=2, ws=torch.zeros(1 << 24, dtype=torch.uint8, device=dev))(s)
+    with pytest.raises(OPS.MvdError):  # ... and an fp32 output
+        nat.gemm(A, W, torch.zeros(M, C, dtype=torch.float16, device=dev), M, C, C, ln_stats_out=st)(s)
+    with pytest.raises(OPS.MvdError):  # the fold exists for the QKV scatter and GEGLU only
+        nat.gemm(A, W, torch.zeros(M, C, device=dev), M, C, C, ln=(st, torch.zeros(C, device=dev), 1e-5))(s)
+
+
 @pytest.mark.parametrize("n,seq,C", [(2, 1024, 320), (2, 256, 640), (3, 64, 1280), (2, 16, 1280), (2, 1024, 64)])
 def test_qkv_and_attention(nat, dbl, n, seq, C):
     heads = 8

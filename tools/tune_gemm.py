@@ -58,6 +58,7 @@ def main():
     ap.add_argument("--latent", type=int, default=32, help="latent side (32 = 256^2 images, 64 = 512^2)")
     ap.add_argument("--shards", default="1", help="comma list of GPU counts whose per-rank shapes (views/G per GPU) to tune")
     ap.add_argument("--merge", default="", help="existing tuning file whose choices are kept for signatures not re-measured")
+    ap.add_argument("--only", default="", help="re-measure only the signatures that contain this substring (e.g. '+st')")
     ap.add_argument("--out", default=os.path.join(ROOT, "mvdfusion_b200", "gemm_tuning.json"))
     a = ap.parse_args()
     os.environ["MVD_GEMM_NO_TUNING"] = "1"  # start from the heuristics
@@ -79,7 +80,7 @@ def main():
             if c.name != "mvd_gemm_f16":
                 continue
             sig = c.meta["sig"]
-            if sig in seen:
+            if sig in seen or (a.only and a.only not in sig):
                 continue
             seen[sig] = True
             choices.pop(sig, None)
