@@ -420,7 +420,7 @@ def run_native(args):
         top = ktab[0]
         traffic, traffic_src = None, None
         tensor_pct, tensor_pct_step = None, None
-        for tname in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):  # written by tools/ncu_summary.py from an ncu pass of this command
+        for tname in ("r02_gemm_traffic_v6.json", "r02_gemm_traffic.json", "r01_gemm_traffic.json"):  # written by tools/ncu_summary.py from an ncu pass of this command
             tpath = os.path.join(ROOT, "profiles", tname)
             if os.path.exists(tpath) and S == 32:
                 tj = json.load(open(tpath))

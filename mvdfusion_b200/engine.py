@@ -328,6 +328,9 @@ class Builder:
         # nn.LayerNorm (norm1 / norm3 of the transformer blocks) without a pass of its own: the GEMM that produces the rows leaves their
         # fp16 copy and per-chunk (sum, sum of squares), the QKV / GEGLU GEMM folds the normalisation (ABI 13); MVD_NO_LN_FOLD=1: ln_kernel
         self.ln_fold = not os.environ.get("MVD_NO_LN_FOLD")
+        # ... where it pays: up to 4096 rows.  Above that (the 32^2 level of an 8-view step, M = 16384) the consumers' per-unit epilogue work
+        # outweighs a LayerNorm pass that streams at L2 speed (measured, profiles/r02_bench_v6_ab_lnfold_rows.md); MVD_LN_FOLD_MAX_ROWS overrides
+        self.ln_fold_max_rows = int(os.environ.get("MVD_LN_FOLD_MAX_ROWS", "4096"))
 
     # -- buffers
     def t16(self, *shape):
@@ -523,7 +526,7 @@ class Builder:
     # -- attention blocks
     def ln_ok(self, M, C):
         """can the LayerNorm over rows [M, C] ride in its neighbours' epilogues?  (ABI 13: whole 32-column chunks, the TMA epilogue)"""
-        return self.ln_fold and C % 32 == 0 and C <= 1536 and (C // self.heads) % 8 == 0
+        return self.ln_fold and M <= self.ln_fold_max_rows and C % 32 == 0 and C <= 1536 and (C // self.heads) % 8 == 0
 
     def ln_pair(self, M, C):
         """-> keywords for the GEMM that produces rows a folded LayerNorm will read: their fp16 copy + the per-chunk statistics"""
