@@ -126,6 +126,16 @@ typedef struct mvd_gemm_args {
   const float* ln_stats;
   const float* ln_colsum;
   float ln_eps;
+  /* ABI 14: nearest x2 upsample folded into the convolution — Upsample.forward, F.interpolate(scale_factor=2, mode="nearest") followed by
+   * conv3x3 padding 1 (external/sd1/ldm/modules/diffusionmodules/openaimodel.py:107-119).  An output pixel (2y + py, 2x + px) sees only
+   * the 2 x 2 source pixels (y + py - 1 + a, x + px - 1 + b), a, b in {0, 1}, each with the SUM of the 3 x 3 taps that land on it:
+   * four 2 x 2 convolutions of the source image, 16 C instead of 36 C multiply-adds per output value, no upsampled tensor.
+   * conv_up2 = 1 (CONV3X3): A is the SOURCE image fp16 [n_img, H, W, C] (H, W powers of two), M = n_img * H * W, K = 4 * C,
+   *   N = 4 * Cout; Wt is [N, K]: row phase * Cout + n (phase = 2 py + px), column (2 a + b) * C + c, holding
+   *   sum over ky in Sa(py), kx in Sb(px) of w[n, c, ky, kx] with S0(0) = {0}, S1(0) = {1, 2}, S0(1) = {0, 1}, S1(1) = {2};
+   *   bias is [N] (the convolution's bias once per phase); out / out16 are the UPSAMPLED-resolution matrices [n_img * 2H * 2W, ldc]
+   *   with ldc >= Cout.  Bias only (no residual / row bias / activation / split precision); tile_n must divide Cout. */
+  int32_t conv_up2;
 } mvd_gemm_args;
 
 int mvd_gemm_f16(const mvd_gemm_args* args, void* stream);

@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_float, c_int32, c_longlong, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # MVD_B200_LIB: another build of the same library (e.g. the instrumented `make trace` one); it must exist — there is no fallback
 LIB_PATH = os.environ.get("MVD_B200_LIB") or os.path.join(_HERE, "libmvd_b200.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 
 class GemmArgs(ctypes.Structure):
@@ -30,7 +30,7 @@ class GemmArgs(ctypes.Structure):
         ("split_k", c_int32), ("tile_n", c_int32), ("cta_pair", c_int32),
         ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_longlong),
         ("out16", c_void_p), ("ld16", c_int32), ("hilo", c_int32), ("out16_lo", c_int32), ("a_lo_off", c_int32), ("conv_stride", c_int32), ("conv_no_pad_lo", c_int32),
-        ("ln_stats_out", c_void_p), ("ln_stats", c_void_p), ("ln_colsum", c_void_p), ("ln_eps", c_float),
+        ("ln_stats_out", c_void_p), ("ln_stats", c_void_p), ("ln_colsum", c_void_p), ("ln_eps", c_float), ("conv_up2", c_int32),
     ]
 
 

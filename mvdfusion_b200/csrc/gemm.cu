@@ -121,6 +121,11 @@ struct GemmKParams {
   // A_hi W_hi, A_lo W_hi, A_hi W_lo (kb_seg k-blocks each).  a_lo_off / w_lo_off: column (channel) offsets of the lo halves.
   int hilo, kb_seg, a_lo_off, w_lo_off;
   int cstride, cpad;        // CONV3X3: stride (1 / 2) and low-side padding (1, or 0 for the VAE encoder's pad-high-only downsample)
+  // CONV3X3 + conv_up2 (nearest x2 upsample folded into the convolution): the N columns are four phase blocks of n_real = N / 4 output
+  // channels; phase (py, px) reads the 2 x 2 source taps at offsets (py - 1 + a, px - 1 + b) and owns the output pixels (2y + py, 2x + px)
+  int taps_w, taps;         // taps per row / per pixel: 3 / 9, or 2 / 4 with up2
+  int up2, n_real, up_lw, up_lh;
+  FastDiv fd_tpp;           // n-tiles per phase
   // TMA epilogue (template TMAE): per-warpgroup chunk slots [32 fp32 columns x 128 rows | fp16 copy | fp16 lo] that the residual
   // is loaded into and the finished chunk is stored from, both by TMA
   int spw, slot_bytes, slot_h16, slot_lo;  // slots per warpgroup (1 / 2), bytes per slot, offsets of the fp16 tiles inside a slot
@@ -218,8 +223,8 @@ struct KbIter {
     if (p.a_mode == MVD_A_CONV3X3) {
       tap = kb / p.kb_per_tap;
       cb = kb - tap * p.kb_per_tap;
-      ky = tap / 3;
-      kx = tap - ky * 3;
+      ky = tap / p.taps_w;
+      kx = tap - ky * p.taps_w;
     } else {
       tap = 0; ky = 0; kx = 0;
       cb = kb;
@@ -239,8 +244,8 @@ struct KbIter {
       if (cb == p.kb_per_tap) {
         cb = 0;
         ++tap;
-        if (++kx == 3) { kx = 0; ++ky; }
-        if (tap == 9) { tap = 0; kx = 0; ky = 0; ++seg; }
+        if (++kx == p.taps_w) { kx = 0; ++ky; }
+        if (tap == p.taps) { tap = 0; kx = 0; ky = 0; ++seg; }
         place(p);
       }
     } else if (cb == p.kb_seg) {  // plain GEMM: only the hilo form ever gets here before the unit ends
@@ -255,6 +260,8 @@ struct Unit {
   int tile, s, m_tile, n_tile, kb0, kb1;
   int x0, y0, img0;  // conv tile origin
   int grow0;         // first output row of the tile
+  int ox, oy;        // conv: low-side offset of the taps (the padding; with up2 it depends on the unit's phase)
+  int ph;            // up2: phase 2 py + px of the unit's columns
 };
 
 // pair_rank < 0: one CTA per tile.  Otherwise the unit list enumerates 256-row tile PAIRS and CTA `pair_rank` of the
@@ -271,6 +278,13 @@ __device__ __forceinline__ Unit decode_unit(const GemmKParams& p, int u, int pai
   t.kb0 = t.s * p.kb_per_split;
   t.kb1 = min(p.num_kb, t.kb0 + p.kb_per_split);
   t.x0 = t.y0 = t.img0 = 0;
+  t.ox = t.oy = p.cpad;
+  t.ph = 0;
+  if (p.up2) {
+    t.ph = p.fd_tpp.div(t.n_tile);
+    t.oy = 1 - (t.ph >> 1);
+    t.ox = 1 - (t.ph & 1);
+  }
   if (p.a_mode == MVD_A_CONV3X3) {
     int tx, ty, tz, rest;
     p.fd_tiles_x.divmod(t.m_tile, rest, tx);
@@ -497,12 +511,12 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
           uint8_t* sb = sa + A_BYTES;
           if (PAIR) {
             const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
-            if (p.a_mode == MVD_A_CONV3X3) tma_load_4d_pair(sa, &tmA, lbar, ki.a_col, t.x0 * p.cstride + ki.kx - p.cpad, t.y0 * p.cstride + ki.ky - p.cpad, t.img0);
+            if (p.a_mode == MVD_A_CONV3X3) tma_load_4d_pair(sa, &tmA, lbar, ki.a_col, t.x0 * p.cstride + ki.kx - t.ox, t.y0 * p.cstride + ki.ky - t.oy, t.img0);
             else tma_load_2d_pair(sa, &tmA, lbar, ki.a_col, t.m_tile * BM);
             tma_load_2d_pair(sb, &tmB, lbar, ki.w_col, t.n_tile * p.BN + w_row0);
             if (w_wide) tma_load_2d_pair(sb + w_half_bytes, &tmB, lbar, ki.w_col, t.n_tile * p.BN + w_row1);
           } else {
-            if (p.a_mode == MVD_A_CONV3X3) tma_load_4d(sa, &tmA, &full_bar[s], ki.a_col, t.x0 * p.cstride + ki.kx - p.cpad, t.y0 * p.cstride + ki.ky - p.cpad, t.img0);
+            if (p.a_mode == MVD_A_CONV3X3) tma_load_4d(sa, &tmA, &full_bar[s], ki.a_col, t.x0 * p.cstride + ki.kx - t.ox, t.y0 * p.cstride + ki.ky - t.oy, t.img0);
             else tma_load_2d(sa, &tmA, &full_bar[s], ki.a_col, t.m_tile * BM);
             tma_load_2d(sb, &tmB, &full_bar[s], ki.w_col, t.n_tile * p.BN);
           }
@@ -1068,8 +1082,15 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
           if (PREFETCH_RES && nxt_valid) rn[i] = res_load(nxt_grow0, nxt_oc, i);
         }
         if (!live) continue;
+        size_t orow = static_cast<size_t>(grow);
+        int ocol = col;
+        if (p.up2) {  // source pixel (img, y, x), phase (py, px) -> output pixel (img, 2y + py, 2x + px); columns of the phase block
+          const int x = grow & ((1 << p.up_lw) - 1), y = (grow >> p.up_lw) & ((1 << p.up_lh) - 1), img = grow >> (p.up_lw + p.up_lh);
+          orow = (((static_cast<size_t>(img) << (p.up_lh + 1)) + 2 * y + (t.ph >> 1)) << (p.up_lw + 1)) + 2 * x + (t.ph & 1);
+          ocol = col - t.ph * p.n_real;
+        }
         if (out_mode == MVD_OUT_F32) {
-          float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(grow) * p.ldc + col;
+          float* dst = reinterpret_cast<float*>(p.out) + orow * p.ldc + ocol;
           if (VEC || (p.vec_out && nvalid >= 4)) {
             *reinterpret_cast<float4*>(dst) = v;
           } else {
@@ -1079,7 +1100,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
             if (nvalid > 3) dst[3] = v.w;
           }
           if (p.out16 != nullptr) {  // the same values once more as the fp16 operand of the next GEMM
-            __half* d16 = p.out16 + static_cast<size_t>(grow) * p.ld16 + col;
+            __half* d16 = p.out16 + orow * p.ld16 + ocol;
             if (p.vec_out16 && nvalid >= 4) {
               *reinterpret_cast<uint2*>(d16) = make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
             } else {
@@ -1103,7 +1124,7 @@ __global__ void __launch_bounds__(128 + 128 * NWG, 1)
             }
           }
         } else if (out_mode == MVD_OUT_F16) {
-          __half* dst = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(grow) * p.ldc + col;
+          __half* dst = reinterpret_cast<__half*>(p.out) + orow * p.ldc + ocol;
           if (VEC || (p.vec_out && nvalid >= 4)) {
             *reinterpret_cast<uint2*>(dst) = make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
           } else {
@@ -1347,9 +1368,24 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   if (a->out_mode < MVD_OUT_F32 || a->out_mode > MVD_OUT_QKV_HEADS)
     return set_error(MVD_EINVAL, "mvd_gemm_f16: bad out_mode");
 
+  // conv_up2: nearest x2 upsample folded into the convolution (mvd_b200.h, ABI 14).  N counts the four phase blocks; the output has N / 4 columns
+  const bool up2 = a->conv_up2 != 0;
+  if (up2) {
+    if (a->a_mode != MVD_A_CONV3X3 || hilo || a->conv_stride == 2 || a->conv_no_pad_lo || (a->N & 3) != 0 || ((a->N / 4) & 3) != 0 ||
+        a->residual != nullptr || a->rowbias != nullptr || a->colscale != nullptr || a->act != MVD_ACT_NONE || a->out_mode == MVD_OUT_QKV_HEADS ||
+        a->ln_stats_out != nullptr || a->ln_stats != nullptr)
+      return set_error(MVD_EINVAL, "mvd_gemm_f16: conv_up2 needs a plain CONV3X3 (bias only, F32 / F16 output, N = 4 x output channels)");
+    if (a->H <= 0 || (a->H & (a->H - 1)) != 0) return set_error(MVD_EINVAL, "mvd_gemm_f16: conv_up2 needs H and W to be powers of two");
+  }
+  const int n_cols = up2 ? a->N / 4 : a->N;  // columns of the output matrix
+
   GemmKParams p{};
   p.M = a->M;
   p.N = a->N;
+  p.up2 = up2 ? 1 : 0;
+  p.n_real = n_cols;
+  p.taps_w = up2 ? 2 : 3;
+  p.taps = up2 ? 4 : 9;
   p.a_mode = a->a_mode;
   p.bias = a->bias;
   p.rowbias = a->rowbias;
@@ -1370,11 +1406,11 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   p.out16 = static_cast<__half*>(a->out16);
   p.ld16 = a->ld16;
   p.out16_lo = a->out16 != nullptr ? a->out16_lo : 0;
-  if (p.out16_lo < 0 || (p.out16_lo > 0 && (p.out16_lo < a->N || (p.out16_lo & 3) != 0)))
+  if (p.out16_lo < 0 || (p.out16_lo > 0 && (p.out16_lo < n_cols || (p.out16_lo & 3) != 0)))
     return set_error(MVD_EINVAL, "mvd_gemm_f16: out16_lo must be 0 or a multiple of 4 that is >= N");
   if (a->out16 != nullptr) {
     if (a->out_mode != MVD_OUT_F32 || a->act == MVD_ACT_GEGLU) return set_error(MVD_EINVAL, "mvd_gemm_f16: out16 accompanies an F32 output only");
-    if (a->ld16 < a->N) return set_error(MVD_EINVAL, "mvd_gemm_f16: ld16 is smaller than N");
+    if (a->ld16 < n_cols) return set_error(MVD_EINVAL, "mvd_gemm_f16: ld16 is smaller than N");
     p.vec_out16 = (reinterpret_cast<uintptr_t>(a->out16) & 7) == 0 && (a->ld16 & 3) == 0;
   }
 
@@ -1430,6 +1466,13 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   const int slots = pair ? sms / 2 : sms;
   int bn = a->tile_n;
   if (bn == 0) bn = geglu ? 256 : pick_bn(a->N, tiles_mp, slots, pair);
+  if (up2) {  // a tile stays inside one phase block: the widest multiple of 32 up to the chosen width that divides the output channels
+    if (a->tile_n == 0) {
+      while (bn > 32 && (n_cols % bn) != 0) bn -= 32;
+    }
+    if (bn > 256 || (bn & 31) != 0 || (n_cols % bn) != 0)
+      return set_error(MVD_EINVAL, "mvd_gemm_f16: conv_up2 needs tile_n to be a multiple of 32 (<= 256) that divides N / 4");
+  }
   if (pair && (bn & 31) != 0) return set_error(MVD_EINVAL, "mvd_gemm_f16: tile_n must be a multiple of 32 here");
   const bool wide = bn > 256;
   if (wide && (!pair || bn > 320 || (bn & 63) != 0 || geglu || a->out_mode == MVD_OUT_QKV_HEADS))
@@ -1461,7 +1504,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     if (rc != MVD_OK) return rc;
   } else if (a->a_mode == MVD_A_CONV3X3) {
     if (a->n_img <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || (a->C & 7) != 0 || !is_pow2(a->W) || a->W > 4096 ||
-        a->K != 9 * a->C || static_cast<long long>(a->M) != static_cast<long long>(a->n_img) * a->H * a->W)
+        a->K != (up2 ? 4 : 9) * a->C || static_cast<long long>(a->M) != static_cast<long long>(a->n_img) * a->H * a->W)
       return set_error(MVD_EINVAL, "mvd_gemm_f16: bad CONV3X3 geometry");
     p.n_img = a->n_img;
     p.H = a->H;
@@ -1477,9 +1520,9 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     const int tiles_z = (a->n_img + p.tn - 1) / p.tn;
     p.tiles_m_real = p.tiles_x * p.tiles_y * tiles_z;
     p.kb_per_tap = (a->C + BK - 1) / BK;
-    p.num_kb = 9 * p.kb_per_tap;
+    p.num_kb = p.taps * p.kb_per_tap;
     p.a_lo_off = a->C;       // the image batch holds 2C channels: [hi | lo]
-    p.w_lo_off = 9 * a->C;
+    p.w_lo_off = p.taps * a->C;
     if (a->conv_stride != 0 && a->conv_stride != 1 && a->conv_stride != 2) return set_error(MVD_EINVAL, "mvd_gemm_f16: conv_stride must be 1 or 2");
     p.cstride = a->conv_stride == 2 ? 2 : 1;
     p.cpad = a->conv_no_pad_lo ? 0 : 1;
@@ -1539,6 +1582,13 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   p.fd_inner = make_fastdiv(p.heads * p.dhead > 0 ? p.heads * p.dhead : 1);
   p.fd_dhead = make_fastdiv(p.dhead > 0 ? p.dhead : 1);
   p.fd_rpg = make_fastdiv(p.rows_per_group);
+  p.fd_tpp = make_fastdiv(up2 ? n_cols / bn : 1);
+  if (up2) {
+    p.up_lw = 0;
+    while ((1 << p.up_lw) < a->W) ++p.up_lw;
+    p.up_lh = 0;
+    while ((1 << p.up_lh) < a->H) ++p.up_lh;
+  }
   if (split > 1) {
     if ((reinterpret_cast<uintptr_t>(a->splitk_ws) & 15) != 0) return set_error(MVD_EALIGN, "mvd_gemm_f16: splitk_ws must be 16-byte aligned");
     p.counters = reinterpret_cast<int*>(a->splitk_ws);
@@ -1548,7 +1598,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
   // ---- epilogue access widths
   const int n_out = geglu ? a->N / 2 : a->N;
   auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
-  if (a->out_mode != MVD_OUT_QKV_HEADS && a->ldc < n_out) return set_error(MVD_EINVAL, "mvd_gemm_f16: ldc is smaller than the output width");
+  if (a->out_mode != MVD_OUT_QKV_HEADS && a->ldc < (up2 ? n_cols : n_out)) return set_error(MVD_EINVAL, "mvd_gemm_f16: ldc is smaller than the output width");
   if (a->residual != nullptr && a->ldr < a->N) return set_error(MVD_EINVAL, "mvd_gemm_f16: ldr is smaller than N");
   p.vec_bias = al16(a->bias);
   p.vec_rowbias = al16(a->rowbias) && (a->N & 3) == 0;
@@ -1614,7 +1664,7 @@ extern "C" int mvd_gemm_f16(const mvd_gemm_args* a, void* stream_) {
     // Deep-K GEMMs hide their epilogue behind the mainloop and lose 5-6 % with the TMA stores in flight (conv 16384x640x5760
     // 75.5 -> 80.7 us): they keep the thread-store epilogue.
     // (a wide pair tile runs one tile per CTA pair with nothing to overlap: it takes the TMA epilogue whatever its K)
-    const bool tma_ok = !is_split && a->out_mode != MVD_OUT_QKV_HEADS && (p.kb_per_split <= 24 || wide) && al16(a->out) &&
+    const bool tma_ok = !up2 && !is_split && a->out_mode != MVD_OUT_QKV_HEADS && (p.kb_per_split <= 24 || wide) && al16(a->out) &&
                         ((static_cast<long long>(a->ldc) * (a->out_mode == MVD_OUT_F32 ? 4 : 2)) & 15) == 0 &&
                         (a->residual == nullptr || (al16(a->residual) && (a->ldr & 3) == 0)) &&
                         (a->out16 == nullptr || (al16(a->out16) && (a->ld16 & 7) == 0 && (p.out16_lo & 7) == 0));

@@ -123,6 +123,27 @@ class PackedWeights:
             return w.reshape(co, 9 * cp).half()
         return self._put("conv3", (key, c_pad), f)
 
+    def conv3_up2(self, key):
+        """conv3x3 weight [Cout, Cin, 3, 3] behind a nearest x2 upsample -> the four 2 x 2 phase convolutions of the source image
+        (include/mvd_b200.h, conv_up2): fp16 [4*Cout, 4*Cin], row (2 py + px) * Cout + n, column (2 a + b) * Cin + c, each entry the fp32 sum
+        of the 3 x 3 taps that land on source tap (a, b) for output phase (py, px)."""
+        def f():
+            w = self.raw(key).double().permute(0, 2, 3, 1)  # [Cout, ky, kx, Cin]
+            sets = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}   # phase -> taps summed onto source tap 0 / 1
+            blocks = []
+            for py in range(2):
+                for px in range(2):
+                    taps = []
+                    for a in range(2):
+                        for b in range(2):
+                            taps.append(sum(w[:, ky, kx, :] for ky in sets[py][a] for kx in sets[px][b]))
+                    blocks.append(torch.cat(taps, dim=1))
+            return torch.cat(blocks, dim=0).float().half()
+        return self._put("conv3_up2", key, f)
+
+    def f32_tiled(self, key, reps):
+        return self._put("f32t", (key, reps), lambda: self.raw(key).float().reshape(-1).repeat(reps))
+
     @staticmethod
     def _hilo(w):
         """fp32 -> (fp16 hi, fp16 lo) with hi + lo == w to ~2^-22 relative (include/mvd_b200.h, mvd_gemm_args.hilo)"""
@@ -328,6 +349,9 @@ class Builder:
         # nn.LayerNorm (norm1 / norm3 of the transformer blocks) without a pass of its own: the GEMM that produces the rows leaves their
         # fp16 copy and per-chunk (sum, sum of squares), the QKV / GEGLU GEMM folds the normalisation (ABI 13); MVD_NO_LN_FOLD=1: ln_kernel
         self.ln_fold = not os.environ.get("MVD_NO_LN_FOLD")
+        # nearest x2 upsample folded into the following convolution (ABI 14): four 2 x 2 phase convolutions of the source image,
+        # no upsampled tensor, 16 C instead of 36 C multiply-adds per output value; MVD_NO_FOLD_UP=1 = upsample pass + conv3x3 (A/B)
+        self.fold_up = not os.environ.get("MVD_NO_FOLD_UP")
         # ... where it pays: up to 4096 rows.  Above that (the 32^2 level of an 8-view step, M = 16384) the consumers' per-unit epilogue work
         # outweighs a LayerNorm pass that streams at L2 speed (measured, profiles/r02_bench_v6_ab_lnfold_rows.md); MVD_LN_FOLD_MAX_ROWS overrides
         self.ln_fold_max_rows = int(os.environ.get("MVD_LN_FOLD_MAX_ROWS", "4096"))
@@ -371,7 +395,7 @@ class Builder:
         can_split = allow_split and act != ACT_GEGLU and kw.get("qkv") is None and kw.get("ln_stats_out") is None
         sig = gemm_signature(kw.get("conv") is not None, M, N, K * (3 if kw.get("hilo") else 1),  # hi/lo operands: three passes over K
                              "qkv" if kw.get("qkv") is not None else str(out.dtype).split(".")[-1], kw.get("residual") is not None, act,
-                             "+st" if kw.get("ln_stats_out") is not None else ("+ln" if kw.get("ln") is not None else ""))
+                             "+st" if kw.get("ln_stats_out") is not None else ("+ln" if kw.get("ln") is not None else ("+up" if kw.get("conv_up2") else "")))
         tuned = gemm_tuning().get(sig)
         if tuned is None and sig[-3:] in ("+st", "+ln"):  # not measured in this form yet: the choice of the plain form
             tuned = gemm_tuning().get(sig[:-3])
@@ -515,8 +539,19 @@ class Builder:
         self.free(col)
         return out
 
-    def upsample(self, x, p, n_img, H, C, out16=None):
-        """Upsample: nearest x2 then conv3x3 (openaimodel.py:107-119)"""
+    def up_ok(self, H, C):
+        return self.fold_up and H & (H - 1) == 0 and C % 32 == 0
+
+    def upsample(self, x, p, n_img, H, C, out16=None, x16=None):
+        """Upsample: nearest x2 then conv3x3 (openaimodel.py:107-119).  With the input available as fp16 (x16 = (tensor, pixel pitch) written
+        by its producer's epilogue) the upsample is folded into the convolution: four 2 x 2 phase convolutions of the SOURCE image in one
+        launch (conv_up2) — no upsampled tensor, 2.25 x fewer multiply-adds."""
+        if x16 is not None and self.up_ok(H, C):
+            Mo = n_img * 4 * H * H
+            out = self.t32(Mo, C)
+            self.gemm(x16[0], self.W.conv3_up2(p + ".conv.weight"), out, n_img * H * H, 4 * C, 4 * C, allow_split=True, conv=(n_img, H, H, C),
+                      conv_up2=True, lda=x16[1], bias=self.W.f32_tiled(p + ".conv.bias", 4), ldc=C, **self._o16(out16))
+            return out
         u = self.t16(n_img * 4 * H * H, C)
         self.prog.append(self.ops.upsample2x(x, u, n_img, H, H, C))
         out = self.conv3x3(u, p + ".conv.weight", n_img, 2 * H, 2 * H, C, C, bias=self.W.f32(p + ".conv.bias"), out16=out16)
@@ -793,6 +828,18 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
         c = cat16[i] if i < len(cat16) else None
         return None if c is None else (c[0][:, :c[1]], c[3] * (c[1] + c[2]), (c[1] + c[2]) if c[3] == 2 else 0)
 
+    def first_up16(layers, H):
+        if not up_src_wanted(layers, 0, H):
+            return None
+        c_out = layers[0][2]
+        up16[0] = (b.t16(n_img * H * H, c_out), c_out)
+        return up16[0]
+
+    up16 = [None]  # (fp16 copy of the tensor entering the next Upsample, pitch), written by the epilogue of the layer in front of it
+
+    def up_src_wanted(layers, j, H):
+        return j + 1 < len(layers) and layers[j + 1][0] == "up" and layers[j][0] in ("res", "st", "vaft") and b.up_ok(H, layers[j + 1][1])
+
     def run_layers(h, prefix, layers, H, start=0, h16=None, last16=None):
         for j, l in enumerate(layers):
             if j < start:
@@ -800,6 +847,10 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
             p = f"{prefix}.{j}"
             kind = l[0]
             o16 = last16 if j == len(layers) - 1 else None
+            if o16 is None and up_src_wanted(layers, j, H):  # the layer behind this one is an Upsample: leave it its input as fp16
+                c_out = l[2] if kind == "res" else l[1]
+                up16[0] = (b.t16(n_img * H * H, c_out), c_out)
+                o16 = up16[0]
             if kind == "stem":
                 new = b.conv3x3(h, p + ".weight", n_img, H, H, l[1], l[2], bias=b.W.f32(p + ".bias"), c_pad=c_in_pad, out16=o16,
                                 w=b.W.conv3_stem_hilo(p + ".weight", c_in_pad) if stem_hilo else None)
@@ -814,7 +865,10 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
                 new = b.downsample(h, p, n_img, H, l[1], out16=o16, x16=h16 if j == 0 else None)
                 H //= 2
             elif kind == "up":
-                new = b.upsample(h, p, n_img, H, l[1], out16=o16)
+                new = b.upsample(h, p, n_img, H, l[1], out16=o16, x16=up16[0])
+                if up16[0] is not None:
+                    b.free(up16[0][0])
+                    up16[0] = None
                 H *= 2
             else:
                 raise ValueError(kind)
@@ -845,7 +899,7 @@ def emit_unet(b, spec, x_in16, n_img, S, D, t_dev, freqs, clipvecs, pyramid16, c
             nxt = head_window(i + 1)
             new = b.resblock(None, p0, n_img, H, c1 + c2, layers[0][2], emb, spec.emb_dim, cat=(h, skip),
                              x16=None if c16 is None else (c16[0], c16[3] * (c1 + c2), (c1 + c2) if c16[3] == 2 else 0),
-                             out16=nxt if len(layers) == 1 else None)
+                             out16=nxt if len(layers) == 1 else first_up16(layers, H))
             b.free(h, skip)
             if c16 is not None:
                 b.free(c16[0])

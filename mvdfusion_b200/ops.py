@@ -81,8 +81,10 @@ class NativeOps:
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
              colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None, cta_pair=0,
              out16=None, ld16=None, hilo=False, out16_lo=0, a_lo_off=0, conv_stride=1, conv_no_pad_lo=False,
-             ln_stats_out=None, ln=None):
-        """ln_stats_out: fp32 [N/32, M, 2] — the epilogue leaves (sum, sum of squares) per row and 32-column chunk of an fp32 output;
+             ln_stats_out=None, ln=None, conv_up2=False):
+        """conv_up2: nearest x2 upsample folded into the convolution (ABI 14) — conv = (n_img, H, W, C) is the SOURCE image, M = n_img*H*W,
+        N = 4 * Cout (phase blocks), K = 4 * C, `out` / `out16` have the upsampled resolution (4 M rows, Cout columns).
+        ln_stats_out: fp32 [N/32, M, 2] — the epilogue leaves (sum, sum of squares) per row and 32-column chunk of an fp32 output;
         ln = (stats, colsum, eps): nn.LayerNorm folded into this GEMM — A holds the raw rows, Wt the gamma-scaled weights, stats what the
         GEMM that produced A's rows wrote (include/mvd_b200.h, ABI 13).
         out16: optional fp16 tensor (or column window of a wider one, row pitch ld16) that receives a copy of an fp32 output
@@ -104,6 +106,7 @@ class NativeOps:
             g.lda = lda if lda is not None else 0
             g.conv_stride = conv_stride
             g.conv_no_pad_lo = int(bool(conv_no_pad_lo))
+            g.conv_up2 = int(bool(conv_up2))
         else:
             g.a_mode = A_ROWMAJOR
             g.lda = lda if lda is not None else A.shape[-1]
@@ -141,15 +144,19 @@ class NativeOps:
         keep = (g, A, Wt, out, bias, rowbias, colscale, residual, qkv, ws, out16, ln_stats_out, ln)
         n_out = N // 2 if act == ACT_GEGLU else N
         a_bytes = (conv[0] * conv[1] * conv[2] * conv[3] * conv_stride * conv_stride if conv is not None else M * K) * 2
-        o_bytes = M * n_out * (4 if (qkv is None and out.dtype == torch.float32) else 2)
+        if conv_up2:
+            n_out = N // 4  # four phase blocks of Cout columns; 4 M output rows
+        o_bytes = (4 * M if conv_up2 else M) * n_out * (4 if (qkv is None and out.dtype == torch.float32) else 2)
         desc = (f"{'conv' if conv is not None else 'lin'} M{M} N{N} K{K} "
                 f"{'qkv' if qkv is not None else ('f32' if out.dtype == torch.float32 else 'f16')}"
                 f"{' res' if residual is not None else ''}{' act%d' % act if act else ''}{' sk' if split_k != 1 else ''}"
                 f"{' +f16' if out16 is not None else ''}{' hilo' if hilo else ''}{' s2' if conv_stride == 2 else ''}"
-                f"{' +st' if ln_stats_out is not None else ''}{' ln' if ln is not None else ''}")
+                f"{' +st' if ln_stats_out is not None else ''}{' ln' if ln is not None else ''}{' up2' if conv_up2 else ''}")
         sig = gemm_signature(conv is not None, M, N, K, "qkv" if qkv is not None else str(out.dtype).split(".")[-1], residual is not None, act,
-                             "+st" if ln_stats_out is not None else ("+ln" if ln is not None else ""))
-        meta = {"kernel": "gemm_tc_kernel", "flops": 2.0 * M * N * K, "executed_flops": 2.0 * M * N * K * (3 if hilo else 1), "shape": (M, N, K, split_k), "desc": desc, "sig": sig, "can_split": ws is not None,
+                             "+st" if ln_stats_out is not None else ("+ln" if ln is not None else ("+up" if conv_up2 else "")))
+        # algorithmic flops = those of the reference operation: the folded upsample convolution stands for conv3x3 over 4 M output pixels
+        # (2 * 4M * Cout * 9C = 4.5 M N K with N = 4 Cout, K = 4 C) and executes 2 M N K
+        meta = {"kernel": "gemm_tc_kernel", "flops": (4.5 if conv_up2 else 2.0) * M * N * K, "executed_flops": 2.0 * M * N * K * (3 if hilo else 1), "shape": (M, N, K, split_k), "desc": desc, "sig": sig, "can_split": ws is not None,
                 "bytes": a_bytes + N * K * 2 + o_bytes + (M * n_out * 4 if residual is not None else 0) + (M * n_out * 2 if out16 is not None else 0)
                 + (M * N // 4 if ln_stats_out is not None else 0) + (M * K // 4 if ln is not None else 0)}
         return self._bind("mvd_gemm_f16", (ctypes.byref(g),), keep, meta)

@@ -49,8 +49,13 @@ class TorchOpsDouble:
     def gemm(self, A, Wt, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, rowbias=None, rows_per_group=1,
              colscale=None, residual=None, ldr=0, act=ACT_NONE, conv=None, qkv=None, split_k=1, tile_n=0, ws=None, cta_pair=0,
              out16=None, ld16=None, hilo=False, out16_lo=0, a_lo_off=0, conv_stride=1, conv_no_pad_lo=False,
-             ln_stats_out=None, ln=None):
+             ln_stats_out=None, ln=None, conv_up2=False):
         assert A.dtype == torch.float16 and Wt.dtype == torch.float16
+        if conv_up2:
+            return self._gemm_up2(A, Wt, out, M, N, K, lda=lda, ldw=ldw, ldc=ldc, bias=bias, conv=conv, out16=out16, ld16=ld16, out16_lo=out16_lo,
+                                  plain=(rowbias is None and colscale is None and residual is None and act == ACT_NONE and qkv is None
+                                         and not hilo and conv_stride == 1 and not conv_no_pad_lo and ln is None and ln_stats_out is None),
+                                  tile_n=tile_n)
         # ABI 13 (LayerNorm between two GEMMs): the producer leaves per-chunk (sum, sum of squares), the consumer folds the normalisation
         assert ln_stats_out is None or (out.dtype == torch.float32 and qkv is None and act != ACT_GEGLU and N % 32 == 0 and split_k in (0, 1)
                                         and K <= 1536 and ln_stats_out.numel() >= (N // 32) * M * 2)
@@ -135,6 +140,41 @@ class TorchOpsDouble:
                 if out16_lo:
                     lo = torch.as_strided(out16, (M, N), (ld16_, 1), out16.storage_offset() + out16_lo)
                     lo.copy_((acc - acc.half().float()).half())
+        return self._call(fn)
+
+    def _gemm_up2(self, A, Wt, out, M, N, K, *, lda, ldw, ldc, bias, conv, out16, ld16, out16_lo, plain, tile_n):
+        """ABI 14: nearest x2 upsample folded into the convolution — four 2 x 2 phase convolutions of the SOURCE image."""
+        n_img, H, Wd, C = conv
+        Co = N // 4
+        assert plain and conv is not None and N % 4 == 0 and K == 4 * C and M == n_img * H * Wd and H & (H - 1) == 0 and Wd & (Wd - 1) == 0
+        assert tile_n == 0 or (tile_n % 32 == 0 and tile_n <= 256 and Co % tile_n == 0)
+        ldw_ = ldw if ldw is not None else Wt.shape[-1]
+
+        def fn():
+            W = Wt.reshape(-1)[: N * ldw_].reshape(N, ldw_)[:, :K].float()
+            pitch = lda if lda else C
+            x = torch.as_strided(A, (n_img, H, Wd, C), (H * Wd * pitch, Wd * pitch, pitch, 1), A.storage_offset()).float()
+            xp = F.pad(x, (0, 0, 1, 1, 1, 1))  # source pixel (y, x) at [y + 1, x + 1]
+            ldc_ = ldc if ldc is not None else out.shape[-1]
+            o = torch.as_strided(out, (n_img, 2 * H, 2 * Wd, Co), (4 * H * Wd * ldc_, 2 * Wd * ldc_, ldc_, 1), out.storage_offset())
+            res = torch.empty(n_img, 2 * H, 2 * Wd, Co)
+            for py in range(2):
+                for px in range(2):
+                    ph = 2 * py + px
+                    # taps (a, b): source pixel (y + py - 1 + a, x + px - 1 + b)
+                    cols = torch.cat([xp[:, py + a:py + a + H, px + b_:px + b_ + Wd, :] for a in range(2) for b_ in range(2)], dim=-1).reshape(M, K)
+                    acc = cols @ W[ph * Co:(ph + 1) * Co].t()
+                    if bias is not None:
+                        acc = acc + bias.reshape(-1)[ph * Co:(ph + 1) * Co]
+                    res[:, py::2, px::2, :] = acc.reshape(n_img, H, Wd, Co)
+            o.copy_(res.to(out.dtype))
+            if out16 is not None:
+                ld16_ = ld16 if ld16 is not None else out16.shape[-1]
+                o16 = torch.as_strided(out16, (n_img, 2 * H, 2 * Wd, Co), (4 * H * Wd * ld16_, 2 * Wd * ld16_, ld16_, 1), out16.storage_offset())
+                o16.copy_(res.half())
+                if out16_lo:
+                    lo = torch.as_strided(out16, (n_img, 2 * H, 2 * Wd, Co), (4 * H * Wd * ld16_, 2 * Wd * ld16_, ld16_, 1), out16.storage_offset() + out16_lo)
+                    lo.copy_((res - res.half().float()).half())
         return self._call(fn)
 
     def attn_self(self, q, k, vt, out, n_img, heads, seq, dhead, dpad, ldo, seq_valid=None):

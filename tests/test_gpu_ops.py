@@ -181,6 +181,38 @@ def test_conv3x3(nat, dbl, n, H, Cin, Cout):
              split_k=(0 if H <= 8 else 1), ws="ws")
 
 
+@pytest.mark.parametrize("n,H,C,Cout,tile,split,pair", [(16, 4, 1280, 1280, 0, 0, 0), (16, 4, 1280, 1280, 160, 2, 2), (16, 16, 640, 640, 160, 1, 2),
+                                                        (2, 16, 640, 640, 0, 1, 0), (3, 8, 64, 32, 0, 1, 1), (16, 4, 1280, 1280, 256, 3, 1),
+                                                        (2, 4, 1280, 1280, 256, 7, 1)])
+def test_conv3x3_behind_nearest_upsample_as_phase_convolutions(nat, dbl, n, H, C, Cout, tile, split, pair):
+    """ABI 14 (conv_up2): Upsample = nearest x2 + conv3x3 as four 2 x 2 phase convolutions of the source image in one launch — against
+    the emulation and against F.interpolate + F.conv2d in fp32; output rows interleave the phases, out16 into a column window"""
+    import torch.nn.functional as F
+    from mvdfusion_b200.engine import PackedWeights
+    g = torch.Generator().manual_seed(n * 1000 + H)
+    w = torch.randn(Cout, C, 3, 3, generator=g) * (9 * C) ** -0.5
+    bias = torch.randn(Cout, generator=g)
+    x = torch.randn(n, H, H, C, generator=g)
+    W = PackedWeights({"k.weight": w, "k.bias": bias}, dbl)
+    wp, bp = W.conv3_up2("k.weight"), W.f32_tiled("k.bias", 4)
+    M, Mo = n * H * H, n * 4 * H * H
+    x16 = x.half().reshape(M, C)
+    outs = {}
+    for side, ops, dev in (("cpu", dbl, "cpu"), ("gpu", nat, "cuda")):
+        out = torch.zeros(Mo, Cout, device=dev)
+        wide = torch.zeros(Mo, Cout + 64, dtype=torch.float16, device=dev)
+        kw = dict(tile_n=tile, split_k=split, cta_pair=pair, ws=torch.zeros(64 << 20, dtype=torch.uint8, device=dev)) if side == "gpu" else {}
+        ops.gemm(x16.to(dev), wp.to(dev), out, M, 4 * Cout, 4 * C, conv=(n, H, H, C), conv_up2=True, bias=bp.to(dev), ldc=Cout,
+                 out16=wide[:, 64:], ld16=Cout + 64, **kw)(torch.cuda.current_stream().cuda_stream if side == "gpu" else None)
+        outs[side] = (out, wide)
+    torch.cuda.synchronize()
+    _close(outs["gpu"][0], outs["cpu"][0], 2e-3, "phase convolutions")
+    _close(outs["gpu"][1], outs["cpu"][1], 2e-3, "fp16 copy")
+    assert (outs["gpu"][1][:, :64] == 0).all()
+    ref = F.conv2d(F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="nearest"), w, bias, padding=1).permute(0, 2, 3, 1).reshape(Mo, Cout)
+    assert rel(outs["gpu"][0].cpu(), ref) < 1e-3
+
+
 def _close(a, b, tol, what):
     a, b = a.float().cpu(), b.float().cpu()
     assert torch.isfinite(a).all(), f"{what}: non-finite values"

@@ -186,6 +186,34 @@ def test_step_program_has_no_layernorm_passes(ops_double, D, monkeypatch):
     assert rel_l2(eps_fold, eps_plain) < 2 * TOL
 
 
+def test_step_program_has_no_upsample_passes(ops_double, monkeypatch):
+    """Upsample (nearest x2 + conv3x3, openaimodel.py:107-119) runs as four 2 x 2 phase convolutions of the source image in one launch
+    (mvd_gemm_args.conv_up2, ABI 14): no upsample2x launch and no upsampled tensor in the step program; the MVD_NO_FOLD_UP program is
+    equally close to the fp32 oracle."""
+    sc = synthetic.scene_inputs(2, 32)
+    de, _ = synthetic.step_noises(2, 1, 32, 1)
+    t = torch.full((2,), 501, dtype=torch.long)
+    args = (sc["x_T"], cams_of(sc["cams"]), sc["input_latents"], cams_of(sc["in_cams"]), sc["clip_v_embed"], t)
+
+    def count(plan, name):
+        return sum(1 for c in plan.core_prog.calls if getattr(c, "name", "") == name)
+
+    m = build_model(64, 8, D=1, S=32)
+    eps_fold = m.apply_model(*args, cfg_scale=2.5, depth_eps=de[0])
+    plan = m.step_plan(2, 32, 1, use_cfg=True)
+    monkeypatch.setenv("MVD_NO_FOLD_UP", "1")
+    m2 = build_model(64, 8, D=1, S=32)
+    eps_plain = m2.apply_model(*args, cfg_scale=2.5, depth_eps=de[0])
+    plan2 = m2.step_plan(2, 32, 1, use_cfg=True)
+    assert count(plan, "upsample2x") == 0 and count(plan2, "upsample2x") == 3 and count(plan, "_gemm_up2") == 3
+    assert len(plan2.core_prog) - len(plan.core_prog) == 3
+    sd = state_dict_cpu(m)
+    ref = O.apply_model(sd, sc["x_T"], sc["cams"], sc["input_latents"], sc["in_cams"], sc["clip_v_embed"], t, de[0],
+                        unet_cfg=unet_cfg_of(m), D=1, cfg_scale=2.5)
+    e_fold, e_plain = rel_l2(eps_fold, ref), rel_l2(eps_plain, ref)
+    assert e_fold < TOL and e_fold < 1.1 * e_plain + 1e-5
+
+
 def test_weight_cache_follows_parameter_updates(ops_double, model):
     m, sd = model
     st = m.unet_model.unet_model.input_blocks[1][1]
