@@ -555,7 +555,9 @@ def run_train(args):
               "unit": "scenes/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
               "vs_baseline": None, "dtype": "f16 operands / f32 accumulate, f32 master weights + gradients, bf16-compressed all-reduce", "data": "synthetic",
               "config": {"workload": f"BASELINE configs[3]: train fwd+bwd, N={n} views {8 * S}^2, D=3, all {n_train / 1e6:.1f} M parameters trainable, DDP x{world}",
-                         "native": "contractions (forward, dgrad, wgrad) on mvd_gemm_f16; norms / softmax / gather backward via ATen (first slice)"},
+                         "native": ("contractions (forward, dgrad, wgrad) on mvd_gemm_f16; norms / activations via ATen (MVD_TRAIN_ATEN_POINTWISE=1); attention cores / gather via ATen"
+                                    if os.environ.get("MVD_TRAIN_ATEN_POINTWISE") == "1" else
+                                    "contractions (forward, dgrad, wgrad) on mvd_gemm_f16; LayerNorm / GroupNorm+SiLU / GELU / SiLU / GEGLU forward + backward on csrc/train.cu (ABI 15); attention cores / gather via ATen")},
               "gpu_launches": int(launches), "loss": float(loss), "finite": bool(torch.isfinite(loss)),
               "achieved_tflops_per_gpu": round(3 * f_fwd * K / (ms * 1e-3) / 1e12, 2)})
     if world > 1:

@@ -303,6 +303,33 @@ int mvd_gridattn_dit_f16(const mvd_dit_args* args, void* stream);
 typedef struct mvd_fold_job { const void* w; const float* gate; const float* bias; void* w_out; float* b_out; int32_t N, K; } mvd_fold_job;
 int mvd_dit_fold_gates(const mvd_fold_job* jobs, int32_t n_jobs, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training (ABI 15): fp32 forward passes that keep what their backward needs, and the backward passes, of
+ * the normalisation / activation layers between the GEMMs.  In the reference they are ATen kernels recorded by autograd and
+ * replayed by loss.backward() (train.py:90-94; mvdfusion/viewfusion_zero_depth_rgb.py:362-392).  Activations are fp32 [rows, C]
+ * channels-last rows; every call zeroes and then accumulates the reductions it owns (dgamma, dbeta, ws) on `stream`.
+ * ---------------------------------------------------------------------------------------------- */
+/* nn.LayerNorm (external/sd1/ldm/modules/attention.py:210-212; timm LayerNorm + adaLN modulate with gamma = 1 + scale, beta = shift,
+ * mvdfusion/view_attn_efficient2.py:61-66).  y = (x - mean) * rstd * gamma + beta; stats fp32 [rows, 2] = (mean, rstd).
+ * gamma = beta = NULL: no affine part.  C % 4 == 0. */
+int mvd_layernorm_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* stats, int32_t rows, int32_t C,
+                          float eps, void* stream);
+/* dx [rows, C]; dgamma / dbeta fp32 [C] (NULL together when the layer has no affine part).  gamma may be NULL (= 1). */
+int mvd_layernorm_bwd_f32(const float* dy, const float* x, const float* gamma, const float* stats, float* dx, float* dgamma,
+                          float* dbeta, int32_t rows, int32_t C, void* stream);
+/* GroupNorm32 (+ SiLU) on x fp32 [n_img, hw, C], 32 groups (external/sd1/ldm/modules/diffusionmodules/util.py:204-216,
+ * openaimodel.py:199-203,224-228; attention.py:242).  stats fp32 [n_img, 32, 2] = (mean, rstd) per (image, group), written by the
+ * forward and read by the backward; ws: scratch of n_img * 32 * 24 bytes, 8-byte aligned (fp64 group sums). */
+int mvd_groupnorm_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* stats, void* ws, int32_t n_img,
+                          int32_t hw, int32_t C, float eps, int32_t apply_silu, void* stream);
+int mvd_groupnorm_bwd_f32(const float* dy, const float* x, const float* gamma, const float* beta, const float* stats, float* dx,
+                          float* dgamma, float* dbeta, void* ws, int32_t n_img, int32_t hw, int32_t C, int32_t apply_silu, void* stream);
+/* mode 1 GELU (exact erf), 2 SiLU: y[i] = act(x[i]) over rows * cols elements; mode 3 GEGLU: x [rows, 2 cols] = (a | gate),
+ * y [rows, cols] = a * gelu(gate) (external/sd1/ldm/modules/attention.py:42-44; cols % 4 == 0).
+ * Backward: dx has x's shape; GEGLU: dx = (dy * gelu(gate) | dy * a * gelu'(gate)). */
+int mvd_act_fwd_f32(const float* x, float* y, long long rows, int32_t cols, int32_t mode, void* stream);
+int mvd_act_bwd_f32(const float* dy, const float* x, float* dx, long long rows, int32_t cols, int32_t mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

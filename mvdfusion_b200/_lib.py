@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_float, c_int32, c_longlong, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # MVD_B200_LIB: another build of the same library (e.g. the instrumented `make trace` one); it must exist — there is no fallback
 LIB_PATH = os.environ.get("MVD_B200_LIB") or os.path.join(_HERE, "libmvd_b200.so")
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 
 class GemmArgs(ctypes.Structure):
@@ -100,6 +100,12 @@ SIGNATURES = {
     "mvd_view_pool_f16": [vp, vp, vp, vp, i32, i32, i32, vp],
     "mvd_frustum_pool_f16": [vp, vp, i32, i32, i32, i32, i32, vp],
     "mvd_pixel_cross_attn_f16": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "mvd_layernorm_fwd_f32": [vp, vp, vp, vp, vp, i32, i32, f32, vp],
+    "mvd_layernorm_bwd_f32": [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp],
+    "mvd_groupnorm_fwd_f32": [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp],
+    "mvd_groupnorm_bwd_f32": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
+    "mvd_act_fwd_f32": [vp, vp, i64, i32, i32, vp],
+    "mvd_act_bwd_f32": [vp, vp, vp, i64, i32, i32, vp],
 }
 _RESTYPE = {"mvd_last_error": c_char_p, "mvd_launch_count": c_longlong}
 

@@ -1,0 +1,457 @@
+// Training-side normalisation / activation kernels (second slice): the fp32 forward passes that save what
+// their backward needs, and the backward passes, of the non-contraction layers between the GEMMs of mvdfusion_b200/training.py —
+// nn.LayerNorm (external/sd1/ldm/modules/attention.py:210-212; timm LayerNorm + adaLN modulate, mvdfusion/view_attn_efficient2.py:61-66),
+// GroupNorm32 (+ SiLU) on channels-last rows (external/sd1/ldm/modules/diffusionmodules/util.py:204-216, openaimodel.py:199-203,224-228),
+// GELU / SiLU / GEGLU (external/sd1/ldm/modules/attention.py:42-44).  In the reference these are ATen kernels recorded by autograd
+// (train.py:90-94, loss.backward()).
+//
+// All of them are HBM-bound streaming passes: activations are fp32 [rows, C] (row = (image*H + y)*W + x), consecutive threads read
+// consecutive channels, every per-channel / per-group constant is loaded once per thread and kept in registers over the pixel loop.
+// Reductions over rows (dgamma, dbeta, group sums) end in atomics on small zero-initialised vectors: fp32 for the parameter
+// gradients, fp64 for the (sum, sum of squares) of a group, whose difference is the variance.
+// The launches are plain stream launches (no programmatic dependent launch): in the training graph their neighbours are ATen kernels.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.h"
+
+namespace mvd {
+namespace {
+
+constexpr int GN_PX = 16;  // pixels per CTA of the GroupNorm passes
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
+__device__ __forceinline__ float silu_d(float x) {
+  const float s = sigmoid_f(x);
+  return s * (1.f + x * (1.f - s));
+}
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_d(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.39894228040143268f * expf(-0.5f * x * x);
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm
+// one warp per row; the row is read three times (mean, centred variance, output) out of L1 / L2
+__global__ void ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b, float* __restrict__ y,
+                              float* __restrict__ stats, int rows, int C, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * C);
+  const int n4 = C >> 2;
+  float s = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = xr[i];
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = xr[i];
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  if (lane == 0) {
+    stats[2 * static_cast<size_t>(row)] = mean;
+    stats[2 * static_cast<size_t>(row) + 1] = rstd;
+  }
+  float4* yr = reinterpret_cast<float4*>(y + static_cast<size_t>(row) * C);
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = xr[i];
+    float4 ga = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g != nullptr) {
+      ga = __ldg(reinterpret_cast<const float4*>(g) + i);
+      be = __ldg(reinterpret_cast<const float4*>(b) + i);
+    }
+    yr[i] = make_float4((v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y, (v.z - mean) * rstd * ga.z + be.z,
+                        (v.w - mean) * rstd * ga.w + be.w);
+  }
+}
+
+// dx = rstd * (g - mean_C(g) - xhat * mean_C(g * xhat)),  g = dy * gamma,  xhat = (x - mean) * rstd
+__global__ void ln_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ g,
+                                 const float* __restrict__ stats, float* __restrict__ dx, int rows, int C) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float mean = stats[2 * static_cast<size_t>(row)], rstd = stats[2 * static_cast<size_t>(row) + 1];
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * C);
+  const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * C);
+  const int n4 = C >> 2;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = xr[i], d = dr[i];
+    const float4 ga = g != nullptr ? __ldg(reinterpret_cast<const float4*>(g) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float g0 = d.x * ga.x, g1 = d.y * ga.y, g2 = d.z * ga.z, g3 = d.w * ga.w;
+    s1 += (g0 + g1) + (g2 + g3);
+    s2 += g0 * ((v.x - mean) * rstd) + g1 * ((v.y - mean) * rstd) + g2 * ((v.z - mean) * rstd) + g3 * ((v.w - mean) * rstd);
+  }
+  s1 = warp_sum(s1) / C;
+  s2 = warp_sum(s2) / C;
+  float4* or_ = reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * C);
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = xr[i], d = dr[i];
+    const float4 ga = g != nullptr ? __ldg(reinterpret_cast<const float4*>(g) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+    or_[i] = make_float4(rstd * (d.x * ga.x - s1 - (v.x - mean) * rstd * s2), rstd * (d.y * ga.y - s1 - (v.y - mean) * rstd * s2),
+                         rstd * (d.z * ga.z - s1 - (v.z - mean) * rstd * s2), rstd * (d.w * ga.w - s1 - (v.w - mean) * rstd * s2));
+  }
+}
+
+// dgamma[c] += sum_r dy[r, c] * xhat[r, c], dbeta[c] += sum_r dy[r, c] over one chunk of rows; block (32 columns, 8 rows in flight)
+__global__ void ln_bwd_param_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ stats,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C, int rows_per_chunk) {
+  __shared__ float sa[8][33], sb[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(rows, r0 + rows_per_chunk);
+  float a = 0.f, b = 0.f;
+  if (c < C) {
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + r);
+      const size_t o = static_cast<size_t>(r) * C + c;
+      const float d = dy[o];
+      a += d;
+      b += d * ((x[o] - st.x) * st.y);
+    }
+  }
+  sa[ty][tx] = a;
+  sb[ty][tx] = b;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+      a += sa[j][tx];
+      b += sb[j][tx];
+    }
+    atomicAdd(dbeta + c, a);
+    atomicAdd(dgamma + c, b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- GroupNorm (32 groups, channels-last)
+// grid (pixel chunks, channel blocks, images); thread = one channel, loop over the chunk's pixels
+__global__ void gn_sums_kernel(const float* __restrict__ x, double* __restrict__ ws, int hw, int C, int cpg) {
+  __shared__ double sh[2][256];
+  const int tid = threadIdx.x, n = blockIdx.z;
+  const int cb = blockIdx.y * blockDim.x;
+  const int c = cb + tid;
+  const int p0 = blockIdx.x * GN_PX, p1 = min(hw, p0 + GN_PX);
+  const int g0 = cb / cpg;
+  sh[0][tid] = 0.0;
+  sh[1][tid] = 0.0;
+  __syncthreads();
+  if (c < C) {
+    const float* xp = x + (static_cast<size_t>(n) * hw + p0) * C + c;
+    float s = 0.f, q = 0.f;
+    for (int p = p0; p < p1; ++p, xp += C) {
+      const float v = *xp;
+      s += v;
+      q += v * v;
+    }
+    const int lg = c / cpg - g0;
+    atomicAdd(&sh[0][lg], static_cast<double>(s));
+    atomicAdd(&sh[1][lg], static_cast<double>(q));
+  }
+  __syncthreads();
+  const int cend = min(C, cb + static_cast<int>(blockDim.x));
+  const int nl = (cend - 1) / cpg - g0 + 1;
+  if (tid < nl) {
+    double* w = ws + (static_cast<size_t>(n) * 32 + g0 + tid) * 2;
+    atomicAdd(w, sh[0][tid]);
+    atomicAdd(w + 1, sh[1][tid]);
+  }
+}
+
+// (sum, sum of squares) -> (mean, rstd); m = elements per group
+__global__ void gn_finalize_kernel(const double* __restrict__ ws, float* __restrict__ stats, int count, double m, double eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const double mean = ws[2 * i] / m;
+  double var = ws[2 * i + 1] / m - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  stats[2 * i] = static_cast<float>(mean);
+  stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + eps));
+}
+
+__global__ void gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ stats, float* __restrict__ y, int hw, int C, int cpg, int silu) {
+  const int n = blockIdx.z;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int p0 = blockIdx.x * GN_PX, p1 = min(hw, p0 + GN_PX);
+  const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + n * 32 + c / cpg);
+  const float sc = st.y * __ldg(gamma + c);
+  const float be = __ldg(beta + c);
+  size_t o = (static_cast<size_t>(n) * hw + p0) * C + c;
+  for (int p = p0; p < p1; ++p, o += C) {
+    float v = (x[o] - st.x) * sc + be;
+    if (silu) v = silu_f(v);
+    y[o] = v;
+  }
+}
+
+// per channel: a = sum dz, b = sum dz * xhat over the chunk -> dbeta, dgamma (fp32 atomics) and the group's
+// (sum dz * gamma, sum dz * gamma * xhat) (fp64 atomics);  dz = dy * silu'(xhat * gamma + beta) or dy
+__global__ void gn_bwd_sums_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ stats, float* __restrict__ dgamma,
+                                   float* __restrict__ dbeta, double* __restrict__ ws, int hw, int C, int cpg, int silu) {
+  __shared__ double sh[2][256];
+  const int tid = threadIdx.x, n = blockIdx.z;
+  const int cb = blockIdx.y * blockDim.x;
+  const int c = cb + tid;
+  const int p0 = blockIdx.x * GN_PX, p1 = min(hw, p0 + GN_PX);
+  const int g0 = cb / cpg;
+  sh[0][tid] = 0.0;
+  sh[1][tid] = 0.0;
+  __syncthreads();
+  if (c < C) {
+    const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + n * 32 + c / cpg);
+    const float ga = __ldg(gamma + c), be = __ldg(beta + c);
+    size_t o = (static_cast<size_t>(n) * hw + p0) * C + c;
+    float a = 0.f, b = 0.f;
+    for (int p = p0; p < p1; ++p, o += C) {
+      const float xh = (x[o] - st.x) * st.y;
+      float dz = dy[o];
+      if (silu) dz *= silu_d(xh * ga + be);
+      a += dz;
+      b += dz * xh;
+    }
+    atomicAdd(dbeta + c, a);
+    atomicAdd(dgamma + c, b);
+    const int lg = c / cpg - g0;
+    atomicAdd(&sh[0][lg], static_cast<double>(a * ga));
+    atomicAdd(&sh[1][lg], static_cast<double>(b * ga));
+  }
+  __syncthreads();
+  const int cend = min(C, cb + static_cast<int>(blockDim.x));
+  const int nl = (cend - 1) / cpg - g0 + 1;
+  if (tid < nl) {
+    double* w = ws + (static_cast<size_t>(n) * 32 + g0 + tid) * 2;
+    atomicAdd(w, sh[0][tid]);
+    atomicAdd(w + 1, sh[1][tid]);
+  }
+}
+
+// group sums / m as fp32 pairs behind the fp64 accumulators
+__global__ void gn_bwd_finalize_kernel(const double* __restrict__ ws, float* __restrict__ red, int count, double m) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  red[2 * i] = static_cast<float>(ws[2 * i] / m);
+  red[2 * i + 1] = static_cast<float>(ws[2 * i + 1] / m);
+}
+
+// dx = rstd * (dz * gamma - s1 / m - xhat * s2 / m)
+__global__ void gn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ stats, const float* __restrict__ red,
+                                    float* __restrict__ dx, int hw, int C, int cpg, int silu) {
+  const int n = blockIdx.z;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int p0 = blockIdx.x * GN_PX, p1 = min(hw, p0 + GN_PX);
+  const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + n * 32 + c / cpg);
+  const float2 rd = __ldg(reinterpret_cast<const float2*>(red) + n * 32 + c / cpg);
+  const float ga = __ldg(gamma + c), be = __ldg(beta + c);
+  size_t o = (static_cast<size_t>(n) * hw + p0) * C + c;
+  for (int p = p0; p < p1; ++p, o += C) {
+    const float xh = (x[o] - st.x) * st.y;
+    float dz = dy[o];
+    if (silu) dz *= silu_d(xh * ga + be);
+    dx[o] = st.y * (dz * ga - rd.x - xh * rd.y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- activations
+enum { ACT_GELU = 1, ACT_SILU = 2, ACT_GEGLU = 3 };
+
+template <int MODE, bool BWD>
+__device__ __forceinline__ float act1(float x, float dy) {
+  if (MODE == ACT_GELU) return BWD ? dy * gelu_d(x) : gelu_f(x);
+  return BWD ? dy * silu_d(x) : silu_f(x);
+}
+
+// y[i] = act(x[i]) (BWD: dx[i] = dy[i] * act'(x[i])); n4 float4 elements + a scalar tail
+template <int MODE, bool BWD>
+__global__ void act_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ out, long long n, int vec) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n4 = vec ? (n >> 2) : 0;
+  for (long long i = t; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (BWD) d = reinterpret_cast<const float4*>(dy)[i];
+    reinterpret_cast<float4*>(out)[i] =
+        make_float4(act1<MODE, BWD>(v.x, d.x), act1<MODE, BWD>(v.y, d.y), act1<MODE, BWD>(v.z, d.z), act1<MODE, BWD>(v.w, d.w));
+  }
+  for (long long i = (n4 << 2) + t; i < n; i += stride) out[i] = act1<MODE, BWD>(x[i], BWD ? dy[i] : 0.f);
+}
+
+// GEGLU: x [rows, 2 cols] = (a | gate); forward y [rows, cols] = a * gelu(gate);
+// backward dx [rows, 2 cols] = (dy * gelu(gate) | dy * a * gelu'(gate)).  One CTA per row, float4 columns.
+template <bool BWD>
+__global__ void geglu_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ out, int cols) {
+  const size_t row = blockIdx.x;
+  const float4* a4 = reinterpret_cast<const float4*>(x + row * 2 * cols);
+  const float4* g4 = reinterpret_cast<const float4*>(x + row * 2 * cols + cols);
+  const int n4 = cols >> 2;
+  if (!BWD) {
+    float4* y4 = reinterpret_cast<float4*>(out + row * cols);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 a = a4[i], g = g4[i];
+      y4[i] = make_float4(a.x * gelu_f(g.x), a.y * gelu_f(g.y), a.z * gelu_f(g.z), a.w * gelu_f(g.w));
+    }
+  } else {
+    const float4* d4 = reinterpret_cast<const float4*>(dy + row * cols);
+    float4* da4 = reinterpret_cast<float4*>(out + row * 2 * cols);
+    float4* dg4 = reinterpret_cast<float4*>(out + row * 2 * cols + cols);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 a = a4[i], g = g4[i], d = d4[i];
+      da4[i] = make_float4(d.x * gelu_f(g.x), d.y * gelu_f(g.y), d.z * gelu_f(g.z), d.w * gelu_f(g.w));
+      dg4[i] = make_float4(d.x * a.x * gelu_d(g.x), d.y * a.y * gelu_d(g.y), d.z * a.z * gelu_d(g.z), d.w * a.w * gelu_d(g.w));
+    }
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+struct GnGeometry {
+  dim3 grid, block;
+  int cpg;
+};
+inline GnGeometry gn_geometry(int n_img, int hw, int C) {
+  GnGeometry g;
+  const int bd = C >= 256 ? 256 : ((C + 31) / 32) * 32;
+  g.block = dim3(bd);
+  g.grid = dim3((hw + GN_PX - 1) / GN_PX, (C + bd - 1) / bd, n_img);
+  g.cpg = C / 32;
+  return g;
+}
+
+template <bool BWD>
+int act_launch(const char* name, const float* x, const float* dy, float* out, long long rows, int32_t cols, int32_t mode, cudaStream_t stream) {
+  if (!x || !out || (BWD && !dy)) return set_error(MVD_EINVAL, "%s: null pointer", name);
+  if (rows <= 0 || cols <= 0) return set_error(MVD_EINVAL, "%s: empty input", name);
+  if (mode == ACT_GEGLU) {
+    if ((cols & 3) != 0 || !aligned16(x) || !aligned16(out) || (BWD && !aligned16(dy)))
+      return set_error(MVD_EALIGN, "%s: GEGLU needs cols %% 4 == 0 and 16-byte aligned pointers", name);
+    if (rows > 2147483647LL) return set_error(MVD_EINVAL, "%s: too many rows", name);
+    geglu_kernel<BWD><<<static_cast<unsigned>(rows), 256, 0, stream>>>(x, dy, out, cols);
+  } else if (mode == ACT_GELU || mode == ACT_SILU) {
+    const long long n = rows * cols;
+    const int vec = aligned16(x) && aligned16(out) && (!BWD || aligned16(dy));
+    const long long work = vec ? (n + 3) / 4 : n;
+    long long blocks = (work + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (mode == ACT_GELU)
+      act_kernel<ACT_GELU, BWD><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, dy, out, n, vec);
+    else
+      act_kernel<ACT_SILU, BWD><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, dy, out, n, vec);
+  } else {
+    return set_error(MVD_EINVAL, "%s: mode must be 1 (GELU), 2 (SiLU) or 3 (GEGLU)", name);
+  }
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+}  // namespace
+}  // namespace mvd
+
+using namespace mvd;
+
+extern "C" int mvd_layernorm_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* stats, int32_t rows,
+                                     int32_t C, float eps, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !y || !stats) return set_error(MVD_EINVAL, "mvd_layernorm_fwd_f32: null pointer");
+  if ((gamma == nullptr) != (beta == nullptr)) return set_error(MVD_EINVAL, "mvd_layernorm_fwd_f32: gamma and beta go together");
+  if (rows <= 0 || C <= 0 || (C & 3) != 0) return set_error(MVD_EINVAL, "mvd_layernorm_fwd_f32: C must be a multiple of 4");
+  if (!aligned16(x) || !aligned16(y) || !aligned16(gamma) || !aligned16(beta) || (reinterpret_cast<uintptr_t>(stats) & 7))
+    return set_error(MVD_EALIGN, "mvd_layernorm_fwd_f32: x / y / gamma / beta must be 16-byte, stats 8-byte aligned");
+  ln_fwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, stats, rows, C, eps);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_layernorm_bwd_f32(const float* dy, const float* x, const float* gamma, const float* stats, float* dx, float* dgamma,
+                                     float* dbeta, int32_t rows, int32_t C, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!dy || !x || !stats || !dx) return set_error(MVD_EINVAL, "mvd_layernorm_bwd_f32: null pointer");
+  if ((dgamma == nullptr) != (dbeta == nullptr)) return set_error(MVD_EINVAL, "mvd_layernorm_bwd_f32: dgamma and dbeta go together");
+  if (rows <= 0 || C <= 0 || (C & 3) != 0) return set_error(MVD_EINVAL, "mvd_layernorm_bwd_f32: C must be a multiple of 4");
+  if (!aligned16(dy) || !aligned16(x) || !aligned16(dx) || !aligned16(gamma) || (reinterpret_cast<uintptr_t>(stats) & 7))
+    return set_error(MVD_EALIGN, "mvd_layernorm_bwd_f32: dy / x / dx / gamma must be 16-byte, stats 8-byte aligned");
+  ln_bwd_dx_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(dy, x, gamma, stats, dx, rows, C);
+  count_launch();
+  if (dgamma != nullptr) {
+    MVD_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, stream));
+    MVD_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, sizeof(float) * C, stream));
+    int rpc = (rows + 127) / 128;
+    if (rpc < 64) rpc = 64;
+    ln_bwd_param_kernel<<<dim3((C + 31) / 32, (rows + rpc - 1) / rpc), dim3(32, 8), 0, stream>>>(dy, x, stats, dgamma, dbeta, rows, C, rpc);
+    count_launch();
+  }
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_groupnorm_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* stats, void* ws,
+                                     int32_t n_img, int32_t hw, int32_t C, float eps, int32_t apply_silu, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !gamma || !beta || !y || !stats || !ws) return set_error(MVD_EINVAL, "mvd_groupnorm_fwd_f32: null pointer");
+  if (n_img <= 0 || hw <= 0 || C <= 0 || (C % 32) != 0 || n_img > 65535)
+    return set_error(MVD_EINVAL, "mvd_groupnorm_fwd_f32: C must be a multiple of 32 (32 groups), n_img <= 65535");
+  if ((reinterpret_cast<uintptr_t>(ws) & 7) || (reinterpret_cast<uintptr_t>(stats) & 7))
+    return set_error(MVD_EALIGN, "mvd_groupnorm_fwd_f32: ws / stats must be 8-byte aligned");
+  const GnGeometry g = gn_geometry(n_img, hw, C);
+  const int count = n_img * 32;
+  double* sums = static_cast<double*>(ws);
+  MVD_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * count, stream));
+  gn_sums_kernel<<<g.grid, g.block, 0, stream>>>(x, sums, hw, C, g.cpg);
+  gn_finalize_kernel<<<(count + 127) / 128, 128, 0, stream>>>(sums, stats, count, static_cast<double>(hw) * g.cpg, static_cast<double>(eps));
+  gn_apply_kernel<<<g.grid, g.block, 0, stream>>>(x, gamma, beta, stats, y, hw, C, g.cpg, apply_silu);
+  count_launch(3);
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_groupnorm_bwd_f32(const float* dy, const float* x, const float* gamma, const float* beta, const float* stats,
+                                     float* dx, float* dgamma, float* dbeta, void* ws, int32_t n_img, int32_t hw, int32_t C,
+                                     int32_t apply_silu, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!dy || !x || !gamma || !beta || !stats || !dx || !dgamma || !dbeta || !ws)
+    return set_error(MVD_EINVAL, "mvd_groupnorm_bwd_f32: null pointer");
+  if (n_img <= 0 || hw <= 0 || C <= 0 || (C % 32) != 0 || n_img > 65535)
+    return set_error(MVD_EINVAL, "mvd_groupnorm_bwd_f32: C must be a multiple of 32 (32 groups), n_img <= 65535");
+  if ((reinterpret_cast<uintptr_t>(ws) & 7) || (reinterpret_cast<uintptr_t>(stats) & 7))
+    return set_error(MVD_EALIGN, "mvd_groupnorm_bwd_f32: ws / stats must be 8-byte aligned");
+  const GnGeometry g = gn_geometry(n_img, hw, C);
+  const int count = n_img * 32;
+  double* sums = static_cast<double*>(ws);
+  float* red = reinterpret_cast<float*>(sums + 2 * static_cast<size_t>(count));
+  MVD_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * count, stream));
+  MVD_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, stream));
+  MVD_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, sizeof(float) * C, stream));
+  gn_bwd_sums_kernel<<<g.grid, g.block, 0, stream>>>(dy, x, gamma, beta, stats, dgamma, dbeta, sums, hw, C, g.cpg, apply_silu);
+  gn_bwd_finalize_kernel<<<(count + 127) / 128, 128, 0, stream>>>(sums, red, count, static_cast<double>(hw) * g.cpg);
+  gn_bwd_apply_kernel<<<g.grid, g.block, 0, stream>>>(dy, x, gamma, beta, stats, red, dx, hw, C, g.cpg, apply_silu);
+  count_launch(3);
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_act_fwd_f32(const float* x, float* y, long long rows, int32_t cols, int32_t mode, void* stream_) {
+  return act_launch<false>("mvd_act_fwd_f32", x, nullptr, y, rows, cols, mode, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mvd_act_bwd_f32(const float* dy, const float* x, float* dx, long long rows, int32_t cols, int32_t mode, void* stream_) {
+  return act_launch<true>("mvd_act_bwd_f32", x, dy, dx, rows, cols, mode, static_cast<cudaStream_t>(stream_));
+}

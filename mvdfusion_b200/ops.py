@@ -13,6 +13,7 @@ from . import _lib
 
 A_ROWMAJOR, A_CONV3X3 = 0, 1
 ACT_NONE, ACT_GELU, ACT_SILU, ACT_GEGLU = 0, 1, 2, 3
+GN_WS_BYTES_PER_GROUP = 24   # mvd_groupnorm_{fwd,bwd}_f32 scratch: n_img * 32 groups * (2 fp64 sums + 2 fp32 means)
 OUT_F32, OUT_F16, OUT_QKV_HEADS = 0, 1, 2
 
 
@@ -342,3 +343,46 @@ class NativeOps:
     def pixel_cross_attn(self, q, kv, out, M, D, heads, dhead):
         return self._bind("mvd_pixel_cross_attn_f16", (_ptr(q, torch.float16), _ptr(kv, torch.float16),
                                                        _ptr(out, torch.float16), M, D, heads, dhead), (q, kv, out))
+
+    # ------------------------------------------------------------------ training (ABI 15): fp32 passes with saved statistics + backward
+    def layernorm_fwd(self, x, gamma, beta, y, stats, rows, C, eps):
+        """y fp32 [rows, C], stats fp32 [rows, 2] = (mean, rstd); gamma = beta = None: no affine part"""
+        return self._bind("mvd_layernorm_fwd_f32", (_ptr(x, torch.float32), _ptr(gamma, torch.float32), _ptr(beta, torch.float32),
+                                                    _ptr(y, torch.float32), _ptr(stats, torch.float32), rows, C, eps),
+                          (x, gamma, beta, y, stats), {"kernel": "train_layernorm", "desc": f"rows{rows} C{C}", "bytes": 8.0 * rows * C})
+
+    def layernorm_bwd(self, dy, x, gamma, stats, dx, dgamma, dbeta, rows, C):
+        return self._bind("mvd_layernorm_bwd_f32", (_ptr(dy, torch.float32), _ptr(x, torch.float32), _ptr(gamma, torch.float32),
+                                                    _ptr(stats, torch.float32), _ptr(dx, torch.float32), _ptr(dgamma, torch.float32),
+                                                    _ptr(dbeta, torch.float32), rows, C),
+                          (dy, x, gamma, stats, dx, dgamma, dbeta), {"kernel": "train_layernorm", "desc": f"bwd rows{rows} C{C}",
+                                                                     "bytes": (12.0 + (8.0 if dgamma is not None else 0.0)) * rows * C})
+
+    def groupnorm_fwd(self, x, gamma, beta, y, stats, ws, n_img, hw, C, eps, silu):
+        """x, y fp32 [n_img, hw, C]; stats fp32 [n_img, 32, 2]; ws: uint8 scratch of n_img * 32 * GN_WS_BYTES_PER_GROUP bytes"""
+        if ws.numel() < n_img * 32 * GN_WS_BYTES_PER_GROUP:
+            raise MvdError("groupnorm_fwd: workspace too small")
+        return self._bind("mvd_groupnorm_fwd_f32", (_ptr(x, torch.float32), _ptr(gamma, torch.float32), _ptr(beta, torch.float32),
+                                                    _ptr(y, torch.float32), _ptr(stats, torch.float32), _ptr(ws, torch.uint8), n_img, hw, C,
+                                                    eps, int(silu)),
+                          (x, gamma, beta, y, stats, ws), {"kernel": "train_groupnorm", "desc": f"img{n_img} hw{hw} C{C}", "bytes": 12.0 * n_img * hw * C})
+
+    def groupnorm_bwd(self, dy, x, gamma, beta, stats, dx, dgamma, dbeta, ws, n_img, hw, C, silu):
+        if ws.numel() < n_img * 32 * GN_WS_BYTES_PER_GROUP:
+            raise MvdError("groupnorm_bwd: workspace too small")
+        return self._bind("mvd_groupnorm_bwd_f32", (_ptr(dy, torch.float32), _ptr(x, torch.float32), _ptr(gamma, torch.float32),
+                                                    _ptr(beta, torch.float32), _ptr(stats, torch.float32), _ptr(dx, torch.float32),
+                                                    _ptr(dgamma, torch.float32), _ptr(dbeta, torch.float32), _ptr(ws, torch.uint8),
+                                                    n_img, hw, C, int(silu)),
+                          (dy, x, gamma, beta, stats, dx, dgamma, dbeta, ws),
+                          {"kernel": "train_groupnorm", "desc": f"bwd img{n_img} hw{hw} C{C}", "bytes": 20.0 * n_img * hw * C})
+
+    def act_fwd(self, x, y, rows, cols, mode):
+        """mode ACT_GELU / ACT_SILU: elementwise over rows * cols; ACT_GEGLU: x [rows, 2 cols] -> y [rows, cols]"""
+        return self._bind("mvd_act_fwd_f32", (_ptr(x, torch.float32), _ptr(y, torch.float32), rows, cols, mode), (x, y),
+                          {"kernel": "train_act", "desc": f"rows{rows} cols{cols} mode{mode}", "bytes": (12.0 if mode == ACT_GEGLU else 8.0) * rows * cols})
+
+    def act_bwd(self, dy, x, dx, rows, cols, mode):
+        return self._bind("mvd_act_bwd_f32", (_ptr(dy, torch.float32), _ptr(x, torch.float32), _ptr(dx, torch.float32), rows, cols, mode),
+                          (dy, x, dx), {"kernel": "train_act", "desc": f"bwd rows{rows} cols{cols} mode{mode}",
+                                        "bytes": (20.0 if mode == ACT_GEGLU else 12.0) * rows * cols})

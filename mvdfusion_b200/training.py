@@ -12,12 +12,17 @@ Functions over the library's tcgen05 GEMM / implicit-GEMM kernel (mvd_gemm_f16):
     wgrad     dW = dy^T x           A = dy^T [N, M], "weights" = x^T [K, M]: contraction over the M rows
     conv3x3   dgrad = implicit-GEMM convolution of dy with the flipped / transposed kernel; wgrad = dy^T im2col(x)
 
-What is NOT native yet (this round): the normalisations, activations, softmax / attention cores, the bilinear gather and the data
-movement run as ATen ops inside the same autograd graph (their backward is 6 % of the FLOPs but most of the launches); fused native
-backward kernels for them are the next slice.  Gradients are fp32; parameters stay the nn.Module's fp32 tensors,
-so torch optimizers and DistributedDataParallel (train.py:38,93-95) work unchanged.
+Second slice (ABI 15, csrc/train.cu): the normalisations and activations between the GEMMs — nn.LayerNorm and the adaLN-modulated
+LayerNorm of the DiT blocks, GroupNorm32 (+ SiLU), GELU, SiLU, GEGLU — are autograd Functions over the library's fp32 forward /
+backward kernels (forward saves per-row / per-group (mean, rstd); backward recomputes the normalised values from them).
+MVD_TRAIN_ATEN_POINTWISE=1 puts the ATen ops back for an A/B.
+
+What is NOT native yet: the softmax / attention cores (torch SDPA), the bilinear gather of GridAttn and the data movement
+(concat, pad, pooling) run as ATen ops inside the same autograd graph.  Gradients are fp32; parameters stay the nn.Module's fp32
+tensors, so torch optimizers and DistributedDataParallel (train.py:38,93-95) work unchanged.
 """
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -150,14 +155,138 @@ def conv3x3_stride2(x, w, b=None):
     return linear(cols, w.permute(0, 2, 3, 1).reshape(w.shape[0], -1), b)
 
 
+# ------------------------------------------------------------------------------------------------ normalisation / activation primitives
+ATEN_POINTWISE = os.environ.get("MVD_TRAIN_ATEN_POINTWISE") == "1"   # A/B: the first slice's ATen ops instead of csrc/train.cu
+_ACT_GELU, _ACT_SILU, _ACT_GEGLU = 1, 2, 3                           # mvd_act_{fwd,bwd}_f32 modes (include/mvd_b200.h)
+
+
+def _f32c(t):
+    return t.detach().float().contiguous()
+
+
+class _LayerNormFn(torch.autograd.Function):
+    """y = LayerNorm(x) * gamma + beta over the last dimension; gamma / beta [C] or both None (mvd_layernorm_{fwd,bwd}_f32)"""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        C = x.shape[-1]
+        x2 = _f32c(x).reshape(-1, C)
+        rows = x2.shape[0]
+        ops = runtime.get_ops(x.device)
+        g = None if gamma is None else _f32c(gamma).reshape(C)
+        b = None if beta is None else _f32c(beta).reshape(C)
+        y, stats = ops.empty((rows, C), torch.float32), ops.empty((rows, 2), torch.float32)
+        ops.layernorm_fwd(x2, g, b, y, stats, rows, C, float(eps))(_stream(x))
+        ctx.save_for_backward(x2, g, stats)
+        ctx.affine = gamma is not None
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, g, stats = ctx.saved_tensors
+        rows, C = x2.shape
+        ops = runtime.get_ops(dy.device)
+        d = _f32c(dy).reshape(rows, C)
+        dx = ops.empty((rows, C), torch.float32)
+        dg = ops.empty((C,), torch.float32) if ctx.affine else None
+        db = ops.empty((C,), torch.float32) if ctx.affine else None
+        ops.layernorm_bwd(d, x2, g, stats, dx, dg, db, rows, C)(_stream(dy))
+        return dx.reshape(dy.shape), dg, db, None
+
+
+def layer_norm(x, gamma, beta, eps):
+    if ATEN_POINTWISE:
+        return F.layer_norm(x, (x.shape[-1],), gamma, beta, eps)
+    return _LayerNormFn.apply(x, gamma, beta, eps)
+
+
+class _GroupNormFn(torch.autograd.Function):
+    """GroupNorm32 (+ SiLU) on channels-last x [n, ..., C] (mvd_groupnorm_{fwd,bwd}_f32)"""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, silu):
+        n, C = x.shape[0], x.shape[-1]
+        xc = _f32c(x)
+        hw = xc.numel() // (n * C)
+        ops = runtime.get_ops(x.device)
+        g, b = _f32c(gamma), _f32c(beta)
+        y, stats = ops.empty(tuple(x.shape), torch.float32), ops.empty((n, 32, 2), torch.float32)
+        ws = ops.empty((n * 32 * 24,), torch.uint8)
+        ops.groupnorm_fwd(xc, g, b, y, stats, ws, n, hw, C, float(eps), silu)(_stream(x))
+        ctx.save_for_backward(xc, g, b, stats)
+        ctx.dims = (n, hw, C, bool(silu))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, g, b, stats = ctx.saved_tensors
+        n, hw, C, silu = ctx.dims
+        ops = runtime.get_ops(dy.device)
+        dx = ops.empty(tuple(xc.shape), torch.float32)
+        dg, db = ops.empty((C,), torch.float32), ops.empty((C,), torch.float32)
+        ws = ops.empty((n * 32 * 24,), torch.uint8)
+        ops.groupnorm_bwd(_f32c(dy), xc, g, b, stats, dx, dg, db, ws, n, hw, C, silu)(_stream(dy))
+        return dx, dg, db, None, None
+
+
+class _ActFn(torch.autograd.Function):
+    """GELU (exact erf) / SiLU elementwise, GEGLU over the last dimension ([..., 2 I] -> [..., I]) (mvd_act_{fwd,bwd}_f32)"""
+
+    @staticmethod
+    def forward(ctx, x, mode):
+        xc = _f32c(x)
+        ops = runtime.get_ops(x.device)
+        if mode == _ACT_GEGLU:
+            cols = x.shape[-1] // 2
+            rows = xc.numel() // (2 * cols)
+            y = ops.empty(tuple(x.shape[:-1]) + (cols,), torch.float32)
+        else:
+            rows, cols = 1, xc.numel()
+            if cols >= 1 << 31:                          # cols is an int32 in the ABI
+                cols = x.shape[-1]
+                rows = xc.numel() // cols
+            y = ops.empty(tuple(x.shape), torch.float32)
+        ops.act_fwd(xc, y, rows, cols, mode)(_stream(x))
+        ctx.save_for_backward(xc)
+        ctx.dims = (rows, cols, mode)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xc,) = ctx.saved_tensors
+        rows, cols, mode = ctx.dims
+        ops = runtime.get_ops(dy.device)
+        dx = ops.empty(tuple(xc.shape), torch.float32)
+        ops.act_bwd(_f32c(dy), xc, dx, rows, cols, mode)(_stream(dy))
+        return dx, None
+
+
+def gelu(x):
+    return F.gelu(x) if ATEN_POINTWISE else _ActFn.apply(x, _ACT_GELU)
+
+
+def silu(x):
+    return F.silu(x) if ATEN_POINTWISE else _ActFn.apply(x, _ACT_SILU)
+
+
+def geglu(h):
+    """external/sd1/ldm/modules/attention.py:42-44: h = proj(x) = (a | gate) -> a * gelu(gate)"""
+    if ATEN_POINTWISE:
+        a, gate = h.chunk(2, dim=-1)
+        return a * F.gelu(gate)
+    return _ActFn.apply(h, _ACT_GEGLU)
+
+
 # ------------------------------------------------------------------------------------------------ UNet (channels-last activations)
 def _gn(P, p, x, eps, silu=False):
-    y = F.group_norm(x.permute(0, 3, 1, 2), 32, P[p + ".weight"], P[p + ".bias"], eps).permute(0, 2, 3, 1)
-    return F.silu(y) if silu else y
+    if ATEN_POINTWISE:
+        y = F.group_norm(x.permute(0, 3, 1, 2), 32, P[p + ".weight"], P[p + ".bias"], eps).permute(0, 2, 3, 1)
+        return F.silu(y) if silu else y
+    return _GroupNormFn.apply(x, P[p + ".weight"], P[p + ".bias"], eps, silu)
 
 
 def _ln(P, p, x):
-    return F.layer_norm(x, (x.shape[-1],), P[p + ".weight"], P[p + ".bias"], 1e-5)
+    return layer_norm(x, P[p + ".weight"], P[p + ".bias"], 1e-5)
 
 
 def _lin(P, p, x):
@@ -182,8 +311,7 @@ def cross_attention(P, p, x, context, heads):
 
 
 def feed_forward(P, p, x):
-    a, gate = _lin(P, p + ".net.0.proj", x).chunk(2, dim=-1)
-    return _lin(P, p + ".net.2", a * F.gelu(gate))
+    return _lin(P, p + ".net.2", geglu(_lin(P, p + ".net.0.proj", x)))
 
 
 def spatial_transformer(P, p, x, context, heads):
@@ -215,7 +343,7 @@ def view_aligned_transformer(P, p, x, pyramid, heads, image_size):
 def resblock(P, p, x, emb):
     """external/sd1/ldm/modules/diffusionmodules/openaimodel.py:255-275"""
     h = conv3x3(_gn(P, p + ".in_layers.0", x, 1e-5, silu=True), P[p + ".in_layers.2.weight"], P[p + ".in_layers.2.bias"])
-    h = h + _lin(P, p + ".emb_layers.1", F.silu(emb))[:, None, None, :]
+    h = h + _lin(P, p + ".emb_layers.1", silu(emb))[:, None, None, :]
     h = conv3x3(_gn(P, p + ".out_layers.0", h, 1e-5, silu=True), P[p + ".out_layers.3.weight"], P[p + ".out_layers.3.bias"])
     if p + ".skip_connection.weight" in P:
         x = linear(x, P[p + ".skip_connection.weight"], P[p + ".skip_connection.bias"])
@@ -252,7 +380,7 @@ def timestep_embedding(t, dim, max_period=10000):
 
 def unet_forward(P, p, x, timesteps, context, pyramid, *, model_channels, num_heads, image_size):
     """mvdfusion/unet.py:524-556; x (n, S, S, C_in) channels-last -> (n, S, S, C_out)"""
-    emb = _lin(P, p + "time_embed.2", F.silu(_lin(P, p + "time_embed.0", timestep_embedding(timesteps, model_channels))))
+    emb = _lin(P, p + "time_embed.2", silu(_lin(P, p + "time_embed.0", timestep_embedding(timesteps, model_channels))))
 
     def count(name):
         pre = f"{p}{name}."
@@ -317,7 +445,7 @@ def gridattn_forward(P, p, noisy, cams, in_cams, t_embed, sac, somac, depth_eps,
     dev = noisy.device
     depth = (noisy[:, 4:] / sac).expand(-1, D, -1, -1) + (somac / sac / 10.0) * depth_eps
     zdepth = (torch.clip((depth + 1.0) / 2.0, 0.0, 1.0) * depth_scale + depth_shift).detach()   # torch.normal: no gradient path
-    zemb = lambda x: F.gelu(linear(x.permute(0, 2, 3, 1), P[p + "z_embedder.0.weight"], P[p + "z_embedder.0.bias"])).permute(0, 3, 1, 2)
+    zemb = lambda x: gelu(linear(x.permute(0, 2, 3, 1), P[p + "z_embedder.0.weight"], P[p + "z_embedder.0.bias"])).permute(0, 3, 1, 2)
     feat, in_feat = zemb(noisy), zemb(input_latents)
     half = 1.0 / float(S)
     lin_ = torch.linspace(1.0 - half, -1.0 + half, S, dtype=torch.float32, device=dev)
@@ -347,19 +475,20 @@ def gridattn_forward(P, p, noisy, cams, in_cams, t_embed, sac, somac, depth_eps,
     mask = torch.ones(V, N, HWD, 1, device=dev)
     z = torch.cat((ref_feat, inp_feat, ref_pl, ref_depth, q_pl, q_depth, mask), dim=-1)          # (V, N, HWD, 723)
     x = z.reshape(V, N * HWD, z.shape[-1]).permute(1, 0, 2)                                        # (P, V, 723)
-    x = F.gelu(_lin(P, p + "pre_layer_b.0", x))
+    x = gelu(_lin(P, p + "pre_layer_b.0", x))
     c = t_embed[:1]
     C = x.shape[-1]
     hd = C // num_heads
     i = 0
     while f"{p}aggregation_transformer.layer_list.{i}.attn.qkv.weight" in P:
         q = f"{p}aggregation_transformer.layer_list.{i}"
-        sh_a, sc_a, g_a, sh_m, sc_m, g_m = _lin(P, q + ".adaLN_modulation.1", F.silu(c)).chunk(6, dim=1)
-        modln = lambda v, sh, sc: F.layer_norm(v, (C,), None, None, 1e-6) * (1 + sc.unsqueeze(1)) + sh.unsqueeze(1)
+        sh_a, sc_a, g_a, sh_m, sc_m, g_m = _lin(P, q + ".adaLN_modulation.1", silu(c)).chunk(6, dim=1)
+        # modulate(norm(x), shift, scale) with one conditioning row (c = t_embed[:1]) is a LayerNorm with gamma = 1 + scale, beta = shift
+        modln = lambda v, sh, sc: layer_norm(v, (1 + sc).reshape(C), sh.reshape(C), 1e-6)
         qkv = _lin(P, q + ".attn.qkv", modln(x, sh_a, sc_a)).reshape(x.shape[0], V, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
         a = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2]).transpose(1, 2).reshape(x.shape[0], V, C)
         x = x + g_a.unsqueeze(1) * _lin(P, q + ".attn.proj", a)
-        x = x + g_m.unsqueeze(1) * _lin(P, q + ".mlp.fc2", F.gelu(_lin(P, q + ".mlp.fc1", modln(x, sh_m, sc_m))))
+        x = x + g_m.unsqueeze(1) * _lin(P, q + ".mlp.fc2", gelu(_lin(P, q + ".mlp.fc1", modln(x, sh_m, sc_m))))
         i += 1
     w = _lin(P, p + "aggregation_transformer.weight_layer", x).softmax(dim=-2)
     return _lin(P, p + "final_layer_b", (x * w).sum(dim=-2)).reshape(N, S, S, D, -1)
@@ -387,14 +516,14 @@ def apply_model_train(model, noisy, cams, input_latents, in_cams, clip_v_embed, 
     if depth_eps is None:
         depth_eps = torch.randn(N, D, S, S, device=noisy.device)
     te = timestep_embedding(t.float(), 256)
-    t_embed = _lin(P, "time_embed.2", F.silu(_lin(P, "time_embed.0", te)))
+    t_embed = _lin(P, "time_embed.2", silu(_lin(P, "time_embed.0", te)))
     vol = gridattn_forward(P, "view_attn.", noisy, cd(cams), cd(in_cams), t_embed, sac, somac, depth_eps, input_latents, D=D,
                            num_heads=model.view_attn.num_heads, depth_scale=model.view_attn.depth_scale, depth_shift=model.view_attn.depth_shift)
     clip_embed = clip_v_embed
     for n_, i in enumerate((0, 2, 4)):
         clip_embed = _lin(P, f"cc_projection.{i}", clip_embed)
         if n_ < 2:
-            clip_embed = F.silu(clip_embed)
+            clip_embed = silu(clip_embed)
     x_concat = input_latents.expand(N, -1, -1, -1)
     if model.drop_conditions:  # unet.py:118-127,140-151
         r = drop_random if drop_random is not None else torch.rand(N, device=noisy.device)

@@ -510,3 +510,84 @@ class TorchOpsDouble:
             a = ((Q @ K.transpose(-1, -2)) * dhead ** -0.5).softmax(-1) @ V
             out.reshape(-1)[: M * C].copy_(a.reshape(-1).half())
         return self._call(fn)
+
+    # ------------------------------------------------------------------ training (ABI 15): closed forms; tests/test_training.py pins them to torch.autograd
+    def layernorm_fwd(self, x, gamma, beta, y, stats, rows, C, eps):
+        def fn():
+            v = x.reshape(-1)[: rows * C].reshape(rows, C)
+            mean = v.mean(dim=1)
+            rstd = (v.var(dim=1, unbiased=False) + eps).rsqrt()
+            stats.reshape(-1)[: 2 * rows].reshape(rows, 2).copy_(torch.stack([mean, rstd], dim=1))
+            y.reshape(-1)[: rows * C].copy_(F.layer_norm(v, (C,), gamma, beta, eps).reshape(-1))
+        return self._call(fn)
+
+    def layernorm_bwd(self, dy, x, gamma, stats, dx, dgamma, dbeta, rows, C):
+        def fn():
+            v = x.reshape(-1)[: rows * C].reshape(rows, C)
+            d = dy.reshape(-1)[: rows * C].reshape(rows, C)
+            st = stats.reshape(-1)[: 2 * rows].reshape(rows, 2)
+            xh = (v - st[:, :1]) * st[:, 1:]                              # the SAVED statistics, as the kernel uses them
+            gx = d if gamma is None else d * gamma.reshape(1, C)
+            dxv = st[:, 1:] * (gx - gx.mean(dim=1, keepdim=True) - xh * (gx * xh).mean(dim=1, keepdim=True))
+            dx.reshape(-1)[: rows * C].copy_(dxv.reshape(-1))
+            if dgamma is not None:
+                dgamma.reshape(-1)[:C].copy_((d * xh).sum(0))
+                dbeta.reshape(-1)[:C].copy_(d.sum(0))
+        return self._call(fn)
+
+    def groupnorm_fwd(self, x, gamma, beta, y, stats, ws, n_img, hw, C, eps, silu):
+        def fn():
+            v = x.reshape(-1)[: n_img * hw * C].reshape(n_img, hw, 32, C // 32)
+            mean = v.mean(dim=(1, 3))
+            rstd = (v.var(dim=(1, 3), unbiased=False) + eps).rsqrt()
+            stats.reshape(-1)[: n_img * 64].reshape(n_img, 32, 2).copy_(torch.stack([mean, rstd], dim=2))
+            o = F.group_norm(v.reshape(n_img, hw, C).permute(0, 2, 1), 32, gamma, beta, eps)
+            if silu:
+                o = F.silu(o)
+            y.reshape(-1)[: n_img * hw * C].copy_(o.permute(0, 2, 1).reshape(-1))
+        return self._call(fn)
+
+    def groupnorm_bwd(self, dy, x, gamma, beta, stats, dx, dgamma, dbeta, ws, n_img, hw, C, silu):
+        def fn():
+            cpg = C // 32
+            st = stats.reshape(-1)[: n_img * 64].reshape(n_img, 1, 32, 2)
+            v = x.reshape(-1)[: n_img * hw * C].reshape(n_img, hw, 32, cpg)
+            d = dy.reshape(-1)[: n_img * hw * C].reshape(n_img, hw, 32, cpg)
+            ga, be = gamma.reshape(1, 1, 32, cpg), beta.reshape(1, 1, 32, cpg)
+            xh = (v - st[..., :1]) * st[..., 1:]
+            dz = d
+            if silu:
+                z = xh * ga + be
+                sg = torch.sigmoid(z)
+                dz = d * sg * (1 + z * (1 - sg))
+            dgamma.reshape(-1)[:C].copy_((dz * xh).sum(dim=(0, 1)).reshape(-1))
+            dbeta.reshape(-1)[:C].copy_(dz.sum(dim=(0, 1)).reshape(-1))
+            gz = dz * ga
+            s1 = gz.mean(dim=(1, 3), keepdim=True)
+            s2 = (gz * xh).mean(dim=(1, 3), keepdim=True)
+            dx.reshape(-1)[: n_img * hw * C].copy_((st[..., 1:] * (gz - s1 - xh * s2)).reshape(-1))
+        return self._call(fn)
+
+    def act_fwd(self, x, y, rows, cols, mode):
+        def fn():
+            if mode == ACT_GEGLU:
+                a, gate = x.reshape(-1)[: rows * 2 * cols].reshape(rows, 2 * cols).chunk(2, dim=1)
+                y.reshape(-1)[: rows * cols].copy_((a * F.gelu(gate)).reshape(-1))
+            else:
+                v = x.reshape(-1)[: rows * cols]
+                y.reshape(-1)[: rows * cols].copy_(F.gelu(v) if mode == ACT_GELU else F.silu(v))
+        return self._call(fn)
+
+    def act_bwd(self, dy, x, dx, rows, cols, mode):
+        def fn():
+            n_in = rows * cols * (2 if mode == ACT_GEGLU else 1)
+            with torch.enable_grad():
+                v = x.detach().reshape(-1)[:n_in].clone().requires_grad_(True)
+                if mode == ACT_GEGLU:
+                    a, gate = v.reshape(rows, 2 * cols).chunk(2, dim=1)
+                    out = (a * F.gelu(gate)).reshape(-1)
+                else:
+                    out = F.gelu(v) if mode == ACT_GELU else F.silu(v)
+                (g,) = torch.autograd.grad(out, v, dy.detach().reshape(-1)[: rows * cols])
+            dx.reshape(-1)[:n_in].copy_(g)
+        return self._call(fn)

@@ -133,3 +133,62 @@ def test_contraction_functions_forward_dgrad_wgrad():
     assert rel_l2(y, ref) < 2e-3
     for got, want in zip(torch.autograd.grad(y, (x, w, b), gy), torch.autograd.grad(ref, (x, w, b), gy)):
         assert rel_l2(got, want) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ ABI 15: normalisation / activation kernels
+def _pointwise_cases():
+    """(name, Function-level callable, torch reference, inputs) at the shapes of the training graph: LayerNorm with / without the affine
+    part, GroupNorm32 (+ SiLU) with 2 / 10 / 40 channels per group and a ragged last pixel chunk, GELU / SiLU with a scalar tail, GEGLU"""
+    from mvdfusion_b200 import training as T
+    g = torch.Generator().manual_seed(5)
+    r = lambda *s, scale=1.0, shift=0.0: torch.randn(*s, generator=g) * scale + shift
+    cases = []
+    for rows, C, affine in ((300, 320, True), (64, 1280, True), (1000, 256, False), (37, 64, True)):
+        ins = [r(rows, C, scale=2.0, shift=0.5)] + ([r(C, shift=1.0), r(C)] if affine else [])
+        cases.append((f"layernorm_{rows}x{C}_{'affine' if affine else 'plain'}",
+                      (lambda x, *gb: T.layer_norm(x, gb[0] if gb else None, gb[1] if gb else None, 1e-5)),
+                      (lambda x, *gb: F.layer_norm(x, (x.shape[-1],), gb[0] if gb else None, gb[1] if gb else None, 1e-5)), ins))
+    for n, H, W, C, act in ((2, 8, 8, 64, True), (3, 5, 7, 320, True), (2, 16, 16, 1280, False), (1, 4, 4, 2560, True), (2, 32, 32, 320, False)):
+        ins = [r(n, H, W, C, scale=1.5, shift=0.3), r(C, shift=1.0), r(C)]
+        ref = lambda x, ga, be, act=act: (lambda y: F.silu(y) if act else y)(F.group_norm(x.permute(0, 3, 1, 2), 32, ga, be, 1e-5).permute(0, 2, 3, 1))
+        cases.append((f"groupnorm_{n}x{H}x{W}x{C}_{'silu' if act else 'plain'}", (lambda x, ga, be, act=act: T._GroupNormFn.apply(x, ga, be, 1e-5, act)), ref, ins))
+    cases.append(("gelu_tail", T.gelu, F.gelu, [r(7, 331, scale=2.0)]))
+    cases.append(("gelu_vec", T.gelu, F.gelu, [r(64, 512, scale=2.0)]))
+    cases.append(("silu", T.silu, F.silu, [r(2, 1280, scale=3.0)]))
+    cases.append(("geglu", T.geglu, (lambda h: h.chunk(2, dim=-1)[0] * F.gelu(h.chunk(2, dim=-1)[1])), [r(5, 40, 2560, scale=1.5)]))
+    return cases
+
+
+def _check_pointwise(dev, tol):
+    """every case runs (one failing kernel does not hide the others); returns name -> worst rel-L2 over (y, grads)"""
+    worst, bad = {}, []
+    for name, fn, ref, ins in _pointwise_cases():
+        a = [t.clone().to(dev).requires_grad_(True) for t in ins]
+        b = [t.clone().double().requires_grad_(True) for t in ins]
+        y, yr = fn(*a), ref(*b)
+        gy = torch.randn(yr.shape, generator=torch.Generator().manual_seed(9))
+        got = torch.autograd.grad(y, a, gy.to(dev))
+        want = torch.autograd.grad(yr, b, gy.double())
+        errs = [rel_l2(y.detach().cpu(), yr.detach().float())] + [rel_l2(p.cpu(), q.float()) for p, q in zip(got, want)]
+        finite = bool(torch.isfinite(y).all()) and all(bool(torch.isfinite(p).all()) for p in got)
+        print(f"pointwise {name}: y / grads rel-L2 {['%.2e' % e for e in errs]} finite={finite}")
+        worst[name] = max(errs)
+        if not finite or not max(errs) < tol:
+            bad.append((name, errs, finite))
+    assert not bad, bad
+    return worst
+
+
+def test_pointwise_functions_cpu_emulation_matches_autograd(ops_double):
+    """pins the closed forms of tests/ops_double.py (and the Functions' host logic: shapes, saved tensors, optional affine part)
+    to torch.autograd in float64"""
+    _check_pointwise("cpu", 2e-5)
+
+
+@pytest.mark.gpu
+def test_pointwise_kernels_forward_backward_gpu():
+    """mvd_layernorm / groupnorm / act _{fwd,bwd}_f32 (csrc/train.cu) through their autograd Functions against torch.autograd in
+    float64: outputs and every gradient (dx, dgamma, dbeta) at rel-L2 <= 2e-5 (fp32 kernels; atomics change the summation order only)"""
+    from common import record_parity
+    for name, err in _check_pointwise("cuda", 2e-5).items():
+        record_parity(f"train_pointwise_{name}_vs_autograd_f64", err, 2e-5)
