@@ -10,10 +10,17 @@
 // Reductions over rows (dgamma, dbeta, group sums) end in atomics on small zero-initialised vectors: fp32 for the parameter
 // gradients, fp64 for the (sum, sum of squares) of a group, whose difference is the variance.
 // The launches are plain stream launches (no programmatic dependent launch): in the training graph their neighbours are ATen kernels.
+#ifdef MVD_CPU_EMULATION
+// test infrastructure: the same source compiled as plain C++ and run on host threads (tests/native/cpu_emul/cuda_on_cpu.h), so that
+// the kernels' indexing and arithmetic are checked in a container without a GPU; the product is the nvcc build below
+#include "cuda_on_cpu.h"
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "common.h"
+#define MVD_KLAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#endif
 
 namespace mvd {
 namespace {
@@ -343,17 +350,15 @@ int act_launch(const char* name, const float* x, const float* dy, float* out, lo
     if ((cols & 3) != 0 || !aligned16(x) || !aligned16(out) || (BWD && !aligned16(dy)))
       return set_error(MVD_EALIGN, "%s: GEGLU needs cols %% 4 == 0 and 16-byte aligned pointers", name);
     if (rows > 2147483647LL) return set_error(MVD_EINVAL, "%s: too many rows", name);
-    geglu_kernel<BWD><<<static_cast<unsigned>(rows), 256, 0, stream>>>(x, dy, out, cols);
+    MVD_KLAUNCH(geglu_kernel<BWD>, static_cast<unsigned>(rows), 256, stream, x, dy, out, cols);
   } else if (mode == ACT_GELU || mode == ACT_SILU) {
     const long long n = rows * cols;
     const int vec = aligned16(x) && aligned16(out) && (!BWD || aligned16(dy));
     const long long work = vec ? (n + 3) / 4 : n;
     long long blocks = (work + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    if (mode == ACT_GELU)
-      act_kernel<ACT_GELU, BWD><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, dy, out, n, vec);
-    else
-      act_kernel<ACT_SILU, BWD><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, dy, out, n, vec);
+    auto kernel = mode == ACT_GELU ? act_kernel<ACT_GELU, BWD> : act_kernel<ACT_SILU, BWD>;  // (a template-id with a comma cannot be a macro argument)
+    MVD_KLAUNCH(kernel, static_cast<unsigned>(blocks), 256, stream, x, dy, out, n, vec);
   } else {
     return set_error(MVD_EINVAL, "%s: mode must be 1 (GELU), 2 (SiLU) or 3 (GEGLU)", name);
   }
@@ -375,7 +380,7 @@ extern "C" int mvd_layernorm_fwd_f32(const float* x, const float* gamma, const f
   if (rows <= 0 || C <= 0 || (C & 3) != 0) return set_error(MVD_EINVAL, "mvd_layernorm_fwd_f32: C must be a multiple of 4");
   if (!aligned16(x) || !aligned16(y) || !aligned16(gamma) || !aligned16(beta) || (reinterpret_cast<uintptr_t>(stats) & 7))
     return set_error(MVD_EALIGN, "mvd_layernorm_fwd_f32: x / y / gamma / beta must be 16-byte, stats 8-byte aligned");
-  ln_fwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, gamma, beta, y, stats, rows, C, eps);
+  MVD_KLAUNCH(ln_fwd_kernel, (rows + 7) / 8, 256, stream, x, gamma, beta, y, stats, rows, C, eps);
   count_launch();
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -389,14 +394,14 @@ extern "C" int mvd_layernorm_bwd_f32(const float* dy, const float* x, const floa
   if (rows <= 0 || C <= 0 || (C & 3) != 0) return set_error(MVD_EINVAL, "mvd_layernorm_bwd_f32: C must be a multiple of 4");
   if (!aligned16(dy) || !aligned16(x) || !aligned16(dx) || !aligned16(gamma) || (reinterpret_cast<uintptr_t>(stats) & 7))
     return set_error(MVD_EALIGN, "mvd_layernorm_bwd_f32: dy / x / dx / gamma must be 16-byte, stats 8-byte aligned");
-  ln_bwd_dx_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(dy, x, gamma, stats, dx, rows, C);
+  MVD_KLAUNCH(ln_bwd_dx_kernel, (rows + 7) / 8, 256, stream, dy, x, gamma, stats, dx, rows, C);
   count_launch();
   if (dgamma != nullptr) {
     MVD_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, stream));
     MVD_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, sizeof(float) * C, stream));
     int rpc = (rows + 127) / 128;
     if (rpc < 64) rpc = 64;
-    ln_bwd_param_kernel<<<dim3((C + 31) / 32, (rows + rpc - 1) / rpc), dim3(32, 8), 0, stream>>>(dy, x, stats, dgamma, dbeta, rows, C, rpc);
+    MVD_KLAUNCH(ln_bwd_param_kernel, dim3((C + 31) / 32, (rows + rpc - 1) / rpc), dim3(32, 8), stream, dy, x, stats, dgamma, dbeta, rows, C, rpc);
     count_launch();
   }
   MVD_CUDA_CHECK(cudaGetLastError());
@@ -415,9 +420,9 @@ extern "C" int mvd_groupnorm_fwd_f32(const float* x, const float* gamma, const f
   const int count = n_img * 32;
   double* sums = static_cast<double*>(ws);
   MVD_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * count, stream));
-  gn_sums_kernel<<<g.grid, g.block, 0, stream>>>(x, sums, hw, C, g.cpg);
-  gn_finalize_kernel<<<(count + 127) / 128, 128, 0, stream>>>(sums, stats, count, static_cast<double>(hw) * g.cpg, static_cast<double>(eps));
-  gn_apply_kernel<<<g.grid, g.block, 0, stream>>>(x, gamma, beta, stats, y, hw, C, g.cpg, apply_silu);
+  MVD_KLAUNCH(gn_sums_kernel, g.grid, g.block, stream, x, sums, hw, C, g.cpg);
+  MVD_KLAUNCH(gn_finalize_kernel, (count + 127) / 128, 128, stream, sums, stats, count, static_cast<double>(hw) * g.cpg, static_cast<double>(eps));
+  MVD_KLAUNCH(gn_apply_kernel, g.grid, g.block, stream, x, gamma, beta, stats, y, hw, C, g.cpg, apply_silu);
   count_launch(3);
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -440,9 +445,9 @@ extern "C" int mvd_groupnorm_bwd_f32(const float* dy, const float* x, const floa
   MVD_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * count, stream));
   MVD_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, stream));
   MVD_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, sizeof(float) * C, stream));
-  gn_bwd_sums_kernel<<<g.grid, g.block, 0, stream>>>(dy, x, gamma, beta, stats, dgamma, dbeta, sums, hw, C, g.cpg, apply_silu);
-  gn_bwd_finalize_kernel<<<(count + 127) / 128, 128, 0, stream>>>(sums, red, count, static_cast<double>(hw) * g.cpg);
-  gn_bwd_apply_kernel<<<g.grid, g.block, 0, stream>>>(dy, x, gamma, beta, stats, red, dx, hw, C, g.cpg, apply_silu);
+  MVD_KLAUNCH(gn_bwd_sums_kernel, g.grid, g.block, stream, dy, x, gamma, beta, stats, dgamma, dbeta, sums, hw, C, g.cpg, apply_silu);
+  MVD_KLAUNCH(gn_bwd_finalize_kernel, (count + 127) / 128, 128, stream, sums, red, count, static_cast<double>(hw) * g.cpg);
+  MVD_KLAUNCH(gn_bwd_apply_kernel, g.grid, g.block, stream, dy, x, gamma, beta, stats, red, dx, hw, C, g.cpg, apply_silu);
   count_launch(3);
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

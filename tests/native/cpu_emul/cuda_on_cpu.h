@@ -1,0 +1,184 @@
+// TEST INFRASTRUCTURE — a minimal CUDA-on-CPU execution shim, never part of the product.
+//
+// Purpose: the build container has no GPU.  Kernels that only use the classic SIMT subset (thread / block indices, static
+// __shared__ arrays, __syncthreads, warp shuffles, atomics, __ldg, float2 / float4) are compiled a second time as plain C++
+// (-DMVD_CPU_EMULATION) and executed here with one std::thread per CUDA thread of a block, blocks one after the other, so that
+// their indexing, reductions and closed forms are checked against torch.autograd before the code ever reaches a B200
+// (tests/test_training.py::test_pointwise_kernel_source_on_the_cpu_shim).  It says nothing about performance, memory coalescing or
+// races between blocks (blocks run sequentially); the -m gpu tests remain the proof on hardware.
+//
+// Semantics kept: a block's threads run concurrently (real threads), __syncthreads() is a block-wide barrier, __shfl_xor_sync
+// exchanges through a per-warp buffer between two warp barriers (all 32 lanes of a warp must take part, as on hardware with a full
+// mask), `static` stands in for __shared__ (valid because only one block is resident at a time), atomicAdd is serialised.
+#pragma once
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../../include/mvd_b200.h"
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+constexpr cudaError_t cudaSuccess = 0;
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __shared__ static
+
+namespace cpu_emul {
+
+class Barrier {  // reusable (generation-counted) barrier for `n` threads
+ public:
+  explicit Barrier(int n) : n_(n) {}
+  void wait() {
+    std::unique_lock<std::mutex> lk(m_);
+    const unsigned gen = gen_;
+    if (++count_ == n_) {
+      count_ = 0;
+      ++gen_;
+      cv_.notify_all();
+    } else {
+      cv_.wait(lk, [&] { return gen_ != gen; });
+    }
+  }
+
+ private:
+  std::mutex m_;
+  std::condition_variable cv_;
+  int n_, count_ = 0;
+  unsigned gen_ = 0;
+};
+
+struct Warp {
+  Barrier bar{32};
+  uint32_t slot[32];
+};
+
+struct Ctx {
+  dim3 threadIdx, blockIdx, blockDim, gridDim;
+  Barrier* block_bar = nullptr;
+  Warp* warp = nullptr;
+  int lane = 0;
+};
+inline Ctx& ctx() {
+  thread_local Ctx c;
+  return c;
+}
+inline std::mutex& atomic_mutex() {
+  static std::mutex m;
+  return m;
+}
+
+// run `body` once per (block, thread): blockDim threads live for the whole launch and walk over the blocks together
+inline void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
+  const int nt = static_cast<int>(block.x * block.y * block.z);
+  const int nw = (nt + 31) / 32;
+  if (nt % 32 != 0) {  // the kernels under test use full warps only; partial warps would dead-lock the shuffle barrier
+    fprintf(stderr, "cpu_emul::launch: block size %d is not a multiple of 32\n", nt);
+    abort();
+  }
+  Barrier block_bar(nt), end_bar(nt);
+  std::vector<Warp> warps(nw);
+  std::vector<std::thread> threads;
+  threads.reserve(nt);
+  for (int t = 0; t < nt; ++t) {
+    threads.emplace_back([&, t] {
+      Ctx& c = ctx();
+      c.blockDim = block;
+      c.gridDim = grid;
+      c.threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+      c.block_bar = &block_bar;
+      c.warp = &warps[t / 32];
+      c.lane = t % 32;
+      for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+          for (unsigned bx = 0; bx < grid.x; ++bx) {
+            c.blockIdx = dim3(bx, by, bz);
+            body();
+            end_bar.wait();  // the next block may reuse the `static` shared arrays only after every thread has left this one
+          }
+    });
+  }
+  for (auto& th : threads) th.join();
+}
+
+}  // namespace cpu_emul
+
+#define threadIdx (cpu_emul::ctx().threadIdx)
+#define blockIdx (cpu_emul::ctx().blockIdx)
+#define blockDim (cpu_emul::ctx().blockDim)
+#define gridDim (cpu_emul::ctx().gridDim)
+
+inline void __syncthreads() { cpu_emul::ctx().block_bar->wait(); }
+
+template <typename T>
+inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+  static_assert(sizeof(T) == 4, "32-bit shuffles only");
+  cpu_emul::Ctx& c = cpu_emul::ctx();
+  memcpy(&c.warp->slot[c.lane], &v, 4);
+  c.warp->bar.wait();
+  T r;
+  memcpy(&r, &c.warp->slot[c.lane ^ lane_mask], 4);
+  c.warp->bar.wait();
+  return r;
+}
+
+template <typename T>
+inline T atomicAdd(T* p, T v) {
+  std::lock_guard<std::mutex> lk(cpu_emul::atomic_mutex());
+  const T old = *p;
+  *p = old + v;
+  return old;
+}
+
+template <typename T>
+inline T __ldg(const T* p) { return *p; }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+using std::max;
+using std::min;
+
+namespace mvd {
+inline int set_error(int code, const char* fmt, ...) {
+  static thread_local char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  fprintf(stderr, "mvd (cpu shim): %s\n", buf);
+  return code;
+}
+inline void count_launch(int = 1) {}
+}  // namespace mvd
+
+#define MVD_CUDA_CHECK(expr)                                                      \
+  do {                                                                            \
+    if ((expr) != cudaSuccess) return ::mvd::set_error(MVD_ECUDA, "%s", #expr);   \
+  } while (0)
+
+// kernel<<<grid, block, 0, stream>>>(args...) of the real build
+#define MVD_KLAUNCH(kernel, grid, block, stream, ...) \
+  cpu_emul::launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
