@@ -329,6 +329,14 @@ int mvd_groupnorm_bwd_f32(const float* dy, const float* x, const float* gamma, c
  * Backward: dx has x's shape; GEGLU: dx = (dy * gelu(gate) | dy * a * gelu'(gate)). */
 int mvd_act_fwd_f32(const float* x, float* y, long long rows, int32_t cols, int32_t mode, void* stream);
 int mvd_act_bwd_f32(const float* dy, const float* x, float* dx, long long rows, int32_t cols, int32_t mode, void* stream);
+/* ABI 16: F.grid_sample(fmap, grid, mode="bilinear", padding_mode="border", align_corners=True) of GridAttn's aggregate_features
+ * (mvdfusion/view_attn_efficient2.py:303-318) on channels-last maps: fmap fp32 [V, H, W, C], xy fp32 [V, P, 2] = the grid's (x, y) in
+ * [-1, 1], out fp32 [V, P, C].  Backward: dfmap [V, H, W, C] is zeroed, then dfmap[v, tap, :] += w_tap * dout[v, p, :] (16-byte
+ * reductions).  The grid carries no gradient on this path (the sampled depth is detached, :291-296).  C % 4 == 0. */
+int mvd_bilinear_gather_fwd_f32(const float* fmap, const float* xy, float* out, int32_t V, int32_t H, int32_t W, int32_t C, long long P,
+                                void* stream);
+int mvd_bilinear_gather_bwd_f32(const float* dout, const float* xy, float* dfmap, int32_t V, int32_t H, int32_t W, int32_t C, long long P,
+                                void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_float, c_int32, c_longlong, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # MVD_B200_LIB: another build of the same library (e.g. the instrumented `make trace` one); it must exist — there is no fallback
 LIB_PATH = os.environ.get("MVD_B200_LIB") or os.path.join(_HERE, "libmvd_b200.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 
 class GemmArgs(ctypes.Structure):
@@ -106,6 +106,8 @@ SIGNATURES = {
     "mvd_groupnorm_bwd_f32": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "mvd_act_fwd_f32": [vp, vp, i64, i32, i32, vp],
     "mvd_act_bwd_f32": [vp, vp, vp, i64, i32, i32, vp],
+    "mvd_bilinear_gather_fwd_f32": [vp, vp, vp, i32, i32, i32, i32, i64, vp],
+    "mvd_bilinear_gather_bwd_f32": [vp, vp, vp, i32, i32, i32, i32, i64, vp],
 }
 _RESTYPE = {"mvd_last_error": c_char_p, "mvd_launch_count": c_longlong}
 

@@ -327,6 +327,77 @@ __global__ void geglu_kernel(const float* __restrict__ x, const float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------- bilinear gather (GridAttn)
+// F.grid_sample(fmap, grid, mode="bilinear", padding_mode="border", align_corners=True) on a channels-last map: one warp per
+// (view, point), lanes over float4 channel groups.  Taps past the border carry zero weight (the clamped coordinate makes tx or ty 0).
+struct Taps {
+  int idx[4];
+  float w[4];
+};
+__device__ __forceinline__ Taps bilinear_taps_f32(float gx, float gy, int H, int W) {
+  float ix = (gx + 1.f) * 0.5f * (W - 1);
+  float iy = (gy + 1.f) * 0.5f * (H - 1);
+  ix = fminf(fmaxf(ix, 0.f), static_cast<float>(W - 1));
+  iy = fminf(fmaxf(iy, 0.f), static_cast<float>(H - 1));
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const int x0 = static_cast<int>(x0f), y0 = static_cast<int>(y0f);
+  const float tx = ix - x0f, ty = iy - y0f;
+  const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+  Taps t;
+  t.idx[0] = y0 * W + x0; t.w[0] = (1.f - tx) * (1.f - ty);
+  t.idx[1] = y0 * W + x1; t.w[1] = tx * (1.f - ty);
+  t.idx[2] = y1 * W + x0; t.w[2] = (1.f - tx) * ty;
+  t.idx[3] = y1 * W + x1; t.w[3] = tx * ty;
+  return t;
+}
+
+__device__ __forceinline__ void atomic_add4(float* p, float4 v) {
+#ifdef MVD_CPU_EMULATION
+  atomicAdd(p, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w);
+#else
+  atomicAdd(reinterpret_cast<float4*>(p), v);  // one 16-byte reduction (sm_90+)
+#endif
+}
+
+// BWD = false: out[v, p, :] = sum_t w_t fmap[v, idx_t, :];  BWD = true: dfmap[v, idx_t, :] += w_t dout[v, p, :]
+template <bool BWD>
+__global__ void gather_kernel(const float* __restrict__ src, const float* __restrict__ xy, float* __restrict__ dst, int H, int W, int C,
+                              long long P, long long total) {
+  const long long pt = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pt >= total) return;
+  const long long v = pt / P;
+  const float2 g = __ldg(reinterpret_cast<const float2*>(xy) + pt);
+  const Taps t = bilinear_taps_f32(g.x, g.y, H, W);
+  const size_t map0 = static_cast<size_t>(v) * H * W * C;
+  const int n4 = C >> 2;
+  if (!BWD) {
+    float4* o = reinterpret_cast<float4*>(dst + static_cast<size_t>(pt) * C);
+    for (int i = lane; i < n4; i += 32) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(src + map0 + static_cast<size_t>(t.idx[k]) * C) + i);
+        acc.x = fmaf(t.w[k], f.x, acc.x);
+        acc.y = fmaf(t.w[k], f.y, acc.y);
+        acc.z = fmaf(t.w[k], f.z, acc.z);
+        acc.w = fmaf(t.w[k], f.w, acc.w);
+      }
+      o[i] = acc;
+    }
+  } else {
+    const float4* d = reinterpret_cast<const float4*>(src + static_cast<size_t>(pt) * C);
+    for (int i = lane; i < n4; i += 32) {
+      const float4 f = d[i];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (t.w[k] == 0.f) continue;
+        atomic_add4(dst + map0 + static_cast<size_t>(t.idx[k]) * C + 4 * i, make_float4(t.w[k] * f.x, t.w[k] * f.y, t.w[k] * f.z, t.w[k] * f.w));
+      }
+    }
+  }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 struct GnGeometry {
@@ -459,4 +530,30 @@ extern "C" int mvd_act_fwd_f32(const float* x, float* y, long long rows, int32_t
 
 extern "C" int mvd_act_bwd_f32(const float* dy, const float* x, float* dx, long long rows, int32_t cols, int32_t mode, void* stream_) {
   return act_launch<true>("mvd_act_bwd_f32", x, dy, dx, rows, cols, mode, static_cast<cudaStream_t>(stream_));
+}
+
+template <bool BWD>
+static int gather_launch(const char* name, const float* src, const float* xy, float* dst, int32_t V, int32_t H, int32_t W, int32_t C, long long P,
+                         cudaStream_t stream) {
+  if (!src || !xy || !dst) return set_error(MVD_EINVAL, "%s: null pointer", name);
+  if (V <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) != 0 || P <= 0 || static_cast<long long>(V) * P > (1LL << 33))
+    return set_error(MVD_EINVAL, "%s: C must be a multiple of 4, V * P <= 2^33", name);
+  if (!aligned16(src) || !aligned16(dst) || (reinterpret_cast<uintptr_t>(xy) & 7))
+    return set_error(MVD_EALIGN, "%s: the maps / rows must be 16-byte, xy 8-byte aligned", name);
+  const long long total = static_cast<long long>(V) * P;
+  if (BWD) MVD_CUDA_CHECK(cudaMemsetAsync(dst, 0, sizeof(float) * static_cast<size_t>(V) * H * W * C, stream));
+  MVD_KLAUNCH(gather_kernel<BWD>, static_cast<unsigned>((total + 7) / 8), 256, stream, src, xy, dst, H, W, C, P, total);
+  count_launch();
+  MVD_CUDA_CHECK(cudaGetLastError());
+  return MVD_OK;
+}
+
+extern "C" int mvd_bilinear_gather_fwd_f32(const float* fmap, const float* xy, float* out, int32_t V, int32_t H, int32_t W, int32_t C,
+                                           long long P, void* stream_) {
+  return gather_launch<false>("mvd_bilinear_gather_fwd_f32", fmap, xy, out, V, H, W, C, P, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mvd_bilinear_gather_bwd_f32(const float* dout, const float* xy, float* dfmap, int32_t V, int32_t H, int32_t W, int32_t C,
+                                           long long P, void* stream_) {
+  return gather_launch<true>("mvd_bilinear_gather_bwd_f32", dout, xy, dfmap, V, H, W, C, P, static_cast<cudaStream_t>(stream_));
 }

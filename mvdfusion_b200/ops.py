@@ -386,3 +386,12 @@ class NativeOps:
         return self._bind("mvd_act_bwd_f32", (_ptr(dy, torch.float32), _ptr(x, torch.float32), _ptr(dx, torch.float32), rows, cols, mode),
                           (dy, x, dx), {"kernel": "train_act", "desc": f"bwd rows{rows} cols{cols} mode{mode}",
                                         "bytes": (20.0 if mode == ACT_GEGLU else 12.0) * rows * cols})
+
+    def bilinear_gather_fwd(self, fmap, xy, out, V, H, W, C, P):
+        """fmap fp32 [V, H, W, C] (channels-last), xy fp32 [V, P, 2] grid_sample coordinates, out fp32 [V, P, C] (ABI 16)"""
+        return self._bind("mvd_bilinear_gather_fwd_f32", (_ptr(fmap, torch.float32), _ptr(xy, torch.float32), _ptr(out, torch.float32), V, H, W, C, P),
+                          (fmap, xy, out), {"kernel": "train_gather", "desc": f"V{V} {H}x{W}x{C} P{P}", "bytes": 4.0 * V * P * C})
+
+    def bilinear_gather_bwd(self, dout, xy, dfmap, V, H, W, C, P):
+        return self._bind("mvd_bilinear_gather_bwd_f32", (_ptr(dout, torch.float32), _ptr(xy, torch.float32), _ptr(dfmap, torch.float32), V, H, W, C, P),
+                          (dout, xy, dfmap), {"kernel": "train_gather", "desc": f"bwd V{V} {H}x{W}x{C} P{P}", "bytes": 4.0 * V * P * C})

@@ -17,8 +17,10 @@ LayerNorm of the DiT blocks, GroupNorm32 (+ SiLU), GELU, SiLU, GEGLU — are aut
 backward kernels (forward saves per-row / per-group (mean, rstd); backward recomputes the normalised values from them).
 MVD_TRAIN_ATEN_POINTWISE=1 puts the ATen ops back for an A/B.
 
-What is NOT native yet: the softmax / attention cores (torch SDPA), the bilinear gather of GridAttn and the data movement
-(concat, pad, pooling) run as ATen ops inside the same autograd graph.  Gradients are fp32; parameters stay the nn.Module's fp32
+GridAttn's bilinear gather and its scatter-add backward run on mvd_bilinear_gather_{fwd,bwd}_f32 (ABI 16).
+
+What is NOT native yet: the softmax / attention cores (torch SDPA) and the data movement (concat, pad, pooling) run as ATen ops
+inside the same autograd graph.  Gradients are fp32; parameters stay the nn.Module's fp32
 tensors, so torch optimizers and DistributedDataParallel (train.py:38,93-95) work unchanged.
 """
 import math
@@ -261,6 +263,37 @@ class _ActFn(torch.autograd.Function):
         return dx, None
 
 
+class _GatherFn(torch.autograd.Function):
+    """grid_sample(bilinear, border, align_corners=True) of a channels-last map at fixed coordinates: fmap [V, H, W, C], xy [V, P, 2]
+    -> [V, P, C]; the backward scatters dout into the four taps (mvd_bilinear_gather_{fwd,bwd}_f32)"""
+
+    @staticmethod
+    def forward(ctx, fmap, xy):
+        V, H, W, C = fmap.shape
+        P = xy.shape[1]
+        ops = runtime.get_ops(fmap.device)
+        f, g = _f32c(fmap), _f32c(xy)
+        out = ops.empty((V, P, C), torch.float32)
+        ops.bilinear_gather_fwd(f, g, out, V, H, W, C, P)(_stream(fmap))
+        ctx.save_for_backward(g)
+        ctx.dims = (V, H, W, C, P)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (g,) = ctx.saved_tensors
+        V, H, W, C, P = ctx.dims
+        ops = runtime.get_ops(dout.device)
+        dfmap = ops.empty((V, H, W, C), torch.float32)
+        ops.bilinear_gather_bwd(_f32c(dout), g, dfmap, V, H, W, C, P)(_stream(dout))
+        return dfmap, None
+
+
+def bilinear_gather(fmap, xy):
+    assert not xy.requires_grad, "the sampling coordinates carry no gradient on this path"
+    return _GatherFn.apply(fmap, xy)
+
+
 def gelu(x):
     return F.gelu(x) if ATEN_POINTWISE else _ActFn.apply(x, _ACT_GELU)
 
@@ -445,7 +478,7 @@ def gridattn_forward(P, p, noisy, cams, in_cams, t_embed, sac, somac, depth_eps,
     dev = noisy.device
     depth = (noisy[:, 4:] / sac).expand(-1, D, -1, -1) + (somac / sac / 10.0) * depth_eps
     zdepth = (torch.clip((depth + 1.0) / 2.0, 0.0, 1.0) * depth_scale + depth_shift).detach()   # torch.normal: no gradient path
-    zemb = lambda x: gelu(linear(x.permute(0, 2, 3, 1), P[p + "z_embedder.0.weight"], P[p + "z_embedder.0.bias"])).permute(0, 3, 1, 2)
+    zemb = lambda x: gelu(linear(x.permute(0, 2, 3, 1), P[p + "z_embedder.0.weight"], P[p + "z_embedder.0.bias"]))   # channels-last (V, S, S, 256)
     feat, in_feat = zemb(noisy), zemb(input_latents)
     half = 1.0 / float(S)
     lin_ = torch.linspace(1.0 - half, -1.0 + half, S, dtype=torch.float32, device=dev)
@@ -460,8 +493,11 @@ def gridattn_forward(P, p, noisy, cams, in_cams, t_embed, sac, somac, depth_eps,
     V, HWD = N, S * S * D
 
     def sample(fmap, c):
-        g = F.grid_sample(fmap, -_project_xy(c, pts).unsqueeze(2), align_corners=True, mode="bilinear", padding_mode="border")
-        return g[..., 0].reshape(g.shape[0], g.shape[1], N, HWD).permute(0, 2, 3, 1)
+        xy = -_project_xy(c, pts)                                                                  # (V', P, 2), no gradient path (zdepth is detached)
+        if ATEN_POINTWISE:
+            g = F.grid_sample(fmap.permute(0, 3, 1, 2), xy.unsqueeze(2), align_corners=True, mode="bilinear", padding_mode="border")
+            return g[..., 0].reshape(g.shape[0], g.shape[1], N, HWD).permute(0, 2, 3, 1)
+        return bilinear_gather(fmap, xy).reshape(fmap.shape[0], N, HWD, fmap.shape[-1])
 
     ref_feat = sample(feat, cams)
     inp_feat = sample(in_feat, in_cams).expand(V, -1, -1, -1)

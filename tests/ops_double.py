@@ -591,3 +591,22 @@ class TorchOpsDouble:
                 (g,) = torch.autograd.grad(out, v, dy.detach().reshape(-1)[: rows * cols])
             dx.reshape(-1)[:n_in].copy_(g)
         return self._call(fn)
+
+    def _gather_grid(self, xy, V, P):
+        return xy.reshape(-1)[: V * P * 2].reshape(V, P, 1, 2)
+
+    def bilinear_gather_fwd(self, fmap, xy, out, V, H, W, C, P):
+        def fn():
+            m = fmap.reshape(-1)[: V * H * W * C].reshape(V, H, W, C).permute(0, 3, 1, 2)
+            g = F.grid_sample(m, self._gather_grid(xy, V, P), mode="bilinear", padding_mode="border", align_corners=True)   # [V, C, P, 1]
+            out.reshape(-1)[: V * P * C].copy_(g[..., 0].permute(0, 2, 1).reshape(-1))
+        return self._call(fn)
+
+    def bilinear_gather_bwd(self, dout, xy, dfmap, V, H, W, C, P):
+        def fn():
+            with torch.enable_grad():
+                m = torch.zeros(V, C, H, W, requires_grad=True)
+                g = F.grid_sample(m, self._gather_grid(xy, V, P).detach(), mode="bilinear", padding_mode="border", align_corners=True)
+                (gm,) = torch.autograd.grad(g, m, dout.detach().reshape(-1)[: V * P * C].reshape(V, P, C).permute(0, 2, 1).unsqueeze(-1))
+            dfmap.reshape(-1)[: V * H * W * C].copy_(gm.permute(0, 2, 3, 1).reshape(-1))
+        return self._call(fn)

@@ -154,6 +154,13 @@ def _pointwise_cases():
         ins = [r(n, H, W, C, scale=1.5, shift=0.3), r(C, shift=1.0), r(C)]
         ref = lambda x, ga, be, act=act: (lambda y: F.silu(y) if act else y)(F.group_norm(x.permute(0, 3, 1, 2), 32, ga, be, 1e-5).permute(0, 2, 3, 1))
         cases.append((f"groupnorm_{n}x{H}x{W}x{C}_{'silu' if act else 'plain'}", (lambda x, ga, be, act=act: T._GroupNormFn.apply(x, ga, be, 1e-5, act)), ref, ins))
+    # bilinear gather (grid_sample, border clamp, align_corners): coordinates beyond [-1, 1] exercise the clamp; xy is not differentiated
+    for V, H, W, C, Pn in ((3, 8, 8, 256, 1000), (1, 32, 32, 64, 333), (2, 5, 7, 12, 50)):
+        xy = (torch.rand(V, Pn, 2, generator=g) * 2.6 - 1.3)
+        xy[:, :4] = torch.tensor([[-1.0, -1.0], [1.0, 1.0], [1.0, -1.0], [0.0, 0.0]])      # exact corners / centre
+        ref = lambda m, xy=xy: F.grid_sample(m.permute(0, 3, 1, 2), xy.to(m.dtype).unsqueeze(2), mode="bilinear", padding_mode="border",
+                                             align_corners=True)[..., 0].permute(0, 2, 1)
+        cases.append((f"gather_{V}x{H}x{W}x{C}_P{Pn}", (lambda m, xy=xy: T.bilinear_gather(m, xy.to(m.device))), ref, [r(V, H, W, C)]))
     cases.append(("gelu_tail", T.gelu, F.gelu, [r(7, 331, scale=2.0)]))
     cases.append(("gelu_vec", T.gelu, F.gelu, [r(64, 512, scale=2.0)]))
     cases.append(("silu", T.silu, F.silu, [r(2, 1280, scale=3.0)]))
@@ -216,7 +223,8 @@ def test_pointwise_kernel_source_on_the_cpu_shim(tmp_path, monkeypatch):
     import mvdfusion_b200.runtime as rt
     from mvdfusion_b200 import _lib, ops as OPS
     lib = ctypes.CDLL(_build_cpu_shim(tmp_path))
-    for name in ("mvd_layernorm_fwd_f32", "mvd_layernorm_bwd_f32", "mvd_groupnorm_fwd_f32", "mvd_groupnorm_bwd_f32", "mvd_act_fwd_f32", "mvd_act_bwd_f32"):
+    for name in ("mvd_layernorm_fwd_f32", "mvd_layernorm_bwd_f32", "mvd_groupnorm_fwd_f32", "mvd_groupnorm_bwd_f32", "mvd_act_fwd_f32", "mvd_act_bwd_f32",
+                 "mvd_bilinear_gather_fwd_f32", "mvd_bilinear_gather_bwd_f32"):
         getattr(lib, name).argtypes = _lib.SIGNATURES[name]
         getattr(lib, name).restype = ctypes.c_int32
 
@@ -228,4 +236,4 @@ def test_pointwise_kernel_source_on_the_cpu_shim(tmp_path, monkeypatch):
     monkeypatch.setattr(OPS, "_ptr", lambda t, dtype=None: None if t is None else (t.data_ptr() if dtype is None or t.dtype == dtype else (_ for _ in ()).throw(OPS.MvdError(f"expected {dtype}, got {t.dtype}"))))
     monkeypatch.setattr(rt, "get_ops", lambda dev: shim)
     worst = _check_pointwise("cpu", 2e-5)
-    assert len(worst) >= 13
+    assert len(worst) >= 16

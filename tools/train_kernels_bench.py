@@ -91,6 +91,16 @@ def main():
     record("gelu_fwd 196608x512", us, 8 * n_el, 8 * n_el)
     us = timed([ops.act_bwd(ds[i], xs[i], ys[i], 1, n_el, OPS.ACT_GELU) for i in range(k)])
     record("gelu_bwd 196608x512", us, 12 * n_el, 12 * n_el)
+    del xs, ys, ds
+    # GridAttn's bilinear gather: V = 8 maps of 32 x 32 x 256, P = N HW D = 24576 points per view (the maps stay L2-resident; the rows stream)
+    V, S, C, Pn = 8, 32, 256, 24576
+    fm, xy = r(V, S, S, C), torch.rand(V, Pn, 2, device="cuda") * 2.2 - 1.1
+    k = copies(V * Pn * C * 4)
+    outs, dms = [torch.empty(V, Pn, C, device="cuda") for _ in range(k)], [torch.empty(V, S, S, C, device="cuda") for _ in range(k)]
+    us = timed([ops.bilinear_gather_fwd(fm, xy, outs[i], V, S, S, C, Pn) for i in range(k)])
+    record(f"bilinear_gather_fwd V{V} {S}x{S}x{C} P{Pn}", us, 4 * V * Pn * C + 4 * V * S * S * C, 4 * V * Pn * C + 4 * V * S * S * C)
+    us = timed([ops.bilinear_gather_bwd(outs[i], xy, dms[i], V, S, S, C, Pn) for i in range(k)])
+    record(f"bilinear_gather_bwd V{V} {S}x{S}x{C} P{Pn}", us, 4 * V * Pn * C + 4 * V * S * S * C, 4 * V * Pn * C + 8 * V * S * S * C)
     print(json.dumps({"what": "csrc/train.cu kernels, CUDA-event timed, buffers rotating through > 300 MB (HBM-resident inputs)", "hbm_peak_gbs": peak,
                       "peak_source": "MEASURED_PEAKS.json (copy bandwidth)", "gpu": torch.cuda.get_device_name(0), "rows": rows}))
 
