@@ -319,7 +319,9 @@ int mvd_layernorm_bwd_f32(const float* dy, const float* x, const float* gamma, c
                           float* dbeta, int32_t rows, int32_t C, void* stream);
 /* GroupNorm32 (+ SiLU) on x fp32 [n_img, hw, C], 32 groups (external/sd1/ldm/modules/diffusionmodules/util.py:204-216,
  * openaimodel.py:199-203,224-228; attention.py:242).  stats fp32 [n_img, 32, 2] = (mean, rstd) per (image, group), written by the
- * forward and read by the backward; ws: scratch of n_img * 32 * 24 bytes, 8-byte aligned (fp64 group sums). */
+ * forward and read by the backward; ws: scratch of n_img * 16384 bytes, 16-byte aligned (ABI 17: fp64 per-chunk group partials, <= 32
+ * chunks x 32 groups x 2 per image — two launches each way, no memset / atomics on the statistics).  dgamma / dbeta are zeroed by the
+ * backward call (one memset when dbeta == dgamma + C). */
 int mvd_groupnorm_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* stats, void* ws, int32_t n_img,
                           int32_t hw, int32_t C, float eps, int32_t apply_silu, void* stream);
 int mvd_groupnorm_bwd_f32(const float* dy, const float* x, const float* gamma, const float* beta, const float* stats, float* dx,

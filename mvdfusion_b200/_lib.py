@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_float, c_int32, c_longlong, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # MVD_B200_LIB: another build of the same library (e.g. the instrumented `make trace` one); it must exist — there is no fallback
 LIB_PATH = os.environ.get("MVD_B200_LIB") or os.path.join(_HERE, "libmvd_b200.so")
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 
 class GemmArgs(ctypes.Structure):

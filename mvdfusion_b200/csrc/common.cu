@@ -109,5 +109,5 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, int n, int h, int w, int 
 }  // namespace mvd
 
 extern "C" const char* mvd_last_error(void) { return mvd::g_err; }
-extern "C" int mvd_abi_version(void) { return 16; }
+extern "C" int mvd_abi_version(void) { return 17; }
 extern "C" long long mvd_launch_count(void) { return mvd::g_launches.load(std::memory_order_relaxed); }

@@ -7,8 +7,8 @@
 //
 // All of them are HBM-bound streaming passes: activations are fp32 [rows, C] (row = (image*H + y)*W + x), consecutive threads read
 // consecutive channels, every per-channel / per-group constant is loaded once per thread and kept in registers over the pixel loop.
-// Reductions over rows (dgamma, dbeta, group sums) end in atomics on small zero-initialised vectors: fp32 for the parameter
-// gradients, fp64 for the (sum, sum of squares) of a group, whose difference is the variance.
+// Parameter gradients (dgamma, dbeta) end in fp32 atomics on small zero-initialised vectors; the (sum, sum of squares) of a group,
+// whose difference is the variance, is carried in fp64 through per-chunk partials with one writer each.
 // The launches are plain stream launches (no programmatic dependent launch): in the training graph their neighbours are ATen kernels.
 #ifdef MVD_CPU_EMULATION
 // test infrastructure: the same source compiled as plain C++ and run on host threads (tests/native/cpu_emul/cuda_on_cpu.h), so that
@@ -24,8 +24,6 @@
 
 namespace mvd {
 namespace {
-
-constexpr int GN_PX = 16;  // pixels per CTA of the GroupNorm passes
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -145,134 +143,147 @@ __global__ void ln_bwd_param_kernel(const float* __restrict__ dy, const float* _
 }
 
 // ---------------------------------------------------------------------------------------------- GroupNorm (32 groups, channels-last)
-// grid (pixel chunks, channel blocks, images); thread = one channel, loop over the chunk's pixels
-__global__ void gn_sums_kernel(const float* __restrict__ x, double* __restrict__ ws, int hw, int C, int cpg) {
-  __shared__ double sh[2][256];
-  const int tid = threadIdx.x, n = blockIdx.z;
-  const int cb = blockIdx.y * blockDim.x;
-  const int c = cb + tid;
-  const int p0 = blockIdx.x * GN_PX, p1 = min(hw, p0 + GN_PX);
-  const int g0 = cb / cpg;
-  sh[0][tid] = 0.0;
-  sh[1][tid] = 0.0;
+// Two launches each way, no memset, no global atomics on the statistics.  grid = (pixel chunks, channel blocks, images); a channel
+// block covers `gpb` WHOLE groups (gpb * cpg <= 256 channels), thread = one channel, loop over the chunk's pixels with independent
+// loads in flight.  Pass 1 leaves the chunk's per-group partial sums as fp64 pairs in ws[image][chunk][group] (exactly one writer per
+// slot); pass 2 sums the <= 32 chunk partials of its group (broadcast loads), forms the statistics, and streams the pixels again.
+struct GnDims {
+  int hw, C, cpg, gpb, px, chunks;
+};
+
+struct GnThread {
+  int c, g, lg, p0, p1;
+  bool valid;
+};
+__device__ __forceinline__ GnThread gn_thread(const GnDims& d) {
+  GnThread t;
+  const int tid = threadIdx.x;
+  t.lg = tid / d.cpg;
+  t.g = blockIdx.y * d.gpb + t.lg;
+  t.c = blockIdx.y * d.gpb * d.cpg + tid;
+  t.valid = tid < d.gpb * d.cpg && t.g < 32;
+  t.p0 = blockIdx.x * d.px;
+  t.p1 = min(d.hw, t.p0 + d.px);
+  return t;
+}
+
+// the block's per-group (u, v) pairs -> ws[image][chunk][group]; sh is zeroed here, every valid thread adds its pair
+__device__ __forceinline__ void gn_store_partials(double (*sh)[32], const GnThread& t, const GnDims& d, float u, float v, double* ws) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 64; i += blockDim.x) sh[i >> 5][i & 31] = 0.0;
   __syncthreads();
-  if (c < C) {
-    const float* xp = x + (static_cast<size_t>(n) * hw + p0) * C + c;
-    float s = 0.f, q = 0.f;
-    for (int p = p0; p < p1; ++p, xp += C) {
+  if (t.valid) {
+    atomicAdd(&sh[0][t.lg], static_cast<double>(u));
+    atomicAdd(&sh[1][t.lg], static_cast<double>(v));
+  }
+  __syncthreads();
+  if (tid < d.gpb && blockIdx.y * d.gpb + tid < 32) {
+    double* w = ws + ((static_cast<size_t>(blockIdx.z) * d.chunks + blockIdx.x) * 32 + blockIdx.y * d.gpb + tid) * 2;
+    w[0] = sh[0][tid];
+    w[1] = sh[1][tid];
+  }
+}
+
+// sum of the group's chunk partials
+__device__ __forceinline__ void gn_sum_partials(const double* __restrict__ ws, const GnDims& d, int g, double& u, double& v) {
+  const double* w = ws + (static_cast<size_t>(blockIdx.z) * d.chunks * 32 + g) * 2;
+  u = 0.0;
+  v = 0.0;
+  for (int ch = 0; ch < d.chunks; ++ch, w += 64) {
+    u += w[0];
+    v += w[1];
+  }
+}
+
+__global__ void gn_partials_kernel(const float* __restrict__ x, double* __restrict__ ws, GnDims d) {
+  __shared__ double sh[2][32];
+  const GnThread t = gn_thread(d);
+  float s = 0.f, q = 0.f;
+  if (t.valid) {
+    const float* xp = x + (static_cast<size_t>(blockIdx.z) * d.hw + t.p0) * d.C + t.c;
+#pragma unroll 8
+    for (int p = t.p0; p < t.p1; ++p, xp += d.C) {
       const float v = *xp;
       s += v;
       q += v * v;
     }
-    const int lg = c / cpg - g0;
-    atomicAdd(&sh[0][lg], static_cast<double>(s));
-    atomicAdd(&sh[1][lg], static_cast<double>(q));
   }
-  __syncthreads();
-  const int cend = min(C, cb + static_cast<int>(blockDim.x));
-  const int nl = (cend - 1) / cpg - g0 + 1;
-  if (tid < nl) {
-    double* w = ws + (static_cast<size_t>(n) * 32 + g0 + tid) * 2;
-    atomicAdd(w, sh[0][tid]);
-    atomicAdd(w + 1, sh[1][tid]);
-  }
-}
-
-// (sum, sum of squares) -> (mean, rstd); m = elements per group
-__global__ void gn_finalize_kernel(const double* __restrict__ ws, float* __restrict__ stats, int count, double m, double eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const double mean = ws[2 * i] / m;
-  double var = ws[2 * i + 1] / m - mean * mean;
-  var = var > 0.0 ? var : 0.0;
-  stats[2 * i] = static_cast<float>(mean);
-  stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + eps));
+  gn_store_partials(sh, t, d, s, q, ws);
 }
 
 __global__ void gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ stats, float* __restrict__ y, int hw, int C, int cpg, int silu) {
-  const int n = blockIdx.z;
-  const int c = blockIdx.y * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const int p0 = blockIdx.x * GN_PX, p1 = min(hw, p0 + GN_PX);
-  const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + n * 32 + c / cpg);
-  const float sc = st.y * __ldg(gamma + c);
-  const float be = __ldg(beta + c);
-  size_t o = (static_cast<size_t>(n) * hw + p0) * C + c;
-  for (int p = p0; p < p1; ++p, o += C) {
-    float v = (x[o] - st.x) * sc + be;
+                                const double* __restrict__ ws, float* __restrict__ stats, float* __restrict__ y, GnDims d, double eps,
+                                int silu) {
+  const GnThread t = gn_thread(d);
+  if (!t.valid) return;
+  double su, sq;
+  gn_sum_partials(ws, d, t.g, su, sq);
+  const double m = static_cast<double>(d.hw) * d.cpg;
+  const double mean_d = su / m;
+  double var = sq / m - mean_d * mean_d;
+  var = var > 0.0 ? var : 0.0;
+  const float mean = static_cast<float>(mean_d), rstd = static_cast<float>(1.0 / sqrt(var + eps));
+  if (blockIdx.x == 0 && threadIdx.x == t.lg * d.cpg) {  // the group's first channel thread of the first chunk: (mean, rstd) for the backward
+    stats[(static_cast<size_t>(blockIdx.z) * 32 + t.g) * 2] = mean;
+    stats[(static_cast<size_t>(blockIdx.z) * 32 + t.g) * 2 + 1] = rstd;
+  }
+  const float sc = rstd * __ldg(gamma + t.c);
+  const float be = __ldg(beta + t.c);
+  size_t o = (static_cast<size_t>(blockIdx.z) * d.hw + t.p0) * d.C + t.c;
+#pragma unroll 8
+  for (int p = t.p0; p < t.p1; ++p, o += d.C) {
+    float v = (x[o] - mean) * sc + be;
     if (silu) v = silu_f(v);
     y[o] = v;
   }
 }
 
-// per channel: a = sum dz, b = sum dz * xhat over the chunk -> dbeta, dgamma (fp32 atomics) and the group's
-// (sum dz * gamma, sum dz * gamma * xhat) (fp64 atomics);  dz = dy * silu'(xhat * gamma + beta) or dy
-__global__ void gn_bwd_sums_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, const float* __restrict__ stats, float* __restrict__ dgamma,
-                                   float* __restrict__ dbeta, double* __restrict__ ws, int hw, int C, int cpg, int silu) {
-  __shared__ double sh[2][256];
-  const int tid = threadIdx.x, n = blockIdx.z;
-  const int cb = blockIdx.y * blockDim.x;
-  const int c = cb + tid;
-  const int p0 = blockIdx.x * GN_PX, p1 = min(hw, p0 + GN_PX);
-  const int g0 = cb / cpg;
-  sh[0][tid] = 0.0;
-  sh[1][tid] = 0.0;
-  __syncthreads();
-  if (c < C) {
-    const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + n * 32 + c / cpg);
-    const float ga = __ldg(gamma + c), be = __ldg(beta + c);
-    size_t o = (static_cast<size_t>(n) * hw + p0) * C + c;
-    float a = 0.f, b = 0.f;
-    for (int p = p0; p < p1; ++p, o += C) {
+// per channel: a = sum dz, b = sum dz * xhat over the chunk -> dbeta, dgamma (fp32 atomics on the zeroed vectors) and the group's
+// (sum dz * gamma, sum dz * gamma * xhat) partials;  dz = dy * silu'(xhat * gamma + beta) or dy
+__global__ void gn_bwd_partials_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const float* __restrict__ stats, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, double* __restrict__ ws, GnDims d, int silu) {
+  __shared__ double sh[2][32];
+  const GnThread t = gn_thread(d);
+  float a = 0.f, b = 0.f, ga = 0.f;
+  if (t.valid) {
+    const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + blockIdx.z * 32 + t.g);
+    ga = __ldg(gamma + t.c);
+    const float be = __ldg(beta + t.c);
+    size_t o = (static_cast<size_t>(blockIdx.z) * d.hw + t.p0) * d.C + t.c;
+#pragma unroll 8
+    for (int p = t.p0; p < t.p1; ++p, o += d.C) {
       const float xh = (x[o] - st.x) * st.y;
       float dz = dy[o];
       if (silu) dz *= silu_d(xh * ga + be);
       a += dz;
       b += dz * xh;
     }
-    atomicAdd(dbeta + c, a);
-    atomicAdd(dgamma + c, b);
-    const int lg = c / cpg - g0;
-    atomicAdd(&sh[0][lg], static_cast<double>(a * ga));
-    atomicAdd(&sh[1][lg], static_cast<double>(b * ga));
+    atomicAdd(dbeta + t.c, a);
+    atomicAdd(dgamma + t.c, b);
   }
-  __syncthreads();
-  const int cend = min(C, cb + static_cast<int>(blockDim.x));
-  const int nl = (cend - 1) / cpg - g0 + 1;
-  if (tid < nl) {
-    double* w = ws + (static_cast<size_t>(n) * 32 + g0 + tid) * 2;
-    atomicAdd(w, sh[0][tid]);
-    atomicAdd(w + 1, sh[1][tid]);
-  }
-}
-
-// group sums / m as fp32 pairs behind the fp64 accumulators
-__global__ void gn_bwd_finalize_kernel(const double* __restrict__ ws, float* __restrict__ red, int count, double m) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  red[2 * i] = static_cast<float>(ws[2 * i] / m);
-  red[2 * i + 1] = static_cast<float>(ws[2 * i + 1] / m);
+  gn_store_partials(sh, t, d, a * ga, b * ga, ws);
 }
 
 // dx = rstd * (dz * gamma - s1 / m - xhat * s2 / m)
 __global__ void gn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, const float* __restrict__ stats, const float* __restrict__ red,
-                                    float* __restrict__ dx, int hw, int C, int cpg, int silu) {
-  const int n = blockIdx.z;
-  const int c = blockIdx.y * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const int p0 = blockIdx.x * GN_PX, p1 = min(hw, p0 + GN_PX);
-  const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + n * 32 + c / cpg);
-  const float2 rd = __ldg(reinterpret_cast<const float2*>(red) + n * 32 + c / cpg);
-  const float ga = __ldg(gamma + c), be = __ldg(beta + c);
-  size_t o = (static_cast<size_t>(n) * hw + p0) * C + c;
-  for (int p = p0; p < p1; ++p, o += C) {
+                                    const float* __restrict__ beta, const float* __restrict__ stats, const double* __restrict__ ws,
+                                    float* __restrict__ dx, GnDims d, int silu) {
+  const GnThread t = gn_thread(d);
+  if (!t.valid) return;
+  double s1d, s2d;
+  gn_sum_partials(ws, d, t.g, s1d, s2d);
+  const double m = static_cast<double>(d.hw) * d.cpg;
+  const float s1 = static_cast<float>(s1d / m), s2 = static_cast<float>(s2d / m);
+  const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + blockIdx.z * 32 + t.g);
+  const float ga = __ldg(gamma + t.c), be = __ldg(beta + t.c);
+  size_t o = (static_cast<size_t>(blockIdx.z) * d.hw + t.p0) * d.C + t.c;
+#pragma unroll 8
+  for (int p = t.p0; p < t.p1; ++p, o += d.C) {
     const float xh = (x[o] - st.x) * st.y;
     float dz = dy[o];
     if (silu) dz *= silu_d(xh * ga + be);
-    dx[o] = st.y * (dz * ga - rd.x - xh * rd.y);
+    dx[o] = st.y * (dz * ga - s1 - xh * s2);
   }
 }
 
@@ -402,14 +413,19 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 struct GnGeometry {
   dim3 grid, block;
-  int cpg;
+  GnDims d;
 };
 inline GnGeometry gn_geometry(int n_img, int hw, int C) {
   GnGeometry g;
-  const int bd = C >= 256 ? 256 : ((C + 31) / 32) * 32;
-  g.block = dim3(bd);
-  g.grid = dim3((hw + GN_PX - 1) / GN_PX, (C + bd - 1) / bd, n_img);
-  g.cpg = C / 32;
+  GnDims& d = g.d;
+  d.hw = hw;
+  d.C = C;
+  d.cpg = C / 32;
+  d.gpb = 256 / d.cpg < 1 ? 1 : (256 / d.cpg > 32 ? 32 : 256 / d.cpg);  // whole groups per block, <= 256 channels
+  d.px = (hw + 31) / 32 < 8 ? 8 : (hw + 31) / 32;                           // <= 32 chunks per image, >= 8 pixels per thread
+  d.chunks = (hw + d.px - 1) / d.px;
+  g.block = dim3(((d.gpb * d.cpg + 31) / 32) * 32);
+  g.grid = dim3(d.chunks, (32 + d.gpb - 1) / d.gpb, n_img);
   return g;
 }
 
@@ -483,18 +499,15 @@ extern "C" int mvd_groupnorm_fwd_f32(const float* x, const float* gamma, const f
                                      int32_t n_img, int32_t hw, int32_t C, float eps, int32_t apply_silu, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !gamma || !beta || !y || !stats || !ws) return set_error(MVD_EINVAL, "mvd_groupnorm_fwd_f32: null pointer");
-  if (n_img <= 0 || hw <= 0 || C <= 0 || (C % 32) != 0 || n_img > 65535)
-    return set_error(MVD_EINVAL, "mvd_groupnorm_fwd_f32: C must be a multiple of 32 (32 groups), n_img <= 65535");
-  if ((reinterpret_cast<uintptr_t>(ws) & 7) || (reinterpret_cast<uintptr_t>(stats) & 7))
-    return set_error(MVD_EALIGN, "mvd_groupnorm_fwd_f32: ws / stats must be 8-byte aligned");
+  if (n_img <= 0 || hw <= 0 || C <= 0 || (C % 32) != 0 || C > 8192 || n_img > 65535)
+    return set_error(MVD_EINVAL, "mvd_groupnorm_fwd_f32: C must be a multiple of 32 (32 groups) and <= 8192, n_img <= 65535");
+  if ((reinterpret_cast<uintptr_t>(ws) & 15) || (reinterpret_cast<uintptr_t>(stats) & 7))
+    return set_error(MVD_EALIGN, "mvd_groupnorm_fwd_f32: ws must be 16-byte, stats 8-byte aligned");
   const GnGeometry g = gn_geometry(n_img, hw, C);
-  const int count = n_img * 32;
-  double* sums = static_cast<double*>(ws);
-  MVD_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * count, stream));
-  MVD_KLAUNCH(gn_sums_kernel, g.grid, g.block, stream, x, sums, hw, C, g.cpg);
-  MVD_KLAUNCH(gn_finalize_kernel, (count + 127) / 128, 128, stream, sums, stats, count, static_cast<double>(hw) * g.cpg, static_cast<double>(eps));
-  MVD_KLAUNCH(gn_apply_kernel, g.grid, g.block, stream, x, gamma, beta, stats, y, hw, C, g.cpg, apply_silu);
-  count_launch(3);
+  double* part = static_cast<double*>(ws);
+  MVD_KLAUNCH(gn_partials_kernel, g.grid, g.block, stream, x, part, g.d);
+  MVD_KLAUNCH(gn_apply_kernel, g.grid, g.block, stream, x, gamma, beta, part, stats, y, g.d, static_cast<double>(eps), apply_silu);
+  count_launch(2);
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
 }
@@ -505,21 +518,21 @@ extern "C" int mvd_groupnorm_bwd_f32(const float* dy, const float* x, const floa
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!dy || !x || !gamma || !beta || !stats || !dx || !dgamma || !dbeta || !ws)
     return set_error(MVD_EINVAL, "mvd_groupnorm_bwd_f32: null pointer");
-  if (n_img <= 0 || hw <= 0 || C <= 0 || (C % 32) != 0 || n_img > 65535)
-    return set_error(MVD_EINVAL, "mvd_groupnorm_bwd_f32: C must be a multiple of 32 (32 groups), n_img <= 65535");
-  if ((reinterpret_cast<uintptr_t>(ws) & 7) || (reinterpret_cast<uintptr_t>(stats) & 7))
-    return set_error(MVD_EALIGN, "mvd_groupnorm_bwd_f32: ws / stats must be 8-byte aligned");
+  if (n_img <= 0 || hw <= 0 || C <= 0 || (C % 32) != 0 || C > 8192 || n_img > 65535)
+    return set_error(MVD_EINVAL, "mvd_groupnorm_bwd_f32: C must be a multiple of 32 (32 groups) and <= 8192, n_img <= 65535");
+  if ((reinterpret_cast<uintptr_t>(ws) & 15) || (reinterpret_cast<uintptr_t>(stats) & 7))
+    return set_error(MVD_EALIGN, "mvd_groupnorm_bwd_f32: ws must be 16-byte, stats 8-byte aligned");
   const GnGeometry g = gn_geometry(n_img, hw, C);
-  const int count = n_img * 32;
-  double* sums = static_cast<double*>(ws);
-  float* red = reinterpret_cast<float*>(sums + 2 * static_cast<size_t>(count));
-  MVD_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * count, stream));
-  MVD_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, stream));
-  MVD_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, sizeof(float) * C, stream));
-  MVD_KLAUNCH(gn_bwd_sums_kernel, g.grid, g.block, stream, dy, x, gamma, beta, stats, dgamma, dbeta, sums, hw, C, g.cpg, apply_silu);
-  MVD_KLAUNCH(gn_bwd_finalize_kernel, (count + 127) / 128, 128, stream, sums, red, count, static_cast<double>(hw) * g.cpg);
-  MVD_KLAUNCH(gn_bwd_apply_kernel, g.grid, g.block, stream, dy, x, gamma, beta, stats, red, dx, hw, C, g.cpg, apply_silu);
-  count_launch(3);
+  double* part = static_cast<double*>(ws);
+  if (dbeta == dgamma + C) {  // one vector [2, C]: one memset
+    MVD_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, sizeof(float) * 2 * C, stream));
+  } else {
+    MVD_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, stream));
+    MVD_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, sizeof(float) * C, stream));
+  }
+  MVD_KLAUNCH(gn_bwd_partials_kernel, g.grid, g.block, stream, dy, x, gamma, beta, stats, dgamma, dbeta, part, g.d, apply_silu);
+  MVD_KLAUNCH(gn_bwd_apply_kernel, g.grid, g.block, stream, dy, x, gamma, beta, stats, part, dx, g.d, apply_silu);
+  count_launch(2);
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
 }

@@ -13,7 +13,7 @@ from . import _lib
 
 A_ROWMAJOR, A_CONV3X3 = 0, 1
 ACT_NONE, ACT_GELU, ACT_SILU, ACT_GEGLU = 0, 1, 2, 3
-GN_WS_BYTES_PER_GROUP = 24   # mvd_groupnorm_{fwd,bwd}_f32 scratch: n_img * 32 groups * (2 fp64 sums + 2 fp32 means)
+GN_WS_BYTES_PER_IMAGE = 16384   # mvd_groupnorm_{fwd,bwd}_f32 scratch per image: <= 32 chunks x 32 groups x 2 fp64 partials
 OUT_F32, OUT_F16, OUT_QKV_HEADS = 0, 1, 2
 
 
@@ -359,8 +359,8 @@ class NativeOps:
                                                                      "bytes": (12.0 + (8.0 if dgamma is not None else 0.0)) * rows * C})
 
     def groupnorm_fwd(self, x, gamma, beta, y, stats, ws, n_img, hw, C, eps, silu):
-        """x, y fp32 [n_img, hw, C]; stats fp32 [n_img, 32, 2]; ws: uint8 scratch of n_img * 32 * GN_WS_BYTES_PER_GROUP bytes"""
-        if ws.numel() < n_img * 32 * GN_WS_BYTES_PER_GROUP:
+        """x, y fp32 [n_img, hw, C]; stats fp32 [n_img, 32, 2]; ws: uint8 scratch of n_img * GN_WS_BYTES_PER_IMAGE bytes"""
+        if ws.numel() < n_img * GN_WS_BYTES_PER_IMAGE:
             raise MvdError("groupnorm_fwd: workspace too small")
         return self._bind("mvd_groupnorm_fwd_f32", (_ptr(x, torch.float32), _ptr(gamma, torch.float32), _ptr(beta, torch.float32),
                                                     _ptr(y, torch.float32), _ptr(stats, torch.float32), _ptr(ws, torch.uint8), n_img, hw, C,
@@ -368,7 +368,7 @@ class NativeOps:
                           (x, gamma, beta, y, stats, ws), {"kernel": "train_groupnorm", "desc": f"img{n_img} hw{hw} C{C}", "bytes": 12.0 * n_img * hw * C})
 
     def groupnorm_bwd(self, dy, x, gamma, beta, stats, dx, dgamma, dbeta, ws, n_img, hw, C, silu):
-        if ws.numel() < n_img * 32 * GN_WS_BYTES_PER_GROUP:
+        if ws.numel() < n_img * GN_WS_BYTES_PER_IMAGE:
             raise MvdError("groupnorm_bwd: workspace too small")
         return self._bind("mvd_groupnorm_bwd_f32", (_ptr(dy, torch.float32), _ptr(x, torch.float32), _ptr(gamma, torch.float32),
                                                     _ptr(beta, torch.float32), _ptr(stats, torch.float32), _ptr(dx, torch.float32),

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2 visit X (1 GPU, ~1 minute): the ABI-16 bilinear gather kernels on hardware — pointwise + training-gradient tests, micro-benchmark
+# Round-2 visit X / Y (1 GPU, ~1 minute each): the ABI-16 bilinear gather kernels, then the ABI-17 two-launch GroupNorm, on hardware — pointwise + training-gradient tests, micro-benchmark
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 120 python -m pytest tests/test_training.py tests/test_lib_abi.py -q -m gpu -s > gpurun_out/x_train.log 2>&1

@@ -68,8 +68,9 @@ def main():
         k = copies(e * 4)
         xs, ys, ds = [r(n, hw, C) for _ in range(k)], [torch.empty(n, hw, C, device="cuda") for _ in range(k)], [r(n, hw, C) for _ in range(k)]
         g, b = r(C), r(C)
-        st, ws = torch.empty(n, 32, 2, device="cuda"), torch.empty(n * 32 * 24, dtype=torch.uint8, device="cuda")
-        dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+        st, ws = torch.empty(n, 32, 2, device="cuda"), torch.empty(n * 16384, dtype=torch.uint8, device="cuda")
+        dgb = torch.empty(2, C, device="cuda")
+        dg, db = dgb[0], dgb[1]
         us = timed([ops.groupnorm_fwd(xs[i], g, b, ys[i], st, ws, n, hw, C, 1e-5, True) for i in range(k)])
         record(f"groupnorm_silu_fwd {n}x{hw}x{C}", us, 8 * e, 12 * e)
         us = timed([ops.groupnorm_bwd(ds[i], xs[i], g, b, st, ys[i], dg, db, ws, n, hw, C, True) for i in range(k)])
