@@ -9,7 +9,8 @@
 // consecutive channels, every per-channel / per-group constant is loaded once per thread and kept in registers over the pixel loop.
 // Parameter gradients (dgamma, dbeta) end in fp32 atomics on small zero-initialised vectors; the (sum, sum of squares) of a group,
 // whose difference is the variance, is carried in fp64 through per-chunk partials with one writer each.
-// The launches are plain stream launches (no programmatic dependent launch): in the training graph their neighbours are ATen kernels.
+// The launches are plain stream launches (their neighbours in the training graph are ATen kernels); only the second kernel of a
+// GroupNorm pair carries the programmatic-dependent-launch attribute.
 #ifdef MVD_CPU_EMULATION
 // test infrastructure: the same source compiled as plain C++ and run on host threads (tests/native/cpu_emul/cuda_on_cpu.h), so that
 // the kernels' indexing and arithmetic are checked in a container without a GPU; the product is the nvcc build below
@@ -19,7 +20,12 @@
 #include <stdint.h>
 
 #include "common.h"
+#include "ptx.cuh"
 #define MVD_KLAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
+// second kernel of a pair: launched with the programmatic-dependent-launch attribute (common.h) so that its launch overlaps the first
+// one's tail; it calls pdl_wait() before touching memory
+#define MVD_KLAUNCH_PDL(kernel, grid, block, stream, ...) \
+  MVD_CUDA_CHECK(::mvd::launch_kernel(kernel, dim3(grid), dim3(block), 0, stream, 1, __VA_ARGS__))
 #endif
 
 namespace mvd {
@@ -167,20 +173,28 @@ __device__ __forceinline__ GnThread gn_thread(const GnDims& d) {
   return t;
 }
 
-// the block's per-group (u, v) pairs -> ws[image][chunk][group]; sh is zeroed here, every valid thread adds its pair
-__device__ __forceinline__ void gn_store_partials(double (*sh)[32], const GnThread& t, const GnDims& d, float u, float v, double* ws) {
+// the block's per-group (u, v) pairs -> ws[image][chunk][group]: every thread parks its pair in shared memory, one warp per group
+// sums the group's cpg entries (shuffle reduction; no atomics), lane 0 stores the fp64 pair
+__device__ __forceinline__ void gn_store_partials(float (*sh)[256], const GnThread& t, const GnDims& d, float u, float v, double* ws) {
   const int tid = threadIdx.x;
-  for (int i = tid; i < 64; i += blockDim.x) sh[i >> 5][i & 31] = 0.0;
+  sh[0][tid] = t.valid ? u : 0.f;
+  sh[1][tid] = t.valid ? v : 0.f;
   __syncthreads();
-  if (t.valid) {
-    atomicAdd(&sh[0][t.lg], static_cast<double>(u));
-    atomicAdd(&sh[1][t.lg], static_cast<double>(v));
-  }
-  __syncthreads();
-  if (tid < d.gpb && blockIdx.y * d.gpb + tid < 32) {
-    double* w = ws + ((static_cast<size_t>(blockIdx.z) * d.chunks + blockIdx.x) * 32 + blockIdx.y * d.gpb + tid) * 2;
-    w[0] = sh[0][tid];
-    w[1] = sh[1][tid];
+  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  for (int lg = warp; lg < d.gpb; lg += nwarps) {  // uniform per warp
+    float a = 0.f, b = 0.f;
+    for (int j = lane; j < d.cpg; j += 32) {
+      a += sh[0][lg * d.cpg + j];
+      b += sh[1][lg * d.cpg + j];
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    const int g = blockIdx.y * d.gpb + lg;
+    if (lane == 0 && g < 32) {
+      double* w = ws + ((static_cast<size_t>(blockIdx.z) * d.chunks + blockIdx.x) * 32 + g) * 2;
+      w[0] = static_cast<double>(a);
+      w[1] = static_cast<double>(b);
+    }
   }
 }
 
@@ -196,7 +210,8 @@ __device__ __forceinline__ void gn_sum_partials(const double* __restrict__ ws, c
 }
 
 __global__ void gn_partials_kernel(const float* __restrict__ x, double* __restrict__ ws, GnDims d) {
-  __shared__ double sh[2][32];
+  __shared__ float sh[2][256];
+  pdl_trigger();  // the apply pass may be launched under this one's tail
   const GnThread t = gn_thread(d);
   float s = 0.f, q = 0.f;
   if (t.valid) {
@@ -214,6 +229,7 @@ __global__ void gn_partials_kernel(const float* __restrict__ x, double* __restri
 __global__ void gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const double* __restrict__ ws, float* __restrict__ stats, float* __restrict__ y, GnDims d, double eps,
                                 int silu) {
+  pdl_wait();  // launched with the PDL attribute behind gn_partials_kernel
   const GnThread t = gn_thread(d);
   if (!t.valid) return;
   double su, sq;
@@ -243,7 +259,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, const float* __rest
 __global__ void gn_bwd_partials_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, const float* __restrict__ stats, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, double* __restrict__ ws, GnDims d, int silu) {
-  __shared__ double sh[2][32];
+  __shared__ float sh[2][256];
+  pdl_trigger();
   const GnThread t = gn_thread(d);
   float a = 0.f, b = 0.f, ga = 0.f;
   if (t.valid) {
@@ -269,6 +286,7 @@ __global__ void gn_bwd_partials_kernel(const float* __restrict__ dy, const float
 __global__ void gn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, const float* __restrict__ stats, const double* __restrict__ ws,
                                     float* __restrict__ dx, GnDims d, int silu) {
+  pdl_wait();
   const GnThread t = gn_thread(d);
   if (!t.valid) return;
   double s1d, s2d;
@@ -506,7 +524,7 @@ extern "C" int mvd_groupnorm_fwd_f32(const float* x, const float* gamma, const f
   const GnGeometry g = gn_geometry(n_img, hw, C);
   double* part = static_cast<double*>(ws);
   MVD_KLAUNCH(gn_partials_kernel, g.grid, g.block, stream, x, part, g.d);
-  MVD_KLAUNCH(gn_apply_kernel, g.grid, g.block, stream, x, gamma, beta, part, stats, y, g.d, static_cast<double>(eps), apply_silu);
+  MVD_KLAUNCH_PDL(gn_apply_kernel, g.grid, g.block, stream, x, gamma, beta, part, stats, y, g.d, static_cast<double>(eps), apply_silu);
   count_launch(2);
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;
@@ -531,7 +549,7 @@ extern "C" int mvd_groupnorm_bwd_f32(const float* dy, const float* x, const floa
     MVD_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, sizeof(float) * C, stream));
   }
   MVD_KLAUNCH(gn_bwd_partials_kernel, g.grid, g.block, stream, dy, x, gamma, beta, stats, dgamma, dbeta, part, g.d, apply_silu);
-  MVD_KLAUNCH(gn_bwd_apply_kernel, g.grid, g.block, stream, dy, x, gamma, beta, stats, part, dx, g.d, apply_silu);
+  MVD_KLAUNCH_PDL(gn_bwd_apply_kernel, g.grid, g.block, stream, dy, x, gamma, beta, stats, part, dx, g.d, apply_silu);
   count_launch(2);
   MVD_CUDA_CHECK(cudaGetLastError());
   return MVD_OK;

@@ -172,6 +172,8 @@ inline int set_error(int code, const char* fmt, ...) {
   return code;
 }
 inline void count_launch(int = 1) {}
+inline void pdl_trigger() {}  // programmatic dependent launch: blocks and kernels run strictly in order here
+inline void pdl_wait() {}
 }  // namespace mvd
 
 #define MVD_CUDA_CHECK(expr)                                                      \
@@ -182,3 +184,4 @@ inline void count_launch(int = 1) {}
 // kernel<<<grid, block, 0, stream>>>(args...) of the real build
 #define MVD_KLAUNCH(kernel, grid, block, stream, ...) \
   cpu_emul::launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
+#define MVD_KLAUNCH_PDL(kernel, grid, block, stream, ...) MVD_KLAUNCH(kernel, grid, block, stream, __VA_ARGS__)
