@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--train-graph", action="store_true",
+                    help="--mode train on one GPU: capture forward + backward + AdamW of the training step in ONE CUDA graph and time its replays "
+                         "(the eager step is host-bound); experimental")
     ap.add_argument("--mode", default="replicas", choices=["shard", "replicas", "train"],
                     help="train: BASELINE configs[3] — forward + backward + AdamW of one scene per rank per step under DDP (not the headline metric)")
     ap.add_argument("--views", type=int, default=8)
@@ -515,7 +518,8 @@ def run_train(args):
         from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
         net.register_comm_hook(state=None, hook=default_hooks.bf16_compress_hook)
-    opt = torch.optim.AdamW([p_ for p_ in model.parameters() if p_.requires_grad], lr=1e-5)
+    use_graph = bool(getattr(args, "train_graph", False)) and world == 1
+    opt = torch.optim.AdamW([p_ for p_ in model.parameters() if p_.requires_grad], lr=1e-5, capturable=use_graph)
     tc = {"input_batch_size": 1, "train_batch_size": n, "random_views": False}
     batch = synthetic_dataset_batch(n + 1, 8 * S, seed=rank)
     images = batch.pop("images")
@@ -530,6 +534,30 @@ def run_train(args):
         loss.backward()
         opt.step()
         return loss
+
+    launches_per_replay = None
+    if use_graph:
+        # whole-step capture (the PyTorch whole-network recipe): eager warm-up on a side stream, gradients allocated inside the capture,
+        # AdamW(capturable=True); every replay draws fresh t / noise / depth jitter from the graph-registered generator
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        c_cap = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            static_loss = net(batch, tc)
+            static_loss.backward()
+            opt.step()
+        launches_per_replay = _lib.launch_count() - c_cap
+
+        def step():  # noqa: F811
+            graph.replay()
+            return static_loss
 
     for _ in range(Wm):
         loss = step()
@@ -548,7 +576,7 @@ def run_train(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
-    launches = _lib.launch_count() - c0
+    launches = _lib.launch_count() - c0 if launches_per_replay is None else launches_per_replay * K
     if rank == 0:
         f_fwd = (F_GRID_GFLOP * n * n * S * S * D + n * 235.8) * 1e9   # F_U(32, D=3) = 235.8 GFLOP per view
         emit({"metric": "training scenes/sec (forward + backward + AdamW, one scene of N views per rank per step)", "value": world * K / (ms * 1e-3),
@@ -558,7 +586,7 @@ def run_train(args):
                          "native": ("contractions (forward, dgrad, wgrad) on mvd_gemm_f16; norms / activations via ATen (MVD_TRAIN_ATEN_POINTWISE=1); attention cores / gather via ATen"
                                     if os.environ.get("MVD_TRAIN_ATEN_POINTWISE") == "1" else
                                     "contractions (forward, dgrad, wgrad) on mvd_gemm_f16; LayerNorm / GroupNorm+SiLU / GELU / SiLU / GEGLU forward + backward on csrc/train.cu (ABI 15); attention cores / gather via ATen")},
-              "gpu_launches": int(launches), "loss": float(loss), "finite": bool(torch.isfinite(loss)),
+              "cuda_graph": use_graph, "gpu_launches": int(launches), "loss": float(loss), "finite": bool(torch.isfinite(loss)),
               "achieved_tflops_per_gpu": round(3 * f_fwd * K / (ms * 1e-3) / 1e12, 2)})
     if world > 1:
         dist.barrier()

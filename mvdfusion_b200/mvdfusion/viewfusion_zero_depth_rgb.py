@@ -175,7 +175,13 @@ class ViewFusion(nn.Module):
         if trainer_config["random_views"]:
             rand = torch.randperm(B, generator=generator) if generator is not None else torch.randperm(B)
         else:
-            rand = torch.linspace(0, B - 1, n_in + n_tr).long()
+            # fixed view selection: the index vector lives on the batch's device, built once (indexing a CUDA tensor with a host index
+            # tensor is a synchronous copy per call — and not capturable in a CUDA graph)
+            cache = self.__dict__.setdefault("_fixed_view_idx", {})
+            key_ = (B, n_in, n_tr, str(dev))
+            if key_ not in cache:
+                cache[key_] = torch.linspace(0, B - 1, n_in + n_tr).long().to(dev)
+            rand = cache[key_]
         input_idx, batch_idx = rand[:n_in], rand[n_in:n_tr + n_in]
         if "latents" in batch:
             input_latents, batch_latents = batch["latents"][input_idx].float(), batch["latents"][batch_idx].float()

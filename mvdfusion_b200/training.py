@@ -474,7 +474,7 @@ def _plucker(o, d):
 def gridattn_forward(P, p, noisy, cams, in_cams, t_embed, sac, somac, depth_eps, input_latents, *, D, num_heads=8, depth_scale=2.0,
                      depth_shift=0.5):
     """GridAttn.forward + aggregate_features (mvdfusion/view_attn_efficient2.py:269-442) -> (N, S, S, D, 768).  sac / somac =
-    sqrt(alphas_cumprod)[t], sqrt(1 - alphas_cumprod)[t] (scalars); depth_eps (N, D, S, S) stands in for torch.normal's draw."""
+    sqrt(alphas_cumprod)[t], sqrt(1 - alphas_cumprod)[t] (scalars or 0-d tensors); depth_eps (N, D, S, S) stands in for torch.normal's draw."""
     N, _, S, _ = noisy.shape
     dev = noisy.device
     depth = (noisy[:, 4:] / sac).expand(-1, D, -1, -1) + (somac / sac / 10.0) * depth_eps
@@ -547,9 +547,9 @@ def apply_model_train(model, noisy, cams, input_latents, in_cams, clip_v_embed, 
     D = model.view_attn.n_pts_per_ray
     um = model.unet_model.unet_model
     cd = lambda c: {"R": c.R.float(), "T": c.T.float(), "f": c.focal_length.float(), "p": c.principal_point.float()}
-    t0 = int(t.reshape(-1)[0])
     sch = model.scheduler
-    sac, somac = float(sch.sqrt_alphas_cumprod[t0]), float(sch.sqrt_one_minus_alphas_cumprod[t0])
+    t0 = t.reshape(-1)[0]                                  # the shared timestep stays on the device: no host round trip, graph-capturable
+    sac, somac = sch.sqrt_alphas_cumprod[t0], sch.sqrt_one_minus_alphas_cumprod[t0]   # 0-d tensors
     if depth_eps is None:
         depth_eps = torch.randn(N, D, S, S, device=noisy.device)
     te = timestep_embedding(t.float(), 256)
