@@ -548,8 +548,10 @@ def apply_model_train(model, noisy, cams, input_latents, in_cams, clip_v_embed, 
     um = model.unet_model.unet_model
     cd = lambda c: {"R": c.R.float(), "T": c.T.float(), "f": c.focal_length.float(), "p": c.principal_point.float()}
     sch = model.scheduler
-    t0 = t.reshape(-1)[0]                                  # the shared timestep stays on the device: no host round trip, graph-capturable
-    sac, somac = sch.sqrt_alphas_cumprod[t0], sch.sqrt_one_minus_alphas_cumprod[t0]   # 0-d tensors
+    # the shared timestep stays on the device (no host round trip, graph-capturable).  Indexed with a 1-element vector: a 0-d index
+    # tensor would be read back as a Python integer (an implicit .item()), which is what stopped the first capture attempt
+    t0 = t.reshape(-1)[:1]
+    sac, somac = sch.sqrt_alphas_cumprod[t0].reshape(()), sch.sqrt_one_minus_alphas_cumprod[t0].reshape(())   # 0-d tensors
     if depth_eps is None:
         depth_eps = torch.randn(N, D, S, S, device=noisy.device)
     te = timestep_embedding(t.float(), 256)
