@@ -51,6 +51,9 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 #define MVD_LAUNCH(kernel, grid, block, smem, stream, ...) \
   MVD_CUDA_CHECK(::mvd::launch_kernel(kernel, dim3(grid), dim3(block), smem, stream, 1, __VA_ARGS__))
 
+// dynamic shared memory of a kernel as a typed array (a macro so that tests/native/cpu_emul can substitute a host buffer)
+#define MVD_DYNAMIC_SHARED(type, name) extern __shared__ type name[]
+
 // fp16 row-major matrix [rows, ld] of which [rows, cols] is addressable; box = box_cols x box_rows, 128B swizzle.
 int make_tmap_2d(CUtensorMap* out, const void* base, int cols, int rows, int ld, int box_cols, int box_rows);
 // fp16 3-D tensor [d2, d1, d0] with strides (ld1, ld2 elements); box (b0, b1, b2), 128B swizzle.

@@ -1,8 +1,13 @@
 // Data-movement / elementwise kernels of the UNet path (HBM/L2-bound; coalesced, vectorised):
 //   cast, channel concat, nearest x2 upsample, stride-2 im2col, small-M GEMV, sinusoidal timestep
 //   embedding, UNet input assembly, CFG combine + DDIM update.
+#ifdef MVD_CPU_EMULATION
+// test infrastructure: this file compiled as plain C++ and run on host threads (tests/native/cpu_emul/cuda_on_cpu.h)
+#include "cuda_on_cpu.h"
+#else
 #include "common.h"
 #include "ptx.cuh"
+#endif
 
 namespace mvd {
 
@@ -170,7 +175,7 @@ __global__ void gemv_grouped_kernel(const float* __restrict__ x, int K, int silu
                                     int n_jobs, int total_cols) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float gx[];  // act_in(x), K floats (zero-padded to a multiple of 8)
+  MVD_DYNAMIC_SHARED(float, gx);  // act_in(x), K floats (zero-padded to a multiple of 8)
   const int K8 = (K + 7) & ~7;
   for (int k = threadIdx.x; k < K8; k += blockDim.x) {
     float v = k < K ? x[k] : 0.f;

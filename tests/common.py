@@ -117,3 +117,44 @@ class fast_init:
         import torch.nn.init as I
         for n, f in self.saved.items():
             setattr(I, n, f)
+
+
+def build_cpu_shim(sources, out_dir, name="libmvd_cpuemul.so"):
+    """TEST INFRASTRUCTURE: compile kernel sources of mvdfusion_b200/csrc as plain C++ against tests/native/cpu_emul/cuda_on_cpu.h
+    (-DMVD_CPU_EMULATION: one host thread per CUDA thread of a block) into one shared object; returns its path."""
+    import subprocess
+    out = os.path.join(str(out_dir), name)
+    objs = []
+    for src in sources:
+        obj = os.path.join(str(out_dir), os.path.basename(src) + ".o")
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-x", "c++", "-DMVD_CPU_EMULATION", "-I", os.path.join(ROOT, "tests", "native", "cpu_emul"),
+                               "-fPIC", "-c", os.path.join(ROOT, "mvdfusion_b200", "csrc", src), "-o", obj])
+        objs.append(obj)
+    subprocess.check_call(["g++", "-shared", "-o", out] + objs + ["-lpthread"])
+    return out
+
+
+def shim_ops(lib_path, monkeypatch):
+    """the product's own binding layer (ops.NativeOps: argument order, workspace sizes, job tables) over a CPU-shim build of the kernels;
+    ops._ptr is patched to accept host tensors for the duration of the test"""
+    import ctypes
+    from mvdfusion_b200 import _lib, ops as OPS
+    lib = ctypes.CDLL(lib_path)
+    for name, argtypes in _lib.SIGNATURES.items():
+        if hasattr(lib, name):
+            getattr(lib, name).argtypes = argtypes
+            getattr(lib, name).restype = _lib._RESTYPE.get(name, ctypes.c_int32)
+
+    class ShimOps(OPS.NativeOps):
+        def __init__(self):
+            self.lib, self.device = lib, torch.device("cpu")
+
+    def ptr(t, dtype=None):
+        if t is None:
+            return None
+        if dtype is not None and t.dtype != dtype:
+            raise OPS.MvdError(f"expected {dtype}, got {t.dtype}")
+        return t.data_ptr()
+
+    monkeypatch.setattr(OPS, "_ptr", ptr)
+    return ShimOps()

@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -34,6 +35,17 @@ struct alignas(8) float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
+struct uint2 { uint32_t x, y; };
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+// IEEE binary16 through the compiler's _Float16 (conversions from float round to nearest even, like __float2half_rn)
+typedef _Float16 __half;
+struct alignas(4) __half2 { __half x, y; };
+inline __half __float2half_rn(float f) { return static_cast<__half>(f); }
+inline float __half2float(__half h) { return static_cast<float>(h); }
+inline __half2 __floats2half2_rn(float a, float b) { return __half2{static_cast<__half>(a), static_cast<__half>(b)}; }
+inline float2 __half22float2(__half2 h) { return float2{static_cast<float>(h.x), static_cast<float>(h.y)}; }
 
 typedef void* cudaStream_t;
 typedef int cudaError_t;
@@ -74,7 +86,8 @@ class Barrier {  // reusable (generation-counted) barrier for `n` threads
 };
 
 struct Warp {
-  Barrier bar{32};
+  explicit Warp(int lanes) : bar(lanes) {}
+  Barrier bar;      // as many lanes as the warp really has (a 1-thread block is a 1-lane warp)
   uint32_t slot[32];
 };
 
@@ -83,6 +96,7 @@ struct Ctx {
   Barrier* block_bar = nullptr;
   Warp* warp = nullptr;
   int lane = 0;
+  void* dyn_smem = nullptr;  // the launch's dynamic shared memory (one buffer: one block is resident at a time)
 };
 inline Ctx& ctx() {
   thread_local Ctx c;
@@ -94,15 +108,13 @@ inline std::mutex& atomic_mutex() {
 }
 
 // run `body` once per (block, thread): blockDim threads live for the whole launch and walk over the blocks together
-inline void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
+inline void launch(dim3 grid, dim3 block, const std::function<void()>& body, size_t dyn_smem_bytes = 0) {
   const int nt = static_cast<int>(block.x * block.y * block.z);
   const int nw = (nt + 31) / 32;
-  if (nt % 32 != 0) {  // the kernels under test use full warps only; partial warps would dead-lock the shuffle barrier
-    fprintf(stderr, "cpu_emul::launch: block size %d is not a multiple of 32\n", nt);
-    abort();
-  }
   Barrier block_bar(nt), end_bar(nt);
-  std::vector<Warp> warps(nw);
+  std::vector<std::unique_ptr<Warp>> warps;
+  for (int w = 0; w < nw; ++w) warps.emplace_back(new Warp(std::min(32, nt - 32 * w)));
+  std::vector<uint64_t> dyn((dyn_smem_bytes + 7) / 8 + 1);
   std::vector<std::thread> threads;
   threads.reserve(nt);
   for (int t = 0; t < nt; ++t) {
@@ -112,7 +124,8 @@ inline void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
       c.gridDim = grid;
       c.threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
       c.block_bar = &block_bar;
-      c.warp = &warps[t / 32];
+      c.warp = warps[t / 32].get();
+      c.dyn_smem = dyn.data();
       c.lane = t % 32;
       for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
@@ -185,3 +198,7 @@ inline void pdl_wait() {}
 #define MVD_KLAUNCH(kernel, grid, block, stream, ...) \
   cpu_emul::launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
 #define MVD_KLAUNCH_PDL(kernel, grid, block, stream, ...) MVD_KLAUNCH(kernel, grid, block, stream, __VA_ARGS__)
+// common.h's MVD_LAUNCH(kernel, grid, block, dynamic shared bytes, stream, args...) and the dynamic shared array declaration
+#define MVD_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  cpu_emul::launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); }, smem)
+#define MVD_DYNAMIC_SHARED(type, name) type* name = static_cast<type*>(cpu_emul::ctx().dyn_smem)

@@ -19,10 +19,20 @@ def dbl():
     return TorchOpsDouble()
 
 
+def stream_of(nat):
+    return torch.cuda.current_stream().cuda_stream if nat.device.type == "cuda" else None
+
+
+def sync(nat):
+    if nat.device.type == "cuda":
+        torch.cuda.synchronize()
+
+
 def run_both(nat, dbl, name, tensors, out_names, *args, tol=2e-3, **kw):
     """tensors: dict name -> cpu tensor (inputs and pre-filled outputs).  Calls op `name` on both, compares outputs."""
     cpu = {k: (v.clone() if v is not None else None) for k, v in tensors.items()}
-    gpu = {k: (v.cuda() if v is not None else None) for k, v in tensors.items()}
+    gpu = {k: (v.clone().to(nat.device) if v is not None else None) for k, v in tensors.items()}   # the B200 — or the host, when `nat` is
+    # the kernel source on the CUDA-on-CPU shim (tests/test_kernel_sources_cpu_shim.py reuses these test bodies)
 
     def bind(o, t):
         a = [t[x] if isinstance(x, str) and x in t else x for x in args]
@@ -32,8 +42,8 @@ def run_both(nat, dbl, name, tensors, out_names, *args, tol=2e-3, **kw):
         return getattr(o, name)(*a, **k)
 
     bind(dbl, cpu)(None)
-    bind(nat, gpu)(torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
+    bind(nat, gpu)(stream_of(nat))
+    sync(nat)
     for o in out_names:
         a, b = gpu[o].float().cpu(), cpu[o].float()
         assert torch.isfinite(a).all(), f"{name}: non-finite values in {o}"
@@ -403,11 +413,12 @@ def test_gemv_grouped(nat, dbl):
     Ws = [rnd(n, K, dtype=torch.float16, seed=10 + i, scale=K ** -0.5) for i, n in enumerate(sizes)]
     bs = [rnd(n, seed=20 + i) if i != 3 else None for i, n in enumerate(sizes)]
     y_cpu = [torch.zeros(n) for n in sizes]
-    y_gpu = [torch.zeros(n).cuda() for n in sizes]
+    dev = nat.device
+    y_gpu = [torch.zeros(n).to(dev) for n in sizes]
     dbl.gemv_grouped(x, K, list(zip(Ws, bs, y_cpu)), silu_in=True)(None)
-    nat.gemv_grouped(x.cuda(), K, [(w.cuda(), b.cuda() if b is not None else None, y) for w, b, y in zip(Ws, bs, y_gpu)],
-                     silu_in=True)(torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
+    nat.gemv_grouped(x.clone().to(dev), K, [(w.clone().to(dev), b.clone().to(dev) if b is not None else None, y) for w, b, y in zip(Ws, bs, y_gpu)],
+                     silu_in=True)(stream_of(nat))
+    sync(nat)
     for a, b in zip(y_gpu, y_cpu):
         assert (a.cpu() - b).abs().max().item() <= 1e-4 * (b.abs().max().item() + 1e-6)
 

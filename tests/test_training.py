@@ -205,36 +205,14 @@ def test_pointwise_kernels_forward_backward_gpu():
 
 
 # ------------------------------------------------------------------------------------------------ the kernel SOURCE on the CPU shim
-def _build_cpu_shim(tmp_dir):
-    """csrc/train.cu compiled as plain C++ against tests/native/cpu_emul/cuda_on_cpu.h (one host thread per CUDA thread)"""
-    import subprocess
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = os.path.join(str(tmp_dir), "libmvd_train_cpuemul.so")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-x", "c++", "-DMVD_CPU_EMULATION", "-I", os.path.join(root, "tests", "native", "cpu_emul"),
-                           "-shared", "-fPIC", os.path.join(root, "mvdfusion_b200", "csrc", "train.cu"), "-o", out, "-lpthread"])
-    return out
-
-
 def test_pointwise_kernel_source_on_the_cpu_shim(tmp_path, monkeypatch):
     """The CUDA kernels of csrc/train.cu themselves — not an emulation of their semantics — executed on host threads
     (tests/native/cpu_emul/cuda_on_cpu.h: real threads per block, barriers for __syncthreads / warp shuffles, serialised atomics),
     bound through the product's own ops.NativeOps methods and autograd Functions, against torch.autograd in float64.  Checks the
     indexing, reductions, ragged chunks and closed forms in a container without a GPU; the -m gpu twin checks the nvcc build."""
-    import ctypes
     import mvdfusion_b200.runtime as rt
-    from mvdfusion_b200 import _lib, ops as OPS
-    lib = ctypes.CDLL(_build_cpu_shim(tmp_path))
-    for name in ("mvd_layernorm_fwd_f32", "mvd_layernorm_bwd_f32", "mvd_groupnorm_fwd_f32", "mvd_groupnorm_bwd_f32", "mvd_act_fwd_f32", "mvd_act_bwd_f32",
-                 "mvd_bilinear_gather_fwd_f32", "mvd_bilinear_gather_bwd_f32"):
-        getattr(lib, name).argtypes = _lib.SIGNATURES[name]
-        getattr(lib, name).restype = ctypes.c_int32
-
-    class ShimOps(OPS.NativeOps):      # the product's binding code (argument order, workspace sizes) over the shim library
-        def __init__(self):
-            self.lib, self.device = lib, torch.device("cpu")
-
-    shim = ShimOps()
-    monkeypatch.setattr(OPS, "_ptr", lambda t, dtype=None: None if t is None else (t.data_ptr() if dtype is None or t.dtype == dtype else (_ for _ in ()).throw(OPS.MvdError(f"expected {dtype}, got {t.dtype}"))))
+    from common import build_cpu_shim, shim_ops
+    shim = shim_ops(build_cpu_shim(["train.cu"], tmp_path), monkeypatch)
     monkeypatch.setattr(rt, "get_ops", lambda dev: shim)
     worst = _check_pointwise("cpu", 2e-5)
     assert len(worst) >= 18
