@@ -53,6 +53,7 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 
 // dynamic shared memory of a kernel as a typed array (a macro so that tests/native/cpu_emul can substitute a host buffer)
 #define MVD_DYNAMIC_SHARED(type, name) extern __shared__ type name[]
+#define MVD_DYNAMIC_SHARED_ALIGNED16(type, name) extern __shared__ __align__(16) type name[]
 
 // fp16 row-major matrix [rows, ld] of which [rows, cols] is addressable; box = box_cols x box_rows, 128B swizzle.
 int make_tmap_2d(CUtensorMap* out, const void* base, int cols, int rows, int ld, int box_cols, int box_rows);

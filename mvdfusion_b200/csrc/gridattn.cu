@@ -12,8 +12,13 @@
 //   frustum_pool    : 2^l x 2^l area pooling of the frustum features (mvdfusion/unet.py:198-209)
 //
 // These are gather / transcendental / tiny-attention kernels: HBM/L2-bound, no tensor cores.
+#ifdef MVD_CPU_EMULATION
+// test infrastructure: this file compiled as plain C++ and run on host threads (tests/native/cpu_emul/cuda_on_cpu.h)
+#include "cuda_on_cpu.h"
+#else
 #include "common.h"
 #include "ptx.cuh"
+#endif
 
 namespace mvd {
 
@@ -321,11 +326,20 @@ __global__ void view_attention_kernel(const __half* __restrict__ qkv, __half* __
 
 // acc += a.lo * b.lo + a.hi * b.hi   (half2 operands, fp32 accumulator; two FHFMA)
 __device__ __forceinline__ void dot2_f16(float& acc, uint32_t a2, uint32_t b2) {
+#ifdef MVD_CPU_EMULATION
+  acc = cpu_emul::fma_f16(cpu_emul::fma_f16(acc, a2 & 0xffffu, b2 & 0xffffu), a2 >> 16, b2 >> 16);
+  return;
+#endif
   asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"
       "fma.rn.f32.f16 %0, al, bl, %0;\n\tfma.rn.f32.f16 %0, ah, bh, %0;\n\t}\n" : "+f"(acc) : "r"(a2), "r"(b2));
 }
 // acc0 += p * v.lo ; acc1 += p * v.hi   (p duplicated in both halves of p2)
 __device__ __forceinline__ void axpy2_f16(float& acc0, float& acc1, uint32_t p2, uint32_t v2) {
+#ifdef MVD_CPU_EMULATION
+  acc0 = cpu_emul::fma_f16(acc0, p2 & 0xffffu, v2 & 0xffffu);
+  acc1 = cpu_emul::fma_f16(acc1, p2 >> 16, v2 >> 16);
+  return;
+#endif
   asm("{\n\t.reg .b16 pl, ph, vl, vh;\n\tmov.b32 {pl, ph}, %2;\n\tmov.b32 {vl, vh}, %3;\n\t"
       "fma.rn.f32.f16 %0, pl, vl, %0;\n\tfma.rn.f32.f16 %1, ph, vh, %1;\n\t}\n" : "+f"(acc0), "+f"(acc1) : "r"(p2), "r"(v2));
 }
@@ -337,7 +351,7 @@ __device__ __forceinline__ void axpy2_f16(float& acc0, float& acc1, uint32_t p2,
 template <int HD>
 __global__ void __launch_bounds__(256)
     view_attention_staged_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int P, int V, int heads) {
-  extern __shared__ __align__(16) uint8_t va_smem[];
+  MVD_DYNAMIC_SHARED_ALIGNED16(uint8_t, va_smem);
   pdl_trigger();
   pdl_wait();
   const int C = heads * HD;
@@ -401,7 +415,11 @@ __global__ void __launch_bounds__(256)
   for (int kj = 0; kj < MAXV; ++kj) {
     if (kj < V) {
       float pe;
+#ifdef MVD_CPU_EMULATION
+      pe = exp2f(sc[kj] - m);
+#else
       asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(sc[kj] - m));
+#endif
       const __half ph = __float2half_rn(pe);
       l += __half2float(ph);
       const uint32_t p2 = static_cast<uint32_t>(__half_as_ushort(ph)) * 0x10001u;

@@ -46,6 +46,20 @@ inline __half __float2half_rn(float f) { return static_cast<__half>(f); }
 inline float __half2float(__half h) { return static_cast<float>(h); }
 inline __half2 __floats2half2_rn(float a, float b) { return __half2{static_cast<__half>(a), static_cast<__half>(b)}; }
 inline float2 __half22float2(__half2 h) { return float2{static_cast<float>(h.x), static_cast<float>(h.y)}; }
+inline unsigned short __half_as_ushort(__half h) { unsigned short u; memcpy(&u, &h, 2); return u; }
+inline float __sinf(float x) { return sinf(x); }
+inline float __cosf(float x) { return cosf(x); }
+#define __launch_bounds__(...)
+namespace cpu_emul {
+// fma.rn.f32.f16: fp16 x fp16 (exact in fp32) + fp32, one rounding; operands as raw binary16 bit patterns
+inline float fma_f16(float acc, uint32_t a_bits, uint32_t b_bits) {
+  unsigned short ua = static_cast<unsigned short>(a_bits), ub = static_cast<unsigned short>(b_bits);
+  __half a, b;
+  memcpy(&a, &ua, 2);
+  memcpy(&b, &ub, 2);
+  return fmaf(static_cast<float>(a), static_cast<float>(b), acc);
+}
+}  // namespace cpu_emul
 
 typedef void* cudaStream_t;
 typedef int cudaError_t;
@@ -53,6 +67,9 @@ constexpr cudaError_t cudaSuccess = 0;
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 
 #define __global__
 #define __device__
@@ -114,7 +131,7 @@ inline void launch(dim3 grid, dim3 block, const std::function<void()>& body, siz
   Barrier block_bar(nt), end_bar(nt);
   std::vector<std::unique_ptr<Warp>> warps;
   for (int w = 0; w < nw; ++w) warps.emplace_back(new Warp(std::min(32, nt - 32 * w)));
-  std::vector<uint64_t> dyn((dyn_smem_bytes + 7) / 8 + 1);
+  std::vector<uint4> dyn(dyn_smem_bytes / 16 + 1);  // 16-byte aligned
   std::vector<std::thread> threads;
   threads.reserve(nt);
   for (int t = 0; t < nt; ++t) {
@@ -187,6 +204,21 @@ inline int set_error(int code, const char* fmt, ...) {
 inline void count_launch(int = 1) {}
 inline void pdl_trigger() {}  // programmatic dependent launch: blocks and kernels run strictly in order here
 inline void pdl_wait() {}
+// ptx.cuh's gelu_erf restated with exact division / exp2f in place of the two approximate SFU instructions (same A&S 7.1.26 polynomial)
+inline float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = 1.0f / fmaf(0.3275911f, z, 1.0f);
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = exp2f(z * z * -1.4426950408889634f);
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs, hx);
+}
+inline float silu(float x) { return x / (1.0f + expf(-x)); }
 }  // namespace mvd
 
 #define MVD_CUDA_CHECK(expr)                                                      \
@@ -202,3 +234,4 @@ inline void pdl_wait() {}
 #define MVD_LAUNCH(kernel, grid, block, smem, stream, ...) \
   cpu_emul::launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); }, smem)
 #define MVD_DYNAMIC_SHARED(type, name) type* name = static_cast<type*>(cpu_emul::ctx().dyn_smem)
+#define MVD_DYNAMIC_SHARED_ALIGNED16(type, name) MVD_DYNAMIC_SHARED(type, name)

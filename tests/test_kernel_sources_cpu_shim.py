@@ -1,7 +1,10 @@
-"""CPU: the SOURCE of the plain-SIMT kernels of the hot path (csrc/elementwise.cu: cast / concat / upsample / im2col / GEMV / grouped GEMV /
-timestep embedding / UNet input assembly / CFG combine + DDIM update / layout converters / table gather) compiled as C++ and executed on
+"""CPU: the SOURCE of the plain-SIMT kernels of the hot path — csrc/elementwise.cu (cast / concat / upsample / im2col / GEMV / grouped GEMV /
+timestep embedding / UNet input assembly / CFG combine + DDIM update / layout converters / table gather) and csrc/gridattn.cu (GridAttn's
+depth de-bias + z_embedder, the unproject -> reproject -> bilinear-gather -> harmonic-embedding token producer, the V x V view attention in
+both variants, view pooling, frustum pooling, the D-key pixel cross-attention) — compiled as C++ and executed on
 host threads (tests/native/cpu_emul/cuda_on_cpu.h), through the product's own ops.NativeOps bindings, against the same emulations of the
 documented semantics the B200 tests use — the very test bodies of tests/test_gpu_ops.py, with `nat` bound to the shim build.
+(The three inline-PTX spots of gridattn.cu — fma.rn.f32.f16 and ex2.approx — have plain C++ stand-ins under MVD_CPU_EMULATION.)
 
 What this proves without a GPU: indexing, tails, fp16 rounding (IEEE binary16 through _Float16), the grouped-GEMV job table, the DDIM /
 CFG arithmetic.  What it cannot prove: anything about tcgen05 / TMA / clusters (gemm.cu, attention.cu, dit.cu, norm.cu's cluster
@@ -14,7 +17,7 @@ from common import build_cpu_shim, shim_ops
 
 @pytest.fixture(scope="module")
 def shim_lib(tmp_path_factory):
-    return build_cpu_shim(["elementwise.cu"], tmp_path_factory.mktemp("cpu_shim"), "libmvd_elementwise_cpuemul.so")
+    return build_cpu_shim(["elementwise.cu", "gridattn.cu"], tmp_path_factory.mktemp("cpu_shim"), "libmvd_simt_cpuemul.so")
 
 
 @pytest.fixture
@@ -47,3 +50,16 @@ def test_gemv_and_timestep_embedding_kernels(nat, dbl):
 
 def test_unet_input_cfg_ddim_and_table_kernels(nat, dbl):
     G.test_unet_input_cfg_ddim_tables(nat, dbl)
+
+
+@pytest.mark.parametrize("N,D,q_first,q_count", [(3, 3, 1, 2)])   # D = 3 keys per pixel, a strict subset of query views (the sharded form)
+def test_gridattn_kernels(nat, dbl, N, D, q_first, q_count):
+    """rows a8 / a9 / a10 (per-op form) / a11's pyramid: prep, token producer, view attention, view pooling, frustum pooling, pixel
+    cross-attention — the geometry (unproject, reproject, border-clamped bilinear taps, Plucker / depth harmonics) runs from the .cu source"""
+    G.test_gridattn_kernels(nat, dbl, N, D, q_first, q_count)
+
+
+@pytest.mark.parametrize("P,V", [(130, 8), (50, 3)])
+def test_view_attention_kernels(nat, dbl, P, V):
+    """staged kernel (heads * V divides 256, ragged last CTA) and the per-thread variant (V = 3)"""
+    G.test_view_attention_layouts(nat, dbl, P, V)
