@@ -9,7 +9,7 @@ Runs on the host cores (the oracle is CPU code; the comparison is between arithm
 parameters), N = 2 views, cfg 2.5, the same seeds / timesteps as tests/test_gpu_parity.py::test_apply_model_full_size_vs_oracle.
 Test infrastructure: imports oracle/, never imported by the product.
 
-    python tools/autocast_parity.py --out profiles/r02_autocast_parity.json
+    python tests/autocast_parity.py --out profiles/r02_autocast_parity.json
 """
 import argparse
 import json
