@@ -7,8 +7,14 @@
 #include <cstdio>
 #include <cstdlib>
 
+#ifdef MVD_CPU_EMULATION
+// test infrastructure: this file compiled as plain C++ and run on host threads (tests/native/cpu_emul/cuda_on_cpu.h); the blocks of a
+// cluster run together there, the distributed-shared-memory reads become plain loads from the peer block's buffer
+#include "cuda_on_cpu.h"
+#else
 #include "common.h"
 #include "ptx.cuh"
+#endif
 
 namespace mvd {
 
@@ -29,7 +35,7 @@ __global__ void __launch_bounds__(NT, MAXP == 16 ? 2 : (MAXP == 4 ? 4 : 3))  // 
                       const float* __restrict__ beta, __half* __restrict__ y, int hw, int C, int cpg, int gpc, int rows, int csplit,
                       float eps, int apply_silu, int ldy, int lo_off) {
   pdl_trigger();
-  extern __shared__ __align__(16) uint8_t gn_smem[];
+  MVD_DYNAMIC_SHARED_ALIGNED16(uint8_t, gn_smem);
   const int span = gpc * cpg;
   const int span4 = span >> 2;
   double* gsum = reinterpret_cast<double*>(gn_smem);      // [32][2] group sums of this CTA (read by the cluster peers)
@@ -120,8 +126,18 @@ __global__ void __launch_bounds__(NT, MAXP == 16 ? 2 : (MAXP == 4 ? 4 : 3))  // 
     const int g = threadIdx.x;
     double a = 0.0, b = 0.0;
     if (csplit > 1) {
-      const uint32_t local = smem_u32(gsum + 2 * g);
       double ra[8], rb[8];
+#ifdef MVD_CPU_EMULATION
+      for (int r = 0; r < 8; ++r) {
+        ra[r] = rb[r] = 0.0;
+        if (r < csplit) {
+          const double* remote = cpu_emul::cluster_peer(gsum + 2 * g, r);
+          ra[r] = remote[0];
+          rb[r] = remote[1];
+        }
+      }
+#else
+      const uint32_t local = smem_u32(gsum + 2 * g);
 #pragma unroll
       for (int r = 0; r < 8; ++r) {  // all remote loads in flight together
         ra[r] = rb[r] = 0.0;
@@ -130,6 +146,7 @@ __global__ void __launch_bounds__(NT, MAXP == 16 ? 2 : (MAXP == 4 ? 4 : 3))  // 
           asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(ra[r]), "=d"(rb[r]) : "r"(remote) : "memory");
         }
       }
+#endif
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         a += ra[r];
@@ -146,7 +163,9 @@ __global__ void __launch_bounds__(NT, MAXP == 16 ? 2 : (MAXP == 4 ? 4 : 3))  // 
     s_rstd[g] = rsqrtf(static_cast<float>(var) + eps);
   }
   // peers may still be reading this CTA's gsum: arrive now, wait just before exit (the normalisation runs in between)
+#ifndef MVD_CPU_EMULATION
   if (csplit > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+#endif
   __syncthreads();
   if (active) {
     float sc[4], sh[4];  // y = x * sc + sh
@@ -195,7 +214,11 @@ __global__ void __launch_bounds__(NT, MAXP == 16 ? 2 : (MAXP == 4 ? 4 : 3))  // 
     }
     }
   }
+#ifdef MVD_CPU_EMULATION
+  if (csplit > 1) cpu_emul::cluster_barrier();  // arrive (above, a no-op here) + wait as one barrier
+#else
   if (csplit > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+#endif
 }
 
 // ---------------------------------------------------------------------------- LayerNorm family

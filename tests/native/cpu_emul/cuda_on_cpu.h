@@ -48,6 +48,8 @@ inline __half2 __floats2half2_rn(float a, float b) { return __half2{static_cast<
 inline float2 __half22float2(__half2 h) { return float2{static_cast<float>(h.x), static_cast<float>(h.y)}; }
 inline unsigned short __half_as_ushort(__half h) { unsigned short u; memcpy(&u, &h, 2); return u; }
 inline float __sinf(float x) { return sinf(x); }
+inline float __expf(float x) { return expf(x); }
+inline float __fdividef(float a, float b) { return a / b; }
 inline float __cosf(float x) { return cosf(x); }
 #define __launch_bounds__(...)
 namespace cpu_emul {
@@ -105,7 +107,7 @@ class Barrier {  // reusable (generation-counted) barrier for `n` threads
 struct Warp {
   explicit Warp(int lanes) : bar(lanes) {}
   Barrier bar;      // as many lanes as the warp really has (a 1-thread block is a 1-lane warp)
-  uint32_t slot[32];
+  uint64_t slot[32];
 };
 
 struct Ctx {
@@ -113,7 +115,11 @@ struct Ctx {
   Barrier* block_bar = nullptr;
   Warp* warp = nullptr;
   int lane = 0;
-  void* dyn_smem = nullptr;  // the launch's dynamic shared memory (one buffer: one block is resident at a time)
+  void* dyn_smem = nullptr;  // the block's dynamic shared memory
+  // thread-block cluster (launches with cluster_x > 1: the cluster's blocks are resident together, each with its own dynamic shared memory)
+  int cluster_rank = 0, cluster_size = 1;
+  Barrier* cluster_bar = nullptr;
+  char** peer_dyn = nullptr;
 };
 inline Ctx& ctx() {
   thread_local Ctx c;
@@ -124,36 +130,63 @@ inline std::mutex& atomic_mutex() {
   return m;
 }
 
-// run `body` once per (block, thread): blockDim threads live for the whole launch and walk over the blocks together
-inline void launch(dim3 grid, dim3 block, const std::function<void()>& body, size_t dyn_smem_bytes = 0) {
+// run `body` once per (block, thread).  blockDim x cluster_x threads live for the whole launch; the cluster_x blocks of a cluster run
+// together (their threads share a cluster barrier and can read each other's dynamic shared memory), clusters one after the other.
+// `static` shared arrays are only valid for cluster_x == 1 (one resident block); cluster kernels here use dynamic shared memory only.
+inline void launch(dim3 grid, dim3 block, const std::function<void()>& body, size_t dyn_smem_bytes = 0, int cluster_x = 1) {
   const int nt = static_cast<int>(block.x * block.y * block.z);
   const int nw = (nt + 31) / 32;
-  Barrier block_bar(nt), end_bar(nt);
-  std::vector<std::unique_ptr<Warp>> warps;
-  for (int w = 0; w < nw; ++w) warps.emplace_back(new Warp(std::min(32, nt - 32 * w)));
-  std::vector<uint4> dyn(dyn_smem_bytes / 16 + 1);  // 16-byte aligned
-  std::vector<std::thread> threads;
-  threads.reserve(nt);
-  for (int t = 0; t < nt; ++t) {
-    threads.emplace_back([&, t] {
-      Ctx& c = ctx();
-      c.blockDim = block;
-      c.gridDim = grid;
-      c.threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
-      c.block_bar = &block_bar;
-      c.warp = warps[t / 32].get();
-      c.dyn_smem = dyn.data();
-      c.lane = t % 32;
-      for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-          for (unsigned bx = 0; bx < grid.x; ++bx) {
-            c.blockIdx = dim3(bx, by, bz);
-            body();
-            end_bar.wait();  // the next block may reuse the `static` shared arrays only after every thread has left this one
-          }
-    });
+  const int cs = cluster_x < 1 ? 1 : cluster_x;
+  if (grid.x % cs != 0) {
+    fprintf(stderr, "cpu_emul::launch: grid.x %u is not a multiple of the cluster size %d\n", grid.x, cs);
+    abort();
   }
+  Barrier cluster_bar(nt * cs);
+  std::vector<std::unique_ptr<Barrier>> block_bars;
+  std::vector<std::unique_ptr<Warp>> warps;
+  std::vector<std::vector<uint4>> dyn(cs, std::vector<uint4>(dyn_smem_bytes / 16 + 1));  // 16-byte aligned
+  std::vector<char*> peer(cs);
+  for (int r = 0; r < cs; ++r) {
+    block_bars.emplace_back(new Barrier(nt));
+    for (int w = 0; w < nw; ++w) warps.emplace_back(new Warp(std::min(32, nt - 32 * w)));
+    peer[r] = reinterpret_cast<char*>(dyn[r].data());
+  }
+  std::vector<std::thread> threads;
+  threads.reserve(static_cast<size_t>(nt) * cs);
+  for (int r = 0; r < cs; ++r)
+    for (int t = 0; t < nt; ++t) {
+      threads.emplace_back([&, r, t] {
+        Ctx& c = ctx();
+        c.blockDim = block;
+        c.gridDim = grid;
+        c.threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+        c.block_bar = block_bars[r].get();
+        c.warp = warps[r * nw + t / 32].get();
+        c.lane = t % 32;
+        c.dyn_smem = peer[r];
+        c.cluster_rank = r;
+        c.cluster_size = cs;
+        c.cluster_bar = &cluster_bar;
+        c.peer_dyn = peer.data();
+        for (unsigned bz = 0; bz < grid.z; ++bz)
+          for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; bx += cs) {
+              c.blockIdx = dim3(bx + r, by, bz);
+              body();
+              cluster_bar.wait();  // the next blocks may reuse the shared arrays only after every thread has left these
+            }
+      });
+    }
   for (auto& th : threads) th.join();
+}
+
+// barrier.cluster arrive + wait over every thread of the cluster
+inline void cluster_barrier() { ctx().cluster_bar->wait(); }
+// the same dynamic-shared-memory location in block `rank` of the cluster (mapa + ld.shared::cluster of the real build)
+template <typename T>
+inline const T* cluster_peer(const T* p, int rank) {
+  Ctx& c = ctx();
+  return reinterpret_cast<const T*>(c.peer_dyn[rank] + (reinterpret_cast<const char*>(p) - static_cast<const char*>(c.dyn_smem)));
 }
 
 }  // namespace cpu_emul
@@ -167,12 +200,12 @@ inline void __syncthreads() { cpu_emul::ctx().block_bar->wait(); }
 
 template <typename T>
 inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
-  static_assert(sizeof(T) == 4, "32-bit shuffles only");
+  static_assert(sizeof(T) == 4 || sizeof(T) == 8, "32- and 64-bit shuffles only");
   cpu_emul::Ctx& c = cpu_emul::ctx();
-  memcpy(&c.warp->slot[c.lane], &v, 4);
+  memcpy(&c.warp->slot[c.lane], &v, sizeof(T));
   c.warp->bar.wait();
   T r;
-  memcpy(&r, &c.warp->slot[c.lane ^ lane_mask], 4);
+  memcpy(&r, &c.warp->slot[c.lane ^ lane_mask], sizeof(T));
   c.warp->bar.wait();
   return r;
 }
@@ -203,6 +236,13 @@ inline int set_error(int code, const char* fmt, ...) {
 }
 inline void count_launch(int = 1) {}
 inline void pdl_trigger() {}  // programmatic dependent launch: blocks and kernels run strictly in order here
+inline void cluster_sync_all() { cpu_emul::cluster_barrier(); }
+// common.h's launch_kernel(kernel, grid, block, dynamic shared bytes, stream, cluster size along x, args...)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, int cluster_x, Args&&... args) {
+  cpu_emul::launch(grid, block, [&] { kernel(static_cast<KArgs>(args)...); }, smem, cluster_x);
+  return cudaSuccess;
+}
 inline void pdl_wait() {}
 // ptx.cuh's gelu_erf restated with exact division / exp2f in place of the two approximate SFU instructions (same A&S 7.1.26 polynomial)
 inline float gelu_erf(float x) {

@@ -171,8 +171,9 @@ def test_groupnorm_split_precision_output(nat, dbl, n, hw, C):
     t = {"x": rnd(n * hw, C) * 2 + 0.5, "g": rnd(C, seed=1), "b": rnd(C, seed=2), "y": torch.zeros(n * hw, 2 * C, dtype=torch.float16)}
     run_both(nat, dbl, "groupnorm_hilo", t, ["y"], "x", "g", "b", "y", n, hw, C, 1e-5, True)
     y = nat.empty((n * hw, 2 * C), torch.float16)
-    nat.groupnorm_hilo(t["x"].cuda(), t["g"].cuda(), t["b"].cuda(), y, n, hw, C, 1e-5, True)(torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
+    dev = nat.device
+    nat.groupnorm_hilo(t["x"].clone().to(dev), t["g"].clone().to(dev), t["b"].clone().to(dev), y, n, hw, C, 1e-5, True)(stream_of(nat))
+    sync(nat)
     import torch.nn.functional as F
     exact = F.silu(F.group_norm(t["x"].double().reshape(n, hw, C).permute(0, 2, 1), 32, t["g"].double(), t["b"].double(), 1e-5))
     exact = exact.permute(0, 2, 1).reshape(n * hw, C).float()

@@ -1,14 +1,17 @@
 """CPU: the SOURCE of the plain-SIMT kernels of the hot path — csrc/elementwise.cu (cast / concat / upsample / im2col / GEMV / grouped GEMV /
 timestep embedding / UNet input assembly / CFG combine + DDIM update / layout converters / table gather) and csrc/gridattn.cu (GridAttn's
 depth de-bias + z_embedder, the unproject -> reproject -> bilinear-gather -> harmonic-embedding token producer, the V x V view attention in
-both variants, view pooling, frustum pooling, the D-key pixel cross-attention) — compiled as C++ and executed on
+both variants, view pooling, frustum pooling, the D-key pixel cross-attention) and csrc/norm.cu (the cluster GroupNorm(+SiLU) in its
+one- / two-source and split-precision forms — the blocks of a thread-block cluster run together on the shim and read each other's
+shared memory, as over DSMEM — LayerNorm, adaLN modulate, fp32 LayerNorm with row pitches, row softmax) — compiled as C++ and executed on
 host threads (tests/native/cpu_emul/cuda_on_cpu.h), through the product's own ops.NativeOps bindings, against the same emulations of the
 documented semantics the B200 tests use — the very test bodies of tests/test_gpu_ops.py, with `nat` bound to the shim build.
 (The three inline-PTX spots of gridattn.cu — fma.rn.f32.f16 and ex2.approx — have plain C++ stand-ins under MVD_CPU_EMULATION.)
 
 What this proves without a GPU: indexing, tails, fp16 rounding (IEEE binary16 through _Float16), the grouped-GEMV job table, the DDIM /
-CFG arithmetic.  What it cannot prove: anything about tcgen05 / TMA / clusters (gemm.cu, attention.cu, dit.cu, norm.cu's cluster
-GroupNorm are hardware-only) or timing; the -m gpu suite remains the proof on the B200."""
+CFG arithmetic, GroupNorm slice / cluster geometry and statistics exchange.  What it cannot prove: anything about tcgen05 / TMA
+(gemm.cu, attention.cu, dit.cu are hardware-only), memory ordering of the real cluster barrier, or timing; the -m gpu suite remains the
+proof on the B200."""
 import pytest
 
 import test_gpu_ops as G
@@ -17,7 +20,7 @@ from common import build_cpu_shim, shim_ops
 
 @pytest.fixture(scope="module")
 def shim_lib(tmp_path_factory):
-    return build_cpu_shim(["elementwise.cu", "gridattn.cu"], tmp_path_factory.mktemp("cpu_shim"), "libmvd_simt_cpuemul.so")
+    return build_cpu_shim(["elementwise.cu", "gridattn.cu", "norm.cu"], tmp_path_factory.mktemp("cpu_shim"), "libmvd_simt_cpuemul.so")
 
 
 @pytest.fixture
@@ -63,3 +66,22 @@ def test_gridattn_kernels(nat, dbl, N, D, q_first, q_count):
 def test_view_attention_kernels(nat, dbl, P, V):
     """staged kernel (heads * V divides 256, ragged last CTA) and the per-thread variant (V = 3)"""
     G.test_view_attention_layouts(nat, dbl, P, V)
+
+
+@pytest.mark.parametrize("n,hw,C,silu", [(1, 1024, 320, True), (2, 64, 1280, True), (1, 100, 64, True), (1, 4096, 64, False), (2, 16, 2560, True)])
+def test_groupnorm_cluster_kernel(nat, dbl, n, hw, C, silu):
+    """gn_cluster_kernel: slices of a few groups, pixels interleaved over a cluster of 1-8 blocks, fp64 group sums exchanged through the
+    peers' shared memory (32^2 x 320: a cluster split; 64^2: pixels streamed twice; ragged hw = 100)"""
+    G.test_groupnorm(nat, dbl, n, hw, C, silu)
+
+
+def test_groupnorm_two_sources_and_split_precision(nat, dbl):
+    G.test_groupnorm_two_sources_and_concat16(nat, dbl, 1, 256, 640, 320)
+    G.test_groupnorm_split_precision_output(nat, dbl, 1, 1024, 320)
+
+
+def test_layernorm_family_and_softmax(nat, dbl):
+    G.test_layernorms(nat, dbl)
+    G.test_layernorm_f32_with_row_pitch(nat, dbl)
+    t = {"s": G.rnd(70, 512) * 3, "p": G.torch.zeros(70, 512, dtype=G.torch.float16)}
+    G.run_both(nat, dbl, "softmax_rows", t, ["p"], "s", "p", 70, 512, 512 ** -0.5)
