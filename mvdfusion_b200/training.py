@@ -30,6 +30,7 @@ import torch
 import torch.nn.functional as F
 
 from . import runtime
+from .ops import GN_WS_BYTES_PER_IMAGE
 
 Z_SCALE = 0.18215
 
@@ -213,7 +214,7 @@ class _GroupNormFn(torch.autograd.Function):
         ops = runtime.get_ops(x.device)
         g, b = _f32c(gamma), _f32c(beta)
         y, stats = ops.empty(tuple(x.shape), torch.float32), ops.empty((n, 32, 2), torch.float32)
-        ws = ops.empty((n * 16384,), torch.uint8)
+        ws = ops.empty((n * GN_WS_BYTES_PER_IMAGE,), torch.uint8)
         ops.groupnorm_fwd(xc, g, b, y, stats, ws, n, hw, C, float(eps), silu)(_stream(x))
         ctx.save_for_backward(xc, g, b, stats)
         ctx.dims = (n, hw, C, bool(silu))
@@ -227,7 +228,7 @@ class _GroupNormFn(torch.autograd.Function):
         dx = ops.empty(tuple(xc.shape), torch.float32)
         dgb = ops.empty((2, C), torch.float32)                 # (dgamma | dbeta) as one vector: one memset in the call
         dg, db = dgb[0], dgb[1]
-        ws = ops.empty((n * 16384,), torch.uint8)
+        ws = ops.empty((n * GN_WS_BYTES_PER_IMAGE,), torch.uint8)
         ops.groupnorm_bwd(_f32c(dy), xc, g, b, stats, dx, dg, db, ws, n, hw, C, silu)(_stream(dy))
         return dx, dg, db, None, None
 
