@@ -12,6 +12,8 @@ What this proves without a GPU: indexing, tails, fp16 rounding (IEEE binary16 th
 CFG arithmetic, GroupNorm slice / cluster geometry and statistics exchange.  What it cannot prove: anything about tcgen05 / TMA
 (gemm.cu, attention.cu, dit.cu are hardware-only), memory ordering of the real cluster barrier, or timing; the -m gpu suite remains the
 proof on the B200."""
+import os
+
 import pytest
 
 import test_gpu_ops as G
@@ -85,3 +87,51 @@ def test_layernorm_family_and_softmax(nat, dbl):
     G.test_layernorm_f32_with_row_pitch(nat, dbl)
     t = {"s": G.rnd(70, 512) * 3, "p": G.torch.zeros(70, 512, dtype=G.torch.float16)}
     G.run_both(nat, dbl, "softmax_rows", t, ["p"], "s", "p", 70, 512, 512 ** -0.5)
+
+
+# ------------------------------------------------------------------------------------------------ the whole step program, SIMT kernels from source
+SIMT_OPS = ("groupnorm", "groupnorm_hilo", "groupnorm2", "layernorm", "layernorm_f32", "ln_modulate", "softmax_rows", "cast", "concat", "concat16",
+            "upsample2x", "im2col_s2", "gemv", "gemv_grouped", "timestep_embedding", "unet_input", "cfg_ddim", "nchw_to_rows", "rows_to_nchw",
+            "nchw_to_nhwc16", "gather_rows", "increment", "gridattn_prep", "gridattn_tokens", "view_attention", "view_pool", "frustum_pool",
+            "pixel_cross_attn")
+
+
+@pytest.mark.skipif(os.environ.get("MVD_SLOW_SHIM") != "1",
+                    reason="~7 minutes of host-thread barriers: run with MVD_SLOW_SHIM=1 (last result: profiles/r02_shim_apply_model.txt)")
+def test_apply_model_with_every_simt_kernel_from_source_vs_oracle(nat, monkeypatch):
+    """ViewFusion.apply_model (N = 2, D = 3, cfg 2.5, the 64-channel topology-complete model) through the product's step compiler with EVERY
+    non-tensor-core kernel executed from its .cu source on the shim — in the real program: the engine's buffer arena, pitches, column
+    windows, two-source GroupNorms, CLIP row biases — and only the tcgen05 kernels (GEMM / implicit-GEMM conv, flash attention, fused DiT)
+    emulated; against the fp32 oracle at the path's own gate."""
+    import torch
+    import mvdfusion_b200.runtime as rt
+    from common import build_model, rel_l2, state_dict_cpu, unet_cfg_of
+    from test_host_engine import cams_of
+    from mvdfusion_b200 import synthetic
+    from ops_double import TorchOpsDouble
+    from oracle import mvd_oracle as O
+
+    class HybridOps(TorchOpsDouble):
+        used = set()
+
+        def __getattribute__(self, name):
+            if name in SIMT_OPS:
+                HybridOps.used.add(name)
+                return getattr(nat, name)
+            return object.__getattribute__(self, name)
+
+    hyb = HybridOps()
+    monkeypatch.setattr(rt, "get_ops", lambda dev: hyb)
+    D = 3
+    m = build_model(64, 8, D=D, S=32)
+    sd = state_dict_cpu(m)
+    sc = synthetic.scene_inputs(2, 32)
+    de, _ = synthetic.step_noises(2, D, 32, 1)
+    t = torch.full((2,), 501, dtype=torch.long)
+    eps = m.apply_model(sc["x_T"], cams_of(sc["cams"]), sc["input_latents"], cams_of(sc["in_cams"]), sc["clip_v_embed"], t, cfg_scale=2.5, depth_eps=de[0])
+    ref = O.apply_model(sd, sc["x_T"], sc["cams"], sc["input_latents"], sc["in_cams"], sc["clip_v_embed"], t, de[0], unet_cfg=unet_cfg_of(m), D=D, cfg_scale=2.5)
+    assert torch.isfinite(eps).all()
+    r = rel_l2(eps, ref)
+    print("apply_model, SIMT kernels from source: rel-L2 vs oracle", r, "ops from source:", sorted(HybridOps.used))
+    assert r < 1e-3, r
+    assert {"groupnorm", "gridattn_prep", "gridattn_tokens", "unet_input", "cfg_ddim", "gemv_grouped", "frustum_pool", "pixel_cross_attn"} <= HybridOps.used
