@@ -48,6 +48,21 @@ def test_argument_validation_reports_errors():
     assert lib.mvd_attn_self_f16(None, None, None, None, 1, 8, 1024, 40, 64, 320, None) == -1
     assert lib.mvd_geglu_row_permutation(100, 100, None) == -1
     assert lib.mvd_groupnorm_f32_f16(None, None, None, None, None, 1, 1, 32, 1e-5, 0, None) == -1
+    # ABI 15-17 (training kernels): null pointers, channel counts, alignment
+    assert lib.mvd_layernorm_fwd_f32(None, None, None, None, None, 4, 320, 1e-5, None) == -1
+    assert lib.mvd_layernorm_bwd_f32(None, None, None, None, None, None, None, 4, 320, None) == -1
+    assert lib.mvd_groupnorm_fwd_f32(None, None, None, None, None, None, 1, 16, 320, 1e-5, 1, None) == -1
+    assert lib.mvd_groupnorm_bwd_f32(None, None, None, None, None, None, None, None, None, 1, 16, 320, 1, None) == -1
+    assert lib.mvd_act_fwd_f32(None, None, 4, 4, 1, None) == -1
+    assert lib.mvd_bilinear_gather_fwd_f32(None, None, None, 1, 8, 8, 256, 10, None) == -1
+    buf = (ctypes.c_float * 4096)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.mvd_layernorm_fwd_f32(p, None, None, p, p, 4, 322, 1e-5, None) == -1          # C % 4
+    assert lib.mvd_layernorm_fwd_f32(p, p, None, p, p, 4, 320, 1e-5, None) == -1            # gamma without beta
+    assert lib.mvd_groupnorm_fwd_f32(p, p, p, p, p, p, 1, 4, 48, 1e-5, 0, None) == -1       # C % 32
+    assert lib.mvd_act_fwd_f32(p, p, 4, 4, 7, None) == -1 and b"mode" in lib.mvd_last_error()
+    assert lib.mvd_act_fwd_f32(p, p, 4, 6, 3, None) == -3                                    # GEGLU needs cols % 4 == 0
+    assert lib.mvd_bilinear_gather_fwd_f32(p, p, p, 1, 8, 8, 6, 10, None) == -1              # C % 4
     assert lib.mvd_launch_count() == 0  # validation failures launch nothing
 
 
