@@ -1,28 +1,27 @@
 // TEST INFRASTRUCTURE — a minimal CUDA-on-CPU execution shim, never part of the product.
 //
-// Purpose: the build container has no GPU.  Kernels that only use the classic SIMT subset (thread / block indices, static
-// __shared__ arrays, __syncthreads, warp shuffles, atomics, __ldg, float2 / float4) are compiled a second time as plain C++
-// (-DMVD_CPU_EMULATION) and executed here with one std::thread per CUDA thread of a block, blocks one after the other, so that
-// their indexing, reductions and closed forms are checked against torch.autograd before the code ever reaches a B200
-// (tests/test_training.py::test_pointwise_kernel_source_on_the_cpu_shim).  It says nothing about performance, memory coalescing or
-// races between blocks (blocks run sequentially); the -m gpu tests remain the proof on hardware.
+// Purpose: the build container has no GPU.  Kernel files that only use the classic SIMT subset (thread / block indices, shared memory,
+// __syncthreads, warp shuffles, atomics, __ldg, vector types, fp16 conversions, thread-block clusters with distributed shared memory)
+// — csrc/elementwise.cu, gridattn.cu, norm.cu, train.cu — are compiled a second time as plain C++ (-DMVD_CPU_EMULATION) and executed
+// here with one fiber per CUDA thread, blocks (or clusters) one after the other, so that their indexing, reductions, rounding and closed
+// forms are checked before the code reaches a B200 (tests/test_kernel_sources_cpu_shim.py, tests/test_training.py).  It says nothing
+// about performance, memory coalescing, the hardware memory model or races between blocks; the -m gpu tests remain the proof.
 //
-// Semantics kept: a block's threads run concurrently (real threads), __syncthreads() is a block-wide barrier, __shfl_xor_sync
-// exchanges through a per-warp buffer between two warp barriers (all 32 lanes of a warp must take part, as on hardware with a full
-// mask), `static` stands in for __shared__ (valid because only one block is resident at a time), atomicAdd is serialised.
+// Semantics kept: the threads of a block (and the blocks of a cluster) are all live at once and interleave at barriers,
+// __syncthreads() is a block-wide barrier, __shfl_xor_sync exchanges through a per-warp buffer between two warp barriers (every lane
+// of the warp must take part, as on hardware with a full mask), `static` stands in for __shared__ (valid because one block is resident
+// at a time; cluster kernels use dynamic shared memory only), fp16 is IEEE binary16 (_Float16, round to nearest even).
 #pragma once
 #include <stdint.h>
+#include <ucontext.h>
 
 #include <algorithm>
 #include <cmath>
-#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <functional>
 #include <memory>
-#include <mutex>
-#include <thread>
 #include <vector>
 
 #include "../../../include/mvd_b200.h"
@@ -82,26 +81,17 @@ inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cuda
 
 namespace cpu_emul {
 
-class Barrier {  // reusable (generation-counted) barrier for `n` threads
- public:
-  explicit Barrier(int n) : n_(n) {}
-  void wait() {
-    std::unique_lock<std::mutex> lk(m_);
-    const unsigned gen = gen_;
-    if (++count_ == n_) {
-      count_ = 0;
-      ++gen_;
-      cv_.notify_all();
-    } else {
-      cv_.wait(lk, [&] { return gen_ != gen; });
-    }
-  }
-
- private:
-  std::mutex m_;
-  std::condition_variable cv_;
-  int n_, count_ = 0;
-  unsigned gen_ = 0;
+// Execution model: every CUDA thread of the resident block(s) is a FIBER (ucontext) on the calling host thread.  A fiber runs until it
+// reaches a barrier (__syncthreads, the two barriers inside a warp shuffle, a cluster barrier, the end of its block) and yields to the
+// scheduler, which resumes the next runnable fiber in thread order; the last arrival releases the barrier and keeps running.  No OS
+// threads, no locks: execution is deterministic, atomics are plain read-modify-writes, and a barrier costs one context switch per
+// waiting thread instead of a futex round trip.  A barrier that can never complete (a kernel bug: some threads skipped it) is detected
+// as "no runnable fiber" and aborts with a message.
+struct Barrier {  // reusable, generation-counted
+  explicit Barrier(int n_) : n(n_) {}
+  int n, count = 0;
+  unsigned gen = 0;
+  inline void wait();
 };
 
 struct Warp {
@@ -121,17 +111,58 @@ struct Ctx {
   Barrier* cluster_bar = nullptr;
   char** peer_dyn = nullptr;
 };
-inline Ctx& ctx() {
-  thread_local Ctx c;
-  return c;
+
+struct Fiber {
+  ucontext_t uc;
+  std::unique_ptr<char[]> stack;
+  Ctx ctx;
+  bool done = false;
+  Barrier* wait_bar = nullptr;  // the barrier this fiber sleeps on, released once its generation moves past wait_gen
+  unsigned wait_gen = 0;
+};
+
+struct Sched {
+  ucontext_t main_uc;
+  Fiber* cur = nullptr;
+  const std::function<void()>* body = nullptr;
+  dim3 grid;
+  int cluster = 1;
+};
+inline Sched& sched() {
+  static thread_local Sched s;
+  return s;
 }
-inline std::mutex& atomic_mutex() {
-  static std::mutex m;
-  return m;
+inline Ctx& ctx() { return sched().cur->ctx; }
+
+inline void Barrier::wait() {
+  const unsigned g = gen;
+  if (++count == n) {  // last arrival: release everybody, keep running
+    count = 0;
+    ++gen;
+    return;
+  }
+  Fiber* f = sched().cur;
+  f->wait_bar = this;
+  f->wait_gen = g;
+  swapcontext(&f->uc, &sched().main_uc);
 }
 
-// run `body` once per (block, thread).  blockDim x cluster_x threads live for the whole launch; the cluster_x blocks of a cluster run
-// together (their threads share a cluster barrier and can read each other's dynamic shared memory), clusters one after the other.
+inline void fiber_main() {
+  Sched& s = sched();
+  Fiber* f = s.cur;
+  Ctx& c = f->ctx;
+  for (unsigned bz = 0; bz < s.grid.z; ++bz)
+    for (unsigned by = 0; by < s.grid.y; ++by)
+      for (unsigned bx = 0; bx < s.grid.x; bx += s.cluster) {
+        c.blockIdx = dim3(bx + c.cluster_rank, by, bz);
+        (*s.body)();
+        c.cluster_bar->wait();  // the next blocks may reuse the shared arrays only after every thread has left these
+      }
+  f->done = true;  // returning switches to uc_link = the scheduler
+}
+
+// run `body` once per (block, thread).  blockDim x cluster_x fibers live for the whole launch; the cluster_x blocks of a cluster are
+// resident together (their threads share a cluster barrier and can read each other's dynamic shared memory), clusters one after the other.
 // `static` shared arrays are only valid for cluster_x == 1 (one resident block); cluster kernels here use dynamic shared memory only.
 inline void launch(dim3 grid, dim3 block, const std::function<void()>& body, size_t dyn_smem_bytes = 0, int cluster_x = 1) {
   const int nt = static_cast<int>(block.x * block.y * block.z);
@@ -139,6 +170,11 @@ inline void launch(dim3 grid, dim3 block, const std::function<void()>& body, siz
   const int cs = cluster_x < 1 ? 1 : cluster_x;
   if (grid.x % cs != 0) {
     fprintf(stderr, "cpu_emul::launch: grid.x %u is not a multiple of the cluster size %d\n", grid.x, cs);
+    abort();
+  }
+  Sched& s = sched();
+  if (s.cur != nullptr) {
+    fprintf(stderr, "cpu_emul::launch: nested launch\n");
     abort();
   }
   Barrier cluster_bar(nt * cs);
@@ -151,33 +187,54 @@ inline void launch(dim3 grid, dim3 block, const std::function<void()>& body, siz
     for (int w = 0; w < nw; ++w) warps.emplace_back(new Warp(std::min(32, nt - 32 * w)));
     peer[r] = reinterpret_cast<char*>(dyn[r].data());
   }
-  std::vector<std::thread> threads;
-  threads.reserve(static_cast<size_t>(nt) * cs);
+  constexpr size_t kStack = 256 * 1024;  // untouched pages are never committed
+  std::vector<Fiber> fibers(static_cast<size_t>(nt) * cs);
+  s.body = &body;
+  s.grid = grid;
+  s.cluster = cs;
   for (int r = 0; r < cs; ++r)
     for (int t = 0; t < nt; ++t) {
-      threads.emplace_back([&, r, t] {
-        Ctx& c = ctx();
-        c.blockDim = block;
-        c.gridDim = grid;
-        c.threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
-        c.block_bar = block_bars[r].get();
-        c.warp = warps[r * nw + t / 32].get();
-        c.lane = t % 32;
-        c.dyn_smem = peer[r];
-        c.cluster_rank = r;
-        c.cluster_size = cs;
-        c.cluster_bar = &cluster_bar;
-        c.peer_dyn = peer.data();
-        for (unsigned bz = 0; bz < grid.z; ++bz)
-          for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; bx += cs) {
-              c.blockIdx = dim3(bx + r, by, bz);
-              body();
-              cluster_bar.wait();  // the next blocks may reuse the shared arrays only after every thread has left these
-            }
-      });
+      Fiber& f = fibers[static_cast<size_t>(r) * nt + t];
+      Ctx& c = f.ctx;
+      c.blockDim = block;
+      c.gridDim = grid;
+      c.threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+      c.block_bar = block_bars[r].get();
+      c.warp = warps[r * nw + t / 32].get();
+      c.lane = t % 32;
+      c.dyn_smem = peer[r];
+      c.cluster_rank = r;
+      c.cluster_size = cs;
+      c.cluster_bar = &cluster_bar;
+      c.peer_dyn = peer.data();
+      f.stack.reset(new char[kStack]);
+      getcontext(&f.uc);
+      f.uc.uc_stack.ss_sp = f.stack.get();
+      f.uc.uc_stack.ss_size = kStack;
+      f.uc.uc_link = &s.main_uc;
+      makecontext(&f.uc, reinterpret_cast<void (*)()>(fiber_main), 0);
     }
-  for (auto& th : threads) th.join();
+  size_t remaining = fibers.size();
+  while (remaining > 0) {
+    bool progressed = false;
+    for (Fiber& f : fibers) {
+      if (f.done) continue;
+      if (f.wait_bar != nullptr) {
+        if (f.wait_bar->gen == f.wait_gen) continue;  // still waiting
+        f.wait_bar = nullptr;
+      }
+      s.cur = &f;
+      swapcontext(&s.main_uc, &f.uc);
+      progressed = true;
+      if (f.done) --remaining;
+    }
+    if (!progressed) {
+      fprintf(stderr, "cpu_emul::launch: dead-lock — %zu thread(s) wait on a barrier that the others never reach\n", remaining);
+      abort();
+    }
+  }
+  s.cur = nullptr;
+  s.body = nullptr;
 }
 
 // barrier.cluster arrive + wait over every thread of the cluster
@@ -211,8 +268,7 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
 }
 
 template <typename T>
-inline T atomicAdd(T* p, T v) {
-  std::lock_guard<std::mutex> lk(cpu_emul::atomic_mutex());
+inline T atomicAdd(T* p, T v) {  // fibers run one at a time: a plain read-modify-write is atomic
   const T old = *p;
   *p = old + v;
   return old;

@@ -97,7 +97,7 @@ SIMT_OPS = ("groupnorm", "groupnorm_hilo", "groupnorm2", "layernorm", "layernorm
 
 
 @pytest.mark.skipif(os.environ.get("MVD_SLOW_SHIM") != "1",
-                    reason="~7 minutes of host-thread barriers: run with MVD_SLOW_SHIM=1 (last result: profiles/r02_shim_apply_model.txt)")
+                    reason="two minutes (emulated GEMMs + 1.5 M fiber switches): run with MVD_SLOW_SHIM=1 (last result: profiles/r02_shim_apply_model.txt)")
 def test_apply_model_with_every_simt_kernel_from_source_vs_oracle(nat, monkeypatch):
     """ViewFusion.apply_model (N = 2, D = 3, cfg 2.5, the 64-channel topology-complete model) through the product's step compiler with EVERY
     non-tensor-core kernel executed from its .cu source on the shim — in the real program: the engine's buffer arena, pitches, column
