@@ -19,9 +19,11 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <random>
 #include <vector>
 
 #include "../../../include/mvd_b200.h"
@@ -214,10 +216,21 @@ inline void launch(dim3 grid, dim3 block, const std::function<void()>& body, siz
       f.uc.uc_link = &s.main_uc;
       makecontext(&f.uc, reinterpret_cast<void (*)()>(fiber_main), 0);
     }
+  // MVD_SHIM_ORDER = "reverse" | "shuffle:<seed>": the order in which runnable threads are resumed between barriers.  Results must not
+  // depend on it — a kernel that misses a barrier (a shared-memory race) gives different answers under a different order.
+  std::vector<size_t> order(fibers.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+  const char* ord = getenv("MVD_SHIM_ORDER");
+  const bool reverse = ord != nullptr && strcmp(ord, "reverse") == 0;
+  const bool shuffle = ord != nullptr && strncmp(ord, "shuffle:", 8) == 0;
+  std::mt19937 rng(shuffle ? static_cast<unsigned>(atoi(ord + 8)) : 0u);
+  if (reverse) std::reverse(order.begin(), order.end());
   size_t remaining = fibers.size();
   while (remaining > 0) {
     bool progressed = false;
-    for (Fiber& f : fibers) {
+    if (shuffle) std::shuffle(order.begin(), order.end(), rng);
+    for (size_t idx : order) {
+      Fiber& f = fibers[idx];
       if (f.done) continue;
       if (f.wait_bar != nullptr) {
         if (f.wait_bar->gen == f.wait_gen) continue;  // still waiting

@@ -135,3 +135,17 @@ def test_apply_model_with_every_simt_kernel_from_source_vs_oracle(nat, monkeypat
     print("apply_model, SIMT kernels from source: rel-L2 vs oracle", r, "ops from source:", sorted(HybridOps.used))
     assert r < 1e-3, r
     assert {"groupnorm", "gridattn_prep", "gridattn_tokens", "unet_input", "cfg_ddim", "gemv_grouped", "frustum_pool", "pixel_cross_attn"} <= HybridOps.used
+
+
+@pytest.mark.parametrize("order", ["reverse", "shuffle:7"])
+def test_results_do_not_depend_on_the_thread_schedule(nat, dbl, monkeypatch, order):
+    """A CPU stand-in for racecheck: the shim resumes runnable threads in a different order between barriers (MVD_SHIM_ORDER); kernels
+    whose shared-memory traffic is correctly fenced by __syncthreads / shuffles / cluster barriers give the same answers — here the
+    cluster GroupNorm (partials in shared memory, DSMEM exchange), the grouped GEMV (staged input row), the staged view attention and
+    the token producer, against the same references at the same tolerances."""
+    monkeypatch.setenv("MVD_SHIM_ORDER", order)
+    G.test_groupnorm(nat, dbl, 1, 1024, 320, True)
+    G.test_groupnorm_two_sources_and_concat16(nat, dbl, 1, 256, 640, 320)
+    G.test_gemv_grouped(nat, dbl)
+    G.test_view_attention_layouts(nat, dbl, 130, 8)
+    G.test_layernorms(nat, dbl)

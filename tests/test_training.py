@@ -216,3 +216,15 @@ def test_pointwise_kernel_source_on_the_cpu_shim(tmp_path, monkeypatch):
     monkeypatch.setattr(rt, "get_ops", lambda dev: shim)
     worst = _check_pointwise("cpu", 2e-5)
     assert len(worst) >= 18
+
+
+@pytest.mark.parametrize("order", ["reverse", "shuffle:3"])
+def test_pointwise_kernel_source_is_schedule_independent(tmp_path, monkeypatch, order):
+    """racecheck stand-in for csrc/train.cu (no compute-sanitizer run exists for these kernels: the GPU budget went elsewhere): the shim
+    resumes threads in another order between barriers; every case still matches float64 autograd"""
+    import mvdfusion_b200.runtime as rt
+    from common import build_cpu_shim, shim_ops
+    shim = shim_ops(build_cpu_shim(["train.cu"], tmp_path), monkeypatch)
+    monkeypatch.setattr(rt, "get_ops", lambda dev: shim)
+    monkeypatch.setenv("MVD_SHIM_ORDER", order)
+    _check_pointwise("cpu", 2e-5)
