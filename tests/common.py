@@ -134,6 +134,30 @@ def build_cpu_shim(sources, out_dir, name="libmvd_cpuemul.so"):
     return out
 
 
+def guarded_clone(t):
+    """TEST INFRASTRUCTURE (memcheck stand-in for kernels run on the CPU shim): a copy of `t` whose last byte sits right in front of an
+    inaccessible page (anonymous mmap + mprotect(PROT_NONE)) — a kernel that reads or writes past the end of the buffer dies with SIGSEGV
+    instead of silently touching a neighbour.  The start stays 16-byte aligned (sizes are rounded up to 16 bytes: <= 15 bytes of slack)."""
+    import ctypes
+    import mmap
+    page = mmap.PAGESIZE
+    t = t.detach().contiguous()
+    nbytes = max(16, (t.numel() * t.element_size() + 15) // 16 * 16)
+    size = (nbytes + page - 1) // page * page + page
+    m = mmap.mmap(-1, size)
+    probe = ctypes.c_char.from_buffer(m)
+    base = ctypes.addressof(probe)
+    del probe
+    libc = ctypes.CDLL(None, use_errno=True)
+    libc.mprotect.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    if libc.mprotect(base + size - page, page, 0) != 0:
+        raise OSError(ctypes.get_errno(), "mprotect failed")
+    off = size - page - nbytes
+    g = torch.frombuffer(m, dtype=t.dtype, count=t.numel(), offset=off).reshape(t.shape)
+    g.copy_(t)
+    return g
+
+
 def shim_ops(lib_path, monkeypatch):
     """the product's own binding layer (ops.NativeOps: argument order, workspace sizes, job tables) over a CPU-shim build of the kernels;
     ops._ptr is patched to accept host tensors for the duration of the test"""
@@ -148,6 +172,15 @@ def shim_ops(lib_path, monkeypatch):
     class ShimOps(OPS.NativeOps):
         def __init__(self):
             self.lib, self.device = lib, torch.device("cpu")
+
+        # every buffer the kernels see ends at a guard page (see guarded_clone)
+        guarded = staticmethod(guarded_clone)
+
+        def empty(self, shape, dtype):
+            return guarded_clone(torch.full(shape, float("nan") if dtype.is_floating_point else 255, dtype=dtype))
+
+        def zeros(self, shape, dtype):
+            return guarded_clone(torch.zeros(shape, dtype=dtype))
 
     def ptr(t, dtype=None):
         if t is None:

@@ -31,8 +31,10 @@ def sync(nat):
 def run_both(nat, dbl, name, tensors, out_names, *args, tol=2e-3, **kw):
     """tensors: dict name -> cpu tensor (inputs and pre-filled outputs).  Calls op `name` on both, compares outputs."""
     cpu = {k: (v.clone() if v is not None else None) for k, v in tensors.items()}
-    gpu = {k: (v.clone().to(nat.device) if v is not None else None) for k, v in tensors.items()}   # the B200 — or the host, when `nat` is
-    # the kernel source on the CUDA-on-CPU shim (tests/test_kernel_sources_cpu_shim.py reuses these test bodies)
+    # the B200 — or the host, when `nat` is the kernel source on the CUDA-on-CPU shim (tests/test_kernel_sources_cpu_shim.py reuses these
+    # test bodies; there every buffer ends at an inaccessible page, so an out-of-bounds access is a crash)
+    place = getattr(nat, "guarded", None) or (lambda v: v.clone().to(nat.device))
+    gpu = {k: (place(v) if v is not None else None) for k, v in tensors.items()}
 
     def bind(o, t):
         a = [t[x] if isinstance(x, str) and x in t else x for x in args]
@@ -172,7 +174,8 @@ def test_groupnorm_split_precision_output(nat, dbl, n, hw, C):
     run_both(nat, dbl, "groupnorm_hilo", t, ["y"], "x", "g", "b", "y", n, hw, C, 1e-5, True)
     y = nat.empty((n * hw, 2 * C), torch.float16)
     dev = nat.device
-    nat.groupnorm_hilo(t["x"].clone().to(dev), t["g"].clone().to(dev), t["b"].clone().to(dev), y, n, hw, C, 1e-5, True)(stream_of(nat))
+    place = getattr(nat, "guarded", None) or (lambda v: v.clone().to(dev))
+    nat.groupnorm_hilo(place(t["x"]), place(t["g"]), place(t["b"]), y, n, hw, C, 1e-5, True)(stream_of(nat))
     sync(nat)
     import torch.nn.functional as F
     exact = F.silu(F.group_norm(t["x"].double().reshape(n, hw, C).permute(0, 2, 1), 32, t["g"].double(), t["b"].double(), 1e-5))
@@ -415,9 +418,10 @@ def test_gemv_grouped(nat, dbl):
     bs = [rnd(n, seed=20 + i) if i != 3 else None for i, n in enumerate(sizes)]
     y_cpu = [torch.zeros(n) for n in sizes]
     dev = nat.device
-    y_gpu = [torch.zeros(n).to(dev) for n in sizes]
+    place = getattr(nat, "guarded", None) or (lambda v: v.clone().to(dev))
+    y_gpu = [place(torch.zeros(n)) for n in sizes]
     dbl.gemv_grouped(x, K, list(zip(Ws, bs, y_cpu)), silu_in=True)(None)
-    nat.gemv_grouped(x.clone().to(dev), K, [(w.clone().to(dev), b.clone().to(dev) if b is not None else None, y) for w, b, y in zip(Ws, bs, y_gpu)],
+    nat.gemv_grouped(place(x), K, [(place(w), place(b) if b is not None else None, y) for w, b, y in zip(Ws, bs, y_gpu)],
                      silu_in=True)(stream_of(nat))
     sync(nat)
     for a, b in zip(y_gpu, y_cpu):

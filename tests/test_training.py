@@ -169,11 +169,13 @@ def _pointwise_cases():
     return cases
 
 
-def _check_pointwise(dev, tol):
-    """every case runs (one failing kernel does not hide the others); returns name -> worst rel-L2 over (y, grads)"""
+def _check_pointwise(dev, tol, place=None):
+    """every case runs (one failing kernel does not hide the others); returns name -> worst rel-L2 over (y, grads).
+    place: how the inputs are put in front of the kernels (the CPU-shim runs pass common.guarded_clone: buffers that end at a guard page)"""
     worst, bad = {}, []
+    place = place or (lambda t: t.clone().to(dev))
     for name, fn, ref, ins in _pointwise_cases():
-        a = [t.clone().to(dev).requires_grad_(True) for t in ins]
+        a = [place(t).requires_grad_(True) for t in ins]
         b = [t.clone().double().requires_grad_(True) for t in ins]
         y, yr = fn(*a), ref(*b)
         gy = torch.randn(yr.shape, generator=torch.Generator().manual_seed(9))
@@ -214,7 +216,8 @@ def test_pointwise_kernel_source_on_the_cpu_shim(tmp_path, monkeypatch):
     from common import build_cpu_shim, shim_ops
     shim = shim_ops(build_cpu_shim(["train.cu"], tmp_path), monkeypatch)
     monkeypatch.setattr(rt, "get_ops", lambda dev: shim)
-    worst = _check_pointwise("cpu", 2e-5)
+    from common import guarded_clone
+    worst = _check_pointwise("cpu", 2e-5, place=guarded_clone)
     assert len(worst) >= 18
 
 
