@@ -1,8 +1,9 @@
-// Training-side normalisation / activation kernels (second slice): the fp32 forward passes that save what
+// Training-side normalisation / activation / gather kernels (second slice): the fp32 forward passes that save what
 // their backward needs, and the backward passes, of the non-contraction layers between the GEMMs of mvdfusion_b200/training.py —
 // nn.LayerNorm (external/sd1/ldm/modules/attention.py:210-212; timm LayerNorm + adaLN modulate, mvdfusion/view_attn_efficient2.py:61-66),
 // GroupNorm32 (+ SiLU) on channels-last rows (external/sd1/ldm/modules/diffusionmodules/util.py:204-216, openaimodel.py:199-203,224-228),
-// GELU / SiLU / GEGLU (external/sd1/ldm/modules/attention.py:42-44).  In the reference these are ATen kernels recorded by autograd
+// GELU / SiLU / GEGLU (external/sd1/ldm/modules/attention.py:42-44), and GridAttn's bilinear gather with its scatter-add backward
+// (F.grid_sample, mvdfusion/view_attn_efficient2.py:303-318).  In the reference these are ATen kernels recorded by autograd
 // (train.py:90-94, loss.backward()).
 //
 // All of them are HBM-bound streaming passes: activations are fp32 [rows, C] (row = (image*H + y)*W + x), consecutive threads read
